@@ -1,0 +1,71 @@
+"""Pin the oracle restatement against outputs of the unmodified reference (tests/golden/*.npz)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as oin
+from oracle.vispeech_oracle import expansion_indices, infer_one
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _control(d, name):
+    kind = int(d[name + "_kind"])
+    if kind == 0:
+        return None
+    if kind == 1:
+        return float(d[name + "_control"][0])
+    return torch.from_numpy(d[name + "_control"])
+
+
+def run_oracle_on_golden(sd, d):
+    tf = d["z"].shape[1]
+    noise = torch.from_numpy(d["noise"]) if "noise" in d else oin.draw_noise([tf], 100)[0]
+    max_len = int(d["max_len"])
+    return infer_one(sd, torch.from_numpy(d["ids"]), int(d["sid"]), float(d["noise_scale"]), noise,
+                     None if max_len < 0 else max_len, _control(d, "energy"), _control(d, "pitch"),
+                     _control(d, "duration"))
+
+
+def snr_db(ref, x):
+    ref, x = ref.double(), x.double()
+    return float(10 * torch.log10((ref ** 2).sum() / ((ref - x) ** 2).sum().clamp_min(1e-300)))
+
+
+def test_golden_files_exist():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_reference(path, state_dict):
+    d = dict(np.load(path))
+    t = run_oracle_on_golden(state_dict, d)
+    # integer work: bit exact
+    assert t["x_mask"].numpy().reshape(-1).tolist() == d["x_mask"].reshape(-1).tolist()
+    if int(d["duration_kind"]) == 2:
+        dur = torch.from_numpy(d["duration_control"])
+        assert torch.equal(expansion_indices(dur), t["lr_index"])
+        assert np.array_equal(t["duration"].numpy(), d["duration"])
+    else:
+        assert np.array_equal(t["duration"].numpy(), d["duration"])        # ceil() of predictions: integral
+    if "x_lr" in d:
+        # the reference builds x_lr by per-phoneme expand+cat (models.py:418-427): same columns as our gather
+        assert np.allclose(t["x_lr"].numpy(), d["x_lr"], atol=2e-5)
+    # floating point: same torch build, same ops => tight tolerance (not bit exact: different op order in attention)
+    for k, tol in (("x_enc", 2e-5), ("F0", 2e-3), ("energy", 2e-4), ("m_p", 5e-5), ("z", 1e-4)):
+        err = float(np.abs(t[k].numpy() - d[k]).max())
+        assert err <= tol, (k, err)
+    for k in ("z_p", "logs_p"):
+        if k in d:
+            assert float(np.abs(t[k].numpy() - d[k]).max()) <= 1e-4, k
+    o_ref = torch.from_numpy(d["o"].astype(np.float32))
+    if int(d["o_is_f16x64"]):
+        o_ref = o_ref / 64
+        assert snr_db(o_ref, t["o"]) > 60.0          # fp16 storage of the fixture bounds this
+    else:
+        assert float((o_ref - t["o"]).abs().max()) <= 2e-5
+        assert snr_db(o_ref, t["o"]) > 80.0
+    assert t["o"].numel() == o_ref.numel()
