@@ -1,0 +1,149 @@
+/*
+ * vispeech_b200.h - C ABI of the B200-native SynthesizerTrn.infer hot path.
+ *
+ * The reference (innnky/vispeech) has no FFI / plugin layer: its boundary is the Python method
+ * SynthesizerTrn.infer (models.py:672-722) fed by utils.load_checkpoint (utils.py:21-51).
+ * This header is the boundary a maintainer would bind instead (INTEGRATION.md shows the ctypes
+ * stub); vispeech_b200/synthesizer.py is that binding, keeping the reference's call surface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates: the caller owns outputs and the workspace;
+ *   - return value 0 = ok; otherwise a VS_ERR_* code, text via vs_last_error();
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Ragged rows ("VsRows"): a batch is a single long sequence of rows.  Utterance b owns rows
+ * [utt_start[b], utt_start[b]+utt_len[b]); between utterances lie >= `gap` rows that are kept
+ * exactly zero, so a convolution across the gap sees the zero padding a batch-1 reference call
+ * would see (per-utterance batch-1 semantics).  row_utt[r] is the owning
+ * utterance or -1.  Phoneme-level and frame-level tensors each have their own VsRows.
+ * fp32 activations are row-major [n_rows][C].
+ */
+#ifndef VISPEECH_B200_H
+#define VISPEECH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_OK 0
+#define VS_ERR_INVALID 1      /* bad argument / unsupported shape */
+#define VS_ERR_MISSING 2      /* weight tensor not registered */
+#define VS_ERR_CUDA 3         /* CUDA runtime error (text in vs_last_error) */
+#define VS_ERR_WORKSPACE 4    /* workspace too small */
+
+#define VS_DTYPE_F32 0
+#define VS_DTYPE_BF16 1
+#define VS_DTYPE_I64 2
+#define VS_DTYPE_F64 3
+
+typedef struct VsModel VsModel;
+
+/* configs/config.json:39-90 + inference.py:26-33.  v1 kernels are specialised for the reference
+ * config; vs_model_create rejects anything else with VS_ERR_INVALID. */
+typedef struct {
+  int32_t n_vocab;            /* 519  text/symbols.py:22 */
+  int32_t hidden;             /* 192 */
+  int32_t filter;             /* 768 */
+  int32_t n_heads;            /* 2 */
+  int32_t n_layers;           /* 4  (text encoder, frame prior) */
+  int32_t pitch_layers;       /* 6  models.py:498 */
+  int32_t window;             /* 4  attentions.py:14 */
+  int32_t gin;                /* 256 */
+  int32_t n_speakers;         /* 200 */
+  int32_t flow_layers;        /* 4 */
+  int32_t n_flows;            /* 4 */
+  int32_t upsample_initial;   /* 512 */
+  int32_t hop;                /* 512 = 8*8*4*2 */
+} VsConfig;
+
+typedef struct {
+  int32_t n_utt;
+  int32_t n_rows;             /* allocated rows; every kernel writes all of them (zeros where invalid) */
+  int32_t max_len;            /* max over utt_len (host-known; sizes attention grids) */
+  int32_t reserved;
+  const int32_t* row_utt;     /* [n_rows]  utterance index or -1 */
+  const int32_t* utt_start;   /* [n_utt] */
+  const int32_t* utt_len;     /* [n_utt] */
+  const int32_t* sid;         /* [n_utt]   speaker id (emb_g row, models.py:674) */
+} VsRows;
+
+const char* vs_last_error(void);
+int vs_version(void);
+
+/* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
+ * Tensors are registered by name in the PACKED layouts listed in vispeech_b200/packing.py
+ * (folded weight norm, [tap][Cin][Cout] fp32 conv weights, per-speaker conditioning tables,
+ * planar bf16 decoder weights).  The model keeps the pointers; the caller keeps ownership. */
+int vs_model_create(const VsConfig* cfg, VsModel** out);
+void vs_model_destroy(VsModel* m);
+int vs_model_set_tensor(VsModel* m, const char* name, const void* ptr, int64_t numel, int32_t dtype);
+int vs_model_finalize(VsModel* m);                       /* VS_ERR_MISSING if any tensor is absent */
+
+/* workspace bytes needed by any single call below for these row counts */
+int64_t vs_workspace_bytes(const VsModel* m, int32_t n_rows_phoneme, int32_t n_rows_frame);
+
+/* ---- a3-a7: TextEncoder.forward (models.py:168-174) = embedding*sqrt(H) + 4-layer attentions.Encoder */
+int vs_text_encode(const VsModel* m, const VsRows* rows_p, const int32_t* ids_rows /*[n_rows], -1 in gaps*/,
+                   float* x_out /*[n_rows][192]*/, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a8-a11: duration / pitch / energy predictors + prenets (models.py:681-708).
+ * *_mode: 0 = predict, scale by *_scale (None -> 1, scalar control);  2 = per-phoneme override in
+ * *_ctrl (durations in frames, F0 in Hz, raw energy).  x is updated in place (x += prenet(..)). */
+int vs_variance_adapter(const VsModel* m, const VsRows* rows_p, float* x /*[n_rows][192] in/out*/,
+                        int32_t dur_mode, float dur_scale, const double* dur_ctrl /*[n_rows]*/,
+                        int32_t pitch_mode, float pitch_scale, const float* pitch_ctrl,
+                        int32_t energy_mode, float energy_scale, const float* energy_ctrl,
+                        double* duration_out /*[n_rows] as models.py:688 returns it*/,
+                        float* f0_out, float* energy_out, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a12-a13: LengthRegulator (models.py:398-427).  Step 1: n_i = max(int(d_i),0), inclusive
+ * per-utterance prefix sum and per-utterance frame counts (host reads frames[] to lay out frame rows).
+ * Step 2: gather.  lr_index[r] = phoneme index within its utterance, -1 in gaps: bit-exact with the
+ * reference expansion for identical durations. */
+int vs_length_regulate_count(const VsRows* rows_p, const double* duration /*[n_rows]*/,
+                             int32_t* cum_out /*[n_rows] inclusive*/, int32_t* frames_out /*[n_utt]*/, void* stream);
+int vs_length_regulate_gather(const VsRows* rows_p, const VsRows* rows_f, const float* x_p, const int32_t* cum,
+                              float* x_f /*[rows_f.n_rows][192]*/, int32_t* lr_index /*[rows_f.n_rows]*/, void* stream);
+
+/* ---- a14-a16: FramePriorNet + Projection + prior sample (models.py:715-718) */
+int vs_frame_prior(const VsModel* m, const VsRows* rows_f, const float* x_f, const float* noise /*[n_rows][192]*/,
+                   float noise_scale, float* x_frame_out, float* m_p, float* logs_p, float* z_p,
+                   void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a17: ResidualCouplingBlock reverse (models.py:202-209), in place on z ([n_rows][192]) */
+int vs_flow_reverse(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a18: HiFi-GAN Generator (models.py:271-290).  max_len < 0 = no truncation (models.py:720).
+ * wave_out is [rows_f.n_rows * hop] in ragged order.  precision: 0 = bf16 tcgen05 path (product),
+ * 1 = fp32 SIMT path (test-only cross-check of the same math, NOT a fallback). */
+int vs_hifigan_decode(const VsModel* m, const VsRows* rows_f, const float* z, int32_t max_len, float* wave_out,
+                      int32_t precision, void* ws, int64_t ws_bytes, void* stream);
+
+/* ragged rows -> reference layout [n_utt][C][t_max] (zero padded), rows_per_step = samples per row entry */
+int vs_unpack_rows(const VsRows* rows, const float* x /*[n_rows*rows_mul][C]*/, int32_t C, int32_t rows_mul,
+                   int32_t t_max, float* out /*[n_utt][C][t_max]*/, void* stream);
+
+/* ---- op-level entry points (used by the parity tests; same kernels as above) */
+int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w /*[k][Cin][Cout]*/, const float* bias,
+                     float* out, int32_t out_ld, int32_t n_rows, int32_t c_in, int32_t c_out, int32_t k, int32_t dil,
+                     int32_t pad_l, float in_slope, int32_t act, const int32_t* row_utt, int32_t row_div, void* stream);
+int vs_op_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float* out,
+                    int32_t n_rows, int32_t C, const int32_t* row_utt, void* stream);
+int vs_op_rel_attention(const VsRows* rows, const float* qkv /*[n_rows][576]*/, const float* emb_rel_k,
+                        const float* emb_rel_v, float* out /*[n_rows][192]*/, void* stream);
+/* bf16 tcgen05 implicit-GEMM conv on planar [C/8][n_rows][8] activations (csrc/umma_conv.cu):
+ * y = conv(in) + bias + res;  out_raw = y;  out_act = leaky_relu(y*act_scale, act_slope); either output may be
+ * null.  up > 1 = polyphase ConvTranspose1d (column gn -> phase gn/Cout, output row up*r+phase). */
+int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,
+                      void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
+                      int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
+                      const int32_t* row_utt, int32_t row_div, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,83 @@
+"""Helpers shared by the GPU parity tests (op-level calls through the C ABI)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from vispeech_b200 import _lib
+from vispeech_b200._lib import check, ptr
+from vispeech_b200.layout import make_rows
+from vispeech_b200.packing import pack_umma
+
+DEV = "cuda:0"
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_planar(x: torch.Tensor) -> torch.Tensor:
+    """[R][C] fp32 -> planar bf16 [C/8][R][8] (on the same device)."""
+    R, C = x.shape
+    return x.to(torch.bfloat16).reshape(R, C // 8, 8).permute(1, 0, 2).contiguous()
+
+
+def from_planar(p: torch.Tensor) -> torch.Tensor:
+    """planar bf16 [C/8][R][8] -> [R][C] fp32."""
+    P, R, _ = p.shape
+    return p.permute(1, 0, 2).reshape(R, P * 8).float()
+
+
+def bf16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).float()
+
+
+def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0, act_scale=1.0, row_utt=None,
+              row_div=1, want_raw=True, want_act=True):
+    """x [R][Cin] fp32 (device), w_tcn [taps][Cin][N] fp32.  Returns (raw, act) as [R*up][N/up] fp32."""
+    lib = _lib.load()
+    R, cin = x.shape
+    taps, _, n = w_tcn.shape
+    cout = n // up
+    xin = to_planar(x)
+    wp = pack_umma(w_tcn.cpu()).to(x.device)
+    raw = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.bfloat16, device=x.device) if want_raw else None
+    act = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.bfloat16, device=x.device) if want_act else None
+    resp = to_planar(res) if res is not None else None
+    check(lib.vs_op_conv1d_umma(ptr(xin), ptr(wp), ptr(bias), ptr(resp), ptr(raw), ptr(act), R, cin, n, taps, dil, pad_l,
+                                up, float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()),
+          "vs_op_conv1d_umma")
+    torch.cuda.synchronize()
+    return (from_planar(raw) if want_raw else None), (from_planar(act) if want_act else None)
+
+
+def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=None, row_div=1):
+    lib = _lib.load()
+    R, cin = x.shape
+    k, _, cout = w_tcn.shape
+    out = torch.full((R, cout), float("nan"), dtype=torch.float32, device=x.device)
+    check(lib.vs_op_conv1d_f32(ptr(x), cin, ptr(w_tcn), ptr(bias), ptr(out), cout, R, cin, cout, k, dil, pad_l,
+                               float(in_slope), act, ptr(row_utt), row_div, stream()), "vs_op_conv1d_f32")
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_conv_rows(x, w_tcn, bias=None, dil=1, pad_l=0):
+    """CPU reference of the row conv: out[r] = sum_t in[r + (t-pad_l)*dil] @ W[t] (+bias); zero outside [0,R)."""
+    x = x.double().cpu()
+    w = w_tcn.double().cpu()
+    R = x.shape[0]
+    out = torch.zeros(R, w.shape[2], dtype=torch.float64)
+    for t in range(w.shape[0]):
+        sh = (t - pad_l) * dil
+        lo, hi = max(0, -sh), min(R, R - sh)
+        if hi > lo:
+            out[lo:hi] += x[lo + sh:hi + sh] @ w[t]
+    if bias is not None:
+        out += bias.double().cpu()
+    return out
+
+
+def snr_db(ref, x):
+    ref, x = ref.double().cpu().reshape(-1), x.double().cpu().reshape(-1)
+    return float(10 * torch.log10((ref ** 2).sum() / ((ref - x) ** 2).sum().clamp_min(1e-300)))

@@ -1,0 +1,102 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol of include/vispeech_b200.h; host-side
+layout / packing / sharding logic.  No compute entry point is called (there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vispeech_b200.build import build
+    build()
+    from vispeech_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from vispeech_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vispeech_b200.h")).read()
+    declared = set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vs_version() == 1
+
+
+def test_sass_is_blackwell_native():
+    """The decoder conv must be tcgen05 + TMA bulk copies + TMEM loads, not a legacy mma.sync path."""
+    import subprocess
+    from vispeech_b200.build import LIB_PATH
+    sass = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass
+
+
+def test_no_cpu_fallback_without_cuda():
+    from vispeech_b200 import _lib, build_from_hparams, get_hparams_from_file
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.VsError):
+        build_from_hparams(get_hparams_from_file())
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vispeech_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_row_layout_plan():
+    from vispeech_b200.layout import plan_starts
+    starts, n = plan_starts([5, 1, 9], gap=4, align=16)
+    assert starts.tolist() == [0, 9, 14] and n == 32
+    starts, n = plan_starts([431] * 64, gap=4, align=16)
+    assert n % 16 == 0 and n >= 64 * 435 and all(b - a == 435 for a, b in zip(starts[:-1], starts[1:]))
+
+
+def test_packing_shapes_and_flow_flip(state_dict):
+    from vispeech_b200.packing import pack_state_dict, pack_umma, ups_union_taps
+    p = pack_state_dict(state_dict)
+    assert p["enc_p.encoder.0.wqkv"].shape == (192, 576)
+    assert p["dec.ups.0.w"].shape == (8, 2, 512, 256) and p["dec.ups.2.w"].shape == (4, 1, 128, 64)
+    assert [ups_union_taps(i) for i in range(4)] == [(3, 1), (3, 1), (1, 0), (3, 1)]
+    assert p["dec16.ups.0.w"].numel() == 3 * 512 * 2048 and p["dec16.ups.0.w"].dtype == torch.bfloat16
+    # flow 1 and 3 run on a flipped tensor: pre reads reversed upper-half channels, post writes reversed lower half
+    w = state_dict["flow.flows.2.pre.weight"][:, :, 0]            # [192 co, 96 ci]
+    assert torch.equal(p["flow.1.pre.w"], torch.flip(w.t(), [0]))
+    assert torch.equal(p["flow.0.pre.w"], state_dict["flow.flows.0.pre.weight"][:, :, 0].t())
+    # slab layout: element (nb,t,kc,p,n,e) = W[t][kc*KC+8p+e][nb*Nblk+n]
+    wt = torch.arange(2 * 128 * 512, dtype=torch.float32).reshape(2, 128, 512) % 251
+    sl = pack_umma(wt).float().reshape(2, 2, 2, 8, 256, 8)
+    assert sl[1, 1, 1, 3, 17, 5] == wt[1, 64 + 24 + 5, 256 + 17]
+
+
+def test_polyphase_equals_conv_transpose(state_dict):
+    """The polyphase rewrite used by both decoder paths equals F.conv_transpose1d (pure host math check)."""
+    from vispeech_b200.packing import UP_KERNELS, UP_RATES, pack_state_dict, ups_phase_range
+    p = pack_state_dict(state_dict)
+    from oracle.weights import fold_weight_norm
+    for i in (2, 3):
+        s, K = UP_RATES[i], UP_KERNELS[i]
+        wt = fold_weight_norm(state_dict, "dec.ups.%d" % i)
+        cin, cout, _ = wt.shape
+        x = torch.randn(1, cin, 11)
+        ref = torch.nn.functional.conv_transpose1d(x, wt, None, stride=s, padding=(K - s) // 2)[0]
+        per = p["dec.ups.%d.w" % i]
+        out = torch.zeros(cout, 11 * s)
+        for ph in range(s):
+            lo, hi = ups_phase_range(i, ph)
+            for t, d in enumerate(range(lo, hi + 1)):
+                for q in range(11):
+                    if 0 <= q + d < 11:
+                        out[:, s * q + ph] += per[ph, t].t() @ x[0, :, q + d]
+        assert torch.allclose(out, ref, atol=1e-5)

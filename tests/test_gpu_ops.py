@@ -1,0 +1,153 @@
+"""GPU parity, op level: every CUDA kernel family against a CPU fp64/fp32 statement of the same op.
+All calls go through the C ABI (ctypes).  Tolerances are stated per test."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    assert torch.cuda.is_available()
+    return gpu_util
+
+
+UMMA_CASES = [
+    # (R, Cin, N, taps, dil) - the decoder's shapes plus ragged row counts
+    (1000, 32, 32, 3, 1), (517, 32, 32, 11, 5), (640, 64, 64, 7, 3), (384, 128, 128, 11, 5), (300, 128, 128, 3, 1),
+    (256, 256, 256, 3, 3), (200, 256, 256, 11, 5), (130, 192, 512, 7, 1),
+]
+
+
+@pytest.mark.parametrize("R,cin,n,taps,dil", UMMA_CASES)
+def test_umma_conv_matches_cpu(G, R, cin, n, taps, dil):
+    """bf16 operands, fp32 accumulate: compare against an fp64 conv of the bf16-rounded operands.
+    Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation noise."""
+    g = torch.Generator().manual_seed(R + cin + taps)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(taps, cin, n, generator=g) / (cin * taps) ** 0.5
+    b = torch.randn(n, generator=g) * 0.1
+    pad_l = (taps - 1) // 2
+    raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), dil=dil, pad_l=pad_l, act_slope=0.1)
+    ref = G.ref_conv_rows(G.bf16_round(x), G.bf16_round(w), b, dil=dil, pad_l=pad_l)
+    err = (raw.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err
+    ref_act = torch.where(ref > 0, ref, 0.1 * ref)
+    assert (act.cpu().double() - ref_act).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_umma_conv_residual_mask_and_scale(G):
+    R, C = 700, 64
+    g = torch.Generator().manual_seed(5)
+    x, res = torch.randn(R, C, generator=g), torch.randn(R, C, generator=g)
+    w = torch.randn(7, C, C, generator=g) / (7 * C) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    row_utt = torch.zeros(R // 4, dtype=torch.int32)
+    row_utt[40:50] = -1                                            # rows 160..199 invalid
+    raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), dil=1, pad_l=3, act_slope=0.01,
+                           act_scale=1 / 3, row_utt=row_utt.to(G.DEV), row_div=4)
+    ref = G.ref_conv_rows(G.bf16_round(x), G.bf16_round(w), b, pad_l=3) + G.bf16_round(res).double()
+    ref[160:200] = 0
+    assert (raw.cpu().double() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    ra = ref / 3
+    ra = torch.where(ra > 0, ra, 0.01 * ra)
+    assert (act.cpu().double() - ra).abs().max().item() <= 2e-2 * ra.abs().max().item()
+    assert raw[160:200].abs().max().item() == 0 and act[160:200].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("stage", [0, 2, 3])
+def test_umma_conv_transpose_polyphase(G, stage):
+    """ConvTranspose1d (models.py:257-259) as a polyphase UMMA conv vs F.conv_transpose1d."""
+    from vispeech_b200.packing import UP_KERNELS, UP_RATES, ups_phase_range, ups_union_taps
+    s, K = UP_RATES[stage], UP_KERNELS[stage]
+    cin, cout = 512 >> stage, 256 >> stage
+    R = 260
+    g = torch.Generator().manual_seed(stage)
+    x = torch.randn(R, cin, generator=g)
+    wt = torch.randn(cin, cout, K, generator=g) / (cin * K / s) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    taps, pad_l = ups_union_taps(stage)
+    uni = torch.zeros(taps, cin, s * cout)
+    pad = (K - s) // 2
+    for ph in range(s):
+        lo, hi = ups_phase_range(stage, ph)
+        for d in range(lo, hi + 1):
+            uni[d + pad_l, :, ph * cout:(ph + 1) * cout] = wt[:, :, ph + pad - s * d]
+    raw, _ = G.umma_conv(x.to(G.DEV), uni, b.to(G.DEV), pad_l=pad_l, up=s, want_act=False)
+    ref = torch.nn.functional.conv_transpose1d(G.bf16_round(x).t()[None].double(), G.bf16_round(wt).double(), b.double(),
+                                               stride=s, padding=pad)[0].t()
+    assert raw.shape == ref.shape
+    assert (raw.cpu().double() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("R,cin,cout,k,dil", [(100, 192, 576, 1, 1), (333, 192, 768, 3, 1), (77, 768, 192, 3, 1),
+                                             (500, 96, 192, 1, 1), (260, 32, 1, 7, 1), (190, 64, 64, 11, 5)])
+def test_conv_f32_matches_cpu(G, R, cin, cout, k, dil):
+    """fp32 CUDA-core conv vs fp64: tolerance = fp32 accumulation error."""
+    g = torch.Generator().manual_seed(k + cout)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(k, cin, cout, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    out = G.conv_f32(x.to(G.DEV), w.to(G.DEV), b.to(G.DEV), dil=dil, pad_l=(k - 1) // 2)
+    ref = G.ref_conv_rows(x, w, b, dil=dil, pad_l=(k - 1) // 2)
+    assert (out.cpu().double() - ref).abs().max().item() <= 1e-4
+
+
+def test_layernorm_rows(G):
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    for C in (192, 256, 768):
+        g = torch.Generator().manual_seed(C)
+        a, b = torch.randn(50, C, generator=g), torch.randn(50, C, generator=g)
+        gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        row_utt = torch.zeros(50, dtype=torch.int32)
+        row_utt[7] = -1
+        out = torch.empty(50, C, device=G.DEV)
+        args = [t.to(G.DEV) for t in (a, b, gamma, beta)]
+        _lib.check(lib.vs_op_layernorm(*[t.data_ptr() for t in args], out.data_ptr(), 50, C,
+                                       row_utt.to(G.DEV).data_ptr(), G.stream()))
+        ref = torch.nn.functional.layer_norm(a + b, (C,), gamma, beta, 1e-5)
+        ref[7] = 0
+        assert (out.cpu() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("lengths", [[40], [3, 1, 70, 130], [431, 200]])
+def test_rel_attention_matches_oracle(G, lengths, state_dict):
+    """Banded relative attention (attentions.py:148-179) vs the oracle's restatement, several ragged lengths
+    including T < window+1 and T > one key tile.  fp32 tolerance 2e-5 on O(1) outputs."""
+    from oracle.vispeech_oracle import DEFAULT_CONFIG, relative_attention
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    sd = state_dict
+    p = "enc_p.encoder.attn_layers.1"
+    rows = G.make_rows(lengths, [0] * len(lengths), 4, G.DEV)
+    g = torch.Generator().manual_seed(sum(lengths))
+    xs = [torch.randn(1, 192, n, generator=g) for n in lengths]
+    qkv_rows = np.zeros((rows.n_rows, 576), np.float32)
+    refs = []
+    F = torch.nn.functional
+    for b, x in enumerate(xs):
+        q = F.conv1d(x, sd[p + ".conv_q.weight"], sd[p + ".conv_q.bias"])
+        k = F.conv1d(x, sd[p + ".conv_k.weight"], sd[p + ".conv_k.bias"])
+        v = F.conv1d(x, sd[p + ".conv_v.weight"], sd[p + ".conv_v.bias"])
+        s = rows.starts[b]
+        qkv_rows[s:s + lengths[b]] = torch.cat([q, k, v], 1)[0].t().numpy()
+        # oracle output BEFORE conv_o: rerun with identity conv_o
+        sd2 = dict(sd)
+        sd2[p + ".conv_o.weight"] = torch.eye(192)[:, :, None]
+        sd2[p + ".conv_o.bias"] = torch.zeros(192)
+        refs.append(relative_attention(sd2, p, x, DEFAULT_CONFIG)[0].t())
+    out = torch.empty(rows.n_rows, 192, device=G.DEV)
+    d_qkv = torch.from_numpy(qkv_rows).to(G.DEV)
+    d_ek = sd[p + ".emb_rel_k"][0].contiguous().to(G.DEV)
+    d_ev = sd[p + ".emb_rel_v"][0].contiguous().to(G.DEV)
+    _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
+                                       out.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    for b, ref in enumerate(refs):
+        s = rows.starts[b]
+        assert (out[s:s + lengths[b]].cpu() - ref).abs().max().item() <= 2e-5

@@ -1,0 +1,163 @@
+// bf16 tcgen05 HiFi-GAN decoder: Generator.forward (reference models.py:271-290) as a chain of
+// umma_conv1d launches over planar bf16 activations.  All leaky-relus, biases, residual adds, the MRF
+// sum (/3) and the ConvTranspose1d phase scatter are fused into conv epilogues; no elementwise pass
+// touches HBM between convs.
+#include "decoder.cuh"
+#include "ops_misc.cuh"
+#include "umma_conv.cuh"
+
+namespace vs {
+
+int ups_taps(int i, int* pad_l) {
+  const int s = kUpRate[i], K = kUpKernel[i], p = kUpPad[i];
+  int dmax = -1000, dmin = 1000;
+  for (int ph = 0; ph < s; ++ph) {
+    const int hi = (ph + p) / s, lo = hi - K / s + 1;
+    dmax = hi > dmax ? hi : dmax;
+    dmin = lo < dmin ? lo : dmin;
+  }
+  *pad_l = -dmin;
+  return dmax - dmin + 1;
+}
+
+int resolve_decoder_bf16(const FetchFn& fetch, DecoderW* d) {
+#define DBF16(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_BF16, reinterpret_cast<const void**>(&(field))))
+  DBF16(d->pre16.w, "dec16.pre.w", 7 * 192 * 512);
+  d->pre16.b = d->pre.b;
+  for (int i = 0; i < kDecStages; ++i) {
+    const int cin = kStageC[i], cout = kStageC[i + 1];
+    int pad_l = 0;
+    const int taps = ups_taps(i, &pad_l);
+    DBF16(d->ups16[i].w, "dec16.ups." + std::to_string(i) + ".w", (int64_t)taps * cin * cout * kUpRate[i]);
+    d->ups16[i].b = d->ups[i].b;
+    for (int j = 0; j < kDecKernels; ++j) {
+      const int n = i * kDecKernels + j;
+      for (int mth = 0; mth < kDecDils; ++mth) {
+        const std::string q = "dec16.rb." + std::to_string(n) + ".";
+        const int64_t numel = (int64_t)kResK[j] * cout * cout;
+        DBF16(d->c1_16[n][mth].w, q + "c1." + std::to_string(mth) + ".w", numel);
+        DBF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
+        d->c1_16[n][mth].b = d->c1[n][mth].b;
+        d->c2_16[n][mth].b = d->c2[n][mth].b;
+      }
+    }
+  }
+#undef DBF16
+  return VS_OK;
+}
+
+// fp32 row-major [R][C] -> planar bf16 [C/8][R][8], zero on invalid rows
+__global__ void to_planar_bf16_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
+                                      __nv_bfloat16* __restrict__ out, int R, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (plane, row)
+  if (i >= (C / 8) * R) return;
+  const int pl = i / R, r = i % R;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (row_utt[r] >= 0) {
+    const float4 a = *reinterpret_cast<const float4*>(x + (size_t)r * C + pl * 8);
+    const float4 b = *reinterpret_cast<const float4*>(x + (size_t)r * C + pl * 8 + 4);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
+}
+
+// conv_post (32 -> 1, k7, no bias) + tanh on planar bf16 input that already carries leaky_relu(.,0.01)
+// (models.py:286-288).  224 MACs per sample: CUDA cores, one thread per output sample.
+__global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                 const int32_t* __restrict__ row_utt, int row_div, float* __restrict__ wave, int R) {
+  __shared__ float ws[7 * 32];
+  for (int i = threadIdx.x; i < 7 * 32; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (row_utt[r / row_div] < 0) { wave[r] = 0.f; return; }
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const int rr = r + t - 3;
+    if (rr < 0 || rr >= R) continue;
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)pl * R + rr) * 8);
+      const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc = fmaf(__uint_as_float(wd[e] << 16), ws[t * 32 + pl * 8 + 2 * e], acc);
+        acc = fmaf(__uint_as_float(wd[e] & 0xFFFF0000u), ws[t * 32 + pl * 8 + 2 * e + 1], acc);
+      }
+    }
+  }
+  wave[r] = tanhf(acc);
+}
+
+int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
+                cudaStream_t st) {
+  const int R = rows.n_rows;
+  int32_t* valid = ws.take<int32_t>(R);
+  __nv_bfloat16* zin = ws.take<__nv_bfloat16>((int64_t)R * kHidden);
+  __nv_bfloat16* buf[9];
+  for (int i = 0; i < 9; ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
+  if (!ws.ok) { set_error("decode_bf16: workspace too small"); return VS_ERR_WORKSPACE; }
+  __nv_bfloat16 *XR = buf[0], *XA = buf[1], *T = buf[2], *AR = buf[3], *AA = buf[4], *BR = buf[5], *BA = buf[6],
+                *S = buf[7], *NEXT = buf[8];
+
+  VS_TRY(mask_frames(rows, max_len, valid, st));                         // (z * x_mask)[:, :, :max_len]  models.py:720
+  to_planar_bf16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
+  VS_LAUNCH_CHECK();
+
+  UmmaConv c;
+  c.in = zin; c.w = w.pre16.w; c.bias = w.pre16.b; c.ubias = w.cond_tab; c.ubias_idx = rows.sid;
+  c.out_act = NEXT; c.act_slope = 0.1f; c.row_utt = valid; c.row_div = 1; c.R = R; c.Cin = kHidden; c.N = 512;
+  c.taps = 7; c.pad_l = 3;
+  VS_TRY(umma_conv1d(c, st));                                            // lrelu(conv_pre(z) + cond(g))  models.py:272-276
+
+  int mul = 1;
+  for (int i = 0; i < kDecStages; ++i) {
+    const int cin = kStageC[i], cout = kStageC[i + 1], s = kUpRate[i];
+    int pad_l = 0;
+    const int taps = ups_taps(i, &pad_l);
+    c = UmmaConv();
+    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = XR; c.out_act = XA; c.act_slope = 0.1f;
+    c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
+    c.up = s;
+    VS_TRY(umma_conv1d(c, st));                                          // ups[i] (ConvTranspose1d)  models.py:277
+    mul *= s;
+    const int Rs = R * mul;
+    for (int j = 0; j < kDecKernels; ++j) {
+      const int n = i * kDecKernels + j, k = kResK[j];
+      const __nv_bfloat16* cur_raw = XR;
+      const __nv_bfloat16* cur_act = XA;
+      for (int mth = 0; mth < kDecDils; ++mth) {
+        const bool last = (mth == kDecDils - 1);
+        c = UmmaConv();
+        c.row_utt = valid; c.row_div = mul; c.R = Rs; c.Cin = cout; c.N = cout; c.taps = k; c.pad_l = (k - 1) / 2;
+        c.in = cur_act; c.w = w.c1_16[n][mth].w; c.bias = w.c1_16[n][mth].b; c.dil = kResD[mth];
+        c.out_act = T; c.act_slope = 0.1f;
+        VS_TRY(umma_conv1d(c, st));                                      // lrelu(c1(lrelu(x)))  modules.py:211-218
+        c.in = T; c.w = w.c2_16[n][mth].w; c.bias = w.c2_16[n][mth].b; c.dil = 1; c.res = cur_raw;
+        if (!last) {
+          c.out_raw = (mth == 0) ? AR : BR; c.out_act = (mth == 0) ? AA : BA;      // x = c2(.) + x  modules.py:219-220
+        } else {
+          c.res2 = (j > 0) ? S : nullptr;                                // xs += resblock_j(x)  models.py:280-284
+          if (j < kDecKernels - 1) { c.out_raw = S; c.out_act = nullptr; }
+          else {                                                         // x = xs / 3, then the next stage's leaky_relu
+            c.out_raw = nullptr; c.out_act = NEXT; c.act_scale = 1.f / kDecKernels;
+            c.act_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;          // final lrelu uses the default slope (Q3)
+          }
+        }
+        VS_TRY(umma_conv1d(c, st));
+        cur_raw = (mth == 0) ? AR : BR;
+        cur_act = (mth == 0) ? AA : BA;
+      }
+    }
+  }
+  const int Rw = R * mul;
+  conv_post_kernel<<<(Rw + 255) / 256, 256, 0, st>>>(NEXT, w.post_w, valid, mul, wave, Rw);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+}  // namespace vs

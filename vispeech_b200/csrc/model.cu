@@ -1,0 +1,397 @@
+// Weight registry + subsystem orchestration + the C ABI of include/vispeech_b200.h.
+// Each vs_* subsystem mirrors one block of SynthesizerTrn.infer (reference models.py:672-722).
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ops_misc.cuh"
+#include "decoder.cuh"
+#include "umma_conv.cuh"
+
+namespace vs {
+
+struct Tensor { const void* ptr; int64_t numel; int32_t dtype; };
+
+struct EncLayer {
+  const float *wqkv, *bqkv, *wo, *bo, *ek, *ev, *g1, *b1, *g2, *b2, *w1, *bf1, *w2, *bf2;
+};
+struct FlowW {
+  const float *pre_w, *pre_b, *post_w, *post_b, *cond_tab;
+  const float *in_w[8], *in_b[8], *rs_w[8], *rs_b[8];
+};
+
+}  // namespace vs
+
+struct VsModel {
+  VsConfig cfg;
+  std::unordered_map<std::string, vs::Tensor> tensors;
+  bool finalized = false;
+  // resolved views
+  const float* emb = nullptr;
+  std::vector<vs::EncLayer> enc_text, enc_pitch, enc_prior;
+  const float *dp_cond, *dp_w1, *dp_b1, *dp_g1, *dp_be1, *dp_w2, *dp_b2, *dp_g2, *dp_be2, *dp_wp, *dp_bp;
+  const float *pp_cond, *pp_wf0, *pp_bf0;
+  const float *ep_cond, *ep_w1, *ep_b1, *ep_g1, *ep_be1, *ep_w2, *ep_b2, *ep_g2, *ep_be2, *ep_wl, *ep_bl;
+  const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
+  const float *proj_w, *proj_b;
+  std::vector<vs::FlowW> flows;
+  vs::DecoderW dec;
+};
+
+namespace vs {
+
+static int fetch(VsModel* m, const std::string& name, int64_t numel, int32_t dtype, const void** out) {
+  auto it = m->tensors.find(name);
+  if (it == m->tensors.end()) { set_error("weight '%s' was never registered", name.c_str()); return VS_ERR_MISSING; }
+  if (it->second.numel != numel || it->second.dtype != dtype) {
+    set_error("weight '%s': expected numel=%lld dtype=%d, got numel=%lld dtype=%d", name.c_str(), (long long)numel,
+              dtype, (long long)it->second.numel, it->second.dtype);
+    return VS_ERR_INVALID;
+  }
+  *out = it->second.ptr;
+  return VS_OK;
+}
+#define FETCH_F32(field, name, numel) VS_TRY(fetch(m, name, numel, VS_DTYPE_F32, reinterpret_cast<const void**>(&(field))))
+
+static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::vector<EncLayer>* out) {
+  const int H = kHidden, F = kFilter;
+  out->resize(n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    EncLayer& L = (*out)[i];
+    const std::string q = p + "." + std::to_string(i) + ".";
+    FETCH_F32(L.wqkv, q + "wqkv", (int64_t)H * 3 * H);  FETCH_F32(L.bqkv, q + "bqkv", 3 * H);
+    FETCH_F32(L.wo, q + "wo", (int64_t)H * H);          FETCH_F32(L.bo, q + "bo", H);
+    FETCH_F32(L.ek, q + "ek", kRel * kHeadDim);         FETCH_F32(L.ev, q + "ev", kRel * kHeadDim);
+    FETCH_F32(L.g1, q + "g1", H);  FETCH_F32(L.b1, q + "b1", H);
+    FETCH_F32(L.g2, q + "g2", H);  FETCH_F32(L.b2, q + "b2", H);
+    FETCH_F32(L.w1, q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.bf1, q + "bf1", F);
+    FETCH_F32(L.w2, q + "w2", (int64_t)3 * F * H);      FETCH_F32(L.bf2, q + "bf2", H);
+  }
+  return VS_OK;
+}
+
+static int finalize(VsModel* m) {
+  const int H = kHidden, S = m->cfg.n_speakers;
+  FETCH_F32(m->emb, "emb", (int64_t)m->cfg.n_vocab * H);
+  VS_TRY(resolve_encoder(m, "enc_p.encoder", m->cfg.n_layers, &m->enc_text));
+  VS_TRY(resolve_encoder(m, "pitch_predictor.pitch_net", m->cfg.pitch_layers, &m->enc_pitch));
+  VS_TRY(resolve_encoder(m, "frame_prior_net.fft_block", m->cfg.n_layers, &m->enc_prior));
+  FETCH_F32(m->dp_cond, "dp.cond_tab", (int64_t)S * H);
+  FETCH_F32(m->dp_w1, "dp.w1", 3 * H * 256);   FETCH_F32(m->dp_b1, "dp.b1", 256);
+  FETCH_F32(m->dp_g1, "dp.g1", 256);           FETCH_F32(m->dp_be1, "dp.be1", 256);
+  FETCH_F32(m->dp_w2, "dp.w2", 3 * 256 * 256); FETCH_F32(m->dp_b2, "dp.b2", 256);
+  FETCH_F32(m->dp_g2, "dp.g2", 256);           FETCH_F32(m->dp_be2, "dp.be2", 256);
+  FETCH_F32(m->dp_wp, "dp.wp", 256);           FETCH_F32(m->dp_bp, "dp.bp", 1);
+  FETCH_F32(m->pp_cond, "pp.cond_tab", (int64_t)S * H);
+  FETCH_F32(m->pp_wf0, "pp.wf0", H);           FETCH_F32(m->pp_bf0, "pp.bf0", 1);
+  FETCH_F32(m->ep_cond, "ep.cond_tab", (int64_t)S * H);
+  FETCH_F32(m->ep_w1, "ep.w1", 3 * H * 768);   FETCH_F32(m->ep_b1, "ep.b1", 768);
+  FETCH_F32(m->ep_g1, "ep.g1", 768);           FETCH_F32(m->ep_be1, "ep.be1", 768);
+  FETCH_F32(m->ep_w2, "ep.w2", 3 * 768 * 768); FETCH_F32(m->ep_b2, "ep.b2", 768);
+  FETCH_F32(m->ep_g2, "ep.g2", 768);           FETCH_F32(m->ep_be2, "ep.be2", 768);
+  FETCH_F32(m->ep_wl, "ep.wl", 768);           FETCH_F32(m->ep_bl, "ep.bl", 1);
+  FETCH_F32(m->pitch_pre_w, "pitch_prenet.w", H * 3);   FETCH_F32(m->pitch_pre_b, "pitch_prenet.b", H);
+  FETCH_F32(m->energy_pre_w, "energy_prenet.w", H * 3); FETCH_F32(m->energy_pre_b, "energy_prenet.b", H);
+  FETCH_F32(m->proj_w, "proj.w", H * 2 * H);   FETCH_F32(m->proj_b, "proj.b", 2 * H);
+  const int L = m->cfg.flow_layers;
+  m->flows.resize(m->cfg.n_flows);
+  for (int f = 0; f < m->cfg.n_flows; ++f) {
+    FlowW& w = m->flows[f];
+    const std::string p = "flow." + std::to_string(f) + ".";
+    FETCH_F32(w.pre_w, p + "pre.w", (H / 2) * H);   FETCH_F32(w.pre_b, p + "pre.b", H);
+    FETCH_F32(w.post_w, p + "post.w", H * (H / 2)); FETCH_F32(w.post_b, p + "post.b", H / 2);
+    FETCH_F32(w.cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
+    for (int l = 0; l < L; ++l) {
+      const std::string q = p + std::to_string(l) + ".";
+      const int rs = (l < L - 1) ? 2 * H : H;
+      FETCH_F32(w.in_w[l], q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.in_b[l], q + "in.b", 2 * H);
+      FETCH_F32(w.rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w.rs_b[l], q + "rs.b", rs);
+    }
+  }
+  VS_TRY(resolve_decoder(
+      [m](const std::string& name, int64_t numel, int32_t dtype, const void** out) { return fetch(m, name, numel, dtype, out); },
+      m->cfg.n_speakers, &m->dec));
+  m->finalized = true;
+  return VS_OK;
+}
+
+// ---- attentions.Encoder.forward (attentions.py:35-47), in place on x -------------------------------
+static int64_t encoder_ws_floats(int R) { return (int64_t)R * (3 * kHidden + kHidden + kHidden + kFilter); }
+
+static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& rows, float* x, Workspace& ws,
+                           cudaStream_t st) {
+  const int R = rows.n_rows, H = kHidden, F = kFilter;
+  float* qkv = ws.take<float>((int64_t)R * 3 * H);
+  float* att = ws.take<float>((int64_t)R * H);
+  float* y = ws.take<float>((int64_t)R * H);
+  float* hbuf = ws.take<float>((int64_t)R * F);
+  if (!ws.ok) { set_error("encoder: workspace too small"); return VS_ERR_WORKSPACE; }
+  for (const EncLayer& L : layers) {
+    ConvF32 c;
+    c.R = R; c.row_utt = rows.row_utt;
+    c.in = x; c.in_ld = H; c.Cin = H; c.w = L.wqkv; c.bias = L.bqkv; c.out = qkv; c.out_ld = 3 * H; c.Cout = 3 * H;
+    VS_TRY(conv1d_f32(c, st));                                             // conv_q|k|v (attentions.py:139-141)
+    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st));                 // attentions.py:148-179
+    c.in = att; c.w = L.wo; c.bias = L.bo; c.out = y; c.out_ld = H; c.Cout = H;
+    VS_TRY(conv1d_f32(c, st));                                             // conv_o
+    VS_TRY(layernorm_rows(x, y, L.g1, L.b1, x, R, H, rows.row_utt, st));   // x = LN(x + y)
+    c.in = x; c.Cin = H; c.w = L.w1; c.bias = L.bf1; c.out = hbuf; c.out_ld = F; c.Cout = F; c.k = 3; c.pad_l = 1; c.act = 1;
+    VS_TRY(conv1d_f32(c, st));                                             // FFN conv_1 + relu (attentions.py:278-282)
+    c.in = hbuf; c.in_ld = F; c.Cin = F; c.w = L.w2; c.bias = L.bf2; c.out = y; c.out_ld = H; c.Cout = H; c.act = 0;
+    VS_TRY(conv1d_f32(c, st));                                             // FFN conv_2
+    VS_TRY(layernorm_rows(x, y, L.g2, L.b2, x, R, H, rows.row_utt, st));
+  }
+  return VS_OK;
+}
+
+static int check_rows(const VsRows* r, const char* what) {
+  VS_REQUIRE(r && r->n_utt > 0 && r->n_rows > 0 && r->row_utt && r->utt_start && r->utt_len && r->sid,
+             "%s: incomplete VsRows", what);
+  return VS_OK;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+extern "C" {
+
+const char* vs_last_error(void) { return vs::last_error(); }
+int vs_version(void) { return 1; }
+
+int vs_model_create(const VsConfig* cfg, VsModel** out) {
+  VS_REQUIRE(cfg && out, "vs_model_create: null argument");
+  VS_REQUIRE(cfg->hidden == kHidden && cfg->filter == kFilter && cfg->n_heads == kHeads && cfg->window == kWindow &&
+                 cfg->hop == kHop && cfg->upsample_initial == 512 && cfg->gin == 256 && cfg->flow_layers <= 8,
+             "vs_model_create: only the configs/config.json architecture is built (hidden 192, filter 768, 2 heads, "
+             "window 4, hop 512)");
+  int n_dev = 0;
+  VS_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  VS_REQUIRE(n_dev > 0, "vs_model_create: no CUDA device; there is no CPU fallback");
+  VsModel* m = new VsModel();
+  m->cfg = *cfg;
+  *out = m;
+  return VS_OK;
+}
+
+void vs_model_destroy(VsModel* m) { delete m; }
+
+int vs_model_set_tensor(VsModel* m, const char* name, const void* ptr, int64_t numel, int32_t dtype) {
+  VS_REQUIRE(m && name && ptr && numel > 0, "vs_model_set_tensor: bad argument");
+  m->tensors[name] = vs::Tensor{ptr, numel, dtype};
+  m->finalized = false;
+  return VS_OK;
+}
+
+int vs_model_finalize(VsModel* m) {
+  VS_REQUIRE(m, "vs_model_finalize: null model");
+  return vs::finalize(m);
+}
+
+int64_t vs_workspace_bytes(const VsModel* m, int32_t rp, int32_t rf) {
+  (void)m;
+  const int64_t H = kHidden;
+  const int64_t enc_p = encoder_ws_floats(rp), enc_f = encoder_ws_floats(rf);
+  const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8);
+  const int64_t prior = enc_f + (int64_t)rf * 2 * H;
+  const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + H / 2);
+  const int64_t dec = decoder_ws_floats(rf);
+  int64_t mx = variance;
+  if (prior > mx) mx = prior;
+  if (flow > mx) mx = flow;
+  if (dec > mx) mx = dec;
+  return mx * 4 + (1 << 20);
+}
+
+#define VS_ENTER(m, rows, what)                                                          \
+  VS_REQUIRE((m) && (m)->finalized, what ": model not finalized");                       \
+  VS_TRY(check_rows(rows, what));                                                        \
+  cudaStream_t st = static_cast<cudaStream_t>(stream);                                   \
+  Workspace W(ws, ws_bytes);
+
+int vs_text_encode(const VsModel* m, const VsRows* rows, const int32_t* ids_rows, float* x_out, void* ws,
+                   int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_text_encode");
+  VS_TRY(embed_rows(ids_rows, m->emb, x_out, rows->n_rows, m->cfg.n_vocab, st));
+  return encoder_forward(m->enc_text, *rows, x_out, W, st);
+}
+
+int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t dur_mode, float dur_scale,
+                        const double* dur_ctrl, int32_t pitch_mode, float pitch_scale, const float* pitch_ctrl,
+                        int32_t energy_mode, float energy_scale, const float* energy_ctrl, double* duration_out,
+                        float* f0_out, float* energy_out, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_variance_adapter");
+  VS_REQUIRE((dur_mode == 0 || (dur_mode == 2 && dur_ctrl)) && (pitch_mode == 0 || (pitch_mode == 2 && pitch_ctrl)) &&
+                 (energy_mode == 0 || (energy_mode == 2 && energy_ctrl)),
+             "vs_variance_adapter: mode must be 0 (predict) or 2 (override, needs the control array)");
+  const int R = rows->n_rows, H = kHidden;
+  float* t = W.take<float>((int64_t)R * H);
+  float* h1 = W.take<float>((int64_t)R * 768);
+  float* h2 = W.take<float>((int64_t)R * 768);
+  float* s0 = W.take<float>(R);
+  float* s1 = W.take<float>(R);
+  if (!W.ok) { set_error("vs_variance_adapter: workspace too small"); return VS_ERR_WORKSPACE; }
+  ConvF32 c;
+
+  // duration (models.py:681-688; DurationPredictor.forward :119-133) - uses x BEFORE the prenets touch it
+  if (dur_mode == 0) {
+    VS_TRY(add_speaker_rows(x, m->dp_cond, *rows, t, H, st));
+    c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
+    c.in = t; c.in_ld = H; c.Cin = H; c.w = m->dp_w1; c.bias = m->dp_b1; c.out = h1; c.out_ld = 256; c.Cout = 256;
+    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(layernorm_rows(h1, nullptr, m->dp_g1, m->dp_be1, h1, R, 256, rows->row_utt, st));
+    c.in = h1; c.in_ld = 256; c.Cin = 256; c.w = m->dp_w2; c.bias = m->dp_b2; c.out = h2;
+    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(layernorm_rows(h2, nullptr, m->dp_g2, m->dp_be2, h2, R, 256, rows->row_utt, st));
+    VS_TRY(row_dot(h2, 256, m->dp_wp, m->dp_bp, s0, R, 256, rows->row_utt, st));
+  }
+  VS_TRY(duration_rows(s0, dur_ctrl, dur_mode, dur_scale, *rows, duration_out, st));
+
+  // pitch (models.py:691-698; PitchPredictor.forward :505-514)
+  if (pitch_mode == 0) {
+    VS_TRY(add_speaker_rows(x, m->pp_cond, *rows, t, H, st));
+    Workspace W2 = W;
+    VS_TRY(encoder_forward(m->enc_pitch, *rows, t, W2, st));
+    VS_TRY(row_dot(t, H, m->pp_wf0, m->pp_bf0, s0, R, H, rows->row_utt, st));
+  }
+  VS_TRY(pitch_rows(s0, pitch_ctrl, pitch_mode, pitch_scale, *rows, s1, f0_out, st));
+  VS_TRY(prenet_add(x, s1, m->pitch_pre_w, m->pitch_pre_b, *rows, st));   // x += pitch_prenet(LF0)
+
+  // energy (models.py:701-708; EnergyPredictor frame_prior_network.py:119-124) - sees x after the pitch prenet
+  if (energy_mode == 0) {
+    VS_TRY(add_speaker_rows(x, m->ep_cond, *rows, t, H, st));
+    c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
+    c.in = t; c.in_ld = H; c.Cin = H; c.w = m->ep_w1; c.bias = m->ep_b1; c.out = h1; c.out_ld = 768; c.Cout = 768;
+    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(layernorm_rows(h1, nullptr, m->ep_g1, m->ep_be1, h1, R, 768, rows->row_utt, st));
+    c.in = h1; c.in_ld = 768; c.Cin = 768; c.w = m->ep_w2; c.bias = m->ep_b2; c.out = h2;
+    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(layernorm_rows(h2, nullptr, m->ep_g2, m->ep_be2, h2, R, 768, rows->row_utt, st));
+    VS_TRY(row_dot(h2, 768, m->ep_wl, m->ep_bl, s0, R, 768, rows->row_utt, st));
+  }
+  VS_TRY(energy_rows(s0, energy_ctrl, energy_mode, energy_scale, *rows, s1, energy_out, st));
+  VS_TRY(prenet_add(x, s1, m->energy_pre_w, m->energy_pre_b, *rows, st)); // x += energy_prenet(norm_energy)
+  return VS_OK;
+}
+
+int vs_length_regulate_count(const VsRows* rows, const double* duration, int32_t* cum_out, int32_t* frames_out,
+                             void* stream) {
+  VS_TRY(check_rows(rows, "vs_length_regulate_count"));
+  VS_REQUIRE(duration && cum_out && frames_out, "vs_length_regulate_count: null pointer");
+  return lr_count(*rows, duration, cum_out, frames_out, static_cast<cudaStream_t>(stream));
+}
+
+int vs_length_regulate_gather(const VsRows* rows_p, const VsRows* rows_f, const float* x_p, const int32_t* cum,
+                              float* x_f, int32_t* lr_index, void* stream) {
+  VS_TRY(check_rows(rows_p, "vs_length_regulate_gather"));
+  VS_TRY(check_rows(rows_f, "vs_length_regulate_gather"));
+  VS_REQUIRE(rows_p->n_utt == rows_f->n_utt, "vs_length_regulate_gather: utterance counts differ");
+  return lr_gather(*rows_p, *rows_f, x_p, cum, x_f, lr_index, static_cast<cudaStream_t>(stream));
+}
+
+int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const float* noise, float noise_scale,
+                   float* x_frame_out, float* m_p, float* logs_p, float* z_p, void* ws, int64_t ws_bytes,
+                   void* stream) {
+  VS_ENTER(m, rows, "vs_frame_prior");
+  const int R = rows->n_rows, H = kHidden;
+  float* stats = W.take<float>((int64_t)R * 2 * H);
+  if (!W.ok) { set_error("vs_frame_prior: workspace too small"); return VS_ERR_WORKSPACE; }
+  if (x_frame_out != x_f)
+    VS_CUDA_CHECK(cudaMemcpyAsync(x_frame_out, x_f, sizeof(float) * (size_t)R * H, cudaMemcpyDeviceToDevice, st));
+  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st));       // FramePriorNet.forward models.py:466-470
+  ConvF32 c;                                                               // Projection.forward models.py:526-529
+  c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
+  c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
+  VS_TRY(conv1d_f32(c, st));
+  return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
+}
+
+int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_flow_reverse");
+  const int R = rows->n_rows, H = kHidden, L = m->cfg.flow_layers;
+  float* h = W.take<float>((int64_t)R * H);
+  float* a = W.take<float>((int64_t)R * 2 * H);
+  float* acts = W.take<float>((int64_t)R * H);
+  float* rs = W.take<float>((int64_t)R * 2 * H);
+  float* skip = W.take<float>((int64_t)R * H);
+  float* mm = W.take<float>((int64_t)R * (H / 2));
+  if (!W.ok) { set_error("vs_flow_reverse: workspace too small"); return VS_ERR_WORKSPACE; }
+  // reversed(flows) = Flip,RCL3,Flip,RCL2,Flip,RCL1,Flip,RCL0 (models.py:206-208).  The Flips are folded into
+  // packed weights: layer f runs on the physically un-flipped tensor with `flipped = f odd` (packing.py).
+  for (int f = m->cfg.n_flows - 1; f >= 0; --f) {
+    const FlowW& w = m->flows[f];
+    const bool flipped = (f & 1) != 0;
+    const int in_off = flipped ? H / 2 : 0, upd_off = flipped ? 0 : H / 2;
+    ConvF32 c;
+    c.R = R; c.row_utt = rows->row_utt;
+    c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;
+    VS_TRY(conv1d_f32(c, st));                                             // h = pre(x0) * mask  (modules.py:326)
+    for (int l = 0; l < L; ++l) {                                          // WN.forward (modules.py:148-176)
+      const int rsC = (l < L - 1) ? 2 * H : H;
+      c = ConvF32(); c.R = R;
+      c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = a; c.out_ld = 2 * H; c.Cout = 2 * H;
+      c.k = 5; c.pad_l = 2;
+      VS_TRY(conv1d_f32(c, st));
+      VS_TRY(wn_gate(a, w.cond_tab, 2 * H * L, 2 * H * l, *rows, acts, st));
+      c = ConvF32(); c.R = R;
+      c.in = acts; c.in_ld = H; c.Cin = H; c.w = w.rs_w[l]; c.bias = w.rs_b[l]; c.out = rs; c.out_ld = rsC; c.Cout = rsC;
+      VS_TRY(conv1d_f32(c, st));
+      VS_TRY(wn_update(rs, rsC, l == L - 1, l == 0, *rows, h, skip, st));
+    }
+    c = ConvF32(); c.R = R;
+    c.in = skip; c.in_ld = H; c.Cin = H; c.w = w.post_w; c.bias = w.post_b; c.out = mm; c.out_ld = H / 2; c.Cout = H / 2;
+    VS_TRY(conv1d_f32(c, st));                                             // m = post(h) (modules.py:328)
+    VS_TRY(coupling_sub(z, upd_off, mm, *rows, st));                       // x1 = (x1 - m) * mask (modules.py:341)
+  }
+  return VS_OK;
+}
+
+int vs_hifigan_decode(const VsModel* m, const VsRows* rows, const float* z, int32_t max_len, float* wave_out,
+                      int32_t precision, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_hifigan_decode");
+  VS_REQUIRE(precision == 0 || precision == 1, "vs_hifigan_decode: precision must be 0 (bf16 tcgen05) or 1 (fp32 check)");
+  if (precision == 1) return decode_f32(m->dec, *rows, z, max_len, wave_out, W, st);
+  return decode_bf16(m->dec, *rows, z, max_len, wave_out, W, st);
+}
+
+int vs_unpack_rows(const VsRows* rows, const float* x, int32_t C, int32_t rows_mul, int32_t t_max, float* out,
+                   void* stream) {
+  VS_TRY(check_rows(rows, "vs_unpack_rows"));
+  return unpack_rows(*rows, x, C, rows_mul, t_max, out, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w, const float* bias, float* out, int32_t out_ld,
+                     int32_t n_rows, int32_t c_in, int32_t c_out, int32_t k, int32_t dil, int32_t pad_l, float in_slope,
+                     int32_t act, const int32_t* row_utt, int32_t row_div, void* stream) {
+  ConvF32 c;
+  c.in = in; c.in_ld = in_ld; c.w = w; c.bias = bias; c.out = out; c.out_ld = out_ld; c.R = n_rows; c.Cin = c_in;
+  c.Cout = c_out; c.k = k; c.dil = dil; c.pad_l = pad_l; c.in_slope = in_slope; c.act = act; c.row_utt = row_utt;
+  c.row_div = row_div > 0 ? row_div : 1;
+  return conv1d_f32(c, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float* out, int32_t n_rows,
+                    int32_t C, const int32_t* row_utt, void* stream) {
+  return layernorm_rows(a, b, gamma, beta, out, n_rows, C, row_utt, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_rel_attention(const VsRows* rows, const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
+                        float* out, void* stream) {
+  VS_TRY(check_rows(rows, "vs_op_rel_attention"));
+  return rel_attention(*rows, qkv, emb_rel_k, emb_rel_v, out, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,
+                      void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
+                      int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
+                      const int32_t* row_utt, int32_t row_div, void* stream) {
+  UmmaConv c;
+  c.in = static_cast<const __nv_bfloat16*>(in_planar); c.w = static_cast<const __nv_bfloat16*>(w_packed);
+  c.bias = bias; c.res = static_cast<const __nv_bfloat16*>(res_planar);
+  c.out_raw = static_cast<__nv_bfloat16*>(out_raw); c.out_act = static_cast<__nv_bfloat16*>(out_act);
+  c.R = n_rows; c.Cin = c_in; c.N = n_cols; c.taps = taps; c.dil = dil; c.pad_l = pad_l; c.up = up;
+  c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
+  return umma_conv1d(c, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

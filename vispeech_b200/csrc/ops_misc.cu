@@ -1,0 +1,321 @@
+// Small memory-bound kernels of the path: embedding, speaker-conditioning adds, variance-adapter
+// formulas and prenets, the length regulator (prefix sum + search + gather), WN gate / residual
+// updates, coupling update, prior sampling, ragged-rows -> [B][C][T] unpack.
+#include "ops_misc.cuh"
+
+namespace vs {
+
+// ---- TextEncoder embedding: x = emb[id] * sqrt(H) (models.py:169); gaps -> 0 -----------------------
+__global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
+                                  int R, int n_vocab, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * kHidden) return;
+  const int r = i / kHidden, c = i % kHidden;
+  const int id = ids[r];
+  x[i] = (id >= 0 && id < n_vocab) ? emb[(size_t)id * kHidden + c] * scale : 0.f;
+}
+int embed_rows(const int32_t* ids, const float* emb, float* x, int R, int n_vocab, cudaStream_t st) {
+  embed_rows_kernel<<<(R * kHidden + 255) / 256, 256, 0, st>>>(ids, emb, x, R, n_vocab, sqrtf((float)kHidden));
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- out = valid ? x + tab[sid[utt]] : 0   (x + cond(g): models.py:123, :509, frame_prior_network.py:121) ----
+__global__ void add_speaker_rows_kernel(const float* __restrict__ x, const float* __restrict__ tab,
+                                        const int32_t* __restrict__ row_utt, const int32_t* __restrict__ sid,
+                                        float* __restrict__ out, int R, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * C) return;
+  const int r = i / C, c = i % C;
+  const int u = row_utt[r];
+  out[i] = (u >= 0) ? x[i] + tab[(size_t)sid[u] * C + c] : 0.f;
+}
+int add_speaker_rows(const float* x, const float* tab, const VsRows& rows, float* out, int C, cudaStream_t st) {
+  add_speaker_rows_kernel<<<(rows.n_rows * C + 255) / 256, 256, 0, st>>>(x, tab, rows.row_utt, rows.sid, out,
+                                                                        rows.n_rows, C);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- variance adapter glue (models.py:681-708) ------------------------------------------------------
+// duration: mode 0: ceil((exp(logw) - 1) * scale) (x_mask == 1 on valid rows); mode 2: control verbatim.
+__global__ void duration_kernel(const float* __restrict__ logw, const double* __restrict__ ctrl, int mode, float scale,
+                                const int32_t* __restrict__ row_utt, double* __restrict__ dur, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (row_utt[r] < 0) { dur[r] = 0.0; return; }
+  if (mode == 2) dur[r] = ctrl[r];
+  else dur[r] = (double)ceilf((expf(logw[r]) - 1.f) * scale);
+}
+// pitch: lf0 (mode 0: pred*scale; mode 2: 2595*log10(1+hz/700)/500), F0 = (10^(lf0*500/2590)-1)*700 (sic, Q2)
+__global__ void pitch_kernel(const float* __restrict__ pred, const float* __restrict__ ctrl, int mode, float scale,
+                             const int32_t* __restrict__ row_utt, float* __restrict__ lf0, float* __restrict__ f0, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (row_utt[r] < 0) { lf0[r] = 0.f; f0[r] = 0.f; return; }
+  float v;
+  if (mode == 2) v = (2595.f * log10f(1.f + ctrl[r] / 700.f)) / 500.f;
+  else v = pred[r] * scale;
+  lf0[r] = v;
+  f0[r] = (powf(10.f, v * 500.f / 2590.f) - 1.f) * 700.f;
+}
+// energy: norm (mode 0: (((pred*36+60)*scale)-60)/36; mode 2: (raw-60)/36), energy = norm*36+60
+__global__ void energy_kernel(const float* __restrict__ pred, const float* __restrict__ ctrl, int mode, float scale,
+                              const int32_t* __restrict__ row_utt, float* __restrict__ norm, float* __restrict__ energy,
+                              int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (row_utt[r] < 0) { norm[r] = 0.f; energy[r] = 0.f; return; }
+  float v;
+  if (mode == 2) v = (ctrl[r] - 60.f) / 36.f;
+  else v = (((pred[r] * 36.f + 60.f) * scale) - 60.f) / 36.f;
+  norm[r] = v;
+  energy[r] = v * 36.f + 60.f;
+}
+int duration_rows(const float* logw, const double* ctrl, int mode, float scale, const VsRows& rows, double* dur,
+                  cudaStream_t st) {
+  duration_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(logw, ctrl, mode, scale, rows.row_utt, dur, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+int pitch_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* lf0, float* f0,
+               cudaStream_t st) {
+  pitch_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(pred, ctrl, mode, scale, rows.row_utt, lf0, f0, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+int energy_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* norm,
+                float* energy, cudaStream_t st) {
+  energy_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(pred, ctrl, mode, scale, rows.row_utt, norm, energy,
+                                                          rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// x[r][c] += b[c] + w[c][0]*v[r-1] + w[c][1]*v[r] + w[c][2]*v[r+1]   (Conv1d(1,192,3,padding=1): models.py:612-613,697,707)
+// v is zero on gap rows, which is exactly the zero padding of a batch-1 call.
+__global__ void prenet_add_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ w,
+                                  const float* __restrict__ b, const int32_t* __restrict__ row_utt, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * kHidden) return;
+  const int r = i / kHidden, c = i % kHidden;
+  if (row_utt[r] < 0) return;
+  const float vm = r > 0 ? v[r - 1] : 0.f, v0 = v[r], vp = r + 1 < R ? v[r + 1] : 0.f;
+  x[i] += b[c] + w[c * 3 + 0] * vm + w[c * 3 + 1] * v0 + w[c * 3 + 2] * vp;
+}
+int prenet_add(float* x, const float* v, const float* w, const float* b, const VsRows& rows, cudaStream_t st) {
+  prenet_add_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(x, v, w, b, rows.row_utt, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- length regulator (models.py:398-427) -----------------------------------------------------------
+// count: one CTA per utterance; n_i = max(int(d_i), 0) with int() = truncation toward zero of the
+// Python float that .item() returned (models.py:421-423); inclusive scan in phoneme order.
+__global__ void lr_count_kernel(VsRows rows, const double* __restrict__ dur, int32_t* __restrict__ cum,
+                                int32_t* __restrict__ frames) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int b = blockIdx.x, T = rows.utt_len[b], start = rows.utt_start[b];
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int i = base + tid;
+    int32_t n = 0;
+    if (i < T) {
+      double d = trunc(dur[start + i]);
+      if (!(d > 0.0)) d = 0.0;                 // also maps NaN to 0
+      if (d > 1.0e6) d = 1.0e6;                // guard: one phoneme never spans > 1e6 frames
+      n = (int32_t)d;
+    }
+    int32_t v = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = lane < (int)(blockDim.x / 32) ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int32_t before = carry_s + (warp > 0 ? warp_tot[warp - 1] : 0);
+    if (i < T) cum[start + i] = before + v;
+    __syncthreads();
+    if (tid == 0) carry_s += warp_tot[blockDim.x / 32 - 1];
+    __syncthreads();
+  }
+  if (tid == 0) frames[b] = carry_s;
+}
+int lr_count(const VsRows& rows, const double* dur, int32_t* cum, int32_t* frames, cudaStream_t st) {
+  VS_CUDA_CHECK(cudaMemsetAsync(cum, 0, sizeof(int32_t) * rows.n_rows, st));
+  lr_count_kernel<<<rows.n_utt, 256, 0, st>>>(rows, dur, cum, frames);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// gather: frame t of utterance b copies phoneme idx = #{i : cum[i] <= t} (== searchsorted(cum, t, right=True)),
+// which is the index the reference's expand()+cat() places at frame t.  One warp per frame row.
+__global__ void lr_gather_kernel(VsRows rp, VsRows rf, const float* __restrict__ xp, const int32_t* __restrict__ cum,
+                                 float* __restrict__ xf, int32_t* __restrict__ lr_index) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (r >= rf.n_rows) return;
+  const int b = rf.row_utt[r];
+  float* dst = xf + (size_t)r * kHidden;
+  if (b < 0) {
+    for (int c = lane; c < kHidden; c += 32) dst[c] = 0.f;
+    if (lane == 0) lr_index[r] = -1;
+    return;
+  }
+  const int t = r - rf.utt_start[b];
+  const int32_t* cb = cum + rp.utt_start[b];
+  int lo = 0, hi = rp.utt_len[b];          // first i with cum[i] > t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cb[mid] <= t) lo = mid + 1; else hi = mid;
+  }
+  const float* src = xp + (size_t)(rp.utt_start[b] + lo) * kHidden;
+  for (int c = lane; c < kHidden; c += 32) dst[c] = src[c];
+  if (lane == 0) lr_index[r] = lo;
+}
+int lr_gather(const VsRows& rp, const VsRows& rf, const float* xp, const int32_t* cum, float* xf, int32_t* lr_index,
+              cudaStream_t st) {
+  lr_gather_kernel<<<(rf.n_rows + 7) / 8, 256, 0, st>>>(rp, rf, xp, cum, xf, lr_index);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- prior sample: z_p = m_p + eps * exp(logs_p) * noise_scale (models.py:718); stats = [m_p | logs_p] ----
+__global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, float ns,
+                                    const int32_t* __restrict__ row_utt, float* __restrict__ m_p,
+                                    float* __restrict__ logs_p, float* __restrict__ z_p, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * kHidden) return;
+  const int r = i / kHidden, c = i % kHidden;
+  if (row_utt[r] < 0) { m_p[i] = 0.f; logs_p[i] = 0.f; z_p[i] = 0.f; return; }
+  const float m = stats[(size_t)r * 2 * kHidden + c], ls = stats[(size_t)r * 2 * kHidden + kHidden + c];
+  m_p[i] = m;
+  logs_p[i] = ls;
+  z_p[i] = m + noise[i] * expf(ls) * ns;
+}
+int prior_sample(const float* stats, const float* noise, float ns, const VsRows& rows, float* m_p, float* logs_p,
+                 float* z_p, cudaStream_t st) {
+  prior_sample_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(stats, noise, ns, rows.row_utt, m_p, logs_p,
+                                                                          z_p, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- WN pieces (modules.py:148-176) -----------------------------------------------------------------
+// acts = tanh(a[:192] + g[:192]) * sigmoid(a[192:] + g[192:])   (commons.py:100-107); g = cond row of the speaker
+__global__ void wn_gate_kernel(const float* __restrict__ a, const float* __restrict__ cond, int cond_ld, int cond_off,
+                               const int32_t* __restrict__ row_utt, const int32_t* __restrict__ sid,
+                               float* __restrict__ acts, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * kHidden) return;
+  const int r = i / kHidden, c = i % kHidden;
+  const int u = row_utt[r];
+  if (u < 0) { acts[i] = 0.f; return; }
+  const float* g = cond + (size_t)sid[u] * cond_ld + cond_off;
+  const float t = a[(size_t)r * 2 * kHidden + c] + g[c];
+  const float s = a[(size_t)r * 2 * kHidden + kHidden + c] + g[kHidden + c];
+  acts[i] = tanhf(t) * (1.f / (1.f + expf(-s)));
+}
+int wn_gate(const float* a, const float* cond, int cond_ld, int cond_off, const VsRows& rows, float* acts,
+            cudaStream_t st) {
+  wn_gate_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(a, cond, cond_ld, cond_off, rows.row_utt, rows.sid,
+                                                                     acts, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+// h += rs[:, :192]; skip (+)= rs[:, 192:]   (or skip += rs when last)
+__global__ void wn_update_kernel(const float* __restrict__ rs, int rs_ld, int last, int first,
+                                 const int32_t* __restrict__ row_utt, float* __restrict__ h, float* __restrict__ skip,
+                                 int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * kHidden) return;
+  const int r = i / kHidden, c = i % kHidden;
+  if (row_utt[r] < 0) { if (first) skip[i] = 0.f; return; }
+  const float* row = rs + (size_t)r * rs_ld;
+  float sk;
+  if (last) sk = row[c];
+  else { h[i] += row[c]; sk = row[kHidden + c]; }
+  skip[i] = first ? sk : skip[i] + sk;
+}
+int wn_update(const float* rs, int rs_ld, int last, int first, const VsRows& rows, float* h, float* skip,
+              cudaStream_t st) {
+  wn_update_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(rs, rs_ld, last, first, rows.row_utt, h, skip,
+                                                                       rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+// coupling reverse with mean_only (modules.py:340-343): x1 = (x1 - m) on valid rows
+__global__ void coupling_sub_kernel(float* __restrict__ z, int z_off, const float* __restrict__ m,
+                                    const int32_t* __restrict__ row_utt, int R) {
+  const int half = kHidden / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * half) return;
+  const int r = i / half, c = i % half;
+  if (row_utt[r] < 0) return;
+  z[(size_t)r * kHidden + z_off + c] -= m[i];
+}
+int coupling_sub(float* z, int z_off, const float* m, const VsRows& rows, cudaStream_t st) {
+  coupling_sub_kernel<<<(rows.n_rows * (kHidden / 2) + 255) / 256, 256, 0, st>>>(z, z_off, m, rows.row_utt, rows.n_rows);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- copy with validity mask limited to the first max_len frames of each utterance (models.py:720) ----
+__global__ void mask_frames_kernel(VsRows rows, int max_len, int32_t* __restrict__ row_utt_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows.n_rows) return;
+  int u = rows.row_utt[r];
+  if (u >= 0 && max_len >= 0 && r - rows.utt_start[u] >= max_len) u = -1;
+  row_utt_out[r] = u;
+}
+int mask_frames(const VsRows& rows, int max_len, int32_t* row_utt_out, cudaStream_t st) {
+  mask_frames_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(rows, max_len, row_utt_out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+__global__ void masked_copy_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
+                                   float* __restrict__ out, int R, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * C) return;
+  out[i] = row_utt[i / C] >= 0 ? x[i] : 0.f;
+}
+int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C, cudaStream_t st) {
+  masked_copy_kernel<<<(R * C + 255) / 256, 256, 0, st>>>(x, row_utt, out, R, C);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ---- ragged rows -> [n_utt][C][t_max] (the reference's output layout), tiled transpose ----------------
+__global__ void unpack_rows_kernel(VsRows rows, const float* __restrict__ x, int C, int mul, int t_max,
+                                   float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int len = rows.utt_len[b] * mul;
+  const size_t start = (size_t)rows.utt_start[b] * mul;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < len && t < t_max && c < C) ? x[(start + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < t_max) out[((size_t)b * C + c) * t_max + t] = tile[threadIdx.x][i];
+  }
+}
+int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st) {
+  VS_REQUIRE(t_max > 0 && C > 0, "unpack_rows: empty output");
+  dim3 grid((t_max + 31) / 32, (C + 31) / 32, rows.n_utt);
+  unpack_rows_kernel<<<grid, dim3(32, 8), 0, st>>>(rows, x, C, mul, t_max, out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+}  // namespace vs

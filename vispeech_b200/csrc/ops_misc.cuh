@@ -1,0 +1,29 @@
+// Declarations of the small memory-bound kernels in ops_misc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace vs {
+int embed_rows(const int32_t* ids, const float* emb, float* x, int R, int n_vocab, cudaStream_t st);
+int add_speaker_rows(const float* x, const float* tab, const VsRows& rows, float* out, int C, cudaStream_t st);
+int duration_rows(const float* logw, const double* ctrl, int mode, float scale, const VsRows& rows, double* dur,
+                  cudaStream_t st);
+int pitch_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* lf0, float* f0,
+               cudaStream_t st);
+int energy_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* norm,
+                float* energy, cudaStream_t st);
+int prenet_add(float* x, const float* v, const float* w, const float* b, const VsRows& rows, cudaStream_t st);
+int lr_count(const VsRows& rows, const double* dur, int32_t* cum, int32_t* frames, cudaStream_t st);
+int lr_gather(const VsRows& rp, const VsRows& rf, const float* xp, const int32_t* cum, float* xf, int32_t* lr_index,
+              cudaStream_t st);
+int prior_sample(const float* stats, const float* noise, float ns, const VsRows& rows, float* m_p, float* logs_p,
+                 float* z_p, cudaStream_t st);
+int wn_gate(const float* a, const float* cond, int cond_ld, int cond_off, const VsRows& rows, float* acts,
+            cudaStream_t st);
+int wn_update(const float* rs, int rs_ld, int last, int first, const VsRows& rows, float* h, float* skip,
+              cudaStream_t st);
+int coupling_sub(float* z, int z_off, const float* m, const VsRows& rows, cudaStream_t st);
+int mask_frames(const VsRows& rows, int max_len, int32_t* row_utt_out, cudaStream_t st);
+int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C, cudaStream_t st);
+int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st);
+const char* last_error();
+}  // namespace vs

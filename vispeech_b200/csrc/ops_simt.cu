@@ -1,0 +1,381 @@
+// fp32 CUDA-core kernels over ragged rows: generic conv1d (implicit GEMM), channel LayerNorm,
+// windowed relative-position attention (streaming softmax), row dot products.
+// These serve the HBM/latency-bound part of the path (text encoder, predictors, frame prior, flow);
+// the decoder's dense contractions run on tcgen05 (umma_conv.cu).
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace vs {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// conv1d_f32: out[orow(r)][co] = f( sum_{j<k} sum_ci W[j][ci][co] * lrelu(in[r + (j-pad_l)*dil][ci]) )
+// Tile 64 rows x 64 couts per CTA, K-step 16 input channels per tap, 256 threads x (4x4) outputs.
+// Rows outside [0,R) read as zero; gap rows of the input are zero by the ragged-rows invariant.
+// ------------------------------------------------------------------------------------------------
+constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
+
+__global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a) {
+  __shared__ __align__(16) float As[CV_BK][CV_BM + 4];
+  __shared__ __align__(16) float Bs[CV_BK][CV_BN];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * CV_BM, c0 = blockIdx.y * CV_BN;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int am = tid / 4, akq = tid % 4;          // A loader: row am, channels 4*akq..+3
+  const int bk = tid / 16, bn4 = tid % 16;        // B loader: k row bk, couts 4*bn4..+3
+  const bool vec_b = (a.Cout % 4 == 0);
+
+  for (int j = 0; j < a.k; ++j) {
+    const int shift = (j - a.pad_l) * a.dil;
+    const int ar = r0 + am + shift;
+    const bool a_ok = (ar >= 0 && ar < a.R);
+    const float* arow = a.in + (size_t)(a_ok ? ar : 0) * a.in_ld;
+    const float* wj = a.w + (size_t)j * a.Cin * a.Cout;
+    for (int ci0 = 0; ci0 < a.Cin; ci0 += CV_BK) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_ok) av = *reinterpret_cast<const float4*>(arow + ci0 + 4 * akq);
+      if (a.in_slope != 1.f) {
+        av.x = lrelu(av.x, a.in_slope); av.y = lrelu(av.y, a.in_slope);
+        av.z = lrelu(av.z, a.in_slope); av.w = lrelu(av.w, a.in_slope);
+      }
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const float* wrow = wj + (size_t)(ci0 + bk) * a.Cout + c0 + 4 * bn4;
+        const int cc = c0 + 4 * bn4;
+        if (vec_b && cc + 3 < a.Cout) bv = *reinterpret_cast<const float4*>(wrow);
+        else {
+          if (cc + 0 < a.Cout) bv.x = wrow[0];
+          if (cc + 1 < a.Cout) bv.y = wrow[1];
+          if (cc + 2 < a.Cout) bv.z = wrow[2];
+          if (cc + 3 < a.Cout) bv.w = wrow[3];
+        }
+      }
+      __syncthreads();
+      As[4 * akq + 0][am] = av.x; As[4 * akq + 1][am] = av.y;
+      As[4 * akq + 2][am] = av.z; As[4 * akq + 3][am] = av.w;
+      *reinterpret_cast<float4*>(&Bs[bk][4 * bn4]) = bv;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < CV_BK; ++kk) {
+        const float4 x = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
+        const float4 y = *reinterpret_cast<const float4*>(&Bs[kk][4 * tx]);
+        const float xa[4] = {x.x, x.y, x.z, x.w}, ya[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(xa[i], ya[jj], acc[i][jj]);
+      }
+    }
+  }
+
+  const int R_out = a.R_out ? a.R_out : a.R;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 4 * ty + i;
+    if (r >= a.R) continue;
+    const int orow = r * a.out_row_mul + a.out_row_off;
+    if (orow >= R_out) continue;
+    int utt = 0;
+    if (a.row_utt) utt = a.row_utt[orow / a.row_div];
+    const bool valid = utt >= 0;
+    const float* ub = nullptr;
+    if (a.ubias && valid) ub = a.ubias + (size_t)(a.ubias_idx ? a.ubias_idx[utt] : utt) * a.ubias_ld;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int c = c0 + 4 * tx + jj;
+      if (c >= a.Cout) continue;
+      float* o = a.out + (size_t)orow * a.out_ld + c;
+      if (!valid) { if (!a.accumulate) *o = 0.f; continue; }
+      float y = acc[i][jj];
+      if (a.bias) y += a.bias[c];
+      if (ub) y += ub[c];
+      if (a.act == 1) y = fmaxf(y, 0.f);
+      else if (a.act == 2) y = tanhf(y);
+      if (a.res) y += a.res[(size_t)orow * a.res_ld + c];
+      y *= a.out_scale;
+      *o = a.accumulate ? (*o + y) : y;
+    }
+  }
+}
+
+int conv1d_f32(const ConvF32& a, cudaStream_t st) {
+  VS_REQUIRE(a.Cin % CV_BK == 0, "conv1d_f32: Cin=%d must be a multiple of %d", a.Cin, CV_BK);
+  VS_REQUIRE(a.in_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0, "conv1d_f32: input not 16B aligned");
+  VS_REQUIRE(a.R > 0 && a.Cout > 0, "conv1d_f32: empty problem");
+  dim3 grid((a.R + CV_BM - 1) / CV_BM, (a.Cout + CV_BN - 1) / CV_BN);
+  conv1d_f32_kernel<<<grid, 256, 0, st>>>(a);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over channels of (a + b), one warp per row; invalid rows are written as zero.
+// modules.py:29-32 (gamma/beta) and nn.LayerNorm(768) of frame_prior_network.py:83,95 share this.
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_rows_kernel(const float* a, const float* b,   // a/b may alias out (in-place residual LN)
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float* out, int R, int C, const int32_t* __restrict__ row_utt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= R) return;
+  const size_t base = (size_t)warp * C;
+  const bool valid = !row_utt || row_utt[warp] >= 0;
+  if (!valid) {
+    for (int c = lane; c < C; c += 32) out[base + c] = 0.f;
+    return;
+  }
+  float v[24];  // C <= 768; fully unrolled so v stays in registers
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = 0.f;
+    if (c < C) {
+      float x = a[base + c];
+      if (b) x += b[base + c];
+      v[i] = x;
+      s += x;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i)
+    if (lane + 32 * i < C) { const float d = v[i] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) out[base + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
+                   const int32_t* row_utt, cudaStream_t st) {
+  VS_REQUIRE(C <= 768 && C % 32 == 0, "layernorm: C=%d unsupported", C);
+  const int warps_per_block = 8;
+  layernorm_rows_kernel<<<(R + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+      a, b, gamma, beta, out, R, C, row_utt);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Windowed relative-position self-attention (attentions.py:148-179), banded form, streaming softmax.
+// One CTA = 64 queries of one (utterance, head).  qkv rows are [q(192) | k(192) | v(192)], head h owns
+// channels [96h, 96h+96) of each.  scores = (q/sqrt(96)).k + (q/sqrt(96)).Ek[j-i+4] for |j-i|<=4;
+// out = softmax(scores).(v) + sum_d p[i,i+d] Ev[d+4].  Keys are the utterance's own rows only, so the
+// reference's -1e4 pad fill (attentions.py:166) never triggers (batch-1 semantics).
+// ------------------------------------------------------------------------------------------------
+constexpr int AT_BQ = 64, AT_BK = 64, AT_D = kHeadDim, AT_LD = AT_D + 1;
+
+__global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const float* __restrict__ qkv,
+                                                            const float* __restrict__ ek,
+                                                            const float* __restrict__ ev, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                          // [64][97]
+  float* Ks = Qs + AT_BQ * AT_LD;          // [64][97]
+  float* Vs = Ks + AT_BK * AT_LD;          // [64][97]
+  float* Ss = Vs + AT_BK * AT_LD;          // [64][65]
+  float* Ev = Ss + AT_BQ * (AT_BK + 1);    // [9][96]
+  float* relq = Ev + kRel * AT_D;          // [64][9]
+  float* row_m = relq + AT_BQ * kRel;      // [64]
+  float* row_l = row_m + AT_BQ;            // [64]
+  float* row_alpha = row_l + AT_BQ;        // [64]
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int T = rows.utt_len[b], start = rows.utt_start[b];
+  const int q0 = blockIdx.x * AT_BQ;
+  if (q0 >= T) return;
+  const int tid = threadIdx.x;
+  const int ld = 3 * kHidden;
+  const float scale = rsqrtf((float)AT_D);
+
+  for (int i = tid; i < AT_BQ * AT_D; i += 256) {
+    const int r = i / AT_D, d = i % AT_D;
+    Qs[r * AT_LD + d] = (q0 + r < T) ? qkv[(size_t)(start + q0 + r) * ld + h * AT_D + d] * scale : 0.f;
+  }
+  for (int i = tid; i < kRel * AT_D; i += 256) Ev[i] = ev[i];
+  if (tid < AT_BQ) { row_m[tid] = -INFINITY; row_l[tid] = 0.f; }
+  __syncthreads();
+  for (int i = tid; i < AT_BQ * kRel; i += 256) {
+    const int r = i / kRel, w = i % kRel;
+    float s = 0.f;
+    for (int d = 0; d < AT_D; ++d) s = fmaf(Qs[r * AT_LD + d], ek[w * AT_D + d], s);
+    relq[i] = s;
+  }
+
+  const int ty = tid / 16, tx = tid % 16;   // S tile: rows 4ty..+3, cols tx+16c ; O tile: rows 4ty..+3, dims tx+16c (c<6)
+  float o_acc[4][6];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o_acc[i][c] = 0.f;
+
+  for (int k0 = 0; k0 < T; k0 += AT_BK) {
+    __syncthreads();
+    for (int i = tid; i < AT_BK * AT_D; i += 256) {
+      const int r = i / AT_D, d = i % AT_D;
+      const bool ok = k0 + r < T;
+      const size_t g = (size_t)(start + k0 + r) * ld + h * AT_D + d;
+      Ks[r * AT_LD + d] = ok ? qkv[g + kHidden] : 0.f;
+      Vs[r * AT_LD + d] = ok ? qkv[g + 2 * kHidden] : 0.f;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[i][c] = 0.f;
+    for (int d = 0; d < AT_D; ++d) {
+      float qa[4], kb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = Qs[(4 * ty + i) * AT_LD + d];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kb[c] = Ks[(tx + 16 * c) * AT_LD + d];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[i][c] = fmaf(qa[i], kb[c], s[i][c]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int qi = q0 + 4 * ty + i, kj = k0 + tx + 16 * c;
+        float v = s[i][c];
+        const int dd = kj - qi;
+        if (dd >= -kWindow && dd <= kWindow) v += relq[(4 * ty + i) * kRel + dd + kWindow];
+        if (kj >= T) v = -INFINITY;
+        Ss[(4 * ty + i) * (AT_BK + 1) + tx + 16 * c] = v;
+      }
+    __syncthreads();
+    // row-wise streaming softmax: 4 threads per row
+    {
+      const int r = tid / 4, part = tid % 4;
+      float mx = -INFINITY;
+      for (int c = part; c < AT_BK; c += 4) mx = fmaxf(mx, Ss[r * (AT_BK + 1) + c]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_old = row_m[r];
+      const float m_new = fmaxf(m_old, mx);
+      float sum = 0.f;
+      for (int c = part; c < AT_BK; c += 4) {
+        const float p = __expf(Ss[r * (AT_BK + 1) + c] - m_new);
+        Ss[r * (AT_BK + 1) + c] = p;
+        sum += p;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      __syncwarp();
+      if (part == 0) {
+        const float alpha = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+        row_alpha[r] = alpha;
+        row_l[r] = row_l[r] * alpha + sum;
+        row_m[r] = m_new;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float al = row_alpha[4 * ty + i];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o_acc[i][c] *= al;
+    }
+    for (int j = 0; j < AT_BK; ++j) {
+      float p[4], vv[6];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = Ss[(4 * ty + i) * (AT_BK + 1) + j];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vv[c] = Vs[j * AT_LD + tx + 16 * c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p[i], vv[c], o_acc[i][c]);
+    }
+    // relative values on the band (attentions.py:174-177)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + 4 * ty + i;
+      for (int dd = -kWindow; dd <= kWindow; ++dd) {
+        const int j = qi + dd - k0;
+        if (j < 0 || j >= AT_BK || qi + dd >= T) continue;
+        const float p = Ss[(4 * ty + i) * (AT_BK + 1) + j];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p, Ev[(dd + kWindow) * AT_D + tx + 16 * c], o_acc[i][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + 4 * ty + i;
+    if (qi >= T) continue;
+    const float inv = 1.f / row_l[4 * ty + i];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[(size_t)(start + qi) * kHidden + h * AT_D + tx + 16 * c] = o_acc[i][c] * inv;
+  }
+}
+
+static size_t attention_smem_bytes() {
+  return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * (AT_BK + 1) + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
+}
+
+int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = attention_smem_bytes();
+  if (!configured) {
+    VS_CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  // gap rows of `out` must be zero: the caller feeds out into a k=1 conv whose epilogue masks, but keep it clean
+  VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));
+  // grid.x covers the longest utterance; CTAs beyond an utterance's length exit immediately
+  VS_REQUIRE(rows.max_len > 0 && rows.max_len <= rows.n_rows, "rel_attention: bad max_len %d", rows.max_len);
+  dim3 grid((rows.max_len + AT_BQ - 1) / AT_BQ, kHeads, rows.n_utt);
+  rel_attention_kernel<<<grid, 256, smem, st>>>(rows, qkv, ek, ev, out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[r] = bias + w . x[r]   (the 1-channel projections: duration proj, proj_f0, energy linear)
+// ------------------------------------------------------------------------------------------------
+__global__ void row_dot_kernel(const float* __restrict__ x, int ld, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ out, int R, int C,
+                               const int32_t* __restrict__ row_utt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= R) return;
+  float s = 0.f;
+  const bool valid = !row_utt || row_utt[warp] >= 0;
+  if (valid)
+    for (int c = lane; c < C; c += 32) s = fmaf(x[(size_t)warp * ld + c], w[c], s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[warp] = valid ? s + bias[0] : 0.f;
+}
+
+int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,
+            const int32_t* row_utt, cudaStream_t st) {
+  row_dot_kernel<<<(R + 7) / 8, 256, 0, st>>>(x, ld, w, bias, out, R, C, row_utt);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
+}  // namespace vs

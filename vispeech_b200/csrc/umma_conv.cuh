@@ -1,0 +1,33 @@
+// tcgen05 / TMEM implicit-GEMM conv1d over planar bf16 ragged rows (sm_100a).  See umma_conv.cu.
+#pragma once
+#include "common.cuh"
+
+namespace vs {
+
+// Activations: planar bf16 [C/8][R][8]  (plane p holds channels 8p..8p+7 of every row, 16 B per row).
+// Weights:     bf16 [NB][taps][Cin/KC][KC/8][Nblk][8], KC = min(Cin, 64), Nblk = min(N, 256), N = NB*Nblk:
+//              element (nb, t, kc, p, n, e) = W[t][kc*KC + 8p + e][nb*Nblk + n].  One (nb,t,kc) slab is one
+//              cp.async.bulk of KC*Nblk*2 bytes and lands in smem already in the UMMA K-major no-swizzle layout.
+struct UmmaConv {
+  const __nv_bfloat16* in = nullptr;   // planar [Cin/8][R][8]
+  const __nv_bfloat16* w = nullptr;    // packed as above
+  const float* bias = nullptr;         // [N % upsample-aware: bias[gn % Cout]] or null
+  const float* ubias = nullptr;        // optional per-speaker table [n_spk][N]
+  const int32_t* ubias_idx = nullptr;  // [n_utt] -> row of ubias
+  const __nv_bfloat16* res = nullptr;  // optional residual, planar like out (same rows/channels)
+  const __nv_bfloat16* res2 = nullptr; // optional second residual (MRF running sum)
+  __nv_bfloat16* out_raw = nullptr;    // optional: y
+  __nv_bfloat16* out_act = nullptr;    // optional: lrelu(y * act_scale, act_slope)
+  const int32_t* row_utt = nullptr;    // validity of OUTPUT row: row_utt[orow / row_div] >= 0 (also gives utt for ubias)
+  int row_div = 1;
+  int R = 0;                           // input rows
+  int Cin = 0, N = 0;                  // N = total GEMM columns (= Cout * up for transposed conv)
+  int taps = 1, dil = 1, pad_l = 0;
+  int up = 1;                          // ConvTranspose1d polyphase: column gn -> phase gn / Cout, channel gn % Cout;
+                                       // output row = up*r + phase; output planes have R*up rows
+  float act_slope = 1.f, act_scale = 1.f;
+};
+
+int umma_conv1d(const UmmaConv& a, cudaStream_t st);
+
+}  // namespace vs

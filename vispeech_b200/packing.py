@@ -1,0 +1,174 @@
+"""Reference state dict -> packed device tensors for libvispeech_b200 (load-time work, not the hot path).
+
+Replaces what the reference gets implicitly from `utils.load_checkpoint` (utils.py:21-51) plus the
+weight-norm forward pre-hooks (checkpoints hold un-folded weight_g/weight_v):
+  * weight norm folded: w = g * v / ||v|| over every dim but 0 (ConvTranspose1d: per INPUT channel);
+  * conv weights [Cout,Cin,k] -> [k][Cin][Cout] fp32 (coalesced over Cout);
+  * conv_q|k|v fused into one [192][576] matrix;
+  * speaker conditioning (emb_g -> 1x1 conv, models.py:674-675 + every `.cond`/`cond_layer`) evaluated once
+    for all 200 speakers into lookup tables;
+  * the Flip() layers of the flow (modules.py:270-277) folded into channel-permuted pre/post weights of the
+    odd coupling layers (csrc/model.cu vs_flow_reverse);
+  * ConvTranspose1d rewritten as polyphase taps;
+  * decoder weights additionally in the bf16 slab layout of csrc/umma_conv.cuh.
+Names on the right-hand side are the keys `vs_model_set_tensor` expects (csrc/model.cu, csrc/decoder*.cu).
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+UP_RATES = (8, 8, 4, 2)
+UP_KERNELS = (16, 16, 4, 4)
+RES_KERNELS = (3, 7, 11)
+N_DIL = 3
+
+
+def fold(sd, prefix: str) -> torch.Tensor:
+    v, g = sd[prefix + ".weight_v"].float(), sd[prefix + ".weight_g"].float()
+    n = v.reshape(v.shape[0], -1).norm(dim=1).reshape(g.shape)
+    return v * (g / n)
+
+
+def tcn(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, k] -> [k][Cin][Cout]."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+def ups_phase_range(i: int, ph: int) -> Tuple[int, int]:
+    s, K, p = UP_RATES[i], UP_KERNELS[i], (UP_KERNELS[i] - UP_RATES[i]) // 2
+    dmax = (ph + p) // s
+    return dmax - K // s + 1, dmax
+
+
+def ups_union_taps(i: int) -> Tuple[int, int]:
+    """(taps, pad_l) of the union over phases - must match csrc/decoder_umma.cu ups_taps()."""
+    lo = min(ups_phase_range(i, ph)[0] for ph in range(UP_RATES[i]))
+    hi = max(ups_phase_range(i, ph)[1] for ph in range(UP_RATES[i]))
+    return hi - lo + 1, -lo
+
+
+def pack_umma(w: torch.Tensor) -> torch.Tensor:
+    """[taps][Cin][N] fp32 -> bf16 [NB][taps][Cin/KC][KC/8][Nblk][8] (csrc/umma_conv.cuh)."""
+    taps, cin, n = w.shape
+    kc = min(cin, 64)
+    nblk = min(n, 256)
+    assert cin % kc == 0 and n % nblk == 0 and kc % 16 == 0
+    x = w.reshape(taps, cin // kc, kc // 8, 8, n // nblk, nblk)
+    x = x.permute(4, 0, 1, 2, 5, 3).contiguous()
+    return x.to(torch.bfloat16).reshape(-1)
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_flows=4, flow_layers=4) -> Dict[str, torch.Tensor]:
+    """Returns {packed name: CPU tensor (fp32 or bf16, contiguous)}."""
+    sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+    out: Dict[str, torch.Tensor] = {}
+    emb_g = sd["emb_g.weight"]                                     # [200, 256]
+
+    def cond_table(w, b):                                          # Conv1d(gin, C, 1) applied to every speaker
+        return (emb_g @ w[:, :, 0].t() + b).contiguous()
+
+    out["emb"] = sd["enc_p.symbol_emb.weight"].contiguous()
+
+    def encoder(prefix, layers):
+        for i in range(layers):
+            a = "%s.attn_layers.%d" % (prefix, i)
+            q = "%s.%d." % (prefix, i)
+            out[q + "wqkv"] = torch.cat([tcn(sd["%s.conv_%s.weight" % (a, n)])[0] for n in "qkv"], dim=1).contiguous()
+            out[q + "bqkv"] = torch.cat([sd["%s.conv_%s.bias" % (a, n)] for n in "qkv"]).contiguous()
+            out[q + "wo"] = tcn(sd[a + ".conv_o.weight"])[0].contiguous()
+            out[q + "bo"] = sd[a + ".conv_o.bias"]
+            out[q + "ek"] = sd[a + ".emb_rel_k"][0].contiguous()
+            out[q + "ev"] = sd[a + ".emb_rel_v"][0].contiguous()
+            out[q + "g1"] = sd["%s.norm_layers_1.%d.gamma" % (prefix, i)]
+            out[q + "b1"] = sd["%s.norm_layers_1.%d.beta" % (prefix, i)]
+            out[q + "g2"] = sd["%s.norm_layers_2.%d.gamma" % (prefix, i)]
+            out[q + "b2"] = sd["%s.norm_layers_2.%d.beta" % (prefix, i)]
+            out[q + "w1"] = tcn(sd["%s.ffn_layers.%d.conv_1.weight" % (prefix, i)])
+            out[q + "bf1"] = sd["%s.ffn_layers.%d.conv_1.bias" % (prefix, i)]
+            out[q + "w2"] = tcn(sd["%s.ffn_layers.%d.conv_2.weight" % (prefix, i)])
+            out[q + "bf2"] = sd["%s.ffn_layers.%d.conv_2.bias" % (prefix, i)]
+
+    encoder("enc_p.encoder", n_layers)
+    encoder("pitch_predictor.pitch_net", pitch_layers)
+    encoder("frame_prior_net.fft_block", n_layers)
+
+    p = "duration_predictor"
+    out["dp.cond_tab"] = cond_table(sd[p + ".cond.weight"], sd[p + ".cond.bias"])
+    out["dp.w1"], out["dp.b1"] = tcn(sd[p + ".conv_1.weight"]), sd[p + ".conv_1.bias"]
+    out["dp.g1"], out["dp.be1"] = sd[p + ".norm_1.gamma"], sd[p + ".norm_1.beta"]
+    out["dp.w2"], out["dp.b2"] = tcn(sd[p + ".conv_2.weight"]), sd[p + ".conv_2.bias"]
+    out["dp.g2"], out["dp.be2"] = sd[p + ".norm_2.gamma"], sd[p + ".norm_2.beta"]
+    out["dp.wp"], out["dp.bp"] = sd[p + ".proj.weight"].reshape(-1).contiguous(), sd[p + ".proj.bias"]
+
+    p = "pitch_predictor"
+    out["pp.cond_tab"] = cond_table(sd[p + ".cond.weight"], sd[p + ".cond.bias"])
+    out["pp.wf0"], out["pp.bf0"] = sd[p + ".proj_f0.weight"].reshape(-1).contiguous(), sd[p + ".proj_f0.bias"]
+
+    p = "energy_predictor"
+    c = p + ".predictor.conv_layer"
+    out["ep.cond_tab"] = cond_table(sd[p + ".cond.weight"], sd[p + ".cond.bias"])
+    out["ep.w1"], out["ep.b1"] = tcn(sd[c + ".conv_1.conv.weight"]), sd[c + ".conv_1.conv.bias"]
+    out["ep.g1"], out["ep.be1"] = sd[c + ".layer_norm_1.weight"], sd[c + ".layer_norm_1.bias"]
+    out["ep.w2"], out["ep.b2"] = tcn(sd[c + ".conv_2.conv.weight"]), sd[c + ".conv_2.conv.bias"]
+    out["ep.g2"], out["ep.be2"] = sd[c + ".layer_norm_2.weight"], sd[c + ".layer_norm_2.bias"]
+    out["ep.wl"] = sd[p + ".predictor.linear_layer.weight"].reshape(-1).contiguous()
+    out["ep.bl"] = sd[p + ".predictor.linear_layer.bias"]
+
+    for n in ("pitch_prenet", "energy_prenet"):
+        out[n + ".w"] = sd[n + ".weight"].reshape(-1, 3).contiguous()         # [192][3]
+        out[n + ".b"] = sd[n + ".bias"]
+    out["proj.w"], out["proj.b"] = tcn(sd["project.proj.weight"])[0].contiguous(), sd["project.proj.bias"]
+
+    for f in range(n_flows):
+        src = "flow.flows.%d" % (2 * f)
+        dst = "flow.%d." % f
+        flipped = (f % 2) == 1       # reversed(flows) starts with a Flip: layers 3 and 1 see a flipped tensor
+        pre = tcn(sd[src + ".pre.weight"])[0]            # [96 ci][192 co]
+        post = tcn(sd[src + ".post.weight"])[0]          # [192 ci][96 co]
+        post_b = sd[src + ".post.bias"]
+        if flipped:
+            pre = torch.flip(pre, [0])                   # x0[c] = phys[191-c]
+            post = torch.flip(post, [1])                 # m_phys[p] = m[95-p]
+            post_b = torch.flip(post_b, [0])
+        out[dst + "pre.w"], out[dst + "pre.b"] = pre.contiguous(), sd[src + ".pre.bias"]
+        out[dst + "post.w"], out[dst + "post.b"] = post.contiguous(), post_b.contiguous()
+        out[dst + "cond_tab"] = cond_table(fold(sd, src + ".enc.cond_layer"), sd[src + ".enc.cond_layer.bias"])
+        for l in range(flow_layers):
+            out["%s%d.in.w" % (dst, l)] = tcn(fold(sd, "%s.enc.in_layers.%d" % (src, l)))
+            out["%s%d.in.b" % (dst, l)] = sd["%s.enc.in_layers.%d.bias" % (src, l)]
+            out["%s%d.rs.w" % (dst, l)] = tcn(fold(sd, "%s.enc.res_skip_layers.%d" % (src, l)))[0].contiguous()
+            out["%s%d.rs.b" % (dst, l)] = sd["%s.enc.res_skip_layers.%d.bias" % (src, l)]
+
+    # ---- decoder
+    out["dec.pre.w"], out["dec.pre.b"] = tcn(sd["dec.conv_pre.weight"]), sd["dec.conv_pre.bias"]
+    out["dec16.pre.w"] = pack_umma(out["dec.pre.w"])
+    out["dec.cond_tab"] = cond_table(sd["dec.cond.weight"], sd["dec.cond.bias"])
+    out["dec.post.w"] = tcn(sd["dec.conv_post.weight"]).reshape(-1).contiguous()        # [7][32]
+    for i, (s, K) in enumerate(zip(UP_RATES, UP_KERNELS)):
+        wt = fold(sd, "dec.ups.%d" % i)                   # [Cin, Cout, K]
+        cin, cout, _ = wt.shape
+        pad = (K - s) // 2
+        per = torch.zeros(s, K // s, cin, cout)
+        taps, pad_l = ups_union_taps(i)
+        uni = torch.zeros(taps, cin, s * cout)
+        for ph in range(s):
+            lo, hi = ups_phase_range(i, ph)
+            for t, d in enumerate(range(lo, hi + 1)):
+                k = ph + pad - s * d
+                assert 0 <= k < K
+                per[ph, t] = wt[:, :, k]
+                uni[d + pad_l, :, ph * cout:(ph + 1) * cout] = wt[:, :, k]
+        out["dec.ups.%d.w" % i] = per.contiguous()
+        out["dec.ups.%d.b" % i] = sd["dec.ups.%d.bias" % i]
+        out["dec16.ups.%d.w" % i] = pack_umma(uni)
+        for j in range(len(RES_KERNELS)):
+            n = i * len(RES_KERNELS) + j
+            for m in range(N_DIL):
+                for cname, key in (("c1", "convs1"), ("c2", "convs2")):
+                    w = tcn(fold(sd, "dec.resblocks.%d.%s.%d" % (n, key, m)))
+                    out["dec.rb.%d.%s.%d.w" % (n, cname, m)] = w
+                    out["dec.rb.%d.%s.%d.b" % (n, cname, m)] = sd["dec.resblocks.%d.%s.%d.bias" % (n, key, m)]
+                    out["dec16.rb.%d.%s.%d.w" % (n, cname, m)] = pack_umma(w)
+    return {k: v.contiguous() for k, v in out.items()}

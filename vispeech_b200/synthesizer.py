@@ -1,0 +1,245 @@
+"""`SynthesizerTrn` with the reference's inference call surface, running on libvispeech_b200 (CUDA only).
+
+Mirrors reference models.py:537-561 (ctor) and models.py:672-722 (`infer`), i.e. the surface used by
+inference.py:26-44, inference_api.py:21-47, gui.py:96-100 and train.py:300-301.  Differences, all deliberate:
+  * `infer` takes two extra keyword arguments: `noise` (the eps of models.py:718, needed for parity - the
+    reference can only be seeded) and `outputs` ("all" | "audio") to skip unpacking the latents;
+  * batches are processed with per-utterance (batch-1) semantics: pad positions never influence an
+    utterance - every reference call site is batch 1, where both agree;
+  * there is no CPU path: construction fails without a CUDA device / the built library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VsConfig, check, ptr
+from .layout import FRAME_GAP, PHONEME_GAP, RaggedRows, make_rows
+from .packing import pack_state_dict
+
+Control = Union[None, float, int, torch.Tensor]
+_DTYPES = {torch.float32: _lib.VS_DTYPE_F32, torch.bfloat16: _lib.VS_DTYPE_BF16}
+
+
+class SynthesizerTrn:
+    """Inference-only drop-in for reference `models.SynthesizerTrn` (same positional/keyword ctor args)."""
+
+    def __init__(self, n_vocab, spec_channels, hop_length, sampling_rate, segment_size, inter_channels,
+                 hidden_channels, filter_channels, n_heads, n_layers, kernel_size, p_dropout, resblock,
+                 resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates, upsample_initial_channel,
+                 upsample_kernel_sizes, n_speakers=0, gin_channels=0, use_sdp=False, freeze_textencoder=False,
+                 freeze_decoder=False, device: Union[str, torch.device, None] = None, **kwargs):
+        if not torch.cuda.is_available():
+            raise _lib.VsError("vispeech_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if (inter_channels, hidden_channels, filter_channels, n_heads, kernel_size) != (192, 192, 768, 2, 3) or \
+                str(resblock) != "1" or list(resblock_kernel_sizes) != [3, 7, 11] or \
+                [list(d) for d in resblock_dilation_sizes] != [[1, 3, 5]] * 3 or \
+                list(upsample_rates) != [8, 8, 4, 2] or list(upsample_kernel_sizes) != [16, 16, 4, 4] or \
+                upsample_initial_channel != 512 or gin_channels != 256 or n_speakers <= 1 or hop_length != 512:
+            raise _lib.VsError("only the configs/config.json architecture is built (see include/vispeech_b200.h)")
+        self.n_vocab, self.n_speakers, self.hop_length, self.sampling_rate = n_vocab, n_speakers, hop_length, sampling_rate
+        self.inter_channels, self.hidden_channels = inter_channels, hidden_channels
+        self.n_layers = n_layers
+        self.decoder_precision = 0          # 0 = bf16 tcgen05 (product); 1 = fp32 cross-check (tests only)
+        self._lib = _lib.load()
+        self._cfg = VsConfig(n_vocab=n_vocab, hidden=hidden_channels, filter=filter_channels, n_heads=n_heads,
+                             n_layers=n_layers, pitch_layers=6, window=4, gin=gin_channels, n_speakers=n_speakers,
+                             flow_layers=4, n_flows=4, upsample_initial=upsample_initial_channel, hop=hop_length)
+        self._model = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.vs_model_create(ctypes.byref(self._cfg), ctypes.byref(self._model)), "vs_model_create")
+        self._weights: Dict[str, torch.Tensor] = {}
+        self._ws: Optional[torch.Tensor] = None
+        self._loaded = False
+
+    # -- nn.Module-ish surface used by the reference scripts
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device) != self.device and self._loaded:
+            raise _lib.VsError("move before loading weights")
+        self.device = torch.device(device)
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_model", None):
+                self._lib.vs_model_destroy(self._model)
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = False):
+        """Takes the reference's own state dict (un-folded weight norm; extra keys such as enc_q.* ignored)."""
+        packed = pack_state_dict(state_dict, n_layers=self.n_layers)
+        with torch.cuda.device(self.device):
+            for name, t in packed.items():
+                d = t.to(self.device)
+                self._weights[name] = d
+                check(self._lib.vs_model_set_tensor(self._model, name.encode(), d.data_ptr(), d.numel(),
+                                                    _DTYPES[d.dtype]), "vs_model_set_tensor(%s)" % name)
+            check(self._lib.vs_model_finalize(self._model), "vs_model_finalize")
+        self._loaded = True
+        return self
+
+    # -- helpers
+    def _workspace(self, rp: int, rf: int) -> torch.Tensor:
+        need = int(self._lib.vs_workspace_bytes(self._model, rp, rf))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _per_utt(c: torch.Tensor, B: int, lengths: np.ndarray, name: str) -> List[np.ndarray]:
+        c = c.detach()
+        if c.dim() == 3:                      # durations also arrive as [B,1,Tp] (models.py:420 squeezes)
+            c = c.reshape(c.shape[0], -1)
+        if c.dim() == 1:
+            c = c[None]
+        if c.shape[0] != B or c.shape[1] < int(lengths.max()):
+            raise ValueError("%s: expected [B=%d, Tp>=%d], got %s" % (name, B, int(lengths.max()), tuple(c.shape)))
+        if c.is_floating_point():
+            c = c.to(torch.float64)
+        else:
+            c = c.to(torch.int64)
+        c = c.cpu().numpy()
+        return [c[b, :lengths[b]] for b in range(B)]
+
+    @torch.no_grad()
+    def infer(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None, energy_control: Control = None,
+              pitch_control: Control = None, duration_control: Control = None, noise=None, outputs: str = "all"):
+        """Same arguments and return tuple as reference models.py:672-722:
+        (o [B,1,hop*Tf'], x_mask bool [B,1,Tf], (z, z_p, m_p, logs_p) [B,192,Tf], duration, F0 [B,Tp], energy [B,Tp]).
+        `noise`: optional eps, a [B,192,Tf] tensor or a list of [192,Tf_b] tensors.
+        """
+        if not self._loaded:
+            raise _lib.VsError("load_state_dict()/load_checkpoint() first")
+        if sid is None:
+            raise ValueError("sid is required (n_speakers > 0, models.py:674)")
+        lib, dev = self._lib, self.device
+        phon = phonemes.detach().cpu().numpy()
+        if phon.ndim == 1:
+            phon = phon[None]
+        B, Tp = phon.shape
+        lens = phonemes_lengths.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        sids = sid.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        if lens.shape[0] != B or sids.shape[0] != B:
+            raise ValueError("phonemes_lengths / sid must have one entry per utterance")
+        if lens.min() < 1 or lens.max() > Tp:
+            raise ValueError("phonemes_lengths out of range")
+        if sids.min() < 0 or sids.max() >= self.n_speakers:
+            raise ValueError("sid out of range")
+
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rp = make_rows(lens, sids, PHONEME_GAP, dev)
+            Rp = rp.n_rows
+            ids_rows = torch.from_numpy(rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1)).to(dev)
+
+            def control(c, name):
+                """-> (mode, scale, device array or None)"""
+                if isinstance(c, torch.Tensor):
+                    per = self._per_utt(c, B, lens, name)
+                    return 2, 1.0, per
+                return 0, 1.0 if c is None else float(c), None
+
+            d_mode, d_scale, d_per = control(duration_control, "duration_control")
+            p_mode, p_scale, p_per = control(pitch_control, "pitch_control")
+            e_mode, e_scale, e_per = control(energy_control, "energy_control")
+            d_ctrl = torch.from_numpy(rp.scatter(d_per, np.float64)).to(dev) if d_per is not None else None
+            p_ctrl = torch.from_numpy(rp.scatter(p_per, np.float32)).to(dev) if p_per is not None else None
+            e_ctrl = torch.from_numpy(rp.scatter(e_per, np.float32)).to(dev) if e_per is not None else None
+
+            # frame layout is only known after the durations: size the workspace for the phoneme stage first
+            ws = self._workspace(Rp, 16)
+            x = torch.empty(Rp, 192, dtype=torch.float32, device=dev)
+            check(lib.vs_text_encode(self._model, ctypes.byref(rp.struct), ptr(ids_rows), ptr(x), ptr(ws), ws.numel(),
+                                     stream), "vs_text_encode")
+            dur = torch.empty(Rp, dtype=torch.float64, device=dev)
+            f0 = torch.empty(Rp, dtype=torch.float32, device=dev)
+            energy = torch.empty(Rp, dtype=torch.float32, device=dev)
+            check(lib.vs_variance_adapter(self._model, ctypes.byref(rp.struct), ptr(x), d_mode, d_scale, ptr(d_ctrl),
+                                          p_mode, p_scale, ptr(p_ctrl), e_mode, e_scale, ptr(e_ctrl), ptr(dur), ptr(f0),
+                                          ptr(energy), ptr(ws), ws.numel(), stream), "vs_variance_adapter")
+            cum = torch.empty(Rp, dtype=torch.int32, device=dev)
+            frames_d = torch.empty(B, dtype=torch.int32, device=dev)
+            check(lib.vs_length_regulate_count(ctypes.byref(rp.struct), ptr(dur), ptr(cum), ptr(frames_d), stream),
+                  "vs_length_regulate_count")
+            frames = frames_d.cpu().numpy()            # the one host sync of the path: frame layout needs the counts
+            if frames.max() < 1:
+                raise ValueError("all durations are <= 0: nothing to synthesise")
+            rf = make_rows(frames, sids, FRAME_GAP, dev)
+            Rf, Tf = rf.n_rows, int(frames.max())
+            ws = self._workspace(Rp, Rf)
+
+            x_f = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
+            lr_index = torch.empty(Rf, dtype=torch.int32, device=dev)
+            check(lib.vs_length_regulate_gather(ctypes.byref(rp.struct), ctypes.byref(rf.struct), ptr(x), ptr(cum),
+                                                ptr(x_f), ptr(lr_index), stream), "vs_length_regulate_gather")
+            if noise is None:
+                eps = torch.randn(Rf, 192, dtype=torch.float32, device=dev)          # models.py:718 randn_like
+            else:
+                if isinstance(noise, torch.Tensor):
+                    per = [noise[b, :, :frames[b]].t().cpu().numpy() for b in range(B)]
+                else:
+                    per = [noise[b][:, :frames[b]].t().cpu().numpy() for b in range(B)]
+                eps = torch.from_numpy(rf.scatter(per, np.float32, width=192)).to(dev)
+            m_p = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
+            logs_p = torch.empty_like(m_p)
+            z = torch.empty_like(m_p)
+            check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(eps), float(noise_scale),
+                                     ptr(x_f), ptr(m_p), ptr(logs_p), ptr(z), ptr(ws), ws.numel(), stream),
+                  "vs_frame_prior")
+            z_p = z.clone() if outputs == "all" else None
+            check(lib.vs_flow_reverse(self._model, ctypes.byref(rf.struct), ptr(z), ptr(ws), ws.numel(), stream),
+                  "vs_flow_reverse")
+            wave = torch.empty(Rf * self.hop_length, dtype=torch.float32, device=dev)
+            ml = -1 if max_len is None else int(max_len)
+            check(lib.vs_hifigan_decode(self._model, ctypes.byref(rf.struct), ptr(z), ml, ptr(wave),
+                                        int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
+
+            def unpack(src, C, mul, t_max):
+                out = torch.empty(B, C, t_max, dtype=torch.float32, device=dev)
+                check(lib.vs_unpack_rows(ctypes.byref(rf.struct), ptr(src), C, mul, t_max, ptr(out), stream),
+                      "vs_unpack_rows")
+                return out
+
+            t_dec = Tf if ml < 0 else max(0, min(Tf, ml))
+            if t_dec == 0:
+                o = torch.zeros(B, 1, 0, dtype=torch.float32, device=dev)
+            else:
+                o = unpack(wave, 1, self.hop_length, t_dec * self.hop_length)
+            self.last_rows = (rp, rf)
+            self.last_lr_index = lr_index
+            x_mask = (torch.arange(Tf, device=dev)[None, :] < torch.from_numpy(frames).to(dev)[:, None])[:, None, :]
+            if outputs != "all":
+                return o, x_mask, None, None, None, None
+            lat = tuple(unpack(t, 192, 1, Tf) for t in (z, z_p, m_p, logs_p))
+
+            def phon_out(t):                       # ragged [Rp] -> [B,Tp] (zero at pads)
+                res = torch.zeros(B, Tp, dtype=t.dtype, device=dev)
+                idx_b = torch.from_numpy(np.repeat(np.arange(B), lens)).to(dev)
+                idx_t = torch.from_numpy(np.concatenate([np.arange(n) for n in lens])).to(dev)
+                src = torch.from_numpy(np.concatenate([np.arange(s, s + n) for s, n in zip(rp.starts, lens)])).to(dev)
+                res[idx_b, idx_t] = t[src]
+                return res
+
+            if isinstance(duration_control, torch.Tensor):
+                duration = duration_control                       # returned verbatim (models.py:682, Q7)
+            else:
+                duration = phon_out(dur).to(torch.float32)[:, None, :]
+            return o, x_mask, lat, duration, phon_out(f0), phon_out(energy)
+
+
+def load_checkpoint(checkpoint_path: str, model: SynthesizerTrn, optimizer=None, skip_optimizer: bool = False):
+    """utils.load_checkpoint (utils.py:21-51) for this model: reads ckpt['model'], tolerant of extra keys.
+    Returns (model, optimizer, learning_rate, iteration) like the reference."""
+    ckpt = torch.load(checkpoint_path, map_location="cpu")
+    model.load_state_dict(ckpt["model"])
+    return model, optimizer, ckpt.get("learning_rate"), ckpt.get("iteration")
