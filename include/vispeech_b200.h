@@ -73,6 +73,7 @@ typedef struct {
 
 const char* vs_last_error(void);
 int vs_version(void);
+int64_t vs_launch_count(void);   /* kernels launched by this library so far (process-wide) */
 
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
  * Tensors are registered by name in the PACKED layouts listed in vispeech_b200/packing.py

@@ -28,6 +28,7 @@ class VsError(RuntimeError):
 _SIGNATURES = {
     "vs_last_error": (c_char_p, []),
     "vs_version": (c_int32, []),
+    "vs_launch_count": (c_int64, []),
     "vs_model_create": (c_int32, [POINTER(VsConfig), POINTER(c_void_p)]),
     "vs_model_destroy": (None, [c_void_p]),
     "vs_model_set_tensor": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_int32]),

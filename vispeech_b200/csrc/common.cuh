@@ -21,7 +21,13 @@ void set_error(const char* fmt, ...);
     }                                                                                           \
   } while (0)
 
-#define VS_LAUNCH_CHECK() VS_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site ends with this: counts launches (vs_launch_count) and surfaces launch errors
+extern unsigned long long g_launch_count;
+#define VS_LAUNCH_CHECK()                      \
+  do {                                         \
+    ++vs::g_launch_count;                      \
+    VS_CUDA_CHECK(cudaGetLastError());         \
+  } while (0)
 
 #define VS_REQUIRE(cond, ...)                                                                   \
   do {                                                                                          \

@@ -158,6 +158,7 @@ extern "C" {
 
 const char* vs_last_error(void) { return vs::last_error(); }
 int vs_version(void) { return 1; }
+int64_t vs_launch_count(void) { return (int64_t)vs::g_launch_count; }
 
 int vs_model_create(const VsConfig* cfg, VsModel** out) {
   VS_REQUIRE(cfg && out, "vs_model_create: null argument");

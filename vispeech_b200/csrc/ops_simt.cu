@@ -7,6 +7,7 @@
 
 namespace vs {
 
+unsigned long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -111,18 +111,18 @@ class SynthesizerTrn:
         c = c.cpu().numpy()
         return [c[b, :lengths[b]] for b in range(B)]
 
+    # ------------------------------------------------------------------------------------------------
+    # infer = prepare (host: validate, lay out ragged rows, upload inputs) + run (device work) + outputs
+    # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def infer(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None, energy_control: Control = None,
-              pitch_control: Control = None, duration_control: Control = None, noise=None, outputs: str = "all"):
-        """Same arguments and return tuple as reference models.py:672-722:
-        (o [B,1,hop*Tf'], x_mask bool [B,1,Tf], (z, z_p, m_p, logs_p) [B,192,Tf], duration, F0 [B,Tp], energy [B,Tp]).
-        `noise`: optional eps, a [B,192,Tf] tensor or a list of [192,Tf_b] tensors.
-        """
+    def prepare(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None, energy_control: Control = None,
+                pitch_control: Control = None, duration_control: Control = None, noise=None) -> "Prepared":
+        """Host side of `infer`: everything up to (and including) the host->device copies of the inputs."""
         if not self._loaded:
             raise _lib.VsError("load_state_dict()/load_checkpoint() first")
         if sid is None:
             raise ValueError("sid is required (n_speakers > 0, models.py:674)")
-        lib, dev = self._lib, self.device
+        dev = self.device
         phon = phonemes.detach().cpu().numpy()
         if phon.ndim == 1:
             phon = phon[None]
@@ -135,74 +135,110 @@ class SynthesizerTrn:
             raise ValueError("phonemes_lengths out of range")
         if sids.min() < 0 or sids.max() >= self.n_speakers:
             raise ValueError("sid out of range")
+        P = Prepared()
+        P.B, P.Tp, P.lens, P.sids = B, Tp, lens, sids
+        P.noise_scale, P.max_len = float(noise_scale), (-1 if max_len is None else int(max_len))
+        P.duration_control = duration_control
+        with torch.cuda.device(dev):
+            P.rp = make_rows(lens, sids, PHONEME_GAP, dev)
+            P.ids_rows = _upload(P.rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1), dev)
+
+            def control(c, name, dtype):
+                if isinstance(c, torch.Tensor):
+                    per = self._per_utt(c, B, lens, name)
+                    return 2, 1.0, _upload(P.rp.scatter(per, dtype), dev), per
+                return 0, 1.0 if c is None else float(c), None, None
+
+            P.d_mode, P.d_scale, P.d_ctrl, d_per = control(duration_control, "duration_control", np.float64)
+            P.p_mode, P.p_scale, P.p_ctrl, _ = control(pitch_control, "pitch_control", np.float32)
+            P.e_mode, P.e_scale, P.e_ctrl, _ = control(energy_control, "energy_control", np.float32)
+            P.noise = noise
+            P.frames = None
+            P.rf = None
+            P.eps = None
+            if d_per is not None:
+                # durations given: frame counts follow on the host by the same rule the kernel applies
+                # (n_i = max(int(d_i), 0), models.py:421-423), so the frame layout needs no device round trip
+                P.frames = np.asarray([int(np.clip(np.trunc(np.asarray(d, np.float64)), 0, 1.0e6).sum()) for d in d_per],
+                                      np.int32)
+                self._layout_frames(P)
+        return P
+
+    def _layout_frames(self, P: "Prepared") -> None:
+        if int(P.frames.max()) < 1:
+            raise ValueError("all durations are <= 0: nothing to synthesise")
+        dev = self.device
+        P.rf = make_rows(P.frames, P.sids, FRAME_GAP, dev)
+        if P.noise is not None:
+            fr = P.frames
+            if isinstance(P.noise, torch.Tensor):
+                per = [P.noise[b, :, :fr[b]].t().cpu().numpy() for b in range(P.B)]
+            else:
+                per = [P.noise[b][:, :fr[b]].t().cpu().numpy() for b in range(P.B)]
+            P.eps = _upload(P.rf.scatter(per, np.float32, width=192), dev)
+
+    @torch.no_grad()
+    def run(self, P: "Prepared", outputs: str = "all", timings: Optional[dict] = None):
+        """Device side of `infer`: kernels only (plus one small D2H of frame counts when durations are predicted)."""
+        lib, dev = self._lib, self.device
+        B, Tp, rp = P.B, P.Tp, P.rp
+        Rp = rp.n_rows
+        ev = []
+
+        def mark(name):
+            if timings is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(dev))
+                ev.append((name, e))
 
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rp = make_rows(lens, sids, PHONEME_GAP, dev)
-            Rp = rp.n_rows
-            ids_rows = torch.from_numpy(rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1)).to(dev)
-
-            def control(c, name):
-                """-> (mode, scale, device array or None)"""
-                if isinstance(c, torch.Tensor):
-                    per = self._per_utt(c, B, lens, name)
-                    return 2, 1.0, per
-                return 0, 1.0 if c is None else float(c), None
-
-            d_mode, d_scale, d_per = control(duration_control, "duration_control")
-            p_mode, p_scale, p_per = control(pitch_control, "pitch_control")
-            e_mode, e_scale, e_per = control(energy_control, "energy_control")
-            d_ctrl = torch.from_numpy(rp.scatter(d_per, np.float64)).to(dev) if d_per is not None else None
-            p_ctrl = torch.from_numpy(rp.scatter(p_per, np.float32)).to(dev) if p_per is not None else None
-            e_ctrl = torch.from_numpy(rp.scatter(e_per, np.float32)).to(dev) if e_per is not None else None
-
-            # frame layout is only known after the durations: size the workspace for the phoneme stage first
-            ws = self._workspace(Rp, 16)
+            ws = self._workspace(Rp, P.rf.n_rows if P.rf is not None else 16)
+            mark("start")
             x = torch.empty(Rp, 192, dtype=torch.float32, device=dev)
-            check(lib.vs_text_encode(self._model, ctypes.byref(rp.struct), ptr(ids_rows), ptr(x), ptr(ws), ws.numel(),
+            check(lib.vs_text_encode(self._model, ctypes.byref(rp.struct), ptr(P.ids_rows), ptr(x), ptr(ws), ws.numel(),
                                      stream), "vs_text_encode")
+            mark("text_encoder")
             dur = torch.empty(Rp, dtype=torch.float64, device=dev)
             f0 = torch.empty(Rp, dtype=torch.float32, device=dev)
             energy = torch.empty(Rp, dtype=torch.float32, device=dev)
-            check(lib.vs_variance_adapter(self._model, ctypes.byref(rp.struct), ptr(x), d_mode, d_scale, ptr(d_ctrl),
-                                          p_mode, p_scale, ptr(p_ctrl), e_mode, e_scale, ptr(e_ctrl), ptr(dur), ptr(f0),
-                                          ptr(energy), ptr(ws), ws.numel(), stream), "vs_variance_adapter")
+            check(lib.vs_variance_adapter(self._model, ctypes.byref(rp.struct), ptr(x), P.d_mode, P.d_scale, ptr(P.d_ctrl),
+                                          P.p_mode, P.p_scale, ptr(P.p_ctrl), P.e_mode, P.e_scale, ptr(P.e_ctrl),
+                                          ptr(dur), ptr(f0), ptr(energy), ptr(ws), ws.numel(), stream),
+                  "vs_variance_adapter")
+            mark("variance_adapter")
             cum = torch.empty(Rp, dtype=torch.int32, device=dev)
             frames_d = torch.empty(B, dtype=torch.int32, device=dev)
             check(lib.vs_length_regulate_count(ctypes.byref(rp.struct), ptr(dur), ptr(cum), ptr(frames_d), stream),
                   "vs_length_regulate_count")
-            frames = frames_d.cpu().numpy()            # the one host sync of the path: frame layout needs the counts
-            if frames.max() < 1:
-                raise ValueError("all durations are <= 0: nothing to synthesise")
-            rf = make_rows(frames, sids, FRAME_GAP, dev)
+            if P.rf is None:
+                P.frames = frames_d.cpu().numpy()        # predicted durations: the one host sync of the path
+                self._layout_frames(P)
+                ws = self._workspace(Rp, P.rf.n_rows)
+            rf, frames = P.rf, P.frames
             Rf, Tf = rf.n_rows, int(frames.max())
-            ws = self._workspace(Rp, Rf)
-
             x_f = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             lr_index = torch.empty(Rf, dtype=torch.int32, device=dev)
             check(lib.vs_length_regulate_gather(ctypes.byref(rp.struct), ctypes.byref(rf.struct), ptr(x), ptr(cum),
                                                 ptr(x_f), ptr(lr_index), stream), "vs_length_regulate_gather")
-            if noise is None:
-                eps = torch.randn(Rf, 192, dtype=torch.float32, device=dev)          # models.py:718 randn_like
-            else:
-                if isinstance(noise, torch.Tensor):
-                    per = [noise[b, :, :frames[b]].t().cpu().numpy() for b in range(B)]
-                else:
-                    per = [noise[b][:, :frames[b]].t().cpu().numpy() for b in range(B)]
-                eps = torch.from_numpy(rf.scatter(per, np.float32, width=192)).to(dev)
+            mark("length_regulator")
+            eps = P.eps if P.eps is not None else torch.randn(Rf, 192, dtype=torch.float32, device=dev)  # models.py:718
             m_p = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             logs_p = torch.empty_like(m_p)
             z = torch.empty_like(m_p)
-            check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(eps), float(noise_scale),
+            check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(eps), P.noise_scale,
                                      ptr(x_f), ptr(m_p), ptr(logs_p), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_frame_prior")
+            mark("frame_prior")
             z_p = z.clone() if outputs == "all" else None
             check(lib.vs_flow_reverse(self._model, ctypes.byref(rf.struct), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_flow_reverse")
+            mark("flow")
             wave = torch.empty(Rf * self.hop_length, dtype=torch.float32, device=dev)
-            ml = -1 if max_len is None else int(max_len)
+            ml = P.max_len
             check(lib.vs_hifigan_decode(self._model, ctypes.byref(rf.struct), ptr(z), ml, ptr(wave),
                                         int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
+            mark("decoder")
 
             def unpack(src, C, mul, t_max):
                 out = torch.empty(B, C, t_max, dtype=torch.float32, device=dev)
@@ -215,12 +251,16 @@ class SynthesizerTrn:
                 o = torch.zeros(B, 1, 0, dtype=torch.float32, device=dev)
             else:
                 o = unpack(wave, 1, self.hop_length, t_dec * self.hop_length)
+            mark("unpack")
             self.last_rows = (rp, rf)
             self.last_lr_index = lr_index
+            if timings is not None:
+                timings["_events"] = ev
             x_mask = (torch.arange(Tf, device=dev)[None, :] < torch.from_numpy(frames).to(dev)[:, None])[:, None, :]
             if outputs != "all":
                 return o, x_mask, None, None, None, None
             lat = tuple(unpack(t, 192, 1, Tf) for t in (z, z_p, m_p, logs_p))
+            lens = P.lens
 
             def phon_out(t):                       # ragged [Rp] -> [B,Tp] (zero at pads)
                 res = torch.zeros(B, Tp, dtype=t.dtype, device=dev)
@@ -230,11 +270,43 @@ class SynthesizerTrn:
                 res[idx_b, idx_t] = t[src]
                 return res
 
-            if isinstance(duration_control, torch.Tensor):
-                duration = duration_control                       # returned verbatim (models.py:682, Q7)
+            if isinstance(P.duration_control, torch.Tensor):
+                duration = P.duration_control                     # returned verbatim (models.py:682, Q7)
             else:
                 duration = phon_out(dur).to(torch.float32)[:, None, :]
             return o, x_mask, lat, duration, phon_out(f0), phon_out(energy)
+
+    @staticmethod
+    def resolve_timings(timings: dict) -> Dict[str, float]:
+        """After a synchronize: milliseconds per subsystem from the CUDA events `run(timings=...)` recorded."""
+        ev = timings.pop("_events")
+        out = {}
+        for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    @torch.no_grad()
+    def infer(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None, energy_control: Control = None,
+              pitch_control: Control = None, duration_control: Control = None, noise=None, outputs: str = "all"):
+        """Same arguments and return tuple as reference models.py:672-722:
+        (o [B,1,hop*Tf'], x_mask bool [B,1,Tf], (z, z_p, m_p, logs_p) [B,192,Tf], duration, F0 [B,Tp], energy [B,Tp]).
+        `noise`: optional eps, a [B,192,Tf] tensor or a list of [192,Tf_b] tensors.  `outputs="audio"` skips the
+        latents (returns None in their place).
+        """
+        P = self.prepare(phonemes, phonemes_lengths, sid, noise_scale, max_len, energy_control, pitch_control,
+                         duration_control, noise)
+        return self.run(P, outputs)
+
+
+class Prepared:
+    """Device-resident inputs + row layouts of one `infer` call (see SynthesizerTrn.prepare)."""
+
+
+def _upload(a: np.ndarray, dev) -> torch.Tensor:
+    t = torch.from_numpy(a)
+    if t.numel() > 4096:
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=True)
 
 
 def load_checkpoint(checkpoint_path: str, model: SynthesizerTrn, optimizer=None, skip_optimizer: bool = False):
