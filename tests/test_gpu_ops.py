@@ -62,7 +62,7 @@ def test_umma_conv_residual_mask_and_scale(G):
 @pytest.mark.parametrize("stage", [0, 2, 3])
 def test_umma_conv_transpose_polyphase(G, stage):
     """ConvTranspose1d (models.py:257-259) as a polyphase UMMA conv vs F.conv_transpose1d."""
-    from vispeech_b200.packing import UP_KERNELS, UP_RATES, ups_phase_range, ups_union_taps
+    from vispeech_b200.packing import UP_KERNELS, UP_RATES, up_columns, ups_phase_range, ups_union_taps
     s, K = UP_RATES[stage], UP_KERNELS[stage]
     cin, cout = 512 >> stage, 256 >> stage
     R = 260
@@ -73,10 +73,11 @@ def test_umma_conv_transpose_polyphase(G, stage):
     taps, pad_l = ups_union_taps(stage)
     uni = torch.zeros(taps, cin, s * cout)
     pad = (K - s) // 2
+    cols = up_columns(cout, s)
     for ph in range(s):
         lo, hi = ups_phase_range(stage, ph)
         for d in range(lo, hi + 1):
-            uni[d + pad_l, :, ph * cout:(ph + 1) * cout] = wt[:, :, ph + pad - s * d]
+            uni[d + pad_l, :, cols[ph * cout:(ph + 1) * cout]] = wt[:, :, ph + pad - s * d]
     raw, _ = G.umma_conv(x.to(G.DEV), uni, b.to(G.DEV), pad_l=pad_l, up=s, want_act=False)
     ref = torch.nn.functional.conv_transpose1d(G.bf16_round(x).t()[None].double(), G.bf16_round(wt).double(), b.double(),
                                                stride=s, padding=pad)[0].t()

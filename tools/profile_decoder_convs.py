@@ -1,0 +1,64 @@
+"""Per-shape timing of the tcgen05 decoder conv (CUDA events, op-level C-ABI calls) at the C2 workload size.
+Prints, for every distinct conv shape of the HiFi-GAN decoder, time, TFLOP/s and algorithmic GB/s."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vispeech_b200 import _lib                     # noqa: E402
+from vispeech_b200._lib import check, ptr          # noqa: E402
+
+FRAMES = int(os.environ.get("FRAMES", 27840))
+REPS = 5
+lib = _lib.load()
+dev = "cuda:0"
+st = torch.cuda.current_stream().cuda_stream
+
+
+def run(name, R, cin, n, taps, dil, up=1, res=False, two_out=False, count=1):
+    cout = n // up
+    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(cout, device=dev)
+    r = (torch.randn(cout // 8, R * up, 8, device=dev)).to(torch.bfloat16) if res else None
+    o1 = torch.empty(cout // 8, R * up, 8, device=dev, dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1) if two_out else None
+    pad_l = (taps - 1) // 2
+
+    def call():
+        check(lib.vs_op_conv1d_umma(ptr(x), ptr(w), ptr(b), ptr(r), ptr(o2), ptr(o1), R, cin, n, taps, dil, pad_l, up, 0.1, 1.0,
+                                    None, 1, st))
+    call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    flop = 2.0 * R * cin * n * taps
+    if up > 1:
+        flop = 2.0 * R * cin * n * 2 * (taps > 1) + 2.0 * R * cin * n * (taps == 1)   # algorithmic: K/s taps per phase
+    byts = 2.0 * R * cin + 2.0 * R * up * cout * ((1 if res else 0) + 1 + (1 if two_out else 0))
+    print("%-22s R=%9d Cin=%3d N=%4d k=%2d d=%d  %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s   x%d = %7.2f ms" % (
+        name, R, cin, n, taps, dil, ms, flop / ms / 1e9, byts / ms / 1e6, count, ms * count))
+    return ms * count
+
+
+total = 0.0
+total += run("conv_pre", FRAMES, 192, 512, 7, 1)
+mul = 1
+for i, (s, K) in enumerate(zip((8, 8, 4, 2), (16, 16, 4, 4))):
+    cin, cout = 512 >> i, 256 >> i
+    taps = 1 if K == s else 3
+    total += run("ups%d" % i, FRAMES * mul, cin, cout * s, taps, 1, up=s, two_out=True)
+    mul *= s
+    R = FRAMES * mul
+    for k in (3, 7, 11):
+        for d in (1, 3, 5):
+            total += run("s%d c1 k%d d%d" % (i, k, d), R, cout, cout, k, d)
+        total += run("s%d c2 k%d (res,2out)" % (i, k), R, cout, cout, k, 1, res=True, two_out=True, count=3)
+print("sum of decoder convs: %.2f ms" % total)

@@ -24,13 +24,21 @@ namespace vs {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter, splitting the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 8;                   // TMEM accumulator ring depth (small N: many tiles in flight)
 
 struct Plan {
   int rows_a, halo_l, planes, KC, n_kc, Nblk, NB, SA, SB, tmem_cols, n_tiles, Cout;
+  int up_shift, row_div_shift, ctas_per_sm;
+  int NACC;               // accumulator buffers in TMEM (ring between the MMA issuer and the epilogue)
+  int MT;                 // row tiles (128 rows each) per A stage
+  int resident_b;         // 1: every weight slab stays in smem for the whole kernel; 0: slabs stream through a ring
+  int n_super;            // number of A stages' worth of work = ceil(n_tiles / MT)
+  uint32_t w_bytes;       // all weight slabs
   uint32_t a_bytes, b_bytes, smem_bytes;
-  uint32_t off_b, off_bar;
+  uint32_t off_b, off_bar, off_bias;
 };
 
 struct Params {
@@ -79,8 +87,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar) {   // whole warp calls, one elected lane commits
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation.
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -90,6 +102,22 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with the descriptors passed as 32-bit halves: only the low words (start address, 16 B units) change
+// between MMAs, so the issue loop is two integer adds per instruction.
+// Executed by the whole (converged) MMA warp: one elected lane issues, so the surrounding loop stays
+// warp-uniform and the compiler keeps the descriptors in uniform registers.
+__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
@@ -122,6 +150,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -135,7 +174,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   const UmmaConv& c = prm.c;
   const Plan& p = prm.p;
@@ -145,19 +184,19 @@ __global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_cons
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + p.off_b;
   const uint32_t bar_base = smem_base + p.off_bar;
-  // barrier table (8 B each): a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+  // barrier table (8 B each): a_full[8] a_empty[8] b_full[8] b_empty[8] acc_full[8] acc_empty[8]
   auto a_full = [&](int i) { return bar_base + 8u * i; };
   auto a_empty = [&](int i) { return bar_base + 8u * (kMaxStages + i); };
   auto b_full = [&](int i) { return bar_base + 8u * (2 * kMaxStages + i); };
   auto b_empty = [&](int i) { return bar_base + 8u * (3 * kMaxStages + i); };
   auto acc_full = [&](int i) { return bar_base + 8u * (4 * kMaxStages + i); };
-  auto acc_empty = [&](int i) { return bar_base + 8u * (4 * kMaxStages + 2 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (4 * kMaxStages + 4));
+  auto acc_empty = [&](int i) { return bar_base + 8u * (4 * kMaxStages + kMaxAcc + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (4 * kMaxStages + 2 * kMaxAcc));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+    for (int i = 0; i < (p.SB > 0 ? p.SB : 1); ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < p.NACC; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -166,6 +205,8 @@ __global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);     // [Cout] (zeros when the conv has no bias)
+  for (int i = threadIdx.x; i < p.Cout; i += kThreads) bias_s[i] = c.bias ? c.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,11 +218,19 @@ __global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t a_it = 0, b_it = 0;
-    auto issue_a = [&](int tile) {
+    const int n_slabs = p.NB * stages_per_unit;
+    if (p.resident_b) {              // small convs: all weights fetched once, never streamed again
+      if (lane == 0) mbar_arrive_expect_tx(b_full(0), p.w_bytes);
+      __syncwarp();
+      for (int sl = lane; sl < n_slabs; sl += 32)
+        bulk_g2s(b_base + sl * p.b_bytes, reinterpret_cast<const uint8_t*>(c.w) + (size_t)sl * p.b_bytes, p.b_bytes,
+                 b_full(0));
+    }
+    auto issue_a = [&](int super) {
       const int sa = a_it % p.SA;
       const uint32_t ph = (a_it / p.SA) & 1;
       mbar_wait(a_empty(sa), ph ^ 1, 1);
-      const int row_lo = tile * kTileM - p.halo_l, row_hi = row_lo + p.rows_a;
+      const int row_lo = super * p.MT * kTileM - p.halo_l, row_hi = row_lo + p.rows_a;
       const int c_lo = row_lo < 0 ? 0 : row_lo, c_hi = row_hi > c.R ? c.R : row_hi;
       const uint32_t stage = a_base + sa * p.a_bytes;
       const int n_zero_lo = c_lo - row_lo, n_zero_hi = row_hi - c_hi;
@@ -205,18 +254,18 @@ __global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_cons
     };
     const int look = p.SA - 1;
     int next_a = blockIdx.x;
-    for (int i = 0; i < look && next_a < p.n_tiles; ++i, next_a += gridDim.x) issue_a(next_a);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      if (next_a < p.n_tiles) { issue_a(next_a); next_a += gridDim.x; }
-      if (lane == 0) {
-        for (int nb = 0; nb < p.NB; ++nb)
-          for (int s = 0; s < stages_per_unit; ++s) {
+    for (int i = 0; i < look && next_a < p.n_super; ++i, next_a += gridDim.x) issue_a(next_a);
+    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x) {
+      if (next_a < p.n_super) { issue_a(next_a); next_a += gridDim.x; }
+      if (!p.resident_b && lane == 0) {
+        const int tiles_here = min(p.MT, p.n_tiles - super * p.MT);
+        for (int m = 0; m < tiles_here; ++m)
+          for (int sl = 0; sl < n_slabs; ++sl) {
             const int sb = b_it % p.SB;
             const uint32_t ph = (b_it / p.SB) & 1;
             mbar_wait(b_empty(sb), ph ^ 1, 2);
             mbar_arrive_expect_tx(b_full(sb), p.b_bytes);
-            bulk_g2s(b_base + sb * p.b_bytes,
-                     reinterpret_cast<const uint8_t*>(c.w) + ((size_t)nb * stages_per_unit + s) * p.b_bytes, p.b_bytes,
+            bulk_g2s(b_base + sb * p.b_bytes, reinterpret_cast<const uint8_t*>(c.w) + (size_t)sl * p.b_bytes, p.b_bytes,
                      b_full(sb));
             ++b_it;
           }
@@ -224,112 +273,199 @@ __global__ void __launch_bounds__(kThreads) umma_conv1d_kernel(const __grid_cons
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    {
       const uint32_t idesc = make_idesc(p.Nblk);
       const uint32_t a_lbo = (uint32_t)p.rows_a * 16u, b_lbo = (uint32_t)p.Nblk * 16u;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int sa = a_it % p.SA;
-        mbar_wait(a_full(sa), (a_it / p.SA) & 1, 3);
+      // loop-invariant descriptor pieces (all in 16-byte units): see make_desc()
+      const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32), b_hi = (uint32_t)(make_desc(0, b_lbo, 128u) >> 32);
+      const uint32_t a_lo_fixed = (uint32_t)make_desc(0, a_lbo, 128u), b_lo_fixed = (uint32_t)make_desc(0, b_lbo, 128u);
+      const uint32_t a_kstep = 2u * (uint32_t)p.rows_a;          // two planes per K=16 step
+      const uint32_t b_kstep = 2u * (uint32_t)p.Nblk;
+      const int taps = c.taps, dil = c.dil, n_kc = p.n_kc, k16s = p.KC / 16, MT = p.MT, NACC = p.NACC, SB = p.SB, SA = p.SA;
+      const int n_tiles = p.n_tiles, n_super = p.n_super;
+      const bool resident = p.resident_b != 0;
+      const int IL = (resident && p.NB == 1) ? min(min(4, MT), NACC / 2) : 1;
+      const uint32_t slab16 = p.b_bytes >> 4, a_bytes = p.a_bytes, nblk = (uint32_t)p.Nblk;
+      const uint32_t b_base16 = b_base >> 4;
+      uint32_t acc_slot = 0, acc_phase = 0, b_slot = 0, b_phase = 0, a_slot = 0, a_phase = 0;
+      if (resident) { mbar_wait(b_full(0), 0, 7); tc_fence_after(); }
+      for (int super = blockIdx.x; super < n_super; super += gridDim.x) {
+        mbar_wait(a_full(a_slot), a_phase, 3);
         tc_fence_after();
-        const uint32_t a_stage = a_base + sa * p.a_bytes;
-        for (int nb = 0; nb < n_units_per_tile; ++nb) {
-          const int ab = acc_it & 1;
-          mbar_wait(acc_empty(ab), ((acc_it >> 1) & 1) ^ 1, 4);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.Nblk);
-          uint32_t accumulate = 0;
-          for (int t = 0; t < c.taps; ++t)
-            for (int kc = 0; kc < p.n_kc; ++kc) {
-              const int sb = b_it % p.SB;
-              mbar_wait(b_full(sb), (b_it / p.SB) & 1, 5);
-              tc_fence_after();
-              const uint32_t b_stage = b_base + sb * p.b_bytes;
-              for (int k16 = 0; k16 < p.KC / 16; ++k16) {
-                const uint32_t plane0 = (uint32_t)(kc * (p.KC / 8) + 2 * k16);
-                const uint64_t ad = make_desc(a_stage + (plane0 * p.rows_a + (uint32_t)(t * c.dil)) * 16u, a_lbo, 128u);
-                const uint64_t bd = make_desc(b_stage + (uint32_t)(2 * k16 * p.Nblk) * 16u, b_lbo, 128u);
-                tc_mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                accumulate = 1;
+        const uint32_t a_stage16 = (a_base + a_slot * a_bytes) >> 4;
+        const int tiles_here = min(MT, n_tiles - super * MT);
+        if (IL > 1) {
+          // Small-N convs: consecutive MMAs into ONE accumulator form a dependent chain and expose the tensor
+          // pipeline latency.  Interleave up to IL row tiles of this A stage: each K-step issues one MMA per
+          // tile (independent accumulators, same weight operand), so the chains overlap.
+          for (int m0 = 0; m0 < tiles_here; m0 += IL) {
+            const int g = min(IL, tiles_here - m0);
+            uint32_t d_tmem[4], slot[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              d_tmem[j] = 0; slot[j] = 0;
+              if (j < g) {
+                mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4);
+                slot[j] = acc_slot;
+                d_tmem[j] = tmem_base + acc_slot * nblk;
+                if (++acc_slot == (uint32_t)NACC) { acc_slot = 0; acc_phase ^= 1; }
               }
-              tc_commit(b_empty(sb));      // frees the weight slot once these MMAs have read it
-              ++b_it;
             }
-          tc_commit(acc_full(ab));         // accumulator complete -> epilogue
-          ++acc_it;
+            tc_fence_after();
+            uint32_t accumulate = 0;
+            uint32_t b_lo = b_lo_fixed + b_base16;
+            uint32_t a_tap = a_lo_fixed + a_stage16 + (uint32_t)(m0 * kTileM);
+            for (int t = 0; t < taps; ++t, a_tap += (uint32_t)dil) {
+              uint32_t a_lo = a_tap;
+              for (int ks = 0; ks < n_kc * k16s; ++ks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < g) tc_mma_bf16_lohi(d_tmem[j], a_lo + (uint32_t)(j * kTileM), a_hi, b_lo, b_hi, idesc, accumulate);
+                accumulate = 1;
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < g) tc_commit(acc_full(slot[j]));
+          }
+        } else {
+          for (int m = 0; m < tiles_here; ++m)
+            for (int nb = 0; nb < n_units_per_tile; ++nb) {
+              mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + acc_slot * nblk;
+              uint32_t accumulate = 0;
+              uint32_t b_lo = b_lo_fixed + b_base16 + (uint32_t)(nb * taps * n_kc) * slab16;   // resident: walks all slabs
+              uint32_t a_tap = a_lo_fixed + a_stage16 + (uint32_t)(m * kTileM);
+              for (int t = 0; t < taps; ++t, a_tap += (uint32_t)dil) {
+                uint32_t a_lo = a_tap;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                  if (!resident) {
+                    mbar_wait(b_full(b_slot), b_phase, 5);
+                    tc_fence_after();
+                    b_lo = b_lo_fixed + b_base16 + b_slot * slab16;
+                  }
+#pragma unroll 4
+                  for (int k16 = 0; k16 < k16s; ++k16) {
+                    tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                    accumulate = 1;
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
+                  }
+                  if (!resident) {
+                    tc_commit(b_empty(b_slot));    // frees the weight slot once these MMAs have read it
+                    if (++b_slot == (uint32_t)SB) { b_slot = 0; b_phase ^= 1; }
+                  }
+                }
+              }
+              tc_commit(acc_full(acc_slot));       // accumulator complete -> epilogue
+              if (++acc_slot == (uint32_t)NACC) { acc_slot = 0; acc_phase ^= 1; }
+            }
         }
-        tc_commit(a_empty(sa));            // every MMA of the tile has read the A stage
-        ++a_it;
+        tc_commit(a_empty(a_slot));              // every MMA of the stage has read the A tile
+        if (++a_slot == (uint32_t)SA) { a_slot = 0; a_phase ^= 1; }
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;                // TMEM lane quarter this warp may access
-    uint32_t acc_it = 0;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Warp w may touch TMEM lanes [32*(w%4), +32).  Two warps share each lane quarter and take alternate
+    // column chunks, so 8 warps drain one accumulator; per-row facts (validity, utterance) are hoisted out of
+    // the column loop, bias comes from smem, residual loads are issued before the TMEM load is waited on.
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int CW = p.Nblk >= 64 ? 32 : 16;            // columns per tcgen05.ld
+    const int n_chunks = p.Nblk / CW;
+    uint32_t acc_slot = 0, acc_phase = 0;
     const int R_out = c.R * c.up;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const uint32_t up_mask = (uint32_t)c.up - 1u;
+    const int plane_shift = 3 + p.up_shift;
+    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x)
+    for (int tile = super * p.MT; tile < min(p.n_tiles, (super + 1) * p.MT); ++tile) {
       const int r = tile * kTileM + q * 32 + lane;
+      const bool in_range = r < c.R;
+      int utt = -1;
+      if (in_range) utt = c.row_utt ? c.row_utt[(c.up * r) >> p.row_div_shift] : 0;
+      const bool valid = utt >= 0;
+      const float* ub = nullptr;
+      if (c.ubias && valid) ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.N;
+      const size_t row_base = (size_t)c.up * r;
       for (int nb = 0; nb < n_units_per_tile; ++nb) {
-        const int ab = acc_it & 1;
-        mbar_wait(acc_full(ab), (acc_it >> 1) & 1, 6);
+        const int ab = (int)acc_slot;
+        mbar_wait(acc_full(ab), acc_phase, 6);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Nblk);
-        for (int col0 = 0; col0 < p.Nblk; col0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)col0, v);
-          if (r < c.R) {
+        for (int cc = hsel; cc < n_chunks; cc += 2) {
+          const int col0 = cc * CW;
+          const int n_groups = CW / 8;
+          uint4 rv[4], rv2[4];
+          if (valid && (c.res || c.res2)) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int gn0 = nb * p.Nblk + col0 + 8 * g;
-              const int phs = gn0 / p.Cout, co0 = gn0 - phs * p.Cout;
-              const int orow = c.up * r + phs;
-              const int utt = c.row_utt ? c.row_utt[orow / c.row_div] : 0;
-              const size_t o = ((size_t)(co0 >> 3) * R_out + orow) * 8;
-              uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
-              if (utt >= 0) {
-                float y[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[8 * g + e]);
-                if (c.bias) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] += __ldg(c.bias + co0 + e);
-                }
-                if (c.ubias) {
-                  const float* ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.N + gn0;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] += __ldg(ub + e);
-                }
-                if (c.res) {
-                  float f[8];
-                  unpack_bf16x8(*reinterpret_cast<const uint4*>(c.res + o), f);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] += f[e];
-                }
-                if (c.res2) {
-                  float f[8];
-                  unpack_bf16x8(*reinterpret_cast<const uint4*>(c.res2 + o), f);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] += f[e];
-                }
-                raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                                 pack_bf16x2(y[6], y[7]));
-                float z[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) z[e] = lrelu(y[e] * c.act_scale, c.act_slope);
-                act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
-                                 pack_bf16x2(z[6], z[7]));
+              if (g < n_groups) {
+                const uint32_t gn0 = (uint32_t)(nb * p.Nblk + col0 + 8 * g);
+                const size_t o = ((size_t)(gn0 >> plane_shift) * R_out + row_base + ((gn0 >> 3) & up_mask)) * 8;
+                if (c.res) rv[g] = *reinterpret_cast<const uint4*>(c.res + o);
+                if (c.res2) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + o);
               }
-              if (c.out_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;
-              if (c.out_act) *reinterpret_cast<uint4*>(c.out_act + o) = act;
+            }
+          }
+          uint32_t v[32];
+          if (CW == 32) tmem_ld32(t_row + (uint32_t)col0, v);
+          else tmem_ld16(t_row + (uint32_t)col0, v);
+          if (in_range) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g < n_groups) {
+                const uint32_t gn0 = (uint32_t)(nb * p.Nblk + col0 + 8 * g);
+                const uint32_t co0 = (gn0 >> plane_shift) << 3;
+                const size_t o = ((size_t)(gn0 >> plane_shift) * R_out + row_base + ((gn0 >> 3) & up_mask)) * 8;
+                uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
+                if (valid) {
+                  float y[8];
+                  const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co0);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co0 + 4);
+                  y[0] = __uint_as_float(v[8 * g + 0]) + b0.x; y[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+                  y[2] = __uint_as_float(v[8 * g + 2]) + b0.z; y[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+                  y[4] = __uint_as_float(v[8 * g + 4]) + b1.x; y[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+                  y[6] = __uint_as_float(v[8 * g + 6]) + b1.z; y[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+                  if (ub) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] += __ldg(ub + gn0 + e);
+                  }
+                  if (c.res) {
+                    float f[8];
+                    unpack_bf16x8(rv[g], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] += f[e];
+                  }
+                  if (c.res2) {
+                    float f[8];
+                    unpack_bf16x8(rv2[g], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] += f[e];
+                  }
+                  raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                                   pack_bf16x2(y[6], y[7]));
+                  float z[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) z[e] = lrelu(y[e] * c.act_scale, c.act_slope);
+                  act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
+                                   pack_bf16x2(z[6], z[7]));
+                }
+                if (c.out_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;
+                if (c.out_act) *reinterpret_cast<uint4*>(c.out_act + o) = act;
+              }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(ab));
-        ++acc_it;
+        if (++acc_slot == (uint32_t)p.NACC) { acc_slot = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -357,27 +493,70 @@ int make_plan(const UmmaConv& c, Plan* out) {
   p.n_kc = c.Cin / p.KC;
   p.planes = c.Cin / 8;
   p.halo_l = c.pad_l * c.dil;
-  p.rows_a = kTileM + (c.taps - 1) * c.dil;
-  p.a_bytes = (uint32_t)p.planes * p.rows_a * 16u;
+  const int halo = (c.taps - 1) * c.dil;
   p.b_bytes = (uint32_t)p.KC * p.Nblk * 2u;
+  p.w_bytes = p.b_bytes * (uint32_t)(p.NB * c.taps * p.n_kc);
+  auto log2_exact = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  p.up_shift = log2_exact(c.up);
+  p.row_div_shift = log2_exact(c.row_div);
+  VS_REQUIRE(p.up_shift >= 0 && p.row_div_shift >= 0, "umma_conv1d: up=%d and row_div=%d must be powers of two", c.up,
+             c.row_div);
+  const uint32_t bar_bytes = 8u * (4 * kMaxStages + 2 * kMaxAcc) + 16u;
+  const uint32_t fixed = bar_bytes + 128u + (uint32_t)p.Cout * 4u;
+  // Shared-memory policy.
+  //  * Small convs (all weight slabs <= 96 KB): weights stay resident, the A stage spans MT row tiles so that
+  //    activation fetches are few and large, two A stages.  Preferred footprint <= half an SM so two CTAs co-reside.
+  //  * Large convs: one row tile per A stage, weights stream through a ring of >= 4 slabs out of L2.
+  const uint32_t half_sm = 110u * 1024, full_sm = 220u * 1024;
+  auto a_bytes_for = [&](int mt) { return (uint32_t)p.planes * (uint32_t)(kTileM * mt + halo) * 16u; };
+  p.resident_b = p.w_bytes <= 96u * 1024 ? 1 : 0;
+  uint32_t cap = full_sm;
+  if (p.resident_b) {
+    p.SB = 0;
+    p.SA = 2;
+    p.MT = 0;
+    const int mts[3] = {4, 2, 1};
+    for (int pass = 0; pass < 2 && !p.MT; ++pass)
+      for (int i = 0; i < 3 && !p.MT; ++i)
+        if (2 * a_bytes_for(mts[i]) + p.w_bytes + fixed <= (pass == 0 ? half_sm : full_sm)) p.MT = mts[i];
+    if (!p.MT) { p.MT = 1; p.SA = 1; }
+    VS_REQUIRE(p.SA * a_bytes_for(p.MT) + p.w_bytes + fixed <= full_sm, "umma_conv1d: tile does not fit in shared memory");
+  } else {
+    p.MT = 1;
+    const uint32_t a1 = a_bytes_for(1);
+    auto fits = [&](int sa, int sb, uint32_t lim) { return sa * a1 + sb * p.b_bytes + fixed <= lim; };
+    if (fits(2, 4, half_sm)) { p.SA = 2; cap = half_sm; }
+    else if (fits(1, 4, half_sm)) { p.SA = 1; cap = half_sm; }
+    else if (fits(2, 3, full_sm)) { p.SA = 2; cap = full_sm; }
+    else { p.SA = 1; cap = full_sm; }
+    VS_REQUIRE(fits(p.SA, 2, cap), "umma_conv1d: tile does not fit in shared memory");
+    const int sb = (int)((cap - fixed - p.SA * a1) / p.b_bytes);
+    const int sb_max = cap == half_sm ? 6 : kMaxStages;
+    p.SB = sb > sb_max ? sb_max : sb;
+  }
+  p.rows_a = kTileM * p.MT + halo;
+  p.a_bytes = a_bytes_for(p.MT);
   VS_REQUIRE(p.rows_a * 16 < (1 << 18), "umma_conv1d: halo too large for the descriptor pitch");
-  const uint32_t bar_bytes = 8u * (4 * kMaxStages + 4) + 16u;
-  const uint32_t budget_small = 96u * 1024, budget_max = 220u * 1024;
-  p.SA = (2 * p.a_bytes + 2 * p.b_bytes + bar_bytes <= budget_max) ? 2 : 1;
-  VS_REQUIRE(p.SA * p.a_bytes + 2 * p.b_bytes + bar_bytes <= budget_max, "umma_conv1d: tile does not fit in shared memory");
-  uint32_t budget = budget_small;
-  if (p.SA * p.a_bytes + 3 * p.b_bytes + bar_bytes > budget) budget = budget_max;
-  int sb = (int)((budget - bar_bytes - p.SA * p.a_bytes) / p.b_bytes);
-  p.SB = sb > kMaxStages ? kMaxStages : sb;
-  if (p.SB < 2) p.SB = 2;
-  int cols = 32;
-  while (cols < 2 * p.Nblk) cols *= 2;
-  p.tmem_cols = cols;
   p.off_b = p.SA * p.a_bytes;
-  p.off_bar = (p.off_b + p.SB * p.b_bytes + 127u) & ~127u;
-  p.smem_bytes = p.off_bar + bar_bytes;
-  if (p.tmem_cols > 256 && p.smem_bytes < 120u * 1024) p.smem_bytes = 120u * 1024;   // one CTA per SM: TMEM has 512 columns
+  p.off_bar = (p.off_b + (p.resident_b ? p.w_bytes : p.SB * p.b_bytes) + 127u) & ~127u;
+  p.off_bias = (p.off_bar + bar_bytes + 15u) & ~15u;
+  p.smem_bytes = p.off_bias + (uint32_t)p.Cout * 4u;
+  int per_sm = (int)((227u * 1024) / (p.smem_bytes + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  // TMEM: 512 columns per SM shared by the co-resident CTAs; as many accumulator buffers as fit (>= 2, <= 8)
+  int nacc = (512 / per_sm) / p.Nblk;
+  if (nacc < 2) { per_sm = 1; nacc = 512 / p.Nblk; }
+  p.NACC = nacc > kMaxAcc ? kMaxAcc : nacc;
+  int cols = 32;
+  while (cols < p.NACC * p.Nblk) cols *= 2;
+  p.tmem_cols = cols;
+  // request enough shared memory that no more than per_sm CTAs can ever share an SM (their TMEM would not fit)
+  const uint32_t min_smem = (227u * 1024) / (uint32_t)(per_sm + 1) + 1024u;
+  if (p.smem_bytes < min_smem) p.smem_bytes = min_smem;
+  p.ctas_per_sm = per_sm;
   p.n_tiles = (c.R + kTileM - 1) / kTileM;
+  p.n_super = (p.n_tiles + p.MT - 1) / p.MT;
   *out = p;
   return VS_OK;
 }
@@ -398,13 +577,9 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  int per_sm = (int)((227u * 1024) / (prm.p.smem_bytes + 1024));
-  const int tmem_limit = 512 / prm.p.tmem_cols;
-  if (per_sm > tmem_limit) per_sm = tmem_limit;
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
+  const int per_sm = prm.p.ctas_per_sm;
   int grid = n_sm * per_sm;
-  if (grid > prm.p.n_tiles) grid = prm.p.n_tiles;
+  if (grid > prm.p.n_super) grid = prm.p.n_super;
   umma_conv1d_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
   VS_LAUNCH_CHECK();
   return VS_OK;

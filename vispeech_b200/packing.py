@@ -49,6 +49,15 @@ def ups_union_taps(i: int) -> Tuple[int, int]:
     return hi - lo + 1, -lo
 
 
+def up_columns(cout: int, s: int) -> torch.Tensor:
+    """GEMM column of (phase ph, channel co) for a polyphase ConvTranspose1d in csrc/umma_conv.cu:
+    col = (co // 8) * 8 * s + ph * 8 + co % 8, so that one epilogue thread writes the s phases of a channel
+    group to s consecutive output rows (s * 16 contiguous bytes).  Returns index [s * cout] (phase-major input)."""
+    ph = torch.arange(s).repeat_interleave(cout)
+    co = torch.arange(cout).repeat(s)
+    return (co // 8) * 8 * s + ph * 8 + co % 8
+
+
 def pack_umma(w: torch.Tensor) -> torch.Tensor:
     """[taps][Cin][N] fp32 -> bf16 [NB][taps][Cin/KC][KC/8][Nblk][8] (csrc/umma_conv.cuh)."""
     taps, cin, n = w.shape
@@ -153,13 +162,14 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
         per = torch.zeros(s, K // s, cin, cout)
         taps, pad_l = ups_union_taps(i)
         uni = torch.zeros(taps, cin, s * cout)
+        cols = up_columns(cout, s)
         for ph in range(s):
             lo, hi = ups_phase_range(i, ph)
             for t, d in enumerate(range(lo, hi + 1)):
                 k = ph + pad - s * d
                 assert 0 <= k < K
                 per[ph, t] = wt[:, :, k]
-                uni[d + pad_l, :, ph * cout:(ph + 1) * cout] = wt[:, :, k]
+                uni[d + pad_l, :, cols[ph * cout:(ph + 1) * cout]] = wt[:, :, k]
         out["dec.ups.%d.w" % i] = per.contiguous()
         out["dec.ups.%d.b" % i] = sd["dec.ups.%d.bias" % i]
         out["dec16.ups.%d.w" % i] = pack_umma(uni)
