@@ -7,7 +7,7 @@ import torch
 from vispeech_b200 import _lib
 from vispeech_b200._lib import check, ptr
 from vispeech_b200.layout import make_rows
-from vispeech_b200.packing import pack_umma
+from vispeech_b200.packing import pack_tf32, pack_umma, round_tf32
 
 DEV = "cuda:0"
 
@@ -58,6 +58,18 @@ def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=N
     out = torch.full((R, cout), float("nan"), dtype=torch.float32, device=x.device)
     check(lib.vs_op_conv1d_f32(ptr(x), cin, ptr(w_tcn), ptr(bias), ptr(out), cout, R, cin, cout, k, dil, pad_l,
                                float(in_slope), act, ptr(row_utt), row_div, stream()), "vs_op_conv1d_f32")
+    torch.cuda.synchronize()
+    return out
+
+
+def conv_tf32(x, w_tcn, bias=None, dil=1, pad_l=0, act=0, row_utt=None):
+    lib = _lib.load()
+    R, cin = x.shape
+    k, _, cout = w_tcn.shape
+    wp = pack_tf32(w_tcn.cpu()).to(x.device)
+    out = torch.full((R, cout), float("nan"), dtype=torch.float32, device=x.device)
+    check(lib.vs_op_conv1d_tf32(ptr(x), cin, ptr(wp), ptr(bias), ptr(out), cout, R, cin, cout, k, dil, pad_l, act,
+                                ptr(row_utt), stream()), "vs_op_conv1d_tf32")
     torch.cuda.synchronize()
     return out
 

@@ -23,6 +23,16 @@ def net(state_dict):
     return n
 
 
+@pytest.fixture
+def force_tf32():
+    """Run every eligible conv on the TF32 tensor-core kernel regardless of the row count."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.vs_set_option(b"tf32_min_rows", 1))
+    yield
+    _lib.check(lib.vs_set_option(b"tf32_min_rows", 4096))
+
+
 def _control(d, name):
     kind = int(d[name + "_kind"])
     if kind == 0:
@@ -70,6 +80,48 @@ def test_infer_matches_reference_golden(net, path, precision):
     assert o.shape == (1, 1, o_ref.numel())
     snr = snr_db(o_ref, o[0, 0].cpu())
     assert snr >= (50.0 if precision == 1 else 30.0), snr
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_infer_matches_reference_golden_tf32(net, path, force_tf32):
+    """Same golden cases with the frame-level AND phoneme-level GEMMs forced onto the TF32 tensor-core kernel + bf16
+    decoder: the product precision for large batches.  Bars of BASELINE.json: latents <= 1e-2, waveform SNR >= 30 dB."""
+    d = dict(np.load(path))
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = run_golden(net, d, 0)
+    assert x_mask[0, 0].cpu().numpy().tolist() == d["x_mask"].tolist()
+    for name, got in (("m_p", m_p), ("z", z)):
+        err = float(np.abs(got[0].cpu().numpy() - d[name]).max())
+        assert err <= 1e-2, (name, err)
+    o_ref = torch.from_numpy(d["o"].astype(np.float32))
+    if int(d["o_is_f16x64"]):
+        o_ref = o_ref / 64
+    assert snr_db(o_ref, o[0, 0].cpu()) >= 30.0
+
+
+def test_large_batch_uses_tensor_cores_and_matches_oracle(net, state_dict):
+    """12 utterances x ~5 s = ~5200 frame rows: above the TF32 threshold, so flow / frame prior / projection run on
+    tcgen05 kind::tf32 and the decoder on kind::f16, exactly as in the benchmark.  Compared per utterance with the oracle."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import infer_one
+    utts = oin.c2(batch=12, seed=9)
+    frames = oin.frame_counts(utts)
+    assert sum(frames) + 4 * 12 >= 4096
+    noises = oin.draw_noise(frames, 21)
+    ids = torch.stack([u["ids"] for u in utts])
+    dur = torch.stack([u["duration"] for u in utts])
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = net.infer(
+        ids, torch.LongTensor([40] * 12), sid=torch.LongTensor([u["sid"] for u in utts]), noise_scale=0.667,
+        duration_control=dur, noise=noises)
+    torch.cuda.synchronize()
+    worst = {"z": 0.0, "m_p": 0.0, "snr": 1e9}
+    for b in (0, 5, 11):
+        ref = infer_one(state_dict, utts[b]["ids"], utts[b]["sid"], 0.667, noises[b], duration_control=utts[b]["duration"])
+        tf = frames[b]
+        worst["z"] = max(worst["z"], float((z[b, :, :tf].cpu() - ref["z"]).abs().max()))
+        worst["m_p"] = max(worst["m_p"], float((m_p[b, :, :tf].cpu() - ref["m_p"]).abs().max()))
+        worst["snr"] = min(worst["snr"], snr_db(ref["o"], o[b, 0, :tf * 512].cpu()))
+    print("large batch worst-case:", worst)
+    assert worst["z"] <= 1e-2 and worst["m_p"] <= 1e-2 and worst["snr"] >= 30.0, worst
 
 
 def test_latents_are_fp32_tight_on_golden(net):

@@ -98,6 +98,31 @@ def test_conv_f32_matches_cpu(G, R, cin, cout, k, dil):
     assert (out.cpu().double() - ref).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("R,cin,cout,k,dil,act", [(300, 192, 576, 1, 1, 0), (1000, 192, 768, 3, 1, 1), (260, 768, 192, 3, 1, 0),
+                                                 (500, 96, 192, 1, 1, 0), (700, 192, 384, 5, 1, 0), (129, 192, 96, 1, 1, 0),
+                                                 (4100, 192, 192, 1, 1, 0)])
+def test_conv_tf32_matches_cpu(G, R, cin, cout, k, dil, act):
+    """TF32 tensor-core conv (operands rounded to 10-bit mantissa, fp32 accumulate) vs fp64 on the same rounded
+    operands (tolerance: fp32 accumulation), and vs un-rounded fp64 (tolerance: TF32 operand rounding, 2^-11 relative
+    per operand -> ~1e-3 of the output scale)."""
+    from vispeech_b200.packing import round_tf32
+    g = torch.Generator().manual_seed(k * 7 + cout)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(k, cin, cout, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    row_utt[5:9] = -1
+    out = G.conv_tf32(x.to(G.DEV), w, b.to(G.DEV), dil=dil, pad_l=(k - 1) // 2, act=act, row_utt=row_utt.to(G.DEV)).cpu().double()
+    ref_r = G.ref_conv_rows(round_tf32(x), round_tf32(w), b, dil=dil, pad_l=(k - 1) // 2)
+    ref = G.ref_conv_rows(x, w, b, dil=dil, pad_l=(k - 1) // 2)
+    if act:
+        ref_r, ref = ref_r.clamp_min(0), ref.clamp_min(0)
+    ref_r[5:9] = 0
+    ref[5:9] = 0
+    assert (out - ref_r).abs().max().item() <= 2e-4
+    assert (out - ref).abs().max().item() <= 5e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_layernorm_rows(G):
     from vispeech_b200 import _lib
     lib = _lib.load()

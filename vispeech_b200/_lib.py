@@ -29,6 +29,7 @@ _SIGNATURES = {
     "vs_last_error": (c_char_p, []),
     "vs_version": (c_int32, []),
     "vs_launch_count": (c_int64, []),
+    "vs_set_option": (c_int32, [c_char_p, c_int64]),
     "vs_model_create": (c_int32, [POINTER(VsConfig), POINTER(c_void_p)]),
     "vs_model_destroy": (None, [c_void_p]),
     "vs_model_set_tensor": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_int32]),
@@ -51,6 +52,8 @@ _SIGNATURES = {
                                    c_int32, c_int32, c_int32, c_float, c_int32, c_void_p, c_int32, c_void_p]),
     "vs_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "vs_op_rel_attention": (c_int32, [POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vs_op_conv1d_tf32": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "vs_op_conv1d_umma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
 }

@@ -7,6 +7,7 @@
 #include "ops_misc.cuh"
 #include "decoder.cuh"
 #include "umma_conv.cuh"
+#include "umma_tf32.cuh"
 
 namespace vs {
 
@@ -14,11 +15,31 @@ struct Tensor { const void* ptr; int64_t numel; int32_t dtype; };
 
 struct EncLayer {
   const float *wqkv, *bqkv, *wo, *bo, *ek, *ev, *g1, *b1, *g2, *b2, *w1, *bf1, *w2, *bf2;
+  const float *t_wqkv, *t_wo, *t_w1, *t_w2;            // TF32 slab copies (umma_tf32.cuh)
 };
 struct FlowW {
   const float *pre_w, *pre_b, *post_w, *post_b, *cond_tab;
   const float *in_w[8], *in_b[8], *rs_w[8], *rs_b[8];
+  const float *t_pre, *t_post, *t_in[8], *t_rs[8];     // TF32 slab copies
 };
+
+// Rows below this run the fp32 CUDA-core conv (a handful of 128-row tiles cannot fill 148 SMs, and the phoneme-level
+// predictors keep full fp32); above it the conv runs on the tensor cores in TF32.
+constexpr int kTf32MinRowsDefault = 4096;
+static int g_tf32_min_rows = kTf32MinRowsDefault;      // vs_set_option("tf32_min_rows", n); tests force n = 1
+
+// conv through the TF32 tensor-core kernel when eligible, else the fp32 CUDA-core kernel (same arguments)
+static int conv_rows(const ConvF32& c, const float* w_tf32, cudaStream_t st) {
+  const bool eligible = w_tf32 && c.R >= g_tf32_min_rows && !c.res && !c.accumulate && c.in_slope == 1.f &&
+                        c.out_row_mul == 1 && c.out_row_off == 0 && c.out_scale == 1.f && c.act <= 1 && c.row_div == 1 &&
+                        c.Cin % 32 == 0 && c.Cout % 32 == 0;
+  if (!eligible) return conv1d_f32(c, st);
+  UmmaTf32 u;
+  u.in = c.in; u.in_ld = c.in_ld; u.w = w_tf32; u.bias = c.bias; u.ubias = c.ubias; u.ubias_ld = c.ubias_ld;
+  u.ubias_idx = c.ubias_idx; u.out = c.out; u.out_ld = c.out_ld; u.row_utt = c.row_utt; u.R = c.R; u.Cin = c.Cin;
+  u.N = c.Cout; u.taps = c.k; u.dil = c.dil; u.pad_l = c.pad_l; u.act = c.act;
+  return umma_tf32(u, st);
+}
 
 }  // namespace vs
 
@@ -33,7 +54,7 @@ struct VsModel {
   const float *pp_cond, *pp_wf0, *pp_bf0;
   const float *ep_cond, *ep_w1, *ep_b1, *ep_g1, *ep_be1, *ep_w2, *ep_b2, *ep_g2, *ep_be2, *ep_wl, *ep_bl;
   const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
-  const float *proj_w, *proj_b;
+  const float *proj_w, *proj_b, *t_proj_w;
   std::vector<vs::FlowW> flows;
   vs::DecoderW dec;
 };
@@ -66,6 +87,8 @@ static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::
     FETCH_F32(L.g2, q + "g2", H);  FETCH_F32(L.b2, q + "b2", H);
     FETCH_F32(L.w1, q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.bf1, q + "bf1", F);
     FETCH_F32(L.w2, q + "w2", (int64_t)3 * F * H);      FETCH_F32(L.bf2, q + "bf2", H);
+    FETCH_F32(L.t_wqkv, "tf32." + q + "wqkv", (int64_t)H * 3 * H);  FETCH_F32(L.t_wo, "tf32." + q + "wo", (int64_t)H * H);
+    FETCH_F32(L.t_w1, "tf32." + q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.t_w2, "tf32." + q + "w2", (int64_t)3 * F * H);
   }
   return VS_OK;
 }
@@ -93,6 +116,7 @@ static int finalize(VsModel* m) {
   FETCH_F32(m->pitch_pre_w, "pitch_prenet.w", H * 3);   FETCH_F32(m->pitch_pre_b, "pitch_prenet.b", H);
   FETCH_F32(m->energy_pre_w, "energy_prenet.w", H * 3); FETCH_F32(m->energy_pre_b, "energy_prenet.b", H);
   FETCH_F32(m->proj_w, "proj.w", H * 2 * H);   FETCH_F32(m->proj_b, "proj.b", 2 * H);
+  FETCH_F32(m->t_proj_w, "tf32.proj.w", H * 2 * H);
   const int L = m->cfg.flow_layers;
   m->flows.resize(m->cfg.n_flows);
   for (int f = 0; f < m->cfg.n_flows; ++f) {
@@ -101,11 +125,13 @@ static int finalize(VsModel* m) {
     FETCH_F32(w.pre_w, p + "pre.w", (H / 2) * H);   FETCH_F32(w.pre_b, p + "pre.b", H);
     FETCH_F32(w.post_w, p + "post.w", H * (H / 2)); FETCH_F32(w.post_b, p + "post.b", H / 2);
     FETCH_F32(w.cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
+    FETCH_F32(w.t_pre, "tf32." + p + "pre.w", (H / 2) * H);   FETCH_F32(w.t_post, "tf32." + p + "post.w", H * (H / 2));
     for (int l = 0; l < L; ++l) {
       const std::string q = p + std::to_string(l) + ".";
       const int rs = (l < L - 1) ? 2 * H : H;
       FETCH_F32(w.in_w[l], q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.in_b[l], q + "in.b", 2 * H);
       FETCH_F32(w.rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w.rs_b[l], q + "rs.b", rs);
+      FETCH_F32(w.t_in[l], "tf32." + q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.t_rs[l], "tf32." + q + "rs.w", H * rs);
     }
   }
   VS_TRY(resolve_decoder(
@@ -130,15 +156,15 @@ static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& ro
     ConvF32 c;
     c.R = R; c.row_utt = rows.row_utt;
     c.in = x; c.in_ld = H; c.Cin = H; c.w = L.wqkv; c.bias = L.bqkv; c.out = qkv; c.out_ld = 3 * H; c.Cout = 3 * H;
-    VS_TRY(conv1d_f32(c, st));                                             // conv_q|k|v (attentions.py:139-141)
+    VS_TRY(conv_rows(c, L.t_wqkv, st));                                    // conv_q|k|v (attentions.py:139-141)
     VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st));                 // attentions.py:148-179
     c.in = att; c.w = L.wo; c.bias = L.bo; c.out = y; c.out_ld = H; c.Cout = H;
-    VS_TRY(conv1d_f32(c, st));                                             // conv_o
+    VS_TRY(conv_rows(c, L.t_wo, st));                                      // conv_o
     VS_TRY(layernorm_rows(x, y, L.g1, L.b1, x, R, H, rows.row_utt, st));   // x = LN(x + y)
     c.in = x; c.Cin = H; c.w = L.w1; c.bias = L.bf1; c.out = hbuf; c.out_ld = F; c.Cout = F; c.k = 3; c.pad_l = 1; c.act = 1;
-    VS_TRY(conv1d_f32(c, st));                                             // FFN conv_1 + relu (attentions.py:278-282)
+    VS_TRY(conv_rows(c, L.t_w1, st));                                      // FFN conv_1 + relu (attentions.py:278-282)
     c.in = hbuf; c.in_ld = F; c.Cin = F; c.w = L.w2; c.bias = L.bf2; c.out = y; c.out_ld = H; c.Cout = H; c.act = 0;
-    VS_TRY(conv1d_f32(c, st));                                             // FFN conv_2
+    VS_TRY(conv_rows(c, L.t_w2, st));                                      // FFN conv_2
     VS_TRY(layernorm_rows(x, y, L.g2, L.b2, x, R, H, rows.row_utt, st));
   }
   return VS_OK;
@@ -159,6 +185,17 @@ extern "C" {
 const char* vs_last_error(void) { return vs::last_error(); }
 int vs_version(void) { return 1; }
 int64_t vs_launch_count(void) { return (int64_t)vs::g_launch_count; }
+
+int vs_set_option(const char* name, int64_t value) {
+  VS_REQUIRE(name, "vs_set_option: null name");
+  if (std::string(name) == "tf32_min_rows") {
+    VS_REQUIRE(value >= 1, "vs_set_option: tf32_min_rows must be >= 1");
+    vs::g_tf32_min_rows = (int)value;
+    return VS_OK;
+  }
+  vs::set_error("vs_set_option: unknown option '%s'", name);
+  return VS_ERR_INVALID;
+}
 
 int vs_model_create(const VsConfig* cfg, VsModel** out) {
   VS_REQUIRE(cfg && out, "vs_model_create: null argument");
@@ -303,7 +340,7 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   ConvF32 c;                                                               // Projection.forward models.py:526-529
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
-  VS_TRY(conv1d_f32(c, st));
+  VS_TRY(conv_rows(c, m->t_proj_w, st));
   return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 
@@ -326,22 +363,22 @@ int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, in
     ConvF32 c;
     c.R = R; c.row_utt = rows->row_utt;
     c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;
-    VS_TRY(conv1d_f32(c, st));                                             // h = pre(x0) * mask  (modules.py:326)
+    VS_TRY(conv_rows(c, w.t_pre, st));                                     // h = pre(x0) * mask  (modules.py:326)
     for (int l = 0; l < L; ++l) {                                          // WN.forward (modules.py:148-176)
       const int rsC = (l < L - 1) ? 2 * H : H;
       c = ConvF32(); c.R = R;
       c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = a; c.out_ld = 2 * H; c.Cout = 2 * H;
       c.k = 5; c.pad_l = 2;
-      VS_TRY(conv1d_f32(c, st));
+      VS_TRY(conv_rows(c, w.t_in[l], st));
       VS_TRY(wn_gate(a, w.cond_tab, 2 * H * L, 2 * H * l, *rows, acts, st));
       c = ConvF32(); c.R = R;
       c.in = acts; c.in_ld = H; c.Cin = H; c.w = w.rs_w[l]; c.bias = w.rs_b[l]; c.out = rs; c.out_ld = rsC; c.Cout = rsC;
-      VS_TRY(conv1d_f32(c, st));
+      VS_TRY(conv_rows(c, w.t_rs[l], st));
       VS_TRY(wn_update(rs, rsC, l == L - 1, l == 0, *rows, h, skip, st));
     }
     c = ConvF32(); c.R = R;
     c.in = skip; c.in_ld = H; c.Cin = H; c.w = w.post_w; c.bias = w.post_b; c.out = mm; c.out_ld = H / 2; c.Cout = H / 2;
-    VS_TRY(conv1d_f32(c, st));                                             // m = post(h) (modules.py:328)
+    VS_TRY(conv_rows(c, w.t_post, st));                                    // m = post(h) (modules.py:328)
     VS_TRY(coupling_sub(z, upd_off, mm, *rows, st));                       // x1 = (x1 - m) * mask (modules.py:341)
   }
   return VS_OK;
@@ -380,6 +417,15 @@ int vs_op_rel_attention(const VsRows* rows, const float* qkv, const float* emb_r
                         float* out, void* stream) {
   VS_TRY(check_rows(rows, "vs_op_rel_attention"));
   return rel_attention(*rows, qkv, emb_rel_k, emb_rel_v, out, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,
+                      int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
+                      const int32_t* row_utt, void* stream) {
+  UmmaTf32 u;
+  u.in = in; u.in_ld = in_ld; u.w = w_packed; u.bias = bias; u.out = out; u.out_ld = out_ld; u.row_utt = row_utt;
+  u.R = n_rows; u.Cin = c_in; u.N = c_out; u.taps = taps; u.dil = dil; u.pad_l = pad_l; u.act = act;
+  return umma_tf32(u, static_cast<cudaStream_t>(stream));
 }
 
 int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,

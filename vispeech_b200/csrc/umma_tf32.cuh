@@ -1,0 +1,22 @@
+// TF32 tcgen05 conv over fp32 row-major ragged rows.  See umma_tf32.cu.
+#pragma once
+#include "common.cuh"
+
+namespace vs {
+
+// Weights: fp32 words already rounded to TF32, slabs [NB][Cin/96][taps][3][8 planes][Nblk][4]:
+// element (nb, ka, t, j, p, n, e) = W[t][96*ka + 32*j + 4*p + e][nb*Nblk + n]   (packing.py pack_tf32)
+struct UmmaTf32 {
+  const float* in = nullptr; int in_ld = 0;          // [R][in_ld], channel offset folded into the pointer
+  const float* w = nullptr;
+  const float* bias = nullptr;                       // [N] or null
+  const float* ubias = nullptr; int ubias_ld = 0;    // optional per-speaker bias rows (column offset folded in)
+  const int32_t* ubias_idx = nullptr;                // [n_utt] -> row of ubias (sid)
+  float* out = nullptr; int out_ld = 0;              // [R][out_ld]
+  const int32_t* row_utt = nullptr;                  // null = every row valid; invalid rows are written as zeros
+  int R = 0, Cin = 0, N = 0, taps = 1, dil = 1, pad_l = 0;
+  int act = 0;                                       // 0 none, 1 relu
+};
+int umma_tf32(const UmmaTf32& c, cudaStream_t st);
+
+}  // namespace vs

@@ -69,6 +69,23 @@ def pack_umma(w: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).reshape(-1)
 
 
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 (10-bit mantissa), kept in fp32 words (what tcgen05 kind::tf32 reads)."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_tf32(w: torch.Tensor) -> torch.Tensor:
+    """[taps][Cin][N] fp32 -> TF32 slabs [NB][Cin/KA][taps][KA/32][8][Nblk][4] (csrc/umma_tf32.cuh), KA = min(Cin, 96)."""
+    taps, cin, n = w.shape
+    ka = min(cin, 96)
+    assert cin % ka == 0 and ka % 32 == 0
+    nblk = next(n // nb for nb in range(1, 9) if n % nb == 0 and n // nb <= 256 and (n // nb) % 32 == 0)
+    x = round_tf32(w).reshape(taps, cin // ka, ka // 32, 8, 4, n // nblk, nblk)
+    #                      t     ka         j        p  e   nb         n
+    return x.permute(5, 1, 0, 2, 3, 6, 4).contiguous().reshape(-1)
+
+
 def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_flows=4, flow_layers=4) -> Dict[str, torch.Tensor]:
     """Returns {packed name: CPU tensor (fp32 or bf16, contiguous)}."""
     sd = {k: v.detach().float().cpu() for k, v in sd.items()}
@@ -181,4 +198,10 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
                     out["dec.rb.%d.%s.%d.w" % (n, cname, m)] = w
                     out["dec.rb.%d.%s.%d.b" % (n, cname, m)] = sd["dec.resblocks.%d.%s.%d.bias" % (n, key, m)]
                     out["dec16.rb.%d.%s.%d.w" % (n, cname, m)] = pack_umma(w)
+    # TF32 tensor-core copies of the frame-level GEMM weights (flow, encoders, projection)
+    for name in list(out):
+        if name.endswith((".wqkv", ".wo")) or name == "proj.w" or name.endswith(("pre.w", "post.w", "rs.w")) and name.startswith("flow."):
+            out["tf32." + name] = pack_tf32(out[name][None])
+        elif (name.endswith((".w1", ".w2")) and not name.startswith(("dp.", "ep."))) or (name.endswith("in.w") and name.startswith("flow.")):
+            out["tf32." + name] = pack_tf32(out[name])
     return {k: v.contiguous() for k, v in out.items()}
