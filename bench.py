@@ -258,7 +258,8 @@ def main():
                                    "pitch/energy, noise_scale .667), random-init configs/config.json seed 1234" % args.batch,
                        "utterances_per_gpu": args.batch, "valid_frames_per_gpu": int(sum(frames)),
                        "audio_s_per_step_all_gpus": audio_all, "parallelism": "utterance-sharded x%d, no collectives" % world,
-                       "precision": "decoder bf16 operands / fp32 accumulate (tcgen05); everything upstream fp32",
+                       "precision": "decoder: bf16 operands, fp32 accumulate (tcgen05 kind::f16); flow / frame-prior / projection GEMMs: "
+                                    "TF32 (tcgen05 kind::tf32); phoneme-level encoder + predictors: fp32 CUDA cores",
                        "l2": "per-step activations (~%.1f GB) >> 126 MB L2; no explicit flush needed" % (
                            sum(frames) * 112 * 16384 * 2 / 1e9 / 16)},
             "p50_rtf": rtf[len(rtf) // 2],

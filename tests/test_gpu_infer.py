@@ -103,6 +103,10 @@ def test_large_batch_uses_tensor_cores_and_matches_oracle(net, state_dict):
     tcgen05 kind::tf32 and the decoder on kind::f16, exactly as in the benchmark.  Compared per utterance with the oracle."""
     from oracle import inputs as oin
     from oracle.vispeech_oracle import infer_one
+    import os
+    if os.environ.get("VS_TF32_MIN_ROWS"):
+        from vispeech_b200 import _lib
+        _lib.check(_lib.load().vs_set_option(b"tf32_min_rows", int(os.environ["VS_TF32_MIN_ROWS"])))
     utts = oin.c2(batch=12, seed=9)
     frames = oin.frame_counts(utts)
     assert sum(frames) + 4 * 12 >= 4096

@@ -310,8 +310,38 @@ __global__ void unpack_rows_kernel(VsRows rows, const float* __restrict__ x, int
     if (c < C && t < t_max) out[((size_t)b * C + c) * t_max + t] = tile[threadIdx.x][i];
   }
 }
+// C == 1 (the waveform): no transpose, a masked contiguous copy per utterance, 4 samples per thread
+__global__ void unpack_wave_kernel(VsRows rows, const float* __restrict__ x, int mul, int t_max, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int len = rows.utt_len[b] * mul;
+  const size_t start = (size_t)rows.utt_start[b] * mul;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t >= t_max) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t + 3 < len) v = *reinterpret_cast<const float4*>(x + start + t);
+  else {
+    if (t + 0 < len) v.x = x[start + t + 0];
+    if (t + 1 < len) v.y = x[start + t + 1];
+    if (t + 2 < len) v.z = x[start + t + 2];
+  }
+  float* o = out + (size_t)b * t_max + t;
+  if (t + 3 < t_max) *reinterpret_cast<float4*>(o) = v;
+  else {
+    o[0] = v.x;
+    if (t + 1 < t_max) o[1] = v.y;
+    if (t + 2 < t_max) o[2] = v.z;
+  }
+}
+
 int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st) {
   VS_REQUIRE(t_max > 0 && C > 0, "unpack_rows: empty output");
+  if (C == 1 && mul % 4 == 0 && t_max % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    dim3 grid((t_max / 4 + 255) / 256, rows.n_utt);
+    unpack_wave_kernel<<<grid, 256, 0, st>>>(rows, x, mul, t_max, out);
+    VS_LAUNCH_CHECK();
+    return VS_OK;
+  }
   dim3 grid((t_max + 31) / 32, (C + 31) / 32, rows.n_utt);
   unpack_rows_kernel<<<grid, dim3(32, 8), 0, st>>>(rows, x, C, mul, t_max, out);
   VS_LAUNCH_CHECK();
