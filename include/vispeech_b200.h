@@ -75,7 +75,8 @@ const char* vs_last_error(void);
 int vs_version(void);
 int64_t vs_launch_count(void);
 /* process-wide knobs. "tf32_min_rows": convs over at least this many rows run on the tensor cores in TF32 (default
- * 4096; fewer rows stay on the fp32 CUDA-core kernel).  Used by the parity tests to force either path. */
+ * 4096; fewer rows stay on the fp32 CUDA-core kernel).  Used by the parity tests to force either path.
+ * "fused_respair": 1 = run C<=64 ResBlock iterations through the experimental fused kernel (default 0). */
 int vs_set_option(const char* name, int64_t value);   /* kernels launched by this library so far (process-wide) */
 
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
@@ -150,6 +151,11 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
                       void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
                       const int32_t* row_utt, int32_t row_div, void* stream);
+
+/* fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x (+ res2) on planar bf16 rows (csrc/umma_respair.cu) */
+int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
+                  const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
+                  int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream);
 
 #ifdef __cplusplus
 }

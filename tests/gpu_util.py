@@ -51,6 +51,22 @@ def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0
     return (from_planar(raw) if want_raw else None), (from_planar(act) if want_act else None)
 
 
+def respair(x, w1, w2, b1, b2, dil, res2=None, act_slope=1.0, act_scale=1.0, row_utt=None, row_div=1):
+    """Fused ResBlock1 iteration on planar bf16 rows.  x [R][C] fp32 device, w [k][C][C].  Returns (raw, act) [R][C]."""
+    lib = _lib.load()
+    R, C = x.shape
+    k = w1.shape[0]
+    xin = to_planar(x)
+    w1p, w2p = pack_umma(w1.cpu()).to(x.device), pack_umma(w2.cpu()).to(x.device)
+    r2 = to_planar(res2) if res2 is not None else None
+    raw = torch.full((C // 8, R, 8), float("nan"), dtype=torch.bfloat16, device=x.device)
+    act = torch.full((C // 8, R, 8), float("nan"), dtype=torch.bfloat16, device=x.device)
+    check(lib.vs_op_respair(ptr(xin), ptr(w1p), ptr(w2p), ptr(b1), ptr(b2), ptr(r2), ptr(raw), ptr(act), R, C, k, dil,
+                            float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()), "vs_op_respair")
+    torch.cuda.synchronize()
+    return from_planar(raw), from_planar(act)
+
+
 def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=None, row_div=1):
     lib = _lib.load()
     R, cin = x.shape

@@ -59,6 +59,38 @@ def test_umma_conv_residual_mask_and_scale(G):
     assert raw[160:200].abs().max().item() == 0 and act[160:200].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("R,C,k,dil", [(1000, 32, 3, 1), (777, 32, 11, 5), (1500, 32, 7, 3), (600, 64, 3, 5), (129, 32, 11, 1),
+                                      (246 * 3, 32, 11, 3)])
+def test_fused_resblock_pair_matches_cpu(G, R, C, k, dil):
+    """y = c2(lrelu(c1(lrelu(x)))) + x (modules.py:211-220) in one kernel vs an fp64 chain with the same bf16 roundings
+    (input, lrelu(x), the intermediate), incl. a masked gap (rows that must act as zero padding for BOTH convs)."""
+    g = torch.Generator().manual_seed(R + k)
+    x = torch.randn(R, C, generator=g)
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    row_utt[300:340] = -1
+    x[300:340] = 0                                       # ragged-rows invariant: gap rows of the input are zero
+    w1 = torch.randn(k, C, C, generator=g) / (k * C) ** 0.5
+    w2 = torch.randn(k, C, C, generator=g) / (k * C) ** 0.5
+    b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    res2 = torch.randn(R, C, generator=g)
+    raw, act = G.respair(x.to(G.DEV), w1, w2, b1.to(G.DEV), b2.to(G.DEV), dil, res2=res2.to(G.DEV), act_slope=0.01,
+                         act_scale=1 / 3, row_utt=row_utt.to(G.DEV))
+    xb = G.bf16_round(x).double()
+    a1 = G.bf16_round(torch.where(xb > 0, xb, 0.1 * xb).float())
+    c1 = G.ref_conv_rows(a1, G.bf16_round(w1), b1, dil=dil, pad_l=(k - 1) // 2)
+    t = G.bf16_round(torch.where(c1 > 0, c1, 0.1 * c1).float())
+    t[300:340] = 0
+    y = G.ref_conv_rows(t, G.bf16_round(w2), b2, dil=1, pad_l=(k - 1) // 2) + xb + G.bf16_round(res2).double()
+    y[300:340] = 0
+    scale = y.abs().max().item()
+    assert (raw.cpu().double() - y).abs().max().item() <= 2e-2 * scale
+    ya = y / 3
+    ya = torch.where(ya > 0, ya, 0.01 * ya)
+    assert (act.cpu().double() - ya).abs().max().item() <= 2e-2 * scale
+    if R > 340:
+        assert raw[300:340].abs().max().item() == 0
+
+
 @pytest.mark.parametrize("stage", [0, 2, 3])
 def test_umma_conv_transpose_polyphase(G, stage):
     """ConvTranspose1d (models.py:257-259) as a polyphase UMMA conv vs F.conv_transpose1d."""

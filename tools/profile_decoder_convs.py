@@ -62,3 +62,34 @@ for i, (s, K) in enumerate(zip((8, 8, 4, 2), (16, 16, 4, 4))):
             total += run("s%d c1 k%d d%d" % (i, k, d), R, cout, cout, k, d)
         total += run("s%d c2 k%d (res,2out)" % (i, k), R, cout, cout, k, 1, res=True, two_out=True, count=3)
 print("sum of decoder convs: %.2f ms" % total)
+
+
+def run_pair(name, R, C, k, d, count=1):
+    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    o = torch.empty_like(x)
+
+    def call():
+        check(lib.vs_op_respair(ptr(x), ptr(w1), ptr(w2), ptr(b1), ptr(b2), None, ptr(o), None, R, C, k, d, 1.0, 1.0, None, 1, st))
+    call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    flop = 2 * 2.0 * R * C * C * k
+    byts = 2.0 * R * C * 2
+    print("%-22s R=%9d C=%3d k=%2d d=%d  %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s" % (name, R, C, k, d, ms, flop / ms / 1e9, byts / ms / 1e6))
+
+
+if os.environ.get("PAIRS", "1") == "1":
+    for k in (3, 7, 11):
+        for d in (1, 3, 5):
+            run_pair("s3 pair k%d d%d" % (k, d), FRAMES * 512, 32, k, d)
+    for d in (1, 3, 5):
+        run_pair("s2 pair k3 d%d" % d, FRAMES * 256, 64, 3, d)

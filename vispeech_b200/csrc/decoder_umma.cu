@@ -119,8 +119,17 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     const int cin = kStageC[i], cout = kStageC[i + 1], s = kUpRate[i];
     int pad_l = 0;
     const int taps = ups_taps(i, &pad_l);
+    // which resblocks of this stage run as fused pairs on the raw stream (umma_respair.cu)?
+    bool fused[kDecKernels];
+    bool any_unfused = false;
+    for (int j = 0; j < kDecKernels; ++j) {
+      fused[j] = true;
+      for (int mth = 0; mth < kDecDils; ++mth) fused[j] = fused[j] && umma_respair_supported(cout, kResK[j], kResD[mth]);
+      any_unfused = any_unfused || !fused[j];
+    }
     c = UmmaConv();
-    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = XR; c.out_act = XA; c.act_slope = 0.1f;
+    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = XR; c.out_act = any_unfused ? XA : nullptr;
+    c.act_slope = 0.1f;
     c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
     c.up = s;
     VS_TRY(umma_conv1d(c, st));                                          // ups[i] (ConvTranspose1d)  models.py:277
@@ -128,6 +137,25 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     const int Rs = R * mul;
     for (int j = 0; j < kDecKernels; ++j) {
       const int n = i * kDecKernels + j, k = kResK[j];
+      const float final_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;    // final lrelu uses the default slope (Q3)
+      if (fused[j]) {
+        const __nv_bfloat16* cur = XR;
+        for (int mth = 0; mth < kDecDils; ++mth) {
+          const bool last = (mth == kDecDils - 1);
+          UmmaPair pr;
+          pr.x = cur; pr.w1 = w.c1_16[n][mth].w; pr.b1 = w.c1_16[n][mth].b; pr.w2 = w.c2_16[n][mth].w; pr.b2 = w.c2_16[n][mth].b;
+          pr.row_utt = valid; pr.row_div = mul; pr.R = Rs; pr.C = cout; pr.taps = k; pr.dil = kResD[mth];
+          if (!last) pr.out_raw = (mth == 0) ? AR : BR;                  // x = c2(lrelu(c1(lrelu(x)))) + x  modules.py:211-220
+          else {
+            pr.res2 = (j > 0) ? S : nullptr;                             // xs += resblock_j(x)  models.py:280-284
+            if (j < kDecKernels - 1) pr.out_raw = S;
+            else { pr.out_act = NEXT; pr.act_scale = 1.f / kDecKernels; pr.act_slope = final_slope; }
+          }
+          VS_TRY(umma_respair(pr, st));
+          cur = (mth == 0) ? AR : BR;
+        }
+        continue;
+      }
       const __nv_bfloat16* cur_raw = XR;
       const __nv_bfloat16* cur_act = XA;
       for (int mth = 0; mth < kDecDils; ++mth) {
@@ -144,8 +172,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
           c.res2 = (j > 0) ? S : nullptr;                                // xs += resblock_j(x)  models.py:280-284
           if (j < kDecKernels - 1) { c.out_raw = S; c.out_act = nullptr; }
           else {                                                         // x = xs / 3, then the next stage's leaky_relu
-            c.out_raw = nullptr; c.out_act = NEXT; c.act_scale = 1.f / kDecKernels;
-            c.act_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;          // final lrelu uses the default slope (Q3)
+            c.out_raw = nullptr; c.out_act = NEXT; c.act_scale = 1.f / kDecKernels; c.act_slope = final_slope;
           }
         }
         VS_TRY(umma_conv1d(c, st));

@@ -193,6 +193,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_tf32_min_rows = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "fused_respair") {
+    vs::umma_respair_enable(value != 0);
+    return VS_OK;
+  }
   vs::set_error("vs_set_option: unknown option '%s'", name);
   return VS_ERR_INVALID;
 }
@@ -439,6 +443,18 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
   c.R = n_rows; c.Cin = c_in; c.N = n_cols; c.taps = taps; c.dil = dil; c.pad_l = pad_l; c.up = up;
   c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
   return umma_conv1d(c, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
+                  const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
+                  int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream) {
+  UmmaPair c;
+  c.x = static_cast<const __nv_bfloat16*>(x_planar); c.w1 = static_cast<const __nv_bfloat16*>(w1_packed);
+  c.w2 = static_cast<const __nv_bfloat16*>(w2_packed); c.b1 = b1; c.b2 = b2;
+  c.res2 = static_cast<const __nv_bfloat16*>(res2_planar); c.out_raw = static_cast<__nv_bfloat16*>(out_raw);
+  c.out_act = static_cast<__nv_bfloat16*>(out_act); c.R = n_rows; c.C = channels; c.taps = taps; c.dil = dil;
+  c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
+  return umma_respair(c, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -47,6 +47,10 @@ struct Params {
   Plan p;
 };
 
+// Epilogue feature flags (template parameter F of the kernel; F < 0 = all decided at run time)
+constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128;
+
+template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   const UmmaConv& c = prm.c;
@@ -246,16 +250,27 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     // Warp w may touch TMEM lanes [32*(w%4), +32).  Two warps share each lane quarter and take alternate
-    // column chunks, so 8 warps drain one accumulator; per-row facts (validity, utterance) are hoisted out of
-    // the column loop, bias comes from smem, residual loads are issued before the TMEM load is waited on.
+    // column chunks, so 8 warps drain one accumulator.  The small-C convs are bound by the SM's instruction issue
+    // rate in this loop (ncu: 2.5 of 4 IPC, 60 % of it here), so the feature set F is a template parameter and dead
+    // paths vanish: per 8-channel group the specialised code is ~2 LDS (bias) + 8 FADD + 16 FMUL/FMNMX + 4 F2FP
+    // + 1-2 STG.128 (+ LDG.128 and 16 unpack/add per residual).
+    constexpr bool kGeneric = F < 0;
+    const bool has_res = kGeneric ? (c.res != nullptr) : ((F & F_RES) != 0);
+    const bool has_res2 = kGeneric ? (c.res2 != nullptr) : ((F & F_RES2) != 0);
+    const bool has_ub = kGeneric ? (c.ubias != nullptr) : ((F & F_UBIAS) != 0);
+    const bool has_raw = kGeneric ? (c.out_raw != nullptr) : ((F & F_RAW) != 0);
+    const bool has_act = kGeneric ? (c.out_act != nullptr) : ((F & F_ACT) != 0);
+    const bool has_scale = kGeneric ? (c.act_scale != 1.f) : ((F & F_SCALE) != 0);
+    const bool has_up = kGeneric ? (c.up != 1) : ((F & F_UP) != 0);
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
-    const int CW = p.Nblk >= 64 ? 32 : 16;            // columns per tcgen05.ld
+    const int CW = (kGeneric ? (p.Nblk >= 64) : ((F & F_CW16) == 0)) ? 32 : 16;   // columns per tcgen05.ld
     const int n_chunks = p.Nblk / CW;
     uint32_t acc_slot = 0, acc_phase = 0;
     const int R_out = c.R * c.up;
     const uint32_t up_mask = (uint32_t)c.up - 1u;
-    const int plane_shift = 3 + p.up_shift;
+    const size_t plane_stride = (size_t)R_out * 8;          // elements between consecutive 8-channel planes
+    const float slope = c.act_slope, scale = c.act_scale;
     for (int super = blockIdx.x; super < p.n_super; super += gridDim.x)
     for (int tile = super * p.MT; tile < min(p.n_tiles, (super + 1) * p.MT); ++tile) {
       const int r = tile * kTileM + q * 32 + lane;
@@ -264,8 +279,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       if (in_range) utt = c.row_utt ? c.row_utt[(c.up * r) >> p.row_div_shift] : 0;
       const bool valid = utt >= 0;
       const float* ub = nullptr;
-      if (c.ubias && valid) ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.N;
-      const size_t row_base = (size_t)c.up * r;
+      if (has_ub && valid) ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.N;
+      const size_t row_elem = (size_t)c.up * r * 8;         // element offset of this thread's (first) output row in a plane
       for (int nb = 0; nb < n_units_per_tile; ++nb) {
         const int ab = (int)acc_slot;
         mbar_wait(acc_full(ab), acc_phase, 6);
@@ -273,31 +288,34 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Nblk);
         for (int cc = hsel; cc < n_chunks; cc += 2) {
           const int col0 = cc * CW;
-          const int n_groups = CW / 8;
+          const uint32_t g8 = (uint32_t)(nb * p.Nblk + col0) >> 3;        // index of the chunk's first 8-column group
+          // element offset of group g: plane * plane_stride + (up*r + phase) * 8
+          auto group_off = [&](int g) -> size_t {
+            const uint32_t gg = g8 + (uint32_t)g;
+            if (has_up) return (size_t)(gg >> p.up_shift) * plane_stride + row_elem + (size_t)(gg & up_mask) * 8;
+            return (size_t)gg * plane_stride + row_elem;
+          };
           uint4 rv[4], rv2[4];
-          if (valid && (c.res || c.res2)) {
+          if (valid && (has_res || has_res2)) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g < n_groups) {
-                const uint32_t gn0 = (uint32_t)(nb * p.Nblk + col0 + 8 * g);
-                const size_t o = ((size_t)(gn0 >> plane_shift) * R_out + row_base + ((gn0 >> 3) & up_mask)) * 8;
-                if (c.res) rv[g] = *reinterpret_cast<const uint4*>(c.res + o);
-                if (c.res2) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + o);
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 < CW) {
+                const size_t o = group_off(g);
+                if (has_res) rv[g] = *reinterpret_cast<const uint4*>(c.res + o);
+                if (has_res2) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + o);
               }
-            }
           }
           uint32_t v[32];
           if (CW == 32) tmem_ld32(t_row + (uint32_t)col0, v);
           else tmem_ld16(t_row + (uint32_t)col0, v);
           if (in_range) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g < n_groups) {
-                const uint32_t gn0 = (uint32_t)(nb * p.Nblk + col0 + 8 * g);
-                const uint32_t co0 = (gn0 >> plane_shift) << 3;
-                const size_t o = ((size_t)(gn0 >> plane_shift) * R_out + row_base + ((gn0 >> 3) & up_mask)) * 8;
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 < CW) {
+                const size_t o = group_off(g);
                 uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
                 if (valid) {
+                  const uint32_t co0 = ((g8 + (uint32_t)g) >> p.up_shift) << 3;
                   float y[8];
                   const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co0);
                   const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co0 + 4);
@@ -305,34 +323,40 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                   y[2] = __uint_as_float(v[8 * g + 2]) + b0.z; y[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
                   y[4] = __uint_as_float(v[8 * g + 4]) + b1.x; y[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
                   y[6] = __uint_as_float(v[8 * g + 6]) + b1.z; y[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
-                  if (ub) {
+                  if (has_ub) {
+                    const float* u8 = ub + (size_t)(g8 + (uint32_t)g) * 8;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) y[e] += __ldg(ub + gn0 + e);
+                    for (int e = 0; e < 8; ++e) y[e] += __ldg(u8 + e);
                   }
-                  if (c.res) {
+                  if (has_res) {
                     float f[8];
                     unpack_bf16x8(rv[g], f);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) y[e] += f[e];
                   }
-                  if (c.res2) {
+                  if (has_res2) {
                     float f[8];
                     unpack_bf16x8(rv2[g], f);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) y[e] += f[e];
                   }
-                  raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                                   pack_bf16x2(y[6], y[7]));
-                  float z[8];
+                  if (has_raw)
+                    raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                                     pack_bf16x2(y[6], y[7]));
+                  if (has_act) {
+                    float z[8];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) z[e] = lrelu(y[e] * c.act_scale, c.act_slope);
-                  act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
-                                   pack_bf16x2(z[6], z[7]));
+                    for (int e = 0; e < 8; ++e) {          // leaky_relu(v) = max(v, slope*v) for 0 < slope <= 1
+                      const float t = has_scale ? y[e] * scale : y[e];
+                      z[e] = fmaxf(t, t * slope);
+                    }
+                    act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
+                                     pack_bf16x2(z[6], z[7]));
+                  }
                 }
-                if (c.out_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;
-                if (c.out_act) *reinterpret_cast<uint4*>(c.out_act + o) = act;
+                if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;
+                if (has_act) *reinterpret_cast<uint4*>(c.out_act + o) = act;
               }
-            }
           }
         }
         tc_fence_before();
@@ -442,18 +466,53 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   VS_TRY(make_plan(c, &prm.p));
   VS_REQUIRE(c.in && c.w && (c.out_raw || c.out_act), "umma_conv1d: null pointer");
   static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
+  if (!n_sm) {
     int dev = 0;
     VS_CUDA_CHECK(cudaGetDevice(&dev));
     VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
+  VS_REQUIRE(c.act_slope > 0.f && c.act_slope <= 1.f, "umma_conv1d: act_slope must be in (0, 1]");
   const int per_sm = prm.p.ctas_per_sm;
   int grid = n_sm * per_sm;
   if (grid > prm.p.n_super) grid = prm.p.n_super;
-  umma_conv1d_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+  int flags = (c.res ? F_RES : 0) | (c.res2 ? F_RES2 : 0) | (c.ubias ? F_UBIAS : 0) | (c.out_raw ? F_RAW : 0) |
+              (c.out_act ? F_ACT : 0) | (c.act_scale != 1.f ? F_SCALE : 0) | (c.up != 1 ? F_UP : 0) |
+              (prm.p.Nblk < 64 ? F_CW16 : 0);
+#define VS_UMMA_CASE(FL)                                                                                              \
+  case FL: {                                                                                                          \
+    static bool cfg = false;                                                                                          \
+    if (!cfg) {                                                                                                       \
+      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    umma_conv1d_kernel<FL><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);                                            \
+    break;                                                                                                            \
+  }
+  switch (flags) {
+    // the decoder's epilogues: c1 | c2 mid | c2 last (j<2, j=2) | conv_pre | ups (raw+act, raw) ; each also at N = 32
+    VS_UMMA_CASE(F_ACT)
+    VS_UMMA_CASE(F_ACT | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RAW | F_ACT)
+    VS_UMMA_CASE(F_RES | F_RAW | F_ACT | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RAW)
+    VS_UMMA_CASE(F_RES | F_RAW | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RES2 | F_RAW)
+    VS_UMMA_CASE(F_RES | F_RES2 | F_RAW | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RES2 | F_ACT | F_SCALE)
+    VS_UMMA_CASE(F_RES | F_RES2 | F_ACT | F_SCALE | F_CW16)
+    VS_UMMA_CASE(F_UBIAS | F_ACT)
+    VS_UMMA_CASE(F_RAW | F_ACT | F_UP)
+    VS_UMMA_CASE(F_RAW | F_UP)
+    default: {
+      static bool cfg = false;
+      if (!cfg) {
+        VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cfg = true;
+      }
+      umma_conv1d_kernel<-1><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+    }
+  }
+#undef VS_UMMA_CASE
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

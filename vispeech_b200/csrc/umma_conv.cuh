@@ -30,4 +30,23 @@ struct UmmaConv {
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
 
+// One fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x on the raw stream (umma_respair.cu), C in {32, 64}.
+struct UmmaPair {
+  const __nv_bfloat16* x = nullptr;      // raw input, planar [C/8][R][8]
+  const __nv_bfloat16* w1 = nullptr;     // c1 weights, slabs as in UmmaConv (k taps, dilation dil)
+  const __nv_bfloat16* w2 = nullptr;     // c2 weights (k taps, dilation 1)
+  const float* b1 = nullptr;
+  const float* b2 = nullptr;
+  const __nv_bfloat16* res2 = nullptr;   // optional running MRF sum added to y
+  __nv_bfloat16* out_raw = nullptr;      // y
+  __nv_bfloat16* out_act = nullptr;      // lrelu(y * act_scale, act_slope)
+  const int32_t* row_utt = nullptr; int row_div = 1;
+  int R = 0, C = 0, taps = 3, dil = 1;
+  float in_slope = 0.1f;                 // LRELU_SLOPE of modules.py:17 (both inner leaky-relus)
+  float act_slope = 1.f, act_scale = 1.f;
+};
+bool umma_respair_supported(int C, int taps, int dil);
+void umma_respair_enable(bool on);
+int umma_respair(const UmmaPair& c, cudaStream_t st);
+
 }  // namespace vs
