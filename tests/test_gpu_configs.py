@@ -1,0 +1,91 @@
+"""GPU parity on the BASELINE.json configs that are not the bench line: C3 (512 mixed-length utterances, bucketed and
+sharded), C4 (one 60 s utterance) and the filelist-like real-distribution inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def net(state_dict):
+    from vispeech_b200 import build_from_hparams, get_hparams_from_file
+    n = build_from_hparams(get_hparams_from_file(), device="cuda:0")
+    n.load_state_dict(state_dict)
+    return n
+
+
+def snr_db(ref, x):
+    ref, x = ref.double().reshape(-1), x.double().reshape(-1)
+    return float(10 * torch.log10((ref ** 2).sum() / ((ref - x) ** 2).sum().clamp_min(1e-300)))
+
+
+def test_c3_mixed_lengths_bucketed_and_sharded(net, state_dict):
+    """C3: 512 utterances of 1-15 s.  Both ranks of a 2-way shard are executed here one after the other (same plan a
+    2-GPU run would use); every utterance must come out exactly once with exactly frames*512 samples; a sample of
+    utterances is compared with the oracle; the expansion indices of ALL utterances follow the reference rule."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import expansion_indices, infer_one
+    from vispeech_b200.batching import synthesize
+    utts = oin.c3(batch=512, seed=2)
+    frames = oin.frame_counts(utts)
+    assert min(frames) >= 80 and max(frames) <= 1300
+    noises = {i: oin.draw_noise([frames[i]], 1000 + i)[0] for i in (3, 77, 200, 311, 508)}
+    noise_list = [noises.get(i, torch.zeros(192, frames[i])) for i in range(512)]
+    got = {}
+    for rank in range(2):
+        part = synthesize(net, utts, noise_scale=0.667, rank=rank, world_size=2, noises=noise_list)
+        assert not set(part) & set(got)
+        got.update(part)
+    torch.cuda.synchronize()
+    assert sorted(got) == list(range(512))
+    for i in range(512):
+        assert got[i].numel() == frames[i] * 512
+        assert expansion_indices(utts[i]["duration"]).numel() == frames[i]
+    for i in noises:
+        ref = infer_one(state_dict, utts[i]["ids"], utts[i]["sid"], 0.667, noises[i], duration_control=utts[i]["duration"])
+        assert snr_db(ref["o"], got[i]) >= 30.0, i
+
+
+def test_c4_long_form_60s(net, state_dict):
+    """C4: one 60 s utterance (Tf = 5168, Tp = 492): streaming-softmax attention over 5168 frames, 2.6 M samples."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import infer_one
+    u = oin.c4()[0]
+    tf = oin.frame_counts([u])[0]
+    assert tf == 5168
+    eps = oin.draw_noise([tf], 31)[0]
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = net.infer(
+        u["ids"][None], torch.LongTensor([u["ids"].numel()]), sid=torch.LongTensor([u["sid"]]), noise_scale=0.667,
+        duration_control=u["duration"][None], noise=[eps])
+    torch.cuda.synchronize()
+    ref = infer_one(state_dict, u["ids"], u["sid"], 0.667, eps, duration_control=u["duration"])
+    assert o.shape == (1, 1, tf * 512) and int(x_mask.sum()) == tf
+    assert float((m_p[0].cpu() - ref["m_p"]).abs().max()) <= 1e-2
+    assert float((z[0].cpu() - ref["z"]).abs().max()) <= 1e-2
+    assert snr_db(ref["o"], o[0, 0].cpu()) >= 30.0
+
+
+def test_batch_invariance(net):
+    """An utterance's result must not depend on what else is in the batch or where its rows land (pad-free ragged rows;
+    fixed K order in every MMA): run alone vs inside a batch, with every GEMM forced onto the same (TF32) path."""
+    from oracle import inputs as oin
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    utts = oin.c2(batch=6, seed=5)
+    frames = oin.frame_counts(utts)
+    noises = oin.draw_noise(frames, 6)
+    _lib.check(lib.vs_set_option(b"tf32_min_rows", 1))
+    try:
+        ids = torch.stack([u["ids"] for u in utts])
+        dur = torch.stack([u["duration"] for u in utts])
+        sid = torch.LongTensor([u["sid"] for u in utts])
+        o_b, *_ = net.infer(ids, torch.LongTensor([40] * 6), sid=sid, noise_scale=0.667, duration_control=dur, noise=noises,
+                            outputs="audio")
+        o_1, *_ = net.infer(ids[4:5], torch.LongTensor([40]), sid=sid[4:5], noise_scale=0.667, duration_control=dur[4:5],
+                            noise=noises[4:5], outputs="audio")
+        torch.cuda.synchronize()
+        n = frames[4] * 512
+        assert torch.equal(o_b[4, 0, :n], o_1[0, 0, :n])
+    finally:
+        _lib.check(lib.vs_set_option(b"tf32_min_rows", 4096))
