@@ -21,6 +21,7 @@ struct FlowW {
   const float *pre_w, *pre_b, *post_w, *post_b, *cond_tab;
   const float *in_w[8], *in_b[8], *rs_w[8], *rs_b[8];
   const float *t_pre, *t_post, *t_in[8], *t_rs[8];     // TF32 slab copies
+  const float *t_in_gate[8], *in_gate_b[8], *cond_tab_gate;   // gate-interleaved column order (packing.py gate_columns)
 };
 
 // Rows below this run the fp32 CUDA-core conv (a handful of 128-row tiles cannot fill 148 SMs, and the phoneme-level
@@ -125,6 +126,7 @@ static int finalize(VsModel* m) {
     FETCH_F32(w.pre_w, p + "pre.w", (H / 2) * H);   FETCH_F32(w.pre_b, p + "pre.b", H);
     FETCH_F32(w.post_w, p + "post.w", H * (H / 2)); FETCH_F32(w.post_b, p + "post.b", H / 2);
     FETCH_F32(w.cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
+    FETCH_F32(w.cond_tab_gate, p + "cond_tab_gate", (int64_t)S * 2 * H * L);
     FETCH_F32(w.t_pre, "tf32." + p + "pre.w", (H / 2) * H);   FETCH_F32(w.t_post, "tf32." + p + "post.w", H * (H / 2));
     for (int l = 0; l < L; ++l) {
       const std::string q = p + std::to_string(l) + ".";
@@ -132,6 +134,7 @@ static int finalize(VsModel* m) {
       FETCH_F32(w.in_w[l], q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.in_b[l], q + "in.b", 2 * H);
       FETCH_F32(w.rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w.rs_b[l], q + "rs.b", rs);
       FETCH_F32(w.t_in[l], "tf32." + q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.t_rs[l], "tf32." + q + "rs.w", H * rs);
+      FETCH_F32(w.t_in_gate[l], "tf32." + q + "in_gate.w", 5 * H * 2 * H);  FETCH_F32(w.in_gate_b[l], q + "in_gate.b", 2 * H);
     }
   }
   VS_TRY(resolve_decoder(
@@ -368,8 +371,23 @@ int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, in
     c.R = R; c.row_utt = rows->row_utt;
     c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;
     VS_TRY(conv_rows(c, w.t_pre, st));                                     // h = pre(x0) * mask  (modules.py:326)
+    const bool fused_wn = R >= g_tf32_min_rows;      // tensor-core path: gate and res/skip update live in the conv epilogues
     for (int l = 0; l < L; ++l) {                                          // WN.forward (modules.py:148-176)
       const int rsC = (l < L - 1) ? 2 * H : H;
+      if (fused_wn) {
+        UmmaTf32 u;                                                        // acts = tanh . sigmoid (in_layer(h) + g_l)
+        u.in = h; u.in_ld = H; u.w = w.t_in_gate[l]; u.bias = w.in_gate_b[l];
+        u.ubias = w.cond_tab_gate + (size_t)2 * H * l; u.ubias_ld = 2 * H * L; u.ubias_idx = rows->sid;
+        u.out = acts; u.out_ld = H; u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = 2 * H; u.taps = 5; u.pad_l = 2;
+        u.epi = 1;
+        VS_TRY(umma_tf32(u, st));
+        u = UmmaTf32();                                                    // h += rs[:, :H]; skip (+)= rs[:, H:]
+        u.in = acts; u.in_ld = H; u.w = w.t_rs[l]; u.bias = w.rs_b[l]; u.out = h; u.out_ld = H; u.out2 = skip; u.out2_ld = H;
+        u.nb_split = (l < L - 1) ? 1 : 0; u.accumulate2 = (l > 0); u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = rsC;
+        u.epi = 2;
+        VS_TRY(umma_tf32(u, st));
+        continue;
+      }
       c = ConvF32(); c.R = R;
       c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = a; c.out_ld = 2 * H; c.Cout = 2 * H;
       c.k = 5; c.pad_l = 2;

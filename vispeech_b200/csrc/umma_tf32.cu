@@ -202,6 +202,63 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
         tmem_ld32(t_row + (uint32_t)(cc * 32), v);
         if (in_range) {
           const int col0 = nb * p.Nblk + cc * 32;
+          if (c.epi == 1) {
+            // WN gate: this chunk = [16 tanh pre-activations | 16 sigmoid pre-activations] of channels ch0..ch0+15
+            float* o = c.out + (size_t)r * c.out_ld + (col0 >> 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid) {
+                float t[4], sg[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  t[e] = __uint_as_float(v[4 * g + e]);
+                  sg[e] = __uint_as_float(v[16 + 4 * g + e]);
+                }
+                if (c.bias) {
+                  const float4 bt = __ldg(reinterpret_cast<const float4*>(c.bias + col0 + 4 * g));
+                  const float4 bs = __ldg(reinterpret_cast<const float4*>(c.bias + col0 + 16 + 4 * g));
+                  t[0] += bt.x; t[1] += bt.y; t[2] += bt.z; t[3] += bt.w;
+                  sg[0] += bs.x; sg[1] += bs.y; sg[2] += bs.z; sg[3] += bs.w;
+                }
+                if (ub) {
+                  const float4 bt = __ldg(reinterpret_cast<const float4*>(ub + col0 + 4 * g));
+                  const float4 bs = __ldg(reinterpret_cast<const float4*>(ub + col0 + 16 + 4 * g));
+                  t[0] += bt.x; t[1] += bt.y; t[2] += bt.z; t[3] += bt.w;
+                  sg[0] += bs.x; sg[1] += bs.y; sg[2] += bs.z; sg[3] += bs.w;
+                }
+                y.x = tanhf(t[0]) * (1.f / (1.f + expf(-sg[0])));
+                y.y = tanhf(t[1]) * (1.f / (1.f + expf(-sg[1])));
+                y.z = tanhf(t[2]) * (1.f / (1.f + expf(-sg[2])));
+                y.w = tanhf(t[3]) * (1.f / (1.f + expf(-sg[3])));
+              }
+              *reinterpret_cast<float4*>(o + 4 * g) = y;
+            }
+          } else if (c.epi == 2) {
+            const bool to_h = nb < c.nb_split;
+            float* o = to_h ? c.out + (size_t)r * c.out_ld + col0
+                            : c.out2 + (size_t)r * c.out2_ld + (col0 - c.nb_split * p.Nblk);
+            const bool add = to_h || c.accumulate2;
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 y = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                       __uint_as_float(v[4 * g + 3]));
+                if (c.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(c.bias + col0 + 4 * g));
+                  y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+                }
+                if (add) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + 4 * g);
+                  y.x += old.x; y.y += old.y; y.z += old.z; y.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + 4 * g) = y;
+              }
+            } else if (!add) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(o + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
           float* o = c.out + (size_t)r * c.out_ld + col0;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -220,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
               if (c.act == 1) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
             }
             *reinterpret_cast<float4*>(o + 4 * g) = y;
+          }
           }
         }
       }
@@ -285,6 +343,7 @@ int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
   VS_REQUIRE(c.in && c.w && c.out, "umma_tf32: null pointer");
+  VS_REQUIRE(c.epi != 2 || (c.out2 && c.out2_ld % 4 == 0), "umma_tf32: epi=2 needs out2");
   VS_TRY(make_plan(c, &prm.p));
   static int n_sm = 0;
   static bool configured = false;

@@ -16,6 +16,13 @@ struct UmmaTf32 {
   const int32_t* row_utt = nullptr;                  // null = every row valid; invalid rows are written as zeros
   int R = 0, Cin = 0, N = 0, taps = 1, dil = 1, pad_l = 0;
   int act = 0;                                       // 0 none, 1 relu
+  // Epilogue variants (both used by the flow's WN layers, modules.py:148-176):
+  //  epi = 1  WN gate: weight columns are packed in blocks [16 tanh | 16 sigmoid] (packing.py gate_columns), the epilogue
+  //           writes acts = tanh(a_t) * sigmoid(a_s) to out[r][N/2]              (commons.py:100-107)
+  //  epi = 2  res/skip update: n-blocks < nb_split are ADDED into out (h += res), the others go to out2 (skip), added
+  //           when accumulate2 else assigned; invalid rows are left untouched (out2: zeroed when assigned)
+  int epi = 0;
+  float* out2 = nullptr; int out2_ld = 0; int nb_split = 0; int accumulate2 = 0;
 };
 int umma_tf32(const UmmaTf32& c, cudaStream_t st);
 

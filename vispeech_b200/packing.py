@@ -86,6 +86,13 @@ def pack_tf32(w: torch.Tensor) -> torch.Tensor:
     return x.permute(5, 1, 0, 2, 3, 6, 4).contiguous().reshape(-1)
 
 
+def gate_columns(h: int = 192) -> torch.Tensor:
+    """Column order of a WN in_layer for the fused gate epilogue (csrc/umma_tf32.cuh epi=1): blocks of
+    [16 tanh channels | the same 16 sigmoid channels].  Returns perm with new[:, i] = old[:, perm[i]], len 2h."""
+    c = torch.arange(h).reshape(h // 16, 16)
+    return torch.cat([c, c + h], dim=1).reshape(-1)
+
+
 def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_flows=4, flow_layers=4) -> Dict[str, torch.Tensor]:
     """Returns {packed name: CPU tensor (fp32 or bf16, contiguous)}."""
     sd = {k: v.detach().float().cpu() for k, v in sd.items()}
@@ -198,6 +205,14 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
                     out["dec.rb.%d.%s.%d.w" % (n, cname, m)] = w
                     out["dec.rb.%d.%s.%d.b" % (n, cname, m)] = sd["dec.resblocks.%d.%s.%d.bias" % (n, key, m)]
                     out["dec16.rb.%d.%s.%d.w" % (n, cname, m)] = pack_umma(w)
+    # WN in_layers for the fused tanh*sigmoid epilogue: gate-interleaved columns (weights, bias, per-speaker cond)
+    gperm = gate_columns(192)
+    for f in range(n_flows):
+        tab = out["flow.%d.cond_tab" % f].reshape(emb_g.shape[0], flow_layers, 384)
+        out["flow.%d.cond_tab_gate" % f] = tab[:, :, gperm].reshape(emb_g.shape[0], -1).contiguous()
+        for l in range(flow_layers):
+            out["tf32.flow.%d.%d.in_gate.w" % (f, l)] = pack_tf32(out["flow.%d.%d.in.w" % (f, l)][:, :, gperm].contiguous())
+            out["flow.%d.%d.in_gate.b" % (f, l)] = out["flow.%d.%d.in.b" % (f, l)][gperm].contiguous()
     # TF32 tensor-core copies of the frame-level GEMM weights (flow, encoders, projection)
     for name in list(out):
         if name.endswith((".wqkv", ".wo")) or name == "proj.w" or name.endswith(("pre.w", "post.w", "rs.w")) and name.startswith("flow."):
