@@ -185,17 +185,19 @@ int layernorm_rows(const float* a, const float* b, const float* gamma, const flo
 // out = softmax(scores).(v) + sum_d p[i,i+d] Ev[d+4].  Keys are the utterance's own rows only, so the
 // reference's -1e4 pad fill (attentions.py:166) never triggers (batch-1 semantics).
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_BQ = 64, AT_BK = 64, AT_D = kHeadDim, AT_LD = AT_D + 1;
+constexpr int AT_BQ = 64, AT_BK = 64, AT_D = kHeadDim;
+constexpr int AT_LD = 100;   // row pitch of Q/K/V tiles: 16 B aligned, 400 B = 4 banks apart -> LDS.128 conflict-free
+constexpr int AT_SLD = 68;   // row pitch of the score tile (16 B aligned)
 
 __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const float* __restrict__ qkv,
                                                             const float* __restrict__ ek,
                                                             const float* __restrict__ ev, float* __restrict__ out) {
-  extern __shared__ float sm[];
-  float* Qs = sm;                          // [64][97]
-  float* Ks = Qs + AT_BQ * AT_LD;          // [64][97]
-  float* Vs = Ks + AT_BK * AT_LD;          // [64][97]
-  float* Ss = Vs + AT_BK * AT_LD;          // [64][65]
-  float* Ev = Ss + AT_BQ * (AT_BK + 1);    // [9][96]
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                          // [64][100]
+  float* Ks = Qs + AT_BQ * AT_LD;          // [64][100]
+  float* Vs = Ks + AT_BK * AT_LD;          // [64][100]
+  float* Ss = Vs + AT_BK * AT_LD;          // [64][68]
+  float* Ev = Ss + AT_BQ * AT_SLD;         // [9][96]
   float* relq = Ev + kRel * AT_D;          // [64][9]
   float* row_m = relq + AT_BQ * kRel;      // [64]
   float* row_l = row_m + AT_BQ;            // [64]
@@ -209,9 +211,12 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
   const int ld = 3 * kHidden;
   const float scale = rsqrtf((float)AT_D);
 
-  for (int i = tid; i < AT_BQ * AT_D; i += 256) {
-    const int r = i / AT_D, d = i % AT_D;
-    Qs[r * AT_LD + d] = (q0 + r < T) ? qkv[(size_t)(start + q0 + r) * ld + h * AT_D + d] * scale : 0.f;
+  for (int i = tid; i < AT_BQ * (AT_D / 4); i += 256) {       // float4 loads: 24 per row
+    const int r = i / (AT_D / 4), d4 = i % (AT_D / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) v = *reinterpret_cast<const float4*>(qkv + (size_t)(start + q0 + r) * ld + h * AT_D + 4 * d4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(Qs + r * AT_LD + 4 * d4) = v;
   }
   for (int i = tid; i < kRel * AT_D; i += 256) Ev[i] = ev[i];
   if (tid < AT_BQ) { row_m[tid] = -INFINITY; row_l[tid] = 0.f; }
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     relq[i] = s;
   }
 
-  const int ty = tid / 16, tx = tid % 16;   // S tile: rows 4ty..+3, cols tx+16c ; O tile: rows 4ty..+3, dims tx+16c (c<6)
+  // S tile: rows 4ty..+3, key columns tx+16c (c<4).  O tile: rows 4ty..+3, head dims 6tx..6tx+5.
+  const int ty = tid / 16, tx = tid % 16;
   float o_acc[4][6];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -232,12 +238,16 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
 
   for (int k0 = 0; k0 < T; k0 += AT_BK) {
     __syncthreads();
-    for (int i = tid; i < AT_BK * AT_D; i += 256) {
-      const int r = i / AT_D, d = i % AT_D;
-      const bool ok = k0 + r < T;
-      const size_t g = (size_t)(start + k0 + r) * ld + h * AT_D + d;
-      Ks[r * AT_LD + d] = ok ? qkv[g + kHidden] : 0.f;
-      Vs[r * AT_LD + d] = ok ? qkv[g + 2 * kHidden] : 0.f;
+    for (int i = tid; i < AT_BK * (AT_D / 4); i += 256) {
+      const int r = i / (AT_D / 4), d4 = i % (AT_D / 4);
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (k0 + r < T) {
+        const float* g = qkv + (size_t)(start + k0 + r) * ld + h * AT_D + 4 * d4;
+        kk = *reinterpret_cast<const float4*>(g + kHidden);
+        vv = *reinterpret_cast<const float4*>(g + 2 * kHidden);
+      }
+      *reinterpret_cast<float4*>(Ks + r * AT_LD + 4 * d4) = kk;
+      *reinterpret_cast<float4*>(Vs + r * AT_LD + 4 * d4) = vv;
     }
     __syncthreads();
     float s[4][4];
@@ -245,16 +255,22 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) s[i][c] = 0.f;
-    for (int d = 0; d < AT_D; ++d) {
-      float qa[4], kb[4];
+#pragma unroll 2
+    for (int d = 0; d < AT_D; d += 4) {            // 8 LDS.128 per 64 FMA
+      float4 qa[4], kb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = Qs[(4 * ty + i) * AT_LD + d];
+      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * AT_LD + d);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) kb[c] = Ks[(tx + 16 * c) * AT_LD + d];
+      for (int c = 0; c < 4; ++c) kb[c] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * c) * AT_LD + d);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s[i][c] = fmaf(qa[i], kb[c], s[i][c]);
+        for (int c = 0; c < 4; ++c) {
+          s[i][c] = fmaf(qa[i].x, kb[c].x, s[i][c]);
+          s[i][c] = fmaf(qa[i].y, kb[c].y, s[i][c]);
+          s[i][c] = fmaf(qa[i].z, kb[c].z, s[i][c]);
+          s[i][c] = fmaf(qa[i].w, kb[c].w, s[i][c]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -265,22 +281,22 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
         const int dd = kj - qi;
         if (dd >= -kWindow && dd <= kWindow) v += relq[(4 * ty + i) * kRel + dd + kWindow];
         if (kj >= T) v = -INFINITY;
-        Ss[(4 * ty + i) * (AT_BK + 1) + tx + 16 * c] = v;
+        Ss[(4 * ty + i) * AT_SLD + tx + 16 * c] = v;
       }
     __syncthreads();
     // row-wise streaming softmax: 4 threads per row
     {
       const int r = tid / 4, part = tid % 4;
       float mx = -INFINITY;
-      for (int c = part; c < AT_BK; c += 4) mx = fmaxf(mx, Ss[r * (AT_BK + 1) + c]);
+      for (int c = part; c < AT_BK; c += 4) mx = fmaxf(mx, Ss[r * AT_SLD + c]);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float m_old = row_m[r];
       const float m_new = fmaxf(m_old, mx);
       float sum = 0.f;
       for (int c = part; c < AT_BK; c += 4) {
-        const float p = __expf(Ss[r * (AT_BK + 1) + c] - m_new);
-        Ss[r * (AT_BK + 1) + c] = p;
+        const float p = __expf(Ss[r * AT_SLD + c] - m_new);
+        Ss[r * AT_SLD + c] = p;
         sum += p;
       }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -300,16 +316,24 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
 #pragma unroll
       for (int c = 0; c < 6; ++c) o_acc[i][c] *= al;
     }
-    for (int j = 0; j < AT_BK; ++j) {
-      float p[4], vv[6];
+#pragma unroll 2
+    for (int j = 0; j < AT_BK; j += 4) {            // 4 LDS.128 (P) + 12 LDS.64 (V) per 96 FMA
+      float4 p4[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p[i] = Ss[(4 * ty + i) * (AT_BK + 1) + j];
+      for (int i = 0; i < 4; ++i) p4[i] = *reinterpret_cast<const float4*>(Ss + (4 * ty + i) * AT_SLD + j);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) vv[c] = Vs[j * AT_LD + tx + 16 * c];
+      for (int jj = 0; jj < 4; ++jj) {
+        const float* vr = Vs + (j + jj) * AT_LD + 6 * tx;
+        const float2 v0 = *reinterpret_cast<const float2*>(vr), v1 = *reinterpret_cast<const float2*>(vr + 2),
+                     v2 = *reinterpret_cast<const float2*>(vr + 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p[i], vv[c], o_acc[i][c]);
+        for (int i = 0; i < 4; ++i) {
+          const float p = jj == 0 ? p4[i].x : jj == 1 ? p4[i].y : jj == 2 ? p4[i].z : p4[i].w;
+          o_acc[i][0] = fmaf(p, v0.x, o_acc[i][0]); o_acc[i][1] = fmaf(p, v0.y, o_acc[i][1]);
+          o_acc[i][2] = fmaf(p, v1.x, o_acc[i][2]); o_acc[i][3] = fmaf(p, v1.y, o_acc[i][3]);
+          o_acc[i][4] = fmaf(p, v2.x, o_acc[i][4]); o_acc[i][5] = fmaf(p, v2.y, o_acc[i][5]);
+        }
+      }
     }
     // relative values on the band (attentions.py:174-177)
 #pragma unroll
@@ -318,9 +342,9 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
       for (int dd = -kWindow; dd <= kWindow; ++dd) {
         const int j = qi + dd - k0;
         if (j < 0 || j >= AT_BK || qi + dd >= T) continue;
-        const float p = Ss[(4 * ty + i) * (AT_BK + 1) + j];
+        const float p = Ss[(4 * ty + i) * AT_SLD + j];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p, Ev[(dd + kWindow) * AT_D + tx + 16 * c], o_acc[i][c]);
+        for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p, Ev[(dd + kWindow) * AT_D + 6 * tx + c], o_acc[i][c]);
       }
     }
   }
@@ -329,13 +353,14 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     const int qi = q0 + 4 * ty + i;
     if (qi >= T) continue;
     const float inv = 1.f / row_l[4 * ty + i];
+    float* o = out + (size_t)(start + qi) * kHidden + h * AT_D + 6 * tx;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) out[(size_t)(start + qi) * kHidden + h * AT_D + tx + 16 * c] = o_acc[i][c] * inv;
+    for (int c = 0; c < 6; c += 2) *reinterpret_cast<float2*>(o + c) = make_float2(o_acc[i][c] * inv, o_acc[i][c + 1] * inv);
   }
 }
 
 static size_t attention_smem_bytes() {
-  return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * (AT_BK + 1) + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
+  return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * AT_SLD + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
 }
 
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st) {
