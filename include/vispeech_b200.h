@@ -76,6 +76,8 @@ int vs_version(void);
 int64_t vs_launch_count(void);
 /* process-wide knobs. "tf32_min_rows": convs over at least this many rows run on the tensor cores in TF32 (default
  * 4096; fewer rows stay on the fp32 CUDA-core kernel).  Used by the parity tests to force either path.
+ * "x3_min_rows": convs over at least this many rows (and below tf32_min_rows, or phoneme level) run as error-
+ * compensated 3xTF32 on the tensor cores (default 512; fp32-level accuracy).
  * "fused_respair": 1 = run C<=64 ResBlock iterations through the experimental fused kernel (default 0). */
 int vs_set_option(const char* name, int64_t value);   /* kernels launched by this library so far (process-wide) */
 
@@ -140,10 +142,11 @@ int vs_op_layernorm(const float* a, const float* b, const float* gamma, const fl
                     int32_t n_rows, int32_t C, const int32_t* row_utt, void* stream);
 int vs_op_rel_attention(const VsRows* rows, const float* qkv /*[n_rows][576]*/, const float* emb_rel_k,
                         const float* emb_rel_v, float* out /*[n_rows][192]*/, void* stream);
-/* TF32 tcgen05 conv over fp32 row-major rows (csrc/umma_tf32.cu): out = act(conv(in) + bias), zeros on invalid rows */
+/* TF32 tcgen05 conv over fp32 row-major rows (csrc/umma_tf32.cu): out = act(conv(in) + bias), zeros on invalid rows.
+ * split3 = 1: error-compensated 3xTF32 (weights packed with pack_tf32(split3=True)), fp32-level accuracy. */
 int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,
                       int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
-                      const int32_t* row_utt, void* stream);
+                      int32_t split3, const int32_t* row_utt, void* stream);
 /* bf16 tcgen05 implicit-GEMM conv on planar [C/8][n_rows][8] activations (csrc/umma_conv.cu):
  * y = conv(in) + bias + res;  out_raw = y;  out_act = leaky_relu(y*act_scale, act_slope); either output may be
  * null.  up > 1 = polyphase ConvTranspose1d (column gn -> phase gn/Cout, output row up*r+phase). */

@@ -78,14 +78,14 @@ def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=N
     return out
 
 
-def conv_tf32(x, w_tcn, bias=None, dil=1, pad_l=0, act=0, row_utt=None):
+def conv_tf32(x, w_tcn, bias=None, dil=1, pad_l=0, act=0, row_utt=None, split3=False):
     lib = _lib.load()
     R, cin = x.shape
     k, _, cout = w_tcn.shape
-    wp = pack_tf32(w_tcn.cpu()).to(x.device)
+    wp = pack_tf32(w_tcn.cpu(), split3=split3).to(x.device)
     out = torch.full((R, cout), float("nan"), dtype=torch.float32, device=x.device)
     check(lib.vs_op_conv1d_tf32(ptr(x), cin, ptr(wp), ptr(bias), ptr(out), cout, R, cin, cout, k, dil, pad_l, act,
-                                ptr(row_utt), stream()), "vs_op_conv1d_tf32")
+                                1 if split3 else 0, ptr(row_utt), stream()), "vs_op_conv1d_tf32")
     torch.cuda.synchronize()
     return out
 

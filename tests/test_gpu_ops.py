@@ -155,6 +155,22 @@ def test_conv_tf32_matches_cpu(G, R, cin, cout, k, dil, act):
     assert (out - ref).abs().max().item() <= 5e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("R,cin,cout,k,act", [(300, 192, 576, 1, 0), (1000, 192, 768, 3, 1), (260, 768, 192, 3, 0),
+                                             (500, 96, 192, 1, 0), (700, 192, 384, 5, 0), (2816, 192, 256, 3, 1)])
+def test_conv_3xtf32_is_fp32_accurate(G, R, cin, cout, k, act):
+    """Error-compensated 3xTF32 (a_hi w_hi + a_lo w_hi + a_hi w_lo) vs fp64: the tolerance is that of an fp32 conv
+    (1e-4 absolute on O(1) outputs), i.e. ~50x tighter than plain TF32."""
+    g = torch.Generator().manual_seed(k * 11 + cout)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(k, cin, cout, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    out = G.conv_tf32(x.to(G.DEV), w, b.to(G.DEV), pad_l=(k - 1) // 2, act=act, split3=True).cpu().double()
+    ref = G.ref_conv_rows(x, w, b, pad_l=(k - 1) // 2)
+    if act:
+        ref = ref.clamp_min(0)
+    assert (out - ref).abs().max().item() <= 1e-4
+
+
 def test_layernorm_rows(G):
     from vispeech_b200 import _lib
     lib = _lib.load()

@@ -16,29 +16,35 @@ struct Tensor { const void* ptr; int64_t numel; int32_t dtype; };
 struct EncLayer {
   const float *wqkv, *bqkv, *wo, *bo, *ek, *ev, *g1, *b1, *g2, *b2, *w1, *bf1, *w2, *bf2;
   const float *t_wqkv, *t_wo, *t_w1, *t_w2;            // TF32 slab copies (umma_tf32.cuh)
+  const float *x_wqkv, *x_wo, *x_w1, *x_w2;            // 3xTF32 [hi|lo] slab copies
 };
 struct FlowW {
   const float *pre_w, *pre_b, *post_w, *post_b, *cond_tab;
   const float *in_w[8], *in_b[8], *rs_w[8], *rs_b[8];
   const float *t_pre, *t_post, *t_in[8], *t_rs[8];     // TF32 slab copies
   const float *t_in_gate[8], *in_gate_b[8], *cond_tab_gate;   // gate-interleaved column order (packing.py gate_columns)
+  const float *x_pre, *x_post, *x_in[8], *x_rs[8], *x_in_gate[8];   // 3xTF32 copies
 };
 
-// Rows below this run the fp32 CUDA-core conv (a handful of 128-row tiles cannot fill 148 SMs, and the phoneme-level
-// predictors keep full fp32); above it the conv runs on the tensor cores in TF32.
-constexpr int kTf32MinRowsDefault = 4096;
-static int g_tf32_min_rows = kTf32MinRowsDefault;      // vs_set_option("tf32_min_rows", n); tests force n = 1
+// Precision / engine policy for the GEMM-shaped convs upstream of the decoder (all rows counts are per call):
+//   rows >= tf32_min_rows (4096) and the conv is frame level  -> tcgen05 kind::tf32, operands rounded to TF32
+//   rows >= x3_min_rows (512)                                  -> tcgen05 3xTF32 (hi/lo split, fp32-level accuracy)
+//   otherwise                                                  -> fp32 CUDA cores
+// Phoneme-level convs (text encoder, predictors) never take the plain-TF32 route: their error feeds back through the
+// F0 / energy prenets (measured: z error 7.5e-3 with plain TF32 there vs 4.6e-3 without; bar 1e-2).
+static int g_tf32_min_rows = 4096;      // vs_set_option("tf32_min_rows", n)
+static int g_x3_min_rows = 512;         // vs_set_option("x3_min_rows", n)
 
-// conv through the TF32 tensor-core kernel when eligible, else the fp32 CUDA-core kernel (same arguments)
-static int conv_rows(const ConvF32& c, const float* w_tf32, cudaStream_t st) {
-  const bool eligible = w_tf32 && c.R >= g_tf32_min_rows && !c.res && !c.accumulate && c.in_slope == 1.f &&
-                        c.out_row_mul == 1 && c.out_row_off == 0 && c.out_scale == 1.f && c.act <= 1 && c.row_div == 1 &&
-                        c.Cin % 32 == 0 && c.Cout % 32 == 0;
-  if (!eligible) return conv1d_f32(c, st);
+static int conv_rows(const ConvF32& c, const float* w_tf32, const float* w_x3, cudaStream_t st) {
+  const bool shape_ok = !c.res && !c.accumulate && c.in_slope == 1.f && c.out_row_mul == 1 && c.out_row_off == 0 &&
+                        c.out_scale == 1.f && c.act <= 1 && c.row_div == 1 && c.Cout % 32 == 0;
+  const bool use_tf32 = shape_ok && w_tf32 && c.R >= g_tf32_min_rows;
+  const bool use_x3 = shape_ok && !use_tf32 && w_x3 && c.R >= g_x3_min_rows;
+  if (!use_tf32 && !use_x3) return conv1d_f32(c, st);
   UmmaTf32 u;
-  u.in = c.in; u.in_ld = c.in_ld; u.w = w_tf32; u.bias = c.bias; u.ubias = c.ubias; u.ubias_ld = c.ubias_ld;
-  u.ubias_idx = c.ubias_idx; u.out = c.out; u.out_ld = c.out_ld; u.row_utt = c.row_utt; u.R = c.R; u.Cin = c.Cin;
-  u.N = c.Cout; u.taps = c.k; u.dil = c.dil; u.pad_l = c.pad_l; u.act = c.act;
+  u.in = c.in; u.in_ld = c.in_ld; u.w = use_tf32 ? w_tf32 : w_x3; u.split3 = use_x3 ? 1 : 0; u.bias = c.bias;
+  u.ubias = c.ubias; u.ubias_ld = c.ubias_ld; u.ubias_idx = c.ubias_idx; u.out = c.out; u.out_ld = c.out_ld;
+  u.row_utt = c.row_utt; u.R = c.R; u.Cin = c.Cin; u.N = c.Cout; u.taps = c.k; u.dil = c.dil; u.pad_l = c.pad_l; u.act = c.act;
   return umma_tf32(u, st);
 }
 
@@ -55,7 +61,7 @@ struct VsModel {
   const float *pp_cond, *pp_wf0, *pp_bf0;
   const float *ep_cond, *ep_w1, *ep_b1, *ep_g1, *ep_be1, *ep_w2, *ep_b2, *ep_g2, *ep_be2, *ep_wl, *ep_bl;
   const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
-  const float *proj_w, *proj_b, *t_proj_w;
+  const float *proj_w, *proj_b, *t_proj_w, *x_proj_w, *x_dp_w1, *x_ep_w1, *x_ep_w2;
   std::vector<vs::FlowW> flows;
   vs::DecoderW dec;
 };
@@ -90,6 +96,8 @@ static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::
     FETCH_F32(L.w2, q + "w2", (int64_t)3 * F * H);      FETCH_F32(L.bf2, q + "bf2", H);
     FETCH_F32(L.t_wqkv, "tf32." + q + "wqkv", (int64_t)H * 3 * H);  FETCH_F32(L.t_wo, "tf32." + q + "wo", (int64_t)H * H);
     FETCH_F32(L.t_w1, "tf32." + q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.t_w2, "tf32." + q + "w2", (int64_t)3 * F * H);
+    FETCH_F32(L.x_wqkv, "x3." + q + "wqkv", (int64_t)2 * H * 3 * H);  FETCH_F32(L.x_wo, "x3." + q + "wo", (int64_t)2 * H * H);
+    FETCH_F32(L.x_w1, "x3." + q + "w1", (int64_t)2 * 3 * H * F);      FETCH_F32(L.x_w2, "x3." + q + "w2", (int64_t)2 * 3 * F * H);
   }
   return VS_OK;
 }
@@ -117,7 +125,9 @@ static int finalize(VsModel* m) {
   FETCH_F32(m->pitch_pre_w, "pitch_prenet.w", H * 3);   FETCH_F32(m->pitch_pre_b, "pitch_prenet.b", H);
   FETCH_F32(m->energy_pre_w, "energy_prenet.w", H * 3); FETCH_F32(m->energy_pre_b, "energy_prenet.b", H);
   FETCH_F32(m->proj_w, "proj.w", H * 2 * H);   FETCH_F32(m->proj_b, "proj.b", 2 * H);
-  FETCH_F32(m->t_proj_w, "tf32.proj.w", H * 2 * H);
+  FETCH_F32(m->t_proj_w, "tf32.proj.w", H * 2 * H);       FETCH_F32(m->x_proj_w, "x3.proj.w", 2 * H * 2 * H);
+  FETCH_F32(m->x_dp_w1, "x3.dp.w1", 2 * 3 * H * 256);
+  FETCH_F32(m->x_ep_w1, "x3.ep.w1", 2 * 3 * H * 768);     FETCH_F32(m->x_ep_w2, "x3.ep.w2", 2 * 3 * 768 * 768);
   const int L = m->cfg.flow_layers;
   m->flows.resize(m->cfg.n_flows);
   for (int f = 0; f < m->cfg.n_flows; ++f) {
@@ -128,6 +138,7 @@ static int finalize(VsModel* m) {
     FETCH_F32(w.cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
     FETCH_F32(w.cond_tab_gate, p + "cond_tab_gate", (int64_t)S * 2 * H * L);
     FETCH_F32(w.t_pre, "tf32." + p + "pre.w", (H / 2) * H);   FETCH_F32(w.t_post, "tf32." + p + "post.w", H * (H / 2));
+    FETCH_F32(w.x_pre, "x3." + p + "pre.w", 2 * (H / 2) * H); FETCH_F32(w.x_post, "x3." + p + "post.w", 2 * H * (H / 2));
     for (int l = 0; l < L; ++l) {
       const std::string q = p + std::to_string(l) + ".";
       const int rs = (l < L - 1) ? 2 * H : H;
@@ -135,6 +146,8 @@ static int finalize(VsModel* m) {
       FETCH_F32(w.rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w.rs_b[l], q + "rs.b", rs);
       FETCH_F32(w.t_in[l], "tf32." + q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.t_rs[l], "tf32." + q + "rs.w", H * rs);
       FETCH_F32(w.t_in_gate[l], "tf32." + q + "in_gate.w", 5 * H * 2 * H);  FETCH_F32(w.in_gate_b[l], q + "in_gate.b", 2 * H);
+      FETCH_F32(w.x_in[l], "x3." + q + "in.w", 2 * 5 * H * 2 * H);  FETCH_F32(w.x_rs[l], "x3." + q + "rs.w", 2 * H * rs);
+      FETCH_F32(w.x_in_gate[l], "x3." + q + "in_gate.w", 2 * 5 * H * 2 * H);
     }
   }
   VS_TRY(resolve_decoder(
@@ -148,7 +161,7 @@ static int finalize(VsModel* m) {
 static int64_t encoder_ws_floats(int R) { return (int64_t)R * (3 * kHidden + kHidden + kHidden + kFilter); }
 
 static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& rows, float* x, Workspace& ws,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool frame_level) {
   const int R = rows.n_rows, H = kHidden, F = kFilter;
   float* qkv = ws.take<float>((int64_t)R * 3 * H);
   float* att = ws.take<float>((int64_t)R * H);
@@ -159,15 +172,15 @@ static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& ro
     ConvF32 c;
     c.R = R; c.row_utt = rows.row_utt;
     c.in = x; c.in_ld = H; c.Cin = H; c.w = L.wqkv; c.bias = L.bqkv; c.out = qkv; c.out_ld = 3 * H; c.Cout = 3 * H;
-    VS_TRY(conv_rows(c, L.t_wqkv, st));                                    // conv_q|k|v (attentions.py:139-141)
+    VS_TRY(conv_rows(c, frame_level ? L.t_wqkv : nullptr, L.x_wqkv, st));                                    // conv_q|k|v (attentions.py:139-141)
     VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st));                 // attentions.py:148-179
     c.in = att; c.w = L.wo; c.bias = L.bo; c.out = y; c.out_ld = H; c.Cout = H;
-    VS_TRY(conv_rows(c, L.t_wo, st));                                      // conv_o
+    VS_TRY(conv_rows(c, frame_level ? L.t_wo : nullptr, L.x_wo, st));                                      // conv_o
     VS_TRY(layernorm_rows(x, y, L.g1, L.b1, x, R, H, rows.row_utt, st));   // x = LN(x + y)
     c.in = x; c.Cin = H; c.w = L.w1; c.bias = L.bf1; c.out = hbuf; c.out_ld = F; c.Cout = F; c.k = 3; c.pad_l = 1; c.act = 1;
-    VS_TRY(conv_rows(c, L.t_w1, st));                                      // FFN conv_1 + relu (attentions.py:278-282)
+    VS_TRY(conv_rows(c, frame_level ? L.t_w1 : nullptr, L.x_w1, st));                                      // FFN conv_1 + relu (attentions.py:278-282)
     c.in = hbuf; c.in_ld = F; c.Cin = F; c.w = L.w2; c.bias = L.bf2; c.out = y; c.out_ld = H; c.Cout = H; c.act = 0;
-    VS_TRY(conv_rows(c, L.t_w2, st));                                      // FFN conv_2
+    VS_TRY(conv_rows(c, frame_level ? L.t_w2 : nullptr, L.x_w2, st));                                      // FFN conv_2
     VS_TRY(layernorm_rows(x, y, L.g2, L.b2, x, R, H, rows.row_utt, st));
   }
   return VS_OK;
@@ -194,6 +207,11 @@ int vs_set_option(const char* name, int64_t value) {
   if (std::string(name) == "tf32_min_rows") {
     VS_REQUIRE(value >= 1, "vs_set_option: tf32_min_rows must be >= 1");
     vs::g_tf32_min_rows = (int)value;
+    return VS_OK;
+  }
+  if (std::string(name) == "x3_min_rows") {
+    VS_REQUIRE(value >= 1, "vs_set_option: x3_min_rows must be >= 1");
+    vs::g_x3_min_rows = (int)value;
     return VS_OK;
   }
   if (std::string(name) == "fused_respair") {
@@ -258,7 +276,7 @@ int vs_text_encode(const VsModel* m, const VsRows* rows, const int32_t* ids_rows
                    int64_t ws_bytes, void* stream) {
   VS_ENTER(m, rows, "vs_text_encode");
   VS_TRY(embed_rows(ids_rows, m->emb, x_out, rows->n_rows, m->cfg.n_vocab, st));
-  return encoder_forward(m->enc_text, *rows, x_out, W, st);
+  return encoder_forward(m->enc_text, *rows, x_out, W, st, false);
 }
 
 int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t dur_mode, float dur_scale,
@@ -283,7 +301,7 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
     VS_TRY(add_speaker_rows(x, m->dp_cond, *rows, t, H, st));
     c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
     c.in = t; c.in_ld = H; c.Cin = H; c.w = m->dp_w1; c.bias = m->dp_b1; c.out = h1; c.out_ld = 256; c.Cout = 256;
-    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(conv_rows(c, nullptr, m->x_dp_w1, st));
     VS_TRY(layernorm_rows(h1, nullptr, m->dp_g1, m->dp_be1, h1, R, 256, rows->row_utt, st));
     c.in = h1; c.in_ld = 256; c.Cin = 256; c.w = m->dp_w2; c.bias = m->dp_b2; c.out = h2;
     VS_TRY(conv1d_f32(c, st));
@@ -296,7 +314,7 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
   if (pitch_mode == 0) {
     VS_TRY(add_speaker_rows(x, m->pp_cond, *rows, t, H, st));
     Workspace W2 = W;
-    VS_TRY(encoder_forward(m->enc_pitch, *rows, t, W2, st));
+    VS_TRY(encoder_forward(m->enc_pitch, *rows, t, W2, st, false));
     VS_TRY(row_dot(t, H, m->pp_wf0, m->pp_bf0, s0, R, H, rows->row_utt, st));
   }
   VS_TRY(pitch_rows(s0, pitch_ctrl, pitch_mode, pitch_scale, *rows, s1, f0_out, st));
@@ -307,10 +325,10 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
     VS_TRY(add_speaker_rows(x, m->ep_cond, *rows, t, H, st));
     c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
     c.in = t; c.in_ld = H; c.Cin = H; c.w = m->ep_w1; c.bias = m->ep_b1; c.out = h1; c.out_ld = 768; c.Cout = 768;
-    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(conv_rows(c, nullptr, m->x_ep_w1, st));
     VS_TRY(layernorm_rows(h1, nullptr, m->ep_g1, m->ep_be1, h1, R, 768, rows->row_utt, st));
     c.in = h1; c.in_ld = 768; c.Cin = 768; c.w = m->ep_w2; c.bias = m->ep_b2; c.out = h2;
-    VS_TRY(conv1d_f32(c, st));
+    VS_TRY(conv_rows(c, nullptr, m->x_ep_w2, st));
     VS_TRY(layernorm_rows(h2, nullptr, m->ep_g2, m->ep_be2, h2, R, 768, rows->row_utt, st));
     VS_TRY(row_dot(h2, 768, m->ep_wl, m->ep_bl, s0, R, 768, rows->row_utt, st));
   }
@@ -343,11 +361,11 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   if (!W.ok) { set_error("vs_frame_prior: workspace too small"); return VS_ERR_WORKSPACE; }
   if (x_frame_out != x_f)
     VS_CUDA_CHECK(cudaMemcpyAsync(x_frame_out, x_f, sizeof(float) * (size_t)R * H, cudaMemcpyDeviceToDevice, st));
-  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st));       // FramePriorNet.forward models.py:466-470
+  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st, true));       // FramePriorNet.forward models.py:466-470
   ConvF32 c;                                                               // Projection.forward models.py:526-529
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
-  VS_TRY(conv_rows(c, m->t_proj_w, st));
+  VS_TRY(conv_rows(c, m->t_proj_w, m->x_proj_w, st));
   return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 
@@ -370,19 +388,20 @@ int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, in
     ConvF32 c;
     c.R = R; c.row_utt = rows->row_utt;
     c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;
-    VS_TRY(conv_rows(c, w.t_pre, st));                                     // h = pre(x0) * mask  (modules.py:326)
-    const bool fused_wn = R >= g_tf32_min_rows;      // tensor-core path: gate and res/skip update live in the conv epilogues
+    VS_TRY(conv_rows(c, w.t_pre, w.x_pre, st));                                     // h = pre(x0) * mask  (modules.py:326)
+    const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
+    const bool fused_wn = wn_tf32 || wn_x3;          // tensor-core path: gate and res/skip update live in the conv epilogues
     for (int l = 0; l < L; ++l) {                                          // WN.forward (modules.py:148-176)
       const int rsC = (l < L - 1) ? 2 * H : H;
       if (fused_wn) {
         UmmaTf32 u;                                                        // acts = tanh . sigmoid (in_layer(h) + g_l)
-        u.in = h; u.in_ld = H; u.w = w.t_in_gate[l]; u.bias = w.in_gate_b[l];
+        u.in = h; u.in_ld = H; u.w = wn_tf32 ? w.t_in_gate[l] : w.x_in_gate[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.in_gate_b[l];
         u.ubias = w.cond_tab_gate + (size_t)2 * H * l; u.ubias_ld = 2 * H * L; u.ubias_idx = rows->sid;
         u.out = acts; u.out_ld = H; u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = 2 * H; u.taps = 5; u.pad_l = 2;
         u.epi = 1;
         VS_TRY(umma_tf32(u, st));
         u = UmmaTf32();                                                    // h += rs[:, :H]; skip (+)= rs[:, H:]
-        u.in = acts; u.in_ld = H; u.w = w.t_rs[l]; u.bias = w.rs_b[l]; u.out = h; u.out_ld = H; u.out2 = skip; u.out2_ld = H;
+        u.in = acts; u.in_ld = H; u.w = wn_tf32 ? w.t_rs[l] : w.x_rs[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.rs_b[l]; u.out = h; u.out_ld = H; u.out2 = skip; u.out2_ld = H;
         u.nb_split = (l < L - 1) ? 1 : 0; u.accumulate2 = (l > 0); u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = rsC;
         u.epi = 2;
         VS_TRY(umma_tf32(u, st));
@@ -391,16 +410,16 @@ int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, in
       c = ConvF32(); c.R = R;
       c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = a; c.out_ld = 2 * H; c.Cout = 2 * H;
       c.k = 5; c.pad_l = 2;
-      VS_TRY(conv_rows(c, w.t_in[l], st));
+      VS_TRY(conv_rows(c, w.t_in[l], w.x_in[l], st));
       VS_TRY(wn_gate(a, w.cond_tab, 2 * H * L, 2 * H * l, *rows, acts, st));
       c = ConvF32(); c.R = R;
       c.in = acts; c.in_ld = H; c.Cin = H; c.w = w.rs_w[l]; c.bias = w.rs_b[l]; c.out = rs; c.out_ld = rsC; c.Cout = rsC;
-      VS_TRY(conv_rows(c, w.t_rs[l], st));
+      VS_TRY(conv_rows(c, w.t_rs[l], w.x_rs[l], st));
       VS_TRY(wn_update(rs, rsC, l == L - 1, l == 0, *rows, h, skip, st));
     }
     c = ConvF32(); c.R = R;
     c.in = skip; c.in_ld = H; c.Cin = H; c.w = w.post_w; c.bias = w.post_b; c.out = mm; c.out_ld = H / 2; c.Cout = H / 2;
-    VS_TRY(conv_rows(c, w.t_post, st));                                    // m = post(h) (modules.py:328)
+    VS_TRY(conv_rows(c, w.t_post, w.x_post, st));                                    // m = post(h) (modules.py:328)
     VS_TRY(coupling_sub(z, upd_off, mm, *rows, st));                       // x1 = (x1 - m) * mask (modules.py:341)
   }
   return VS_OK;
@@ -443,10 +462,10 @@ int vs_op_rel_attention(const VsRows* rows, const float* qkv, const float* emb_r
 
 int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,
                       int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
-                      const int32_t* row_utt, void* stream) {
+                      int32_t split3, const int32_t* row_utt, void* stream) {
   UmmaTf32 u;
   u.in = in; u.in_ld = in_ld; u.w = w_packed; u.bias = bias; u.out = out; u.out_ld = out_ld; u.row_utt = row_utt;
-  u.R = n_rows; u.Cin = c_in; u.N = c_out; u.taps = taps; u.dil = dil; u.pad_l = pad_l; u.act = act;
+  u.R = n_rows; u.Cin = c_in; u.N = c_out; u.taps = taps; u.dil = dil; u.pad_l = pad_l; u.act = act; u.split3 = split3;
   return umma_tf32(u, static_cast<cudaStream_t>(stream));
 }
 

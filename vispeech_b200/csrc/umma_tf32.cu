@@ -21,12 +21,13 @@ using namespace umma;
 constexpr int kLoaderWarps = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (kLoaderWarps + 2 + kEpiWarps);   // loaders | weight producer | MMA | epilogue
-constexpr int kKA = 96;            // channels per activation stage (24 planes of 4)
-constexpr int kSlabC = 32;         // channels per weight slab (8 planes, 4 MMAs of K = 8)
 constexpr int kSA = 2, kSB = 3;
+// plain TF32: 96 channels per activation stage, 32 per weight slab; 3xTF32: 48 / 16 with [hi|lo] pairs (same bytes)
 
 struct Plan {
   int rows_a, halo_l, n_ka, slabs_per_ka, Nblk, NB, NACC, tmem_cols, n_tiles, n_units;
+  int KA, slabC;          // channels per activation stage / per weight slab
+  uint32_t a_half, b_half; // byte offset of the lo copy inside a stage / slab (split3)
   uint32_t a_bytes, b_bytes, smem_bytes, off_b, off_bar;
 };
 struct Params {
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
       for (int ka = 0; ka < p.n_ka; ++ka) {
         mbar_wait(a_empty(slot), phase ^ 1, 11);
         const uint32_t stage = a_base + slot * p.a_bytes;
-        const int ch0 = ka * kKA;
-        const int n_planes = min(kKA, c.Cin - ch0) / 4;
+        const int ch0 = ka * p.KA;
+        const int n_planes = min(p.KA, c.Cin - ch0) / 4;
         for (int row = tid; row < p.rows_a; row += 32 * kLoaderWarps) {
           const int rg = row_lo + row;
           const bool ok = rg >= 0 && rg < c.R;
@@ -110,9 +111,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
           for (int pl = 0; pl < n_planes; ++pl) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) v = *reinterpret_cast<const float4*>(src + 4 * pl);
+            const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(pl * p.rows_a) * 16u),
-                         "f"(to_tf32(v.x)), "f"(to_tf32(v.y)), "f"(to_tf32(v.z)), "f"(to_tf32(v.w))
+                         "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
                          : "memory");
+            if (c.split3)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + p.a_half + (uint32_t)(pl * p.rows_a) * 16u),
+                           "f"(to_tf32(v.x - hi.x)), "f"(to_tf32(v.y - hi.y)), "f"(to_tf32(v.z - hi.z)), "f"(to_tf32(v.w - hi.w))
+                           : "memory");
           }
         }
         fence_proxy_async();                         // generic-proxy smem writes -> visible to the tensor core
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32), b_hi = (uint32_t)(make_desc(0, b_lbo, 128u) >> 32);
     const uint32_t a_lo_fixed = (uint32_t)make_desc(0, a_lbo, 128u), b_lo_fixed = (uint32_t)make_desc(0, b_lbo, 128u);
     const uint32_t a_kstep = 2u * (uint32_t)p.rows_a, b_kstep = 2u * (uint32_t)p.Nblk;
-    const uint32_t slab_planes = kSlabC / 4;
+    const uint32_t slab_planes = (uint32_t)p.slabC / 4;
     uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, acc_slot = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 13);
@@ -155,17 +161,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
         mbar_wait(a_full(a_slot), a_phase, 14);
         tc_fence_after();
         const uint32_t a_stage16 = (a_base + a_slot * p.a_bytes) >> 4;
-        const int slabs_here = min(kKA, c.Cin - ka * kKA) / kSlabC;
+        const int slabs_here = min(p.KA, c.Cin - ka * p.KA) / p.slabC;
         for (int t = 0; t < c.taps; ++t)
           for (int j = 0; j < slabs_here; ++j) {
             mbar_wait(b_full(b_slot), b_phase, 15);
             tc_fence_after();
             uint32_t a_lo = a_lo_fixed + a_stage16 + (uint32_t)j * slab_planes * (uint32_t)p.rows_a + (uint32_t)(t * c.dil);
             uint32_t b_lo = b_lo_fixed + ((b_base + b_slot * p.b_bytes) >> 4);
-#pragma unroll
-            for (int k8 = 0; k8 < kSlabC / 8; ++k8) {
+            for (int k8 = 0; k8 < p.slabC / 8; ++k8) {
               tc_mma_tf32_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
               accumulate = 1;
+              if (c.split3) {
+                tc_mma_tf32_lohi(d_tmem, a_lo + (p.a_half >> 4), a_hi, b_lo, b_hi, idesc, 1u);   // a_lo * w_hi
+                tc_mma_tf32_lohi(d_tmem, a_lo, a_hi, b_lo + (p.b_half >> 4), b_hi, idesc, 1u);   // a_hi * w_lo
+              }
               a_lo += a_kstep;
               b_lo += b_kstep;
             }
@@ -298,7 +307,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
 
 int make_plan(const UmmaTf32& c, Plan* out) {
   Plan p{};
-  VS_REQUIRE(c.Cin % kSlabC == 0, "umma_tf32: Cin=%d must be a multiple of %d", c.Cin, kSlabC);
   VS_REQUIRE(c.N % 32 == 0, "umma_tf32: N=%d must be a multiple of 32", c.N);
   VS_REQUIRE(c.R > 0 && c.taps >= 1 && c.dil >= 1 && c.pad_l >= 0, "umma_tf32: bad shape");
   VS_REQUIRE(c.in_ld % 4 == 0 && c.out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0 &&
@@ -311,15 +319,20 @@ int make_plan(const UmmaTf32& c, Plan* out) {
     if (c.N % nb == 0 && c.N / nb <= 256 && (c.N / nb) % 32 == 0) p.Nblk = c.N / nb;
   VS_REQUIRE(p.Nblk > 0, "umma_tf32: cannot split N=%d into <= 256-column blocks", c.N);
   p.NB = c.N / p.Nblk;
-  p.n_ka = (c.Cin + kKA - 1) / kKA;
-  p.slabs_per_ka = kKA / kSlabC;
-  VS_REQUIRE(c.Cin % kKA == 0 || c.Cin < kKA, "umma_tf32: Cin=%d must be < or a multiple of %d", c.Cin, kKA);
-  if (c.Cin < kKA) p.slabs_per_ka = c.Cin / kSlabC;
+  p.KA = c.split3 ? 48 : 96;
+  p.slabC = c.split3 ? 16 : 32;
+  VS_REQUIRE(c.Cin % p.slabC == 0, "umma_tf32: Cin=%d must be a multiple of %d", c.Cin, p.slabC);
+  p.n_ka = (c.Cin + p.KA - 1) / p.KA;
+  p.slabs_per_ka = p.KA / p.slabC;
+  VS_REQUIRE(c.Cin % p.KA == 0 || c.Cin < p.KA, "umma_tf32: Cin=%d must be < or a multiple of %d", c.Cin, p.KA);
+  if (c.Cin < p.KA) p.slabs_per_ka = c.Cin / p.slabC;
   p.halo_l = c.pad_l * c.dil;
   p.rows_a = kTileM + (c.taps - 1) * c.dil;
-  const int planes_stage = (c.Cin < kKA ? c.Cin : kKA) / 4;
-  p.a_bytes = (uint32_t)planes_stage * p.rows_a * 16u;
-  p.b_bytes = (uint32_t)kSlabC * p.Nblk * 4u;
+  const int planes_stage = (c.Cin < p.KA ? c.Cin : p.KA) / 4;
+  p.a_half = (uint32_t)planes_stage * p.rows_a * 16u;
+  p.a_bytes = p.a_half * (c.split3 ? 2u : 1u);
+  p.b_half = (uint32_t)p.slabC * p.Nblk * 4u;
+  p.b_bytes = p.b_half * (c.split3 ? 2u : 1u);
   p.NACC = 512 / p.Nblk;
   if (p.NACC > 8) p.NACC = 8;
   VS_REQUIRE(p.NACC >= 2, "umma_tf32: TMEM too small");

@@ -21,6 +21,10 @@ struct UmmaTf32 {
   //           writes acts = tanh(a_t) * sigmoid(a_s) to out[r][N/2]              (commons.py:100-107)
   //  epi = 2  res/skip update: n-blocks < nb_split are ADDED into out (h += res), the others go to out2 (skip), added
   //           when accumulate2 else assigned; invalid rows are left untouched (out2: zeroed when assigned)
+  // split3 = 1: error-compensated "3xTF32": a = a_hi + a_lo, w = w_hi + w_lo (each TF32), D += a_hi w_hi + a_lo w_hi +
+  // a_hi w_lo (the 2^-22 term a_lo w_lo is dropped): fp32-level accuracy on the tensor cores at 3x the MMA count.
+  // Weights then come in [hi | lo] slab pairs of 16 channels (packing.py pack_tf32(split3=True)).
+  int split3 = 0;
   int epi = 0;
   float* out2 = nullptr; int out2_ld = 0; int nb_split = 0; int accumulate2 = 0;
 };

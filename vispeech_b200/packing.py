@@ -75,15 +75,26 @@ def round_tf32(x: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def pack_tf32(w: torch.Tensor) -> torch.Tensor:
-    """[taps][Cin][N] fp32 -> TF32 slabs [NB][Cin/KA][taps][KA/32][8][Nblk][4] (csrc/umma_tf32.cuh), KA = min(Cin, 96)."""
+def pack_tf32(w: torch.Tensor, split3: bool = False) -> torch.Tensor:
+    """[taps][Cin][N] fp32 -> TF32 slabs (csrc/umma_tf32.cuh).
+    plain : [NB][Cin/KA][taps][KA/32][8 planes][Nblk][4], KA = min(Cin, 96), values rounded to TF32;
+    split3: [NB][Cin/KA][taps][KA/16][hi|lo][4 planes][Nblk][4], KA = min(Cin, 48), w = hi + lo (each TF32)."""
     taps, cin, n = w.shape
-    ka = min(cin, 96)
-    assert cin % ka == 0 and ka % 32 == 0
+    ka_max, slab = (48, 16) if split3 else (96, 32)
+    ka = min(cin, ka_max)
+    assert cin % ka == 0 and ka % slab == 0
     nblk = next(n // nb for nb in range(1, 9) if n % nb == 0 and n // nb <= 256 and (n // nb) % 32 == 0)
-    x = round_tf32(w).reshape(taps, cin // ka, ka // 32, 8, 4, n // nblk, nblk)
-    #                      t     ka         j        p  e   nb         n
-    return x.permute(5, 1, 0, 2, 3, 6, 4).contiguous().reshape(-1)
+
+    def slabs(x):
+        x = x.reshape(taps, cin // ka, ka // slab, slab // 4, 4, n // nblk, nblk)
+        #             t     ka         j           p          e  nb         n
+        return x.permute(5, 1, 0, 2, 3, 6, 4).contiguous()       # nb ka t j p n e
+
+    hi = round_tf32(w)
+    if not split3:
+        return slabs(hi).reshape(-1)
+    lo = round_tf32(w - hi)
+    return torch.stack([slabs(hi), slabs(lo)], dim=4).contiguous().reshape(-1)   # nb ka t j [hi|lo] p n e
 
 
 def gate_columns(h: int = 192) -> torch.Tensor:
@@ -211,12 +222,21 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
         tab = out["flow.%d.cond_tab" % f].reshape(emb_g.shape[0], flow_layers, 384)
         out["flow.%d.cond_tab_gate" % f] = tab[:, :, gperm].reshape(emb_g.shape[0], -1).contiguous()
         for l in range(flow_layers):
-            out["tf32.flow.%d.%d.in_gate.w" % (f, l)] = pack_tf32(out["flow.%d.%d.in.w" % (f, l)][:, :, gperm].contiguous())
+            out["flow.%d.%d.in_gate.w" % (f, l)] = out["flow.%d.%d.in.w" % (f, l)][:, :, gperm].contiguous()
             out["flow.%d.%d.in_gate.b" % (f, l)] = out["flow.%d.%d.in.b" % (f, l)][gperm].contiguous()
-    # TF32 tensor-core copies of the frame-level GEMM weights (flow, encoders, projection)
-    for name in list(out):
-        if name.endswith((".wqkv", ".wo")) or name == "proj.w" or name.endswith(("pre.w", "post.w", "rs.w")) and name.startswith("flow."):
-            out["tf32." + name] = pack_tf32(out[name][None])
-        elif (name.endswith((".w1", ".w2")) and not name.startswith(("dp.", "ep."))) or (name.endswith("in.w") and name.startswith("flow.")):
-            out["tf32." + name] = pack_tf32(out[name])
+    # tensor-core copies of the GEMM-shaped conv weights: "tf32." = plain TF32 (frame level, >= 4096 rows),
+    # "x3." = error-compensated 3xTF32 (fp32-level accuracy: phoneme level and small frame-level calls)
+    def is_gemm(name):
+        if name.startswith(("tf32.", "x3.", "dec", "emb")) or not name.endswith((".wqkv", ".wo", ".w1", ".w2", ".w")):
+            return False
+        return name.startswith(("enc_p.", "pitch_predictor.", "frame_prior_net.", "dp.w", "ep.w", "proj.", "flow."))
+    for name in [k for k in out if is_gemm(k)]:
+        w = out[name] if out[name].dim() == 3 else out[name][None]
+        if w.shape[1] % 32 == 0 and (w.shape[1] < 96 or w.shape[1] % 96 == 0) and w.shape[2] % 32 == 0:
+            out["tf32." + name] = pack_tf32(w)
+        if w.shape[1] % 16 == 0 and (w.shape[1] < 48 or w.shape[1] % 48 == 0) and w.shape[2] % 32 == 0:
+            out["x3." + name] = pack_tf32(w, split3=True)
+    for f in range(n_flows):
+        for l in range(flow_layers):
+            del out["flow.%d.%d.in_gate.w" % (f, l)]          # only its packed copies are used
     return {k: v.contiguous() for k, v in out.items()}
