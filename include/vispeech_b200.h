@@ -124,6 +124,13 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows_f, const float* x_f, con
 /* ---- a17: ResidualCouplingBlock reverse (models.py:202-209), in place on z ([n_rows][192]) */
 int vs_flow_reverse(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- 8(f) voice_conversion (models.py:724-732): PosteriorEncoder.forward (models.py:233-241) on a linear spectrogram
+ * laid out as ragged rows [n_rows][c_in] (c_in = spec channels zero-padded to a multiple of 96, see packing.py), and the
+ * flow in forward direction (models.py:203-205), in place.  Needs the enc_q.* tensors (VS_ERR_MISSING otherwise). */
+int vs_posterior_encode(const VsModel* m, const VsRows* rows_f, const float* spec, const float* noise /*[n_rows][192]*/,
+                        float* z, float* m_q, float* logs_q, void* ws, int64_t ws_bytes, void* stream);
+int vs_flow_forward(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- a18: HiFi-GAN Generator (models.py:271-290).  max_len < 0 = no truncation (models.py:720).
  * wave_out is [rows_f.n_rows * hop] in ragged order.  precision: 0 = bf16 tcgen05 path (product),
  * 1 = fp32 SIMT path (test-only cross-check of the same math, NOT a fallback). */

@@ -145,9 +145,9 @@ def expansion_indices(duration: torch.Tensor) -> torch.Tensor:
     return torch.repeat_interleave(torch.arange(n.numel()), n)
 
 
-def wn(sd, p, x, g, cfg: ModelConfig):
+def wn(sd, p, x, g, cfg: ModelConfig, n_layers=None):
     """modules.py:148-176 (WN.forward) with the fused gate of commons.py:100-107."""
-    H, L, k = cfg.hidden_channels, cfg.flow_layers, cfg.flow_kernel
+    H, L, k = cfg.hidden_channels, (n_layers or cfg.flow_layers), cfg.flow_kernel
     out = torch.zeros_like(x)
     gc = F.conv1d(g, fold_weight_norm(sd, p + ".cond_layer"), sd[p + ".cond_layer.bias"])
     for i in range(L):
@@ -178,6 +178,42 @@ def flow_reverse(sd, z_p, g, cfg: ModelConfig):
         m = F.conv1d(h, sd[p + ".post.weight"], sd[p + ".post.bias"])
         x = torch.cat([x0, x1 - m], 1)
     return x
+
+
+def flow_forward(sd, z, g, cfg: ModelConfig):
+    """models.py:203-205 forward branch: RCL0, Flip, ..., RCL3, Flip with x1 = m + x1 (mean_only, modules.py:334-338)."""
+    half = cfg.inter_channels // 2
+    x = z
+    for f in range(0, 2 * cfg.n_flows, 2):
+        p = "flow.flows.%d" % f
+        x0, x1 = x[:, :half], x[:, half:]
+        h = F.conv1d(x0, sd[p + ".pre.weight"], sd[p + ".pre.bias"])
+        h = wn(sd, p + ".enc", h, g, cfg)
+        m = F.conv1d(h, sd[p + ".post.weight"], sd[p + ".post.bias"])
+        x = torch.flip(torch.cat([x0, m + x1], 1), [1])
+    return x
+
+
+def posterior_encoder(sd, spec, g, noise, cfg: ModelConfig):
+    """models.py:233-241 for one un-padded utterance: spec [1, 1025, T] -> z, m, logs."""
+    x = F.conv1d(spec, sd["enc_q.pre.weight"], sd["enc_q.pre.bias"])
+    x = wn(sd, "enc_q.enc", x, g, cfg, n_layers=16)
+    stats = F.conv1d(x, sd["enc_q.proj.weight"], sd["enc_q.proj.bias"])
+    m, logs = stats[:, :cfg.inter_channels], stats[:, cfg.inter_channels:]
+    return m + noise.reshape(m.shape) * torch.exp(logs), m, logs
+
+
+@torch.no_grad()
+def voice_conversion_one(sd, spec: torch.Tensor, sid_src: int, sid_tgt: int, noise: torch.Tensor,
+                         cfg: ModelConfig = DEFAULT_CONFIG) -> Dict[str, torch.Tensor]:
+    """models.py:724-732 for one utterance: spec [1025, T] (linear spectrogram), noise [192, T]."""
+    g_src = sd["emb_g.weight"][int(sid_src)].reshape(1, -1, 1)
+    g_tgt = sd["emb_g.weight"][int(sid_tgt)].reshape(1, -1, 1)
+    z, m_q, logs_q = posterior_encoder(sd, spec[None].float(), g_src, noise, cfg)
+    z_p = flow_forward(sd, z, g_src, cfg)
+    z_hat = flow_reverse(sd, z_p, g_tgt, cfg)
+    o = generator(sd, z_hat, g_tgt, cfg)
+    return dict(z=z[0], m_q=m_q[0], logs_q=logs_q[0], z_p=z_p[0], z_hat=z_hat[0], o=o[0, 0])
 
 
 def resblock1(sd, p, x, k, dilations):

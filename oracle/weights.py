@@ -51,6 +51,7 @@ class ModelConfig:
     ep_filter: int = 768          # frame_prior_network.py:65
     sampling_rate: int = 44100
     hop_length: int = 512
+    spec_channels: int = 1025     # filter_length // 2 + 1 (inference.py:28)
 
     @property
     def head_dim(self) -> int:
@@ -60,8 +61,8 @@ class ModelConfig:
 DEFAULT_CONFIG = ModelConfig()
 
 
-def schema(cfg: ModelConfig = DEFAULT_CONFIG) -> List[Tuple[str, Tuple[int, ...], str]]:
-    """(key, shape, kind) for every tensor `infer` reads.  kind picks the initialiser."""
+def schema(cfg: ModelConfig = DEFAULT_CONFIG, with_vc: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) for every tensor `infer` reads (with_vc: plus enc_q.* for `voice_conversion`)."""
     H, F, G = cfg.hidden_channels, cfg.filter_channels, cfg.gin_channels
     dk, W = cfg.head_dim, 2 * cfg.window_size + 1
     out: List[Tuple[str, Tuple[int, ...], str]] = []
@@ -151,6 +152,14 @@ def schema(cfg: ModelConfig = DEFAULT_CONFIG) -> List[Tuple[str, Tuple[int, ...]
                 wn_conv("%s.convs1.%d" % (r, m), ch, ch, kk, ch * kk, ch)
                 wn_conv("%s.convs2.%d" % (r, m), ch, ch, kk, ch * kk, ch)
     conv("dec.conv_post", 1, ch, 7, bias=False)
+    if with_vc:   # PosteriorEncoder(spec_channels, inter, hidden, 5, 1, 16, gin) models.py:595-596
+        conv("enc_q.pre", H, cfg.spec_channels, 1)
+        conv("enc_q.proj", 2 * cfg.inter_channels, H, 1)
+        for i in range(16):
+            wn_conv("enc_q.enc.in_layers.%d" % i, 2 * H, H, 5, H * 5, 2 * H)
+            rs = 2 * H if i < 15 else H
+            wn_conv("enc_q.enc.res_skip_layers.%d" % i, rs, H, 1, H, rs)
+        wn_conv("enc_q.enc.cond_layer", 2 * H * 16, G, 1, G, 2 * H * 16)
     return out
 
 
@@ -161,10 +170,10 @@ def _gen_for(key: str, seed: int) -> torch.Generator:
     return g
 
 
-def make_state_dict(seed: int = 1234, cfg: ModelConfig = DEFAULT_CONFIG) -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 1234, cfg: ModelConfig = DEFAULT_CONFIG, with_vc: bool = False) -> Dict[str, torch.Tensor]:
     """fp32 CPU tensors keyed exactly like the reference `state_dict()` (un-folded weight norm)."""
     sd: Dict[str, torch.Tensor] = {}
-    entries = schema(cfg)
+    entries = schema(cfg, with_vc)
     for key, shape, kind in entries:
         if kind == "wn_g":
             continue

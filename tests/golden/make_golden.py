@@ -31,7 +31,7 @@ from oracle import inputs as oin                      # noqa: E402
 from oracle.weights import make_state_dict, schema    # noqa: E402
 
 
-def build_reference(sd):
+def build_reference(sd, with_vc=False):
     import utils  # reference
     logging.disable(logging.CRITICAL)
     from models import SynthesizerTrn
@@ -42,9 +42,9 @@ def build_reference(sd):
                          hps.train.segment_size // hps.data.hop_length, n_speakers=hps.data.n_speakers,
                          **hps.model).eval()
     ref_sd = net.state_dict()
-    off_path = ("enc_q.", "enc_p.proj.", "frame_prior_net.emb.", "energy_predictor.predictor.proj.")
+    off_path = ("enc_p.proj.", "frame_prior_net.emb.", "energy_predictor.predictor.proj.") + (() if with_vc else ("enc_q.",))
     on_path = {k: tuple(v.shape) for k, v in ref_sd.items() if not k.startswith(off_path)}
-    ours = {k: shp for k, shp, _ in schema()}
+    ours = {k: shp for k, shp, _ in schema(with_vc=with_vc)}
     assert set(on_path) == set(ours), (sorted(set(on_path) ^ set(ours))[:10])
     for k in on_path:
         assert on_path[k] == tuple(ours[k]) == tuple(sd[k].shape), k
@@ -113,7 +113,35 @@ def run_case(net, name, ids, sid, noise_scale, noise, max_len=None, energy_contr
         os.path.getsize(path) / 1024))
 
 
+def run_vc_case(net, name, spec, sid_src, sid_tgt, noise):
+    """voice_conversion (models.py:724-732), batch 1, eps of PosteriorEncoder (models.py:239) injected."""
+    real_randn_like = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: noise.reshape(t.shape).to(t.dtype)
+    try:
+        with torch.no_grad():
+            o_hat, y_mask, (z, z_p, z_hat) = net.voice_conversion(spec[None], torch.LongTensor([spec.shape[1]]),
+                                                                   torch.LongTensor([sid_src]), torch.LongTensor([sid_tgt]))
+    finally:
+        torch.randn_like = real_randn_like
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, spec=spec.numpy(), sid_src=np.int64(sid_src), sid_tgt=np.int64(sid_tgt), noise=noise.numpy(),
+                        z=z[0].numpy(), z_p=z_p[0].numpy(), z_hat=z_hat[0].numpy(), o=o_hat[0, 0].numpy(),
+                        y_mask=y_mask[0, 0].numpy())
+    print("%-14s T=%d samples=%d -> %s (%.0f KB)" % (name, spec.shape[1], o_hat.numel(), os.path.basename(path),
+                                                      os.path.getsize(path) / 1024))
+
+
+def main_vc():
+    sd = make_state_dict(1234, with_vc=True)
+    net = build_reference(sd, with_vc=True)
+    g = torch.Generator().manual_seed(123)
+    spec = torch.rand(1025, 23, generator=g) ** 2 * 4.0          # magnitude-spectrogram-like, non-negative
+    run_vc_case(net, "vc1", spec, 7, 64, torch.randn(192, 23, generator=g))
+
+
 def main():
+    if "--vc" in sys.argv:
+        return main_vc()
     sd = make_state_dict(1234)
     net = build_reference(sd)
     g = torch.Generator().manual_seed(99)

@@ -12,7 +12,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("vc"))
 
 
 @pytest.fixture(scope="module")
@@ -227,3 +228,41 @@ def test_predicted_durations_batch(net, state_dict):
         bad = (got != ref["duration"]) & ((w - torch.round(w)).abs() > 1e-3)
         assert not bool(bad.any())
         assert float((energy[b, :tp].cpu() - ref["energy"]).abs().max()) <= 1e-2
+
+
+def test_voice_conversion_matches_reference_golden():
+    """8(f) voice_conversion (models.py:724-732) vs the golden vector made by the unmodified reference, plus a ragged
+    batch vs the oracle (different lengths and speaker pairs)."""
+    from oracle.vispeech_oracle import voice_conversion_one
+    from oracle.weights import make_state_dict
+    from vispeech_b200 import build_from_hparams, get_hparams_from_file
+    sd = make_state_dict(1234, with_vc=True)
+    net = build_from_hparams(get_hparams_from_file(), device="cuda:0")
+    net.load_state_dict(sd)
+    d = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "vc1.npz")))
+    spec, eps = torch.from_numpy(d["spec"]), torch.from_numpy(d["noise"])
+    for precision, bar in ((1, 50.0), (0, 30.0)):
+        net.decoder_precision = precision
+        o, y_mask, (z, z_p, z_hat) = net.voice_conversion(spec[None], torch.LongTensor([spec.shape[1]]),
+                                                          torch.LongTensor([int(d["sid_src"])]),
+                                                          torch.LongTensor([int(d["sid_tgt"])]), noise=[eps])
+        torch.cuda.synchronize()
+        for k, got in (("z", z), ("z_p", z_p), ("z_hat", z_hat)):
+            assert float(np.abs(got[0].cpu().numpy() - d[k]).max()) <= 1e-2, k
+        assert snr_db(torch.from_numpy(d["o"]), o[0, 0].cpu()) >= bar
+        assert y_mask.shape == (1, 1, spec.shape[1]) and float(y_mask.sum()) == spec.shape[1]
+    net.decoder_precision = 0
+    g = torch.Generator().manual_seed(8)
+    lens = [40, 17, 33]
+    specs = [torch.rand(1025, n, generator=g) ** 2 * 4 for n in lens]
+    noises = [torch.randn(192, n, generator=g) for n in lens]
+    y = torch.zeros(3, 1025, 40)
+    for b, sp in enumerate(specs):
+        y[b, :, :lens[b]] = sp
+    o, y_mask, (z, z_p, z_hat) = net.voice_conversion(y, torch.LongTensor(lens), torch.LongTensor([1, 50, 199]),
+                                                      torch.LongTensor([2, 3, 0]), noise=noises)
+    torch.cuda.synchronize()
+    for b in range(3):
+        ref = voice_conversion_one(sd, specs[b], [1, 50, 199][b], [2, 3, 0][b], noises[b])
+        assert float((z_hat[b, :, :lens[b]].cpu() - ref["z_hat"]).abs().max()) <= 1e-2
+        assert snr_db(ref["o"], o[b, 0, :lens[b] * 512].cpu()) >= 30.0

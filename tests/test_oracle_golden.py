@@ -9,7 +9,9 @@ import torch
 from oracle import inputs as oin
 from oracle.vispeech_oracle import expansion_indices, infer_one
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("vc"))
+GOLDEN_VC = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "vc*.npz")))
 
 
 def _control(d, name):
@@ -69,3 +71,16 @@ def test_oracle_matches_reference(path, state_dict):
         assert float((o_ref - t["o"]).abs().max()) <= 2e-5
         assert snr_db(o_ref, t["o"]) > 80.0
     assert t["o"].numel() == o_ref.numel()
+
+
+@pytest.mark.parametrize("path", GOLDEN_VC, ids=[os.path.basename(p)[:-4] for p in GOLDEN_VC])
+def test_oracle_voice_conversion_matches_reference(path):
+    """8(f): voice_conversion (models.py:724-732) - posterior encoder, flow forward, flow reverse, decoder."""
+    from oracle.vispeech_oracle import voice_conversion_one
+    from oracle.weights import make_state_dict
+    d = dict(np.load(path))
+    sd = make_state_dict(1234, with_vc=True)
+    t = voice_conversion_one(sd, torch.from_numpy(d["spec"]), int(d["sid_src"]), int(d["sid_tgt"]), torch.from_numpy(d["noise"]))
+    for k in ("z", "z_p", "z_hat"):
+        assert float(np.abs(t[k].numpy() - d[k]).max()) <= 2e-4, k
+    assert float(np.abs(t["o"].numpy() - d["o"]).max()) <= 2e-5

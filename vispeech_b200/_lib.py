@@ -45,6 +45,9 @@ _SIGNATURES = {
     "vs_frame_prior": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_flow_reverse": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
+    "vs_flow_forward": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
+    "vs_posterior_encode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_void_p]),
     "vs_hifigan_decode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64,
                                     c_void_p]),
     "vs_unpack_rows": (c_int32, [POINTER(VsRows), c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

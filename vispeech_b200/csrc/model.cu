@@ -18,12 +18,26 @@ struct EncLayer {
   const float *t_wqkv, *t_wo, *t_w1, *t_w2;            // TF32 slab copies (umma_tf32.cuh)
   const float *x_wqkv, *x_wo, *x_w1, *x_w2;            // 3xTF32 [hi|lo] slab copies
 };
+constexpr int kMaxWnLayers = 16;
+// WN (modules.py:111-184) weights: flow coupling layers (4 layers) and the posterior encoder (16 layers)
+struct WnW {
+  int n_layers = 0;
+  const float* cond_tab = nullptr;                       // [n_spk][2H*L] = cond_layer(emb_g) incl. bias
+  const float* cond_tab_gate = nullptr;                  // same, gate-interleaved columns (packing.py gate_columns)
+  const float *in_w[kMaxWnLayers], *in_b[kMaxWnLayers], *rs_w[kMaxWnLayers], *rs_b[kMaxWnLayers];
+  const float *t_in[kMaxWnLayers], *t_rs[kMaxWnLayers], *t_in_gate[kMaxWnLayers], *in_gate_b[kMaxWnLayers];   // TF32
+  const float *x_in[kMaxWnLayers], *x_rs[kMaxWnLayers], *x_in_gate[kMaxWnLayers];                             // 3xTF32
+};
 struct FlowW {
-  const float *pre_w, *pre_b, *post_w, *post_b, *cond_tab;
-  const float *in_w[8], *in_b[8], *rs_w[8], *rs_b[8];
-  const float *t_pre, *t_post, *t_in[8], *t_rs[8];     // TF32 slab copies
-  const float *t_in_gate[8], *in_gate_b[8], *cond_tab_gate;   // gate-interleaved column order (packing.py gate_columns)
-  const float *x_pre, *x_post, *x_in[8], *x_rs[8], *x_in_gate[8];   // 3xTF32 copies
+  const float *pre_w, *pre_b, *post_w, *post_b;
+  const float *t_pre, *t_post, *x_pre, *x_post;
+  WnW wn;
+};
+struct PosteriorW {                                      // enc_q (models.py:212-241), only needed by voice_conversion
+  bool present = false;
+  int c_in = 0;                                          // spec channels padded to a multiple of 96 (packing.py)
+  const float *pre_w, *pre_b, *proj_w, *proj_b, *t_pre, *x_pre, *t_proj, *x_proj;
+  WnW wn;
 };
 
 // Precision / engine policy for the GEMM-shaped convs upstream of the decoder (all rows counts are per call):
@@ -63,6 +77,7 @@ struct VsModel {
   const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
   const float *proj_w, *proj_b, *t_proj_w, *x_proj_w, *x_dp_w1, *x_ep_w1, *x_ep_w2;
   std::vector<vs::FlowW> flows;
+  vs::PosteriorW enc_q;
   vs::DecoderW dec;
 };
 
@@ -102,6 +117,25 @@ static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::
   return VS_OK;
 }
 
+static int resolve_wn(VsModel* m, const std::string& p, int L, int S, WnW* w) {
+  const int H = kHidden;
+  VS_REQUIRE(L <= kMaxWnLayers, "WN with %d layers (max %d)", L, kMaxWnLayers);
+  w->n_layers = L;
+  FETCH_F32(w->cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
+  FETCH_F32(w->cond_tab_gate, p + "cond_tab_gate", (int64_t)S * 2 * H * L);
+  for (int l = 0; l < L; ++l) {
+    const std::string q = p + std::to_string(l) + ".";
+    const int rs = (l < L - 1) ? 2 * H : H;
+    FETCH_F32(w->in_w[l], q + "in.w", 5 * H * 2 * H);  FETCH_F32(w->in_b[l], q + "in.b", 2 * H);
+    FETCH_F32(w->rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w->rs_b[l], q + "rs.b", rs);
+    FETCH_F32(w->t_in[l], "tf32." + q + "in.w", 5 * H * 2 * H);  FETCH_F32(w->t_rs[l], "tf32." + q + "rs.w", H * rs);
+    FETCH_F32(w->t_in_gate[l], "tf32." + q + "in_gate.w", 5 * H * 2 * H);  FETCH_F32(w->in_gate_b[l], q + "in_gate.b", 2 * H);
+    FETCH_F32(w->x_in[l], "x3." + q + "in.w", 2 * 5 * H * 2 * H);  FETCH_F32(w->x_rs[l], "x3." + q + "rs.w", 2 * H * rs);
+    FETCH_F32(w->x_in_gate[l], "x3." + q + "in_gate.w", 2 * 5 * H * 2 * H);
+  }
+  return VS_OK;
+}
+
 static int finalize(VsModel* m) {
   const int H = kHidden, S = m->cfg.n_speakers;
   FETCH_F32(m->emb, "emb", (int64_t)m->cfg.n_vocab * H);
@@ -135,20 +169,20 @@ static int finalize(VsModel* m) {
     const std::string p = "flow." + std::to_string(f) + ".";
     FETCH_F32(w.pre_w, p + "pre.w", (H / 2) * H);   FETCH_F32(w.pre_b, p + "pre.b", H);
     FETCH_F32(w.post_w, p + "post.w", H * (H / 2)); FETCH_F32(w.post_b, p + "post.b", H / 2);
-    FETCH_F32(w.cond_tab, p + "cond_tab", (int64_t)S * 2 * H * L);
-    FETCH_F32(w.cond_tab_gate, p + "cond_tab_gate", (int64_t)S * 2 * H * L);
     FETCH_F32(w.t_pre, "tf32." + p + "pre.w", (H / 2) * H);   FETCH_F32(w.t_post, "tf32." + p + "post.w", H * (H / 2));
     FETCH_F32(w.x_pre, "x3." + p + "pre.w", 2 * (H / 2) * H); FETCH_F32(w.x_post, "x3." + p + "post.w", 2 * H * (H / 2));
-    for (int l = 0; l < L; ++l) {
-      const std::string q = p + std::to_string(l) + ".";
-      const int rs = (l < L - 1) ? 2 * H : H;
-      FETCH_F32(w.in_w[l], q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.in_b[l], q + "in.b", 2 * H);
-      FETCH_F32(w.rs_w[l], q + "rs.w", H * rs);         FETCH_F32(w.rs_b[l], q + "rs.b", rs);
-      FETCH_F32(w.t_in[l], "tf32." + q + "in.w", 5 * H * 2 * H);  FETCH_F32(w.t_rs[l], "tf32." + q + "rs.w", H * rs);
-      FETCH_F32(w.t_in_gate[l], "tf32." + q + "in_gate.w", 5 * H * 2 * H);  FETCH_F32(w.in_gate_b[l], q + "in_gate.b", 2 * H);
-      FETCH_F32(w.x_in[l], "x3." + q + "in.w", 2 * 5 * H * 2 * H);  FETCH_F32(w.x_rs[l], "x3." + q + "rs.w", 2 * H * rs);
-      FETCH_F32(w.x_in_gate[l], "x3." + q + "in_gate.w", 2 * 5 * H * 2 * H);
-    }
+    VS_TRY(resolve_wn(m, p, L, S, &w.wn));
+  }
+  // posterior encoder: optional (inference never touches it; voice_conversion does)
+  m->enc_q.present = m->tensors.count("enc_q.pre.w") != 0;
+  if (m->enc_q.present) {
+    PosteriorW& q = m->enc_q;
+    q.c_in = (int)(m->tensors["enc_q.pre.w"].numel / H);
+    FETCH_F32(q.pre_w, "enc_q.pre.w", (int64_t)q.c_in * H);     FETCH_F32(q.pre_b, "enc_q.pre.b", H);
+    FETCH_F32(q.proj_w, "enc_q.proj.w", H * 2 * H);              FETCH_F32(q.proj_b, "enc_q.proj.b", 2 * H);
+    FETCH_F32(q.t_pre, "tf32.enc_q.pre.w", (int64_t)q.c_in * H); FETCH_F32(q.x_pre, "x3.enc_q.pre.w", (int64_t)2 * q.c_in * H);
+    FETCH_F32(q.t_proj, "tf32.enc_q.proj.w", H * 2 * H);         FETCH_F32(q.x_proj, "x3.enc_q.proj.w", 2 * H * 2 * H);
+    VS_TRY(resolve_wn(m, "enc_q.", 16, S, &q.wn));
   }
   VS_TRY(resolve_decoder(
       [m](const std::string& name, int64_t numel, int32_t dtype, const void** out) { return fetch(m, name, numel, dtype, out); },
@@ -257,7 +291,7 @@ int64_t vs_workspace_bytes(const VsModel* m, int32_t rp, int32_t rf) {
   const int64_t enc_p = encoder_ws_floats(rp), enc_f = encoder_ws_floats(rf);
   const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8);
   const int64_t prior = enc_f + (int64_t)rf * 2 * H;
-  const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + H / 2);
+  const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + 2 * H);   // also covers vs_posterior_encode
   const int64_t dec = decoder_ws_floats(rf);
   int64_t mx = variance;
   if (prior > mx) mx = prior;
@@ -369,60 +403,108 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 
-int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, int64_t ws_bytes, void* stream) {
-  VS_ENTER(m, rows, "vs_flow_reverse");
-  const int R = rows->n_rows, H = kHidden, L = m->cfg.flow_layers;
+// WN.forward (modules.py:148-176): h is consumed (updated in place), skip receives the output (already masked).
+struct WnBufs { float *a, *acts, *rs; };
+static int wn_forward(const WnW& w, const VsRows& rows, float* h, float* skip, const WnBufs& b, cudaStream_t st) {
+  const int R = rows.n_rows, H = kHidden, L = w.n_layers;
+  const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
+  const bool fused_wn = wn_tf32 || wn_x3;            // tensor-core path: gate and res/skip update live in the conv epilogues
+  for (int l = 0; l < L; ++l) {
+    const int rsC = (l < L - 1) ? 2 * H : H;
+    if (fused_wn) {
+      UmmaTf32 u;                                                          // acts = tanh . sigmoid (in_layer(h) + g_l)
+      u.in = h; u.in_ld = H; u.w = wn_tf32 ? w.t_in_gate[l] : w.x_in_gate[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.in_gate_b[l];
+      u.ubias = w.cond_tab_gate + (size_t)2 * H * l; u.ubias_ld = 2 * H * L; u.ubias_idx = rows.sid;
+      u.out = b.acts; u.out_ld = H; u.row_utt = rows.row_utt; u.R = R; u.Cin = H; u.N = 2 * H; u.taps = 5; u.pad_l = 2;
+      u.epi = 1;
+      VS_TRY(umma_tf32(u, st));
+      u = UmmaTf32();                                                      // h += rs[:, :H]; skip (+)= rs[:, H:]
+      u.in = b.acts; u.in_ld = H; u.w = wn_tf32 ? w.t_rs[l] : w.x_rs[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.rs_b[l];
+      u.out = h; u.out_ld = H; u.out2 = skip; u.out2_ld = H;
+      u.nb_split = (l < L - 1) ? 1 : 0; u.accumulate2 = (l > 0); u.row_utt = rows.row_utt; u.R = R; u.Cin = H; u.N = rsC;
+      u.epi = 2;
+      VS_TRY(umma_tf32(u, st));
+      continue;
+    }
+    ConvF32 c;
+    c.R = R;
+    c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = b.a; c.out_ld = 2 * H; c.Cout = 2 * H;
+    c.k = 5; c.pad_l = 2;
+    VS_TRY(conv_rows(c, w.t_in[l], w.x_in[l], st));
+    VS_TRY(wn_gate(b.a, w.cond_tab, 2 * H * L, 2 * H * l, rows, b.acts, st));
+    c = ConvF32(); c.R = R;
+    c.in = b.acts; c.in_ld = H; c.Cin = H; c.w = w.rs_w[l]; c.bias = w.rs_b[l]; c.out = b.rs; c.out_ld = rsC; c.Cout = rsC;
+    VS_TRY(conv_rows(c, w.t_rs[l], w.x_rs[l], st));
+    VS_TRY(wn_update(b.rs, rsC, l == L - 1, l == 0, rows, h, skip, st));
+  }
+  return VS_OK;
+}
+
+// ResidualCouplingBlock (models.py:177-209), mean-only layers (modules.py:324-343), in place on z.
+// reverse: Flip,RCL3,Flip,RCL2,Flip,RCL1,Flip,RCL0 with x1 -= m;  forward: RCL0,Flip,...,RCL3,Flip with x1 += m.
+// The Flips are folded into packed weights: layer f runs on the physically un-flipped tensor with `flipped = f odd`
+// in BOTH directions (packing.py).
+static int flow_run(const VsModel* m, const VsRows* rows, float* z, bool reverse, Workspace& W, cudaStream_t st) {
+  const int R = rows->n_rows, H = kHidden, F = m->cfg.n_flows;
   float* h = W.take<float>((int64_t)R * H);
-  float* a = W.take<float>((int64_t)R * 2 * H);
-  float* acts = W.take<float>((int64_t)R * H);
-  float* rs = W.take<float>((int64_t)R * 2 * H);
+  WnBufs b;
+  b.a = W.take<float>((int64_t)R * 2 * H);
+  b.acts = W.take<float>((int64_t)R * H);
+  b.rs = W.take<float>((int64_t)R * 2 * H);
   float* skip = W.take<float>((int64_t)R * H);
   float* mm = W.take<float>((int64_t)R * (H / 2));
-  if (!W.ok) { set_error("vs_flow_reverse: workspace too small"); return VS_ERR_WORKSPACE; }
-  // reversed(flows) = Flip,RCL3,Flip,RCL2,Flip,RCL1,Flip,RCL0 (models.py:206-208).  The Flips are folded into
-  // packed weights: layer f runs on the physically un-flipped tensor with `flipped = f odd` (packing.py).
-  for (int f = m->cfg.n_flows - 1; f >= 0; --f) {
+  if (!W.ok) { set_error("flow: workspace too small"); return VS_ERR_WORKSPACE; }
+  for (int i = 0; i < F; ++i) {
+    const int f = reverse ? F - 1 - i : i;
     const FlowW& w = m->flows[f];
     const bool flipped = (f & 1) != 0;
     const int in_off = flipped ? H / 2 : 0, upd_off = flipped ? 0 : H / 2;
     ConvF32 c;
     c.R = R; c.row_utt = rows->row_utt;
     c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;
-    VS_TRY(conv_rows(c, w.t_pre, w.x_pre, st));                                     // h = pre(x0) * mask  (modules.py:326)
-    const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
-    const bool fused_wn = wn_tf32 || wn_x3;          // tensor-core path: gate and res/skip update live in the conv epilogues
-    for (int l = 0; l < L; ++l) {                                          // WN.forward (modules.py:148-176)
-      const int rsC = (l < L - 1) ? 2 * H : H;
-      if (fused_wn) {
-        UmmaTf32 u;                                                        // acts = tanh . sigmoid (in_layer(h) + g_l)
-        u.in = h; u.in_ld = H; u.w = wn_tf32 ? w.t_in_gate[l] : w.x_in_gate[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.in_gate_b[l];
-        u.ubias = w.cond_tab_gate + (size_t)2 * H * l; u.ubias_ld = 2 * H * L; u.ubias_idx = rows->sid;
-        u.out = acts; u.out_ld = H; u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = 2 * H; u.taps = 5; u.pad_l = 2;
-        u.epi = 1;
-        VS_TRY(umma_tf32(u, st));
-        u = UmmaTf32();                                                    // h += rs[:, :H]; skip (+)= rs[:, H:]
-        u.in = acts; u.in_ld = H; u.w = wn_tf32 ? w.t_rs[l] : w.x_rs[l]; u.split3 = wn_x3 ? 1 : 0; u.bias = w.rs_b[l]; u.out = h; u.out_ld = H; u.out2 = skip; u.out2_ld = H;
-        u.nb_split = (l < L - 1) ? 1 : 0; u.accumulate2 = (l > 0); u.row_utt = rows->row_utt; u.R = R; u.Cin = H; u.N = rsC;
-        u.epi = 2;
-        VS_TRY(umma_tf32(u, st));
-        continue;
-      }
-      c = ConvF32(); c.R = R;
-      c.in = h; c.in_ld = H; c.Cin = H; c.w = w.in_w[l]; c.bias = w.in_b[l]; c.out = a; c.out_ld = 2 * H; c.Cout = 2 * H;
-      c.k = 5; c.pad_l = 2;
-      VS_TRY(conv_rows(c, w.t_in[l], w.x_in[l], st));
-      VS_TRY(wn_gate(a, w.cond_tab, 2 * H * L, 2 * H * l, *rows, acts, st));
-      c = ConvF32(); c.R = R;
-      c.in = acts; c.in_ld = H; c.Cin = H; c.w = w.rs_w[l]; c.bias = w.rs_b[l]; c.out = rs; c.out_ld = rsC; c.Cout = rsC;
-      VS_TRY(conv_rows(c, w.t_rs[l], w.x_rs[l], st));
-      VS_TRY(wn_update(rs, rsC, l == L - 1, l == 0, *rows, h, skip, st));
-    }
+    VS_TRY(conv_rows(c, w.t_pre, w.x_pre, st));                            // h = pre(x0) * mask  (modules.py:326)
+    VS_TRY(wn_forward(w.wn, *rows, h, skip, b, st));
     c = ConvF32(); c.R = R;
     c.in = skip; c.in_ld = H; c.Cin = H; c.w = w.post_w; c.bias = w.post_b; c.out = mm; c.out_ld = H / 2; c.Cout = H / 2;
-    VS_TRY(conv_rows(c, w.t_post, w.x_post, st));                                    // m = post(h) (modules.py:328)
-    VS_TRY(coupling_sub(z, upd_off, mm, *rows, st));                       // x1 = (x1 - m) * mask (modules.py:341)
+    VS_TRY(conv_rows(c, w.t_post, w.x_post, st));                          // m = post(h) (modules.py:328)
+    VS_TRY(coupling_update(z, upd_off, mm, reverse ? -1.f : 1.f, *rows, st));   // x1 = (x1 -/+ m) * mask (modules.py:336,341)
   }
   return VS_OK;
+}
+
+int vs_flow_reverse(const VsModel* m, const VsRows* rows, float* z, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_flow_reverse");
+  return flow_run(m, rows, z, true, W, st);
+}
+
+int vs_flow_forward(const VsModel* m, const VsRows* rows, float* z, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_flow_forward");
+  return flow_run(m, rows, z, false, W, st);
+}
+
+int vs_posterior_encode(const VsModel* m, const VsRows* rows, const float* spec, const float* noise, float* z, float* m_q,
+                        float* logs_q, void* ws, int64_t ws_bytes, void* stream) {
+  VS_ENTER(m, rows, "vs_posterior_encode");
+  if (!m->enc_q.present) { set_error("vs_posterior_encode: enc_q.* weights were not registered"); return VS_ERR_MISSING; }
+  const PosteriorW& q = m->enc_q;
+  const int R = rows->n_rows, H = kHidden;
+  float* h = W.take<float>((int64_t)R * H);
+  WnBufs b;
+  b.a = W.take<float>((int64_t)R * 2 * H);
+  b.acts = W.take<float>((int64_t)R * H);
+  b.rs = W.take<float>((int64_t)R * 2 * H);
+  float* skip = W.take<float>((int64_t)R * H);
+  float* stats = W.take<float>((int64_t)R * 2 * H);
+  if (!W.ok) { set_error("vs_posterior_encode: workspace too small"); return VS_ERR_WORKSPACE; }
+  ConvF32 c;
+  c.R = R; c.row_utt = rows->row_utt; c.in = spec; c.in_ld = q.c_in; c.Cin = q.c_in; c.w = q.pre_w; c.bias = q.pre_b;
+  c.out = h; c.out_ld = H; c.Cout = H;
+  VS_TRY(conv_rows(c, q.t_pre, q.x_pre, st));                              // x = pre(x) * x_mask  (models.py:235)
+  VS_TRY(wn_forward(q.wn, *rows, h, skip, b, st));                         // enc (16-layer WN)  (models.py:236)
+  c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.in = skip; c.in_ld = H; c.Cin = H; c.w = q.proj_w; c.bias = q.proj_b;
+  c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
+  VS_TRY(conv_rows(c, q.t_proj, q.x_proj, st));                            // stats = proj(x) * x_mask  (models.py:237)
+  return prior_sample(stats, noise, 1.f, *rows, m_q, logs_q, z, st);       // z = (m + eps*exp(logs)) * x_mask  (:239)
 }
 
 int vs_hifigan_decode(const VsModel* m, const VsRows* rows, const float* z, int32_t max_len, float* wave_out,

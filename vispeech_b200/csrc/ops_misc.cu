@@ -251,18 +251,19 @@ int wn_update(const float* rs, int rs_ld, int last, int first, const VsRows& row
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
-// coupling reverse with mean_only (modules.py:340-343): x1 = (x1 - m) on valid rows
-__global__ void coupling_sub_kernel(float* __restrict__ z, int z_off, const float* __restrict__ m,
-                                    const int32_t* __restrict__ row_utt, int R) {
+// coupling with mean_only (modules.py:334-343): x1 = x1 + sign * m on valid rows (sign -1: reverse, +1: forward)
+__global__ void coupling_update_kernel(float* __restrict__ z, int z_off, const float* __restrict__ m, float sign,
+                                       const int32_t* __restrict__ row_utt, int R) {
   const int half = kHidden / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * half) return;
   const int r = i / half, c = i % half;
   if (row_utt[r] < 0) return;
-  z[(size_t)r * kHidden + z_off + c] -= m[i];
+  z[(size_t)r * kHidden + z_off + c] += sign * m[i];
 }
-int coupling_sub(float* z, int z_off, const float* m, const VsRows& rows, cudaStream_t st) {
-  coupling_sub_kernel<<<(rows.n_rows * (kHidden / 2) + 255) / 256, 256, 0, st>>>(z, z_off, m, rows.row_utt, rows.n_rows);
+int coupling_update(float* z, int z_off, const float* m, float sign, const VsRows& rows, cudaStream_t st) {
+  coupling_update_kernel<<<(rows.n_rows * (kHidden / 2) + 255) / 256, 256, 0, st>>>(z, z_off, m, sign, rows.row_utt,
+                                                                                   rows.n_rows);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -21,7 +21,7 @@ int wn_gate(const float* a, const float* cond, int cond_ld, int cond_off, const 
             cudaStream_t st);
 int wn_update(const float* rs, int rs_ld, int last, int first, const VsRows& rows, float* h, float* skip,
               cudaStream_t st);
-int coupling_sub(float* z, int z_off, const float* m, const VsRows& rows, cudaStream_t st);
+int coupling_update(float* z, int z_off, const float* m, float sign, const VsRows& rows, cudaStream_t st);
 int mask_frames(const VsRows& rows, int max_len, int32_t* row_utt_out, cudaStream_t st);
 int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C, cudaStream_t st);
 int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st);

@@ -185,6 +185,23 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
             out["%s%d.rs.w" % (dst, l)] = tcn(fold(sd, "%s.enc.res_skip_layers.%d" % (src, l)))[0].contiguous()
             out["%s%d.rs.b" % (dst, l)] = sd["%s.enc.res_skip_layers.%d.bias" % (src, l)]
 
+    # ---- posterior encoder (only voice_conversion uses it; skipped when the checkpoint has no enc_q.*)
+    wn_prefixes = [("flow.%d." % f, flow_layers) for f in range(n_flows)]
+    if "enc_q.pre.weight" in sd:
+        pre = tcn(sd["enc_q.pre.weight"])[0]                      # [1025][192]
+        c_pad = -(-pre.shape[0] // 96) * 96                       # 1056: multiple of 96 (TF32 stage) and 48 (3xTF32)
+        out["enc_q.pre.w"] = torch.cat([pre, torch.zeros(c_pad - pre.shape[0], pre.shape[1])], 0).contiguous()
+        out["enc_q.pre.b"] = sd["enc_q.pre.bias"]
+        out["enc_q.proj.w"], out["enc_q.proj.b"] = tcn(sd["enc_q.proj.weight"])[0].contiguous(), sd["enc_q.proj.bias"]
+        n_q = 16
+        out["enc_q.cond_tab"] = cond_table(fold(sd, "enc_q.enc.cond_layer"), sd["enc_q.enc.cond_layer.bias"])
+        for l in range(n_q):
+            out["enc_q.%d.in.w" % l] = tcn(fold(sd, "enc_q.enc.in_layers.%d" % l))
+            out["enc_q.%d.in.b" % l] = sd["enc_q.enc.in_layers.%d.bias" % l]
+            out["enc_q.%d.rs.w" % l] = tcn(fold(sd, "enc_q.enc.res_skip_layers.%d" % l))[0].contiguous()
+            out["enc_q.%d.rs.b" % l] = sd["enc_q.enc.res_skip_layers.%d.bias" % l]
+        wn_prefixes.append(("enc_q.", n_q))
+
     # ---- decoder
     out["dec.pre.w"], out["dec.pre.b"] = tcn(sd["dec.conv_pre.weight"]), sd["dec.conv_pre.bias"]
     out["dec16.pre.w"] = pack_umma(out["dec.pre.w"])
@@ -218,25 +235,25 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
                     out["dec16.rb.%d.%s.%d.w" % (n, cname, m)] = pack_umma(w)
     # WN in_layers for the fused tanh*sigmoid epilogue: gate-interleaved columns (weights, bias, per-speaker cond)
     gperm = gate_columns(192)
-    for f in range(n_flows):
-        tab = out["flow.%d.cond_tab" % f].reshape(emb_g.shape[0], flow_layers, 384)
-        out["flow.%d.cond_tab_gate" % f] = tab[:, :, gperm].reshape(emb_g.shape[0], -1).contiguous()
-        for l in range(flow_layers):
-            out["flow.%d.%d.in_gate.w" % (f, l)] = out["flow.%d.%d.in.w" % (f, l)][:, :, gperm].contiguous()
-            out["flow.%d.%d.in_gate.b" % (f, l)] = out["flow.%d.%d.in.b" % (f, l)][gperm].contiguous()
+    for pre_, nl in wn_prefixes:
+        tab = out[pre_ + "cond_tab"].reshape(emb_g.shape[0], nl, 384)
+        out[pre_ + "cond_tab_gate"] = tab[:, :, gperm].reshape(emb_g.shape[0], -1).contiguous()
+        for l in range(nl):
+            out["%s%d.in_gate.w" % (pre_, l)] = out["%s%d.in.w" % (pre_, l)][:, :, gperm].contiguous()
+            out["%s%d.in_gate.b" % (pre_, l)] = out["%s%d.in.b" % (pre_, l)][gperm].contiguous()
     # tensor-core copies of the GEMM-shaped conv weights: "tf32." = plain TF32 (frame level, >= 4096 rows),
     # "x3." = error-compensated 3xTF32 (fp32-level accuracy: phoneme level and small frame-level calls)
     def is_gemm(name):
         if name.startswith(("tf32.", "x3.", "dec", "emb")) or not name.endswith((".wqkv", ".wo", ".w1", ".w2", ".w")):
             return False
-        return name.startswith(("enc_p.", "pitch_predictor.", "frame_prior_net.", "dp.w", "ep.w", "proj.", "flow."))
+        return name.startswith(("enc_p.", "pitch_predictor.", "frame_prior_net.", "dp.w", "ep.w", "proj.", "flow.", "enc_q."))
     for name in [k for k in out if is_gemm(k)]:
         w = out[name] if out[name].dim() == 3 else out[name][None]
         if w.shape[1] % 32 == 0 and (w.shape[1] < 96 or w.shape[1] % 96 == 0) and w.shape[2] % 32 == 0:
             out["tf32." + name] = pack_tf32(w)
         if w.shape[1] % 16 == 0 and (w.shape[1] < 48 or w.shape[1] % 48 == 0) and w.shape[2] % 32 == 0:
             out["x3." + name] = pack_tf32(w, split3=True)
-    for f in range(n_flows):
-        for l in range(flow_layers):
-            del out["flow.%d.%d.in_gate.w" % (f, l)]          # only its packed copies are used
+    for pre_, nl in wn_prefixes:
+        for l in range(nl):
+            del out["%s%d.in_gate.w" % (pre_, l)]              # only its packed copies are used
     return {k: v.contiguous() for k, v in out.items()}

@@ -298,6 +298,67 @@ class SynthesizerTrn:
         return self.run(P, outputs)
 
 
+    # ------------------------------------------------------------------------------------------------
+    # 8(f): voice_conversion (reference models.py:724-732)
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def voice_conversion(self, y, y_lengths, sid_src, sid_tgt, noise=None):
+        """y: linear spectrogram [B, spec_channels, T]; returns (o_hat [B,1,hop*T], y_mask [B,1,T] float,
+        (z, z_p, z_hat) [B,192,T]) like the reference.  `noise`: optional eps of PosteriorEncoder (models.py:239),
+        [B,192,T] tensor or list of [192,T_b].  Needs a checkpoint that still has enc_q.* (training checkpoints do)."""
+        if not self._loaded:
+            raise _lib.VsError("load_state_dict()/load_checkpoint() first")
+        if "enc_q.pre.w" not in self._weights:
+            raise _lib.VsError("voice_conversion needs the enc_q.* (posterior encoder) weights in the state dict")
+        lib, dev = self._lib, self.device
+        B, C, T = y.shape
+        lens = y_lengths.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        src = sid_src.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        tgt = sid_tgt.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        if lens.shape[0] != B or src.shape[0] != B or tgt.shape[0] != B or lens.min() < 1 or lens.max() > T:
+            raise ValueError("y_lengths / sid_src / sid_tgt must have one valid entry per utterance")
+        c_pad = self._weights["enc_q.pre.w"].shape[0]
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rows_src = make_rows(lens, src, FRAME_GAP, dev)
+            rows_tgt = make_rows(lens, tgt, FRAME_GAP, dev)       # same layout, target speakers
+            R = rows_src.n_rows
+            yh = y.detach().float().cpu().numpy()
+            spec = torch.from_numpy(rows_src.scatter([np.pad(yh[b, :, :lens[b]].T, ((0, 0), (0, c_pad - C))) for b in range(B)],
+                                                     np.float32, width=c_pad)).to(dev)
+            if noise is None:
+                eps = torch.randn(R, 192, dtype=torch.float32, device=dev)
+            else:
+                per = [(noise[b] if not isinstance(noise, torch.Tensor) else noise[b])[:, :lens[b]].t().cpu().numpy()
+                       for b in range(B)]
+                eps = _upload(rows_src.scatter(per, np.float32, width=192), dev)
+            ws = self._workspace(16, R)
+            z = torch.empty(R, 192, dtype=torch.float32, device=dev)
+            m_q, logs_q = torch.empty_like(z), torch.empty_like(z)
+            check(lib.vs_posterior_encode(self._model, ctypes.byref(rows_src.struct), ptr(spec), ptr(eps), ptr(z), ptr(m_q),
+                                          ptr(logs_q), ptr(ws), ws.numel(), stream), "vs_posterior_encode")
+            z_p = z.clone()
+            check(lib.vs_flow_forward(self._model, ctypes.byref(rows_src.struct), ptr(z_p), ptr(ws), ws.numel(), stream),
+                  "vs_flow_forward")
+            z_hat = z_p.clone()
+            check(lib.vs_flow_reverse(self._model, ctypes.byref(rows_tgt.struct), ptr(z_hat), ptr(ws), ws.numel(), stream),
+                  "vs_flow_reverse")
+            wave = torch.empty(R * self.hop_length, dtype=torch.float32, device=dev)
+            check(lib.vs_hifigan_decode(self._model, ctypes.byref(rows_tgt.struct), ptr(z_hat), -1, ptr(wave),
+                                        int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
+
+            def unpack(srct, Cc, mul, t_max):
+                out = torch.empty(B, Cc, t_max, dtype=torch.float32, device=dev)
+                check(lib.vs_unpack_rows(ctypes.byref(rows_src.struct), ptr(srct), Cc, mul, t_max, ptr(out), stream),
+                      "vs_unpack_rows")
+                return out
+
+            tm = int(lens.max())
+            o = unpack(wave, 1, self.hop_length, tm * self.hop_length)
+            y_mask = (torch.arange(tm, device=dev)[None, :] < torch.from_numpy(lens).to(dev)[:, None])[:, None, :].float()
+            return o, y_mask, tuple(unpack(t, 192, 1, tm) for t in (z, z_p, z_hat))
+
+
 class Prepared:
     """Device-resident inputs + row layouts of one `infer` call (see SynthesizerTrn.prepare)."""
 
