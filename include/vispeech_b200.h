@@ -141,6 +141,12 @@ int vs_hifigan_decode(const VsModel* m, const VsRows* rows_f, const float* z, in
 int vs_unpack_rows(const VsRows* rows, const float* x /*[n_rows*rows_mul][C]*/, int32_t C, int32_t rows_mul,
                    int32_t t_max, float* out /*[n_utt][C][t_max]*/, void* stream);
 
+/* ---- 8(f) waveform post-processing on the GPU (replaces scipy wavfile.write + `ffmpeg -ar 22050`, inference_api.py:50-51):
+ * wave [n_utt][t_max] fp32 -> out [n_utt][t_out] s16 = clip(rint(32768 * FIR-decimated wave)); samples beyond
+ * n_samples[b] count as zero.  decimate = 1 with n_taps = 0 is a plain conversion. */
+int vs_wave_pcm16(const float* wave, int32_t n_utt, int32_t t_max, const int32_t* n_samples, int32_t decimate,
+                  const float* fir /*[n_taps] or NULL*/, int32_t n_taps, int16_t* out, int32_t t_out, void* stream);
+
 /* ---- op-level entry points (used by the parity tests; same kernels as above) */
 int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w /*[k][Cin][Cout]*/, const float* bias,
                      float* out, int32_t out_ld, int32_t n_rows, int32_t c_in, int32_t c_out, int32_t k, int32_t dil,

@@ -521,6 +521,11 @@ int vs_unpack_rows(const VsRows* rows, const float* x, int32_t C, int32_t rows_m
   return unpack_rows(*rows, x, C, rows_mul, t_max, out, static_cast<cudaStream_t>(stream));
 }
 
+int vs_wave_pcm16(const float* wave, int32_t n_utt, int32_t t_max, const int32_t* n_samples, int32_t decimate,
+                  const float* fir, int32_t n_taps, int16_t* out, int32_t t_out, void* stream) {
+  return pcm16(wave, n_utt, t_max, n_samples, decimate, fir, n_taps, out, t_out, static_cast<cudaStream_t>(stream));
+}
+
 int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w, const float* bias, float* out, int32_t out_ld,
                      int32_t n_rows, int32_t c_in, int32_t c_out, int32_t k, int32_t dil, int32_t pad_l, float in_slope,
                      int32_t act, const int32_t* row_utt, int32_t row_div, void* stream) {

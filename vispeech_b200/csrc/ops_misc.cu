@@ -349,4 +349,42 @@ int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, f
   return VS_OK;
 }
 
+// ---- 8(f) waveform post-processing (reference inference_api.py:50-51: scipy wav write + `ffmpeg -ar 22050`) ------------
+// out[b][t] = s16( sum_k fir[k] * x[b][decimate*t + k - ntaps/2] ), samples outside [0, n_samples[b]) are zero;
+// decimate == 1 and ntaps == 0: plain float -> s16.  s16(v) = clip(rint(v * 32768)) (round half to even), ffmpeg's rule.
+__global__ void pcm16_kernel(const float* __restrict__ x, int T, const int32_t* __restrict__ n_samples, int decimate,
+                             const float* __restrict__ fir, int ntaps, int16_t* __restrict__ out, int T_out) {
+  extern __shared__ float taps[];
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) taps[i] = fir[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_out) return;
+  const int n = n_samples[b];
+  const float* xb = x + (size_t)b * T;
+  float v = 0.f;
+  if (ntaps == 0) {
+    const int i = decimate * t;
+    v = (i < n && i < T) ? xb[i] : 0.f;
+  } else {
+    const int c = decimate * t - ntaps / 2;
+    for (int k = 0; k < ntaps; ++k) {
+      const int i = c + k;
+      if (i >= 0 && i < n && i < T) v = fmaf(taps[k], xb[i], v);
+    }
+  }
+  int q = __float2int_rn(v * 32768.f);
+  q = q > 32767 ? 32767 : (q < -32768 ? -32768 : q);
+  out[(size_t)b * T_out + t] = (int16_t)q;
+}
+int pcm16(const float* x, int B, int T, const int32_t* n_samples, int decimate, const float* fir, int ntaps, int16_t* out,
+          int T_out, cudaStream_t st) {
+  VS_REQUIRE(B > 0 && T > 0 && T_out > 0 && decimate >= 1 && ntaps >= 0 && ntaps <= 1024 && (ntaps == 0 || fir),
+             "pcm16: bad arguments");
+  dim3 grid((T_out + 255) / 256, B);
+  pcm16_kernel<<<grid, 256, sizeof(float) * (ntaps > 0 ? ntaps : 1), st>>>(x, T, n_samples, decimate, fir, ntaps, out, T_out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
 }  // namespace vs

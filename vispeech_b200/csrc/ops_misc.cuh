@@ -25,5 +25,7 @@ int coupling_update(float* z, int z_off, const float* m, float sign, const VsRow
 int mask_frames(const VsRows& rows, int max_len, int32_t* row_utt_out, cudaStream_t st);
 int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C, cudaStream_t st);
 int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st);
+int pcm16(const float* x, int B, int T, const int32_t* n_samples, int decimate, const float* fir, int ntaps, int16_t* out,
+          int T_out, cudaStream_t st);
 const char* last_error();
 }  // namespace vs
