@@ -175,6 +175,9 @@ def main():
     net = build_from_hparams(get_hparams_from_file(), device=dev)
     net.load_state_dict(sd)
     lib = _lib.load()
+    for opt in ("fused_respair", "tf32_min_rows", "x3_min_rows"):     # A/B knobs for profiling runs (defaults otherwise)
+        if os.environ.get("VS_" + opt.upper()):
+            _lib.check(lib.vs_set_option(opt.encode(), int(os.environ["VS_" + opt.upper()])))
 
     utts = oin.c2(batch=args.batch, seed=1 + rank)        # independent utterances per rank: no collective on the path
     frames = oin.frame_counts(utts)

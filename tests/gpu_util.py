@@ -52,7 +52,8 @@ def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0
 
 
 def respair(x, w1, w2, b1, b2, dil, res2=None, act_slope=1.0, act_scale=1.0, row_utt=None, row_div=1):
-    """Fused ResBlock1 iteration on planar bf16 rows.  x [R][C] fp32 device, w [k][C][C].  Returns (raw, act) [R][C]."""
+    """Fused ResBlock1 iteration on planar bf16 rows.  x = the ACTIVATED input a = lrelu(x_raw) [R][C] fp32 device,
+    w [k][C][C].  Returns (raw, act) [R][C]."""
     lib = _lib.load()
     R, C = x.shape
     k = w1.shape[0]

@@ -303,3 +303,37 @@ def test_pcm16_postprocess_and_serving_queue(net):
                           duration_control=dur[None], outputs="audio")
         ref = to_pcm16(o, [o.shape[2]], 44100, 22050).cpu().numpy()[0]
         assert got.shape == ref.shape and np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_bf16"])
+def test_c1_log_mel_of_waveform(net, precision):
+    """Log-mel (reference mel_processing.py:85-112, the metric train.py logs) of our C1 waveform vs the reference's.
+    fp32 decoder: within 1e-2 max-abs.  bf16 decoder (40-50 dB SNR): the quiet top mel bands (log-mel ~ -7, i.e. 1e-3
+    linear) see the bf16 noise floor, so the bar there is mean-abs <= 1e-2 and max-abs <= 0.15; the 1e-2 max-abs bar of
+    BASELINE.json is met on the latents (m_p, z), which is where the decoder's input is fixed."""
+    from oracle import inputs as oin
+    from oracle.metrics import mel_spectrogram
+    d = dict(np.load([p for p in GOLDEN if p.endswith("c1.npz")][0]))
+    o, *_ = run_golden(net, d, precision)
+    ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
+    m_ref, m_got = mel_spectrogram(ref), mel_spectrogram(o[0, 0].cpu())
+    err = (m_ref - m_got).abs()
+    print("precision", precision, "log-mel max-abs %.4f mean-abs %.5f" % (float(err.max()), float(err.mean())))
+    if precision == 1:
+        assert float(err.max()) <= 1e-2        # includes the fp16 storage error of the fixture
+    else:
+        assert float(err.mean()) <= 1e-2 and float(err.max()) <= 0.15
+
+
+def test_fused_resblock_everywhere_still_matches(net):
+    """Force every eligible ResBlock iteration (C=32 all k, C=64 k=3) through the fused kernel and re-check C1."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    d = dict(np.load([p for p in GOLDEN if p.endswith("c1.npz")][0]))
+    _lib.check(lib.vs_set_option(b"fused_respair", 2))
+    try:
+        o, *_ = run_golden(net, d, 0)
+    finally:
+        _lib.check(lib.vs_set_option(b"fused_respair", 0))
+    ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
+    assert snr_db(ref, o[0, 0].cpu()) >= 30.0

@@ -62,8 +62,9 @@ def test_umma_conv_residual_mask_and_scale(G):
 @pytest.mark.parametrize("R,C,k,dil", [(1000, 32, 3, 1), (777, 32, 11, 5), (1500, 32, 7, 3), (600, 64, 3, 5), (129, 32, 11, 1),
                                       (246 * 3, 32, 11, 3)])
 def test_fused_resblock_pair_matches_cpu(G, R, C, k, dil):
-    """y = c2(lrelu(c1(lrelu(x)))) + x (modules.py:211-220) in one kernel vs an fp64 chain with the same bf16 roundings
-    (input, lrelu(x), the intermediate), incl. a masked gap (rows that must act as zero padding for BOTH convs)."""
+    """y = c2(lrelu(c1(lrelu(x)))) + x (modules.py:211-220) in one kernel.  The kernel takes a = lrelu(x) and recovers
+    the residual as min(a, a/slope); compared with an fp64 chain using the same bf16 roundings (a, the intermediate),
+    incl. a masked gap (rows that must act as zero padding for BOTH convs)."""
     g = torch.Generator().manual_seed(R + k)
     x = torch.randn(R, C, generator=g)
     row_utt = torch.zeros(R, dtype=torch.int32)
@@ -73,14 +74,15 @@ def test_fused_resblock_pair_matches_cpu(G, R, C, k, dil):
     w2 = torch.randn(k, C, C, generator=g) / (k * C) ** 0.5
     b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
     res2 = torch.randn(R, C, generator=g)
-    raw, act = G.respair(x.to(G.DEV), w1, w2, b1.to(G.DEV), b2.to(G.DEV), dil, res2=res2.to(G.DEV), act_slope=0.01,
+    a = G.bf16_round(torch.where(x > 0, x, 0.1 * x))     # what the previous kernel would have stored
+    raw, act = G.respair(a.to(G.DEV), w1, w2, b1.to(G.DEV), b2.to(G.DEV), dil, res2=res2.to(G.DEV), act_slope=0.01,
                          act_scale=1 / 3, row_utt=row_utt.to(G.DEV))
-    xb = G.bf16_round(x).double()
-    a1 = G.bf16_round(torch.where(xb > 0, xb, 0.1 * xb).float())
-    c1 = G.ref_conv_rows(a1, G.bf16_round(w1), b1, dil=dil, pad_l=(k - 1) // 2)
+    ad = a.double()
+    x_rec = torch.minimum(ad, ad * float(np.float32(1.0) / np.float32(0.1)))
+    c1 = G.ref_conv_rows(a, G.bf16_round(w1), b1, dil=dil, pad_l=(k - 1) // 2)
     t = G.bf16_round(torch.where(c1 > 0, c1, 0.1 * c1).float())
     t[300:340] = 0
-    y = G.ref_conv_rows(t, G.bf16_round(w2), b2, dil=1, pad_l=(k - 1) // 2) + xb + G.bf16_round(res2).double()
+    y = G.ref_conv_rows(t, G.bf16_round(w2), b2, dil=1, pad_l=(k - 1) // 2) + x_rec + G.bf16_round(res2).double()
     y[300:340] = 0
     scale = y.abs().max().item()
     assert (raw.cpu().double() - y).abs().max().item() <= 2e-2 * scale

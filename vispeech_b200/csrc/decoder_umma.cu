@@ -128,7 +128,8 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
       any_unfused = any_unfused || !fused[j];
     }
     c = UmmaConv();
-    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = XR; c.out_act = any_unfused ? XA : nullptr;
+    // fused iterations consume only the activated stream; unfused ones also need the raw copy (residual)
+    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = any_unfused ? XR : nullptr; c.out_act = XA;
     c.act_slope = 0.1f;
     c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
     c.up = s;
@@ -139,20 +140,20 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
       const int n = i * kDecKernels + j, k = kResK[j];
       const float final_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;    // final lrelu uses the default slope (Q3)
       if (fused[j]) {
-        const __nv_bfloat16* cur = XR;
+        const __nv_bfloat16* cur = XA;                                   // a = lrelu(x): the only stream between iterations
         for (int mth = 0; mth < kDecDils; ++mth) {
           const bool last = (mth == kDecDils - 1);
           UmmaPair pr;
           pr.x = cur; pr.w1 = w.c1_16[n][mth].w; pr.b1 = w.c1_16[n][mth].b; pr.w2 = w.c2_16[n][mth].w; pr.b2 = w.c2_16[n][mth].b;
-          pr.row_utt = valid; pr.row_div = mul; pr.R = Rs; pr.C = cout; pr.taps = k; pr.dil = kResD[mth];
-          if (!last) pr.out_raw = (mth == 0) ? AR : BR;                  // x = c2(lrelu(c1(lrelu(x)))) + x  modules.py:211-220
+          pr.row_utt = valid; pr.row_div = mul; pr.R = Rs; pr.C = cout; pr.taps = k; pr.dil = kResD[mth]; pr.in_slope = 0.1f;
+          if (!last) { pr.out_act = (mth == 0) ? AA : BA; pr.act_slope = 0.1f; }   // lrelu(c2(lrelu(c1(a))) + x)  modules.py:211-220
           else {
             pr.res2 = (j > 0) ? S : nullptr;                             // xs += resblock_j(x)  models.py:280-284
             if (j < kDecKernels - 1) pr.out_raw = S;
             else { pr.out_act = NEXT; pr.act_scale = 1.f / kDecKernels; pr.act_slope = final_slope; }
           }
           VS_TRY(umma_respair(pr, st));
-          cur = (mth == 0) ? AR : BR;
+          cur = (mth == 0) ? AA : BA;
         }
         continue;
       }

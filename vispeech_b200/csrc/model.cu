@@ -249,7 +249,7 @@ int vs_set_option(const char* name, int64_t value) {
     return VS_OK;
   }
   if (std::string(name) == "fused_respair") {
-    vs::umma_respair_enable(value != 0);
+    vs::umma_respair_enable((int)value);
     return VS_OK;
   }
   vs::set_error("vs_set_option: unknown option '%s'", name);

@@ -30,9 +30,9 @@ struct UmmaConv {
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
 
-// One fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x on the raw stream (umma_respair.cu), C in {32, 64}.
+// One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
 struct UmmaPair {
-  const __nv_bfloat16* x = nullptr;      // raw input, planar [C/8][R][8]
+  const __nv_bfloat16* x = nullptr;      // ACTIVATED input a = lrelu(x, in_slope), planar [C/8][R][8]
   const __nv_bfloat16* w1 = nullptr;     // c1 weights, slabs as in UmmaConv (k taps, dilation dil)
   const __nv_bfloat16* w2 = nullptr;     // c2 weights (k taps, dilation 1)
   const float* b1 = nullptr;
@@ -46,7 +46,7 @@ struct UmmaPair {
   float act_slope = 1.f, act_scale = 1.f;
 };
 bool umma_respair_supported(int C, int taps, int dil);
-void umma_respair_enable(bool on);
+void umma_respair_enable(int mode);   // 0 off (default), 1 where the isolated kernel is faster, 2 wherever it fits
 int umma_respair(const UmmaPair& c, cudaStream_t st);
 
 }  // namespace vs
