@@ -36,6 +36,7 @@ int resolve_decoder(const FetchFn& fetch, int n_speakers, DecoderW* d) {
 }
 
 // the widest stage buffers are stage 2 (256 rows x 64 ch) and stage 3 (512 x 32): 16384 floats per frame
+// fp32 cross-check: 5 buffers x 16384 floats per frame; bf16 path: 6 buffers x 16384 bf16 (fits in the same bound)
 int64_t decoder_ws_floats(int rf) { return (int64_t)rf * (5 * 16384 + 192 + 8) + 4096; }
 
 int decode_f32(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,

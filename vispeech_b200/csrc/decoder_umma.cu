@@ -98,11 +98,10 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
   const int R = rows.n_rows;
   int32_t* valid = ws.take<int32_t>(R);
   __nv_bfloat16* zin = ws.take<__nv_bfloat16>((int64_t)R * kHidden);
-  __nv_bfloat16* buf[9];
-  for (int i = 0; i < 9; ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
+  __nv_bfloat16* buf[6];
+  for (int i = 0; i < 6; ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
   if (!ws.ok) { set_error("decode_bf16: workspace too small"); return VS_ERR_WORKSPACE; }
-  __nv_bfloat16 *XR = buf[0], *XA = buf[1], *T = buf[2], *AR = buf[3], *AA = buf[4], *BR = buf[5], *BA = buf[6],
-                *S = buf[7], *NEXT = buf[8];
+  __nv_bfloat16 *XA = buf[0], *T = buf[1], *AA = buf[2], *BA = buf[3], *S = buf[4], *NEXT = buf[5];
 
   VS_TRY(mask_frames(rows, max_len, valid, st));                         // (z * x_mask)[:, :, :max_len]  models.py:720
   to_planar_bf16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
@@ -121,15 +120,14 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     const int taps = ups_taps(i, &pad_l);
     // which resblocks of this stage run as fused pairs on the raw stream (umma_respair.cu)?
     bool fused[kDecKernels];
-    bool any_unfused = false;
     for (int j = 0; j < kDecKernels; ++j) {
       fused[j] = true;
       for (int mth = 0; mth < kDecDils; ++mth) fused[j] = fused[j] && umma_respair_supported(cout, kResK[j], kResD[mth]);
-      any_unfused = any_unfused || !fused[j];
     }
     c = UmmaConv();
-    // fused iterations consume only the activated stream; unfused ones also need the raw copy (residual)
-    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = any_unfused ? XR : nullptr; c.out_act = XA;
+    // only the ACTIVATED stream a = lrelu(x) is stored between ResBlock iterations: it is the next conv's operand as
+    // is, and the residual x is recovered in the c2 epilogue as min(a, a/slope) (same bf16 relative rounding as storing x)
+    c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = nullptr; c.out_act = XA;
     c.act_slope = 0.1f;
     c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
     c.up = s;
@@ -157,7 +155,6 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
         }
         continue;
       }
-      const __nv_bfloat16* cur_raw = XR;
       const __nv_bfloat16* cur_act = XA;
       for (int mth = 0; mth < kDecDils; ++mth) {
         const bool last = (mth == kDecDils - 1);
@@ -166,9 +163,10 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
         c.in = cur_act; c.w = w.c1_16[n][mth].w; c.bias = w.c1_16[n][mth].b; c.dil = kResD[mth];
         c.out_act = T; c.act_slope = 0.1f;
         VS_TRY(umma_conv1d(c, st));                                      // lrelu(c1(lrelu(x)))  modules.py:211-218
-        c.in = T; c.w = w.c2_16[n][mth].w; c.bias = w.c2_16[n][mth].b; c.dil = 1; c.res = cur_raw;
+        c.in = T; c.w = w.c2_16[n][mth].w; c.bias = w.c2_16[n][mth].b; c.dil = 1;
+        c.res = cur_act; c.res_inv_slope = 10.f;                         // + x, recovered from lrelu(x, 0.1)
         if (!last) {
-          c.out_raw = (mth == 0) ? AR : BR; c.out_act = (mth == 0) ? AA : BA;      // x = c2(.) + x  modules.py:219-220
+          c.out_act = (mth == 0) ? AA : BA;                              // store lrelu(c2(.) + x)  modules.py:219-220, 211
         } else {
           c.res2 = (j > 0) ? S : nullptr;                                // xs += resblock_j(x)  models.py:280-284
           if (j < kDecKernels - 1) { c.out_raw = S; c.out_act = nullptr; }
@@ -177,7 +175,6 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
           }
         }
         VS_TRY(umma_conv1d(c, st));
-        cur_raw = (mth == 0) ? AR : BR;
         cur_act = (mth == 0) ? AA : BA;
       }
     }

@@ -48,7 +48,7 @@ struct Params {
 };
 
 // Epilogue feature flags (template parameter F of the kernel; F < 0 = all decided at run time)
-constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128;
+constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128, F_RESINV = 256;
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     const bool has_act = kGeneric ? (c.out_act != nullptr) : ((F & F_ACT) != 0);
     const bool has_scale = kGeneric ? (c.act_scale != 1.f) : ((F & F_SCALE) != 0);
     const bool has_up = kGeneric ? (c.up != 1) : ((F & F_UP) != 0);
+    const bool res_inv = kGeneric ? (c.res_inv_slope != 0.f) : ((F & F_RESINV) != 0);
+    const float rinv = c.res_inv_slope;
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int CW = (kGeneric ? (p.Nblk >= 64) : ((F & F_CW16) == 0)) ? 32 : 16;   // columns per tcgen05.ld
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                     float f[8];
                     unpack_bf16x8(rv[g], f);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) y[e] += f[e];
+                    for (int e = 0; e < 8; ++e) y[e] += res_inv ? fminf(f[e], f[e] * rinv) : f[e];
                   }
                   if (has_res2) {
                     float f[8];
@@ -477,7 +479,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   if (grid > prm.p.n_super) grid = prm.p.n_super;
   int flags = (c.res ? F_RES : 0) | (c.res2 ? F_RES2 : 0) | (c.ubias ? F_UBIAS : 0) | (c.out_raw ? F_RAW : 0) |
               (c.out_act ? F_ACT : 0) | (c.act_scale != 1.f ? F_SCALE : 0) | (c.up != 1 ? F_UP : 0) |
-              (prm.p.Nblk < 64 ? F_CW16 : 0);
+              (prm.p.Nblk < 64 ? F_CW16 : 0) | ((c.res && c.res_inv_slope != 0.f) ? F_RESINV : 0);
 #define VS_UMMA_CASE(FL)                                                                                              \
   case FL: {                                                                                                          \
     static bool cfg = false;                                                                                          \
@@ -500,6 +502,15 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
     VS_UMMA_CASE(F_RES | F_RES2 | F_RAW | F_CW16)
     VS_UMMA_CASE(F_RES | F_RES2 | F_ACT | F_SCALE)
     VS_UMMA_CASE(F_RES | F_RES2 | F_ACT | F_SCALE | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_ACT)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_ACT | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RAW)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RAW | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RES2 | F_RAW)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RES2 | F_RAW | F_CW16)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RES2 | F_ACT | F_SCALE)
+    VS_UMMA_CASE(F_RES | F_RESINV | F_RES2 | F_ACT | F_SCALE | F_CW16)
+    VS_UMMA_CASE(F_ACT | F_UP)
     VS_UMMA_CASE(F_UBIAS | F_ACT)
     VS_UMMA_CASE(F_RAW | F_ACT | F_UP)
     VS_UMMA_CASE(F_RAW | F_UP)

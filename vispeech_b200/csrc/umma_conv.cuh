@@ -15,6 +15,9 @@ struct UmmaConv {
   const float* ubias = nullptr;        // optional per-speaker table [n_spk][N]
   const int32_t* ubias_idx = nullptr;  // [n_utt] -> row of ubias
   const __nv_bfloat16* res = nullptr;  // optional residual, planar like out (same rows/channels)
+  float res_inv_slope = 0.f;           // != 0: `res` holds a = lrelu(x, 1/res_inv_slope); the residual added is
+                                       // x = min(a, a * res_inv_slope) (exact inverse up to bf16 rounding), so only the
+                                       // activated stream has to be stored between ResBlock iterations
   const __nv_bfloat16* res2 = nullptr; // optional second residual (MRF running sum)
   __nv_bfloat16* out_raw = nullptr;    // optional: y
   __nv_bfloat16* out_act = nullptr;    // optional: lrelu(y * act_scale, act_slope)
