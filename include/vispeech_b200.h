@@ -79,7 +79,9 @@ int64_t vs_launch_count(void);
  * "x3_min_rows": convs over at least this many rows (and below tf32_min_rows, or phoneme level) run as error-
  * compensated 3xTF32 on the tensor cores (default 512; fp32-level accuracy).
  * "fused_respair": 0 = never (default), 1 = fuse ResBlock iterations where the isolated fused kernel is faster
- * (C=32,k=3), 2 = wherever it fits (C=32 all k, C=64 k=3). */
+ * (C=32,k=3), 2 = wherever it fits (C=32 all k, C=64 k=3).
+ * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 296*12 int64 where the tcgen05 conv kernel
+ * leaves per-CTA clocks spent waiting on each mbarrier (tools/conv_timing.py). */
 int vs_set_option(const char* name, int64_t value);   /* kernels launched by this library so far (process-wide) */
 
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.

@@ -1,0 +1,198 @@
+// tcgen05.mma rate microbenchmark (sm_100a).  One issuing warp, one accumulator chain per CTA, operands are
+// uninitialised shared memory - only the timing matters.  Two questions:
+//   1. cycles per MMA (M=128, K=16, bf16) as a function of N with fixed operand addresses (tensor / smem floors);
+//   2. the same with the conv kernel's real descriptor walk: A start offset = tap*dil rows (16 B each) + K-chunk
+//      planes `rows_a` rows apart (LBO), B walking through contiguous weight slabs.
+// Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -I vispeech_b200/csrc -o tools/_bin/mma_mb tools/mma_microbench.cu
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "umma_common.cuh"
+
+namespace vs { void set_error(const char*, ...) {} unsigned long long g_launch_count = 0; }
+using namespace vs::umma;
+
+struct Walk { int n, taps, dil, nks, rows_a, tiles, iters, b_fixed, a_fixed, variant; };
+
+// NK MMAs of one conv tap in ONE asm block: a single elect, descriptor low words advanced inside the block.
+template <int NK>
+__device__ __forceinline__ void mma_tap_block(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t a_kstep, uint32_t b_kstep) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b32 al, %1;\n\t"
+      "mov.b32 bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      ".pragma \"nounroll\";\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+#pragma unroll
+  for (int i = 1; i < NK; ++i) {
+    a_lo += a_kstep;
+    b_lo += b_kstep;
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+  }
+}
+// plain MMA without election: the caller is already a single lane
+__device__ __forceinline__ void mma_plain(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int NK>
+__device__ __forceinline__ void walk_unrolled(const Walk& w, uint32_t tm, uint32_t a_lo0, uint32_t a_hi, uint32_t b_lo0, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t a_kstep, uint32_t b_kstep, uint32_t dil) {
+  const int taps = w.taps, tiles = w.tiles, iters = w.iters;
+  for (int it = 0; it < iters; ++it)
+    for (int m = 0; m < tiles; ++m) {
+      uint32_t a_tap = a_lo0 + (uint32_t)(m * 128), b_lo = b_lo0, accumulate = 0;
+#pragma unroll 2
+      for (int t = 0; t < taps; ++t, a_tap += dil) {
+        uint32_t a_lo = a_tap;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+          tc_mma_bf16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+          accumulate = 1;
+          a_lo += a_kstep;
+          b_lo += b_kstep;
+        }
+      }
+    }
+}
+template <int NK>
+__device__ __forceinline__ void walk_lane0(const Walk& w, uint32_t tm, uint32_t a_lo0, uint32_t a_hi, uint32_t b_lo0, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t a_kstep, uint32_t b_kstep, uint32_t dil) {
+  const int taps = w.taps, tiles = w.tiles, iters = w.iters;
+  for (int it = 0; it < iters; ++it)
+    for (int m = 0; m < tiles; ++m) {
+      uint32_t a_tap = a_lo0 + (uint32_t)(m * 128), b_lo = b_lo0, accumulate = 0;
+#pragma unroll 2
+      for (int t = 0; t < taps; ++t, a_tap += dil) {
+        uint32_t a_lo = a_tap;
+#pragma unroll
+        for (int ks = 0; ks < NK; ++ks) {
+          mma_plain(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+          accumulate = 1;
+          a_lo += a_kstep;
+          b_lo += b_kstep;
+        }
+      }
+    }
+}
+
+__global__ void __launch_bounds__(64, 2) mma_walk(const Walk w, long long* out_clk) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  if (warp == 1) {
+    const uint32_t base = smem_u32(smem);
+    const uint32_t a_lbo = (uint32_t)w.rows_a * 16u, b_lbo = (uint32_t)w.n * 16u;
+    const uint32_t a_bytes = (uint32_t)w.rows_a * 16u * 2u * (uint32_t)w.nks;
+    const uint64_t ad = make_desc(base, a_lbo, 128), bd = make_desc(base + ((a_bytes + 1023u) & ~1023u), b_lbo, 128);
+    const uint32_t a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+    const uint32_t a_lo0 = (uint32_t)ad, b_lo0 = (uint32_t)bd;
+    const uint32_t idesc = make_idesc(w.n);
+    const uint32_t a_kstep = w.a_fixed ? 0u : 2u * (uint32_t)w.rows_a, b_kstep = w.b_fixed ? 0u : 2u * (uint32_t)w.n;
+    const int taps = w.taps, nks = w.nks, tiles = w.tiles, iters = w.iters;
+    const uint32_t dil = w.a_fixed ? 0u : (uint32_t)w.dil;
+    const long long t0 = clock64();
+    if (w.variant == 1) {
+      if (nks == 2) walk_unrolled<2>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+      else if (nks == 4) walk_unrolled<4>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+      else walk_unrolled<8>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+    } else if (w.variant == 2) {
+      if ((threadIdx.x & 31) == 0) {
+        if (nks == 2) walk_lane0<2>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+        else if (nks == 4) walk_lane0<4>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+        else walk_lane0<8>(w, tm, a_lo0, a_hi, b_lo0, b_hi, idesc, a_kstep, b_kstep, dil);
+      }
+      __syncwarp();
+    } else
+    for (int it = 0; it < iters; ++it)
+      for (int m = 0; m < tiles; ++m) {
+        uint32_t a_tap = a_lo0 + (uint32_t)(m * 128), b_lo = b_lo0, accumulate = 0;
+        for (int t = 0; t < taps; ++t, a_tap += dil) {
+          uint32_t a_lo = a_tap;
+          for (int ks = 0; ks < nks; ++ks) {
+            tc_mma_bf16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+            accumulate = 1;
+            a_lo += a_kstep;
+            b_lo += b_kstep;
+          }
+        }
+      }
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0, 1);
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out_clk[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256u) : "memory");
+}
+
+static long long* d_clk;
+static double run(Walk w, int per_sm) {
+  static long long h[512];
+  const int smem = per_sm == 1 ? 200 * 1024 : 100 * 1024;
+  mma_walk<<<148 * per_sm, 64, smem>>>(w, d_clk);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+  cudaMemcpy(h, d_clk, sizeof(long long) * 148 * per_sm, cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < 148 * per_sm; ++i) avg += (double)h[i];
+  avg /= 148 * per_sm;
+  return avg / ((double)w.iters * w.tiles * w.taps * w.nks) / per_sm;   // clocks per MMA per SM
+}
+
+int main() {
+  cudaMalloc(&d_clk, 512 * sizeof(long long));
+  cudaFuncSetAttribute(mma_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("fixed operands (floors): clk/MMA/SM at 1 and 2 CTAs/SM\n");
+  for (int n : {32, 64, 128, 256}) {
+    Walk w{n, 8, 1, 4, 256, 1, 200, 1, 1, 0};
+    printf("  N=%3d : %6.1f %6.1f\n", n, run(w, 1), n <= 128 ? run(w, 2) : 0.0);
+  }
+  printf("conv descriptor walk, 1 CTA/SM: N=C, taps, dil, MT -> clk/MMA/SM issue-loop variants\n");
+  for (int c : {32, 64, 128})
+    for (int taps : {3, 7, 11})
+      for (int dil : {1, 5}) {
+        const int mt = c == 128 ? 1 : 2;
+        const int rows_a = 128 * mt + (taps - 1) * dil;
+        if ((size_t)rows_a * c * 2 + (size_t)taps * c * c * 2 > 190 * 1024) continue;
+        Walk w{c, taps, dil, c / 16, rows_a, mt, 40, 0, 0, 0};
+        Walk w1 = w; w1.variant = 1;
+        Walk w2 = w; w2.variant = 2;
+        printf("  C=%3d k=%2d d=%d MT=%d : nested %6.1f | unrolled %6.1f | lane0 %6.1f   (2 CTAs/SM: %6.1f %6.1f %6.1f)\n", c, taps, dil, mt,
+               run(w, 1), run(w1, 1), run(w2, 1), c <= 64 ? run(w, 2) : 0., c <= 64 ? run(w1, 2) : 0., c <= 64 ? run(w2, 2) : 0.);
+      }
+  return 0;
+}

@@ -54,13 +54,13 @@ mul = 1
 for i, (s, K) in enumerate(zip((8, 8, 4, 2), (16, 16, 4, 4))):
     cin, cout = 512 >> i, 256 >> i
     taps = 1 if K == s else 3
-    total += run("ups%d" % i, FRAMES * mul, cin, cout * s, taps, 1, up=s, two_out=True)
+    total += run("ups%d" % i, FRAMES * mul, cin, cout * s, taps, 1, up=s)
     mul *= s
     R = FRAMES * mul
     for k in (3, 7, 11):
         for d in (1, 3, 5):
             total += run("s%d c1 k%d d%d" % (i, k, d), R, cout, cout, k, d)
-        total += run("s%d c2 k%d (res,2out)" % (i, k), R, cout, cout, k, 1, res=True, two_out=True, count=3)
+        total += run("s%d c2 k%d (res)" % (i, k), R, cout, cout, k, 1, res=True, count=3)
 print("sum of decoder convs: %.2f ms" % total)
 
 

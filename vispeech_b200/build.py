@@ -35,6 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vispeech_b200.h"))
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("VS_UMMA_TIMING") == "1":     # diagnostics build for tools/conv_timing.py (use with --force)
+        flags.append("-DVS_UMMA_TIMING")
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

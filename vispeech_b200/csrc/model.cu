@@ -252,6 +252,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::umma_respair_enable((int)value);
     return VS_OK;
   }
+  if (std::string(name) == "umma_timing_buffer") {   // diagnostics (tools/conv_timing.py): device pointer or 0
+    vs::umma_conv_set_timing_buffer(reinterpret_cast<void*>(value));
+    return VS_OK;
+  }
   vs::set_error("vs_set_option: unknown option '%s'", name);
   return VS_ERR_INVALID;
 }

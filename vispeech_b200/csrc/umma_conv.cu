@@ -45,10 +45,41 @@ struct Plan {
 struct Params {
   UmmaConv c;
   Plan p;
+  long long* dbg;         // optional per-CTA wait-time counters (vs_set_option("umma_timing_buffer", device pointer))
 };
+// Wait-time counters are compiled in only with -DVS_UMMA_TIMING (VS_UMMA_TIMING=1 python vispeech_b200/build.py): even
+// the dormant checks cost the streaming convs 5-8 %.
+#ifdef VS_UMMA_TIMING
+#define VS_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = dbg ? clock64() : 0;      \
+    stmt;                                           \
+    if (dbg) var += clock64() - _t0;                \
+  } while (0)
+#else
+#define VS_TIMED(var, stmt) stmt
+#endif
 
 // Epilogue feature flags (template parameter F of the kernel; F < 0 = all decided at run time)
 constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128, F_RESINV = 256;
+
+// All MMAs of one 128-row tile against resident weights: taps x NK K-chunks, accumulating into d_tmem.
+template <int NK>
+__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep) {
+  uint32_t accumulate = 0, a_tap = a_tile;
+#pragma unroll 2
+  for (int t = 0; t < taps; ++t, a_tap += dil) {
+    uint32_t a_lo = a_tap;
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+      tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+      accumulate = 1;
+      a_lo += a_kstep;
+      b_lo += b_kstep;
+    }
+  }
+}
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
@@ -56,6 +87,11 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
   const UmmaConv& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef VS_UMMA_TIMING
+  long long* const dbg = prm.dbg;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  const long long t_start = dbg ? clock64() : 0;
+#endif
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base;
@@ -106,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     auto issue_a = [&](int super) {
       const int sa = a_it % p.SA;
       const uint32_t ph = (a_it / p.SA) & 1;
-      mbar_wait(a_empty(sa), ph ^ 1, 1);
+      VS_TIMED(tw0, mbar_wait(a_empty(sa), ph ^ 1, 1));
       const int row_lo = super * p.MT * kTileM - p.halo_l, row_hi = row_lo + p.rows_a;
       const int c_lo = row_lo < 0 ? 0 : row_lo, c_hi = row_hi > c.R ? c.R : row_hi;
       const uint32_t stage = a_base + sa * p.a_bytes;
@@ -140,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
           for (int sl = 0; sl < n_slabs; ++sl) {
             const int sb = b_it % p.SB;
             const uint32_t ph = (b_it / p.SB) & 1;
-            mbar_wait(b_empty(sb), ph ^ 1, 2);
+            VS_TIMED(tw1, mbar_wait(b_empty(sb), ph ^ 1, 2));
             mbar_arrive_expect_tx(b_full(sb), p.b_bytes);
             bulk_g2s(b_base + sb * p.b_bytes, reinterpret_cast<const uint8_t*>(c.w) + (size_t)sl * p.b_bytes, p.b_bytes,
                      b_full(sb));
@@ -162,56 +198,37 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       const int taps = c.taps, dil = c.dil, n_kc = p.n_kc, k16s = p.KC / 16, MT = p.MT, NACC = p.NACC, SB = p.SB, SA = p.SA;
       const int n_tiles = p.n_tiles, n_super = p.n_super;
       const bool resident = p.resident_b != 0;
-      const int IL = (resident && p.NB == 1) ? min(min(4, MT), NACC / 2) : 1;
+      const int nks = n_kc * k16s;
+      const bool lean = resident && p.NB == 1 && (nks == 2 || nks == 4 || nks == 8);
       const uint32_t slab16 = p.b_bytes >> 4, a_bytes = p.a_bytes, nblk = (uint32_t)p.Nblk;
       const uint32_t b_base16 = b_base >> 4;
       uint32_t acc_slot = 0, acc_phase = 0, b_slot = 0, b_phase = 0, a_slot = 0, a_phase = 0;
       if (resident) { mbar_wait(b_full(0), 0, 7); tc_fence_after(); }
       for (int super = blockIdx.x; super < n_super; super += gridDim.x) {
-        mbar_wait(a_full(a_slot), a_phase, 3);
+        VS_TIMED(tw0, mbar_wait(a_full(a_slot), a_phase, 3));
         tc_fence_after();
         const uint32_t a_stage16 = (a_base + a_slot * a_bytes) >> 4;
         const int tiles_here = min(MT, n_tiles - super * MT);
-        if (IL > 1) {
-          // Small-N convs: consecutive MMAs into ONE accumulator form a dependent chain and expose the tensor
-          // pipeline latency.  Interleave up to IL row tiles of this A stage: each K-step issues one MMA per
-          // tile (independent accumulators, same weight operand), so the chains overlap.
-          for (int m0 = 0; m0 < tiles_here; m0 += IL) {
-            const int g = min(IL, tiles_here - m0);
-            uint32_t d_tmem[4], slot[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              d_tmem[j] = 0; slot[j] = 0;
-              if (j < g) {
-                mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4);
-                slot[j] = acc_slot;
-                d_tmem[j] = tmem_base + acc_slot * nblk;
-                if (++acc_slot == (uint32_t)NACC) { acc_slot = 0; acc_phase ^= 1; }
-              }
-            }
+        if (lean) {
+          // Resident weights, one n-block: the issue loop itself is the bottleneck for the small-C convs (one warp
+          // issues every MMA; tools/mma_microbench.cu: nested runtime loops cost 55-120 clk per MMA against a
+          // 40-48 clk operand-fetch floor).  So the K-chunk walk of a tap is fully unrolled (NK = Cin/16 as a template
+          // parameter) and there is nothing in the loop but descriptor adds and the MMA.
+          for (int m = 0; m < tiles_here; ++m) {
+            VS_TIMED(tw1, mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4));
             tc_fence_after();
-            uint32_t accumulate = 0;
-            uint32_t b_lo = b_lo_fixed + b_base16;
-            uint32_t a_tap = a_lo_fixed + a_stage16 + (uint32_t)(m0 * kTileM);
-            for (int t = 0; t < taps; ++t, a_tap += (uint32_t)dil) {
-              uint32_t a_lo = a_tap;
-              for (int ks = 0; ks < n_kc * k16s; ++ks) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < g) tc_mma_bf16_lohi(d_tmem[j], a_lo + (uint32_t)(j * kTileM), a_hi, b_lo, b_hi, idesc, accumulate);
-                accumulate = 1;
-                a_lo += a_kstep;
-                b_lo += b_kstep;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < g) tc_commit(acc_full(slot[j]));
+            const uint32_t d_tmem = tmem_base + acc_slot * nblk;
+            const uint32_t a_tile = a_lo_fixed + a_stage16 + (uint32_t)(m * kTileM), b0 = b_lo_fixed + b_base16;
+            if (nks == 2) issue_tile<2>(d_tmem, a_tile, a_hi, b0, b_hi, idesc, taps, (uint32_t)dil, a_kstep, b_kstep);
+            else if (nks == 4) issue_tile<4>(d_tmem, a_tile, a_hi, b0, b_hi, idesc, taps, (uint32_t)dil, a_kstep, b_kstep);
+            else issue_tile<8>(d_tmem, a_tile, a_hi, b0, b_hi, idesc, taps, (uint32_t)dil, a_kstep, b_kstep);
+            tc_commit(acc_full(acc_slot));
+            if (++acc_slot == (uint32_t)NACC) { acc_slot = 0; acc_phase ^= 1; }
           }
         } else {
           for (int m = 0; m < tiles_here; ++m)
             for (int nb = 0; nb < n_units_per_tile; ++nb) {
-              mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4);
+              VS_TIMED(tw1, mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4));
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + acc_slot * nblk;
               uint32_t accumulate = 0;
@@ -221,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                 uint32_t a_lo = a_tap;
                 for (int kc = 0; kc < n_kc; ++kc) {
                   if (!resident) {
-                    mbar_wait(b_full(b_slot), b_phase, 5);
+                    VS_TIMED(tw2, mbar_wait(b_full(b_slot), b_phase, 5));
                     tc_fence_after();
                     b_lo = b_lo_fixed + b_base16 + b_slot * slab16;
                   }
@@ -285,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       const size_t row_elem = (size_t)c.up * r * 8;         // element offset of this thread's (first) output row in a plane
       for (int nb = 0; nb < n_units_per_tile; ++nb) {
         const int ab = (int)acc_slot;
-        mbar_wait(acc_full(ab), acc_phase, 6);
+        VS_TIMED(tw0, mbar_wait(acc_full(ab), acc_phase, 6));
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Nblk);
         for (int cc = hsel; cc < n_chunks; cc += 2) {
@@ -369,6 +386,12 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     }
   }
 
+#ifdef VS_UMMA_TIMING
+  if (dbg && lane == 0 && warp < 3) {   // [cta][warp 0 producer | 1 MMA | 2 first epilogue warp][total, wait0, wait1, wait2]
+    long long* o = dbg + ((size_t)blockIdx.x * 3 + warp) * 4;
+    o[0] = clock64() - t_start; o[1] = tw0; o[2] = tw1; o[3] = tw2;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -462,9 +485,13 @@ int make_plan(const UmmaConv& c, Plan* out) {
 
 }  // namespace
 
+static long long* g_timing = nullptr;
+void umma_conv_set_timing_buffer(void* dev) { g_timing = static_cast<long long*>(dev); }
+
 int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
+  prm.dbg = g_timing;
   VS_TRY(make_plan(c, &prm.p));
   VS_REQUIRE(c.in && c.w && (c.out_raw || c.out_act), "umma_conv1d: null pointer");
   static int n_sm = 0;

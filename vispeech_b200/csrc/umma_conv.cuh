@@ -32,6 +32,7 @@ struct UmmaConv {
 };
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
+void umma_conv_set_timing_buffer(void* dev);   // diagnostics: >= 296*12 int64 of per-CTA wait clocks, or null
 
 // One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
 struct UmmaPair {
