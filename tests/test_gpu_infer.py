@@ -326,7 +326,7 @@ def test_c1_log_mel_of_waveform(net, precision):
 
 
 def test_fused_resblock_everywhere_still_matches(net):
-    """Force every eligible ResBlock iteration (C=32 all k, C=64 k=3) through the fused kernel and re-check C1."""
+    """Force every eligible ResBlock iteration (C=32 all k, C=64 k=3,7) through the fused kernel and re-check C1."""
     from vispeech_b200 import _lib
     lib = _lib.load()
     d = dict(np.load([p for p in GOLDEN if p.endswith("c1.npz")][0]))

@@ -7,7 +7,7 @@ from vispeech_b200 import _lib
 from vispeech_b200._lib import check, ptr
 lib = _lib.load(); dev = "cuda:0"; st = torch.cuda.current_stream().cuda_stream
 FRAMES = 27840
-buf = torch.zeros(296 * 12, dtype=torch.int64, device=dev)
+buf = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
 
 
 def run(name, R, cin, n, taps, dil):
@@ -40,6 +40,42 @@ def run(name, R, cin, n, taps, dil):
         print("    %-9s total %8.0f clk  " % (role, tot) + "  ".join("%s %4.1f%%" % (nm, 100 * t[r, 1 + i].item() / tot) for i, nm in enumerate(names) if nm != "-"))
 
 
+def run_pair(name, R, C, k, d):
+    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    o = torch.empty_like(x)
+
+    def call():
+        check(lib.vs_op_respair(ptr(x), ptr(w1), ptr(w2), ptr(b1), ptr(b2), None, None, ptr(o), R, C, k, d, 0.1, 1.0, None, 1, st))
+    check(lib.vs_set_option(b"umma_timing_buffer", 0))
+    call(); call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); call(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    buf.zero_()
+    check(lib.vs_set_option(b"umma_timing_buffer", buf.data_ptr()))
+    call()
+    torch.cuda.synchronize()
+    check(lib.vs_set_option(b"umma_timing_buffer", 0))
+    t = buf[: 296 * 16].view(296, 4, 4).double()
+    used = t[:, 1, 0] > 0
+    t = t[used].mean(0)
+    print("%-14s %.3f ms  ctas=%d" % (name, ms, int(used.sum())))
+    for r, (role, names) in enumerate((("producer", ("xa_empty", "-", "-")), ("mma", ("xa_full+acc1_empty", "a2_full", "acc2_empty")),
+                                        ("epilogue1", ("acc1_full", "a2_empty", "-")), ("epilogue2", ("acc2_full", "-", "-")))):
+        tot = t[r, 0].item()
+        print("    %-9s total %8.0f clk  " % (role, tot) + "  ".join("%s %4.1f%%" % (nm, 100 * t[r, 1 + i].item() / tot) for i, nm in enumerate(names) if nm != "-"))
+
+
+if os.environ.get("PAIRS", "1") == "1":
+    run_pair("s3 pair k3", FRAMES * 512, 32, 3, 1)
+    run_pair("s3 pair k11", FRAMES * 512, 32, 11, 1)
+    run_pair("s2 pair k3", FRAMES * 256, 64, 3, 1)
+    run_pair("s2 pair k7", FRAMES * 256, 64, 7, 1)
+    sys.exit(0)
 run("s0 c1 k3 d1", FRAMES * 8, 256, 256, 3, 1)
 run("s0 c1 k11 d1", FRAMES * 8, 256, 256, 11, 1)
 run("s0 c1 k11 d5", FRAMES * 8, 256, 256, 11, 5)

@@ -12,7 +12,7 @@
 namespace vs { void set_error(const char*, ...) {} unsigned long long g_launch_count = 0; }
 using namespace vs::umma;
 
-struct Walk { int n, taps, dil, nks, rows_a, tiles, iters, b_fixed, a_fixed, variant; };
+struct Walk { int n, taps, dil, nks, rows_a, tiles, iters, b_fixed, a_fixed, variant, fill, noise; float* gbuf; };
 
 // NK MMAs of one conv tap in ONE asm block: a single elect, descriptor low words advanced inside the block.
 template <int NK>
@@ -98,7 +98,8 @@ __device__ __forceinline__ void walk_lane0(const Walk& w, uint32_t tm, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(64, 2) mma_walk(const Walk w, long long* out_clk) {
+__global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_clk) {
+  __shared__ volatile int done_flag;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
@@ -107,7 +108,18 @@ __global__ void __launch_bounds__(64, 2) mma_walk(const Walk w, long long* out_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { done_flag = 0; mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (w.fill) {   // operands: 0 = whatever is there, 1 = zeros, 2 = pseudo-random bf16 in [-1, 1)
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
+    uint32_t x = 1234567u + threadIdx.x * 7919u + blockIdx.x * 104729u;
+    for (int i = threadIdx.x; i < 190 * 256; i += blockDim.x) {
+      x = x * 1664525u + 1013904223u;
+      const uint32_t lo = 0x3F000000u | ((x >> 9) & 0x007F0000u) | (x & 0x80000000u);      // +-[0.5,1) bf16 in the high half
+      const uint32_t hi = 0x3F000000u | ((x << 3) & 0x007F0000u) | ((x << 7) & 0x80000000u);
+      s32[i] = w.fill == 1 ? 0u : ((lo >> 16) | (hi & 0xFFFF0000u));
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,7 +164,39 @@ __global__ void __launch_bounds__(64, 2) mma_walk(const Walk w, long long* out_c
     tc_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0, 1);
     const long long t1 = clock64();
-    if ((threadIdx.x & 31) == 0) out_clk[blockIdx.x] = t1 - t0;
+    if ((threadIdx.x & 31) == 0) { out_clk[blockIdx.x] = t1 - t0; done_flag = 1; }
+  } else if (warp >= 2 && w.noise) {
+    // background traffic from 4 "epilogue" warps while the MMAs run: 1 = tcgen05.ld (TMEM reads), 2 = LDS, 4 = STS, 8 = STG
+    const int lane = threadIdx.x & 31, q = warp & 3;
+    uint32_t v[32];
+    float acc = 0.f;
+    const uint32_t sbase = smem_u32(smem) + 150 * 1024 + (uint32_t)(threadIdx.x - 64) * 16u;
+    long long n_it = 0;
+    const long long tn0 = clock64();
+    while (!done_flag) {
+      ++n_it;
+      if (w.noise & 1) { tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + 128u, v); acc += __uint_as_float(v[lane & 31]); }
+      if (w.noise & 2) {
+        uint32_t x0, x1, x2, x3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sbase + r * 2048u));
+          acc += __uint_as_float(x0 ^ x3);
+        }
+      }
+      if (w.noise & 4) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sbase + r * 2048u), "r"(lane) : "memory");
+      }
+      if (w.noise & 8) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          reinterpret_cast<float4*>(w.gbuf)[((size_t)blockIdx.x * 4 + r) * 128 + (threadIdx.x - 64)] = make_float4(acc, 0, 0, 0);
+      }
+    }
+    if (lane == 0 && warp == 2) out_clk[300 + blockIdx.x] = (clock64() - tn0) / (n_it > 0 ? n_it : 1);
+    if (acc == 123.456f) w.gbuf[0] = acc;
   }
   tc_fence_before();
   __syncthreads();
@@ -160,16 +204,18 @@ __global__ void __launch_bounds__(64, 2) mma_walk(const Walk w, long long* out_c
 }
 
 static long long* d_clk;
+static double g_noise_clk = 0;   // clocks per iteration of the background loop (CTA 0, warp 2)
 static double run(Walk w, int per_sm) {
   static long long h[512];
   const int smem = per_sm == 1 ? 200 * 1024 : 100 * 1024;
-  mma_walk<<<148 * per_sm, 64, smem>>>(w, d_clk);
+  mma_walk<<<148 * per_sm, w.noise ? 192 : 64, smem>>>(w, d_clk);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
-  cudaMemcpy(h, d_clk, sizeof(long long) * 148 * per_sm, cudaMemcpyDeviceToHost);
+  cudaMemcpy(h, d_clk, sizeof(long long) * 512, cudaMemcpyDeviceToHost);
   double avg = 0;
   for (int i = 0; i < 148 * per_sm; ++i) avg += (double)h[i];
   avg /= 148 * per_sm;
+  g_noise_clk = (double)h[300];
   return avg / ((double)w.iters * w.tiles * w.taps * w.nks) / per_sm;   // clocks per MMA per SM
 }
 
@@ -178,8 +224,27 @@ int main() {
   cudaFuncSetAttribute(mma_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   printf("fixed operands (floors): clk/MMA/SM at 1 and 2 CTAs/SM\n");
   for (int n : {32, 64, 128, 256}) {
-    Walk w{n, 8, 1, 4, 256, 1, 200, 1, 1, 0};
+    Walk w{n, 8, 1, 4, 256, 1, 200, 1, 1, 0, 0, 0, nullptr};
     printf("  N=%3d : %6.1f %6.1f\n", n, run(w, 1), n <= 128 ? run(w, 2) : 0.0);
+  }
+  printf("operand data (unrolled issue loop, 1 CTA/SM, 400 tiles): as found | zeros | random\n");
+  for (int c : {32, 64}) {
+    Walk w{c, 7, 1, c / 16, 128 * 2 + 6, 2, 200, 0, 0, 1, 0, 0, nullptr};
+    Walk wz = w; wz.fill = 1;
+    Walk wr = w; wr.fill = 2;
+    printf("  C=%3d k=7 : %6.1f | %6.1f | %6.1f\n", c, run(w, 1), run(wz, 1), run(wr, 1));
+  }
+  float* gbuf;
+  cudaMalloc(&gbuf, (size_t)300 * 4 * 128 * 16);
+  printf("background traffic from 4 other warps (unrolled issue loop, 1 CTA/SM): none | tcgen05.ld | LDS | STS | STG | all\n");
+  for (int c : {32, 64}) {
+    printf("  C=%3d k=7 :", c);
+    for (int noise : {0, 1, 2, 4, 8, 15}) {
+      Walk w{c, 7, 1, c / 16, 128 * 2 + 6, 2, 200, 0, 0, 1, 0, noise, gbuf};
+      const double r = run(w, 1);
+      printf(" %6.1f (bg loop %5.0f clk)", r, noise ? g_noise_clk : 0.0);
+    }
+    printf("\n");
   }
   printf("conv descriptor walk, 1 CTA/SM: N=C, taps, dil, MT -> clk/MMA/SM issue-loop variants\n");
   for (int c : {32, 64, 128})
@@ -187,8 +252,8 @@ int main() {
       for (int dil : {1, 5}) {
         const int mt = c == 128 ? 1 : 2;
         const int rows_a = 128 * mt + (taps - 1) * dil;
-        if ((size_t)rows_a * c * 2 + (size_t)taps * c * c * 2 > 190 * 1024) continue;
-        Walk w{c, taps, dil, c / 16, rows_a, mt, 40, 0, 0, 0};
+        if ((size_t)rows_a * c * 2 + (size_t)taps * c * c * 2 > 90 * 1024) continue;
+        Walk w{c, taps, dil, c / 16, rows_a, mt, 40, 0, 0, 0, 0, 0, nullptr};
         Walk w1 = w; w1.variant = 1;
         Walk w2 = w; w2.variant = 2;
         printf("  C=%3d k=%2d d=%d MT=%d : nested %6.1f | unrolled %6.1f | lane0 %6.1f   (2 CTAs/SM: %6.1f %6.1f %6.1f)\n", c, taps, dil, mt,

@@ -49,18 +49,25 @@ def run(name, R, cin, n, taps, dil, up=1, res=False, two_out=False, count=1):
 
 
 total = 0.0
-total += run("conv_pre", FRAMES, 192, 512, 7, 1)
-mul = 1
-for i, (s, K) in enumerate(zip((8, 8, 4, 2), (16, 16, 4, 4))):
-    cin, cout = 512 >> i, 256 >> i
-    taps = 1 if K == s else 3
-    total += run("ups%d" % i, FRAMES * mul, cin, cout * s, taps, 1, up=s)
-    mul *= s
-    R = FRAMES * mul
-    for k in (3, 7, 11):
-        for d in (1, 3, 5):
-            total += run("s%d c1 k%d d%d" % (i, k, d), R, cout, cout, k, d)
-        total += run("s%d c2 k%d (res)" % (i, k), R, cout, cout, k, 1, res=True, count=3)
+def all_convs():
+    global total
+    total = 0.0
+    total += run("conv_pre", FRAMES, 192, 512, 7, 1)
+    mul = 1
+    for i, (s, K) in enumerate(zip((8, 8, 4, 2), (16, 16, 4, 4))):
+        cin, cout = 512 >> i, 256 >> i
+        taps = 1 if K == s else 3
+        total += run("ups%d" % i, FRAMES * mul, cin, cout * s, taps, 1, up=s)
+        mul *= s
+        R = FRAMES * mul
+        for k in (3, 7, 11):
+            for d in (1, 3, 5):
+                total += run("s%d c1 k%d d%d" % (i, k, d), R, cout, cout, k, d)
+            total += run("s%d c2 k%d (res)" % (i, k), R, cout, cout, k, 1, res=True, count=3)
+
+
+if os.environ.get("CONVS", "1") == "1":
+    all_convs()
 print("sum of decoder convs: %.2f ms" % total)
 
 
@@ -72,6 +79,7 @@ def run_pair(name, R, C, k, d, count=1):
     o = torch.empty_like(x)
 
     def call():
+        check(lib.vs_set_option(b"fused_respair", 2))
         check(lib.vs_op_respair(ptr(x), ptr(w1), ptr(w2), ptr(b1), ptr(b2), None, ptr(o), None, R, C, k, d, 1.0, 1.0, None, 1, st))
     call()
     torch.cuda.synchronize()
@@ -87,9 +95,15 @@ def run_pair(name, R, C, k, d, count=1):
     print("%-22s R=%9d C=%3d k=%2d d=%d  %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s" % (name, R, C, k, d, ms, flop / ms / 1e9, byts / ms / 1e6))
 
 
-if os.environ.get("PAIRS", "1") == "1":
+if os.environ.get("QUICK"):
+    run_pair("s3 pair k3 d1", FRAMES * 512, 32, 3, 1)
+    run_pair("s3 pair k11 d1", FRAMES * 512, 32, 11, 1)
+    run_pair("s2 pair k3 d1", FRAMES * 256, 64, 3, 1)
+    run_pair("s2 pair k7 d1", FRAMES * 256, 64, 7, 1)
+elif os.environ.get("PAIRS", "1") == "1":
     for k in (3, 7, 11):
         for d in (1, 3, 5):
             run_pair("s3 pair k%d d%d" % (k, d), FRAMES * 512, 32, k, d)
-    for d in (1, 3, 5):
-        run_pair("s2 pair k3 d%d" % d, FRAMES * 256, 64, 3, d)
+    for k in (3, 7):
+        for d in (1, 3, 5):
+            run_pair("s2 pair k%d d%d" % (k, d), FRAMES * 256, 64, k, d)

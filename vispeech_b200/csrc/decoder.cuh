@@ -29,6 +29,8 @@ struct DecoderW {
   // bf16 tcgen05 path
   ConvW16 pre16, ups16[kDecStages];
   ConvW16 c1_16[kDecStages * kDecKernels][kDecDils], c2_16[kDecStages * kDecKernels][kDecDils];
+  // host copies of the ResBlock biases of the narrow stages (C <= 64): parameters of the fused pair kernel
+  float bias_host[kDecStages * kDecKernels][kDecDils][2][64];
 };
 
 using FetchFn = std::function<int(const std::string&, int64_t, int32_t, const void**)>;

@@ -39,6 +39,10 @@ int resolve_decoder_bf16(const FetchFn& fetch, DecoderW* d) {
         DBF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
         d->c1_16[n][mth].b = d->c1[n][mth].b;
         d->c2_16[n][mth].b = d->c2[n][mth].b;
+        if (cout <= 64) {
+          VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][0], d->c1[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
+          VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][1], d->c2[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
+        }
       }
     }
   }
@@ -118,7 +122,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     const int cin = kStageC[i], cout = kStageC[i + 1], s = kUpRate[i];
     int pad_l = 0;
     const int taps = ups_taps(i, &pad_l);
-    // which resblocks of this stage run as fused pairs on the raw stream (umma_respair.cu)?
+    // which resblocks of this stage run as fused conv pairs (umma_respair.cu)?
     bool fused[kDecKernels];
     for (int j = 0; j < kDecKernels; ++j) {
       fused[j] = true;
@@ -143,6 +147,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
           const bool last = (mth == kDecDils - 1);
           UmmaPair pr;
           pr.x = cur; pr.w1 = w.c1_16[n][mth].w; pr.b1 = w.c1_16[n][mth].b; pr.w2 = w.c2_16[n][mth].w; pr.b2 = w.c2_16[n][mth].b;
+          pr.b1_host = w.bias_host[n][mth][0]; pr.b2_host = w.bias_host[n][mth][1];
           pr.row_utt = valid; pr.row_div = mul; pr.R = Rs; pr.C = cout; pr.taps = k; pr.dil = kResD[mth]; pr.in_slope = 0.1f;
           if (!last) { pr.out_act = (mth == 0) ? AA : BA; pr.act_slope = 0.1f; }   // lrelu(c2(lrelu(c1(a))) + x)  modules.py:211-220
           else {

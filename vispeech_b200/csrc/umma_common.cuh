@@ -29,13 +29,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
+// Non-blocking probe (try_wait may suspend the thread for a while before it returns false).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Blocking wait = spin on try_wait (which itself parks the warp for a short, hardware-chosen time).  A suspend-time hint
+// (try_wait ..., ns -> NANOSLEEP.SYNCS) removes the spin instructions but wakes up later: measured slower on every conv.
+// Bounded: a protocol bug must abort the kernel (trap) instead of hanging the GPU; the clock is only read every 256 probes
+// so the loop is 3 instructions (spinning warps were 25 % of all issued instructions in the fused ResBlock kernel).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it)
+      if (mbar_try_wait(bar, parity)) return;
     if (clock64() - t0 > 4000000000LL) {
-      printf("umma_conv1d: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+      printf("umma: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
@@ -81,6 +99,26 @@ __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo,
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// All MMAs of one 128-row tile against resident weights: taps x NK K-chunks, accumulating into d_tmem.
+// One warp issues every MMA of a CTA, so this loop's instruction count bounds the small-N convs (tools/mma_microbench.cu:
+// runtime-nested loops cost 55-120 clk per MMA against a 40-48 clk operand-fetch floor): the K-chunk walk is unrolled.
+template <int NK>
+__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep) {
+  uint32_t accumulate = 0, a_tap = a_tile;
+#pragma unroll 2
+  for (int t = 0; t < taps; ++t, a_tap += dil) {
+    uint32_t a_lo = a_tap;
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+      tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+      accumulate = 1;
+      a_lo += a_kstep;
+      b_lo += b_kstep;
+    }
+  }
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4 (pitch between the two 16-byte K chunks of one MMA),
 // [32,46) SBO>>4 (pitch between 8-row groups), [46,48) version = 1 on sm_100, [61,64) layout = 0.

@@ -63,24 +63,6 @@ struct Params {
 // Epilogue feature flags (template parameter F of the kernel; F < 0 = all decided at run time)
 constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128, F_RESINV = 256;
 
-// All MMAs of one 128-row tile against resident weights: taps x NK K-chunks, accumulating into d_tmem.
-template <int NK>
-__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep) {
-  uint32_t accumulate = 0, a_tap = a_tile;
-#pragma unroll 2
-  for (int t = 0; t < taps; ++t, a_tap += dil) {
-    uint32_t a_lo = a_tap;
-#pragma unroll
-    for (int ks = 0; ks < NK; ++ks) {
-      tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
-      accumulate = 1;
-      a_lo += a_kstep;
-      b_lo += b_kstep;
-    }
-  }
-}
-
 template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -487,6 +469,7 @@ int make_plan(const UmmaConv& c, Plan* out) {
 
 static long long* g_timing = nullptr;
 void umma_conv_set_timing_buffer(void* dev) { g_timing = static_cast<long long*>(dev); }
+void* umma_conv_timing_buffer() { return g_timing; }
 
 int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   Params prm;

@@ -32,6 +32,7 @@ struct UmmaConv {
 };
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
+void* umma_conv_timing_buffer();
 void umma_conv_set_timing_buffer(void* dev);   // diagnostics: >= 296*12 int64 of per-CTA wait clocks, or null
 
 // One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
@@ -39,8 +40,10 @@ struct UmmaPair {
   const __nv_bfloat16* x = nullptr;      // ACTIVATED input a = lrelu(x, in_slope), planar [C/8][R][8]
   const __nv_bfloat16* w1 = nullptr;     // c1 weights, slabs as in UmmaConv (k taps, dilation dil)
   const __nv_bfloat16* w2 = nullptr;     // c2 weights (k taps, dilation 1)
-  const float* b1 = nullptr;
+  const float* b1 = nullptr;             // device
   const float* b2 = nullptr;
+  const float* b1_host = nullptr;        // optional host copies of b1 / b2 (they travel in the kernel's parameter block);
+  const float* b2_host = nullptr;        // without them the call fetches the device arrays and synchronises the stream
   const __nv_bfloat16* res2 = nullptr;   // optional running MRF sum added to y
   __nv_bfloat16* out_raw = nullptr;      // y
   __nv_bfloat16* out_act = nullptr;      // lrelu(y * act_scale, act_slope)

@@ -2,63 +2,101 @@
 //
 //     y = c2( lrelu( c1( lrelu(x) ) + b1 ) ) + b2 + x        (c1: k taps, dilation d;  c2: k taps, dilation 1)
 //
-// The unfused chain (umma_conv.cu) moves 6 activation-sized tensors through HBM per iteration (read lrelu(x), write
-// lrelu(c1), read it back, read x, write y and lrelu(y)) and stages 2-3 (C = 64, 32) sit on the HBM roofline of that
-// traffic.  Here ONE tensor is read and ONE written per iteration:
+// The unfused chain (umma_conv.cu) moves 5 activation-sized tensors through HBM per iteration (read a = lrelu(x), write
+// lrelu(c1), read it back, read a again for the residual, write the result) and stages 2-3 (C = 64, 32) sit on the HBM
+// roofline of that traffic.  Here ONE tensor is read and ONE written per iteration:
 //   * only the ACTIVATED stream a = lrelu(x) travels between iterations.  It is the conv's A operand as is (TMA bulk copy
 //     straight into the UMMA layout), and the residual is recovered in the last epilogue by inverting the leaky-relu,
 //     x = min(a, a / slope): in bf16 that costs the same relative rounding as storing x itself;
 //   * the intermediate lrelu(c1 + b1) is written by the first epilogue directly into shared memory in the layout the
 //     second conv reads (rows outside the sequence / in gaps are zeroed there: they are c2's zero padding).
-// Per CTA and super tile of L = 128*MT conv1 rows (outputs valid on L - (k-1) rows):
-//   producer  : XA[s] <- rows [s0-h1, s0+L+h1) of a (2-deep ring, zero fill outside [0,R))
-//   MMA       : conv1 (taps = descriptor offsets t*d rows into XA)   -> TMEM      | each row tile accumulates into S
-//   epilogue  : TMEM -> +b1 -> lrelu -> mask -> bf16 -> A2 (smem)                 | accumulators round-robin by K-step:
-//   MMA       : conv2 over A2 (offsets t)                             -> TMEM      | dependent MMA chains on one
-//   epilogue  : TMEM -> +b2 + x(from XA) [+ MRF sum] -> lrelu -> HBM               | accumulator cost ~250 cycles a link
-// Both convs' weights stay resident in shared memory; 2-3 CTAs share an SM and overlap each other's phases.
+//
+// Per CTA, tile i covers 128 conv1 rows and L = 128 - (k-1) output rows.  Five roles run as a software pipeline over the
+// CTA's tiles, each hand-off an mbarrier ring:
+//   warp 0      producer   XA[i % SX]  <- rows [s0-h1, s0+128+h1) of a (zero fill outside [0,R))
+//   warp 1      MMA        conv1(i) : XA -> acc1[i&1]   then   conv2(i-1) : A2[(i-1)&1] -> acc2[(i-1)&1]
+//   EW warps    epilogue 1 acc1[i&1] -> +b1 -> lrelu -> mask -> bf16 -> A2[i&1] (smem)
+//   2 x EW      epilogue 2 acc2[i&1] + b2 + lrelu^-1(XA rows) [+ MRF sum] -> lrelu -> HBM   (crew i&1 takes tile i)
+// While the tensor pipe runs, its operand fetch owns shared memory: an LDS / STS / mbarrier probe from another warp takes
+// ~250 clk and a tcgen05.ld ~300 (tools/mma_microbench.cu), so each epilogue is a chain of a few such round trips, about
+// 1.5-2.5k clk per tile.  Hence two epilogue-2 crews on alternate tiles, no redundant barriers (acc1_full(i) already
+// implies conv2(i-2) has released A2[i&1], acc2_full(i) that XA(i) has landed), biases in the kernel's constant bank, and
+// an MMA warp that probes all four of its barriers at once.
+// conv1 of the next tile is issued before conv2 of the current one, so the tensor pipe works on conv1(i+1) while epilogue 1
+// turns acc1(i) into A2(i), and on conv2(i) while epilogue 2 drains tile i-1.  Both convs' weights stay resident in shared
+// memory; the MMA issue loops are the unrolled ones of umma_common.cuh (issue rate bounds N = 32 / 64).
 #include "umma_conv.cuh"
 #include "umma_common.cuh"
+#include <type_traits>
 
 namespace vs {
 namespace {
 
 using namespace umma;
 
-constexpr int kThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2..5 epilogue (one per TMEM lane quarter)
-constexpr int kEpiWarps = 4;
-constexpr int kXA = 2;            // input ring depth
+// warp 0 producer, warp 1 MMA, then EW epilogue-1 warps and 2 x EW epilogue-2 warps; every epilogue warp owns one TMEM lane
+// quarter x one 32-column chunk of a tile: EW = N / 8 (4 warps per crew at N = 32, 8 at N = 64)
+__host__ __device__ constexpr int threads_for(int n) { return 64 + 3 * (n / 8) * 32; }
+constexpr int kMaxSX = 4;         // input ring depth (>= 3 keeps load(i+2), conv1(i+1) and the residual read of i apart)
 
 struct Plan {
-  int MT, L, Lout, h1, h2, planes, rows_x, rows_a2, n_super, tmem_cols, ctas_per_sm, row_div_shift, S;
+  int L, h1, h2, planes, rows_x, rows_a2, n_tiles, tmem_cols, ctas_per_sm, row_div_shift, SX;
   uint32_t xa_bytes, a2_bytes, w_bytes, smem_bytes;
-  uint32_t off_a2, off_w1, off_w2, off_bar, off_bias;
+  uint32_t off_a2, off_w1, off_w2, off_bar;
 };
 struct Params {
   UmmaPair c;
   Plan p;
+  float bias[2][64];      // b1, b2 in the kernel's constant bank: the epilogues' bias adds take them as immediate operands
+                          // (shared memory is saturated by the MMA operand fetch, an LDS there costs ~200 clk)
+  long long* dbg;         // wait-clock counters, see umma_conv.cu (only with -DVS_UMMA_TIMING)
 };
+#ifdef VS_UMMA_TIMING
+#define VS_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = dbg ? clock64() : 0;      \
+    stmt;                                           \
+    if (dbg) var += clock64() - _t0;                \
+  } while (0)
+#else
+#define VS_TIMED(var, stmt) stmt
+#endif
 
-template <int N, int S>
-__global__ void __launch_bounds__(kThreads, 3) umma_respair_kernel(const __grid_constant__ Params prm) {
+template <int N>
+__global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
+  constexpr int EW = N / 8, kThreads = threads_for(N);
   extern __shared__ __align__(128) uint8_t smem[];
   const UmmaPair& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef VS_UMMA_TIMING
+  long long* const dbg = prm.dbg;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  const long long t_start = dbg ? clock64() : 0;
+#endif
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t xa = smem_base, a2 = smem_base + p.off_a2;
   const uint32_t w1 = smem_base + p.off_w1, w2 = smem_base + p.off_w2, bar = smem_base + p.off_bar;
-  const uint32_t w_full = bar, acc1_full = bar + 8, a2_full = bar + 16, acc2_full = bar + 24, tmem_free = bar + 32;
-  auto xa_full = [&](int i) { return bar + 40u + 8u * i; };
-  auto xa_empty = [&](int i) { return bar + 56u + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 80);
-  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);      // [2][N]
+  // barrier table (8 B each)
+  const uint32_t w_full = bar;
+  auto xa_full = [&](uint32_t i) { return bar + 8u * (1 + i); };
+  auto xa_empty = [&](uint32_t i) { return bar + 8u * (1 + kMaxSX + i); };
+  auto acc1_full = [&](uint32_t i) { return bar + 8u * (1 + 2 * kMaxSX + i); };
+  auto acc1_empty = [&](uint32_t i) { return bar + 8u * (3 + 2 * kMaxSX + i); };
+  auto a2_full = [&](uint32_t i) { return bar + 8u * (5 + 2 * kMaxSX + i); };
+  auto acc2_full = [&](uint32_t i) { return bar + 8u * (9 + 2 * kMaxSX + i); };
+  auto acc2_empty = [&](uint32_t i) { return bar + 8u * (11 + 2 * kMaxSX + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (13 + 2 * kMaxSX));
 
   if (threadIdx.x == 0) {
-    mbar_init(w_full, 1); mbar_init(acc1_full, 1); mbar_init(a2_full, kEpiWarps); mbar_init(acc2_full, 1);
-    mbar_init(tmem_free, kEpiWarps);
-    for (int i = 0; i < kXA; ++i) { mbar_init(xa_full(i), 1); mbar_init(xa_empty(i), kEpiWarps); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < p.SX; ++i) { mbar_init(xa_full(i), 1); mbar_init(xa_empty(i), 1 + EW); }   // conv1 commit + epilogue 2 warps
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc1_full(i), 1); mbar_init(acc1_empty(i), EW);
+      mbar_init(a2_full(i), EW);
+      mbar_init(acc2_full(i), 1); mbar_init(acc2_empty(i), EW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -67,19 +105,22 @@ __global__ void __launch_bounds__(kThreads, 3) umma_respair_kernel(const __grid_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < N; i += kThreads) { bias_s[i] = c.b1[i]; bias_s[N + i] = c.b2[i]; }
-  // rows [L, L + 2*h2) of A2 are read by the last taps of conv2 (their outputs are discarded): keep them zero
-  for (int i = threadIdx.x; i < p.planes * 2 * p.h2; i += kThreads) {
-    const int pl = i / (2 * p.h2), j = i % (2 * p.h2);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2 + (uint32_t)(pl * p.rows_a2 + p.L + j) * 16u), "r"(0)
+  // rows [128, 128 + 2*h2) of both A2 buffers are read by the last taps of conv2 (those outputs are discarded): keep
+  // them finite
+  for (int i = threadIdx.x; i < 2 * p.planes * 2 * p.h2; i += kThreads) {
+    const int bsel = i / (p.planes * 2 * p.h2), r = i % (p.planes * 2 * p.h2);
+    const int pl = r / (2 * p.h2), j = r % (2 * p.h2);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2 + bsel * p.a2_bytes + (uint32_t)(pl * p.rows_a2 + 128 + j) * 16u),
+                 "r"(0)
                  : "memory");
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;     // accumulator (m, split) lives at column (m*S + split) * N; conv1 and conv2
-                                             // reuse the same columns (conv2 starts after epilogue 1 drained them)
+  const uint32_t tmem_base = *tmem_slot;     // columns [0, 2N): acc1 ring, [2N, 4N): acc2 ring
+  const uint32_t SX = (uint32_t)p.SX;
+
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
@@ -88,10 +129,10 @@ __global__ void __launch_bounds__(kThreads, 3) umma_respair_kernel(const __grid_
       bulk_g2s(w2, c.w2, p.w_bytes, w_full);
     }
     uint32_t slot = 0, phase = 0;
-    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x) {
-      mbar_wait(xa_empty(slot), phase ^ 1, 21);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      VS_TIMED(tw0, mbar_wait(xa_empty(slot), phase ^ 1, 21));
       const uint32_t stage = xa + slot * p.xa_bytes;
-      const int s0 = super * p.Lout - p.h2;
+      const int s0 = tile * p.L - p.h2;
       const int row_lo = s0 - p.h1, row_hi = row_lo + p.rows_x;
       const int c_lo = row_lo < 0 ? 0 : row_lo, c_hi = row_hi > c.R ? c.R : row_hi;
       const int n_zero_lo = c_lo - row_lo, n_zero_hi = row_hi - c_hi;
@@ -111,207 +152,183 @@ __global__ void __launch_bounds__(kThreads, 3) umma_respair_kernel(const __grid_
       __syncwarp();
       for (int pl = lane; pl < p.planes; pl += 32)
         bulk_g2s(stage + (uint32_t)(pl * p.rows_x + n_zero_lo) * 16u, c.x + ((size_t)pl * c.R + c_lo) * 8, bytes, xa_full(slot));
-      if (++slot == kXA) { slot = 0; phase ^= 1; }
+      if (++slot == SX) { slot = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
     const uint32_t idesc = make_idesc(N);
-    const uint32_t b_lbo = (uint32_t)N * 16u;
+    constexpr uint32_t b_lbo = (uint32_t)N * 16u, b_kstep = 2u * N;
+    constexpr int NK = N / 16;
     const uint32_t b_hi = (uint32_t)(make_desc(0, b_lbo, 128u) >> 32), b_lo_fixed = (uint32_t)make_desc(0, b_lbo, 128u);
     const uint32_t a1_lbo = (uint32_t)p.rows_x * 16u, a2_lbo = (uint32_t)p.rows_a2 * 16u;
     const uint32_t a1_hi = (uint32_t)(make_desc(0, a1_lbo, 128u) >> 32), a1_lo_fixed = (uint32_t)make_desc(0, a1_lbo, 128u);
     const uint32_t a2_hi = (uint32_t)(make_desc(0, a2_lbo, 128u) >> 32), a2_lo_fixed = (uint32_t)make_desc(0, a2_lbo, 128u);
-    constexpr uint32_t b_kstep = 2u * N;
-    constexpr int ksteps = N / 16;
-    const int taps = c.taps, MT = p.MT;
+    const uint32_t a1_kstep = 2u * (uint32_t)p.rows_x, a2_kstep = 2u * (uint32_t)p.rows_a2;
+    const uint32_t w1_lo = b_lo_fixed + (w1 >> 4), w2_lo = b_lo_fixed + (w2 >> 4);
+    const int taps = c.taps;
+    const uint32_t dil = (uint32_t)c.dil;
     mbar_wait(w_full, 0, 22);
     tc_fence_after();
-    uint32_t slot = 0, phase = 0, it = 0;
-    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      mbar_wait(tmem_free, ph ^ 1, 28);           // epilogue 2 of the previous super tile has drained the accumulators
-      mbar_wait(xa_full(slot), phase, 23);
+    auto conv2 = [&](uint32_t j, bool ready) {   // conv2 of this CTA's j-th tile: A2 rows o + t
+      const uint32_t b = j & 1u, ph = (j >> 1) & 1u;
+      if (!ready) {
+        VS_TIMED(tw1, mbar_wait(a2_full(b), ph, 24));
+        VS_TIMED(tw2, mbar_wait(acc2_empty(b), ph ^ 1u, 25));
+      }
       tc_fence_after();
-      {  // conv1: XA rows j + t*d
-        uint32_t b_lo = b_lo_fixed + (w1 >> 4);
-        uint32_t a_tap = a1_lo_fixed + ((xa + slot * p.xa_bytes) >> 4);
-        int step = 0;
-        for (int t = 0; t < taps; ++t, a_tap += (uint32_t)c.dil) {
-          uint32_t a_lo = a_tap;
-#pragma unroll
-          for (int ks = 0; ks < ksteps; ++ks, ++step) {
-            const uint32_t sp = (uint32_t)(step % S);
-            const uint32_t accumulate = step >= S ? 1u : 0u;
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-              if (m < MT)
-                tc_mma_bf16_lohi(tmem_base + (uint32_t)(m * S) * N + sp * N, a_lo + (uint32_t)(m * kTileM), a1_hi, b_lo, b_hi,
-                                 idesc, accumulate);
-            a_lo += 2u * (uint32_t)p.rows_x;
-            b_lo += b_kstep;
-          }
-        }
-        tc_commit(acc1_full);
-      }
-      mbar_wait(a2_full, ph, 24);
-      tc_fence_after();
-      {  // conv2: A2 rows o + t (dilation 1)
-        uint32_t b_lo = b_lo_fixed + (w2 >> 4);
-        uint32_t a_tap = a2_lo_fixed + (a2 >> 4);
-        int step = 0;
-        for (int t = 0; t < taps; ++t, a_tap += 1u) {
-          uint32_t a_lo = a_tap;
-#pragma unroll
-          for (int ks = 0; ks < ksteps; ++ks, ++step) {
-            const uint32_t sp = (uint32_t)(step % S);
-            const uint32_t accumulate = step >= S ? 1u : 0u;
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-              if (m < MT)
-                tc_mma_bf16_lohi(tmem_base + (uint32_t)(m * S) * N + sp * N, a_lo + (uint32_t)(m * kTileM), a2_hi, b_lo, b_hi,
-                                 idesc, accumulate);
-            a_lo += 2u * (uint32_t)p.rows_a2;
-            b_lo += b_kstep;
-          }
-        }
-        tc_commit(acc2_full);
-      }
-      if (++slot == kXA) { slot = 0; phase ^= 1; }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;
-    constexpr int n_chunks = N / 32;
-    const float slope = c.in_slope, inv_slope = 1.f / c.in_slope;
-    const float oslope = c.act_slope, oscale = c.act_scale;
-    const bool has_res2 = c.res2 != nullptr, has_raw = c.out_raw != nullptr, has_act = c.out_act != nullptr;
-    uint32_t slot = 0, it = 0;
-    // sum of the S split accumulators of row tile m, 32 columns from column cc*32
-    auto load_acc = [&](int m, int cc, uint32_t (&v)[32]) {
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * S) * N + (uint32_t)(cc * 32);
-      tmem_ld32(t_row, v);
-#pragma unroll
-      for (int sp = 1; sp < S; ++sp) {
-        uint32_t u[32];
-        tmem_ld32(t_row + (uint32_t)sp * N, u);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
-      }
+      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((a2 + b * p.a2_bytes) >> 4), a2_hi, w2_lo, b_hi, idesc, taps, 1u,
+                     a2_kstep, b_kstep);
+      tc_commit(acc2_full(b));
     };
-    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      const int s0 = super * p.Lout - p.h2;
-      const uint32_t stage = xa + slot * p.xa_bytes;
-      // ---- epilogue 1: conv1 accumulators -> A2 = lrelu(c1 + b1), zero where c2 must see padding
-      mbar_wait(acc1_full, ph, 26);
+    uint32_t slot = 0, phase = 0, i = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+      const uint32_t b = i & 1u, ph = (i >> 1) & 1u;
+      // probe all four barriers of this iteration at once (each probe is a ~250 clk shared-memory round trip)
+      const uint32_t jb = (i - 1u) & 1u, jph = ((i - 1u) >> 1) & 1u;
+      const bool r0 = mbar_test_wait(xa_full(slot), phase), r1 = mbar_test_wait(acc1_empty(b), ph ^ 1u);
+      bool r2 = false, r3 = false;
+      if (i > 0) { r2 = mbar_test_wait(a2_full(jb), jph); r3 = mbar_test_wait(acc2_empty(jb), jph ^ 1u); }
+      if (!r0) VS_TIMED(tw0, mbar_wait(xa_full(slot), phase, 23));
+      if (!r1) VS_TIMED(tw0, mbar_wait(acc1_empty(b), ph ^ 1u, 26));
       tc_fence_after();
-      for (int m = 0; m < p.MT; ++m) {
-        const int j = m * kTileM + q * 32 + lane;         // A2 local row = conv1 output row
-        const int g = s0 + j;
-        bool valid = g >= 0 && g < c.R;
-        if (valid && c.row_utt) valid = c.row_utt[g >> p.row_div_shift] >= 0;
+      issue_tile<NK>(tmem_base + b * N, a1_lo_fixed + ((xa + slot * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
+                     a1_kstep, b_kstep);     // conv1: XA rows j + t*d
+      tc_commit(acc1_full(b));
+      tc_commit(xa_empty(slot));
+      if (++slot == SX) { slot = 0; phase ^= 1; }
+      if (i > 0) conv2(i - 1, r2 && r3);
+    }
+    if (i > 0) conv2(i - 1, false);
+  } else if (warp < 2 + EW) {
+    // ------------------------------------------------------------------ epilogue 1: acc1 -> A2 = lrelu(c1 + b1)
+    const int q = warp & 3, cc = (warp - 2) >> 2;       // TMEM lane quarter, 32-column chunk
+    const float slope = c.in_slope;
+    uint32_t i = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+      const uint32_t b = i & 1u, ph = (i >> 1) & 1u;
+      const int j = q * 32 + lane;                      // A2 local row = conv1 output row
+      const int g = tile * p.L - p.h2 + j;
+      bool valid = g >= 0 && g < c.R;                   // outside the sequence / in gap rows: c2 must see zero padding
+      if (valid && c.row_utt) valid = c.row_utt[g >> p.row_div_shift] >= 0;
+      VS_TIMED(tw0, mbar_wait(acc1_full(b), ph, 27));
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * N + (uint32_t)(cc * 32), v);
+      const uint32_t a2_row = a2 + b * p.a2_bytes + (uint32_t)j * 16u;
+      auto chunk = [&](auto cc_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
-        for (int cc = 0; cc < n_chunks; ++cc) {
-          uint32_t v[32];
-          load_acc(m, cc, v);
+        for (int gq = 0; gq < 4; ++gq) {
+          constexpr int dummy = 0; (void)dummy;
+          const int co0 = CC * 32 + gq * 8;
+          uint32_t o[4] = {0, 0, 0, 0};
+          if (valid) {
+            float y[8];
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const int co0 = cc * 32 + gq * 8;
-            uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-            if (valid) {
-              float y[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co0);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + co0 + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float t = __uint_as_float(v[8 * gq + e]) + bb[e];
-                y[e] = fmaxf(t, t * slope);
-              }
-              o0 = pack_bf16x2(y[0], y[1]); o1 = pack_bf16x2(y[2], y[3]); o2 = pack_bf16x2(y[4], y[5]); o3 = pack_bf16x2(y[6], y[7]);
+            for (int e = 0; e < 8; ++e) {
+              const float t = __uint_as_float(v[8 * gq + e]) + prm.bias[0][co0 + e];
+              y[e] = fmaxf(t, t * slope);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2 + (uint32_t)((co0 >> 3) * p.rows_a2 + j) * 16u),
-                         "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                         : "memory");
+            o[0] = pack_bf16x2(y[0], y[1]); o[1] = pack_bf16x2(y[2], y[3]); o[2] = pack_bf16x2(y[4], y[5]); o[3] = pack_bf16x2(y[6], y[7]);
           }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (uint32_t)((co0 >> 3) * p.rows_a2) * 16u),
+                       "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                       : "memory");
         }
-      }
+      };
+      if (N == 32 || cc == 0) chunk(std::integral_constant<int, 0>{});
+      else chunk(std::integral_constant<int, 1>{});
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a2_full);
-
-      // ---- epilogue 2: conv2 accumulators + b2 + x (inverse lrelu of the staged input) [+ MRF sum] -> HBM
-      mbar_wait(acc2_full, ph, 27);
+      if (lane == 0) { mbar_arrive(a2_full(b)); mbar_arrive(acc1_empty(b)); }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue 2: acc2 + b2 + x [+ MRF sum] -> HBM
+    const int crew = (warp - 2 - EW) / EW;               // crew c takes this CTA's tiles i = c, c + 2, ... (accumulator buffer c)
+    const int q = warp & 3, cc = ((warp - 2 - EW) % EW) >> 2;
+    const float inv_slope = 1.f / c.in_slope;
+    const float oslope = c.act_slope, oscale = c.act_scale;
+    const bool has_res2 = c.res2 != nullptr, has_raw = c.out_raw != nullptr, has_act = c.out_act != nullptr;
+    uint32_t i = (uint32_t)crew;
+    for (int tile = blockIdx.x + crew * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, i += 2) {
+      const uint32_t b = i & 1u, ph = (i >> 1) & 1u, slot = i % SX;
+      const int o = q * 32 + lane;                      // conv2 output position within the tile
+      const int g = tile * p.L + o;
+      const bool in_tile = o < p.L && g < c.R;
+      int utt = -1;
+      if (in_tile) utt = c.row_utt ? c.row_utt[g >> p.row_div_shift] : 0;
+      const bool valid = utt >= 0;
+      // the MRF sum is fetched before waiting for the accumulator; the residual rows (staged input) right after (XA(i) is
+      // known to have landed once conv2(i) has completed)
+      uint4 rv2[4], xv[4];
+      if (valid && has_res2) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) rv2[gq] = *reinterpret_cast<const uint4*>(c.res2 + ((size_t)(cc * 4 + gq) * c.R + g) * 8);
+      }
+      VS_TIMED(tw0, mbar_wait(acc2_full(b), ph, 29));
       tc_fence_after();
-      for (int m = 0; m < p.MT; ++m) {
-        const int o = m * kTileM + q * 32 + lane;         // conv2 output position within the super tile
-        const int g = s0 + p.h2 + o;
-        const bool in_tile = o < p.Lout && g < c.R;       // g >= 0 always (s0 + h2 = super * Lout)
-        int utt = -1;
-        if (in_tile) utt = c.row_utt ? c.row_utt[g >> p.row_div_shift] : 0;
-        const bool valid = utt >= 0;
-        const uint32_t xa_row = stage + (uint32_t)(p.h1 + p.h2 + o) * 16u;
+      {
+        const uint32_t xa_row = xa + slot * p.xa_bytes + (uint32_t)(p.h1 + p.h2 + o) * 16u + (uint32_t)(cc * 4 * p.rows_x) * 16u;
 #pragma unroll
-        for (int cc = 0; cc < n_chunks; ++cc) {
-          uint4 rv2[4];
-          if (valid && has_res2) {
+        for (int gq = 0; gq < 4; ++gq)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(xv[gq].x), "=r"(xv[gq].y), "=r"(xv[gq].z), "=r"(xv[gq].w)
+                       : "r"(xa_row + (uint32_t)(gq * p.rows_x) * 16u));
+      }
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (2u + b) * N + (uint32_t)(cc * 32), v);
+      auto chunk = [&](auto cc_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq)
-              rv2[gq] = *reinterpret_cast<const uint4*>(c.res2 + ((size_t)(cc * 4 + gq) * c.R + g) * 8);
-          }
-          uint32_t v[32];
-          load_acc(m, cc, v);
-          if (in_tile) {
+        for (int gq = 0; gq < 4; ++gq) {
+          const int co0 = CC * 32 + gq * 8;
+          const size_t go = ((size_t)(co0 >> 3) * c.R + g) * 8;
+          uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
+          if (valid) {
+            float xf[8], y[8];
+            unpack_bf16x8(xv[gq], xf);
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const int co0 = cc * 32 + gq * 8;
-              const size_t go = ((size_t)(co0 >> 3) * c.R + g) * 8;
-              uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
-              if (valid) {
-                uint32_t x0, x1, x2, x3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                             : "r"(xa_row + (uint32_t)((co0 >> 3) * p.rows_x) * 16u));
-                float xf[8], y[8];
-                unpack_bf16x8(make_uint4(x0, x1, x2, x3), xf);
-                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + N + co0);
-                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + N + co0 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            for (int e = 0; e < 8; ++e)     // x = lrelu^-1(a) = min(a, a / slope)
+              y[e] = __uint_as_float(v[8 * gq + e]) + prm.bias[1][co0 + e] + fminf(xf[e], xf[e] * inv_slope);
+            if (has_res2) {
+              float f[8];
+              unpack_bf16x8(rv2[gq], f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)     // x = lrelu^-1(a) = min(a, a / slope)
-                  y[e] = __uint_as_float(v[8 * gq + e]) + bb[e] + fminf(xf[e], xf[e] * inv_slope);
-                if (has_res2) {
-                  float f[8];
-                  unpack_bf16x8(rv2[gq], f);
+              for (int e = 0; e < 8; ++e) y[e] += f[e];
+            }
+            if (has_raw)
+              raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            if (has_act) {
+              float z[8];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] += f[e];
-                }
-                if (has_raw)
-                  raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-                if (has_act) {
-                  float z[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float t = y[e] * oscale;
-                    z[e] = fmaxf(t, t * oslope);
-                  }
-                  act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
-                }
+              for (int e = 0; e < 8; ++e) {
+                const float t = y[e] * oscale;
+                z[e] = fmaxf(t, t * oslope);
               }
-              if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + go) = raw;
-              if (has_act) *reinterpret_cast<uint4*>(c.out_act + go) = act;
+              act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
             }
           }
+          if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + go) = raw;
+          if (has_act) *reinterpret_cast<uint4*>(c.out_act + go) = act;
         }
+      };
+      if (in_tile) {
+        if (N == 32 || cc == 0) chunk(std::integral_constant<int, 0>{});
+        else chunk(std::integral_constant<int, 1>{});
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(xa_empty(slot)); mbar_arrive(tmem_free); }
-      if (++slot == kXA) slot = 0;
+      if (lane == 0) { mbar_arrive(acc2_empty(b)); mbar_arrive(xa_empty(slot)); }
     }
   }
 
+#ifdef VS_UMMA_TIMING
+  if (dbg && lane == 0 && (warp < 3 || warp == 2 + EW)) {   // [cta][producer | MMA | epilogue 1 | epilogue 2][total, waits]
+    long long* o = dbg + ((size_t)blockIdx.x * 4 + (warp == 2 + EW ? 3 : warp)) * 4;
+    o[0] = clock64() - t_start; o[1] = tw0; o[2] = tw1; o[3] = tw2;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -333,59 +350,45 @@ int make_plan(const UmmaPair& c, Plan* out) {
   while ((1 << s) < c.row_div) ++s;
   VS_REQUIRE((1 << s) == c.row_div, "umma_respair: row_div=%d must be a power of two", c.row_div);
   p.row_div_shift = s;
-  p.S = (c.taps * (c.C / 16) >= 12) ? 2 : 1;       // split long dependent MMA chains over two accumulators
-  const uint32_t fixed = 128 + 2u * c.C * 4u + 256;
-  const uint32_t caps[3] = {75u * 1024, 110u * 1024, 222u * 1024};     // 3, 2, 1 CTAs per SM
-  p.MT = 0;
-  for (int pass = 0; pass < 3 && !p.MT; ++pass)
-    for (int mt = 2; mt >= 1 && !p.MT; --mt) {
-      const uint32_t L = 128u * mt;
-      const uint32_t need = kXA * p.planes * (L + 2 * p.h1) * 16u + p.planes * (L + 2 * p.h2) * 16u + 2 * p.w_bytes + fixed;
-      if (need <= caps[pass] && mt * p.S * c.C <= 512 / (3 - pass)) p.MT = mt;
-    }
-  VS_REQUIRE(p.MT > 0, "umma_respair: C=%d k=%d d=%d does not fit in shared memory", c.C, c.taps, c.dil);
-  p.L = 128 * p.MT;
-  p.Lout = p.L - 2 * p.h2;
-  p.rows_x = p.L + 2 * p.h1;
-  p.rows_a2 = p.L + 2 * p.h2;
+  p.L = kTileM - 2 * p.h2;
+  p.rows_x = kTileM + 2 * p.h1;
+  p.rows_a2 = kTileM + 2 * p.h2;
   p.xa_bytes = (uint32_t)p.planes * p.rows_x * 16u;
   p.a2_bytes = (uint32_t)p.planes * p.rows_a2 * 16u;
-  p.off_a2 = kXA * p.xa_bytes;
-  p.off_w1 = p.off_a2 + p.a2_bytes;
+  const uint32_t bar_bytes = 8u * (13 + 2 * kMaxSX) + 16u;
+  const uint32_t fixed = 2 * p.a2_bytes + 2 * p.w_bytes + bar_bytes + 256u;
+  // input ring: 3-4 stages; two CTAs per SM when that fits in half an SM's shared memory
+  const uint32_t half_sm = 112u * 1024, full_sm = 224u * 1024;
+  p.SX = 0;
+  int per_sm = 1;
+  if (fixed + 3 * p.xa_bytes <= half_sm) { per_sm = 2; p.SX = (fixed + 4 * p.xa_bytes <= half_sm) ? 4 : 3; }
+  else if (fixed + 3 * p.xa_bytes <= full_sm) { p.SX = (fixed + 4 * p.xa_bytes <= full_sm) ? 4 : 3; }
+  else if (fixed + 2 * p.xa_bytes <= full_sm) p.SX = 2;
+  VS_REQUIRE(p.SX > 0, "umma_respair: C=%d k=%d d=%d does not fit in shared memory", c.C, c.taps, c.dil);
+  p.off_a2 = p.SX * p.xa_bytes;
+  p.off_w1 = p.off_a2 + 2 * p.a2_bytes;
   p.off_w2 = p.off_w1 + p.w_bytes;
   p.off_bar = (p.off_w2 + p.w_bytes + 127u) & ~127u;
-  p.off_bias = p.off_bar + 128u;
-  p.smem_bytes = p.off_bias + 2u * c.C * 4u;
-  int cols = 32;
-  while (cols < p.MT * p.S * c.C) cols *= 2;
-  p.tmem_cols = cols;
-  int per_sm = (int)((227u * 1024) / (p.smem_bytes + 1024));
-  if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
-  if (per_sm > 3) per_sm = 3;
-  if (per_sm < 1) per_sm = 1;
+  p.smem_bytes = p.off_bar + bar_bytes;
+  p.tmem_cols = 4 * c.C;                               // 128 or 256: a power of two >= 32
+  // never more CTAs on an SM than planned (TMEM: 512 columns)
   const uint32_t min_smem = (227u * 1024) / (uint32_t)(per_sm + 1) + 1024u;
   if (p.smem_bytes < min_smem) p.smem_bytes = min_smem;
   p.ctas_per_sm = per_sm;
-  p.n_super = (c.R + p.Lout - 1) / p.Lout;
+  p.n_tiles = (c.R + p.L - 1) / p.L;
   *out = p;
   return VS_OK;
 }
 
-int g_mode = 1;      // 0 off, 1 where faster (default), 2 everywhere it fits
+int g_mode = 1;      // 0 off, 1 (default) the C = 32 stage, 2 every ResBlock iteration whose two weight sets fit in smem
 
 }  // namespace
 
 void umma_respair_enable(int mode) { g_mode = mode; }
 
-// Which ResBlock iterations run fused in the decoder.  Measured on B200 at the C2 size (profiles/decoder_convs_r1.txt):
-// in isolation the fused kernel wins only for C = 32, k = 3 (0.56 ms vs 0.31 + 0.65 ms); for k = 7 / 11 (1.05 / 1.2-1.4
-// ms vs 0.97 / 1.16 ms) and C = 64 (0.97 vs 0.87 ms) its per-CTA phase sequence (conv1 -> epilogue -> conv2 -> epilogue
-// on 4 epilogue warps, 2-3 CTAs per SM) is latency-bound.  Inside the full decoder an A/B on one box showed no net gain
-// (33.6 vs 33.8 ms), so the default is OFF; vs_set_option("fused_respair", 1 | 2) turns it on (parity-tested).
 bool umma_respair_supported(int C, int taps, int dil) {
   if (g_mode == 0) return false;
-  if (g_mode == 1 && !(C == 32 && taps == 3)) return false;
-  if (!(C == 32 || (C == 64 && taps == 3))) return false;
+  if (!(C == 32 || (C == 64 && g_mode == 2))) return false;
   UmmaPair c;
   c.C = C; c.taps = taps; c.dil = dil; c.R = 1024; c.row_div = 1; c.in_slope = 0.1f;
   Plan p;
@@ -395,8 +398,16 @@ bool umma_respair_supported(int C, int taps, int dil) {
 int umma_respair(const UmmaPair& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   VS_REQUIRE(c.x && c.w1 && c.w2 && c.b1 && c.b2 && (c.out_raw || c.out_act), "umma_respair: null pointer");
   VS_TRY(make_plan(c, &prm.p));
+  if (c.b1_host && c.b2_host) {
+    for (int i = 0; i < c.C; ++i) { prm.bias[0][i] = c.b1_host[i]; prm.bias[1][i] = c.b2_host[i]; }
+  } else {   // op-level API (tests, tools): fetch the biases; the decoder passes host copies made at model finalize
+    VS_CUDA_CHECK(cudaMemcpyAsync(prm.bias[0], c.b1, c.C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VS_CUDA_CHECK(cudaMemcpyAsync(prm.bias[1], c.b2, c.C * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -404,20 +415,17 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   int grid = n_sm * prm.p.ctas_per_sm;
-  if (grid > prm.p.n_super) grid = prm.p.n_super;
-#define VS_PAIR_CASE(NN, SS)                                                                                          \
-  if (c.C == NN && prm.p.S == SS) {                                                                                   \
+  if (grid > prm.p.n_tiles) grid = prm.p.n_tiles;
+#define VS_PAIR_CASE(NN)                                                                                              \
+  if (c.C == NN) {                                                                                                    \
     static bool cfg = false;                                                                                          \
     if (!cfg) {                                                                                                       \
-      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       cfg = true;                                                                                                     \
     }                                                                                                                 \
-    umma_respair_kernel<NN, SS><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);                                       \
+    umma_respair_kernel<NN><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                           \
   }
-  VS_PAIR_CASE(32, 1) else VS_PAIR_CASE(32, 2) else VS_PAIR_CASE(64, 1) else VS_PAIR_CASE(64, 2) else {
-    set_error("umma_respair: no instantiation for C=%d S=%d", c.C, prm.p.S);
-    return VS_ERR_INVALID;
-  }
+  VS_PAIR_CASE(32) else VS_PAIR_CASE(64)
 #undef VS_PAIR_CASE
   VS_LAUNCH_CHECK();
   return VS_OK;
