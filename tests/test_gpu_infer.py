@@ -325,15 +325,17 @@ def test_c1_log_mel_of_waveform(net, precision):
         assert float(err.mean()) <= 1e-2 and float(err.max()) <= 0.15
 
 
-def test_fused_resblock_everywhere_still_matches(net):
-    """Force every eligible ResBlock iteration (C=32 all k, C=64 k=3,7) through the fused kernel and re-check C1."""
+@pytest.mark.parametrize("mode", [0, 1])
+def test_unfused_resblock_paths_still_match(net, mode):
+    """The default decoder fuses every ResBlock iteration that fits (C=32 all k, C=64 k=3,7).  Switch the fusion off
+    (0) or restrict it to the C=32 stage (1) so the conv-by-conv tcgen05 path of those stages is re-checked against C1."""
     from vispeech_b200 import _lib
     lib = _lib.load()
     d = dict(np.load([p for p in GOLDEN if p.endswith("c1.npz")][0]))
-    _lib.check(lib.vs_set_option(b"fused_respair", 2))
+    _lib.check(lib.vs_set_option(b"fused_respair", mode))
     try:
         o, *_ = run_golden(net, d, 0)
     finally:
-        _lib.check(lib.vs_set_option(b"fused_respair", 0))
+        _lib.check(lib.vs_set_option(b"fused_respair", 2))
     ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
     assert snr_db(ref, o[0, 0].cpu()) >= 30.0

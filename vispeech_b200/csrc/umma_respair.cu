@@ -16,12 +16,14 @@
 //   warp 0      producer   XA[i % SX]  <- rows [s0-h1, s0+128+h1) of a (zero fill outside [0,R))
 //   warp 1      MMA        conv1(i) : XA -> acc1[i&1]   then   conv2(i-1) : A2[(i-1)&1] -> acc2[(i-1)&1]
 //   EW warps    epilogue 1 acc1[i&1] -> +b1 -> lrelu -> mask -> bf16 -> A2[i&1] (smem)
-//   2 x EW      epilogue 2 acc2[i&1] + b2 + lrelu^-1(XA rows) [+ MRF sum] -> lrelu -> HBM   (crew i&1 takes tile i)
+//   EW warps    epilogue 2 acc2[i&1] + b2 + lrelu^-1(XA rows) [+ MRF sum] -> lrelu -> HBM
 // While the tensor pipe runs, its operand fetch owns shared memory: an LDS / STS / mbarrier probe from another warp takes
 // ~250 clk and a tcgen05.ld ~300 (tools/mma_microbench.cu), so each epilogue is a chain of a few such round trips, about
-// 1.5-2.5k clk per tile.  Hence two epilogue-2 crews on alternate tiles, no redundant barriers (acc1_full(i) already
-// implies conv2(i-2) has released A2[i&1], acc2_full(i) that XA(i) has landed), biases in the kernel's constant bank, and
-// an MMA warp that probes all four of its barriers at once.
+// 1.5-2.5k clk per tile.  Hence no redundant barriers (acc1_full(i) already implies conv2(i-2) has released A2[i&1],
+// acc2_full(i) that XA(i) has landed), biases in the kernel's constant bank, an MMA warp that probes all four of its
+// barriers at once - and, because ncu shows the kernel bound by the instruction issue rate (IPC 2.8, 70 % of slots, two
+// thirds of them epilogue arithmetic), epilogues with a branch-free path for fully valid warps and compile-time output
+// modes.
 // conv1 of the next tile is issued before conv2 of the current one, so the tensor pipe works on conv1(i+1) while epilogue 1
 // turns acc1(i) into A2(i), and on conv2(i) while epilogue 2 drains tile i-1.  Both convs' weights stay resident in shared
 // memory; the MMA issue loops are the unrolled ones of umma_common.cuh (issue rate bounds N = 32 / 64).
@@ -34,9 +36,11 @@ namespace {
 
 using namespace umma;
 
-// warp 0 producer, warp 1 MMA, then EW epilogue-1 warps and 2 x EW epilogue-2 warps; every epilogue warp owns one TMEM lane
-// quarter x one 32-column chunk of a tile: EW = N / 8 (4 warps per crew at N = 32, 8 at N = 64)
-__host__ __device__ constexpr int threads_for(int n) { return 64 + 3 * (n / 8) * 32; }
+// warp 0 producer, warp 1 MMA, then EW epilogue-1 warps and EW epilogue-2 warps; every epilogue warp owns one TMEM lane
+// quarter x one 32-column chunk of a tile: EW = N / 8 (4 warps per stage at N = 32, 8 at N = 64)
+__host__ __device__ constexpr int threads_for(int n) { return 64 + 2 * (n / 8) * 32; }
+// what epilogue 2 writes (compile-time, so its dead paths vanish: the kernel is bound by the SM's instruction issue rate)
+enum { M_ACT = 0, M_RAW = 1, M_RAW_RES2 = 2, M_ACT_RES2_SCALE = 3, M_GENERIC = 4 };
 constexpr int kMaxSX = 4;         // input ring depth (>= 3 keeps load(i+2), conv1(i+1) and the residual read of i apart)
 
 struct Plan {
@@ -62,7 +66,7 @@ struct Params {
 #define VS_TIMED(var, stmt) stmt
 #endif
 
-template <int N>
+template <int N, int MODE>
 __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
   constexpr int EW = N / 8, kThreads = threads_for(N);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -203,36 +207,35 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     // ------------------------------------------------------------------ epilogue 1: acc1 -> A2 = lrelu(c1 + b1)
     const int q = warp & 3, cc = (warp - 2) >> 2;       // TMEM lane quarter, 32-column chunk
     const float slope = c.in_slope;
+    const int j = q * 32 + lane;                        // A2 local row = conv1 output row
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+    const uint32_t a2_lane = a2 + (uint32_t)j * 16u + (uint32_t)(cc * 4 * p.rows_a2) * 16u;
+    const uint32_t a2_plane = (uint32_t)p.rows_a2 * 16u;
     uint32_t i = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
       const uint32_t b = i & 1u, ph = (i >> 1) & 1u;
-      const int j = q * 32 + lane;                      // A2 local row = conv1 output row
       const int g = tile * p.L - p.h2 + j;
       bool valid = g >= 0 && g < c.R;                   // outside the sequence / in gap rows: c2 must see zero padding
       if (valid && c.row_utt) valid = c.row_utt[g >> p.row_div_shift] >= 0;
+      const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
       VS_TIMED(tw0, mbar_wait(acc1_full(b), ph, 27));
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * N + (uint32_t)(cc * 32), v);
-      const uint32_t a2_row = a2 + b * p.a2_bytes + (uint32_t)j * 16u;
+      tmem_ld32(t_lane + b * N, v);
+      const uint32_t a2_row = a2_lane + b * p.a2_bytes;
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
-          constexpr int dummy = 0; (void)dummy;
-          const int co0 = CC * 32 + gq * 8;
-          uint32_t o[4] = {0, 0, 0, 0};
-          if (valid) {
-            float y[8];
+          float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float t = __uint_as_float(v[8 * gq + e]) + prm.bias[0][co0 + e];
-              y[e] = fmaxf(t, t * slope);
-            }
-            o[0] = pack_bf16x2(y[0], y[1]); o[1] = pack_bf16x2(y[2], y[3]); o[2] = pack_bf16x2(y[4], y[5]); o[3] = pack_bf16x2(y[6], y[7]);
+          for (int e = 0; e < 8; ++e) {
+            const float t = __uint_as_float(v[8 * gq + e]) + prm.bias[0][CC * 32 + gq * 8 + e];
+            y[e] = fmaxf(t, t * slope);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (uint32_t)((co0 >> 3) * p.rows_a2) * 16u),
-                       "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (uint32_t)gq * a2_plane),
+                       "r"(pack_bf16x2(y[0], y[1]) & keep), "r"(pack_bf16x2(y[2], y[3]) & keep),
+                       "r"(pack_bf16x2(y[4], y[5]) & keep), "r"(pack_bf16x2(y[6], y[7]) & keep)
                        : "memory");
         }
       };
@@ -245,81 +248,91 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     }
   } else {
     // ------------------------------------------------------------------ epilogue 2: acc2 + b2 + x [+ MRF sum] -> HBM
-    const int crew = (warp - 2 - EW) / EW;               // crew c takes this CTA's tiles i = c, c + 2, ... (accumulator buffer c)
-    const int q = warp & 3, cc = ((warp - 2 - EW) % EW) >> 2;
-    const float inv_slope = 1.f / c.in_slope;
+    constexpr bool kGen = MODE == M_GENERIC;
+    const bool has_res2 = kGen ? (c.res2 != nullptr) : (MODE == M_RAW_RES2 || MODE == M_ACT_RES2_SCALE);
+    const bool has_raw = kGen ? (c.out_raw != nullptr) : (MODE == M_RAW || MODE == M_RAW_RES2);
+    const bool has_act = kGen ? (c.out_act != nullptr) : (MODE == M_ACT || MODE == M_ACT_RES2_SCALE);
+    const bool has_scale = kGen ? (c.act_scale != 1.f) : (MODE == M_ACT_RES2_SCALE);
+    const int q = warp & 3, cc = (warp - 2 - EW) >> 2;
     const float oslope = c.act_slope, oscale = c.act_scale;
-    const bool has_res2 = c.res2 != nullptr, has_raw = c.out_raw != nullptr, has_act = c.out_act != nullptr;
-    uint32_t i = (uint32_t)crew;
-    for (int tile = blockIdx.x + crew * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, i += 2) {
-      const uint32_t b = i & 1u, ph = (i >> 1) & 1u, slot = i % SX;
-      const int o = q * 32 + lane;                      // conv2 output position within the tile
+    const __nv_bfloat162 inv2 = __float2bfloat162_rn(1.f / c.in_slope);
+    const int o = q * 32 + lane;                        // conv2 output position within the tile
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * N + (uint32_t)(cc * 32);
+    const uint32_t xa_lane = xa + (uint32_t)(p.h1 + p.h2 + o) * 16u + (uint32_t)(cc * 4 * p.rows_x) * 16u;
+    const uint32_t xa_plane = (uint32_t)p.rows_x * 16u;
+    const size_t plane_elems = (size_t)c.R * 8;         // elements between consecutive 8-channel planes in HBM
+    uint32_t slot = 0, i = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
+      const uint32_t b = i & 1u, ph = (i >> 1) & 1u;
       const int g = tile * p.L + o;
       const bool in_tile = o < p.L && g < c.R;
       int utt = -1;
       if (in_tile) utt = c.row_utt ? c.row_utt[g >> p.row_div_shift] : 0;
-      const bool valid = utt >= 0;
-      // the MRF sum is fetched before waiting for the accumulator; the residual rows (staged input) right after (XA(i) is
-      // known to have landed once conv2(i) has completed)
-      uint4 rv2[4], xv[4];
-      if (valid && has_res2) {
+      const uint32_t keep = utt >= 0 ? 0xFFFFFFFFu : 0u;               // gap rows are written as exact zeros
+      const size_t row_off = (size_t)(cc * 4) * plane_elems + (size_t)g * 8;
+      uint4 rv2[4];
+      if (has_res2 && in_tile) {                        // the MRF sum is fetched before waiting for the accumulator
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) rv2[gq] = *reinterpret_cast<const uint4*>(c.res2 + ((size_t)(cc * 4 + gq) * c.R + g) * 8);
+        for (int gq = 0; gq < 4; ++gq) rv2[gq] = *reinterpret_cast<const uint4*>(c.res2 + row_off + (size_t)gq * plane_elems);
       }
       VS_TIMED(tw0, mbar_wait(acc2_full(b), ph, 29));
       tc_fence_after();
-      {
-        const uint32_t xa_row = xa + slot * p.xa_bytes + (uint32_t)(p.h1 + p.h2 + o) * 16u + (uint32_t)(cc * 4 * p.rows_x) * 16u;
+      uint4 xv[4];                                      // the residual rows: XA(i) has landed once conv2(i) has completed
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq)
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(xv[gq].x), "=r"(xv[gq].y), "=r"(xv[gq].z), "=r"(xv[gq].w)
-                       : "r"(xa_row + (uint32_t)(gq * p.rows_x) * 16u));
-      }
+      for (int gq = 0; gq < 4; ++gq)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(xv[gq].x), "=r"(xv[gq].y), "=r"(xv[gq].z), "=r"(xv[gq].w)
+                     : "r"(xa_lane + slot * p.xa_bytes + (uint32_t)gq * xa_plane));
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (2u + b) * N + (uint32_t)(cc * 32), v);
+      tmem_ld32(t_lane + b * N, v);
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
-          const int co0 = CC * 32 + gq * 8;
-          const size_t go = ((size_t)(co0 >> 3) * c.R + g) * 8;
-          uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
-          if (valid) {
-            float xf[8], y[8];
-            unpack_bf16x8(xv[gq], xf);
+          // x = lrelu^-1(a) = min(a, a / slope) on the packed pairs (1/slope = 10 is exact in bf16; the product rounds like
+          // a stored bf16 x would have), then everything else in fp32
+          const uint32_t aw[4] = {xv[gq].x, xv[gq].y, xv[gq].z, xv[gq].w};
+          float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)     // x = lrelu^-1(a) = min(a, a / slope)
-              y[e] = __uint_as_float(v[8 * gq + e]) + prm.bias[1][co0 + e] + fminf(xf[e], xf[e] * inv_slope);
-            if (has_res2) {
-              float f[8];
-              unpack_bf16x8(rv2[gq], f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] += f[e];
-            }
-            if (has_raw)
-              raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-            if (has_act) {
-              float z[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float t = y[e] * oscale;
-                z[e] = fmaxf(t, t * oslope);
-              }
-              act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
-            }
+          for (int h = 0; h < 4; ++h) {
+            const __nv_bfloat162 a2v = *reinterpret_cast<const __nv_bfloat162*>(&aw[h]);
+            const __nv_bfloat162 x2 = __hmin2(a2v, __hmul2(a2v, inv2));
+            const uint32_t xw = *reinterpret_cast<const uint32_t*>(&x2);
+            y[2 * h] = __uint_as_float(v[8 * gq + 2 * h]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h] + __uint_as_float(xw << 16);
+            y[2 * h + 1] = __uint_as_float(v[8 * gq + 2 * h + 1]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h + 1] +
+                           __uint_as_float(xw & 0xFFFF0000u);
           }
-          if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + go) = raw;
-          if (has_act) *reinterpret_cast<uint4*>(c.out_act + go) = act;
+          if (has_res2) {
+            float f[8];
+            unpack_bf16x8(rv2[gq], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] += f[e];
+          }
+          const size_t go = row_off + (size_t)gq * plane_elems;
+          if (has_raw) {
+            const uint4 raw = make_uint4(pack_bf16x2(y[0], y[1]) & keep, pack_bf16x2(y[2], y[3]) & keep,
+                                         pack_bf16x2(y[4], y[5]) & keep, pack_bf16x2(y[6], y[7]) & keep);
+            if (in_tile) *reinterpret_cast<uint4*>(c.out_raw + go) = raw;
+          }
+          if (has_act) {
+            float z[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = has_scale ? y[e] * oscale : y[e];
+              z[e] = fmaxf(t, t * oslope);
+            }
+            const uint4 act = make_uint4(pack_bf16x2(z[0], z[1]) & keep, pack_bf16x2(z[2], z[3]) & keep,
+                                         pack_bf16x2(z[4], z[5]) & keep, pack_bf16x2(z[6], z[7]) & keep);
+            if (in_tile) *reinterpret_cast<uint4*>(c.out_act + go) = act;
+          }
         }
       };
-      if (in_tile) {
-        if (N == 32 || cc == 0) chunk(std::integral_constant<int, 0>{});
-        else chunk(std::integral_constant<int, 1>{});
-      }
+      if (N == 32 || cc == 0) chunk(std::integral_constant<int, 0>{});
+      else chunk(std::integral_constant<int, 1>{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(acc2_empty(b)); mbar_arrive(xa_empty(slot)); }
+      if (++slot == SX) slot = 0;
     }
   }
 
@@ -380,7 +393,7 @@ int make_plan(const UmmaPair& c, Plan* out) {
   return VS_OK;
 }
 
-int g_mode = 1;      // 0 off, 1 (default) the C = 32 stage, 2 every ResBlock iteration whose two weight sets fit in smem
+int g_mode = 2;      // 0 off, 1 the C = 32 stage only, 2 (default) every ResBlock iteration whose two weight sets fit in smem
 
 }  // namespace
 
@@ -416,16 +429,24 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
   }
   int grid = n_sm * prm.p.ctas_per_sm;
   if (grid > prm.p.n_tiles) grid = prm.p.n_tiles;
-#define VS_PAIR_CASE(NN)                                                                                              \
-  if (c.C == NN) {                                                                                                    \
+  int mode = M_GENERIC;
+  const bool scale = c.act_scale != 1.f;
+  if (c.out_act && !c.out_raw && !c.res2 && !scale) mode = M_ACT;
+  else if (c.out_raw && !c.out_act && !c.res2) mode = M_RAW;
+  else if (c.out_raw && !c.out_act && c.res2) mode = M_RAW_RES2;
+  else if (c.out_act && !c.out_raw && c.res2 && scale) mode = M_ACT_RES2_SCALE;
+#define VS_PAIR_CASE(NN, MM)                                                                                          \
+  if (c.C == NN && mode == MM) {                                                                                      \
     static bool cfg = false;                                                                                          \
     if (!cfg) {                                                                                                       \
-      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       cfg = true;                                                                                                     \
     }                                                                                                                 \
-    umma_respair_kernel<NN><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                           \
+    umma_respair_kernel<NN, MM><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                \
   }
-  VS_PAIR_CASE(32) else VS_PAIR_CASE(64)
+  VS_PAIR_CASE(32, M_ACT) else VS_PAIR_CASE(32, M_RAW) else VS_PAIR_CASE(32, M_RAW_RES2) else VS_PAIR_CASE(32, M_ACT_RES2_SCALE)
+  else VS_PAIR_CASE(32, M_GENERIC) else VS_PAIR_CASE(64, M_ACT) else VS_PAIR_CASE(64, M_RAW) else VS_PAIR_CASE(64, M_RAW_RES2)
+  else VS_PAIR_CASE(64, M_ACT_RES2_SCALE) else VS_PAIR_CASE(64, M_GENERIC)
 #undef VS_PAIR_CASE
   VS_LAUNCH_CHECK();
   return VS_OK;
