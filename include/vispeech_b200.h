@@ -78,6 +78,8 @@ int64_t vs_launch_count(void);
  * 4096; fewer rows stay on the fp32 CUDA-core kernel).  Used by the parity tests to force either path.
  * "x3_min_rows": convs over at least this many rows (and below tf32_min_rows, or phoneme level) run as error-
  * compensated 3xTF32 on the tensor cores (default 512; fp32-level accuracy).
+ * "tf32_prior": 0 (default) = the frame prior network and the (m_p, logs_p) projection use 3xTF32 at every size (prior
+ * sampling amplifies their error), 1 = plain TF32 above tf32_min_rows like the flow (A/B measurements).
  * "fused_respair": 0 = never, 1 = only the C=32 stage's ResBlock iterations run as one fused conv-pair kernel,
  * 2 (default) = wherever both weight sets fit in shared memory (C=32 all k, C=64 k=3,7).
  * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 296*12 int64 where the tcgen05 conv kernel

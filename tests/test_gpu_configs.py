@@ -68,7 +68,7 @@ def test_c4_long_form_60s(net, state_dict):
 
 def test_batch_invariance(net):
     """An utterance's result must not depend on what else is in the batch or where its rows land (pad-free ragged rows;
-    fixed K order in every MMA): run alone vs inside a batch, with every GEMM forced onto the same (TF32) path."""
+    fixed K order in every MMA): run alone vs inside a batch, with every GEMM forced onto the same (tensor-core) path."""
     from oracle import inputs as oin
     from vispeech_b200 import _lib
     lib = _lib.load()
@@ -76,6 +76,7 @@ def test_batch_invariance(net):
     frames = oin.frame_counts(utts)
     noises = oin.draw_noise(frames, 6)
     _lib.check(lib.vs_set_option(b"tf32_min_rows", 1))
+    _lib.check(lib.vs_set_option(b"x3_min_rows", 1))      # frame prior / phoneme level: 3xTF32 for both runs
     try:
         ids = torch.stack([u["ids"] for u in utts])
         dur = torch.stack([u["duration"] for u in utts])
@@ -89,3 +90,4 @@ def test_batch_invariance(net):
         assert torch.equal(o_b[4, 0, :n], o_1[0, 0, :n])
     finally:
         _lib.check(lib.vs_set_option(b"tf32_min_rows", 4096))
+        _lib.check(lib.vs_set_option(b"x3_min_rows", 512))

@@ -48,6 +48,9 @@ struct PosteriorW {                                      // enc_q (models.py:212
 // F0 / energy prenets (measured: z error 7.5e-3 with plain TF32 there vs 4.6e-3 without; bar 1e-2).
 static int g_tf32_min_rows = 4096;      // vs_set_option("tf32_min_rows", n)
 static int g_x3_min_rows = 512;         // vs_set_option("x3_min_rows", n)
+// The frame prior network and the projection to (m_p, logs_p) stay on 3xTF32 at every size: z_p = m_p + eps * exp(logs_p)
+// amplifies their error (measured on C4: plain TF32 there gives |dz| = 1.2e-2 > the 1e-2 bar, 3xTF32 1.4e-4).
+static int g_tf32_prior = 0;            // vs_set_option("tf32_prior", 0 | 1)
 
 static int conv_rows(const ConvF32& c, const float* w_tf32, const float* w_x3, cudaStream_t st) {
   const bool shape_ok = !c.res && !c.accumulate && c.in_slope == 1.f && c.out_row_mul == 1 && c.out_row_off == 0 &&
@@ -248,6 +251,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_x3_min_rows = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "tf32_prior") {
+    vs::g_tf32_prior = value != 0;
+    return VS_OK;
+  }
   if (std::string(name) == "fused_respair") {
     vs::umma_respair_enable((int)value);
     return VS_OK;
@@ -399,11 +406,11 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   if (!W.ok) { set_error("vs_frame_prior: workspace too small"); return VS_ERR_WORKSPACE; }
   if (x_frame_out != x_f)
     VS_CUDA_CHECK(cudaMemcpyAsync(x_frame_out, x_f, sizeof(float) * (size_t)R * H, cudaMemcpyDeviceToDevice, st));
-  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st, true));       // FramePriorNet.forward models.py:466-470
+  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st, g_tf32_prior != 0));       // FramePriorNet.forward models.py:466-470
   ConvF32 c;                                                               // Projection.forward models.py:526-529
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
-  VS_TRY(conv_rows(c, m->t_proj_w, m->x_proj_w, st));
+  VS_TRY(conv_rows(c, g_tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
   return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 

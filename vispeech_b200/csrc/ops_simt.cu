@@ -127,53 +127,56 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st) {
 // LayerNorm over channels of (a + b), one warp per row; invalid rows are written as zero.
 // modules.py:29-32 (gamma/beta) and nn.LayerNorm(768) of frame_prior_network.py:83,95 share this.
 // ------------------------------------------------------------------------------------------------
-__global__ void layernorm_rows_kernel(const float* a, const float* b,   // a/b may alias out (in-place residual LN)
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float* out, int R, int C, const int32_t* __restrict__ row_utt) {
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, const float* b,   // a/b may alias out (in-place residual LN)
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* out, int R, const int32_t* __restrict__ row_utt) {
+  constexpr int PER = C / 64;                          // float2 per lane: one warp owns a row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= R) return;
-  const size_t base = (size_t)warp * C;
-  const bool valid = !row_utt || row_utt[warp] >= 0;
-  if (!valid) {
-    for (int c = lane; c < C; c += 32) out[base + c] = 0.f;
+  const float2* a2 = reinterpret_cast<const float2*>(a + (size_t)warp * C);
+  const float2* b2 = b ? reinterpret_cast<const float2*>(b + (size_t)warp * C) : nullptr;
+  float2* o2 = reinterpret_cast<float2*>(out + (size_t)warp * C);
+  if (row_utt && row_utt[warp] < 0) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) o2[lane + 32 * i] = make_float2(0.f, 0.f);
     return;
   }
-  float v[24];  // C <= 768; fully unrolled so v stays in registers
+  float2 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) v[i] = a2[lane + 32 * i];
+  if (b2) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { const float2 w = b2[lane + 32 * i]; v[i].x += w.x; v[i].y += w.y; }
+  }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = 0.f;
-    if (c < C) {
-      float x = a[base + c];
-      if (b) x += b[base + c];
-      v[i] = x;
-      s += x;
-    }
-  }
+  for (int i = 0; i < PER; ++i) s += v[i].x + v[i].y;
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 24; ++i)
-    if (lane + 32 * i < C) { const float d = v[i] - mean; q += d * d; }
+  for (int i = 0; i < PER; ++i) { const float dx = v[i].x - mean, dy = v[i].y - mean; q += dx * dx + dy * dy; }
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / C + 1e-5f);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma);
+  const float2* be2 = reinterpret_cast<const float2*>(beta);
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) out[base + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  for (int i = 0; i < PER; ++i) {
+    const float2 g = g2[lane + 32 * i], be = be2[lane + 32 * i];
+    o2[lane + 32 * i] = make_float2((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
   }
 }
 
 int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
                    const int32_t* row_utt, cudaStream_t st) {
-  VS_REQUIRE(C <= 768 && C % 32 == 0, "layernorm: C=%d unsupported", C);
-  const int warps_per_block = 8;
-  layernorm_rows_kernel<<<(R + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-      a, b, gamma, beta, out, R, C, row_utt);
+  VS_REQUIRE(C == 192 || C == 256 || C == 768, "layernorm: C=%d unsupported (192, 256 or 768)", C);
+  const int warps_per_block = 8, grid = (R + warps_per_block - 1) / warps_per_block;
+  if (C == 192) layernorm_rows_kernel<192><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
+  else if (C == 256) layernorm_rows_kernel<256><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
+  else layernorm_rows_kernel<768><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

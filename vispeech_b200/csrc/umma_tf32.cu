@@ -26,6 +26,9 @@ constexpr int kSA = 2, kSB = 3;
 
 struct Plan {
   int rows_a, halo_l, n_ka, slabs_per_ka, Nblk, NB, NACC, tmem_cols, n_tiles, n_units;
+  int NS, Npack;          // the weights are packed in NB blocks of Npack columns; a unit computes Nblk = Npack / NS of them
+                          // (NS > 1 when there are too few row tiles to fill the GPU: phoneme-level convs)
+  uint32_t bp_half, bp_bytes;   // packed slab geometry (bytes of one [hi] half / of the whole slab in HBM)
   int KA, slabC;          // channels per activation stage / per weight slab
   uint32_t a_half, b_half; // byte offset of the lo copy inside a stage / slab (split3)
   uint32_t a_bytes, b_bytes, smem_bytes, off_b, off_bar;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const int tid = threadIdx.x;                       // 0..127
     uint32_t slot = 0, phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int tile = u / p.NB;
+      const int tile = u / (p.NB * p.NS);
       const int row_lo = tile * kTileM - p.halo_l;
       for (int ka = 0; ka < p.n_ka; ++ka) {
         mbar_wait(a_empty(slot), phase ^ 1, 11);
@@ -131,13 +134,22 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     // ------------------------------------------------------------- weight slab producer (TMA bulk)
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
+      const int halves = c.split3 ? 2 : 1, planes = p.slabC / 4;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int nb = u % p.NB;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.w) + (size_t)nb * slabs_per_unit * p.b_bytes;
+        const int nbe = u % (p.NB * p.NS), nb = nbe / p.NS, sub = nbe % p.NS;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.w) + (size_t)nb * slabs_per_unit * p.bp_bytes;
         for (int s = 0; s < slabs_per_unit; ++s) {
           mbar_wait(b_empty(slot), phase ^ 1, 12);
           mbar_arrive_expect_tx(b_full(slot), p.b_bytes);
-          bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.b_bytes, p.b_bytes, b_full(slot));
+          if (p.NS == 1) {
+            bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.bp_bytes, p.b_bytes, b_full(slot));
+          } else {   // column sub-block of a packed slab: one copy per 4-channel plane (Nblk * 16 B each)
+            for (int hf = 0; hf < halves; ++hf)
+              for (int pl = 0; pl < planes; ++pl)
+                bulk_g2s(b_base + slot * p.b_bytes + hf * p.b_half + (uint32_t)(pl * p.Nblk) * 16u,
+                         wsrc + (size_t)s * p.bp_bytes + hf * p.bp_half + (size_t)(pl * p.Npack + sub * p.Nblk) * 16u,
+                         (uint32_t)p.Nblk * 16u, b_full(slot));
+          }
           if (++slot == kSB) { slot = 0; phase ^= 1; }
         }
       }
@@ -195,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const int n_chunks = p.Nblk / 32;
     uint32_t acc_slot = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int tile = u / p.NB, nb = u % p.NB;
+      const int nbe = u % (p.NB * p.NS), tile = u / (p.NB * p.NS), nb = nbe / p.NS;
+      const int nb_col0 = nb * p.Npack + (nbe % p.NS) * p.Nblk;
       const int r = tile * kTileM + q * 32 + lane;
       const bool in_range = r < c.R;
       int utt = -1;
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(cc * 32), v);
         if (in_range) {
-          const int col0 = nb * p.Nblk + cc * 32;
+          const int col0 = nb_col0 + cc * 32;
           if (c.epi == 1) {
             // WN gate: this chunk = [16 tanh pre-activations | 16 sigmoid pre-activations] of channels ch0..ch0+15
             float* o = c.out + (size_t)r * c.out_ld + (col0 >> 1);
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
   }
 }
 
-int make_plan(const UmmaTf32& c, Plan* out) {
+int make_plan(const UmmaTf32& c, int n_sm, Plan* out) {
   Plan p{};
   VS_REQUIRE(c.N % 32 == 0, "umma_tf32: N=%d must be a multiple of 32", c.N);
   VS_REQUIRE(c.R > 0 && c.taps >= 1 && c.dil >= 1 && c.pad_l >= 0, "umma_tf32: bad shape");
@@ -319,6 +332,21 @@ int make_plan(const UmmaTf32& c, Plan* out) {
     if (c.N % nb == 0 && c.N / nb <= 256 && (c.N / nb) % 32 == 0) p.Nblk = c.N / nb;
   VS_REQUIRE(p.Nblk > 0, "umma_tf32: cannot split N=%d into <= 256-column blocks", c.N);
   p.NB = c.N / p.Nblk;
+  p.Npack = p.Nblk;
+  p.n_tiles = (c.R + kTileM - 1) / kTileM;
+  p.NS = 1;
+  if (c.epi == 0 && n_sm > 0) {
+    // too few row tiles for the GPU (phoneme level: 22 tiles) or a ragged last wave: let several CTAs share a row tile, each
+    // computing a column sub-block.  Modelled time = waves * (1 / NS + the per-unit cost of loading the A tile again).
+    double best = 1e30;
+    for (int ns = 1; ns <= 8; ++ns) {
+      if (p.Npack % ns || (p.Npack / ns) % 32) continue;
+      const int units = p.n_tiles * p.NB * ns;
+      const double cost = (double)((units + n_sm - 1) / n_sm) * (1.0 / ns + 0.15);
+      if (cost < best - 1e-9) { best = cost; p.NS = ns; }
+    }
+    p.Nblk = p.Npack / p.NS;
+  }
   p.KA = c.split3 ? 48 : 96;
   p.slabC = c.split3 ? 16 : 32;
   VS_REQUIRE(c.Cin % p.slabC == 0, "umma_tf32: Cin=%d must be a multiple of %d", c.Cin, p.slabC);
@@ -333,6 +361,8 @@ int make_plan(const UmmaTf32& c, Plan* out) {
   p.a_bytes = p.a_half * (c.split3 ? 2u : 1u);
   p.b_half = (uint32_t)p.slabC * p.Nblk * 4u;
   p.b_bytes = p.b_half * (c.split3 ? 2u : 1u);
+  p.bp_half = (uint32_t)p.slabC * p.Npack * 4u;
+  p.bp_bytes = p.bp_half * (c.split3 ? 2u : 1u);
   p.NACC = 512 / p.Nblk;
   if (p.NACC > 8) p.NACC = 8;
   VS_REQUIRE(p.NACC >= 2, "umma_tf32: TMEM too small");
@@ -344,8 +374,7 @@ int make_plan(const UmmaTf32& c, Plan* out) {
   p.smem_bytes = p.off_bar + 8u * 32 + 16u;
   VS_REQUIRE(p.smem_bytes <= 227u * 1024, "umma_tf32: tile does not fit in shared memory");
   if (p.smem_bytes < 120u * 1024) p.smem_bytes = 120u * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
-  p.n_tiles = (c.R + kTileM - 1) / kTileM;
-  p.n_units = p.n_tiles * p.NB;
+  p.n_units = p.n_tiles * p.NB * p.NS;
   *out = p;
   return VS_OK;
 }
@@ -357,7 +386,6 @@ int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
   prm.c = c;
   VS_REQUIRE(c.in && c.w && c.out, "umma_tf32: null pointer");
   VS_REQUIRE(c.epi != 2 || (c.out2 && c.out2_ld % 4 == 0), "umma_tf32: epi=2 needs out2");
-  VS_TRY(make_plan(c, &prm.p));
   static int n_sm = 0;
   static bool configured = false;
   if (!configured) {
@@ -367,6 +395,7 @@ int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  VS_TRY(make_plan(c, n_sm, &prm.p));
   int grid = n_sm < prm.p.n_units ? n_sm : prm.p.n_units;
   umma_tf32_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
   VS_LAUNCH_CHECK();
