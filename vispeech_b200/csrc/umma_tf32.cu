@@ -12,6 +12,7 @@
 //   * Work unit = (128-row tile, n-block <= 256 columns); persistent CTAs stride over units.
 #include "umma_tf32.cuh"
 #include "umma_common.cuh"
+#include "umma_conv.cuh"
 
 namespace vs {
 namespace {
@@ -21,14 +22,12 @@ using namespace umma;
 constexpr int kLoaderWarps = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (kLoaderWarps + 2 + kEpiWarps);   // loaders | weight producer | MMA | epilogue
-constexpr int kSA = 2, kSB = 3;
+constexpr int kSA = 2, kMaxSB = 16;   // weight ring: as many slabs as fit (>= 3): the stream is latency-bound otherwise
 // plain TF32: 96 channels per activation stage, 32 per weight slab; 3xTF32: 48 / 16 with [hi|lo] pairs (same bytes)
 
 struct Plan {
   int rows_a, halo_l, n_ka, slabs_per_ka, Nblk, NB, NACC, tmem_cols, n_tiles, n_units;
-  int NS, Npack;          // the weights are packed in NB blocks of Npack columns; a unit computes Nblk = Npack / NS of them
-                          // (NS > 1 when there are too few row tiles to fill the GPU: phoneme-level convs)
-  uint32_t bp_half, bp_bytes;   // packed slab geometry (bytes of one [hi] half / of the whole slab in HBM)
+  int SB;                 // weight ring depth
   int KA, slabC;          // channels per activation stage / per weight slab
   uint32_t a_half, b_half; // byte offset of the lo copy inside a stage / slab (split3)
   uint32_t a_bytes, b_bytes, smem_bytes, off_b, off_bar;
@@ -36,7 +35,18 @@ struct Plan {
 struct Params {
   UmmaTf32 c;
   Plan p;
+  long long* dbg;         // wait-clock counters, see umma_conv.cu (only with -DVS_UMMA_TIMING)
 };
+#ifdef VS_UMMA_TIMING
+#define VS_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = dbg ? clock64() : 0;      \
+    stmt;                                           \
+    if (dbg) var += clock64() - _t0;                \
+  } while (0)
+#else
+#define VS_TIMED(var, stmt) stmt
+#endif
 
 __device__ __forceinline__ void tc_mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                                  uint32_t idesc, uint32_t accumulate) {
@@ -65,19 +75,24 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
   const UmmaTf32& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef VS_UMMA_TIMING
+  long long* const dbg = prm.dbg;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  const long long t_start = dbg ? clock64() : 0;
+#endif
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base, b_base = smem_base + p.off_b, bar_base = smem_base + p.off_bar;
   auto a_full = [&](int i) { return bar_base + 8u * i; };
   auto a_empty = [&](int i) { return bar_base + 8u * (4 + i); };
-  auto b_full = [&](int i) { return bar_base + 8u * (8 + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (12 + i); };
-  auto acc_full = [&](int i) { return bar_base + 8u * (16 + i); };
-  auto acc_empty = [&](int i) { return bar_base + 8u * (24 + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * 32);
+  auto acc_full = [&](int i) { return bar_base + 8u * (8 + i); };
+  auto acc_empty = [&](int i) { return bar_base + 8u * (16 + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (24 + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (24 + kMaxSB + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_bar + 8 * (24 + 2 * kMaxSB));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSA; ++i) { mbar_init(a_full(i), kLoaderWarps); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < kSB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < p.NACC; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -95,62 +110,91 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
 
   if (warp < kLoaderWarps) {
     // ------------------------------------------------------------- activation loaders (128 threads)
+    // Thread t owns row t of every stage (plus one halo row for the first few threads).  The global loads of stage i+1 are
+    // issued into registers right after stage i has been written to shared memory, so their latency overlaps the wait
+    // for the ring slot (i.e. the MMAs of the stages before) instead of adding ~1.5 us to every stage.
     const int tid = threadIdx.x;                       // 0..127
+    constexpr int kPF = 12;                            // float4 per thread held in flight (= planes of a 48-channel stage)
     uint32_t slot = 0, phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int tile = u / (p.NB * p.NS);
-      const int row_lo = tile * kTileM - p.halo_l;
-      for (int ka = 0; ka < p.n_ka; ++ka) {
-        mbar_wait(a_empty(slot), phase ^ 1, 11);
-        const uint32_t stage = a_base + slot * p.a_bytes;
-        const int ch0 = ka * p.KA;
-        const int n_planes = min(p.KA, c.Cin - ch0) / 4;
-        for (int row = tid; row < p.rows_a; row += 32 * kLoaderWarps) {
-          const int rg = row_lo + row;
-          const bool ok = rg >= 0 && rg < c.R;
-          const float* src = c.in + (size_t)(ok ? rg : 0) * c.in_ld + ch0;
-          const uint32_t dst = stage + (uint32_t)row * 16u;
-#pragma unroll 8
-          for (int pl = 0; pl < n_planes; ++pl) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v = *reinterpret_cast<const float4*>(src + 4 * pl);
-            const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(pl * p.rows_a) * 16u),
-                         "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
-                         : "memory");
-            if (c.split3)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + p.a_half + (uint32_t)(pl * p.rows_a) * 16u),
-                           "f"(to_tf32(v.x - hi.x)), "f"(to_tf32(v.y - hi.y)), "f"(to_tf32(v.z - hi.z)), "f"(to_tf32(v.w - hi.w))
-                           : "memory");
-          }
-        }
-        fence_proxy_async();                         // generic-proxy smem writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(slot));
-        if (++slot == kSA) { slot = 0; phase ^= 1; }
+    float4 pf[kPF];
+    auto stage_src = [&](int u, int ka, int row, bool* ok) -> const float* {
+      const int tile = u / p.NB;
+      const int rg = tile * kTileM - p.halo_l + row;
+      *ok = rg >= 0 && rg < c.R;
+      return c.in + (size_t)(*ok ? rg : 0) * c.in_ld + ka * p.KA;
+    };
+    auto prefetch = [&](int u, int ka) {
+      bool ok;
+      const float* src = stage_src(u, ka, tid, &ok);
+      const int n_planes = min(p.KA, c.Cin - ka * p.KA) / 4;
+#pragma unroll
+      for (int pl = 0; pl < kPF; ++pl) {
+        pf[pl] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && pl < n_planes) pf[pl] = *reinterpret_cast<const float4*>(src + 4 * pl);
       }
+    };
+    auto put = [&](uint32_t dst, const float4& v) {
+      const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+      if (c.split3)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + p.a_half), "f"(to_tf32(v.x - hi.x)),
+                     "f"(to_tf32(v.y - hi.y)), "f"(to_tf32(v.z - hi.z)), "f"(to_tf32(v.w - hi.w))
+                     : "memory");
+    };
+    int u = blockIdx.x, ka = 0;
+    if (u < p.n_units) prefetch(u, 0);
+    while (u < p.n_units) {
+      VS_TIMED(tw0, mbar_wait(a_empty(slot), phase ^ 1, 11));
+      const uint32_t stage = a_base + slot * p.a_bytes;
+      const int n_planes = min(p.KA, c.Cin - ka * p.KA) / 4;
+#pragma unroll
+      for (int pl = 0; pl < kPF; ++pl)
+        if (pl < n_planes) put(stage + (uint32_t)tid * 16u + (uint32_t)(pl * p.rows_a) * 16u, pf[pl]);
+      // planes beyond the prefetch depth (96-channel stages) and the halo rows: loaded here
+      for (int row = tid; row < p.rows_a; row += 32 * kLoaderWarps) {
+        bool ok;
+        const float* src = stage_src(u, ka, row, &ok);
+        for (int pl = (row == tid ? kPF : 0); pl < n_planes; ++pl) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v = *reinterpret_cast<const float4*>(src + 4 * pl);
+          put(stage + (uint32_t)row * 16u + (uint32_t)(pl * p.rows_a) * 16u, v);
+        }
+      }
+      fence_proxy_async();                         // generic-proxy smem writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(slot));
+      if (++slot == kSA) { slot = 0; phase ^= 1; }
+      if (++ka == p.n_ka) { ka = 0; u += gridDim.x; }
+      if (u < p.n_units) prefetch(u, ka);
     }
   } else if (warp == kLoaderWarps) {
     // ------------------------------------------------------------- weight slab producer (TMA bulk)
-    if (lane == 0) {
+    {
+      // Every mbarrier probe is a ~250 clk shared-memory round trip while the tensor pipe runs, and a weight slab is only
+      // 6-24 MMAs of work: the ring slots two and one ahead are probed while the current slab is being issued.
       uint32_t slot = 0, phase = 0;
-      const int halves = c.split3 ? 2 : 1, planes = p.slabC / 4;
+      const uint32_t SB = (uint32_t)p.SB;
+      auto ahead = [&](uint32_t sl, uint32_t ph, uint32_t d, uint32_t* s2, uint32_t* p2) {
+        sl += d;
+        if (sl >= SB) { sl -= SB; ph ^= 1; }
+        *s2 = sl; *p2 = ph;
+      };
+      uint32_t s1, p1, s2, p2;
+      ahead(slot, phase, 1 % SB, &s1, &p1);
+      bool r0 = mbar_test_wait(b_empty(slot), phase ^ 1), r1 = SB > 1 && mbar_test_wait(b_empty(s1), p1 ^ 1);
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int nbe = u % (p.NB * p.NS), nb = nbe / p.NS, sub = nbe % p.NS;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.w) + (size_t)nb * slabs_per_unit * p.bp_bytes;
+        const int nb = u % p.NB;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.w) + (size_t)nb * slabs_per_unit * p.b_bytes;
         for (int s = 0; s < slabs_per_unit; ++s) {
-          mbar_wait(b_empty(slot), phase ^ 1, 12);
-          mbar_arrive_expect_tx(b_full(slot), p.b_bytes);
-          if (p.NS == 1) {
-            bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.bp_bytes, p.b_bytes, b_full(slot));
-          } else {   // column sub-block of a packed slab: one copy per 4-channel plane (Nblk * 16 B each)
-            for (int hf = 0; hf < halves; ++hf)
-              for (int pl = 0; pl < planes; ++pl)
-                bulk_g2s(b_base + slot * p.b_bytes + hf * p.b_half + (uint32_t)(pl * p.Nblk) * 16u,
-                         wsrc + (size_t)s * p.bp_bytes + hf * p.bp_half + (size_t)(pl * p.Npack + sub * p.Nblk) * 16u,
-                         (uint32_t)p.Nblk * 16u, b_full(slot));
+          if (!r0) VS_TIMED(tw0, mbar_wait(b_empty(slot), phase ^ 1, 12));
+          ahead(slot, phase, 2, &s2, &p2);
+          const bool r2 = SB > 2 && mbar_test_wait(b_empty(s2), p2 ^ 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(b_full(slot), p.b_bytes);
+            bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.b_bytes, p.b_bytes, b_full(slot));
           }
-          if (++slot == kSB) { slot = 0; phase ^= 1; }
+          ahead(slot, phase, 1, &slot, &phase);
+          r0 = r1; r1 = r2;
         }
       }
     }
@@ -164,34 +208,52 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const uint32_t a_kstep = 2u * (uint32_t)p.rows_a, b_kstep = 2u * (uint32_t)p.Nblk;
     const uint32_t slab_planes = (uint32_t)p.slabC / 4;
     uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, acc_slot = 0, acc_phase = 0;
+    const uint32_t SB = (uint32_t)p.SB;
+    auto ahead = [&](uint32_t sl, uint32_t ph, uint32_t d, uint32_t* s2, uint32_t* p2) {
+      sl += d;
+      if (sl >= SB) { sl -= SB; ph ^= 1; }
+      *s2 = sl; *p2 = ph;
+    };
+    uint32_t bs1, bp1, bs2, bp2;
+    ahead(b_slot, b_phase, 1 % SB, &bs1, &bp1);
+    bool r0 = mbar_test_wait(b_full(b_slot), b_phase), r1 = SB > 1 && mbar_test_wait(b_full(bs1), bp1);
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 13);
+      VS_TIMED(tw1, mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 13));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc_slot * (uint32_t)p.Nblk;
       uint32_t accumulate = 0;
       for (int ka = 0; ka < p.n_ka; ++ka) {
-        mbar_wait(a_full(a_slot), a_phase, 14);
+        VS_TIMED(tw0, mbar_wait(a_full(a_slot), a_phase, 14));
         tc_fence_after();
         const uint32_t a_stage16 = (a_base + a_slot * p.a_bytes) >> 4;
         const int slabs_here = min(p.KA, c.Cin - ka * p.KA) / p.slabC;
         for (int t = 0; t < c.taps; ++t)
           for (int j = 0; j < slabs_here; ++j) {
-            mbar_wait(b_full(b_slot), b_phase, 15);
+            if (!r0) VS_TIMED(tw2, mbar_wait(b_full(b_slot), b_phase, 15));
+            ahead(b_slot, b_phase, 2, &bs2, &bp2);
+            const bool r2 = SB > 2 && mbar_test_wait(b_full(bs2), bp2);      // probe two slabs ahead (see the producer)
             tc_fence_after();
             uint32_t a_lo = a_lo_fixed + a_stage16 + (uint32_t)j * slab_planes * (uint32_t)p.rows_a + (uint32_t)(t * c.dil);
             uint32_t b_lo = b_lo_fixed + ((b_base + b_slot * p.b_bytes) >> 4);
-            for (int k8 = 0; k8 < p.slabC / 8; ++k8) {
-              tc_mma_tf32_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
-              accumulate = 1;
-              if (c.split3) {
-                tc_mma_tf32_lohi(d_tmem, a_lo + (p.a_half >> 4), a_hi, b_lo, b_hi, idesc, 1u);   // a_lo * w_hi
-                tc_mma_tf32_lohi(d_tmem, a_lo, a_hi, b_lo + (p.b_half >> 4), b_hi, idesc, 1u);   // a_hi * w_lo
+            // fully unrolled per-slab issue (one warp issues every MMA: runtime-nested loops cost ~100 clk per MMA,
+            // tools/mma_microbench.cu): 3xTF32 = 2 K-steps x {hi*hi, lo*hi, hi*lo}, plain = 4 K-steps
+            if (c.split3) {
+              const uint32_t a_lo2 = a_lo + (p.a_half >> 4), b_lo2 = b_lo + (p.b_half >> 4);
+#pragma unroll
+              for (int k8 = 0; k8 < 2; ++k8) {
+                tc_mma_tf32_lohi(d_tmem, a_lo + k8 * a_kstep, a_hi, b_lo + k8 * b_kstep, b_hi, idesc, k8 ? 1u : accumulate);
+                tc_mma_tf32_lohi(d_tmem, a_lo2 + k8 * a_kstep, a_hi, b_lo + k8 * b_kstep, b_hi, idesc, 1u);   // a_lo * w_hi
+                tc_mma_tf32_lohi(d_tmem, a_lo + k8 * a_kstep, a_hi, b_lo2 + k8 * b_kstep, b_hi, idesc, 1u);   // a_hi * w_lo
               }
-              a_lo += a_kstep;
-              b_lo += b_kstep;
+            } else {
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                tc_mma_tf32_lohi(d_tmem, a_lo + k8 * a_kstep, a_hi, b_lo + k8 * b_kstep, b_hi, idesc, k8 ? 1u : accumulate);
             }
+            accumulate = 1;
             tc_commit(b_empty(b_slot));
-            if (++b_slot == kSB) { b_slot = 0; b_phase ^= 1; }
+            ahead(b_slot, b_phase, 1, &b_slot, &b_phase);
+            r0 = r1; r1 = r2;
           }
         tc_commit(a_empty(a_slot));
         if (++a_slot == kSA) { a_slot = 0; a_phase ^= 1; }
@@ -207,8 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const int n_chunks = p.Nblk / 32;
     uint32_t acc_slot = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int nbe = u % (p.NB * p.NS), tile = u / (p.NB * p.NS), nb = nbe / p.NS;
-      const int nb_col0 = nb * p.Npack + (nbe % p.NS) * p.Nblk;
+      const int tile = u / p.NB, nb = u % p.NB;
       const int r = tile * kTileM + q * 32 + lane;
       const bool in_range = r < c.R;
       int utt = -1;
@@ -216,14 +277,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
       const bool valid = utt >= 0;
       const float* ub = nullptr;
       if (c.ubias && valid) ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.ubias_ld;
-      mbar_wait(acc_full(acc_slot), acc_phase, 16);
+      VS_TIMED(tw0, mbar_wait(acc_full(acc_slot), acc_phase, 16));
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc_slot * (uint32_t)p.Nblk;
       for (int cc = hsel; cc < n_chunks; cc += 2) {
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(cc * 32), v);
         if (in_range) {
-          const int col0 = nb_col0 + cc * 32;
+          const int col0 = nb * p.Nblk + cc * 32;
           if (c.epi == 1) {
             // WN gate: this chunk = [16 tanh pre-activations | 16 sigmoid pre-activations] of channels ch0..ch0+15
             float* o = c.out + (size_t)r * c.out_ld + (col0 >> 1);
@@ -310,6 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     }
   }
 
+#ifdef VS_UMMA_TIMING
+  if (dbg && lane == 0 && (warp == 0 || (warp >= kLoaderWarps && warp <= kLoaderWarps + 2))) {
+    // [cta][loader | weight producer | MMA | first epilogue warp][total, waits]
+    long long* o = dbg + ((size_t)blockIdx.x * 4 + (warp == 0 ? 0 : warp - kLoaderWarps + 1)) * 4;
+    o[0] = clock64() - t_start; o[1] = tw0; o[2] = tw1; o[3] = tw2;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == kLoaderWarps + 1) {
@@ -318,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
   }
 }
 
-int make_plan(const UmmaTf32& c, int n_sm, Plan* out) {
+int make_plan(const UmmaTf32& c, Plan* out) {
   Plan p{};
   VS_REQUIRE(c.N % 32 == 0, "umma_tf32: N=%d must be a multiple of 32", c.N);
   VS_REQUIRE(c.R > 0 && c.taps >= 1 && c.dil >= 1 && c.pad_l >= 0, "umma_tf32: bad shape");
@@ -332,22 +400,8 @@ int make_plan(const UmmaTf32& c, int n_sm, Plan* out) {
     if (c.N % nb == 0 && c.N / nb <= 256 && (c.N / nb) % 32 == 0) p.Nblk = c.N / nb;
   VS_REQUIRE(p.Nblk > 0, "umma_tf32: cannot split N=%d into <= 256-column blocks", c.N);
   p.NB = c.N / p.Nblk;
-  p.Npack = p.Nblk;
   p.n_tiles = (c.R + kTileM - 1) / kTileM;
-  p.NS = 1;
-  if (c.epi == 0 && n_sm > 0) {
-    // too few row tiles for the GPU (phoneme level: 22 tiles) or a ragged last wave: let several CTAs share a row tile, each
-    // computing a column sub-block.  Modelled time = waves * (1 / NS + the per-unit cost of loading the A tile again).
-    double best = 1e30;
-    for (int ns = 1; ns <= 8; ++ns) {
-      if (p.Npack % ns || (p.Npack / ns) % 32) continue;
-      const int units = p.n_tiles * p.NB * ns;
-      const double cost = (double)((units + n_sm - 1) / n_sm) * (1.0 / ns + 0.15);
-      if (cost < best - 1e-9) { best = cost; p.NS = ns; }
-    }
-    p.Nblk = p.Npack / p.NS;
-  }
-  p.KA = c.split3 ? 48 : 96;
+  p.KA = c.split3 ? 48 : 96;                                      // must match packing.pack_tf32
   p.slabC = c.split3 ? 16 : 32;
   VS_REQUIRE(c.Cin % p.slabC == 0, "umma_tf32: Cin=%d must be a multiple of %d", c.Cin, p.slabC);
   p.n_ka = (c.Cin + p.KA - 1) / p.KA;
@@ -361,8 +415,6 @@ int make_plan(const UmmaTf32& c, int n_sm, Plan* out) {
   p.a_bytes = p.a_half * (c.split3 ? 2u : 1u);
   p.b_half = (uint32_t)p.slabC * p.Nblk * 4u;
   p.b_bytes = p.b_half * (c.split3 ? 2u : 1u);
-  p.bp_half = (uint32_t)p.slabC * p.Npack * 4u;
-  p.bp_bytes = p.bp_half * (c.split3 ? 2u : 1u);
   p.NACC = 512 / p.Nblk;
   if (p.NACC > 8) p.NACC = 8;
   VS_REQUIRE(p.NACC >= 2, "umma_tf32: TMEM too small");
@@ -370,11 +422,15 @@ int make_plan(const UmmaTf32& c, int n_sm, Plan* out) {
   while (cols < p.NACC * p.Nblk) cols *= 2;
   p.tmem_cols = cols;
   p.off_b = kSA * p.a_bytes;
-  p.off_bar = (p.off_b + kSB * p.b_bytes + 127u) & ~127u;
-  p.smem_bytes = p.off_bar + 8u * 32 + 16u;
+  const uint32_t bar_bytes = 8u * (24 + 2 * kMaxSB) + 16u;
+  p.SB = (int)((220u * 1024 - p.off_b - bar_bytes) / p.b_bytes);
+  if (p.SB > kMaxSB) p.SB = kMaxSB;
+  VS_REQUIRE(p.SB >= 2, "umma_tf32: tile does not fit in shared memory");
+  p.off_bar = (p.off_b + p.SB * p.b_bytes + 127u) & ~127u;
+  p.smem_bytes = p.off_bar + bar_bytes;
   VS_REQUIRE(p.smem_bytes <= 227u * 1024, "umma_tf32: tile does not fit in shared memory");
   if (p.smem_bytes < 120u * 1024) p.smem_bytes = 120u * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
-  p.n_units = p.n_tiles * p.NB * p.NS;
+  p.n_units = p.n_tiles * p.NB;
   *out = p;
   return VS_OK;
 }
@@ -395,7 +451,8 @@ int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  VS_TRY(make_plan(c, n_sm, &prm.p));
+  VS_TRY(make_plan(c, &prm.p));
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   int grid = n_sm < prm.p.n_units ? n_sm : prm.p.n_units;
   umma_tf32_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
   VS_LAUNCH_CHECK();
