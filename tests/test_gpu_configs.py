@@ -91,3 +91,42 @@ def test_batch_invariance(net):
     finally:
         _lib.check(lib.vs_set_option(b"tf32_min_rows", 4096))
         _lib.check(lib.vs_set_option(b"x3_min_rows", 512))
+
+
+@pytest.mark.parametrize("chunk,first", [(128, None), (100, 24)])
+def test_c4_chunked_decoder_is_bit_identical(net, chunk, first):
+    """configs[3]: long-form utterance through the chunked decoder with receptive-field overlap.  The halo (16 frames)
+    covers the decoder's reach (+-12.33 frames), so the concatenated chunks must equal the one-shot
+    decode bit for bit; without the halo they must not (the check has teeth)."""
+    from oracle import inputs as oin
+    u = oin.c4()[0]
+    tf = oin.frame_counts([u])[0]
+    eps = oin.draw_noise([tf], 31)[0]
+    args = (u["ids"][None], torch.LongTensor([u["ids"].numel()]))
+    kw = dict(sid=torch.LongTensor([u["sid"]]), noise_scale=0.667, duration_control=u["duration"][None], noise=[eps])
+    o, *_ = net.infer(*args, outputs="audio", **kw)
+    got = torch.zeros_like(o[0, 0])
+    n_chunks, pos = 0, 0
+    for start, wave in net.infer_stream(*args, chunk_frames=chunk, first_chunk_frames=first, **kw):
+        assert start == pos
+        got[start:start + wave.numel()] = wave
+        pos += wave.numel()
+        n_chunks += 1
+    torch.cuda.synchronize()
+    assert pos == tf * 512 and n_chunks == (1 + -(-(tf - first) // chunk) if first else -(-tf // chunk))
+    assert torch.equal(got, o[0, 0])
+    bad = torch.cat([w for _, w in net.infer_stream(*args, chunk_frames=chunk, halo_frames=0, **kw)])
+    assert not torch.equal(bad, o[0, 0])
+
+
+def test_stream_respects_max_len_and_rejects_batches(net):
+    from oracle import inputs as oin
+    u = oin.c1()[0]
+    kw = dict(sid=torch.LongTensor([0]), noise_scale=0.667, duration_control=u["duration"][None])
+    eps = oin.draw_noise(oin.frame_counts([u]), 3)
+    o, *_ = net.infer(u["ids"][None], torch.LongTensor([40]), max_len=50, noise=eps, outputs="audio", **kw)
+    chunks = list(net.infer_stream(u["ids"][None], torch.LongTensor([40]), max_len=50, noise=eps, chunk_frames=32, **kw))
+    assert torch.equal(torch.cat([w for _, w in chunks]), o[0, 0]) and o.shape[-1] == 50 * 512
+    with pytest.raises(ValueError):
+        next(net.infer_stream(torch.stack([u["ids"]] * 2), torch.LongTensor([40, 40]), sid=torch.LongTensor([0, 1]),
+                              duration_control=torch.stack([u["duration"]] * 2)))

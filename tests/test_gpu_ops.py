@@ -191,10 +191,12 @@ def test_layernorm_rows(G):
         assert (out.cpu() - ref).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("kernel", [0, 2])
 @pytest.mark.parametrize("lengths", [[40], [3, 1, 70, 130], [431, 200]])
-def test_rel_attention_matches_oracle(G, lengths, state_dict):
+def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     """Banded relative attention (attentions.py:148-179) vs the oracle's restatement, several ragged lengths
-    including T < window+1 and T > one key tile.  fp32 tolerance 2e-5 on O(1) outputs."""
+    including T < window+1 and T > one key tile, for both kernels (0 = CUDA-core fp32, 2 = 3xTF32 tensor-core MMA,
+    which the model uses from 128 rows per utterance up).  fp32 tolerance 2e-5 on O(1) outputs."""
     from oracle.vispeech_oracle import DEFAULT_CONFIG, relative_attention
     from vispeech_b200 import _lib
     lib = _lib.load()
@@ -221,9 +223,13 @@ def test_rel_attention_matches_oracle(G, lengths, state_dict):
     d_qkv = torch.from_numpy(qkv_rows).to(G.DEV)
     d_ek = sd[p + ".emb_rel_k"][0].contiguous().to(G.DEV)
     d_ev = sd[p + ".emb_rel_v"][0].contiguous().to(G.DEV)
-    _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
-                                       out.data_ptr(), G.stream()))
-    torch.cuda.synchronize()
+    _lib.check(lib.vs_set_option(b"attention_mma", kernel))
+    try:
+        _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
+                                           out.data_ptr(), G.stream()))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.vs_set_option(b"attention_mma", 1))
     for b, ref in enumerate(refs):
         s = rows.starts[b]
         assert (out[s:s + lengths[b]].cpu() - ref).abs().max().item() <= 2e-5

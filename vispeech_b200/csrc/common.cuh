@@ -74,6 +74,9 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st);
 int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
                    const int32_t* row_utt, cudaStream_t st);
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
+// tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on g_attention_mma
+int rel_attention_mma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
+extern int g_attention_mma;                        // vs_set_option("attention_mma", 0..3), default 1 = auto
 int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,
             const int32_t* row_utt, cudaStream_t st);
 

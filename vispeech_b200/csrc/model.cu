@@ -255,6 +255,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_tf32_prior = value != 0;
     return VS_OK;
   }
+  if (std::string(name) == "attention_mma") {          // 0 CUDA-core fp32 kernel, 1 auto, 2 always 3xTF32 MMA, 3 plain-TF32 MMA (A/B)
+    vs::g_attention_mma = (int)value;
+    return VS_OK;
+  }
   if (std::string(name) == "fused_respair") {
     vs::umma_respair_enable((int)value);
     return VS_OK;

@@ -366,7 +366,11 @@ static size_t attention_smem_bytes() {
   return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * AT_SLD + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
 }
 
+int g_attention_mma = 1;
+
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st) {
+  // 1 = auto (tensor cores from 128 rows per utterance up), 2/3 = always MMA (3xTF32 / plain TF32), 0 = never
+  if (g_attention_mma >= 2 || (g_attention_mma == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
   static bool configured = false;
   const size_t smem = attention_smem_bytes();
   if (!configured) {

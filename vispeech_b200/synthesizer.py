@@ -234,6 +234,10 @@ class SynthesizerTrn:
             check(lib.vs_flow_reverse(self._model, ctypes.byref(rf.struct), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_flow_reverse")
             mark("flow")
+            if outputs == "latents":               # infer_stream: the decoder runs chunk by chunk on these rows
+                if timings is not None:
+                    timings["_events"] = ev
+                return z, rf
             wave = torch.empty(Rf * self.hop_length, dtype=torch.float32, device=dev)
             ml = P.max_len
             check(lib.vs_hifigan_decode(self._model, ctypes.byref(rf.struct), ptr(z), ml, ptr(wave),
@@ -297,6 +301,53 @@ class SynthesizerTrn:
                          duration_control, noise)
         return self.run(P, outputs)
 
+    # ------------------------------------------------------------------------------------------------
+    # Long-form path (BASELINE.json configs[3]): chunked decoder with receptive-field overlap
+    # ------------------------------------------------------------------------------------------------
+    DECODER_HALO_FRAMES = 16     # >= the decoder's reach of +-12.33 frames, kept a multiple of 8
+
+    @torch.no_grad()
+    def infer_stream(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None,
+                     energy_control: Control = None, pitch_control: Control = None, duration_control: Control = None,
+                     noise=None, chunk_frames: int = 128, first_chunk_frames: Optional[int] = None,
+                     halo_frames: Optional[int] = None):
+        """Generator over waveform chunks of ONE utterance (every reference call site is batch 1: inference.py:44,
+        inference_api.py:46): the latent path (text encoder ... flow, < 10 % of the work) runs once, then the HiFi-GAN
+        decoder (models.py:271-290) runs on windows of `chunk_frames` frames extended by `halo_frames` of context on
+        each side; the halo's samples are dropped.  The halo covers the decoder's whole receptive field, so the
+        concatenated chunks are BIT-IDENTICAL to `infer(...)[0]` (tests/test_gpu_configs.py) while the first audio is
+        available after one small decode instead of the whole utterance.
+        Yields (first_sample, wave) with wave a float32 device tensor [n_samples]; the consumer may copy chunk i to the
+        host while chunk i+1 is computed (each chunk owns its buffer)."""
+        P = self.prepare(phonemes, phonemes_lengths, sid, noise_scale, None, energy_control, pitch_control,
+                         duration_control, noise)
+        if P.B != 1:
+            raise ValueError("infer_stream synthesises one utterance per call (batch 1, like the reference call sites)")
+        halo = self.DECODER_HALO_FRAMES if halo_frames is None else int(halo_frames)
+        if chunk_frames < 1 or halo < 0:
+            raise ValueError("chunk_frames must be >= 1 and halo_frames >= 0")
+        z, rf = self.run(P, outputs="latents")
+        lib, dev, hop = self._lib, self.device, self.hop_length
+        tf = int(P.frames[0])
+        if max_len is not None:
+            tf = max(0, min(tf, int(max_len)))                       # models.py:720 truncates before the decoder
+        z0 = int(rf.starts[0])
+        s = 0
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            while s < tf:
+                n = chunk_frames if (s > 0 or first_chunk_frames is None) else int(first_chunk_frames)
+                e = min(tf, s + max(1, n))
+                lo, hi = max(0, s - halo), min(tf, e + halo)
+                rows = make_rows([hi - lo], P.sids, FRAME_GAP, dev)
+                zc = torch.zeros(rows.n_rows, 192, dtype=torch.float32, device=dev)
+                zc[: hi - lo] = z[z0 + lo: z0 + hi]
+                ws = self._workspace(P.rp.n_rows, max(rows.n_rows, rf.n_rows))
+                wave = torch.empty(rows.n_rows * hop, dtype=torch.float32, device=dev)
+                check(lib.vs_hifigan_decode(self._model, ctypes.byref(rows.struct), ptr(zc), -1, ptr(wave),
+                                            int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
+                yield s * hop, wave[(s - lo) * hop: (e - lo) * hop]
+                s = e
 
     # ------------------------------------------------------------------------------------------------
     # 8(f): voice_conversion (reference models.py:724-732)
