@@ -3,7 +3,10 @@
 // These serve the HBM/latency-bound part of the path (text encoder, predictors, frame prior, flow);
 // the decoder's dense contractions run on tcgen05 (umma_conv.cu).
 #include <stdarg.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vs {
 
@@ -24,7 +27,15 @@ const char* last_error() { return g_err; }
 // ------------------------------------------------------------------------------------------------
 constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
 
-__global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a) {
+// Split-K over a thread-block cluster: the latency path (batch 1, a few hundred rows at most) has 1-6 row tiles per
+// conv, so the K loop (up to 3 x 768 channels) is cut into `nchunk` slices, one CTA of a (1,1,nchunk) cluster each;
+// the partial tiles are summed in rank order through distributed shared memory by rank 0 (deterministic - no atomics),
+// which then runs the epilogue.  `nchunk` depends on the conv's shape only, and the un-clustered form (many row tiles)
+// accumulates the same chunks from zero and adds them in the same order, so a row's result is bit-identical whatever
+// else is in the batch (the serving queue and the batch-invariance tests rely on it).
+// The global loads of step i+1 are issued before the FMAs of step i.
+template <bool CLUSTER>
+__global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a, int nchunk) {
   __shared__ __align__(16) float As[CV_BK][CV_BM + 4];
   __shared__ __align__(16) float Bs[CV_BK][CV_BN];
   const int tid = threadIdx.x;
@@ -39,37 +50,42 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a) {
   const int am = tid / 4, akq = tid % 4;          // A loader: row am, channels 4*akq..+3
   const int bk = tid / 16, bn4 = tid % 16;        // B loader: k row bk, couts 4*bn4..+3
   const bool vec_b = (a.Cout % 4 == 0);
+  const int per_tap = a.Cin / CV_BK, n_it = a.k * per_tap;
+  const int c_first = CLUSTER ? (int)blockIdx.z : 0, c_last = CLUSTER ? (int)blockIdx.z + 1 : nchunk;
+  float tot[4][4];
 
-  for (int j = 0; j < a.k; ++j) {
-    const int shift = (j - a.pad_l) * a.dil;
-    const int ar = r0 + am + shift;
-    const bool a_ok = (ar >= 0 && ar < a.R);
-    const float* arow = a.in + (size_t)(a_ok ? ar : 0) * a.in_ld;
-    const float* wj = a.w + (size_t)j * a.Cin * a.Cout;
-    for (int ci0 = 0; ci0 < a.Cin; ci0 += CV_BK) {
-      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_ok) av = *reinterpret_cast<const float4*>(arow + ci0 + 4 * akq);
-      if (a.in_slope != 1.f) {
-        av.x = lrelu(av.x, a.in_slope); av.y = lrelu(av.y, a.in_slope);
-        av.z = lrelu(av.z, a.in_slope); av.w = lrelu(av.w, a.in_slope);
-      }
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      {
-        const float* wrow = wj + (size_t)(ci0 + bk) * a.Cout + c0 + 4 * bn4;
-        const int cc = c0 + 4 * bn4;
-        if (vec_b && cc + 3 < a.Cout) bv = *reinterpret_cast<const float4*>(wrow);
-        else {
-          if (cc + 0 < a.Cout) bv.x = wrow[0];
-          if (cc + 1 < a.Cout) bv.y = wrow[1];
-          if (cc + 2 < a.Cout) bv.z = wrow[2];
-          if (cc + 3 < a.Cout) bv.w = wrow[3];
-        }
-      }
+  auto load = [&](int it, float4& av, float4& bv) {
+    const int j = it / per_tap, ci0 = (it % per_tap) * CV_BK;
+    const int ar = r0 + am + (j - a.pad_l) * a.dil;
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ar >= 0 && ar < a.R) av = *reinterpret_cast<const float4*>(a.in + (size_t)ar * a.in_ld + ci0 + 4 * akq);
+    if (a.in_slope != 1.f) {
+      av.x = lrelu(av.x, a.in_slope); av.y = lrelu(av.y, a.in_slope);
+      av.z = lrelu(av.z, a.in_slope); av.w = lrelu(av.w, a.in_slope);
+    }
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* wrow = a.w + ((size_t)j * a.Cin + ci0 + bk) * a.Cout + c0 + 4 * bn4;
+    const int cc = c0 + 4 * bn4;
+    if (vec_b && cc + 3 < a.Cout) bv = *reinterpret_cast<const float4*>(wrow);
+    else {
+      if (cc + 0 < a.Cout) bv.x = wrow[0];
+      if (cc + 1 < a.Cout) bv.y = wrow[1];
+      if (cc + 2 < a.Cout) bv.z = wrow[2];
+      if (cc + 3 < a.Cout) bv.w = wrow[3];
+    }
+  };
+
+  for (int ch = c_first; ch < c_last; ++ch) {
+    const int it0 = (int)((long long)n_it * ch / nchunk), it1 = (int)((long long)n_it * (ch + 1) / nchunk);
+    float4 av, bv;
+    if (it0 < it1) load(it0, av, bv);
+    for (int it = it0; it < it1; ++it) {
       __syncthreads();
       As[4 * akq + 0][am] = av.x; As[4 * akq + 1][am] = av.y;
       As[4 * akq + 2][am] = av.z; As[4 * akq + 3][am] = av.w;
       *reinterpret_cast<float4*>(&Bs[bk][4 * bn4]) = bv;
       __syncthreads();
+      if (it + 1 < it1) load(it + 1, av, bv);
 #pragma unroll
       for (int kk = 0; kk < CV_BK; ++kk) {
         const float4 x = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
@@ -81,6 +97,45 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a) {
           for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(xa[i], ya[jj], acc[i][jj]);
       }
     }
+    if (!CLUSTER) {                                     // chunk sums are added in chunk order, like rank 0 does below
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          tot[i][jj] = (ch == 0) ? acc[i][jj] : tot[i][jj] + acc[i][jj];
+          acc[i][jj] = 0.f;
+        }
+    }
+  }
+  if (!CLUSTER) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = tot[i][jj];
+  }
+
+  if (CLUSTER) {
+    __shared__ __align__(16) float Ps[16 * 256];       // this CTA's partial tile, [i*4+jj][tid]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)blockIdx.z;
+    if (rank != 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) Ps[(i * 4 + jj) * 256 + tid] = acc[i][jj];
+    }
+    cluster.sync();
+    if (rank == 0) {
+      for (int r = 1; r < nchunk; ++r) {
+        const float* remote = cluster.map_shared_rank(Ps, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] += remote[(i * 4 + jj) * 256 + tid];
+      }
+    }
+    cluster.sync();                                     // remote tiles stay alive until rank 0 has read them
+    if (rank != 0) return;
   }
 
   const int R_out = a.R_out ? a.R_out : a.R;
@@ -118,7 +173,23 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st) {
   VS_REQUIRE(a.in_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0, "conv1d_f32: input not 16B aligned");
   VS_REQUIRE(a.R > 0 && a.Cout > 0, "conv1d_f32: empty problem");
   dim3 grid((a.R + CV_BM - 1) / CV_BM, (a.Cout + CV_BN - 1) / CV_BN);
-  conv1d_f32_kernel<<<grid, 256, 0, st>>>(a);
+  // K is always accumulated in `nchunk` slices (a function of the conv's shape only); the slices run on a cluster's CTAs
+  // when the tile grid alone would leave most SMs idle (latency path), else one after the other in one CTA
+  const int n_it = a.k * (a.Cin / CV_BK), tiles = (int)(grid.x * grid.y);
+  int nchunk = 1;
+  while (nchunk < 8 && n_it / (nchunk * 2) >= 4) nchunk *= 2;
+  if (nchunk == 1 || tiles * nchunk > 296) {
+    conv1d_f32_kernel<false><<<grid, 256, 0, st>>>(a, nchunk);
+  } else {
+    grid.z = nchunk;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = nchunk;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv1d_f32_kernel<true>, a, nchunk));
+  }
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
