@@ -28,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEC_FLOP_PER_FRAME = 815_300_608          # SURVEY.md App. C (2 * 407,650,304 MAC)
+# DRAM bytes (read + write) of one decoder pass over the default workload (64 utterances, 27,591 frames): sum of
+# dram__bytes_read.sum + dram__bytes_write.sum over the decoder's 64 launches, profiles/launches_r1_traffic.csv
+DEC_DRAM_BYTES_C2 = 73.68e9
 HOP, SR = 512, 44100
 
 
@@ -216,7 +219,11 @@ def main():
             stages[k] = stages.get(k, 0.0) + v / args.steps
     dec_ms = stages.get("decoder", float("nan"))
 
-    # ---------------- end-to-end arm: public API from pinned host tensors, waveforms copied back to pinned host memory
+    # ---------------- end-to-end arm: public API from pinned host tensors, waveforms copied back to pinned host memory.
+    # The engine runs in its throughput mode here (overlap_calls: the latent stages of call i+1 are enqueued on a second
+    # stream and overlap the decoder of call i; VS_OVERLAP=0 turns it off for A/B runs).  The device-resident arm above
+    # keeps the stages serialised on one stream so that the stage times and the roofline stay attributable.
+    net.overlap_calls = os.environ.get("VS_OVERLAP", "1") != "0"
     o, _, _, _, _, _ = net.infer(ids, lens, sid=sid, noise_scale=0.667, duration_control=dur, outputs="audio")
     host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for _ in range(2)]
     h2d = int(P.ids_rows.numel() * 4 + P.d_ctrl.numel() * 8 + 2 * (P.rp.n_rows + 3 * P.B) * 4 + P.rf.n_rows * 4)
@@ -273,6 +280,9 @@ def main():
                        "audio_s_per_step_all_gpus": audio_all, "parallelism": "utterance-sharded x%d, no collectives" % world,
                        "precision": "decoder: bf16 operands, fp32 accumulate (tcgen05 kind::f16); flow GEMMs: TF32; frame prior, projection, "
                                     "text encoder and predictors: 3xTF32 (error-compensated, tcgen05 kind::tf32); attention / layernorm: fp32",
+                       "pipelining": "value/roofline: stages serialised on one stream; e2e: public infer() in throughput mode "
+                                     "(latent stages of call i+1 overlap the decoder of call i on a second stream, waveform "
+                                     "D2H of call i overlaps call i+1)" if net.overlap_calls else "none",
                        "l2": "per-step activations (~%.1f GB) >> 126 MB L2; no explicit flush needed" % (
                            sum(frames) * 112 * 16384 * 2 / 1e9 / 16)},
             "p50_rtf": rtf[len(rtf) // 2],
@@ -282,7 +292,11 @@ def main():
             "stages_ms": {k: round(v, 3) for k, v in stages.items()},
             "roofline": {"bound": "tensor", "kernel": "umma_conv1d_kernel + umma_respair_kernel (the whole decoder: ~60 launches per step)",
                          "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s", "frac": dec_tflops / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": DEC_DRAM_BYTES_C2 if (args.batch == 64) else None,
+                         "traffic_note": "DRAM read+write bytes of one decoder pass (all 64 launches), ncu, "
+                                         "profiles/launches_r1_traffic.csv; the unfused algorithmic minimum is 0.07 GB "
+                                         "(z in, waveform out): the rest is the activation stream between the ~60 convs",
+                         "peak_source": peak_src,
                          "ms_per_step": stages["decoder"], "share_of_step": stages["decoder"] / ms_per_step},
             "clocks": clocks,
         }

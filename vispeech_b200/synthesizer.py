@@ -55,6 +55,12 @@ class SynthesizerTrn:
             check(self._lib.vs_model_create(ctypes.byref(self._cfg), ctypes.byref(self._model)), "vs_model_create")
         self._weights: Dict[str, torch.Tensor] = {}
         self._ws: Optional[torch.Tensor] = None
+        self._ws_lat: Optional[torch.Tensor] = None
+        self._lat_stream: Optional[torch.cuda.Stream] = None
+        # Cross-call software pipeline (throughput mode): the latent stages (text encoder ... flow, small / latency-bound
+        # kernels) of call i+1 run on a second stream while the decoder of call i owns the SMs.  Same kernels, same
+        # results; only the enqueue order across calls changes.  Off by default (lowest single-call latency).
+        self.overlap_calls = False
         self._loaded = False
 
     # -- nn.Module-ish surface used by the reference scripts
@@ -94,6 +100,14 @@ class SynthesizerTrn:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def _workspace_lat(self, rp: int, rf: int) -> torch.Tensor:
+        need = int(self._lib.vs_workspace_bytes(self._model, rp, rf))
+        if self._ws_lat is None or self._ws_lat.numel() < need:
+            torch.cuda.synchronize(self.device)          # an older, smaller buffer may still be in use on the side stream
+            self._ws_lat = None
+            self._ws_lat = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws_lat
 
     @staticmethod
     def _per_utt(c: torch.Tensor, B: int, lengths: np.ndarray, name: str) -> List[np.ndarray]:
@@ -139,7 +153,10 @@ class SynthesizerTrn:
         P.B, P.Tp, P.lens, P.sids = B, Tp, lens, sids
         P.noise_scale, P.max_len = float(noise_scale), (-1 if max_len is None else int(max_len))
         P.duration_control = duration_control
-        with torch.cuda.device(dev):
+        # uploads go to the stream that consumes them first (the side stream under overlap_calls: they must not queue
+        # behind the previous call's decoder)
+        up = self._side_stream() if self.overlap_calls else torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev), torch.cuda.stream(up):
             P.rp = make_rows(lens, sids, PHONEME_GAP, dev)
             P.ids_rows = _upload(P.rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1), dev)
 
@@ -179,26 +196,32 @@ class SynthesizerTrn:
 
     @torch.no_grad()
     def run(self, P: "Prepared", outputs: str = "all", timings: Optional[dict] = None):
-        """Device side of `infer`: kernels only (plus one small D2H of frame counts when durations are predicted)."""
+        """Device side of `infer`: kernels only (plus one small D2H of frame counts when durations are predicted).
+        With `overlap_calls` the latent stages are enqueued on the side stream (see __init__); the decoder and the
+        outputs stay on the caller's stream, which waits for the latents through an event."""
         lib, dev = self._lib, self.device
         B, Tp, rp = P.B, P.Tp, P.rp
         Rp = rp.n_rows
         ev = []
+        main = torch.cuda.current_stream(dev)
+        overlap = bool(self.overlap_calls)
+        lat = self._side_stream() if overlap else main
 
-        def mark(name):
+        def mark(name, st):
             if timings is not None:
                 e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream(dev))
+                e.record(st)
                 ev.append((name, e))
 
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            ws = self._workspace(Rp, P.rf.n_rows if P.rf is not None else 16)
-            mark("start")
+        with torch.cuda.device(dev), torch.cuda.stream(lat):
+            stream = lat.cuda_stream
+            rf_rows = P.rf.n_rows if P.rf is not None else 16
+            ws = self._workspace_lat(Rp, rf_rows) if overlap else self._workspace(Rp, rf_rows)
+            mark("start", lat)
             x = torch.empty(Rp, 192, dtype=torch.float32, device=dev)
             check(lib.vs_text_encode(self._model, ctypes.byref(rp.struct), ptr(P.ids_rows), ptr(x), ptr(ws), ws.numel(),
                                      stream), "vs_text_encode")
-            mark("text_encoder")
+            mark("text_encoder", lat)
             dur = torch.empty(Rp, dtype=torch.float64, device=dev)
             f0 = torch.empty(Rp, dtype=torch.float32, device=dev)
             energy = torch.empty(Rp, dtype=torch.float32, device=dev)
@@ -206,7 +229,7 @@ class SynthesizerTrn:
                                           P.p_mode, P.p_scale, ptr(P.p_ctrl), P.e_mode, P.e_scale, ptr(P.e_ctrl),
                                           ptr(dur), ptr(f0), ptr(energy), ptr(ws), ws.numel(), stream),
                   "vs_variance_adapter")
-            mark("variance_adapter")
+            mark("variance_adapter", lat)
             cum = torch.empty(Rp, dtype=torch.int32, device=dev)
             frames_d = torch.empty(B, dtype=torch.int32, device=dev)
             check(lib.vs_length_regulate_count(ctypes.byref(rp.struct), ptr(dur), ptr(cum), ptr(frames_d), stream),
@@ -214,14 +237,14 @@ class SynthesizerTrn:
             if P.rf is None:
                 P.frames = frames_d.cpu().numpy()        # predicted durations: the one host sync of the path
                 self._layout_frames(P)
-                ws = self._workspace(Rp, P.rf.n_rows)
+                ws = self._workspace_lat(Rp, P.rf.n_rows) if overlap else self._workspace(Rp, P.rf.n_rows)
             rf, frames = P.rf, P.frames
             Rf, Tf = rf.n_rows, int(frames.max())
             x_f = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             lr_index = torch.empty(Rf, dtype=torch.int32, device=dev)
             check(lib.vs_length_regulate_gather(ctypes.byref(rp.struct), ctypes.byref(rf.struct), ptr(x), ptr(cum),
                                                 ptr(x_f), ptr(lr_index), stream), "vs_length_regulate_gather")
-            mark("length_regulator")
+            mark("length_regulator", lat)
             eps = P.eps if P.eps is not None else torch.randn(Rf, 192, dtype=torch.float32, device=dev)  # models.py:718
             m_p = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             logs_p = torch.empty_like(m_p)
@@ -229,20 +252,33 @@ class SynthesizerTrn:
             check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(eps), P.noise_scale,
                                      ptr(x_f), ptr(m_p), ptr(logs_p), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_frame_prior")
-            mark("frame_prior")
+            mark("frame_prior", lat)
             z_p = z.clone() if outputs == "all" else None
             check(lib.vs_flow_reverse(self._model, ctypes.byref(rf.struct), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_flow_reverse")
-            mark("flow")
-            if outputs == "latents":               # infer_stream: the decoder runs chunk by chunk on these rows
-                if timings is not None:
-                    timings["_events"] = ev
-                return z, rf
+            mark("flow", lat)
+        if overlap:
+            done = torch.cuda.Event()
+            done.record(lat)
+            main.wait_event(done)
+            for t in (z, z_p, m_p, logs_p, dur, f0, energy, lr_index, rf.row_utt, rp.row_utt):
+                if t is not None:
+                    t.record_stream(main)      # allocated on the side stream, read by the decoder / unpack kernels on `main`
+        if outputs == "latents":               # infer_stream: the decoder runs chunk by chunk on these rows
+            if timings is not None:
+                timings["_events"] = ev
+            return z, rf
+
+        with torch.cuda.device(dev):
+            stream = main.cuda_stream
+            ws = self._workspace(Rp, Rf)
+            if overlap:
+                mark("decoder_start", main)
             wave = torch.empty(Rf * self.hop_length, dtype=torch.float32, device=dev)
             ml = P.max_len
             check(lib.vs_hifigan_decode(self._model, ctypes.byref(rf.struct), ptr(z), ml, ptr(wave),
                                         int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
-            mark("decoder")
+            mark("decoder", main)
 
             def unpack(src, C, mul, t_max):
                 out = torch.empty(B, C, t_max, dtype=torch.float32, device=dev)
@@ -255,15 +291,15 @@ class SynthesizerTrn:
                 o = torch.zeros(B, 1, 0, dtype=torch.float32, device=dev)
             else:
                 o = unpack(wave, 1, self.hop_length, t_dec * self.hop_length)
-            mark("unpack")
+            mark("unpack", main)
             self.last_rows = (rp, rf)
             self.last_lr_index = lr_index
             if timings is not None:
                 timings["_events"] = ev
-            x_mask = (torch.arange(Tf, device=dev)[None, :] < torch.from_numpy(frames).to(dev)[:, None])[:, None, :]
+            x_mask = (torch.arange(Tf, device=dev)[None, :] < P.frames_dev()[:, None])[:, None, :]
             if outputs != "all":
                 return o, x_mask, None, None, None, None
-            lat = tuple(unpack(t, 192, 1, Tf) for t in (z, z_p, m_p, logs_p))
+            lat_out = tuple(unpack(t, 192, 1, Tf) for t in (z, z_p, m_p, logs_p))
             lens = P.lens
 
             def phon_out(t):                       # ragged [Rp] -> [B,Tp] (zero at pads)
@@ -278,7 +314,12 @@ class SynthesizerTrn:
                 duration = P.duration_control                     # returned verbatim (models.py:682, Q7)
             else:
                 duration = phon_out(dur).to(torch.float32)[:, None, :]
-            return o, x_mask, lat, duration, phon_out(f0), phon_out(energy)
+            return o, x_mask, lat_out, duration, phon_out(f0), phon_out(energy)
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._lat_stream is None:
+            self._lat_stream = torch.cuda.Stream(device=self.device)
+        return self._lat_stream
 
     @staticmethod
     def resolve_timings(timings: dict) -> Dict[str, float]:
@@ -286,6 +327,8 @@ class SynthesizerTrn:
         ev = timings.pop("_events")
         out = {}
         for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
+            if name == "decoder_start":            # overlap_calls: the hand-over between the two streams is not a stage
+                continue
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 
@@ -412,6 +455,9 @@ class SynthesizerTrn:
 
 class Prepared:
     """Device-resident inputs + row layouts of one `infer` call (see SynthesizerTrn.prepare)."""
+
+    def frames_dev(self) -> torch.Tensor:
+        return self.rf.utt_len                      # int32 [B] on the device: the frame counts of the row layout
 
 
 def _upload(a: np.ndarray, dev) -> torch.Tensor:
