@@ -130,3 +130,34 @@ def test_stream_respects_max_len_and_rejects_batches(net):
     with pytest.raises(ValueError):
         next(net.infer_stream(torch.stack([u["ids"]] * 2), torch.LongTensor([40, 40]), sid=torch.LongTensor([0, 1]),
                               duration_control=torch.stack([u["duration"]] * 2)))
+
+
+def test_overlap_calls_matches_serial(state_dict):
+    """Throughput mode (latent stages of call i+1 on a second stream under the decoder of call i) must return exactly
+    what serialised calls return, call after call, with buffers recycled between calls and predicted durations (host
+    sync inside the side stream) in the mix."""
+    from oracle import inputs as oin
+    from vispeech_b200 import build_from_hparams, get_hparams_from_file
+    net2 = build_from_hparams(get_hparams_from_file(), device="cuda:0")
+    net2.load_state_dict(state_dict)
+    batches = []
+    for seed in range(4):
+        utts = oin.c2(batch=5 + seed, seed=20 + seed)
+        frames = oin.frame_counts(utts)
+        ids = torch.stack([u["ids"] for u in utts])
+        dur = torch.stack([u["duration"] for u in utts])
+        sid = torch.LongTensor([u["sid"] for u in utts])
+        kw = dict(sid=sid, noise_scale=0.667, noise=oin.draw_noise(frames, 40 + seed), outputs="audio")
+        if seed != 2:
+            kw["duration_control"] = dur
+        else:                                   # predicted durations: frame counts are not known here, so no eps
+            kw.update(noise=None, noise_scale=0.0)
+        batches.append(((ids, torch.LongTensor([40] * len(utts))), kw))
+    results = {}
+    for mode in (False, True):
+        net2.overlap_calls = mode
+        outs = [net2.infer(*a, **kw)[0] for a, kw in batches for _ in range(2)]     # back to back, no sync in between
+        torch.cuda.synchronize()
+        results[mode] = [o.clone() for o in outs]
+    for a, b in zip(results[False], results[True]):
+        assert a.shape == b.shape and torch.equal(a, b)
