@@ -11,7 +11,7 @@
 //
 // One CTA = 64 queries of one (utterance, head), 4 warps x 16 query rows, two CTAs per SM.  Key/value tiles of 32 rows
 // arrive through a cp.async double buffer as raw fp32 and are split hi/lo when a fragment is read.
-// Measured (tools/attention_timing.py, 64 x 431 frames, 2 heads): 0.347 ms vs 0.446 ms for the CUDA-core kernel; the legacy
+// Measured (tools/attention_timing.py, 64 x 431 frames, 2 heads): 0.319 ms vs 0.446 ms for the CUDA-core kernel; the legacy
 // HMMA.1688.TF32 path issues one MMA per ~13 clk per SM sub-partition on sm_100a, so the three-term form is MMA-bound at
 // ~0.16 ms and plain TF32 (0.237 ms, error 6e-4) is not accurate enough for the prior.  Short sequences (phoneme level)
 // stay on the CUDA-core kernel, which is faster below ~128 rows.  Fragment <-> memory maps (g = lane/4, t = lane%4):
@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
+  lo = __float_as_uint(x - __uint_as_float(hi));     // exact difference; the MMA reads its top 19 bits (error 2^-21 |x|)
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
