@@ -95,7 +95,10 @@ def run_pair(name, R, C, k, d, count=1):
     print("%-22s R=%9d C=%3d k=%2d d=%d  %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s" % (name, R, C, k, d, ms, flop / ms / 1e9, byts / ms / 1e6))
 
 
-if os.environ.get("QUICK"):
+if os.environ.get("QUICK") == "k11":
+    for d in (1, 3, 5):
+        run_pair("s2 pair k11 d%d" % d, FRAMES * 256, 64, 11, d)
+elif os.environ.get("QUICK"):
     run_pair("s3 pair k3 d1", FRAMES * 512, 32, 3, 1)
     run_pair("s3 pair k11 d1", FRAMES * 512, 32, 11, 1)
     run_pair("s2 pair k3 d1", FRAMES * 256, 64, 3, 1)
@@ -104,6 +107,6 @@ elif os.environ.get("PAIRS", "1") == "1":
     for k in (3, 7, 11):
         for d in (1, 3, 5):
             run_pair("s3 pair k%d d%d" % (k, d), FRAMES * 512, 32, k, d)
-    for k in (3, 7):
+    for k in (3, 7, 11):
         for d in (1, 3, 5):
             run_pair("s2 pair k%d d%d" % (k, d), FRAMES * 256, 64, k, d)

@@ -45,6 +45,7 @@ constexpr int kMaxSX = 4;         // input ring depth (>= 3 keeps load(i+2), con
 
 struct Plan {
   int L, h1, h2, planes, rows_x, rows_a2, n_tiles, tmem_cols, ctas_per_sm, row_div_shift, SX;
+  int tight;              // 1: one input stage + one A2 buffer, residual re-read from HBM/L2 (C = 64, k = 11: 2 x 90 KB of weights)
   uint32_t xa_bytes, a2_bytes, w_bytes, smem_bytes;
   uint32_t off_a2, off_w1, off_w2, off_bar;
 };
@@ -66,7 +67,12 @@ struct Params {
 #define VS_TIMED(var, stmt) stmt
 #endif
 
-template <int N, int MODE>
+// TIGHT (C = 64, k = 11): both weight sets take 180 KB, so there is room for ONE input stage and ONE A2 buffer only.
+//   * the residual is re-read from global memory (L2) in epilogue 2, so the input stage is free again as soon as conv1 has
+//     consumed it and the load of tile i+1 overlaps conv2(i-1);
+//   * epilogue 1 of tile i waits for conv2(i-1) (observing acc2_full) before it overwrites A2; the MMA order
+//     conv1(i+1), conv2(i) hides that wait behind conv1(i+1).
+template <int N, int MODE, bool TIGHT = false>
 __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
   constexpr int EW = N / 8, kThreads = threads_for(N);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < p.SX; ++i) { mbar_init(xa_full(i), 1); mbar_init(xa_empty(i), 1 + EW); }   // conv1 commit + epilogue 2 warps
+    for (int i = 0; i < p.SX; ++i) { mbar_init(xa_full(i), 1); mbar_init(xa_empty(i), TIGHT ? 1 : 1 + EW); }   // conv1 commit (+ epilogue 2 warps)
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc1_full(i), 1); mbar_init(acc1_empty(i), EW);
       mbar_init(a2_full(i), EW);
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
   }
   // rows [128, 128 + 2*h2) of both A2 buffers are read by the last taps of conv2 (those outputs are discarded): keep
   // them finite
-  for (int i = threadIdx.x; i < 2 * p.planes * 2 * p.h2; i += kThreads) {
+  for (int i = threadIdx.x; i < (TIGHT ? 1 : 2) * p.planes * 2 * p.h2; i += kThreads) {
     const int bsel = i / (p.planes * 2 * p.h2), r = i % (p.planes * 2 * p.h2);
     const int pl = r / (2 * p.h2), j = r % (2 * p.h2);
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2 + bsel * p.a2_bytes + (uint32_t)(pl * p.rows_a2 + 128 + j) * 16u),
@@ -180,8 +186,8 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
         VS_TIMED(tw2, mbar_wait(acc2_empty(b), ph ^ 1u, 25));
       }
       tc_fence_after();
-      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((a2 + b * p.a2_bytes) >> 4), a2_hi, w2_lo, b_hi, idesc, taps, 1u,
-                     a2_kstep, b_kstep);
+      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((a2 + (TIGHT ? 0u : b) * p.a2_bytes) >> 4), a2_hi, w2_lo, b_hi, idesc,
+                     taps, 1u, a2_kstep, b_kstep);
       tc_commit(acc2_full(b));
     };
     uint32_t slot = 0, phase = 0, i = 0;
@@ -219,10 +225,14 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       if (valid && c.row_utt) valid = c.row_utt[g >> p.row_div_shift] >= 0;
       const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
       VS_TIMED(tw0, mbar_wait(acc1_full(b), ph, 27));
+      if (TIGHT && i > 0) {                             // the single A2 buffer is still conv2(i-1)'s operand until it commits
+        const uint32_t jb = (i - 1u) & 1u, jph = ((i - 1u) >> 1) & 1u;
+        VS_TIMED(tw1, mbar_wait(acc2_full(jb), jph, 30));
+      }
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(t_lane + b * N, v);
-      const uint32_t a2_row = a2_lane + b * p.a2_bytes;
+      const uint32_t a2_row = a2_lane + (TIGHT ? 0u : b) * p.a2_bytes;
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
@@ -275,14 +285,23 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) rv2[gq] = *reinterpret_cast<const uint4*>(c.res2 + row_off + (size_t)gq * plane_elems);
       }
+      uint4 xv[4];
+      if (TIGHT) {                                      // the input stage is long gone: fetch the residual rows again (L2)
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          xv[gq] = make_uint4(0u, 0u, 0u, 0u);
+          if (in_tile) xv[gq] = *reinterpret_cast<const uint4*>(c.x + row_off + (size_t)gq * plane_elems);
+        }
+      }
       VS_TIMED(tw0, mbar_wait(acc2_full(b), ph, 29));
       tc_fence_after();
-      uint4 xv[4];                                      // the residual rows: XA(i) has landed once conv2(i) has completed
+      if (!TIGHT) {                                     // the residual rows: XA(i) has landed once conv2(i) has completed
 #pragma unroll
-      for (int gq = 0; gq < 4; ++gq)
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(xv[gq].x), "=r"(xv[gq].y), "=r"(xv[gq].z), "=r"(xv[gq].w)
-                     : "r"(xa_lane + slot * p.xa_bytes + (uint32_t)gq * xa_plane));
+        for (int gq = 0; gq < 4; ++gq)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(xv[gq].x), "=r"(xv[gq].y), "=r"(xv[gq].z), "=r"(xv[gq].w)
+                       : "r"(xa_lane + slot * p.xa_bytes + (uint32_t)gq * xa_plane));
+      }
       uint32_t v[32];
       tmem_ld32(t_lane + b * N, v);
       auto chunk = [&](auto cc_tag) {
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       else chunk(std::integral_constant<int, 1>{});
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(acc2_empty(b)); mbar_arrive(xa_empty(slot)); }
+      if (lane == 0) { mbar_arrive(acc2_empty(b)); if (!TIGHT) mbar_arrive(xa_empty(slot)); }
       if (++slot == SX) slot = 0;
     }
   }
@@ -377,9 +396,10 @@ int make_plan(const UmmaPair& c, Plan* out) {
   if (fixed + 3 * p.xa_bytes <= half_sm) { per_sm = 2; p.SX = (fixed + 4 * p.xa_bytes <= half_sm) ? 4 : 3; }
   else if (fixed + 3 * p.xa_bytes <= full_sm) { p.SX = (fixed + 4 * p.xa_bytes <= full_sm) ? 4 : 3; }
   else if (fixed + 2 * p.xa_bytes <= full_sm) p.SX = 2;
+  else if (c.C == 64 && fixed - p.a2_bytes + p.xa_bytes <= 227u * 1024 - 512u) { p.SX = 1; p.tight = 1; }
   VS_REQUIRE(p.SX > 0, "umma_respair: C=%d k=%d d=%d does not fit in shared memory", c.C, c.taps, c.dil);
   p.off_a2 = p.SX * p.xa_bytes;
-  p.off_w1 = p.off_a2 + 2 * p.a2_bytes;
+  p.off_w1 = p.off_a2 + (p.tight ? 1 : 2) * p.a2_bytes;
   p.off_w2 = p.off_w1 + p.w_bytes;
   p.off_bar = (p.off_w2 + p.w_bytes + 127u) & ~127u;
   p.smem_bytes = p.off_bar + bar_bytes;
@@ -436,7 +456,7 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
   else if (c.out_raw && !c.out_act && c.res2) mode = M_RAW_RES2;
   else if (c.out_act && !c.out_raw && c.res2 && scale) mode = M_ACT_RES2_SCALE;
 #define VS_PAIR_CASE(NN, MM)                                                                                          \
-  if (c.C == NN && mode == MM) {                                                                                      \
+  if (c.C == NN && mode == MM && !(NN == 64 && prm.p.tight)) {                                                        \
     static bool cfg = false;                                                                                          \
     if (!cfg) {                                                                                                       \
       VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
@@ -444,9 +464,21 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
     }                                                                                                                 \
     umma_respair_kernel<NN, MM><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                \
   }
+#define VS_PAIR_TIGHT(MM)                                                                                             \
+  if (c.C == 64 && mode == MM && prm.p.tight) {                                                                       \
+    static bool cfg = false;                                                                                          \
+    if (!cfg) {                                                                                                       \
+      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<64, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      cfg = true;                                                                                                     \
+    }                                                                                                                 \
+    umma_respair_kernel<64, MM, true><<<grid, threads_for(64), prm.p.smem_bytes, st>>>(prm);                          \
+  }
   VS_PAIR_CASE(32, M_ACT) else VS_PAIR_CASE(32, M_RAW) else VS_PAIR_CASE(32, M_RAW_RES2) else VS_PAIR_CASE(32, M_ACT_RES2_SCALE)
   else VS_PAIR_CASE(32, M_GENERIC) else VS_PAIR_CASE(64, M_ACT) else VS_PAIR_CASE(64, M_RAW) else VS_PAIR_CASE(64, M_RAW_RES2)
   else VS_PAIR_CASE(64, M_ACT_RES2_SCALE) else VS_PAIR_CASE(64, M_GENERIC)
+  else VS_PAIR_TIGHT(M_ACT) else VS_PAIR_TIGHT(M_RAW) else VS_PAIR_TIGHT(M_RAW_RES2) else VS_PAIR_TIGHT(M_ACT_RES2_SCALE)
+  else VS_PAIR_TIGHT(M_GENERIC)
+#undef VS_PAIR_TIGHT
 #undef VS_PAIR_CASE
   VS_LAUNCH_CHECK();
   return VS_OK;
