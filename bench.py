@@ -168,6 +168,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("VS_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its banner to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from oracle import inputs as oin                      # synthetic workload generator + CPU baseline only
