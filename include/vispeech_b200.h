@@ -152,6 +152,16 @@ int vs_unpack_rows(const VsRows* rows, const float* x /*[n_rows*rows_mul][C]*/, 
 int vs_wave_pcm16(const float* wave, int32_t n_utt, int32_t t_max, const int32_t* n_samples, int32_t decimate,
                   const float* fir /*[n_taps] or NULL*/, int32_t n_taps, int16_t* out, int32_t t_out, void* stream);
 
+/* ---- 8(f): linear / log-mel spectrogram of waveforms (reference mel_processing.py:50-112: spectrogram_torch feeds
+ * voice_conversion, mel_spectrogram_torch is the evaluation metric of train.py:303-313).  n_fft = win = 4 * hop, hann,
+ * center = False after a reflect pad of (n_fft - hop) / 2.  rows: one entry per utterance with n_frames[b] + 3 rows
+ * (frame j = rows j..j+3); wave [n_utt][t_max] fp32, n_samples[b] valid samples (>= (n_fft - hop) / 2 + 1).
+ * dft_packed / mel_packed: the windowed DFT basis and the mel filterbank as 3xTF32 slabs (vispeech_b200/mel.py).
+ * spec_out [n_utt][n_bins][frames_max] and/or mel_out [n_utt][n_mels][frames_max] (either may be NULL). */
+int vs_mel_spectrogram(const VsRows* rows, const float* wave, int32_t t_max, const int32_t* n_samples, int32_t hop,
+                       int32_t n_bins, int32_t n_mels, const float* dft_packed, const float* mel_packed, int32_t frames_max,
+                       float* spec_out, float* mel_out, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- op-level entry points (used by the parity tests; same kernels as above) */
 int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w /*[k][Cin][Cout]*/, const float* bias,
                      float* out, int32_t out_ld, int32_t n_rows, int32_t c_in, int32_t c_out, int32_t k, int32_t dil,

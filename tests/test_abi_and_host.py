@@ -100,3 +100,37 @@ def test_polyphase_equals_conv_transpose(state_dict):
                     if 0 <= q + d < 11:
                         out[:, s * q + ph] += per[ph, t].t() @ x[0, :, q + d]
         assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_mel_filterbank_matches_torchaudio_slaney():
+    """vispeech_b200.mel.mel_filterbank restates librosa.filters.mel (what mel_processing.py:78 calls); torchaudio's
+    Slaney-scale / Slaney-norm filterbank is the same definition and is the independent check available here."""
+    import torchaudio
+    from vispeech_b200.mel import mel_filterbank
+    for sr, n_fft, n_mels, fmin, fmax in [(44100, 2048, 80, 0.0, None), (22050, 1024, 80, 0.0, 8000.0), (44100, 2048, 64, 50.0, 16000.0)]:
+        ours = torch.from_numpy(mel_filterbank(sr, n_fft, n_mels, fmin, fmax))
+        ref = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, fmin, float(fmax or sr / 2), n_mels, sr, norm="slaney",
+                                                    mel_scale="slaney").t()
+        assert ours.shape == ref.shape and float((ours - ref).abs().max()) <= 1e-5 * float(ref.abs().max())   # fp32 rounding of two float64 recipes
+
+
+def test_dft_basis_reproduces_torch_stft():
+    """The 4-tap conv with the windowed DFT basis over hop-sized rows (what the GPU GEMM computes) equals torch.stft with
+    the reference's padding (mel_processing.py:64-68), in float64 on the CPU."""
+    from vispeech_b200.mel import dft_basis
+    n_fft, hop = 2048, 512
+    w, half = dft_basis(n_fft, hop)
+    g = torch.Generator().manual_seed(0)
+    y = torch.randn(1, 5 * hop + 77, generator=g, dtype=torch.float64)
+    pad = (n_fft - hop) // 2
+    yp = torch.nn.functional.pad(y.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    ref = torch.stft(yp, n_fft, hop_length=hop, win_length=n_fft, window=torch.hann_window(n_fft, dtype=torch.float64),
+                     center=False, return_complex=True)[0]                                    # [1025, frames]
+    n_frames = y.shape[1] // hop
+    assert ref.shape[1] == n_frames
+    rows = torch.zeros(n_frames + 3, w.shape[1], dtype=torch.float64)
+    flat = yp[0, : (n_frames + 3) * hop]
+    rows[: flat.numel() // hop, :hop] = flat[: flat.numel() // hop * hop].reshape(-1, hop)
+    out = sum(rows[t: t + n_frames] @ w[t].double() for t in range(4))                       # [frames, 2 * half]
+    re, im = out[:, :1025].t(), out[:, half:half + 1025].t()
+    assert float((re - ref.real).abs().max()) <= 1e-4 and float((im - ref.imag).abs().max()) <= 1e-4

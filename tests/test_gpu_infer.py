@@ -339,3 +339,43 @@ def test_unfused_resblock_paths_still_match(net, mode):
         _lib.check(lib.vs_set_option(b"fused_respair", 2))
     ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
     assert snr_db(ref, o[0, 0].cpu()) >= 30.0
+
+
+def test_gpu_mel_and_spectrogram_match_reference_definition(net):
+    """8(f) rank 4: spectrogram_torch / mel_spectrogram_torch (mel_processing.py:50-112) as 3xTF32 tensor-core GEMMs vs
+    the oracle's torch.stft statement: linear magnitudes within 2e-4 relative to the spectrum's peak, log-mel within 2e-3,
+    for a ragged batch (lengths that are not multiples of the hop) and for a synthesised waveform."""
+    from oracle.metrics import mel_spectrogram
+    from vispeech_b200.mel import MelSpectrogram, mel_spectrogram_torch, spectrogram_torch
+    g = torch.Generator().manual_seed(11)
+    lens = [44100, 30001, 5 * 512 + 77, 1024]
+    y = torch.zeros(len(lens), max(lens))
+    for b, n in enumerate(lens):
+        t = torch.arange(n) / 44100.0
+        y[b, :n] = 0.3 * torch.sin(2 * np.pi * (200.0 + 900.0 * b) * t) + 0.05 * torch.randn(n, generator=g)
+    ms = MelSpectrogram(device="cuda:0")
+    spec, mel = ms(y.cuda(), lengths=lens, want="both")
+    torch.cuda.synchronize()
+    assert spec.shape == (4, 1025, max(lens) // 512) and mel.shape == (4, 80, max(lens) // 512)
+    pad = (2048 - 512) // 2
+    for b, n in enumerate(lens):
+        nf = n // 512
+        ref_mel = mel_spectrogram(y[b, :n])
+        yp = torch.nn.functional.pad(y[b, :n][None, None], (pad, pad), mode="reflect")[0]
+        st = torch.stft(yp, 2048, hop_length=512, win_length=2048, window=torch.hann_window(2048), center=False,
+                        return_complex=True)[0]
+        ref_spec = torch.sqrt(st.real ** 2 + st.imag ** 2 + 1e-6)
+        assert ref_mel.shape[1] == nf
+        assert float((spec[b, :, :nf].cpu() - ref_spec).abs().max()) <= 2e-4 * float(ref_spec.max())
+        assert float((mel[b, :, :nf].cpu() - ref_mel).abs().max()) <= 2e-3
+        assert float(spec[b, :, nf:].abs().max() if nf < spec.shape[2] else 0.0) == 0.0
+    # the reference-named wrappers on a synthesised waveform
+    from oracle import inputs as oin
+    u = oin.c1()[0]
+    o, *_ = net.infer(u["ids"][None], torch.LongTensor([40]), sid=torch.LongTensor([0]), noise_scale=0.667,
+                      duration_control=u["duration"][None], noise=oin.draw_noise(oin.frame_counts([u]), 3), outputs="audio")
+    m = mel_spectrogram_torch(o[:, 0], 2048, 80, 44100, 512, 2048, 0, None)
+    s = spectrogram_torch(o[:, 0], 2048, 44100, 512, 2048)
+    ref = mel_spectrogram(o[0, 0].cpu())
+    assert m.shape[1:] == ref.shape and s.shape[1] == 1025
+    assert float((m[0].cpu() - ref).abs().max()) <= 2e-3

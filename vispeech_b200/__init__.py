@@ -5,4 +5,7 @@ Host side: `SynthesizerTrn` (reference call surface) -> ctypes -> libvispeech_b2
 from .config import HParams, build_from_hparams, get_hparams_from_file  # noqa: F401
 from .synthesizer import SynthesizerTrn, load_checkpoint  # noqa: F401
 
-__all__ = ["SynthesizerTrn", "load_checkpoint", "get_hparams_from_file", "HParams", "build_from_hparams"]
+from .mel import MelSpectrogram, mel_spectrogram_torch, spectrogram_torch  # noqa: F401
+
+__all__ = ["SynthesizerTrn", "load_checkpoint", "get_hparams_from_file", "HParams", "build_from_hparams",
+           "MelSpectrogram", "mel_spectrogram_torch", "spectrogram_torch"]

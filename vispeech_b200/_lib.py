@@ -51,6 +51,8 @@ _SIGNATURES = {
     "vs_hifigan_decode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64,
                                     c_void_p]),
     "vs_wave_pcm16": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
+    "vs_mel_spectrogram": (c_int32, [POINTER(VsRows), c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                     c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_unpack_rows": (c_int32, [POINTER(VsRows), c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "vs_op_conv1d_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                    c_int32, c_int32, c_int32, c_float, c_int32, c_void_p, c_int32, c_void_p]),

@@ -571,6 +571,44 @@ int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, con
   return umma_tf32(u, static_cast<cudaStream_t>(stream));
 }
 
+// 8(f) rank 4: spectrogram_torch / mel_spectrogram_torch (reference mel_processing.py:50-112) as frame rows -> 3xTF32 DFT
+// GEMM (tcgen05) -> magnitude -> 3xTF32 mel GEMM -> log.  rows: n_frames[b] + 3 rows per utterance (vispeech_b200/mel.py).
+int vs_mel_spectrogram(const VsRows* rows, const float* wave, int32_t t_max, const int32_t* n_samples, int32_t hop,
+                       int32_t n_bins, int32_t n_mels, const float* dft_packed, const float* mel_packed, int32_t frames_max,
+                       float* spec_out, float* mel_out, void* ws, int64_t ws_bytes, void* stream) {
+  VS_TRY(check_rows(rows, "vs_mel_spectrogram"));
+  VS_REQUIRE(wave && n_samples && dft_packed && (spec_out || mel_out), "vs_mel_spectrogram: null pointer");
+  VS_REQUIRE(hop > 0 && hop % 4 == 0 && n_bins == 2 * hop + 1 && n_mels > 0 && n_mels <= 96 && frames_max > 0,
+             "vs_mel_spectrogram: needs n_fft = 4 * hop, n_bins = n_fft / 2 + 1, n_mels <= 96");
+  VS_REQUIRE(!mel_out || mel_packed, "vs_mel_spectrogram: mel basis missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = rows->n_rows;
+  const int ld_x = (hop + 47) / 48 * 48;                  // K of the DFT GEMM, a multiple of the 3xTF32 stage (48)
+  const int half = (n_bins + 191) / 192 * 192;            // re | im column blocks, each a multiple of the 192-column n-block
+  const int ld_mag = (n_bins + 47) / 48 * 48;
+  vs::Workspace w(ws, ws_bytes);
+  float* x = w.take<float>((int64_t)R * ld_x);
+  float* dft = w.take<float>((int64_t)R * 2 * half);
+  float* mag = w.take<float>((int64_t)R * ld_mag);
+  float* melv = w.take<float>((int64_t)R * 96);
+  if (!w.ok) { vs::set_error("vs_mel_spectrogram: workspace too small (%lld bytes given)", (long long)ws_bytes); return VS_ERR_WORKSPACE; }
+  VS_TRY(vs::mel_frame_rows(*rows, wave, t_max, n_samples, hop, ld_x, (4 * hop - hop) / 2, x, st));
+  vs::UmmaTf32 u;
+  u.in = x; u.in_ld = ld_x; u.w = dft_packed; u.out = dft; u.out_ld = 2 * half; u.R = R; u.Cin = ld_x; u.N = 2 * half;
+  u.taps = 4; u.dil = 1; u.pad_l = 0; u.split3 = 1;
+  VS_TRY(vs::umma_tf32(u, st));
+  VS_TRY(vs::mel_magnitude(dft, 2 * half, half, n_bins, ld_mag, R, mag, st));
+  if (spec_out) VS_TRY(vs::mel_unpack(*rows, mag, ld_mag, n_bins, frames_max, 0, spec_out, st));
+  if (mel_out) {
+    vs::UmmaTf32 m;
+    m.in = mag; m.in_ld = ld_mag; m.w = mel_packed; m.out = melv; m.out_ld = 96; m.R = R; m.Cin = ld_mag; m.N = 96;
+    m.taps = 1; m.split3 = 1;
+    VS_TRY(vs::umma_tf32(m, st));
+    VS_TRY(vs::mel_unpack(*rows, melv, 96, n_mels, frames_max, 1, mel_out, st));
+  }
+  return VS_OK;
+}
+
 int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,
                       void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,

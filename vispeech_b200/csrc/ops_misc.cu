@@ -349,6 +349,90 @@ int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, f
   return VS_OK;
 }
 
+// ---- 8(f) spectrogram / log-mel on the GPU (reference mel_processing.py:50-112) --------------------------------------
+// The STFT (n_fft = win = 4 hops, hann, center=False after a reflect pad of (n_fft-hop)/2) is a 4-tap conv over rows of
+// one hop each with the windowed DFT basis as weights, i.e. a GEMM for umma_tf32.cu in 3xTF32.  These three kernels are
+// the memory-bound glue around it.
+// rows: utterance b owns n_frames[b] + 3 rows; row j holds padded samples [j*hop, (j+1)*hop) in columns [0, hop)
+__global__ void mel_frame_rows_kernel(VsRows rows, const float* __restrict__ wave, int t_max,
+                                      const int32_t* __restrict__ n_samples, int hop, int ld, int pad,
+                                      float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int b = rows.row_utt[r];
+  float* o = out + (size_t)r * ld;
+  if (b < 0) {
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) o[c] = 0.f;
+    return;
+  }
+  const int j = r - rows.utt_start[b], L = n_samples[b];
+  const float* w = wave + (size_t)b * t_max;
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float v = 0.f;
+    if (c < hop) {
+      int sidx = j * hop + c - pad;                      // torch 'reflect': no edge repeat
+      if (sidx < 0) sidx = -sidx;
+      if (sidx >= L) sidx = 2 * (L - 1) - sidx;
+      if (sidx >= 0 && sidx < L) v = w[sidx];
+    }
+    o[c] = v;
+  }
+}
+// mag[r][f] = sqrt(re^2 + im^2 + 1e-6) (mel_processing.py:69,107); columns [n_bins, ld_out) are zero padding for the mel GEMM
+__global__ void mel_magnitude_kernel(const float* __restrict__ dft, int ld_in, int im_off, int n_bins, int ld_out, int R,
+                                     float* __restrict__ mag) {
+  const int r = blockIdx.y, f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || f >= ld_out) return;
+  float v = 0.f;
+  if (f < n_bins) {
+    const float re = dft[(size_t)r * ld_in + f], im = dft[(size_t)r * ld_in + im_off + f];
+    v = sqrtf(re * re + im * im + 1e-6f);
+  }
+  mag[(size_t)r * ld_out + f] = v;
+}
+// out[b][c][j] = x[row(b, j)][c] (optionally log(max(x, 1e-5)): spectral_normalize_torch) for j < n_frames[b], else 0
+__global__ void mel_unpack_kernel(VsRows rows, const float* __restrict__ x, int ld, int C, int t_max, int take_log,
+                                  float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int len = rows.utt_len[b] - 3;
+  const size_t start = (size_t)rows.utt_start[b];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (t < len && t < t_max && c < C) {
+      v = x[(start + t) * ld + c];
+      if (take_log) v = logf(fmaxf(v, 1e-5f));
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < t_max) out[((size_t)b * C + c) * t_max + t] = tile[threadIdx.x][i];
+  }
+}
+
+int mel_frame_rows(const VsRows& rows, const float* wave, int t_max, const int32_t* n_samples, int hop, int ld, int pad,
+                   float* out, cudaStream_t st) {
+  mel_frame_rows_kernel<<<rows.n_rows, 192, 0, st>>>(rows, wave, t_max, n_samples, hop, ld, pad, out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+int mel_magnitude(const float* dft, int ld_in, int im_off, int n_bins, int ld_out, int R, float* mag, cudaStream_t st) {
+  dim3 grid((ld_out + 255) / 256, R);
+  mel_magnitude_kernel<<<grid, 256, 0, st>>>(dft, ld_in, im_off, n_bins, ld_out, R, mag);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+int mel_unpack(const VsRows& rows, const float* x, int ld, int C, int t_max, int take_log, float* out, cudaStream_t st) {
+  VS_REQUIRE(t_max > 0 && C > 0, "mel_unpack: empty output");
+  dim3 grid((t_max + 31) / 32, (C + 31) / 32, rows.n_utt);
+  mel_unpack_kernel<<<grid, dim3(32, 8), 0, st>>>(rows, x, ld, C, t_max, take_log, out);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+
 // ---- 8(f) waveform post-processing (reference inference_api.py:50-51: scipy wav write + `ffmpeg -ar 22050`) ------------
 // out[b][t] = s16( sum_k fir[k] * x[b][decimate*t + k - ntaps/2] ), samples outside [0, n_samples[b]) are zero;
 // decimate == 1 and ntaps == 0: plain float -> s16.  s16(v) = clip(rint(v * 32768)) (round half to even), ffmpeg's rule.

@@ -27,5 +27,9 @@ int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C
 int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, float* out, cudaStream_t st);
 int pcm16(const float* x, int B, int T, const int32_t* n_samples, int decimate, const float* fir, int ntaps, int16_t* out,
           int T_out, cudaStream_t st);
+int mel_frame_rows(const VsRows& rows, const float* wave, int t_max, const int32_t* n_samples, int hop, int ld, int pad,
+                   float* out, cudaStream_t st);
+int mel_magnitude(const float* dft, int ld_in, int im_off, int n_bins, int ld_out, int R, float* mag, cudaStream_t st);
+int mel_unpack(const VsRows& rows, const float* x, int ld, int C, int t_max, int take_log, float* out, cudaStream_t st);
 const char* last_error();
 }  // namespace vs

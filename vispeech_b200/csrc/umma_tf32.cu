@@ -396,7 +396,7 @@ int make_plan(const UmmaTf32& c, Plan* out) {
   VS_REQUIRE(!c.ubias || (c.ubias_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(c.ubias) & 15) == 0),
              "umma_tf32: per-speaker bias must be 16-byte aligned");
   p.Nblk = 0;
-  for (int nb = 1; nb <= 8 && !p.Nblk; ++nb)                    // fewest n-blocks with Nblk <= 256, multiple of 32
+  for (int nb = 1; nb <= 16 && !p.Nblk; ++nb)                   // fewest n-blocks with Nblk <= 256, multiple of 32
     if (c.N % nb == 0 && c.N / nb <= 256 && (c.N / nb) % 32 == 0) p.Nblk = c.N / nb;
   VS_REQUIRE(p.Nblk > 0, "umma_tf32: cannot split N=%d into <= 256-column blocks", c.N);
   p.NB = c.N / p.Nblk;

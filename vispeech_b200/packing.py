@@ -83,7 +83,7 @@ def pack_tf32(w: torch.Tensor, split3: bool = False) -> torch.Tensor:
     ka_max, slab = (48, 16) if split3 else (96, 32)
     ka = min(cin, ka_max)
     assert cin % ka == 0 and ka % slab == 0
-    nblk = next(n // nb for nb in range(1, 9) if n % nb == 0 and n // nb <= 256 and (n // nb) % 32 == 0)
+    nblk = next(n // nb for nb in range(1, 17) if n % nb == 0 and n // nb <= 256 and (n // nb) % 32 == 0)
 
     def slabs(x):
         x = x.reshape(taps, cin // ka, ka // slab, slab // 4, 4, n // nblk, nblk)
