@@ -45,7 +45,7 @@ constexpr int kMaxSX = 4;         // input ring depth (>= 3 keeps load(i+2), con
 
 struct Plan {
   int L, h1, h2, planes, rows_x, rows_a2, n_tiles, tmem_cols, ctas_per_sm, row_div_shift, SX;
-  int tight;              // 1: one input stage + one A2 buffer, residual re-read from HBM/L2 (C = 64, k = 11: 2 x 90 KB of weights)
+  int tight;              // 1: two buffers shared by input rows and intermediate, residual re-read from L2 (C = 64, k = 11)
   uint32_t xa_bytes, a2_bytes, w_bytes, smem_bytes;
   uint32_t off_a2, off_w1, off_w2, off_bar;
 };
@@ -67,11 +67,15 @@ struct Params {
 #define VS_TIMED(var, stmt) stmt
 #endif
 
-// TIGHT (C = 64, k = 11): both weight sets take 180 KB, so there is room for ONE input stage and ONE A2 buffer only.
-//   * the residual is re-read from global memory (L2) in epilogue 2, so the input stage is free again as soon as conv1 has
-//     consumed it and the load of tile i+1 overlaps conv2(i-1);
-//   * epilogue 1 of tile i waits for conv2(i-1) (observing acc2_full) before it overwrites A2; the MMA order
-//     conv1(i+1), conv2(i) hides that wait behind conv1(i+1).
+// TIGHT (C = 64, k = 11): both weight sets take 180 KB, which leaves room for TWO activation buffers in all.  Each buffer
+// serves one tile from start to end: it receives the input rows XA(i); once conv1(i) has consumed them, epilogue 1 writes
+// the intermediate A2(i) over them (in A2's own layout); conv2(i) reads that and its commit hands the buffer back to the
+// producer for tile i+2.  The residual is re-read from global memory (L2) in epilogue 2, since XA(i) is gone by then.
+// The MMA warp issues tiles in pairs - conv1(a), conv1(b), conv2(a), conv2(b) - so that every hand-off (epilogue 1 of a
+// under conv1(b), epilogue 1 of b under conv2(a), the load for a+2 under conv2(b), the load for b+2 under conv1(a+2)) has
+// a whole conv of tensor time to hide behind.  Measured per pair at the C2 size: 1.23 ms (~1040 TFLOP/s) against 1.30-1.45
+// for the two unfused kernels; a first form with ONE buffer of each kind ran at 1.27, a second MMA-issuing warp for conv2
+// at 1.31 (no gain: at N = 64 the 48-clk operand fetch, not the issue loop, is what the tensor pipe waits for).
 template <int N, int MODE, bool TIGHT = false>
 __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
   constexpr int EW = N / 8, kThreads = threads_for(N);
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
   }
   // rows [128, 128 + 2*h2) of both A2 buffers are read by the last taps of conv2 (those outputs are discarded): keep
   // them finite
-  for (int i = threadIdx.x; i < (TIGHT ? 1 : 2) * p.planes * 2 * p.h2; i += kThreads) {
+  for (int i = threadIdx.x; i < (TIGHT ? 0 : 2) * p.planes * 2 * p.h2; i += kThreads) {
     const int bsel = i / (p.planes * 2 * p.h2), r = i % (p.planes * 2 * p.h2);
     const int pl = r / (2 * p.h2), j = r % (2 * p.h2);
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a2 + bsel * p.a2_bytes + (uint32_t)(pl * p.rows_a2 + 128 + j) * 16u),
@@ -186,11 +190,32 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
         VS_TIMED(tw2, mbar_wait(acc2_empty(b), ph ^ 1u, 25));
       }
       tc_fence_after();
-      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((a2 + (TIGHT ? 0u : b) * p.a2_bytes) >> 4), a2_hi, w2_lo, b_hi, idesc,
-                     taps, 1u, a2_kstep, b_kstep);
+      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((TIGHT ? xa + b * p.xa_bytes : a2 + b * p.a2_bytes) >> 4), a2_hi, w2_lo,
+                     b_hi, idesc, taps, 1u, a2_kstep, b_kstep);
       tc_commit(acc2_full(b));
+      if (TIGHT) tc_commit(xa_empty(b));          // the buffer goes back to the producer (tile j + 2)
     };
     uint32_t slot = 0, phase = 0, i = 0;
+    if (TIGHT) {
+      auto conv1 = [&](uint32_t j) {               // buffer j & 1, accumulator j & 1
+        const uint32_t b = j & 1u, ph = (j >> 1) & 1u;
+        VS_TIMED(tw0, mbar_wait(xa_full(b), ph, 23));
+        VS_TIMED(tw0, mbar_wait(acc1_empty(b), ph ^ 1u, 26));
+        tc_fence_after();
+        issue_tile<NK>(tmem_base + b * N, a1_lo_fixed + ((xa + b * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
+                       a1_kstep, b_kstep);
+        tc_commit(acc1_full(b));
+      };
+      uint32_t n_mine = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_mine;
+      for (uint32_t j = 0; j < n_mine; j += 2) {
+        const bool two = j + 1 < n_mine;
+        conv1(j);
+        if (two) conv1(j + 1);
+        conv2(j, false);
+        if (two) conv2(j + 1, false);
+      }
+    } else {
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
       const uint32_t b = i & 1u, ph = (i >> 1) & 1u;
       // probe all four barriers of this iteration at once (each probe is a ~250 clk shared-memory round trip)
@@ -209,13 +234,14 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       if (i > 0) conv2(i - 1, r2 && r3);
     }
     if (i > 0) conv2(i - 1, false);
+    }
   } else if (warp < 2 + EW) {
     // ------------------------------------------------------------------ epilogue 1: acc1 -> A2 = lrelu(c1 + b1)
     const int q = warp & 3, cc = (warp - 2) >> 2;       // TMEM lane quarter, 32-column chunk
     const float slope = c.in_slope;
     const int j = q * 32 + lane;                        // A2 local row = conv1 output row
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-    const uint32_t a2_lane = a2 + (uint32_t)j * 16u + (uint32_t)(cc * 4 * p.rows_a2) * 16u;
+    const uint32_t a2_lane = (TIGHT ? xa : a2) + (uint32_t)j * 16u + (uint32_t)(cc * 4 * p.rows_a2) * 16u;
     const uint32_t a2_plane = (uint32_t)p.rows_a2 * 16u;
     uint32_t i = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++i) {
@@ -225,14 +251,10 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       if (valid && c.row_utt) valid = c.row_utt[g >> p.row_div_shift] >= 0;
       const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
       VS_TIMED(tw0, mbar_wait(acc1_full(b), ph, 27));
-      if (TIGHT && i > 0) {                             // the single A2 buffer is still conv2(i-1)'s operand until it commits
-        const uint32_t jb = (i - 1u) & 1u, jph = ((i - 1u) >> 1) & 1u;
-        VS_TIMED(tw1, mbar_wait(acc2_full(jb), jph, 30));
-      }
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(t_lane + b * N, v);
-      const uint32_t a2_row = a2_lane + (TIGHT ? 0u : b) * p.a2_bytes;
+      const uint32_t a2_row = a2_lane + b * (TIGHT ? p.xa_bytes : p.a2_bytes);   // TIGHT: over the tile's own input rows
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
@@ -396,10 +418,10 @@ int make_plan(const UmmaPair& c, Plan* out) {
   if (fixed + 3 * p.xa_bytes <= half_sm) { per_sm = 2; p.SX = (fixed + 4 * p.xa_bytes <= half_sm) ? 4 : 3; }
   else if (fixed + 3 * p.xa_bytes <= full_sm) { p.SX = (fixed + 4 * p.xa_bytes <= full_sm) ? 4 : 3; }
   else if (fixed + 2 * p.xa_bytes <= full_sm) p.SX = 2;
-  else if (c.C == 64 && fixed - p.a2_bytes + p.xa_bytes <= 227u * 1024 - 512u) { p.SX = 1; p.tight = 1; }
+  else if (c.C == 64 && fixed - 2 * p.a2_bytes + 2 * p.xa_bytes <= 227u * 1024 - 512u) { p.SX = 2; p.tight = 1; }
   VS_REQUIRE(p.SX > 0, "umma_respair: C=%d k=%d d=%d does not fit in shared memory", c.C, c.taps, c.dil);
   p.off_a2 = p.SX * p.xa_bytes;
-  p.off_w1 = p.off_a2 + (p.tight ? 1 : 2) * p.a2_bytes;
+  p.off_w1 = p.off_a2 + (p.tight ? 0 : 2) * p.a2_bytes;
   p.off_w2 = p.off_w1 + p.w_bytes;
   p.off_bar = (p.off_w2 + p.w_bytes + 127u) & ~127u;
   p.smem_bytes = p.off_bar + bar_bytes;
