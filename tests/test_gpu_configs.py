@@ -161,3 +161,47 @@ def test_overlap_calls_matches_serial(state_dict):
         results[mode] = [o.clone() for o in outs]
     for a, b in zip(results[False], results[True]):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_filelist_rows_batch_matches_reference(net):
+    """Realism check: all 38 rows of the reference's filelists/train.list (88-1507 frames, zero-length
+    phonemes, measured F0 / energy as controls) as ONE ragged batch.  Expansion indices exact for every row; the three rows
+    the unmodified reference was run on (tests/golden/filelist_ref.npz): z within 1e-2, waveform SNR >= 30 dB."""
+    import os
+    from oracle.vispeech_oracle import expansion_indices
+    here = os.path.dirname(__file__)
+    d = np.load(os.path.join(here, "golden", "filelist_rows.npz"))
+    ref = np.load(os.path.join(here, "golden", "filelist_ref.npz"))
+    off = d["offsets"]
+    B = len(off) - 1
+    lens = [int(b - a) for a, b in zip(off[:-1], off[1:])]
+    tp = max(lens)
+    ids = torch.zeros(B, tp, dtype=torch.long)
+    dur = torch.zeros(B, tp, dtype=torch.long)
+    f0, en = torch.zeros(B, tp), torch.zeros(B, tp)
+    for b, (a, e) in enumerate(zip(off[:-1], off[1:])):
+        ids[b, :e - a] = torch.from_numpy(d["ids"][a:e]); dur[b, :e - a] = torch.from_numpy(d["duration"][a:e])
+        f0[b, :e - a] = torch.from_numpy(d["f0"][a:e]); en[b, :e - a] = torch.from_numpy(d["energy"][a:e])
+    frames = [int(dur[b].sum()) for b in range(B)]
+    picks = [int(i) for i in ref["picks"]]
+    noise = [torch.zeros(192, frames[b]) for b in range(B)]
+    for n, i in enumerate(picks):
+        noise[i] = torch.randn(192, frames[i], generator=torch.Generator().manual_seed(int(ref["eps_seed%d" % n])))
+    o, x_mask, (z, z_p, m_p, logs_p), duration, F0, energy = net.infer(
+        ids, torch.LongTensor(lens), sid=torch.from_numpy(d["sid"]), noise_scale=0.667, duration_control=dur,
+        pitch_control=f0, energy_control=en, noise=noise)
+    torch.cuda.synchronize()
+    rp, rf = net.last_rows
+    idx = net.last_lr_index.cpu().numpy()
+    for b in range(B):
+        want = expansion_indices(dur[b, :lens[b]]).numpy()
+        assert rf.lengths[b] == want.size == frames[b]
+        assert np.array_equal(idx[rf.starts[b]:rf.starts[b] + rf.lengths[b]], want), b
+        assert int(x_mask[b].sum()) == frames[b]
+    for n, i in enumerate(picks):
+        zr = torch.from_numpy(ref["z%d" % n])
+        assert float((z[i, :, :frames[i]].cpu() - zr).abs().max()) <= 1e-2
+        assert float((F0[i, :lens[i]].cpu() - torch.from_numpy(ref["F0_%d" % n])).abs().max()) <= 1e-2
+        o_ref = torch.from_numpy(ref["o%d" % n]).float() / 64
+        assert snr_db(o_ref, o[i, 0, :frames[i] * 512].cpu()) >= 30.0
+        assert float(o[i, 0, frames[i] * 512:].abs().max()) == 0.0

@@ -10,7 +10,7 @@ from oracle import inputs as oin
 from oracle.vispeech_oracle import expansion_indices, infer_one
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("vc"))
+                if not os.path.basename(p).startswith(("vc", "filelist")))
 GOLDEN_VC = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "vc*.npz")))
 
 
@@ -84,3 +84,32 @@ def test_oracle_voice_conversion_matches_reference(path):
     for k in ("z", "z_p", "z_hat"):
         assert float(np.abs(t[k].numpy() - d[k]).max()) <= 2e-4, k
     assert float(np.abs(t["o"].numpy() - d["o"]).max()) <= 2e-5
+
+
+def _filelist_rows():
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "filelist_rows.npz"))
+    off = d["offsets"]
+    return [dict(ids=torch.from_numpy(d["ids"][a:b]), duration=torch.from_numpy(d["duration"][a:b]),
+                 f0=torch.from_numpy(d["f0"][a:b]), energy=torch.from_numpy(d["energy"][a:b]), sid=int(d["sid"][i]))
+            for i, (a, b) in enumerate(zip(off[:-1], off[1:]))]
+
+
+def test_oracle_matches_reference_on_filelist_rows(state_dict):
+    """Realism check: three real rows of the reference's filelists/train.list - MFA durations incl. zeros,
+    measured F0 / energy as controls - run through the UNMODIFIED reference (tests/golden/make_filelist_golden.py)."""
+    from oracle.vispeech_oracle import infer_one
+    rows = _filelist_rows()
+    assert len(rows) == 38
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "filelist_ref.npz"))
+    for n, i in enumerate(ref["picks"]):
+        u = rows[int(i)]
+        tf = int(u["duration"].sum())
+        eps = torch.randn(192, tf, generator=torch.Generator().manual_seed(int(ref["eps_seed%d" % n])))
+        out = infer_one(state_dict, u["ids"], u["sid"], 0.667, eps, duration_control=u["duration"], pitch_control=u["f0"],
+                        energy_control=u["energy"])
+        assert out["z"].shape == ref["z%d" % n].shape
+        assert float((out["z"] - torch.from_numpy(ref["z%d" % n])).abs().max()) <= 1e-4
+        assert float((out["F0"].reshape(-1) - torch.from_numpy(ref["F0_%d" % n])).abs().max()) <= 1e-3
+        assert float((out["energy"].reshape(-1) - torch.from_numpy(ref["energy%d" % n])).abs().max()) <= 1e-3
+        o_ref = torch.from_numpy(ref["o%d" % n]).float() / 64
+        assert snr_db(o_ref, out["o"]) >= 60.0
