@@ -46,3 +46,5 @@ run("frame ffn2 x3", 27840, 768, 192, 3, 1)
 run("frame ffn1 x3", 27840, 192, 768, 3, 1)
 run("frame wn in (tf32)", 27840, 192, 384, 5, 0)
 run("frame wn rs (tf32)", 27840, 192, 384, 1, 0)
+run("frame qkv x3", 27840, 192, 576, 1, 1)
+run("frame o x3", 27840, 192, 192, 1, 1)
