@@ -205,3 +205,36 @@ def test_filelist_rows_batch_matches_reference(net):
         o_ref = torch.from_numpy(ref["o%d" % n]).float() / 64
         assert snr_db(o_ref, o[i, 0, :frames[i] * 512].cpu()) >= 30.0
         assert float(o[i, 0, frames[i] * 512:].abs().max()) == 0.0
+
+
+def test_degenerate_utterances_in_a_batch(net):
+    """Edge cases the reference's length regulator allows (models.py:418-427): an utterance whose durations are all <= 0
+    (zero frames), a single-phoneme / single-frame utterance, next to a normal one.  The normal and the tiny utterance must
+    come out exactly as when synthesised alone; the empty one as silence with an all-False mask."""
+    g = torch.Generator().manual_seed(9)
+    ids = torch.zeros(3, 12, dtype=torch.long)
+    dur = torch.zeros(3, 12, dtype=torch.long)
+    ids[0] = torch.randint(1, 400, (12,), generator=g); dur[0] = torch.randint(2, 9, (12,), generator=g)
+    ids[1, :4] = torch.randint(1, 400, (4,), generator=g); dur[1, :4] = torch.tensor([0, -3, 0, 0])
+    ids[2, 0] = 17; dur[2, 0] = 1
+    lens = torch.LongTensor([12, 4, 1])
+    sid = torch.LongTensor([3, 4, 5])
+    tf0 = int(dur[0].sum())
+    noise = [torch.randn(192, tf0, generator=g), torch.zeros(192, 0), torch.randn(192, 1, generator=g)]
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = net.infer(ids, lens, sid=sid, noise_scale=0.667,
+                                                                     duration_control=dur, noise=noise)
+    torch.cuda.synchronize()
+    assert o.shape == (3, 1, tf0 * 512) and x_mask.shape == (3, 1, tf0)
+    assert [int(x_mask[b].sum()) for b in range(3)] == [tf0, 0, 1]
+    assert float(o[1].abs().max()) == 0.0 and float(z[1].abs().max()) == 0.0
+    assert torch.isfinite(o).all() and torch.isfinite(z).all() and torch.isfinite(f0).all()
+    for b, n in ((0, 12), (2, 1)):
+        o1, m1, (z1, *_), *_ = net.infer(ids[b:b + 1, :n], lens[b:b + 1], sid=sid[b:b + 1], noise_scale=0.667,
+                                         duration_control=dur[b:b + 1, :n], noise=[noise[b]])
+        torch.cuda.synchronize()
+        tf = int(m1.sum())
+        assert torch.equal(z[b, :, :tf], z1[0, :, :tf])
+        assert torch.equal(o[b, 0, :tf * 512], o1[0, 0, :tf * 512])
+        assert float(o[b, 0, tf * 512:].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        net.infer(ids[1:2, :4], lens[1:2], sid=sid[1:2], duration_control=dur[1:2, :4])      # nothing to synthesise
