@@ -33,71 +33,69 @@ constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
 // which then runs the epilogue.  `nchunk` depends on the conv's shape only, and the un-clustered form (many row tiles)
 // accumulates the same chunks from zero and adds them in the same order, so a row's result is bit-identical whatever
 // else is in the batch (the serving queue and the batch-invariance tests rely on it).
-// The global loads of step i+1 are issued before the FMAs of step i.
+// Operands arrive through a 4-deep cp.async ring (the latency path is a chain of 6-18 dependent K-steps per CTA; with one
+// step of register prefetch each step cost a full L2 round trip).
+constexpr int CV_ST = 4;                 // cp.async ring depth: three K-steps of loads are in flight under the FMAs of one
+constexpr int CV_ALD = CV_BK + 4;        // A tile row pitch (floats): 16-byte aligned rows, warp-broadcast reads
+
+__device__ __forceinline__ void cv_cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;                      // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
 template <bool CLUSTER>
 __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a, int nchunk) {
-  __shared__ __align__(16) float As[CV_BK][CV_BM + 4];
-  __shared__ __align__(16) float Bs[CV_BK][CV_BN];
+  __shared__ __align__(16) float ring[CV_ST * (CV_BM * CV_ALD + CV_BK * CV_BN)];   // 36 KB; reused for the cluster reduce
+  float* const As = ring;                                  // [stage][row][CV_ALD]  (row-major: k contiguous)
+  float* const Bs = ring + CV_ST * CV_BM * CV_ALD;         // [stage][k][CV_BN]
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * CV_BM, c0 = blockIdx.y * CV_BN;
   const int ty = tid / 16, tx = tid % 16;
-  float acc[4][4];
+  float acc[4][4], tot[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
   const int am = tid / 4, akq = tid % 4;          // A loader: row am, channels 4*akq..+3
   const int bk = tid / 16, bn4 = tid % 16;        // B loader: k row bk, couts 4*bn4..+3
-  const bool vec_b = (a.Cout % 4 == 0);
+  const bool vec_b = (a.Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.w) & 15) == 0);
   const int per_tap = a.Cin / CV_BK, n_it = a.k * per_tap;
-  const int c_first = CLUSTER ? (int)blockIdx.z : 0, c_last = CLUSTER ? (int)blockIdx.z + 1 : nchunk;
-  float tot[4][4];
+  // this CTA's K-steps: one chunk (cluster rank) or all of them, chunk by chunk
+  const int it_lo = CLUSTER ? (int)((long long)n_it * blockIdx.z / nchunk) : 0;
+  const int it_hi = CLUSTER ? (int)((long long)n_it * (blockIdx.z + 1) / nchunk) : n_it;
 
-  auto load = [&](int it, float4& av, float4& bv) {
+  auto issue = [&](int it) {
+    const int st = (it - it_lo) % CV_ST;
     const int j = it / per_tap, ci0 = (it % per_tap) * CV_BK;
     const int ar = r0 + am + (j - a.pad_l) * a.dil;
-    av = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ar >= 0 && ar < a.R) av = *reinterpret_cast<const float4*>(a.in + (size_t)ar * a.in_ld + ci0 + 4 * akq);
-    if (a.in_slope != 1.f) {
-      av.x = lrelu(av.x, a.in_slope); av.y = lrelu(av.y, a.in_slope);
-      av.z = lrelu(av.z, a.in_slope); av.w = lrelu(av.w, a.in_slope);
-    }
-    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool a_ok = ar >= 0 && ar < a.R;
+    cv_cp_async16(As + (st * CV_BM + am) * CV_ALD + 4 * akq, a.in + (size_t)(a_ok ? ar : 0) * a.in_ld + ci0 + 4 * akq, a_ok);
     const float* wrow = a.w + ((size_t)j * a.Cin + ci0 + bk) * a.Cout + c0 + 4 * bn4;
+    float* bdst = Bs + (st * CV_BK + bk) * CV_BN + 4 * bn4;
     const int cc = c0 + 4 * bn4;
-    if (vec_b && cc + 3 < a.Cout) bv = *reinterpret_cast<const float4*>(wrow);
-    else {
-      if (cc + 0 < a.Cout) bv.x = wrow[0];
-      if (cc + 1 < a.Cout) bv.y = wrow[1];
-      if (cc + 2 < a.Cout) bv.z = wrow[2];
-      if (cc + 3 < a.Cout) bv.w = wrow[3];
+    if (vec_b) {
+      const bool b_ok = cc + 3 < a.Cout;
+      cv_cp_async16(bdst, b_ok ? wrow : a.w, b_ok);
+    } else {                                      // ragged / unaligned Cout (the 1-channel convs): plain loads
+#pragma unroll
+      for (int e = 0; e < 4; ++e) bdst[e] = (cc + e < a.Cout) ? wrow[e] : 0.f;
     }
   };
 
-  for (int ch = c_first; ch < c_last; ++ch) {
-    const int it0 = (int)((long long)n_it * ch / nchunk), it1 = (int)((long long)n_it * (ch + 1) / nchunk);
-    float4 av, bv;
-    if (it0 < it1) load(it0, av, bv);
-    for (int it = it0; it < it1; ++it) {
-      __syncthreads();
-      As[4 * akq + 0][am] = av.x; As[4 * akq + 1][am] = av.y;
-      As[4 * akq + 2][am] = av.z; As[4 * akq + 3][am] = av.w;
-      *reinterpret_cast<float4*>(&Bs[bk][4 * bn4]) = bv;
-      __syncthreads();
-      if (it + 1 < it1) load(it + 1, av, bv);
 #pragma unroll
-      for (int kk = 0; kk < CV_BK; ++kk) {
-        const float4 x = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
-        const float4 y = *reinterpret_cast<const float4*>(&Bs[kk][4 * tx]);
-        const float xa[4] = {x.x, x.y, x.z, x.w}, ya[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(xa[i], ya[jj], acc[i][jj]);
-      }
-    }
-    if (!CLUSTER) {                                     // chunk sums are added in chunk order, like rank 0 does below
+  for (int s = 0; s < CV_ST - 1; ++s) {
+    if (it_lo + s < it_hi) issue(it_lo + s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int ch = 0, ch_end = CLUSTER ? it_hi : (int)((long long)n_it / nchunk);
+  for (int it = it_lo; it < it_hi; ++it) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(CV_ST - 2) : "memory");
+    __syncthreads();                              // K-step `it` has landed for everyone; K-step it-1 is consumed
+    if (it + CV_ST - 1 < it_hi) issue(it + CV_ST - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (!CLUSTER && it == ch_end) {               // chunk sums are added in chunk order, like rank 0 does below
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -105,18 +103,46 @@ __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a, int nchunk) 
           tot[i][jj] = (ch == 0) ? acc[i][jj] : tot[i][jj] + acc[i][jj];
           acc[i][jj] = 0.f;
         }
+      ++ch;
+      ch_end = (int)((long long)n_it * (ch + 1) / nchunk);
+    }
+    const int st = (it - it_lo) % CV_ST;
+    const float* As_s = As + (st * CV_BM + 4 * ty) * CV_ALD;
+    const float* Bs_s = Bs + st * CV_BK * CV_BN + 4 * tx;
+    float xa[4][CV_BK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < CV_BK / 4; ++q) {
+        float4 v = *reinterpret_cast<const float4*>(As_s + i * CV_ALD + 4 * q);
+        if (a.in_slope != 1.f) {
+          v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope);
+          v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope);
+        }
+        xa[i][4 * q] = v.x; xa[i][4 * q + 1] = v.y; xa[i][4 * q + 2] = v.z; xa[i][4 * q + 3] = v.w;
+      }
+#pragma unroll
+    for (int kk = 0; kk < CV_BK; ++kk) {
+      const float4 y = *reinterpret_cast<const float4*>(Bs_s + kk * CV_BN);
+      const float ya[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(xa[i][kk], ya[jj], acc[i][jj]);
     }
   }
   if (!CLUSTER) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = tot[i][jj];
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = (ch == 0) ? acc[i][jj] : tot[i][jj] + acc[i][jj];
   }
 
   if (CLUSTER) {
-    __shared__ __align__(16) float Ps[16 * 256];       // this CTA's partial tile, [i*4+jj][tid]
+    static_assert(sizeof(ring) >= 16 * 256 * sizeof(float), "partial tile must fit in the ring");
+    float* const Ps = ring;                             // this CTA's partial tile, [i*4+jj][tid]; the ring is drained
     cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();                                    // every thread is done reading the ring
     const int rank = (int)blockIdx.z;
     if (rank != 0) {
 #pragma unroll
