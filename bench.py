@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 
 DEC_FLOP_PER_FRAME = 815_300_608          # SURVEY.md App. C (2 * 407,650,304 MAC)
 # DRAM bytes (read + write) of one decoder pass over the default workload (64 utterances, 27,591 frames): sum of
-# dram__bytes_read.sum + dram__bytes_write.sum over the decoder's 64 launches, profiles/launches_r1_traffic.csv
-DEC_DRAM_BYTES_C2 = 73.68e9
+# dram__bytes_read.sum + dram__bytes_write.sum over the decoder's 61 launches, profiles/launches_r1_traffic.csv
+DEC_DRAM_BYTES_C2 = 65.63e9
 HOP, SR = 512, 44100
 
 
@@ -232,8 +232,14 @@ def main():
     d2h = int(o.numel() * 4)
     copy_stream = torch.cuda.Stream(device=dev)
 
+    in_flight = []                                        # copy-done events of the calls not yet retired
+
     def e2e_step(i):
-        # the waveforms of step i travel to pinned host memory on a second stream while step i+1 computes
+        # the waveforms of step i travel to pinned host memory on a second stream while step i+1 computes.  The host may
+        # run at most two calls ahead of the GPU (a bounded request queue): that keeps the device allocator in steady
+        # state - an unbounded run-ahead makes it cudaMalloc, i.e. synchronise, for every call still in flight.
+        if len(in_flight) >= 2:
+            in_flight.pop(0).synchronize()
         o, *_ = net.infer(ids, lens, sid=sid, noise_scale=0.667, duration_control=dur, outputs="audio")
         done = torch.cuda.Event()
         done.record()
@@ -241,10 +247,14 @@ def main():
             copy_stream.wait_event(done)
             host_out[i % 2].copy_(o, non_blocking=True)
             o.record_stream(copy_stream)
+            copied = torch.cuda.Event()
+            copied.record(copy_stream)
+        in_flight.append(copied)
 
-    for i in range(max(1, args.warmup - 1)):
+    for i in range(max(3, args.warmup)):
         e2e_step(i)
     barrier()
+    in_flight.clear()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(i)
@@ -295,7 +305,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "umma_conv1d_kernel + umma_respair_kernel (the whole decoder: ~60 launches per step)",
                          "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s", "frac": dec_tflops / peak,
                          "traffic": DEC_DRAM_BYTES_C2 if (args.batch == 64) else None,
-                         "traffic_note": "DRAM read+write bytes of one decoder pass (all 64 launches), ncu, "
+                         "traffic_note": "DRAM read+write bytes of one decoder pass (all 61 launches), ncu, "
                                          "profiles/launches_r1_traffic.csv; the unfused algorithmic minimum is 0.07 GB "
                                          "(z in, waveform out): the rest is the activation stream between the ~60 convs",
                          "peak_source": peak_src,
