@@ -61,6 +61,7 @@ class SynthesizerTrn:
         # kernels) of call i+1 run on a second stream while the decoder of call i owns the SMs.  Same kernels, same
         # results; only the enqueue order across calls changes.  Off by default (lowest single-call latency).
         self.overlap_calls = False
+        self._in_flight: List[torch.cuda.Event] = []      # overlap_calls: decoder-done events of the calls not yet retired
         self._loaded = False
 
     # -- nn.Module-ish surface used by the reference scripts
@@ -206,6 +207,12 @@ class SynthesizerTrn:
         main = torch.cuda.current_stream(dev)
         overlap = bool(self.overlap_calls)
         lat = self._side_stream() if overlap else main
+        if overlap:
+            # the host may run at most two calls ahead of the GPU: buffers handed between the two streams are recycled by
+            # the caching allocator only once the other stream is done with them, so an unbounded run-ahead would make it
+            # cudaMalloc (and thereby synchronise) for every call still in flight
+            while len(self._in_flight) >= 2:
+                self._in_flight.pop(0).synchronize()
 
         def mark(name, st):
             if timings is not None:
@@ -279,6 +286,10 @@ class SynthesizerTrn:
             check(lib.vs_hifigan_decode(self._model, ctypes.byref(rf.struct), ptr(z), ml, ptr(wave),
                                         int(self.decoder_precision), ptr(ws), ws.numel(), stream), "vs_hifigan_decode")
             mark("decoder", main)
+            if overlap:
+                dec_done = torch.cuda.Event()
+                dec_done.record(main)
+                self._in_flight.append(dec_done)
 
             def unpack(src, C, mul, t_max):
                 out = torch.empty(B, C, t_max, dtype=torch.float32, device=dev)
