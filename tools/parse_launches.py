@@ -33,7 +33,7 @@ def main():
     for i, x in enumerate(step):
         t = x["gpu__time_duration.sum"]
         b = x.get("dram__bytes_read.sum", 0.0) + x.get("dram__bytes_write.sum", 0.0)
-        nm = re.sub(r"\(.*", "", x["name"])[:48]
+        nm = re.sub(r"\(.*", "", x["name"]).replace(", ", ";").replace(",", ";")[:56]
         if "to_planar" in nm:
             in_dec = True
         if in_dec:

@@ -259,6 +259,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_attention_mma = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "respair_grid_div") {
+    vs::umma_respair_grid_div((int)value);
+    return VS_OK;
+  }
   if (std::string(name) == "fused_respair") {
     vs::umma_respair_enable((int)value);
     return VS_OK;

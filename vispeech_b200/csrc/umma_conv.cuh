@@ -53,6 +53,7 @@ struct UmmaPair {
   float act_slope = 1.f, act_scale = 1.f;
 };
 bool umma_respair_supported(int C, int taps, int dil);
+void umma_respair_grid_div(int d);    // experiment knob: use 1/d of the CTA slots (co-scheduling tests)
 void umma_respair_enable(int mode);   // 0 off (default), 1 where the isolated kernel is faster, 2 wherever it fits
 int umma_respair(const UmmaPair& c, cudaStream_t st);
 

@@ -435,11 +435,13 @@ int make_plan(const UmmaPair& c, Plan* out) {
   return VS_OK;
 }
 
+int g_grid_div = 1;  // experiment knob (vs_set_option "respair_grid_div"): launch 1/div of the CTA slots, for co-scheduling tests
 int g_mode = 2;      // 0 off, 1 the C = 32 stage only, 2 (default) every ResBlock iteration whose two weight sets fit in smem
 
 }  // namespace
 
 void umma_respair_enable(int mode) { g_mode = mode; }
+void umma_respair_grid_div(int d) { g_grid_div = d < 1 ? 1 : d; }
 
 bool umma_respair_supported(int C, int taps, int dil) {
   if (g_mode == 0) return false;
@@ -469,7 +471,8 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaGetDevice(&dev));
     VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  int grid = n_sm * prm.p.ctas_per_sm;
+  int grid = n_sm * prm.p.ctas_per_sm / g_grid_div;
+  if (grid < n_sm) grid = n_sm;
   if (grid > prm.p.n_tiles) grid = prm.p.n_tiles;
   int mode = M_GENERIC;
   const bool scale = c.act_scale != 1.f;
