@@ -97,15 +97,45 @@ __global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const floa
   wave[r] = tanhf(acc);
 }
 
+// The three ResBlock chains of an MRF stage (k = 3, 7, 11) are independent until their sums meet (models.py:280-284).
+// With two streams the k = 11 chain runs next to k = 3 then k = 7: every kernel here is a persistent full-grid launch, so
+// nothing runs "in parallel", but the tail of each launch (SMs idle while the last tiles finish) is filled by the other
+// chain's CTAs - 3-5 % per pair of launches in isolation (tools/cosched_pairs.py), but nothing inside the decoder (measured
+// 25.77 vs 25.74 ms per step), so it is OFF by default.  Fork / join through events; the side chain has its own intermediate
+// buffers; the sum keeps its order (k3 + k7) + k11.
+int g_decoder_streams = 1;               // vs_set_option("decoder_streams", 1 | 2); in situ 2 gains nothing (25.77 vs 25.74 ms)
+void decoder_set_streams(int n) { g_decoder_streams = n < 2 ? 1 : 2; }
+
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, sum = nullptr, join = nullptr; };
+static int side_stream(SideStream** out) {
+  static SideStream tab[16];
+  int dev = 0;
+  VS_CUDA_CHECK(cudaGetDevice(&dev));
+  VS_REQUIRE(dev >= 0 && dev < 16, "decode: device index %d", dev);
+  SideStream& t = tab[dev];
+  if (!t.s) {
+    VS_CUDA_CHECK(cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking));
+    VS_CUDA_CHECK(cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming));
+    VS_CUDA_CHECK(cudaEventCreateWithFlags(&t.sum, cudaEventDisableTiming));
+    VS_CUDA_CHECK(cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming));
+  }
+  *out = &t;
+  return VS_OK;
+}
+
 int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
-                cudaStream_t st) {
+                cudaStream_t st_main) {
+  cudaStream_t st = st_main;
   const int R = rows.n_rows;
   int32_t* valid = ws.take<int32_t>(R);
   __nv_bfloat16* zin = ws.take<__nv_bfloat16>((int64_t)R * kHidden);
-  __nv_bfloat16* buf[6];
-  for (int i = 0; i < 6; ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
+  const bool two = g_decoder_streams == 2;
+  __nv_bfloat16* buf[9];
+  for (int i = 0; i < (two ? 9 : 6); ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
   if (!ws.ok) { set_error("decode_bf16: workspace too small"); return VS_ERR_WORKSPACE; }
-  __nv_bfloat16 *XA = buf[0], *T = buf[1], *AA = buf[2], *BA = buf[3], *S = buf[4], *NEXT = buf[5];
+  __nv_bfloat16 *XA = buf[0], *S = buf[4], *NEXT = buf[5];     // buf[1..3] / buf[6..8]: T, AA, BA of the main / side chain
+  SideStream* side = nullptr;
+  if (two) VS_TRY(side_stream(&side));
 
   VS_TRY(mask_frames(rows, max_len, valid, st));                         // (z * x_mask)[:, :, :max_len]  models.py:720
   to_planar_bf16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
@@ -138,13 +168,24 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     VS_TRY(umma_conv1d(c, st));                                          // ups[i] (ConvTranspose1d)  models.py:277
     mul *= s;
     const int Rs = R * mul;
+    if (two) {                                                           // fork: the side chain may start once XA is there
+      VS_CUDA_CHECK(cudaEventRecord(side->fork, st_main));
+      VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
+    }
     for (int j = 0; j < kDecKernels; ++j) {
       const int n = i * kDecKernels + j, k = kResK[j];
       const float final_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;    // final lrelu uses the default slope (Q3)
+      const bool on_side = two && j == kDecKernels - 1;                  // the k = 11 chain
+      st = on_side ? side->s : st_main;
+      __nv_bfloat16* T = on_side ? buf[6] : buf[1];
+      __nv_bfloat16* AA = on_side ? buf[7] : buf[2];
+      __nv_bfloat16* BA = on_side ? buf[8] : buf[3];
+      if (two && j == kDecKernels - 1) VS_CUDA_CHECK(cudaEventRecord(side->sum, st_main));   // S = k3 + k7 is enqueued
       if (fused[j]) {
         const __nv_bfloat16* cur = XA;                                   // a = lrelu(x): the only stream between iterations
         for (int mth = 0; mth < kDecDils; ++mth) {
           const bool last = (mth == kDecDils - 1);
+          if (on_side && last) VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->sum, 0));   // its epilogue reads S
           UmmaPair pr;
           pr.x = cur; pr.w1 = w.c1_16[n][mth].w; pr.b1 = w.c1_16[n][mth].b; pr.w2 = w.c2_16[n][mth].w; pr.b2 = w.c2_16[n][mth].b;
           pr.b1_host = w.bias_host[n][mth][0]; pr.b2_host = w.bias_host[n][mth][1];
@@ -163,6 +204,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
       const __nv_bfloat16* cur_act = XA;
       for (int mth = 0; mth < kDecDils; ++mth) {
         const bool last = (mth == kDecDils - 1);
+        if (on_side && last) VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->sum, 0));     // c2's epilogue reads S
         c = UmmaConv();
         c.row_utt = valid; c.row_div = mul; c.R = Rs; c.Cin = cout; c.N = cout; c.taps = k; c.pad_l = (k - 1) / 2;
         c.in = cur_act; c.w = w.c1_16[n][mth].w; c.bias = w.c1_16[n][mth].b; c.dil = kResD[mth];
@@ -182,6 +224,11 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
         VS_TRY(umma_conv1d(c, st));
         cur_act = (mth == 0) ? AA : BA;
       }
+    }
+    st = st_main;
+    if (two) {                                                           // join: NEXT (written by the side chain) is complete
+      VS_CUDA_CHECK(cudaEventRecord(side->join, side->s));
+      VS_CUDA_CHECK(cudaStreamWaitEvent(st_main, side->join, 0));
     }
   }
   const int Rw = R * mul;

@@ -259,6 +259,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_attention_mma = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "decoder_streams") {
+    vs::decoder_set_streams((int)value);
+    return VS_OK;
+  }
   if (std::string(name) == "respair_grid_div") {
     vs::umma_respair_grid_div((int)value);
     return VS_OK;
