@@ -15,6 +15,10 @@ utts = oin.c2(batch=4, seed=3, target_frames=260)
 ids = torch.stack([u["ids"] for u in utts]); dur = torch.stack([u["duration"] for u in utts])
 sid = torch.LongTensor([u["sid"] for u in utts])
 o, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, duration_control=dur)
+from vispeech_b200 import _lib
+_lib.check(_lib.load().vs_set_option(b"tf32_min_rows", 1))          # plain-TF32 route incl. the one-kernel WN layer (umma_wn.cu)
+o3, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, duration_control=dur, outputs="audio")
+_lib.check(_lib.load().vs_set_option(b"tf32_min_rows", 4096))
 net.overlap_calls = True
 o2, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, outputs="audio")        # predicted durations
 net.overlap_calls = False

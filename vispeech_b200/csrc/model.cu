@@ -51,6 +51,7 @@ static int g_x3_min_rows = 512;         // vs_set_option("x3_min_rows", n)
 // The frame prior network and the projection to (m_p, logs_p) stay on 3xTF32 at every size: z_p = m_p + eps * exp(logs_p)
 // amplifies their error (measured on C4: plain TF32 there gives |dz| = 1.2e-2 > the 1e-2 bar, 3xTF32 1.4e-4).
 static int g_tf32_prior = 0;            // vs_set_option("tf32_prior", 0 | 1)
+static int g_wn_fused = 1;              // vs_set_option("wn_fused", 0 | 1): one kernel per WN layer on the plain-TF32 path (umma_wn.cu)
 
 static int conv_rows(const ConvF32& c, const float* w_tf32, const float* w_x3, cudaStream_t st) {
   const bool shape_ok = !c.res && !c.accumulate && c.in_slope == 1.f && c.out_row_mul == 1 && c.out_row_off == 0 &&
@@ -259,6 +260,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_attention_mma = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "wn_fused") {
+    vs::g_wn_fused = value != 0;
+    return VS_OK;
+  }
   if (std::string(name) == "decoder_streams") {
     vs::decoder_set_streams((int)value);
     return VS_OK;
@@ -432,6 +437,18 @@ static int wn_forward(const WnW& w, const VsRows& rows, float* h, float* skip, c
   const int R = rows.n_rows, H = kHidden, L = w.n_layers;
   const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
   const bool fused_wn = wn_tf32 || wn_x3;            // tensor-core path: gate and res/skip update live in the conv epilogues
+  if (wn_tf32 && g_wn_fused) {                       // one kernel per layer; h ping-pongs between `h` and b.a
+    float* hb[2] = {h, b.a};
+    for (int l = 0; l < L; ++l) {
+      UmmaWn u;
+      u.h_in = hb[l & 1]; u.h_out = hb[(l + 1) & 1]; u.skip = skip;
+      u.w_in = w.t_in_gate[l]; u.b_in = w.in_gate_b[l];
+      u.cond = w.cond_tab_gate + (size_t)2 * H * l; u.cond_ld = 2 * H * L; u.cond_idx = rows.sid;
+      u.w_rs = w.t_rs[l]; u.b_rs = w.rs_b[l]; u.row_utt = rows.row_utt; u.R = R; u.first = (l == 0); u.last = (l == L - 1);
+      VS_TRY(umma_wn_layer(u, st));
+    }
+    return VS_OK;
+  }
   for (int l = 0; l < L; ++l) {
     const int rsC = (l < L - 1) ? 2 * H : H;
     if (fused_wn) {

@@ -30,4 +30,20 @@ struct UmmaTf32 {
 };
 int umma_tf32(const UmmaTf32& c, cudaStream_t st);
 
+// One whole WN layer (in_layer k5 -> gate -> res_skip 1x1 -> h / skip update) in one kernel, plain TF32.  See umma_wn.cu.
+struct UmmaWn {
+  const float* h_in = nullptr;                       // [R][192]
+  float* h_out = nullptr;                            // [R][192], != h_in (neighbouring tiles read h_in's halo rows); unused if last
+  float* skip = nullptr;                             // [R][192]: assigned when first, else accumulated
+  const float* w_in = nullptr;                       // in_layer weights, gate-interleaved columns, pack_tf32 (plain) slabs
+  const float* b_in = nullptr;                       // [384], gate-interleaved
+  const float* cond = nullptr; int cond_ld = 0;      // per-speaker cond rows (gate-interleaved, this layer's 384 columns)
+  const int32_t* cond_idx = nullptr;                 // [n_utt] -> row of cond (sid)
+  const float* w_rs = nullptr;                       // res_skip weights, pack_tf32 (plain) slabs: 384 columns, 192 when last
+  const float* b_rs = nullptr;
+  const int32_t* row_utt = nullptr;
+  int R = 0, first = 0, last = 0;
+};
+int umma_wn_layer(const UmmaWn& c, cudaStream_t st);
+
 }  // namespace vs
