@@ -260,6 +260,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_attention_mma = (int)value;
     return VS_OK;
   }
+  if (std::string(name) == "tf32_cluster") {
+    vs::umma_tf32_set_cluster((int)value);
+    return VS_OK;
+  }
   if (std::string(name) == "wn_fused") {
     vs::g_wn_fused = value != 0;
     return VS_OK;

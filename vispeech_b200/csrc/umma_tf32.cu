@@ -25,8 +25,11 @@ constexpr int kThreads = 32 * (kLoaderWarps + 2 + kEpiWarps);   // loaders | wei
 constexpr int kSA = 2, kMaxSB = 16;   // weight ring: as many slabs as fit (>= 3): the stream is latency-bound otherwise
 // plain TF32: 96 channels per activation stage, 32 per weight slab; 3xTF32: 48 / 16 with [hi|lo] pairs (same bytes)
 
+int g_tf32_cluster = 1;        // vs_set_option("tf32_cluster", 1 | 2): CTAs sharing each weight slab by TMA multicast (off: no gain)
+
 struct Plan {
   int rows_a, halo_l, n_ka, slabs_per_ka, Nblk, NB, NACC, tmem_cols, n_tiles, n_units;
+  int cl;                 // CTAs per cluster sharing every weight slab (1 or 2); n_units counts (tile group of cl tiles, n-block)
   int SB;                 // weight ring depth
   int KA, slabC;          // channels per activation stage / per weight slab
   uint32_t a_half, b_half; // byte offset of the lo copy inside a stage / slab (split3)
@@ -60,6 +63,28 @@ __device__ __forceinline__ void tc_mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo,
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Weight slabs are re-streamed from L2 for every 128-row tile: at 27.6 k rows the frame-level convs move 0.3-0.8 GB of weights
+// per launch (FFN-1: 764 MB in 139 us).  With cl = 2 the two CTAs of a cluster work on neighbouring row tiles of the same
+// n-block in lockstep; each fetches HALF of every slab and multicasts it into both CTAs' rings, and a ring slot is released
+// by a multicast tcgen05.commit from both MMA warps.  Measured: no gain (frame prior 3.42 vs 3.41 ms, flow 2.13 vs 2.10) - L2
+// is not what these kernels wait for - so it is an A/B knob, off by default.  (A first, broken version - UMMA descriptors
+// built from un-masked shared-window addresses, which carry the CTA rank above bit 18 in a cluster launch - "gained" 8 % on
+// the whole step: its MMAs multiplied garbage, drew less power, and the power-capped GPU clocked 1.89 instead of 1.73 GHz.)
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {   // whole warp calls, one elected lane commits
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // a/b format TF32 = 2 (cute::UMMA::F16F32Format), fp32 accumulate, K-major both
 __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -92,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSA; ++i) { mbar_init(a_full(i), kLoaderWarps); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), (uint32_t)p.cl); }
     for (int i = 0; i < p.NACC; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -104,9 +129,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();               // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int slabs_per_unit = p.n_ka * c.taps * p.slabs_per_ka;
+  // work item w = (group of cl neighbouring row tiles, n-block); this CTA takes tile `rank` of the group
+  const int cl = p.cl, rank = cl > 1 ? (int)(blockIdx.x % cl) : 0;
+  const int w_first = blockIdx.x / cl, w_step = gridDim.x / cl;
+  auto tile_of = [&](int w) { return (w / p.NB) * cl + rank; };
 
   if (warp < kLoaderWarps) {
     // ------------------------------------------------------------- activation loaders (128 threads)
@@ -118,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     uint32_t slot = 0, phase = 0;
     float4 pf[kPF];
     auto stage_src = [&](int u, int ka, int row, bool* ok) -> const float* {
-      const int tile = u / p.NB;
+      const int tile = tile_of(u);
       const int rg = tile * kTileM - p.halo_l + row;
       *ok = rg >= 0 && rg < c.R;
       return c.in + (size_t)(*ok ? rg : 0) * c.in_ld + ka * p.KA;
@@ -141,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
                      "f"(to_tf32(v.y - hi.y)), "f"(to_tf32(v.z - hi.z)), "f"(to_tf32(v.w - hi.w))
                      : "memory");
     };
-    int u = blockIdx.x, ka = 0;
+    int u = w_first, ka = 0;
     if (u < p.n_units) prefetch(u, 0);
     while (u < p.n_units) {
       VS_TIMED(tw0, mbar_wait(a_empty(slot), phase ^ 1, 11));
@@ -164,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(slot));
       if (++slot == kSA) { slot = 0; phase ^= 1; }
-      if (++ka == p.n_ka) { ka = 0; u += gridDim.x; }
+      if (++ka == p.n_ka) { ka = 0; u += w_step; }
       if (u < p.n_units) prefetch(u, ka);
     }
   } else if (warp == kLoaderWarps) {
@@ -182,7 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
       uint32_t s1, p1, s2, p2;
       ahead(slot, phase, 1 % SB, &s1, &p1);
       bool r0 = mbar_test_wait(b_empty(slot), phase ^ 1), r1 = SB > 1 && mbar_test_wait(b_empty(s1), p1 ^ 1);
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const uint32_t part = p.b_bytes / (uint32_t)cl;       // this CTA's share of every slab
+      for (int u = w_first; u < p.n_units; u += w_step) {
         const int nb = u % p.NB;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.w) + (size_t)nb * slabs_per_unit * p.b_bytes;
         for (int s = 0; s < slabs_per_unit; ++s) {
@@ -191,7 +222,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
           const bool r2 = SB > 2 && mbar_test_wait(b_empty(s2), p2 ^ 1);
           if (lane == 0) {
             mbar_arrive_expect_tx(b_full(slot), p.b_bytes);
-            bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.b_bytes, p.b_bytes, b_full(slot));
+            if (cl == 1) bulk_g2s(b_base + slot * p.b_bytes, wsrc + (size_t)s * p.b_bytes, p.b_bytes, b_full(slot));
+            else bulk_g2s_multicast(b_base + slot * p.b_bytes + rank * part, wsrc + (size_t)s * p.b_bytes + rank * part, part,
+                                    b_full(slot), (uint16_t)((1u << cl) - 1u));
           }
           ahead(slot, phase, 1, &slot, &phase);
           r0 = r1; r1 = r2;
@@ -217,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     uint32_t bs1, bp1, bs2, bp2;
     ahead(b_slot, b_phase, 1 % SB, &bs1, &bp1);
     bool r0 = mbar_test_wait(b_full(b_slot), b_phase), r1 = SB > 1 && mbar_test_wait(b_full(bs1), bp1);
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = w_first; u < p.n_units; u += w_step) {
       VS_TIMED(tw1, mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 13));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc_slot * (uint32_t)p.Nblk;
@@ -225,7 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
       for (int ka = 0; ka < p.n_ka; ++ka) {
         VS_TIMED(tw0, mbar_wait(a_full(a_slot), a_phase, 14));
         tc_fence_after();
-        const uint32_t a_stage16 = (a_base + a_slot * p.a_bytes) >> 4;
+        // descriptors take the 18-bit offset inside this CTA's shared memory: in a cluster launch the shared-window address
+        // of rank > 0 has higher bits set, which an unmasked add would carry into the LBO field
+        const uint32_t a_stage16 = ((a_base + a_slot * p.a_bytes) & 0x3FFFFu) >> 4;
         const int slabs_here = min(p.KA, c.Cin - ka * p.KA) / p.slabC;
         for (int t = 0; t < c.taps; ++t)
           for (int j = 0; j < slabs_here; ++j) {
@@ -234,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
             const bool r2 = SB > 2 && mbar_test_wait(b_full(bs2), bp2);      // probe two slabs ahead (see the producer)
             tc_fence_after();
             uint32_t a_lo = a_lo_fixed + a_stage16 + (uint32_t)j * slab_planes * (uint32_t)p.rows_a + (uint32_t)(t * c.dil);
-            uint32_t b_lo = b_lo_fixed + ((b_base + b_slot * p.b_bytes) >> 4);
+            uint32_t b_lo = b_lo_fixed + (((b_base + b_slot * p.b_bytes) & 0x3FFFFu) >> 4);
             // fully unrolled per-slab issue (one warp issues every MMA: runtime-nested loops cost ~100 clk per MMA,
             // tools/mma_microbench.cu): 3xTF32 = 2 K-steps x {hi*hi, lo*hi, hi*lo}, plain = 4 K-steps
             if (c.split3) {
@@ -251,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
                 tc_mma_tf32_lohi(d_tmem, a_lo + k8 * a_kstep, a_hi, b_lo + k8 * b_kstep, b_hi, idesc, k8 ? 1u : accumulate);
             }
             accumulate = 1;
-            tc_commit(b_empty(b_slot));
+            if (cl == 1) tc_commit(b_empty(b_slot));
+            else tc_commit_multicast(b_empty(b_slot), (uint16_t)((1u << cl) - 1u));   // releases the slot in both CTAs
             ahead(b_slot, b_phase, 1, &b_slot, &b_phase);
             r0 = r1; r1 = r2;
           }
@@ -268,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
     const int hsel = ew >> 2;
     const int n_chunks = p.Nblk / 32;
     uint32_t acc_slot = 0, acc_phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int tile = u / p.NB, nb = u % p.NB;
+    for (int u = w_first; u < p.n_units; u += w_step) {
+      const int tile = tile_of(u), nb = u % p.NB;
       const int r = tile * kTileM + q * 32 + lane;
       const bool in_range = r < c.R;
       int utt = -1;
@@ -380,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_tf32_kernel(const __grid_con
 #endif
   tc_fence_before();
   __syncthreads();
+  if (p.cl > 1) cluster_sync_all();               // no CTA leaves while its peer may still multicast into it
   if (warp == kLoaderWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -430,12 +467,15 @@ int make_plan(const UmmaTf32& c, Plan* out) {
   p.smem_bytes = p.off_bar + bar_bytes;
   VS_REQUIRE(p.smem_bytes <= 227u * 1024, "umma_tf32: tile does not fit in shared memory");
   if (p.smem_bytes < 120u * 1024) p.smem_bytes = 120u * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
-  p.n_units = p.n_tiles * p.NB;
+  p.cl = (g_tf32_cluster == 2 && p.n_tiles >= 2) ? 2 : 1;
+  p.n_units = ((p.n_tiles + p.cl - 1) / p.cl) * p.NB;
   *out = p;
   return VS_OK;
 }
 
 }  // namespace
+
+void umma_tf32_set_cluster(int n) { g_tf32_cluster = n == 2 ? 2 : 1; }
 
 int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
   Params prm;
@@ -453,8 +493,21 @@ int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
   }
   VS_TRY(make_plan(c, &prm.p));
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
-  int grid = n_sm < prm.p.n_units ? n_sm : prm.p.n_units;
-  umma_tf32_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+  const int cl = prm.p.cl;
+  int groups = n_sm / cl;
+  if (groups > prm.p.n_units) groups = prm.p.n_units;
+  const int grid = groups * cl;
+  if (cl == 1) {
+    umma_tf32_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = prm.p.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    VS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_tf32_kernel, prm));
+  }
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
