@@ -159,6 +159,28 @@ def test_conv_tf32_matches_cpu(G, R, cin, cout, k, dil, act):
     assert (out - ref).abs().max().item() <= 5e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("R,cin,cout,k,split3", [(300, 192, 576, 1, 0), (1000, 192, 768, 3, 1), (700, 192, 384, 5, 0), (129, 96, 192, 1, 1)])
+def test_conv_tf32_cluster_multicast_matches_single_cta(G, R, cin, cout, k, split3):
+    """The optional 2-CTA cluster form of the TF32 conv (each CTA fetches half of every weight slab and multicasts it; ring
+    slots released by a multicast tcgen05.commit; odd tile counts leave one phantom tile) must be bit-identical to the
+    single-CTA form: same MMAs in the same order per tile."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(R + cout)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(k, cin, cout, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    outs = []
+    for cl in (1, 2):
+        _lib.check(lib.vs_set_option(b"tf32_cluster", cl))
+        try:
+            outs.append(G.conv_tf32(x.to(G.DEV), w, b.to(G.DEV), dil=1, pad_l=(k - 1) // 2, act=0, row_utt=None,
+                                    split3=bool(split3)).cpu())
+        finally:
+            _lib.check(lib.vs_set_option(b"tf32_cluster", 1))
+    assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("R,cin,cout,k,act", [(300, 192, 576, 1, 0), (1000, 192, 768, 3, 1), (260, 768, 192, 3, 0),
                                              (500, 96, 192, 1, 0), (700, 192, 384, 5, 0), (2816, 192, 256, 3, 1)])
 def test_conv_3xtf32_is_fp32_accurate(G, R, cin, cout, k, act):
