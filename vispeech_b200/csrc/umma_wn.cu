@@ -16,6 +16,7 @@
 // Weight slabs (24 KB: 32 channels x 192 columns) stream through a 5-deep TMA ring for both GEMMs.
 #include "umma_tf32.cuh"
 #include "umma_common.cuh"
+#include "umma_conv.cuh"
 
 namespace vs {
 namespace {
@@ -35,7 +36,17 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 8u * (4 + 2 * SB + 4) + 16u;
 static_assert(48u * ACT_PLANE <= A_BYTES, "acts must fit over the input stages");
 static_assert(SMEM_BYTES <= 227u * 1024, "smem");
 
-struct Params { UmmaWn c; int n_tiles; };
+struct Params { UmmaWn c; int n_tiles; long long* dbg; };   // dbg: wait-clock counters of the MMA warp (-DVS_UMMA_TIMING only)
+#ifdef VS_UMMA_TIMING
+#define WN_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = prm.dbg ? clock64() : 0;  \
+    stmt;                                           \
+    if (prm.dbg) var += clock64() - _t0;            \
+  } while (0)
+#else
+#define WN_TIMED(var, stmt) stmt
+#endif
 
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -167,19 +178,23 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
     const uint32_t b_hi = (uint32_t)(make_desc(0, b_lbo, 128u) >> 32), b_fix = (uint32_t)make_desc(0, b_lbo, 128u);
     constexpr uint32_t a1_kstep = 2u * ROWS_A, a2_kstep = 2u * kTileM, b_kstep = 2u * NBLK;     // two planes, in 16-byte units
     uint32_t slot = 0, phase = 0, i = 0;
+#ifdef VS_UMMA_TIMING
+    long long tw_a = 0, tw_b = 0, tw_acts = 0, tw_acc2 = 0;
+    const long long t_start = prm.dbg ? clock64() : 0;
+#endif
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++i) {
       const uint32_t par = i & 1u;
-      mbar_wait(acc2_empty, par ^ 1u, 43);           // the previous tile's res/skip accumulators have been drained
+      WN_TIMED(tw_acc2, mbar_wait(acc2_empty, par ^ 1u, 43));   // the previous tile's res/skip accumulators have been drained
       tc_fence_after();
       for (int ka = 0; ka < 2; ++ka) {
-        mbar_wait(a_full(ka), par, 44);
+        WN_TIMED(tw_a, mbar_wait(a_full(ka), par, 44));
         tc_fence_after();
         const uint32_t a_stage16 = (a_base + ka * A_STAGE) >> 4;
         for (int nb = 0; nb < 2; ++nb) {
           const uint32_t d = tmem_base + (uint32_t)nb * NBLK;
           for (int t = 0; t < TAPS; ++t)
             for (int j = 0; j < 3; ++j) {
-              mbar_wait(b_full(slot), phase, 45);
+              WN_TIMED(tw_b, mbar_wait(b_full(slot), phase, 45));
               tc_fence_after();
               const uint32_t a_lo = a1_fix + a_stage16 + (uint32_t)j * 8u * ROWS_A + (uint32_t)t;
               const uint32_t b_lo = b_fix + ((b_base + slot * B_SLAB) >> 4);
@@ -193,13 +208,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
         }
       }
       tc_commit(acc1_full);
-      mbar_wait(acts_full, par, 46);                 // gate output is in smem (over the input tile), acc columns are free
+      WN_TIMED(tw_acts, mbar_wait(acts_full, par, 46));   // gate output is in smem (over the input tile), acc columns are free
       tc_fence_after();
       const uint32_t act16 = a_base >> 4;
       for (int nb = 0; nb < nb2; ++nb) {
         const uint32_t d = tmem_base + (uint32_t)nb * NBLK;
         for (int s6 = 0; s6 < 6; ++s6) {
-          mbar_wait(b_full(slot), phase, 47);
+          WN_TIMED(tw_b, mbar_wait(b_full(slot), phase, 47));
           tc_fence_after();
           const uint32_t a_lo = a2_fix + act16 + (uint32_t)s6 * 8u * kTileM;
           const uint32_t b_lo = b_fix + ((b_base + slot * B_SLAB) >> 4);
@@ -214,6 +229,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
       tc_commit(a_empty(0));                         // the activation region may receive the next tile
       tc_commit(a_empty(1));
     }
+#ifdef VS_UMMA_TIMING
+    if (prm.dbg && lane == 0) {
+      long long* o = prm.dbg + 148 * 16 + (size_t)blockIdx.x * 8;    // behind the region the other tcgen05 kernels use
+      o[0] = clock64() - t_start; o[1] = tw_a; o[2] = tw_b; o[3] = tw_acts; o[4] = tw_acc2; o[5] = i;
+    }
+#endif
   } else {
     // ------------------------------------------------------------- epilogues (8 warps): gate, then res/skip update
     const int ew = warp - (kLoaderWarps + 2);
@@ -234,32 +255,29 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
       mbar_wait(acc1_full, par, 48);
       tc_fence_after();
       for (int cc = hsel; cc < 12; cc += 2) {
+        const int col0 = cc * 32;
+        // bias + per-speaker cond of this chunk first: the st.shared below are asm volatile, so loads issued inside the g loop
+        // would each wait out a full L1/L2 round trip (measured: 17 k clk per tile in this epilogue before, tools/wn_timing.py)
+        float4 bsum[8];                              // [0..3] tanh half, [4..7] sigmoid half
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          bsum[g] = __ldg(reinterpret_cast<const float4*>(c.b_in + col0 + 4 * g));
+          if (ub) {
+            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ub + col0 + 4 * g));
+            bsum[g].x += u4.x; bsum[g].y += u4.y; bsum[g].z += u4.z; bsum[g].w += u4.w;
+          }
+        }
         uint32_t v[32];
         tmem_ld32(t_row + (uint32_t)(cc * 32), v);
-        const int col0 = cc * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) {
-            float t[4], sg[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { t[e] = __uint_as_float(v[4 * g + e]); sg[e] = __uint_as_float(v[16 + 4 * g + e]); }
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(c.b_in + col0 + 4 * g));
-            const float4 bs = __ldg(reinterpret_cast<const float4*>(c.b_in + col0 + 16 + 4 * g));
-            t[0] += bt.x; t[1] += bt.y; t[2] += bt.z; t[3] += bt.w;
-            sg[0] += bs.x; sg[1] += bs.y; sg[2] += bs.z; sg[3] += bs.w;
-            if (ub) {
-              const float4 ut = __ldg(reinterpret_cast<const float4*>(ub + col0 + 4 * g));
-              const float4 us = __ldg(reinterpret_cast<const float4*>(ub + col0 + 16 + 4 * g));
-              t[0] += ut.x; t[1] += ut.y; t[2] += ut.z; t[3] += ut.w;
-              sg[0] += us.x; sg[1] += us.y; sg[2] += us.z; sg[3] += us.w;
-            }
-            // tanh(a) * sigmoid(b) = (1 - e^-2a) / ((1 + e^-2a)(1 + e^-b)) with the fast exponential: relative error ~1e-6,
-            // three orders below the TF32 rounding the result gets as the next GEMM's operand
-            y.x = to_tf32(gate_fast(t[0], sg[0]));
-            y.y = to_tf32(gate_fast(t[1], sg[1]));
-            y.z = to_tf32(gate_fast(t[2], sg[2]));
-            y.w = to_tf32(gate_fast(t[3], sg[3]));
+            const float4 bt = bsum[g], bs = bsum[4 + g];
+            y.x = to_tf32(gate_fast(__uint_as_float(v[4 * g]) + bt.x, __uint_as_float(v[16 + 4 * g]) + bs.x));
+            y.y = to_tf32(gate_fast(__uint_as_float(v[4 * g + 1]) + bt.y, __uint_as_float(v[16 + 4 * g + 1]) + bs.y));
+            y.z = to_tf32(gate_fast(__uint_as_float(v[4 * g + 2]) + bt.z, __uint_as_float(v[16 + 4 * g + 2]) + bs.z));
+            y.w = to_tf32(gate_fast(__uint_as_float(v[4 * g + 3]) + bt.w, __uint_as_float(v[16 + 4 * g + 3]) + bs.w));
           }
           // channels 16cc + 4g .. +3 = plane 4cc + g of the K-major tile
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + (uint32_t)(4 * cc + g) * ACT_PLANE + (uint32_t)rl * 16u),
@@ -281,38 +299,26 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
         const bool to_h = !c.last && cc < 6;
         const int col = (cc % 6) * 32;
         const float* bias = c.b_rs + cc * 32;
-        if (to_h) {
-          const float* hi = c.h_in + (size_t)r * H + col;
-          float* ho = c.h_out + (size_t)r * H + col;
+        // all loads of the chunk before its first store (the compiler may not move a load across a store to a possibly
+        // aliasing pointer: one round trip per float4 otherwise - 20 k clk per tile in this epilogue before)
+        float4 bb[8], old[8];
+        const float* src = to_h ? c.h_in + (size_t)r * H + col : c.skip + (size_t)r * H + col;
+        const bool need_old = valid && (to_h || !c.first);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 4 * g));
-              const float4 old = *reinterpret_cast<const float4*>(hi + 4 * g);
-              y = make_float4(__uint_as_float(v[4 * g]) + b.x + old.x, __uint_as_float(v[4 * g + 1]) + b.y + old.y,
-                              __uint_as_float(v[4 * g + 2]) + b.z + old.z, __uint_as_float(v[4 * g + 3]) + b.w + old.w);
-            }
-            *reinterpret_cast<float4*>(ho + 4 * g) = y;
-          }
-        } else {
-          float* so = c.skip + (size_t)r * H + col;
-          if (valid) {
+        for (int g = 0; g < 8; ++g) {
+          bb[g] = __ldg(reinterpret_cast<const float4*>(bias + 4 * g));
+          old[g] = need_old ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float* dst = to_h ? c.h_out + (size_t)r * H + col : c.skip + (size_t)r * H + col;
+        if (valid) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 4 * g));
-              float4 y = make_float4(__uint_as_float(v[4 * g]) + b.x, __uint_as_float(v[4 * g + 1]) + b.y,
-                                     __uint_as_float(v[4 * g + 2]) + b.z, __uint_as_float(v[4 * g + 3]) + b.w);
-              if (!c.first) {
-                const float4 old = *reinterpret_cast<const float4*>(so + 4 * g);
-                y.x += old.x; y.y += old.y; y.z += old.z; y.w += old.w;
-              }
-              *reinterpret_cast<float4*>(so + 4 * g) = y;
-            }
-          } else if (c.first) {
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(dst + 4 * g) =
+                make_float4(__uint_as_float(v[4 * g]) + bb[g].x + old[g].x, __uint_as_float(v[4 * g + 1]) + bb[g].y + old[g].y,
+                            __uint_as_float(v[4 * g + 2]) + bb[g].z + old[g].z, __uint_as_float(v[4 * g + 3]) + bb[g].w + old[g].w);
+        } else if (to_h || c.first) {                  // gap rows: h' = 0; skip zeroed when assigned, untouched otherwise
 #pragma unroll
-            for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(so + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       tc_fence_before();
@@ -347,6 +353,7 @@ int umma_wn_layer(const UmmaWn& c, cudaStream_t st) {
   }
   Params prm;
   prm.c = c;
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   prm.n_tiles = (c.R + kTileM - 1) / kTileM;
   const int grid = n_sm < prm.n_tiles ? n_sm : prm.n_tiles;
   umma_wn_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(prm);
