@@ -441,17 +441,19 @@ static int wn_forward(const WnW& w, const VsRows& rows, float* h, float* skip, c
   const int R = rows.n_rows, H = kHidden, L = w.n_layers;
   const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
   const bool fused_wn = wn_tf32 || wn_x3;            // tensor-core path: gate and res/skip update live in the conv epilogues
-  if (wn_tf32 && g_wn_fused) {                       // one kernel per layer; h ping-pongs between `h` and b.a
-    float* hb[2] = {h, b.a};
+  if (wn_tf32 && g_wn_fused) {                       // one kernel per layer on planar fp32 h / skip (umma_wn.cu)
+    float* hb[2] = {b.a, b.a + (size_t)R * H};       // b.a and b.rs are [R][2H] scratch of the unfused path
+    float* skip_pl = b.rs;
+    VS_TRY(rows_to_planar4(h, hb[0], R, H, st));
     for (int l = 0; l < L; ++l) {
       UmmaWn u;
-      u.h_in = hb[l & 1]; u.h_out = hb[(l + 1) & 1]; u.skip = skip;
+      u.h_in = hb[l & 1]; u.h_out = hb[(l + 1) & 1]; u.skip = skip_pl;
       u.w_in = w.t_in_gate[l]; u.b_in = w.in_gate_b[l];
       u.cond = w.cond_tab_gate + (size_t)2 * H * l; u.cond_ld = 2 * H * L; u.cond_idx = rows.sid;
       u.w_rs = w.t_rs[l]; u.b_rs = w.rs_b[l]; u.row_utt = rows.row_utt; u.R = R; u.first = (l == 0); u.last = (l == L - 1);
       VS_TRY(umma_wn_layer(u, st));
     }
-    return VS_OK;
+    return planar4_to_rows(skip_pl, skip, R, H, st);
   }
   for (int l = 0; l < L; ++l) {
     const int rsC = (l < L - 1) ? 2 * H : H;

@@ -33,9 +33,10 @@ void umma_tf32_set_cluster(int n);   // 1 | 2 CTAs share each weight slab (TMA m
 
 // One whole WN layer (in_layer k5 -> gate -> res_skip 1x1 -> h / skip update) in one kernel, plain TF32.  See umma_wn.cu.
 struct UmmaWn {
-  const float* h_in = nullptr;                       // [R][192]
-  float* h_out = nullptr;                            // [R][192], != h_in (neighbouring tiles read h_in's halo rows); unused if last
-  float* skip = nullptr;                             // [R][192]: assigned when first, else accumulated
+  // h and skip are PLANAR fp32: [192/4][R][4] (rows_to_planar4 / planar4_to_rows convert at the ends of the WN stack)
+  const float* h_in = nullptr;
+  float* h_out = nullptr;                            // != h_in (neighbouring tiles read h_in's halo rows); unused if last
+  float* skip = nullptr;                             // assigned when first, else accumulated
   const float* w_in = nullptr;                       // in_layer weights, gate-interleaved columns, pack_tf32 (plain) slabs
   const float* b_in = nullptr;                       // [384], gate-interleaved
   const float* cond = nullptr; int cond_ld = 0;      // per-speaker cond rows (gate-interleaved, this layer's 384 columns)
@@ -46,5 +47,7 @@ struct UmmaWn {
   int R = 0, first = 0, last = 0;
 };
 int umma_wn_layer(const UmmaWn& c, cudaStream_t st);
+int rows_to_planar4(const float* in, float* out, int R, int C, cudaStream_t st);    // [R][C] -> [C/4][R][4]
+int planar4_to_rows(const float* in, float* out, int R, int C, cudaStream_t st);    // [C/4][R][4] -> [R][C]
 
 }  // namespace vs

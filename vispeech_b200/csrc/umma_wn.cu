@@ -14,6 +14,11 @@
 //   MMA       res_skip against that smem tile                                                   -> TMEM acc (same columns)
 //   epilogue  h' = h + res (h is double-buffered: neighbouring tiles still read h's halo rows), skip (+)= skip
 // Weight slabs (24 KB: 32 channels x 192 columns) stream through a 5-deep TMA ring for both GEMMs.
+// h and skip live in a PLANAR fp32 layout [C/4][R][4] inside the WN stack (rows_to_planar4 / planar4_to_rows at its ends):
+// a plane-slab of a row tile is contiguous in HBM and IS one K-chunk column of the K-major smem layout, so the input tile
+// arrives by 24 plain TMA bulk copies per stage (no loader warps, no st.shared; the MMA reads the top 19 bits of the fp32
+// words), and the update epilogue's per-row float4 accesses are 512 contiguous bytes per warp instruction instead of 32
+// different 128-byte lines (the row-major form of this kernel spent 20 % of its time there and 13 % in the loaders).
 #include "umma_tf32.cuh"
 #include "umma_common.cuh"
 #include "umma_conv.cuh"
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (4 + 2 * SB + 4));
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), kLoaderWarps); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     mbar_init(acc1_full, 1); mbar_init(acts_full, kEpiWarps); mbar_init(acc2_full, 1); mbar_init(acc2_empty, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -104,50 +109,34 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
   const int nb2 = c.last ? 1 : 2;                      // res_skip n-blocks: [res | skip], or skip only in the last layer
 
   if (warp < kLoaderWarps) {
-    // ------------------------------------------------------------- loaders: h rows -> TF32 -> K-major smem, once per tile
-    const int tid = threadIdx.x;
-    float4 pf[kPF];
-    auto src_of = [&](int tile, int ka, int row, bool* ok) -> const float* {
-      const int rg = tile * kTileM - HALO + row;
-      *ok = rg >= 0 && rg < c.R;
-      return c.h_in + (size_t)(*ok ? rg : 0) * H + ka * 96;
-    };
-    auto prefetch = [&](int tile, int ka) {
-      bool ok;
-      const float* src = src_of(tile, ka, tid, &ok);
-#pragma unroll
-      for (int pl = 0; pl < kPF; ++pl) {
-        pf[pl] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) pf[pl] = *reinterpret_cast<const float4*>(src + 4 * pl);
-      }
-    };
-    auto put = [&](uint32_t dst, const float4& v) {
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(to_tf32(v.x)), "f"(to_tf32(v.y)), "f"(to_tf32(v.z)),
-                   "f"(to_tf32(v.w))
-                   : "memory");
-    };
-    int tile = blockIdx.x, ka = 0;
-    uint32_t i = 0;
-    if (tile < prm.n_tiles) prefetch(tile, 0);
-    while (tile < prm.n_tiles) {
-      mbar_wait(a_empty(ka), (i & 1u) ^ 1u, 41);
-      const uint32_t stage = a_base + ka * A_STAGE;
-#pragma unroll
-      for (int pl = 0; pl < kPF; ++pl) put(stage + (uint32_t)tid * 16u + (uint32_t)(pl * ROWS_A) * 16u, pf[pl]);
-      for (int row = tid; row < ROWS_A; row += 32 * kLoaderWarps) {     // planes 12..23 of this row, and the halo rows
-        bool ok;
-        const float* src = src_of(tile, ka, row, &ok);
-        for (int pl = (row == tid ? kPF : 0); pl < 24; ++pl) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) v = *reinterpret_cast<const float4*>(src + 4 * pl);
-          put(stage + (uint32_t)row * 16u + (uint32_t)(pl * ROWS_A) * 16u, v);
+    // ------------------------------------------------------------- input tile producer (warp 0): TMA bulk copies per plane
+    if (warp == 0) {
+      uint32_t i = 0;
+      for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++i) {
+        const int row_lo = tile * kTileM - HALO, row_hi = row_lo + ROWS_A;
+        const int c_lo = row_lo < 0 ? 0 : row_lo, c_hi = row_hi > c.R ? c.R : row_hi;
+        const int n_zero_lo = c_lo - row_lo, n_zero_hi = row_hi - c_hi;
+        const uint32_t bytes = (uint32_t)(c_hi - c_lo) * 16u;
+        for (int ka = 0; ka < 2; ++ka) {
+          mbar_wait(a_empty(ka), (i & 1u) ^ 1u, 41);
+          const uint32_t stage = a_base + ka * A_STAGE;
+          if (n_zero_lo > 0 || n_zero_hi > 0) {        // rows outside [0, R): the conv's zero padding
+            const int per_plane = n_zero_lo + n_zero_hi;
+            for (int k = lane; k < 24 * per_plane; k += 32) {
+              const int pl = k / per_plane, j = k % per_plane;
+              const int row = j < n_zero_lo ? j : (ROWS_A - n_zero_hi + (j - n_zero_lo));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(stage + (uint32_t)(pl * ROWS_A + row) * 16u), "r"(0) : "memory");
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_expect_tx(a_full(ka), 24u * bytes);
+          __syncwarp();
+          if (lane < 24)
+            bulk_g2s(stage + (uint32_t)(lane * ROWS_A + n_zero_lo) * 16u, c.h_in + ((size_t)(ka * 24 + lane) * c.R + c_lo) * 4, bytes,
+                     a_full(ka));
         }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(ka));
-      if (++ka == 2) { ka = 0; tile += gridDim.x; ++i; }
-      if (tile < prm.n_tiles) prefetch(tile, ka);
     }
   } else if (warp == kLoaderWarps) {
     // ------------------------------------------------------------- weight slabs (TMA bulk), in the MMA warp's order
@@ -302,23 +291,25 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
         // all loads of the chunk before its first store (the compiler may not move a load across a store to a possibly
         // aliasing pointer: one round trip per float4 otherwise - 20 k clk per tile in this epilogue before)
         float4 bb[8], old[8];
-        const float* src = to_h ? c.h_in + (size_t)r * H + col : c.skip + (size_t)r * H + col;
+        const size_t plane = (size_t)c.R * 4;          // floats between consecutive 4-channel planes
+        const size_t off = (size_t)(col / 4) * plane + (size_t)r * 4;
+        const float* src = (to_h ? c.h_in : c.skip) + off;
         const bool need_old = valid && (to_h || !c.first);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           bb[g] = __ldg(reinterpret_cast<const float4*>(bias + 4 * g));
-          old[g] = need_old ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          old[g] = need_old ? *reinterpret_cast<const float4*>(src + g * plane) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float* dst = to_h ? c.h_out + (size_t)r * H + col : c.skip + (size_t)r * H + col;
+        float* dst = (to_h ? c.h_out : c.skip) + off;
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(dst + 4 * g) =
+            *reinterpret_cast<float4*>(dst + g * plane) =
                 make_float4(__uint_as_float(v[4 * g]) + bb[g].x + old[g].x, __uint_as_float(v[4 * g + 1]) + bb[g].y + old[g].y,
                             __uint_as_float(v[4 * g + 2]) + bb[g].z + old[g].z, __uint_as_float(v[4 * g + 3]) + bb[g].w + old[g].w);
         } else if (to_h || c.first) {                  // gap rows: h' = 0; skip zeroed when assigned, untouched otherwise
 #pragma unroll
-          for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(dst + g * plane) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       tc_fence_before();
@@ -335,7 +326,48 @@ __global__ void __launch_bounds__(kThreads, 1) umma_wn_kernel(const __grid_const
   }
 }
 
+// [R][C] fp32 row-major <-> planar [C/4][R][4]: a block moves 32 rows; both sides of the transpose are coalesced
+__global__ void __launch_bounds__(256) rows_planar4_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C,
+                                                           int to_planar) {
+  __shared__ float4 tile[32][49];                      // C / 4 <= 48 planes (+1: conflict-free column reads)
+  const int r0 = blockIdx.x * 32, P = C / 4;
+  if (to_planar) {
+    for (int k = threadIdx.x; k < 32 * P; k += blockDim.x) {
+      const int r = k / P, p = k % P;
+      tile[r][p] = (r0 + r < R) ? *reinterpret_cast<const float4*>(in + (size_t)(r0 + r) * C + 4 * p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 32 * P; k += blockDim.x) {
+      const int p = k / 32, r = k % 32;
+      if (r0 + r < R) *reinterpret_cast<float4*>(out + ((size_t)p * R + r0 + r) * 4) = tile[r][p];
+    }
+  } else {
+    for (int k = threadIdx.x; k < 32 * P; k += blockDim.x) {
+      const int p = k / 32, r = k % 32;
+      tile[r][p] = (r0 + r < R) ? *reinterpret_cast<const float4*>(in + ((size_t)p * R + r0 + r) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 32 * P; k += blockDim.x) {
+      const int r = k / P, p = k % P;
+      if (r0 + r < R) *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * C + 4 * p) = tile[r][p];
+    }
+  }
+}
+
 }  // namespace
+
+int rows_to_planar4(const float* in, float* out, int R, int C, cudaStream_t st) {
+  VS_REQUIRE(C % 4 == 0 && C <= 192 && R > 0, "rows_to_planar4: C=%d", C);
+  rows_planar4_kernel<<<(R + 31) / 32, 256, 0, st>>>(in, out, R, C, 1);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
+int planar4_to_rows(const float* in, float* out, int R, int C, cudaStream_t st) {
+  VS_REQUIRE(C % 4 == 0 && C <= 192 && R > 0, "planar4_to_rows: C=%d", C);
+  rows_planar4_kernel<<<(R + 31) / 32, 256, 0, st>>>(in, out, R, C, 0);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
 
 int umma_wn_layer(const UmmaWn& c, cudaStream_t st) {
   VS_REQUIRE(c.h_in && c.skip && c.w_in && c.b_in && c.w_rs && c.b_rs && (c.last || c.h_out), "umma_wn_layer: null pointer");
