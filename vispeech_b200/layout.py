@@ -73,7 +73,11 @@ def make_rows(lengths: Sequence[int], sids: Sequence[int], gap: int, device) -> 
     for b in range(lengths.size):
         row_utt[starts[b]:starts[b] + lengths[b]] = b
     meta = np.concatenate([row_utt, starts, lengths, np.asarray(sids, dtype=np.int32)])
-    meta_dev = torch.from_numpy(meta).to(device, non_blocking=False)
+    # pinned + asynchronous: a blocking copy would make the host wait for everything already queued on this stream (in the
+    # engine's throughput mode that is the previous call's latent stage, which shares the SMs with a decoder - the host then
+    # falls behind and the GPU idles; seen as sporadic 20-40 % slower end-to-end runs)
+    meta_host = torch.from_numpy(meta).pin_memory() if torch.cuda.is_available() else torch.from_numpy(meta)
+    meta_dev = meta_host.to(device, non_blocking=True)
     B = lengths.size
     d_row_utt = meta_dev[:n_rows]
     d_start = meta_dev[n_rows:n_rows + B]
@@ -82,4 +86,6 @@ def make_rows(lengths: Sequence[int], sids: Sequence[int], gap: int, device) -> 
     st = VsRows(n_utt=B, n_rows=n_rows, max_len=max(1, int(lengths.max())), reserved=0,
                 row_utt=d_row_utt.data_ptr(), utt_start=d_start.data_ptr(), utt_len=d_len.data_ptr(),
                 sid=d_sid.data_ptr())
-    return RaggedRows(lengths, starts, n_rows, row_utt, d_row_utt, d_start, d_len, d_sid, st)
+    rows = RaggedRows(lengths, starts, n_rows, row_utt, d_row_utt, d_start, d_len, d_sid, st)
+    rows.meta_host = meta_host          # keeps the staging buffer referenced with the layout
+    return rows

@@ -472,10 +472,9 @@ class Prepared:
 
 
 def _upload(a: np.ndarray, dev) -> torch.Tensor:
-    t = torch.from_numpy(a)
-    if t.numel() > 4096:
-        t = t.pin_memory()
-    return t.to(dev, non_blocking=True)
+    # always through pinned memory: a copy from pageable memory first synchronises the stream it is queued on, i.e. the
+    # host would wait for whatever the previous call left there (see layout.make_rows)
+    return torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)
 
 
 def load_checkpoint(checkpoint_path: str, model: SynthesizerTrn, optimizer=None, skip_optimizer: bool = False):
