@@ -149,11 +149,28 @@ def run_reference(args):
                              len(utts), audio, args.steps)},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL's version banner, library chatter) has been
+    diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)                   # keep stdout for the JSON line only
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -322,7 +339,7 @@ def main():
                                     "kind": "port",
                                     "sample": "first %d utterances of the batch (%.1f audio-s), oracle port, "
                                               "per-utterance batch-1 loop, 1 warm-up" % (len(sample), oin.audio_seconds(sample))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
