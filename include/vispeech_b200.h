@@ -81,10 +81,18 @@ int64_t vs_launch_count(void);
  * "tf32_prior": 0 (default) = the frame prior network and the (m_p, logs_p) projection use 3xTF32 at every size (prior
  * sampling amplifies their error), 1 = plain TF32 above tf32_min_rows like the flow (A/B measurements).
  * "fused_respair": 0 = never, 1 = only the C=32 stage's ResBlock iterations run as one fused conv-pair kernel,
- * 2 (default) = wherever both weight sets fit in shared memory (C=32 all k, C=64 k=3,7).
- * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 296*12 int64 where the tcgen05 conv kernel
- * leaves per-CTA clocks spent waiting on each mbarrier (tools/conv_timing.py). */
-int vs_set_option(const char* name, int64_t value);   /* kernels launched by this library so far (process-wide) */
+ * 2 (default) = wherever both weight sets fit in shared memory (C=32 and C=64, all k; C=64 k=11 in its TIGHT form).
+ * "attention_mma": 1 (default) = sequences of >= 128 rows use the 3xTF32 tensor-core attention kernel, shorter ones the
+ * fp32 CUDA-core kernel; 0 = always CUDA cores, 2 = always tensor cores, 3 = tensor cores in plain TF32 (A/B only).
+ * "wn_fused": 1 (default) = on the plain-TF32 route every WN layer is ONE kernel on planar fp32 state (csrc/umma_wn.cu),
+ * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
+ * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast
+ * (bit-identical; no gain measured).  "decoder_streams": 1 (default) | 2 = the k=11 ResBlock chains of each decoder stage
+ * run on a side stream (no gain measured).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).
+ * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 148*24 int64 where the tcgen05 kernels built with
+ * -DVS_UMMA_TIMING leave per-CTA clocks spent waiting on each mbarrier (tools/conv_timing.py, tf32_timing.py, wn_timing.py).
+ * One CUDA device per process (the library caches per-kernel attributes process-wide), as torchrun launches it. */
+int vs_set_option(const char* name, int64_t value);
 
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
  * Tensors are registered by name in the PACKED layouts listed in vispeech_b200/packing.py
