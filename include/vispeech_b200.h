@@ -183,6 +183,15 @@ int vs_op_rel_attention(const VsRows* rows, const float* qkv /*[n_rows][576]*/, 
 int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,
                       int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
                       int32_t split3, const int32_t* row_utt, void* stream);
+/* One WN layer (modules.py:153-176) in one kernel, plain TF32 (csrc/umma_wn.cu): acts = tanh.sigmoid(in_layer(h) + cond[sid]);
+ * rs = res_skip(acts); h_out = (h + rs[:, :192]) on valid rows, 0 on gap rows; skip = (first ? 0 : skip) + rs[:, 192:] (the
+ * last layer's res_skip has 192 outputs, all skip; h_out may be NULL).  h_in / h_out / skip are row-major [n_rows][192] here
+ * (the model keeps them planar across the stack); w_in_packed: gate-interleaved columns (packing.gate_columns), pack_tf32
+ * slabs; cond: [n_spk][cond_ld] rows of this layer's 384 gate-interleaved columns; ws >= 3 * n_rows * 192 floats. */
+int vs_op_wn_layer(const float* h_in, const float* w_in_packed, const float* b_in, const float* cond, int32_t cond_ld,
+                   const int32_t* cond_idx, const float* w_rs_packed, const float* b_rs, const int32_t* row_utt,
+                   int32_t n_rows, int32_t first, int32_t last, float* h_out, float* skip, void* ws, int64_t ws_bytes,
+                   void* stream);
 /* bf16 tcgen05 implicit-GEMM conv on planar [C/8][n_rows][8] activations (csrc/umma_conv.cu):
  * y = conv(in) + bias + res;  out_raw = y;  out_act = leaky_relu(y*act_scale, act_slope); either output may be
  * null.  up > 1 = polyphase ConvTranspose1d (column gn -> phase gn/Cout, output row up*r+phase). */

@@ -257,3 +257,59 @@ def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     for b, ref in enumerate(refs):
         s = rows.starts[b]
         assert (out[s:s + lengths[b]].cpu() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("R,first,last", [(300, 1, 0), (1000, 0, 0), (4229, 0, 1), (129, 1, 1)])
+def test_wn_layer_kernel_matches_cpu(G, R, first, last):
+    """The one-kernel WN layer (modules.py:153-176: in_layer k5 -> + cond(g) -> tanh.sigmoid -> res_skip 1x1 -> h / skip
+    update) vs an fp64 statement with the kernel's operand roundings (h truncated to TF32 by the MMA, weights and the gate
+    output rounded to TF32), incl. gap rows, per-speaker cond rows, first / last layer forms and odd tile counts."""
+    from vispeech_b200 import _lib
+    from vispeech_b200.packing import gate_columns, pack_tf32, round_tf32
+    lib = _lib.load()
+    H = 192
+    g = torch.Generator().manual_seed(R + 2 * first + last)
+    h = torch.randn(R, H, generator=g)
+    skip0 = torch.randn(R, H, generator=g)
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    row_utt[R // 2:] = 1
+    row_utt[40:47] = -1
+    h[40:47] = 0                                                 # ragged-rows invariant: gap rows of the input are zero
+    w_in = torch.randn(5, H, 2 * H, generator=g) / (5 * H) ** 0.5
+    b_in = torch.randn(2 * H, generator=g) * 0.1
+    cond = torch.randn(3, 2 * H, generator=g) * 0.3             # 3 "speakers", this layer's columns
+    sid = torch.tensor([2, 0], dtype=torch.int32)
+    n_rs = H if last else 2 * H
+    w_rs = torch.randn(1, H, n_rs, generator=g) / H ** 0.5
+    b_rs = torch.randn(n_rs, generator=g) * 0.1
+    perm = gate_columns(H)
+    dev = G.DEV
+    args = dict(w_in=pack_tf32(w_in[:, :, perm].contiguous()).to(dev), b_in=b_in[perm].contiguous().to(dev),
+                cond=cond[:, perm].contiguous().to(dev), w_rs=pack_tf32(w_rs).to(dev), b_rs=b_rs.to(dev))
+    d_h, d_skip = h.to(dev), skip0.clone().to(dev)
+    d_sid, d_row_utt = sid.to(dev), row_utt.to(dev)              # keep the device copies alive across the call
+    d_out = torch.full((R, H), float("nan"), device=dev)
+    ws = torch.empty(3 * R * H * 4 + 4096, dtype=torch.uint8, device=dev)
+    _lib.check(lib.vs_op_wn_layer(d_h.data_ptr(), args["w_in"].data_ptr(), args["b_in"].data_ptr(), args["cond"].data_ptr(), 2 * H,
+                                  d_sid.data_ptr(), args["w_rs"].data_ptr(), args["b_rs"].data_ptr(),
+                                  d_row_utt.data_ptr(), R, first, last, None if last else d_out.data_ptr(),
+                                  d_skip.data_ptr(), ws.data_ptr(), ws.numel(), G.stream()), "vs_op_wn_layer")
+    torch.cuda.synchronize()
+    # reference
+    h_tr = (h.view(torch.int32) & ~0x1FFF).view(torch.float32)   # the MMA reads the top 19 bits of the fp32 words
+    a = G.ref_conv_rows(h_tr, round_tf32(w_in), b_in, dil=1, pad_l=2)
+    valid = row_utt >= 0
+    a = a + cond[sid.long()[row_utt.clamp_min(0).long()]].double()
+    acts = torch.tanh(a[:, :H]) * torch.sigmoid(a[:, H:])
+    acts[~valid] = 0
+    rs = round_tf32(acts.float()).double() @ round_tf32(w_rs)[0].double() + b_rs.double()
+    skip_ref = (torch.zeros(R, H, dtype=torch.float64) if first else skip0.double()) + (rs if last else rs[:, H:])
+    if first:
+        skip_ref[~valid] = 0
+    else:
+        skip_ref[~valid] = skip0[~valid].double()
+    assert (d_skip.cpu().double() - skip_ref).abs().max().item() <= 2e-3
+    if not last:
+        h_ref = h.double() + rs[:, :H]
+        h_ref[~valid] = 0
+        assert (d_out.cpu().double() - h_ref).abs().max().item() <= 2e-3

@@ -640,6 +640,27 @@ int vs_mel_spectrogram(const VsRows* rows, const float* wave, int32_t t_max, con
   return VS_OK;
 }
 
+// op-level hook for the one-kernel WN layer (csrc/umma_wn.cu): row-major in / out, planar inside, like wn_forward uses it
+int vs_op_wn_layer(const float* h_in, const float* w_in_packed, const float* b_in, const float* cond, int32_t cond_ld,
+                   const int32_t* cond_idx, const float* w_rs_packed, const float* b_rs, const int32_t* row_utt,
+                   int32_t n_rows, int32_t first, int32_t last, float* h_out, float* skip, void* ws, int64_t ws_bytes,
+                   void* stream) {
+  VS_REQUIRE(h_in && skip && ws && n_rows > 0, "vs_op_wn_layer: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vs::Workspace w(ws, ws_bytes);
+  const int64_t n = (int64_t)n_rows * vs::kHidden;
+  float *hp = w.take<float>(n), *ho = w.take<float>(n), *sp = w.take<float>(n);
+  if (!w.ok) { vs::set_error("vs_op_wn_layer: workspace too small"); return VS_ERR_WORKSPACE; }
+  VS_TRY(vs::rows_to_planar4(h_in, hp, n_rows, vs::kHidden, st));
+  if (!first) VS_TRY(vs::rows_to_planar4(skip, sp, n_rows, vs::kHidden, st));
+  vs::UmmaWn u;
+  u.h_in = hp; u.h_out = ho; u.skip = sp; u.w_in = w_in_packed; u.b_in = b_in; u.cond = cond; u.cond_ld = cond_ld;
+  u.cond_idx = cond_idx; u.w_rs = w_rs_packed; u.b_rs = b_rs; u.row_utt = row_utt; u.R = n_rows; u.first = first; u.last = last;
+  VS_TRY(vs::umma_wn_layer(u, st));
+  if (!last) { VS_REQUIRE(h_out, "vs_op_wn_layer: h_out missing"); VS_TRY(vs::planar4_to_rows(ho, h_out, n_rows, vs::kHidden, st)); }
+  return vs::planar4_to_rows(sp, skip, n_rows, vs::kHidden, st);
+}
+
 int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,
                       void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
