@@ -36,7 +36,7 @@ extern "C" {
 #define VS_ERR_WORKSPACE 4    /* workspace too small */
 
 #define VS_DTYPE_F32 0
-#define VS_DTYPE_BF16 1
+#define VS_DTYPE_F16 1
 #define VS_DTYPE_I64 2
 #define VS_DTYPE_F64 3
 
@@ -97,7 +97,7 @@ int vs_set_option(const char* name, int64_t value);
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
  * Tensors are registered by name in the PACKED layouts listed in vispeech_b200/packing.py
  * (folded weight norm, [tap][Cin][Cout] fp32 conv weights, per-speaker conditioning tables,
- * planar bf16 decoder weights).  The model keeps the pointers; the caller keeps ownership. */
+ * planar f16 decoder weights).  The model keeps the pointers; the caller keeps ownership. */
 int vs_model_create(const VsConfig* cfg, VsModel** out);
 void vs_model_destroy(VsModel* m);
 int vs_model_set_tensor(VsModel* m, const char* name, const void* ptr, int64_t numel, int32_t dtype);
@@ -145,7 +145,7 @@ int vs_posterior_encode(const VsModel* m, const VsRows* rows_f, const float* spe
 int vs_flow_forward(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- a18: HiFi-GAN Generator (models.py:271-290).  max_len < 0 = no truncation (models.py:720).
- * wave_out is [rows_f.n_rows * hop] in ragged order.  precision: 0 = bf16 tcgen05 path (product),
+ * wave_out is [rows_f.n_rows * hop] in ragged order.  precision: 0 = f16 tcgen05 path (product),
  * 1 = fp32 SIMT path (test-only cross-check of the same math, NOT a fallback). */
 int vs_hifigan_decode(const VsModel* m, const VsRows* rows_f, const float* z, int32_t max_len, float* wave_out,
                       int32_t precision, void* ws, int64_t ws_bytes, void* stream);
@@ -192,7 +192,7 @@ int vs_op_wn_layer(const float* h_in, const float* w_in_packed, const float* b_i
                    const int32_t* cond_idx, const float* w_rs_packed, const float* b_rs, const int32_t* row_utt,
                    int32_t n_rows, int32_t first, int32_t last, float* h_out, float* skip, void* ws, int64_t ws_bytes,
                    void* stream);
-/* bf16 tcgen05 implicit-GEMM conv on planar [C/8][n_rows][8] activations (csrc/umma_conv.cu):
+/* f16 tcgen05 implicit-GEMM conv on planar [C/8][n_rows][8] activations (csrc/umma_conv.cu):
  * y = conv(in) + bias + res;  out_raw = y;  out_act = leaky_relu(y*act_scale, act_slope); either output may be
  * null.  up > 1 = polyphase ConvTranspose1d (column gn -> phase gn/Cout, output row up*r+phase). */
 int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar,
@@ -200,7 +200,7 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
                       const int32_t* row_utt, int32_t row_div, void* stream);
 
-/* fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x (+ res2) on planar bf16 rows (csrc/umma_respair.cu) */
+/* fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x (+ res2) on planar f16 rows (csrc/umma_respair.cu) */
 int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
                   const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
                   int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream);

@@ -53,8 +53,13 @@ def build_reference(sd, with_vc=False):
     return net
 
 
+ONLY = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]     # e.g. --only=c1 regenerates one fixture
+
+
 def run_case(net, name, ids, sid, noise_scale, noise, max_len=None, energy_control=None, pitch_control=None,
              duration_control=None):
+    if ONLY and name not in ONLY:
+        return
     taps = {}
     h1 = net.enc_p.register_forward_hook(lambda m, i, o: taps.__setitem__("x_enc", o[0][0].clone()))
     h2 = net.lr.register_forward_hook(lambda m, i, o: taps.__setitem__("x_lr", o[0][0].clone()))
@@ -90,7 +95,7 @@ def run_case(net, name, ids, sid, noise_scale, noise, max_len=None, energy_contr
     dc, dk = ctl(duration_control)
     pc, pk = ctl(pitch_control)
     ec, ek = ctl(energy_control)
-    big = o.numel() > 100_000
+    big = o.numel() > 100_000          # C1: drop regenerable / redundant taps, keep the waveform in fp32
     out = dict(
         ids=ids.numpy(), sid=np.int64(sid), noise_scale=np.float64(noise_scale), noise=noise.numpy(),
         max_len=np.int64(-1 if max_len is None else max_len),
@@ -99,9 +104,10 @@ def run_case(net, name, ids, sid, noise_scale, noise, max_len=None, energy_contr
         x_enc=taps["x_enc"].numpy(), x_lr=taps["x_lr"].numpy(),
         x_mask=x_mask[0, 0].numpy(), z=z[0].numpy(), z_p=z_p[0].numpy(), m_p=m_p[0].numpy(), logs_p=logs_p[0].numpy(),
         duration=duration.reshape(-1).numpy(), F0=F0.reshape(-1).numpy(), energy=energy.reshape(-1).numpy(),
-        o_is_f16x64=np.int64(big),
-        # big case: waveform stored as fp16 of 64*o (|o| ~ 0.02 at random init) to keep the fixture small
-        o=(o[0, 0] * 64).half().numpy() if big else o[0, 0].numpy(),
+        # the waveform is stored in fp32 for every case: an fp16 copy (used in round 1 for C1) alone costs 8e-3 of the
+        # 1e-2 log-mel budget of tests/test_gpu_infer.py::test_c1_log_mel_of_waveform
+        o_is_f16x64=np.int64(0),
+        o=o[0, 0].numpy(),
     )
     if big:   # regenerable (oracle.inputs.draw_noise([Tf], 100)) or redundant: keep the fixture small
         for k in ("noise", "x_lr", "logs_p", "z_p"):

@@ -17,19 +17,19 @@ def stream():
 
 
 def to_planar(x: torch.Tensor) -> torch.Tensor:
-    """[R][C] fp32 -> planar bf16 [C/8][R][8] (on the same device)."""
+    """[R][C] fp32 -> planar f16 [C/8][R][8] (on the same device)."""
     R, C = x.shape
-    return x.to(torch.bfloat16).reshape(R, C // 8, 8).permute(1, 0, 2).contiguous()
+    return x.to(torch.float16).reshape(R, C // 8, 8).permute(1, 0, 2).contiguous()
 
 
 def from_planar(p: torch.Tensor) -> torch.Tensor:
-    """planar bf16 [C/8][R][8] -> [R][C] fp32."""
+    """planar f16 [C/8][R][8] -> [R][C] fp32."""
     P, R, _ = p.shape
     return p.permute(1, 0, 2).reshape(R, P * 8).float()
 
 
-def bf16_round(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).float()
+def f16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.float16).float()
 
 
 def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0, act_scale=1.0, row_utt=None,
@@ -41,8 +41,8 @@ def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0
     cout = n // up
     xin = to_planar(x)
     wp = pack_umma(w_tcn.cpu()).to(x.device)
-    raw = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.bfloat16, device=x.device) if want_raw else None
-    act = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.bfloat16, device=x.device) if want_act else None
+    raw = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.float16, device=x.device) if want_raw else None
+    act = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.float16, device=x.device) if want_act else None
     resp = to_planar(res) if res is not None else None
     check(lib.vs_op_conv1d_umma(ptr(xin), ptr(wp), ptr(bias), ptr(resp), ptr(raw), ptr(act), R, cin, n, taps, dil, pad_l,
                                 up, float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()),
@@ -52,7 +52,7 @@ def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0
 
 
 def respair(x, w1, w2, b1, b2, dil, res2=None, act_slope=1.0, act_scale=1.0, row_utt=None, row_div=1):
-    """Fused ResBlock1 iteration on planar bf16 rows.  x = the ACTIVATED input a = lrelu(x_raw) [R][C] fp32 device,
+    """Fused ResBlock1 iteration on planar f16 rows.  x = the ACTIVATED input a = lrelu(x_raw) [R][C] fp32 device,
     w [k][C][C].  Returns (raw, act) [R][C]."""
     lib = _lib.load()
     R, C = x.shape
@@ -60,8 +60,8 @@ def respair(x, w1, w2, b1, b2, dil, res2=None, act_slope=1.0, act_scale=1.0, row
     xin = to_planar(x)
     w1p, w2p = pack_umma(w1.cpu()).to(x.device), pack_umma(w2.cpu()).to(x.device)
     r2 = to_planar(res2) if res2 is not None else None
-    raw = torch.full((C // 8, R, 8), float("nan"), dtype=torch.bfloat16, device=x.device)
-    act = torch.full((C // 8, R, 8), float("nan"), dtype=torch.bfloat16, device=x.device)
+    raw = torch.full((C // 8, R, 8), float("nan"), dtype=torch.float16, device=x.device)
+    act = torch.full((C // 8, R, 8), float("nan"), dtype=torch.float16, device=x.device)
     check(lib.vs_op_respair(ptr(xin), ptr(w1p), ptr(w2p), ptr(b1), ptr(b2), ptr(r2), ptr(raw), ptr(act), R, C, k, dil,
                             float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()), "vs_op_respair")
     torch.cuda.synchronize()

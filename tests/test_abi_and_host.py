@@ -69,7 +69,7 @@ def test_packing_shapes_and_flow_flip(state_dict):
     assert p["enc_p.encoder.0.wqkv"].shape == (192, 576)
     assert p["dec.ups.0.w"].shape == (8, 2, 512, 256) and p["dec.ups.2.w"].shape == (4, 1, 128, 64)
     assert [ups_union_taps(i) for i in range(4)] == [(3, 1), (3, 1), (1, 0), (3, 1)]
-    assert p["dec16.ups.0.w"].numel() == 3 * 512 * 2048 and p["dec16.ups.0.w"].dtype == torch.bfloat16
+    assert p["dec16.ups.0.w"].numel() == 3 * 512 * 2048 and p["dec16.ups.0.w"].dtype == torch.float16
     # flow 1 and 3 run on a flipped tensor: pre reads reversed upper-half channels, post writes reversed lower half
     w = state_dict["flow.flows.2.pre.weight"][:, :, 0]            # [192 co, 96 ci]
     assert torch.equal(p["flow.1.pre.w"], torch.flip(w.t(), [0]))

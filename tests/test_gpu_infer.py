@@ -2,7 +2,7 @@
 unmodified reference and (b) the CPU oracle on seeded synthetic batches.
 
 Bars (BASELINE.json north_star): length-regulator indices exact; mel/latent max-abs <= 1e-2; waveform SNR >= 30 dB.
-The fp32 cross-check decoder (precision=1) is additionally held to 1e-3 so that a bf16-path failure can be told
+The fp32 cross-check decoder (precision=1) is additionally held to 1e-3 so that a fp16-path failure can be told
 apart from an upstream one."""
 import glob
 import os
@@ -65,7 +65,7 @@ def run_golden(net, d, precision):
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_bf16"])
+@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_f16"])
 def test_infer_matches_reference_golden(net, path, precision):
     d = dict(np.load(path))
     o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = run_golden(net, d, precision)
@@ -85,7 +85,7 @@ def test_infer_matches_reference_golden(net, path, precision):
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_infer_matches_reference_golden_tf32(net, path, force_tf32):
-    """Same golden cases with the frame-level AND phoneme-level GEMMs forced onto the TF32 tensor-core kernel + bf16
+    """Same golden cases with the frame-level AND phoneme-level GEMMs forced onto the TF32 tensor-core kernel + fp16
     decoder: the product precision for large batches.  Bars of BASELINE.json: latents <= 1e-2, waveform SNR >= 30 dB."""
     d = dict(np.load(path))
     o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = run_golden(net, d, 0)
@@ -171,7 +171,7 @@ def test_length_regulator_indices_exact_c5(net, state_dict):
     assert (idx[gaps] == -1).all()
 
 
-@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_bf16"])
+@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_f16"])
 def test_batch_matches_per_utterance_oracle(net, state_dict, precision):
     """A ragged batch (different Tp, Tf, speakers; predicted pitch/energy, given durations) must equal per-utterance
     batch-1 oracle runs: pads and neighbours never leak."""
@@ -305,24 +305,20 @@ def test_pcm16_postprocess_and_serving_queue(net):
         assert got.shape == ref.shape and np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= 1
 
 
-@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_bf16"])
+@pytest.mark.parametrize("precision", [1, 0], ids=["dec_fp32", "dec_f16"])
 def test_c1_log_mel_of_waveform(net, precision):
-    """Log-mel (reference mel_processing.py:85-112, the metric train.py logs) of our C1 waveform vs the reference's.
-    fp32 decoder: within 1e-2 max-abs.  bf16 decoder (40-50 dB SNR): the quiet top mel bands (log-mel ~ -7, i.e. 1e-3
-    linear) see the bf16 noise floor, so the bar there is mean-abs <= 1e-2 and max-abs <= 0.15; the 1e-2 max-abs bar of
-    BASELINE.json is met on the latents (m_p, z), which is where the decoder's input is fixed."""
-    from oracle import inputs as oin
+    """Log-mel (reference mel_processing.py:85-112, the metric train.py logs) of our C1 waveform vs the reference's own
+    (fp32 fixture): BASELINE.json's "mel within 1e-2 max abs", unrelaxed, for BOTH decoders.  The product decoder meets it
+    because (a) its operands are fp16, not bf16, and (b) the last MRF stage keeps its residual stream, the MRF sum and the
+    conv_post input in fp32 on chip (csrc/umma_mrf.cu): rounding on that direct signal path was 9/10 of the error."""
     from oracle.metrics import mel_spectrogram
     d = dict(np.load([p for p in GOLDEN if p.endswith("c1.npz")][0]))
     o, *_ = run_golden(net, d, precision)
-    ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
+    ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d["o_is_f16x64"]) else 1)
     m_ref, m_got = mel_spectrogram(ref), mel_spectrogram(o[0, 0].cpu())
     err = (m_ref - m_got).abs()
     print("precision", precision, "log-mel max-abs %.4f mean-abs %.5f" % (float(err.max()), float(err.mean())))
-    if precision == 1:
-        assert float(err.max()) <= 1e-2        # includes the fp16 storage error of the fixture
-    else:
-        assert float(err.mean()) <= 1e-2 and float(err.max()) <= 0.15
+    assert float(err.max()) <= 1e-2
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -337,7 +333,7 @@ def test_unfused_resblock_paths_still_match(net, mode):
         o, *_ = run_golden(net, d, 0)
     finally:
         _lib.check(lib.vs_set_option(b"fused_respair", 2))
-    ref = torch.from_numpy(d["o"].astype(np.float32)) / 64
+    ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d["o_is_f16x64"]) else 1)
     assert snr_db(ref, o[0, 0].cpu()) >= 30.0
 
 

@@ -11,10 +11,10 @@ buf = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
 
 
 def run(name, R, cin, n, taps, dil):
-    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.float16)
     b = torch.randn(n, device=dev)
-    o1 = torch.empty(n // 8, R, 8, device=dev, dtype=torch.bfloat16)
+    o1 = torch.empty(n // 8, R, 8, device=dev, dtype=torch.float16)
 
     def call():
         check(lib.vs_op_conv1d_umma(ptr(x), ptr(w), ptr(b), None, None, ptr(o1), R, cin, n, taps, dil, (taps - 1) // 2, 1, 0.1, 1.0, None, 1, st))
@@ -41,9 +41,9 @@ def run(name, R, cin, n, taps, dil):
 
 
 def run_pair(name, R, C, k, d):
-    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
-    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
+    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
     b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
     o = torch.empty_like(x)
 

@@ -8,9 +8,9 @@ from vispeech_b200._lib import check, ptr
 lib = _lib.load(); dev = "cuda:0"
 R, C = 27840 * 512, 32
 def mk(k):
-    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
-    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
+    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
     return x, w1, w2, torch.randn(C, device=dev), torch.randn(C, device=dev), torch.empty_like(x)
 A, B = mk(int(sys.argv[1]) if len(sys.argv) > 1 else 3), mk(int(sys.argv[2]) if len(sys.argv) > 2 else 11)
 ka, kb = A[1].numel() // (C * C), B[1].numel() // (C * C)

@@ -1,6 +1,6 @@
 // tcgen05.mma rate microbenchmark (sm_100a).  One issuing warp, one accumulator chain per CTA, operands are
 // uninitialised shared memory - only the timing matters.  Two questions:
-//   1. cycles per MMA (M=128, K=16, bf16) as a function of N with fixed operand addresses (tensor / smem floors);
+//   1. cycles per MMA (M=128, K=16, f16) as a function of N with fixed operand addresses (tensor / smem floors);
 //   2. the same with the conv kernel's real descriptor walk: A start offset = tap*dil rows (16 B each) + K-chunk
 //      planes `rows_a` rows apart (LBO), B walking through contiguous weight slabs.
 // Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -I vispeech_b200/csrc -o tools/_bin/mma_mb tools/mma_microbench.cu
@@ -69,7 +69,7 @@ __device__ __forceinline__ void walk_unrolled(const Walk& w, uint32_t tm, uint32
         uint32_t a_lo = a_tap;
 #pragma unroll
         for (int ks = 0; ks < NK; ++ks) {
-          tc_mma_bf16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+          tc_mma_f16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
           accumulate = 1;
           a_lo += a_kstep;
           b_lo += b_kstep;
@@ -109,12 +109,12 @@ __global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) { done_flag = 0; mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  if (w.fill) {   // operands: 0 = whatever is there, 1 = zeros, 2 = pseudo-random bf16 in [-1, 1)
+  if (w.fill) {   // operands: 0 = whatever is there, 1 = zeros, 2 = pseudo-random f16 in [-1, 1)
     uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
     uint32_t x = 1234567u + threadIdx.x * 7919u + blockIdx.x * 104729u;
     for (int i = threadIdx.x; i < 190 * 256; i += blockDim.x) {
       x = x * 1664525u + 1013904223u;
-      const uint32_t lo = 0x3F000000u | ((x >> 9) & 0x007F0000u) | (x & 0x80000000u);      // +-[0.5,1) bf16 in the high half
+      const uint32_t lo = 0x3F000000u | ((x >> 9) & 0x007F0000u) | (x & 0x80000000u);      // +-[0.5,1) f16 in the high half
       const uint32_t hi = 0x3F000000u | ((x << 3) & 0x007F0000u) | ((x << 7) & 0x80000000u);
       s32[i] = w.fill == 1 ? 0u : ((lo >> 16) | (hi & 0xFFFF0000u));
     }
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_
         for (int t = 0; t < taps; ++t, a_tap += dil) {
           uint32_t a_lo = a_tap;
           for (int ks = 0; ks < nks; ++ks) {
-            tc_mma_bf16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+            tc_mma_f16_lohi(tm, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
             accumulate = 1;
             a_lo += a_kstep;
             b_lo += b_kstep;

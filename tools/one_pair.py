@@ -7,9 +7,9 @@ from vispeech_b200._lib import check, ptr
 lib = _lib.load(); dev = "cuda:0"; st = torch.cuda.current_stream().cuda_stream
 R, C, k, d = [int(a) for a in sys.argv[1:5]]
 check(lib.vs_set_option(b"fused_respair", 2))
-x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
-w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
+w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
 b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
 o = torch.empty_like(x)
 for _ in range(3):

@@ -11,10 +11,10 @@ from vispeech_b200._lib import check, ptr
 lib = _lib.load(); dev = "cuda:0"; st = torch.cuda.current_stream().cuda_stream
 
 def run(name, R, cin, n, taps, dil):
-    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.float16)
     b = torch.randn(n, device=dev)
-    o1 = torch.empty(n // 8, R, 8, device=dev, dtype=torch.bfloat16)
+    o1 = torch.empty(n // 8, R, 8, device=dev, dtype=torch.float16)
     pad_l = (taps - 1) // 2
     def call():
         check(lib.vs_op_conv1d_umma(ptr(x), ptr(w), ptr(b), None, None, ptr(o1), R, cin, n, taps, dil, pad_l, 1, 0.1, 1.0, None, 1, st))

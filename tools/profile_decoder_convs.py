@@ -19,11 +19,11 @@ st = torch.cuda.current_stream().cuda_stream
 
 def run(name, R, cin, n, taps, dil, up=1, res=False, two_out=False, count=1):
     cout = n // up
-    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(cin // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w = (torch.randn(taps * cin * n, device=dev) / (cin * taps) ** 0.5).to(torch.float16)
     b = torch.randn(cout, device=dev)
-    r = (torch.randn(cout // 8, R * up, 8, device=dev)).to(torch.bfloat16) if res else None
-    o1 = torch.empty(cout // 8, R * up, 8, device=dev, dtype=torch.bfloat16)
+    r = (torch.randn(cout // 8, R * up, 8, device=dev)).to(torch.float16) if res else None
+    o1 = torch.empty(cout // 8, R * up, 8, device=dev, dtype=torch.float16)
     o2 = torch.empty_like(o1) if two_out else None
     pad_l = (taps - 1) // 2
 
@@ -72,9 +72,9 @@ print("sum of decoder convs: %.2f ms" % total)
 
 
 def run_pair(name, R, C, k, d, count=1):
-    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.bfloat16)
-    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
-    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.bfloat16)
+    x = (torch.randn(C // 8, R, 8, device=dev) * 0.5).to(torch.float16)
+    w1 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
+    w2 = (torch.randn(k * C * C, device=dev) / (C * k) ** 0.5).to(torch.float16)
     b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
     o = torch.empty_like(x)
 

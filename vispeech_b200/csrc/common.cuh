@@ -1,7 +1,7 @@
 // Shared helpers for the vispeech_b200 CUDA sources (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>

@@ -1,5 +1,5 @@
 // HiFi-GAN Generator.forward (reference models.py:271-290; ResBlock1.forward modules.py:210-223).
-// decode_f32: the same math on the fp32 CUDA-core conv - a test-only cross-check of the bf16 tcgen05
+// decode_f32: the same math on the fp32 CUDA-core conv - a test-only cross-check of the f16 tcgen05
 // decoder (decoder_umma.cu), selected explicitly with precision=1; never an automatic fallback.
 #include "decoder.cuh"
 #include "ops_misc.cuh"
@@ -8,7 +8,7 @@ namespace vs {
 
 int resolve_decoder(const FetchFn& fetch, int n_speakers, DecoderW* d) {
 #define DF32(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_F32, reinterpret_cast<const void**>(&(field))))
-#define DBF16(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_BF16, reinterpret_cast<const void**>(&(field))))
+#define DF16(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_F16, reinterpret_cast<const void**>(&(field))))
   DF32(d->pre.w, "dec.pre.w", 7 * 192 * 512);
   DF32(d->pre.b, "dec.pre.b", 512);
   DF32(d->cond_tab, "dec.cond_tab", (int64_t)n_speakers * 512);
@@ -30,13 +30,13 @@ int resolve_decoder(const FetchFn& fetch, int n_speakers, DecoderW* d) {
       }
     }
   }
-  return resolve_decoder_bf16(fetch, d);
+  return resolve_decoder_f16(fetch, d);
 #undef DF32
-#undef DBF16
+#undef DF16
 }
 
 // the widest stage buffers are stage 2 (256 rows x 64 ch) and stage 3 (512 x 32): 16384 floats per frame
-// fp32 cross-check: 5 buffers x 16384 floats per frame; bf16 path: 6 buffers x 16384 bf16 (fits in the same bound)
+// fp32 cross-check: 5 buffers x 16384 floats per frame; f16 path: 6 buffers x 16384 f16 (fits in the same bound)
 int64_t decoder_ws_floats(int rf) { return (int64_t)rf * (5 * 16384 + 192 + 8) + 4096; }
 
 int decode_f32(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,

@@ -17,7 +17,7 @@ constexpr int kUpPad[kDecStages] = {4, 4, 0, 1};     // (k - u) / 2, models.py:2
 constexpr int kStageC[kDecStages + 1] = {512, 256, 128, 64, 32};
 
 struct ConvW { const float* w; const float* b; };                 // fp32 [k][Cin][Cout], [Cout]
-struct ConvW16 { const __nv_bfloat16* w; const float* b; };       // bf16 UMMA-packed (umma_conv.cu), fp32 bias
+struct ConvW16 { const __half* w; const float* b; };       // f16 UMMA-packed (umma_conv.cu), fp32 bias
 
 struct DecoderW {
   // fp32 (precision=1 cross-check path)
@@ -26,7 +26,7 @@ struct DecoderW {
   ConvW ups[kDecStages];                      // [s][K/s][Cin][Cout] polyphase taps
   ConvW c1[kDecStages * kDecKernels][kDecDils], c2[kDecStages * kDecKernels][kDecDils];
   const float* post_w;                        // [7][32][1]
-  // bf16 tcgen05 path
+  // f16 tcgen05 path
   ConvW16 pre16, ups16[kDecStages];
   ConvW16 c1_16[kDecStages * kDecKernels][kDecDils], c2_16[kDecStages * kDecKernels][kDecDils];
   // host copies of the ResBlock biases of the narrow stages (C <= 64): parameters of the fused pair kernel
@@ -35,13 +35,13 @@ struct DecoderW {
 
 using FetchFn = std::function<int(const std::string&, int64_t, int32_t, const void**)>;
 int resolve_decoder(const FetchFn& fetch, int n_speakers, DecoderW* out);
-int resolve_decoder_bf16(const FetchFn& fetch, DecoderW* out);
+int resolve_decoder_f16(const FetchFn& fetch, DecoderW* out);
 int ups_taps(int stage, int* pad_l);   // taps of the polyphase form of ups[stage] (union over phases)
 int64_t decoder_ws_floats(int n_rows_frame);
 int decode_f32(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                cudaStream_t st);
 void decoder_set_streams(int n);     // 1 (default) = every launch on the caller's stream, 2 = k=11 chains on a side stream (A/B knob)
-int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
+int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                 cudaStream_t st);
 
 }  // namespace vs

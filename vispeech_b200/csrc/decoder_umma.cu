@@ -1,5 +1,5 @@
-// bf16 tcgen05 HiFi-GAN decoder: Generator.forward (reference models.py:271-290) as a chain of
-// umma_conv1d launches over planar bf16 activations.  All leaky-relus, biases, residual adds, the MRF
+// f16 tcgen05 HiFi-GAN decoder: Generator.forward (reference models.py:271-290) as a chain of
+// umma_conv1d launches over planar f16 activations.  All leaky-relus, biases, residual adds, the MRF
 // sum (/3) and the ConvTranspose1d phase scatter are fused into conv epilogues; no elementwise pass
 // touches HBM between convs.
 #include "decoder.cuh"
@@ -20,23 +20,23 @@ int ups_taps(int i, int* pad_l) {
   return dmax - dmin + 1;
 }
 
-int resolve_decoder_bf16(const FetchFn& fetch, DecoderW* d) {
-#define DBF16(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_BF16, reinterpret_cast<const void**>(&(field))))
-  DBF16(d->pre16.w, "dec16.pre.w", 7 * 192 * 512);
+int resolve_decoder_f16(const FetchFn& fetch, DecoderW* d) {
+#define DF16(field, name, numel) VS_TRY(fetch(name, numel, VS_DTYPE_F16, reinterpret_cast<const void**>(&(field))))
+  DF16(d->pre16.w, "dec16.pre.w", 7 * 192 * 512);
   d->pre16.b = d->pre.b;
   for (int i = 0; i < kDecStages; ++i) {
     const int cin = kStageC[i], cout = kStageC[i + 1];
     int pad_l = 0;
     const int taps = ups_taps(i, &pad_l);
-    DBF16(d->ups16[i].w, "dec16.ups." + std::to_string(i) + ".w", (int64_t)taps * cin * cout * kUpRate[i]);
+    DF16(d->ups16[i].w, "dec16.ups." + std::to_string(i) + ".w", (int64_t)taps * cin * cout * kUpRate[i]);
     d->ups16[i].b = d->ups[i].b;
     for (int j = 0; j < kDecKernels; ++j) {
       const int n = i * kDecKernels + j;
       for (int mth = 0; mth < kDecDils; ++mth) {
         const std::string q = "dec16.rb." + std::to_string(n) + ".";
         const int64_t numel = (int64_t)kResK[j] * cout * cout;
-        DBF16(d->c1_16[n][mth].w, q + "c1." + std::to_string(mth) + ".w", numel);
-        DBF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
+        DF16(d->c1_16[n][mth].w, q + "c1." + std::to_string(mth) + ".w", numel);
+        DF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
         d->c1_16[n][mth].b = d->c1[n][mth].b;
         d->c2_16[n][mth].b = d->c2[n][mth].b;
         if (cout <= 64) {
@@ -46,13 +46,13 @@ int resolve_decoder_bf16(const FetchFn& fetch, DecoderW* d) {
       }
     }
   }
-#undef DBF16
+#undef DF16
   return VS_OK;
 }
 
-// fp32 row-major [R][C] -> planar bf16 [C/8][R][8], zero on invalid rows
-__global__ void to_planar_bf16_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
-                                      __nv_bfloat16* __restrict__ out, int R, int C) {
+// fp32 row-major [R][C] -> planar f16 [C/8][R][8], zero on invalid rows
+__global__ void to_planar_f16_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
+                                      __half* __restrict__ out, int R, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (plane, row)
   if (i >= (C / 8) * R) return;
   const int pl = i / R, r = i % R;
@@ -60,17 +60,17 @@ __global__ void to_planar_bf16_kernel(const float* __restrict__ x, const int32_t
   if (row_utt[r] >= 0) {
     const float4 a = *reinterpret_cast<const float4*>(x + (size_t)r * C + pl * 8);
     const float4 b = *reinterpret_cast<const float4*>(x + (size_t)r * C + pl * 8 + 4);
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+    __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
     o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                    *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
   }
   *reinterpret_cast<uint4*>(out + (size_t)i * 8) = o;
 }
 
-// conv_post (32 -> 1, k7, no bias) + tanh on planar bf16 input that already carries leaky_relu(.,0.01)
+// conv_post (32 -> 1, k7, no bias) + tanh on planar f16 input that already carries leaky_relu(.,0.01)
 // (models.py:286-288).  224 MACs per sample: CUDA cores, one thread per output sample.
-__global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void conv_post_kernel(const __half* __restrict__ x, const float* __restrict__ w,
                                  const int32_t* __restrict__ row_utt, int row_div, float* __restrict__ wave, int R) {
   __shared__ float ws[7 * 32];
   for (int i = threadIdx.x; i < 7 * 32; i += blockDim.x) ws[i] = w[i];
@@ -89,8 +89,9 @@ __global__ void conv_post_kernel(const __nv_bfloat16* __restrict__ x, const floa
       const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        acc = fmaf(__uint_as_float(wd[e] << 16), ws[t * 32 + pl * 8 + 2 * e], acc);
-        acc = fmaf(__uint_as_float(wd[e] & 0xFFFF0000u), ws[t * 32 + pl * 8 + 2 * e + 1], acc);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wd[e]));
+        acc = fmaf(f.x, ws[t * 32 + pl * 8 + 2 * e], acc);
+        acc = fmaf(f.y, ws[t * 32 + pl * 8 + 2 * e + 1], acc);
       }
     }
   }
@@ -123,22 +124,22 @@ static int side_stream(SideStream** out) {
   return VS_OK;
 }
 
-int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
+int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                 cudaStream_t st_main) {
   cudaStream_t st = st_main;
   const int R = rows.n_rows;
   int32_t* valid = ws.take<int32_t>(R);
-  __nv_bfloat16* zin = ws.take<__nv_bfloat16>((int64_t)R * kHidden);
+  __half* zin = ws.take<__half>((int64_t)R * kHidden);
   const bool two = g_decoder_streams == 2;
-  __nv_bfloat16* buf[9];
-  for (int i = 0; i < (two ? 9 : 6); ++i) buf[i] = ws.take<__nv_bfloat16>((int64_t)R * 16384);
-  if (!ws.ok) { set_error("decode_bf16: workspace too small"); return VS_ERR_WORKSPACE; }
-  __nv_bfloat16 *XA = buf[0], *S = buf[4], *NEXT = buf[5];     // buf[1..3] / buf[6..8]: T, AA, BA of the main / side chain
+  __half* buf[9];
+  for (int i = 0; i < (two ? 9 : 6); ++i) buf[i] = ws.take<__half>((int64_t)R * 16384);
+  if (!ws.ok) { set_error("decode_f16: workspace too small"); return VS_ERR_WORKSPACE; }
+  __half *XA = buf[0], *S = buf[4], *NEXT = buf[5];     // buf[1..3] / buf[6..8]: T, AA, BA of the main / side chain
   SideStream* side = nullptr;
   if (two) VS_TRY(side_stream(&side));
 
   VS_TRY(mask_frames(rows, max_len, valid, st));                         // (z * x_mask)[:, :, :max_len]  models.py:720
-  to_planar_bf16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
+  to_planar_f16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
   VS_LAUNCH_CHECK();
 
   UmmaConv c;
@@ -160,7 +161,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
     }
     c = UmmaConv();
     // only the ACTIVATED stream a = lrelu(x) is stored between ResBlock iterations: it is the next conv's operand as
-    // is, and the residual x is recovered in the c2 epilogue as min(a, a/slope) (same bf16 relative rounding as storing x)
+    // is, and the residual x is recovered in the c2 epilogue as min(a, a/slope) (same f16 relative rounding as storing x)
     c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = nullptr; c.out_act = XA;
     c.act_slope = 0.1f;
     c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
@@ -177,12 +178,12 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
       const float final_slope = (i == kDecStages - 1) ? 0.01f : 0.1f;    // final lrelu uses the default slope (Q3)
       const bool on_side = two && j == kDecKernels - 1;                  // the k = 11 chain
       st = on_side ? side->s : st_main;
-      __nv_bfloat16* T = on_side ? buf[6] : buf[1];
-      __nv_bfloat16* AA = on_side ? buf[7] : buf[2];
-      __nv_bfloat16* BA = on_side ? buf[8] : buf[3];
+      __half* T = on_side ? buf[6] : buf[1];
+      __half* AA = on_side ? buf[7] : buf[2];
+      __half* BA = on_side ? buf[8] : buf[3];
       if (two && j == kDecKernels - 1) VS_CUDA_CHECK(cudaEventRecord(side->sum, st_main));   // S = k3 + k7 is enqueued
       if (fused[j]) {
-        const __nv_bfloat16* cur = XA;                                   // a = lrelu(x): the only stream between iterations
+        const __half* cur = XA;                                   // a = lrelu(x): the only stream between iterations
         for (int mth = 0; mth < kDecDils; ++mth) {
           const bool last = (mth == kDecDils - 1);
           if (on_side && last) VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->sum, 0));   // its epilogue reads S
@@ -201,7 +202,7 @@ int decode_bf16(const DecoderW& w, const VsRows& rows, const float* z, int max_l
         }
         continue;
       }
-      const __nv_bfloat16* cur_act = XA;
+      const __half* cur_act = XA;
       for (int mth = 0; mth < kDecDils; ++mth) {
         const bool last = (mth == kDecDils - 1);
         if (on_side && last) VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->sum, 0));     // c2's epilogue reads S

@@ -556,9 +556,9 @@ int vs_posterior_encode(const VsModel* m, const VsRows* rows, const float* spec,
 int vs_hifigan_decode(const VsModel* m, const VsRows* rows, const float* z, int32_t max_len, float* wave_out,
                       int32_t precision, void* ws, int64_t ws_bytes, void* stream) {
   VS_ENTER(m, rows, "vs_hifigan_decode");
-  VS_REQUIRE(precision == 0 || precision == 1, "vs_hifigan_decode: precision must be 0 (bf16 tcgen05) or 1 (fp32 check)");
+  VS_REQUIRE(precision == 0 || precision == 1, "vs_hifigan_decode: precision must be 0 (f16 tcgen05) or 1 (fp32 check)");
   if (precision == 1) return decode_f32(m->dec, *rows, z, max_len, wave_out, W, st);
-  return decode_bf16(m->dec, *rows, z, max_len, wave_out, W, st);
+  return decode_f16(m->dec, *rows, z, max_len, wave_out, W, st);
 }
 
 int vs_unpack_rows(const VsRows* rows, const float* x, int32_t C, int32_t rows_mul, int32_t t_max, float* out,
@@ -666,9 +666,9 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
                       const int32_t* row_utt, int32_t row_div, void* stream) {
   UmmaConv c;
-  c.in = static_cast<const __nv_bfloat16*>(in_planar); c.w = static_cast<const __nv_bfloat16*>(w_packed);
-  c.bias = bias; c.res = static_cast<const __nv_bfloat16*>(res_planar);
-  c.out_raw = static_cast<__nv_bfloat16*>(out_raw); c.out_act = static_cast<__nv_bfloat16*>(out_act);
+  c.in = static_cast<const __half*>(in_planar); c.w = static_cast<const __half*>(w_packed);
+  c.bias = bias; c.res = static_cast<const __half*>(res_planar);
+  c.out_raw = static_cast<__half*>(out_raw); c.out_act = static_cast<__half*>(out_act);
   c.R = n_rows; c.Cin = c_in; c.N = n_cols; c.taps = taps; c.dil = dil; c.pad_l = pad_l; c.up = up;
   c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
   return umma_conv1d(c, static_cast<cudaStream_t>(stream));
@@ -678,10 +678,10 @@ int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_pa
                   const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
                   int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream) {
   UmmaPair c;
-  c.x = static_cast<const __nv_bfloat16*>(x_planar); c.w1 = static_cast<const __nv_bfloat16*>(w1_packed);
-  c.w2 = static_cast<const __nv_bfloat16*>(w2_packed); c.b1 = b1; c.b2 = b2;
-  c.res2 = static_cast<const __nv_bfloat16*>(res2_planar); c.out_raw = static_cast<__nv_bfloat16*>(out_raw);
-  c.out_act = static_cast<__nv_bfloat16*>(out_act); c.R = n_rows; c.C = channels; c.taps = taps; c.dil = dil;
+  c.x = static_cast<const __half*>(x_planar); c.w1 = static_cast<const __half*>(w1_packed);
+  c.w2 = static_cast<const __half*>(w2_packed); c.b1 = b1; c.b2 = b2;
+  c.res2 = static_cast<const __half*>(res2_planar); c.out_raw = static_cast<__half*>(out_raw);
+  c.out_act = static_cast<__half*>(out_act); c.R = n_rows; c.C = channels; c.taps = taps; c.dil = dil;
   c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
   return umma_respair(c, static_cast<cudaStream_t>(stream));
 }

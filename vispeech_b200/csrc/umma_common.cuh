@@ -1,6 +1,7 @@
 // PTX wrappers shared by the tcgen05 kernels (sm_100a): mbarrier, TMA bulk copy, tcgen05 mma/commit/ld, descriptors.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace vs {
 namespace umma {
@@ -73,8 +74,8 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {   // whole warp calls,
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation.
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers f16 inputs with fp32 accumulation.
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -87,7 +88,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
 // between MMAs, so the issue loop is two integer adds per instruction.
 // Executed by the whole (converged) MMA warp: one elected lane issues, so the surrounding loop stays
 // warp-uniform and the compiler keeps the descriptors in uniform registers.
-__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+__device__ __forceinline__ void tc_mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
@@ -111,7 +112,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uin
     uint32_t a_lo = a_tap;
 #pragma unroll
     for (int ks = 0; ks < NK; ++ks) {
-      tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+      tc_mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
       accumulate = 1;
       a_lo += a_kstep;
       b_lo += b_kstep;
@@ -130,10 +131,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
   d |= (uint64_t)1 << 46;
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format BF16 = 1 @7/@10,
-// a/b major K = 0 @15/@16, N>>3 @17, M>>4 @24.
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format @7/@10 (F16 = 0, BF16 = 1),
+// a/b major K = 0 @15/@16, N>>3 @17, M>>4 @24.  The decoder's operands are IEEE fp16 (11-bit significand, same tensor
+// rate as bf16): with bf16 operands the log-mel of the waveform misses the 1e-2 bar by 10x (precision).
 __device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -160,19 +162,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+// two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 (an overflow must not turn into inf: the next
+// conv would spread NaNs over its whole receptive field)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
-__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+__device__ __forceinline__ void unpack_f16x8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
   }
 }
-
 
 }  // namespace umma
 }  // namespace vs

@@ -1,9 +1,9 @@
 // conv1d as an implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a.
 //
-//   D[128 rows x Nblk] (fp32, TMEM) = sum_{tap t} sum_{ci}  A_t[128 x Cin] (bf16, smem) * W_t[Cin x Nblk] (bf16, smem)
+//   D[128 rows x Nblk] (fp32, TMEM) = sum_{tap t} sum_{ci}  A_t[128 x Cin] (f16, smem) * W_t[Cin x Nblk] (f16, smem)
 //
 // Mapping (time on M, output channels on N):
-//   * Activations live in HBM as planar bf16 [C/8][R][8].  One plane-slab of a row tile (128 + halo rows x 16 B)
+//   * Activations live in HBM as planar f16 [C/8][R][8].  One plane-slab of a row tile (128 + halo rows x 16 B)
 //     is contiguous in HBM *and* is exactly one K-chunk column of the UMMA "K-major, no swizzle" canonical
 //     layout (8-row core matrices of 128 contiguous bytes, SBO = 128 B, LBO = slab pitch).  So the A tile is
 //     fetched by Cin/8 plain TMA bulk copies (cp.async.bulk, completion on an mbarrier) with no tensor map, and
@@ -12,7 +12,7 @@
 //   * Weights are pre-packed (packing.py) so that one (n-block, tap, 64-channel chunk) slab is one bulk copy that
 //     lands in the same canonical layout; they stream through an SB-deep mbarrier ring out of L2.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-//     warps 2..5 = epilogue (tcgen05.ld -> bias/residual/leaky-relu -> bf16 -> coalesced 16 B planar stores).
+//     warps 2..5 = epilogue (tcgen05.ld -> bias/residual/leaky-relu -> f16 -> coalesced 16 B planar stores).
 //     TMEM holds two accumulator buffers so the epilogue of unit i overlaps the MMAs of unit i+1.
 //   * Persistent CTAs stride over row tiles; for N > 256 (conv_pre, ConvTranspose phases) the n-blocks loop
 //     inside the CTA so the A tile is fetched once.
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                   }
 #pragma unroll 4
                   for (int k16 = 0; k16 < k16s; ++k16) {
-                    tc_mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                    tc_mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
                     accumulate = 1;
                     a_lo += a_kstep;
                     b_lo += b_kstep;
@@ -331,19 +331,19 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                   }
                   if (has_res) {
                     float f[8];
-                    unpack_bf16x8(rv[g], f);
+                    unpack_f16x8(rv[g], f);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) y[e] += res_inv ? fminf(f[e], f[e] * rinv) : f[e];
                   }
                   if (has_res2) {
                     float f[8];
-                    unpack_bf16x8(rv2[g], f);
+                    unpack_f16x8(rv2[g], f);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) y[e] += f[e];
                   }
                   if (has_raw)
-                    raw = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                                     pack_bf16x2(y[6], y[7]));
+                    raw = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
+                                     pack_f16x2(y[6], y[7]));
                   if (has_act) {
                     float z[8];
 #pragma unroll
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                       const float t = has_scale ? y[e] * scale : y[e];
                       z[e] = fmaxf(t, t * slope);
                     }
-                    act = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]),
-                                     pack_bf16x2(z[6], z[7]));
+                    act = make_uint4(pack_f16x2(z[0], z[1]), pack_f16x2(z[2], z[3]), pack_f16x2(z[4], z[5]),
+                                     pack_f16x2(z[6], z[7]));
                   }
                 }
                 if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;

@@ -1,26 +1,26 @@
-// tcgen05 / TMEM implicit-GEMM conv1d over planar bf16 ragged rows (sm_100a).  See umma_conv.cu.
+// tcgen05 / TMEM implicit-GEMM conv1d over planar f16 ragged rows (sm_100a).  See umma_conv.cu.
 #pragma once
 #include "common.cuh"
 
 namespace vs {
 
-// Activations: planar bf16 [C/8][R][8]  (plane p holds channels 8p..8p+7 of every row, 16 B per row).
-// Weights:     bf16 [NB][taps][Cin/KC][KC/8][Nblk][8], KC = min(Cin, 64), Nblk = min(N, 256), N = NB*Nblk:
+// Activations: planar f16 [C/8][R][8]  (plane p holds channels 8p..8p+7 of every row, 16 B per row).
+// Weights:     f16 [NB][taps][Cin/KC][KC/8][Nblk][8], KC = min(Cin, 64), Nblk = min(N, 256), N = NB*Nblk:
 //              element (nb, t, kc, p, n, e) = W[t][kc*KC + 8p + e][nb*Nblk + n].  One (nb,t,kc) slab is one
 //              cp.async.bulk of KC*Nblk*2 bytes and lands in smem already in the UMMA K-major no-swizzle layout.
 struct UmmaConv {
-  const __nv_bfloat16* in = nullptr;   // planar [Cin/8][R][8]
-  const __nv_bfloat16* w = nullptr;    // packed as above
+  const __half* in = nullptr;   // planar [Cin/8][R][8]
+  const __half* w = nullptr;    // packed as above
   const float* bias = nullptr;         // [N % upsample-aware: bias[gn % Cout]] or null
   const float* ubias = nullptr;        // optional per-speaker table [n_spk][N]
   const int32_t* ubias_idx = nullptr;  // [n_utt] -> row of ubias
-  const __nv_bfloat16* res = nullptr;  // optional residual, planar like out (same rows/channels)
+  const __half* res = nullptr;  // optional residual, planar like out (same rows/channels)
   float res_inv_slope = 0.f;           // != 0: `res` holds a = lrelu(x, 1/res_inv_slope); the residual added is
-                                       // x = min(a, a * res_inv_slope) (exact inverse up to bf16 rounding), so only the
+                                       // x = min(a, a * res_inv_slope) (exact inverse up to f16 rounding), so only the
                                        // activated stream has to be stored between ResBlock iterations
-  const __nv_bfloat16* res2 = nullptr; // optional second residual (MRF running sum)
-  __nv_bfloat16* out_raw = nullptr;    // optional: y
-  __nv_bfloat16* out_act = nullptr;    // optional: lrelu(y * act_scale, act_slope)
+  const __half* res2 = nullptr; // optional second residual (MRF running sum)
+  __half* out_raw = nullptr;    // optional: y
+  __half* out_act = nullptr;    // optional: lrelu(y * act_scale, act_slope)
   const int32_t* row_utt = nullptr;    // validity of OUTPUT row: row_utt[orow / row_div] >= 0 (also gives utt for ubias)
   int row_div = 1;
   int R = 0;                           // input rows
@@ -37,16 +37,16 @@ void umma_conv_set_timing_buffer(void* dev);   // diagnostics: >= 296*12 int64 o
 
 // One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
 struct UmmaPair {
-  const __nv_bfloat16* x = nullptr;      // ACTIVATED input a = lrelu(x, in_slope), planar [C/8][R][8]
-  const __nv_bfloat16* w1 = nullptr;     // c1 weights, slabs as in UmmaConv (k taps, dilation dil)
-  const __nv_bfloat16* w2 = nullptr;     // c2 weights (k taps, dilation 1)
+  const __half* x = nullptr;      // ACTIVATED input a = lrelu(x, in_slope), planar [C/8][R][8]
+  const __half* w1 = nullptr;     // c1 weights, slabs as in UmmaConv (k taps, dilation dil)
+  const __half* w2 = nullptr;     // c2 weights (k taps, dilation 1)
   const float* b1 = nullptr;             // device
   const float* b2 = nullptr;
   const float* b1_host = nullptr;        // optional host copies of b1 / b2 (they travel in the kernel's parameter block);
   const float* b2_host = nullptr;        // without them the call fetches the device arrays and synchronises the stream
-  const __nv_bfloat16* res2 = nullptr;   // optional running MRF sum added to y
-  __nv_bfloat16* out_raw = nullptr;      // y
-  __nv_bfloat16* out_act = nullptr;      // lrelu(y * act_scale, act_slope)
+  const __half* res2 = nullptr;   // optional running MRF sum added to y
+  __half* out_raw = nullptr;      // y
+  __half* out_act = nullptr;      // lrelu(y * act_scale, act_slope)
   const int32_t* row_utt = nullptr; int row_div = 1;
   int R = 0, C = 0, taps = 3, dil = 1;
   float in_slope = 0.1f;                 // LRELU_SLOPE of modules.py:17 (both inner leaky-relus)

@@ -7,7 +7,7 @@
 // roofline of that traffic.  Here ONE tensor is read and ONE written per iteration:
 //   * only the ACTIVATED stream a = lrelu(x) travels between iterations.  It is the conv's A operand as is (TMA bulk copy
 //     straight into the UMMA layout), and the residual is recovered in the last epilogue by inverting the leaky-relu,
-//     x = min(a, a / slope): in bf16 that costs the same relative rounding as storing x itself;
+//     x = min(a, a / slope): in f16 that costs the same relative rounding as storing x itself;
 //   * the intermediate lrelu(c1 + b1) is written by the first epilogue directly into shared memory in the layout the
 //     second conv reads (rows outside the sequence / in gaps are zeroed there: they are c2's zero padding).
 //
@@ -15,7 +15,7 @@
 // CTA's tiles, each hand-off an mbarrier ring:
 //   warp 0      producer   XA[i % SX]  <- rows [s0-h1, s0+128+h1) of a (zero fill outside [0,R))
 //   warp 1      MMA        conv1(i) : XA -> acc1[i&1]   then   conv2(i-1) : A2[(i-1)&1] -> acc2[(i-1)&1]
-//   EW warps    epilogue 1 acc1[i&1] -> +b1 -> lrelu -> mask -> bf16 -> A2[i&1] (smem)
+//   EW warps    epilogue 1 acc1[i&1] -> +b1 -> lrelu -> mask -> f16 -> A2[i&1] (smem)
 //   EW warps    epilogue 2 acc2[i&1] + b2 + lrelu^-1(XA rows) [+ MRF sum] -> lrelu -> HBM
 // While the tensor pipe runs, its operand fetch owns shared memory: an LDS / STS / mbarrier probe from another warp takes
 // ~250 clk and a tcgen05.ld ~300 (tools/mma_microbench.cu), so each epilogue is a chain of a few such round trips, about
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
             y[e] = fmaxf(t, t * slope);
           }
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (uint32_t)gq * a2_plane),
-                       "r"(pack_bf16x2(y[0], y[1]) & keep), "r"(pack_bf16x2(y[2], y[3]) & keep),
-                       "r"(pack_bf16x2(y[4], y[5]) & keep), "r"(pack_bf16x2(y[6], y[7]) & keep)
+                       "r"(pack_f16x2(y[0], y[1]) & keep), "r"(pack_f16x2(y[2], y[3]) & keep),
+                       "r"(pack_f16x2(y[4], y[5]) & keep), "r"(pack_f16x2(y[6], y[7]) & keep)
                        : "memory");
         }
       };
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     const bool has_scale = kGen ? (c.act_scale != 1.f) : (MODE == M_ACT_RES2_SCALE);
     const int q = warp & 3, cc = (warp - 2 - EW) >> 2;
     const float oslope = c.act_slope, oscale = c.act_scale;
-    const __nv_bfloat162 inv2 = __float2bfloat162_rn(1.f / c.in_slope);
+    const __half2 inv2 = __float2half2_rn(1.f / c.in_slope);
     const int o = q * 32 + lane;                        // conv2 output position within the tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * N + (uint32_t)(cc * 32);
     const uint32_t xa_lane = xa + (uint32_t)(p.h1 + p.h2 + o) * 16u + (uint32_t)(cc * 4 * p.rows_x) * 16u;
@@ -330,29 +330,28 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
-          // x = lrelu^-1(a) = min(a, a / slope) on the packed pairs (1/slope = 10 is exact in bf16; the product rounds like
-          // a stored bf16 x would have), then everything else in fp32
+          // x = lrelu^-1(a) = min(a, a / slope) on the packed pairs (1/slope = 10 is exact in f16; the product rounds like
+          // a stored f16 x would have), then everything else in fp32
           const uint32_t aw[4] = {xv[gq].x, xv[gq].y, xv[gq].z, xv[gq].w};
           float y[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const __nv_bfloat162 a2v = *reinterpret_cast<const __nv_bfloat162*>(&aw[h]);
-            const __nv_bfloat162 x2 = __hmin2(a2v, __hmul2(a2v, inv2));
-            const uint32_t xw = *reinterpret_cast<const uint32_t*>(&x2);
-            y[2 * h] = __uint_as_float(v[8 * gq + 2 * h]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h] + __uint_as_float(xw << 16);
-            y[2 * h + 1] = __uint_as_float(v[8 * gq + 2 * h + 1]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h + 1] +
-                           __uint_as_float(xw & 0xFFFF0000u);
+            const __half2 a2v = *reinterpret_cast<const __half2*>(&aw[h]);
+            const __half2 x2 = __hmin2(a2v, __hmul2(a2v, inv2));
+            const float2 xf = __half22float2(x2);
+            y[2 * h] = __uint_as_float(v[8 * gq + 2 * h]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h] + xf.x;
+            y[2 * h + 1] = __uint_as_float(v[8 * gq + 2 * h + 1]) + prm.bias[1][CC * 32 + gq * 8 + 2 * h + 1] + xf.y;
           }
           if (has_res2) {
             float f[8];
-            unpack_bf16x8(rv2[gq], f);
+            unpack_f16x8(rv2[gq], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] += f[e];
           }
           const size_t go = row_off + (size_t)gq * plane_elems;
           if (has_raw) {
-            const uint4 raw = make_uint4(pack_bf16x2(y[0], y[1]) & keep, pack_bf16x2(y[2], y[3]) & keep,
-                                         pack_bf16x2(y[4], y[5]) & keep, pack_bf16x2(y[6], y[7]) & keep);
+            const uint4 raw = make_uint4(pack_f16x2(y[0], y[1]) & keep, pack_f16x2(y[2], y[3]) & keep,
+                                         pack_f16x2(y[4], y[5]) & keep, pack_f16x2(y[6], y[7]) & keep);
             if (in_tile) *reinterpret_cast<uint4*>(c.out_raw + go) = raw;
           }
           if (has_act) {
@@ -362,8 +361,8 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
               const float t = has_scale ? y[e] * oscale : y[e];
               z[e] = fmaxf(t, t * oslope);
             }
-            const uint4 act = make_uint4(pack_bf16x2(z[0], z[1]) & keep, pack_bf16x2(z[2], z[3]) & keep,
-                                         pack_bf16x2(z[4], z[5]) & keep, pack_bf16x2(z[6], z[7]) & keep);
+            const uint4 act = make_uint4(pack_f16x2(z[0], z[1]) & keep, pack_f16x2(z[2], z[3]) & keep,
+                                         pack_f16x2(z[4], z[5]) & keep, pack_f16x2(z[6], z[7]) & keep);
             if (in_tile) *reinterpret_cast<uint4*>(c.out_act + go) = act;
           }
         }

@@ -10,7 +10,7 @@ weight-norm forward pre-hooks (checkpoints hold un-folded w
   * the Flip() layers of the flow (modules.py:270-277) folded into channel-permuted pre/post weights of the
     odd coupling layers (csrc/model.cu vs_flow_reverse);
   * ConvTranspose1d rewritten as polyphase taps;
-  * decoder weights additionally in the bf16 slab layout of csrc/umma_conv.cuh.
+  * decoder weights additionally in the f16 slab layout of csrc/umma_conv.cuh.
 Names on the right-hand side are the keys `vs_model_set_tensor` expects (csrc/model.cu, csrc/decoder*.cu).
 """
 from __future__ import annotations
@@ -59,14 +59,14 @@ def up_columns(cout: int, s: int) -> torch.Tensor:
 
 
 def pack_umma(w: torch.Tensor) -> torch.Tensor:
-    """[taps][Cin][N] fp32 -> bf16 [NB][taps][Cin/KC][KC/8][Nblk][8] (csrc/umma_conv.cuh)."""
+    """[taps][Cin][N] fp32 -> f16 [NB][taps][Cin/KC][KC/8][Nblk][8] (csrc/umma_conv.cuh)."""
     taps, cin, n = w.shape
     kc = min(cin, 64)
     nblk = min(n, 256)
     assert cin % kc == 0 and n % nblk == 0 and kc % 16 == 0
     x = w.reshape(taps, cin // kc, kc // 8, 8, n // nblk, nblk)
     x = x.permute(4, 0, 1, 2, 5, 3).contiguous()
-    return x.to(torch.bfloat16).reshape(-1)
+    return x.to(torch.float16).reshape(-1)
 
 
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -105,7 +105,7 @@ def gate_columns(h: int = 192) -> torch.Tensor:
 
 
 def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_flows=4, flow_layers=4) -> Dict[str, torch.Tensor]:
-    """Returns {packed name: CPU tensor (fp32 or bf16, contiguous)}."""
+    """Returns {packed name: CPU tensor (fp32 or f16, contiguous)}."""
     sd = {k: v.detach().float().cpu() for k, v in sd.items()}
     out: Dict[str, torch.Tensor] = {}
     emb_g = sd["emb_g.weight"]                                     # [200, 256]

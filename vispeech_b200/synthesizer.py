@@ -22,7 +22,7 @@ from .layout import FRAME_GAP, PHONEME_GAP, RaggedRows, make_rows
 from .packing import pack_state_dict
 
 Control = Union[None, float, int, torch.Tensor]
-_DTYPES = {torch.float32: _lib.VS_DTYPE_F32, torch.bfloat16: _lib.VS_DTYPE_BF16}
+_DTYPES = {torch.float32: _lib.VS_DTYPE_F32, torch.float16: _lib.VS_DTYPE_F16}
 
 
 class SynthesizerTrn:
