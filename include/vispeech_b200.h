@@ -86,6 +86,8 @@ int64_t vs_launch_count(void);
  * fp32 CUDA-core kernel; 0 = always CUDA cores, 2 = always tensor cores, 3 = tensor cores in plain TF32 (A/B only).
  * "wn_fused": 1 (default) = on the plain-TF32 route every WN layer is ONE kernel on planar fp32 state (csrc/umma_wn.cu),
  * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
+ * "mrf_fused": 1 (default) = the decoder's last MRF stage (C = 32: three ResBlocks, sum, conv_post, tanh) is ONE kernel with the
+ * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
  * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast
  * (bit-identical; no gain measured).  "decoder_streams": 1 (default) | 2 = the k=11 ResBlock chains of each decoder stage
  * run on a side stream (no gain measured).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).
@@ -204,6 +206,14 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
 int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
                   const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
                   int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream);
+
+/* The decoder's whole last MRF stage (C = 32) + conv_post + tanh in one kernel (csrc/umma_mrf.cu; reference models.py:279-288,
+ * modules.py:210-223): x0 = x_hi + x_lo (planar f16 [4][n_rows][8] each) -> 3 ResBlock1 (k = 3, 7, 11; d = 1, 3, 5) -> sum / 3 ->
+ * leaky_relu(0.01) -> conv_post (32 -> 1, k = 7) -> tanh -> wave [n_rows].  w_packed[18] / b_host[18]: per ResBlock j and
+ * iteration m, (c1, c2) at index (3 j + m) * 2 + {0, 1}; weights are device pointers (pack_umma slabs), biases and post_w
+ * ([7][32]) HOST pointers (they travel in the kernel's parameter block). */
+int vs_op_mrf32(const void* x_hi, const void* x_lo, const void* const* w_packed, const float* const* b_host,
+                const float* post_w_host, const int32_t* row_utt, int32_t row_div, int32_t n_rows, float* wave, void* stream);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,27 @@ def respair(x, w1, w2, b1, b2, dil, res2=None, act_slope=1.0, act_scale=1.0, row
     return from_planar(raw), from_planar(act)
 
 
+def mrf32(x0, W, B, post_w, row_utt, row_div=1):
+    """Whole last MRF stage + conv_post + tanh (csrc/umma_mrf.cu).  x0 [R][32] fp32 (device), W[j][m][c] = [k][32][32] fp32,
+    B[j][m][c] = [32] fp32 (CPU), post_w [7][32] fp32 (CPU).  x0 is handed over as fp16 hi + lo planes.  Returns wave [R]."""
+    import ctypes
+    lib = _lib.load()
+    R = x0.shape[0]
+    hi = x0.to(torch.float16)
+    lo = (x0 - hi.float()).to(torch.float16)
+    hi_p, lo_p = to_planar(hi.float()), to_planar(lo.float())
+    wp = [pack_umma(W[j][m][c].cpu()).to(x0.device) for j in range(3) for m in range(3) for c in range(2)]
+    bh = [B[j][m][c].float().contiguous().cpu() for j in range(3) for m in range(3) for c in range(2)]
+    w_arr = (ctypes.c_void_p * 18)(*[t.data_ptr() for t in wp])
+    b_arr = (ctypes.c_void_p * 18)(*[t.data_ptr() for t in bh])
+    pw = post_w.float().contiguous().cpu()
+    wave = torch.full((R,), float("nan"), dtype=torch.float32, device=x0.device)
+    check(lib.vs_op_mrf32(ptr(hi_p), ptr(lo_p), ctypes.cast(w_arr, ctypes.c_void_p), ctypes.cast(b_arr, ctypes.c_void_p), ptr(pw),
+                          ptr(row_utt), row_div, R, ptr(wave), stream()), "vs_op_mrf32")
+    torch.cuda.synchronize()
+    return wave
+
+
 def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=None, row_div=1):
     lib = _lib.load()
     R, cin = x.shape

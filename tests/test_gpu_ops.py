@@ -95,6 +95,49 @@ def test_fused_resblock_pair_matches_cpu(G, R, C, k, dil):
         assert raw[300:340].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("R,row_div,gaps", [(100, 1, []), (640 * 3 + 77, 1, [(900, 960)]), (4096, 4, [(0, 8), (2000, 2100), (4000, 4096)]),
+                                              (123456, 512, [(51200, 52224)])])
+def test_mrf_stage_matches_cpu(G, R, row_div, gaps):
+    """The decoder's last MRF stage as one kernel (csrc/umma_mrf.cu): 3 x ResBlock1 (k = 3, 7, 11; d = 1, 3, 5) + sum / 3 +
+    leaky_relu(0.01) + conv_post + tanh (models.py:279-288, modules.py:210-223) against an fp64 chain in which only the
+    conv OPERANDS are rounded to fp16, as in the kernel (x, the MRF sum and the conv_post input stay in full precision).
+    Covers: one partial super tile, several super tiles with a ragged tail, gaps at both ends, more super tiles than CTAs."""
+    g = torch.Generator().manual_seed(R)
+    ks, ds = (3, 7, 11), (1, 3, 5)
+    valid = torch.ones(R, dtype=torch.bool)
+    for lo, hi in gaps:
+        valid[lo:hi] = False
+    row_utt = torch.where(valid[::row_div], 0, -1).to(torch.int32)
+    valid = (row_utt >= 0).repeat_interleave(row_div)[:R]
+    x0 = torch.randn(R, 32, generator=g) * 0.5
+    x0[~valid] = 0                                        # ragged-rows invariant
+    W = [[[torch.randn(k, 32, 32, generator=g) / (32 * k) ** 0.5 for _ in range(2)] for _ in ds] for k in ks]
+    B = [[[torch.randn(32, generator=g) * 0.1 for _ in range(2)] for _ in ds] for _ in ks]
+    post_w = torch.randn(7, 32, generator=g) / (7 * 32) ** 0.5
+    wave = G.mrf32(x0.to(G.DEV), W, B, post_w, row_utt.to(G.DEV), row_div).cpu().double()
+
+    lrelu = lambda t, s=0.1: torch.where(t > 0, t, s * t)
+    hi16 = x0.to(torch.float16)
+    xin = hi16.double() + (x0 - hi16.float()).to(torch.float16).double()
+    vm = valid.double()[:, None]
+    total = torch.zeros(R, 32, dtype=torch.float64)
+    for j, k in enumerate(ks):
+        x = xin.clone()
+        for m, d in enumerate(ds):
+            a = G.f16_round(lrelu(x).float()).double() * vm
+            c1 = G.ref_conv_rows(a, G.f16_round(W[j][m][0]), B[j][m][0], dil=d, pad_l=(k - 1) // 2)
+            t = G.f16_round(lrelu(c1).float()).double() * vm
+            x = x + G.ref_conv_rows(t, G.f16_round(W[j][m][1]), B[j][m][1], dil=1, pad_l=(k - 1) // 2)
+        total += x
+    v = lrelu(total / 3, 0.01) * vm
+    ref = torch.tanh(G.ref_conv_rows(v, post_w[:, :, None], None, pad_l=3)[:, 0]) * valid.double()
+    err = (wave - ref).abs().max().item()
+    print("R=%d  max|wave - ref| = %.3e  (|ref| max %.3f)" % (R, err, ref.abs().max().item()))
+    assert torch.isfinite(wave).all()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert wave[~valid].abs().max().item() == 0 if (~valid).any() else True
+
+
 @pytest.mark.parametrize("stage", [0, 2, 3])
 def test_umma_conv_transpose_polyphase(G, stage):
     """ConvTranspose1d (models.py:257-259) as a polyphase UMMA conv vs F.conv_transpose1d."""

@@ -66,6 +66,7 @@ _SIGNATURES = {
                                     c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
     "vs_op_respair": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                 c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
+    "vs_op_mrf32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

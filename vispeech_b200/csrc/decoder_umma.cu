@@ -39,7 +39,7 @@ int resolve_decoder_f16(const FetchFn& fetch, DecoderW* d) {
         DF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
         d->c1_16[n][mth].b = d->c1[n][mth].b;
         d->c2_16[n][mth].b = d->c2[n][mth].b;
-        if (cout <= 64) {
+        if (cout <= 64) {   // parameters of the fused kernels (umma_respair.cu, umma_mrf.cu)
           VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][0], d->c1[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
           VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][1], d->c2[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
         }
@@ -47,6 +47,7 @@ int resolve_decoder_f16(const FetchFn& fetch, DecoderW* d) {
     }
   }
 #undef DF16
+  VS_CUDA_CHECK(cudaMemcpy(d->post_w_host, d->post_w, sizeof(d->post_w_host), cudaMemcpyDeviceToHost));
   return VS_OK;
 }
 
@@ -104,6 +105,8 @@ __global__ void conv_post_kernel(const __half* __restrict__ x, const float* __re
 // chain's CTAs - 3-5 % per pair of launches in isolation (tools/cosched_pairs.py), but nothing inside the decoder (measured
 // 25.77 vs 25.74 ms per step), so it is OFF by default.  Fork / join through events; the side chain has its own intermediate
 // buffers; the sum keeps its order (k3 + k7) + k11.
+int g_mrf_fused = 1;                     // vs_set_option("mrf_fused", 0 | 1): the last MRF stage + conv_post as ONE kernel (umma_mrf.cu)
+void decoder_set_mrf_fused(int on) { g_mrf_fused = on != 0; }
 int g_decoder_streams = 1;               // vs_set_option("decoder_streams", 1 | 2); in situ 2 gains nothing (25.77 vs 25.74 ms)
 void decoder_set_streams(int n) { g_decoder_streams = n < 2 ? 1 : 2; }
 
@@ -162,13 +165,28 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
     c = UmmaConv();
     // only the ACTIVATED stream a = lrelu(x) is stored between ResBlock iterations: it is the next conv's operand as
     // is, and the residual x is recovered in the c2 epilogue as min(a, a/slope) (same f16 relative rounding as storing x)
+    const bool mrf = g_mrf_fused && i == kDecStages - 1;                 // last stage: x0 in 22 bits (hi + lo), then umma_mrf
     c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = nullptr; c.out_act = XA;
     c.act_slope = 0.1f;
+    if (mrf) { c.out_act = nullptr; c.out_raw = XA; c.out_lo = buf[1]; }
     c.row_utt = valid; c.row_div = mul * s; c.R = R * mul; c.Cin = cin; c.N = cout * s; c.taps = taps; c.pad_l = pad_l;
     c.up = s;
     VS_TRY(umma_conv1d(c, st));                                          // ups[i] (ConvTranspose1d)  models.py:277
     mul *= s;
     const int Rs = R * mul;
+    if (mrf) {
+      // 3 x ResBlock1 + sum / 3 + leaky_relu(0.01) + conv_post + tanh  (models.py:279-288): residual stream, MRF sum and
+      // conv_post input stay in fp32 on chip
+      UmmaMrf f;
+      f.x_hi = XA; f.x_lo = buf[1]; f.wave = wave; f.row_utt = valid; f.row_div = mul; f.R = Rs; f.post_w_host = w.post_w_host;
+      for (int j = 0; j < kDecKernels; ++j)
+        for (int mth = 0; mth < kDecDils; ++mth) {
+          const int n = i * kDecKernels + j;
+          f.w[j][mth][0] = w.c1_16[n][mth].w; f.w[j][mth][1] = w.c2_16[n][mth].w;
+          f.b1_host[j][mth] = w.bias_host[n][mth][0]; f.b2_host[j][mth] = w.bias_host[n][mth][1];
+        }
+      return umma_mrf(f, st_main);
+    }
     if (two) {                                                           // fork: the side chain may start once XA is there
       VS_CUDA_CHECK(cudaEventRecord(side->fork, st_main));
       VS_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));

@@ -268,6 +268,10 @@ int vs_set_option(const char* name, int64_t value) {
     vs::g_wn_fused = value != 0;
     return VS_OK;
   }
+  if (std::string(name) == "mrf_fused") {
+    vs::decoder_set_mrf_fused((int)value);
+    return VS_OK;
+  }
   if (std::string(name) == "decoder_streams") {
     vs::decoder_set_streams((int)value);
     return VS_OK;
@@ -684,6 +688,21 @@ int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_pa
   c.out_act = static_cast<__half*>(out_act); c.R = n_rows; c.C = channels; c.taps = taps; c.dil = dil;
   c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
   return umma_respair(c, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_mrf32(const void* x_hi, const void* x_lo, const void* const* w_packed /*[18]*/, const float* const* b_host /*[18]*/,
+                const float* post_w_host, const int32_t* row_utt, int32_t row_div, int32_t n_rows, float* wave, void* stream) {
+  VS_REQUIRE(w_packed && b_host, "vs_op_mrf32: null pointer");
+  UmmaMrf f;
+  f.x_hi = static_cast<const __half*>(x_hi); f.x_lo = static_cast<const __half*>(x_lo);
+  for (int j = 0; j < 3; ++j)
+    for (int m = 0; m < 3; ++m) {
+      const int q = (j * 3 + m) * 2;
+      f.w[j][m][0] = static_cast<const __half*>(w_packed[q]); f.w[j][m][1] = static_cast<const __half*>(w_packed[q + 1]);
+      f.b1_host[j][m] = b_host[q]; f.b2_host[j][m] = b_host[q + 1];
+    }
+  f.post_w_host = post_w_host; f.row_utt = row_utt; f.row_div = row_div > 0 ? row_div : 1; f.R = n_rows; f.wave = wave;
+  return umma_mrf(f, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -104,9 +104,10 @@ __device__ __forceinline__ void tc_mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, 
 // One warp issues every MMA of a CTA, so this loop's instruction count bounds the small-N convs (tools/mma_microbench.cu:
 // runtime-nested loops cost 55-120 clk per MMA against a 40-48 clk operand-fetch floor): the K-chunk walk is unrolled.
 template <int NK>
-__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep) {
-  uint32_t accumulate = 0, a_tap = a_tile;
+__device__ __forceinline__ void issue_tile_acc(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep,
+                                               uint32_t accumulate) {   // accumulate = 1: D += (keeps what is in TMEM)
+  uint32_t a_tap = a_tile;
 #pragma unroll 2
   for (int t = 0; t < taps; ++t, a_tap += dil) {
     uint32_t a_lo = a_tap;
@@ -118,6 +119,11 @@ __device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uin
       b_lo += b_kstep;
     }
   }
+}
+template <int NK>
+__device__ __forceinline__ void issue_tile(uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, int taps, uint32_t dil, uint32_t a_kstep, uint32_t b_kstep) {
+  issue_tile_acc<NK>(d_tmem, a_tile, a_hi, b_lo, b_hi, idesc, taps, dil, a_kstep, b_kstep, 0u);
 }
 
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):

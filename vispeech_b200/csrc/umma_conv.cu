@@ -61,7 +61,7 @@ struct Params {
 #endif
 
 // Epilogue feature flags (template parameter F of the kernel; F < 0 = all decided at run time)
-constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128, F_RESINV = 256;
+constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE = 32, F_UP = 64, F_CW16 = 128, F_RESINV = 256, F_LO = 512;
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     const bool has_scale = kGeneric ? (c.act_scale != 1.f) : ((F & F_SCALE) != 0);
     const bool has_up = kGeneric ? (c.up != 1) : ((F & F_UP) != 0);
     const bool res_inv = kGeneric ? (c.res_inv_slope != 0.f) : ((F & F_RESINV) != 0);
+    const bool has_lo = kGeneric ? (c.out_lo != nullptr) : ((F & F_LO) != 0);
     const float rinv = c.res_inv_slope;
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
             for (int g = 0; g < 4; ++g)
               if (g * 8 < CW) {
                 const size_t o = group_off(g);
-                uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0);
+                uint4 raw = make_uint4(0, 0, 0, 0), act = make_uint4(0, 0, 0, 0), low = make_uint4(0, 0, 0, 0);
                 if (valid) {
                   const uint32_t co0 = ((g8 + (uint32_t)g) >> p.up_shift) << 3;
                   float y[8];
@@ -344,6 +345,12 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                   if (has_raw)
                     raw = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
                                      pack_f16x2(y[6], y[7]));
+                  if (has_lo) {                            // y = fp16(y) + fp16(y - fp16(y)): 22 bits of y in two planar tensors
+                    float h[8];
+                    unpack_f16x8(raw, h);
+                    low = make_uint4(pack_f16x2(y[0] - h[0], y[1] - h[1]), pack_f16x2(y[2] - h[2], y[3] - h[3]),
+                                     pack_f16x2(y[4] - h[4], y[5] - h[5]), pack_f16x2(y[6] - h[6], y[7] - h[7]));
+                  }
                   if (has_act) {
                     float z[8];
 #pragma unroll
@@ -356,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
                   }
                 }
                 if (has_raw) *reinterpret_cast<uint4*>(c.out_raw + o) = raw;
+                if (has_lo) *reinterpret_cast<uint4*>(c.out_lo + o) = low;
                 if (has_act) *reinterpret_cast<uint4*>(c.out_act + o) = act;
               }
           }
@@ -489,7 +497,8 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   if (grid > prm.p.n_super) grid = prm.p.n_super;
   int flags = (c.res ? F_RES : 0) | (c.res2 ? F_RES2 : 0) | (c.ubias ? F_UBIAS : 0) | (c.out_raw ? F_RAW : 0) |
               (c.out_act ? F_ACT : 0) | (c.act_scale != 1.f ? F_SCALE : 0) | (c.up != 1 ? F_UP : 0) |
-              (prm.p.Nblk < 64 ? F_CW16 : 0) | ((c.res && c.res_inv_slope != 0.f) ? F_RESINV : 0);
+              (prm.p.Nblk < 64 ? F_CW16 : 0) | ((c.res && c.res_inv_slope != 0.f) ? F_RESINV : 0) | (c.out_lo ? F_LO : 0);
+  VS_REQUIRE(!c.out_lo || c.out_raw, "umma_conv1d: out_lo needs out_raw");
 #define VS_UMMA_CASE(FL)                                                                                              \
   case FL: {                                                                                                          \
     static bool cfg = false;                                                                                          \
@@ -524,6 +533,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
     VS_UMMA_CASE(F_UBIAS | F_ACT)
     VS_UMMA_CASE(F_RAW | F_ACT | F_UP)
     VS_UMMA_CASE(F_RAW | F_UP)
+    VS_UMMA_CASE(F_RAW | F_UP | F_LO)
     default: {
       static bool cfg = false;
       if (!cfg) {

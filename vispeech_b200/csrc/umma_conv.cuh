@@ -20,6 +20,7 @@ struct UmmaConv {
                                        // activated stream has to be stored between ResBlock iterations
   const __half* res2 = nullptr; // optional second residual (MRF running sum)
   __half* out_raw = nullptr;    // optional: y
+  __half* out_lo = nullptr;     // optional (needs out_raw): fp16(y - fp16(y)), so that out_raw + out_lo carries y to 22 bits
   __half* out_act = nullptr;    // optional: lrelu(y * act_scale, act_slope)
   const int32_t* row_utt = nullptr;    // validity of OUTPUT row: row_utt[orow / row_div] >= 0 (also gives utt for ubias)
   int row_div = 1;
@@ -52,6 +53,20 @@ struct UmmaPair {
   float in_slope = 0.1f;                 // LRELU_SLOPE of modules.py:17 (both inner leaky-relus)
   float act_slope = 1.f, act_scale = 1.f;
 };
+// The whole last MRF stage (C = 32): 3 ResBlock1 + sum/3 + lrelu(0.01) + conv_post + tanh in one kernel (umma_mrf.cu).
+struct UmmaMrf {
+  const __half* x_hi = nullptr;          // ups[3] output x0 = hi + lo, planar [4][R][8] each (NOT activated)
+  const __half* x_lo = nullptr;
+  const __half* w[3][3][2] = {};         // [resblock k=3,7,11][iteration d=1,3,5][c1 | c2], slabs as in UmmaConv
+  const float* b1_host[3][3] = {};       // host copies of the biases (32 floats each): they travel in the parameter block
+  const float* b2_host[3][3] = {};
+  const float* post_w_host = nullptr;    // conv_post weights [7][32] (host)
+  float* wave = nullptr;                 // [R] tanh(conv_post(...)), zeros on gap rows
+  const int32_t* row_utt = nullptr; int row_div = 1;
+  int R = 0;
+};
+int umma_mrf(const UmmaMrf& c, cudaStream_t st);
+
 bool umma_respair_supported(int C, int taps, int dil);
 void umma_respair_grid_div(int d);    // experiment knob: use 1/d of the CTA slots (co-scheduling tests)
 void umma_respair_enable(int mode);   // 0 off (default), 1 where the isolated kernel is faster, 2 wherever it fits
