@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include "umma_common.cuh"
 
 namespace vs { void set_error(const char*, ...) {} unsigned long long g_launch_count = 0; }
@@ -98,17 +99,18 @@ __device__ __forceinline__ void walk_lane0(const Walk& w, uint32_t tm, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_clk) {
+__global__ void __launch_bounds__(320, 2) mma_walk(const Walk w, long long* out_clk) {
   __shared__ volatile int done_flag;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { done_flag = 0; mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { done_flag = 0; mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (w.fill) {   // operands: 0 = whatever is there, 1 = zeros, 2 = pseudo-random f16 in [-1, 1)
     uint32_t* s32 = reinterpret_cast<uint32_t*>(smem);
     uint32_t x = 1234567u + threadIdx.x * 7919u + blockIdx.x * 104729u;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_
     const int lane = threadIdx.x & 31, q = warp & 3;
     uint32_t v[32];
     float acc = 0.f;
-    const uint32_t sbase = smem_u32(smem) + 150 * 1024 + (uint32_t)(threadIdx.x - 64) * 16u;
+    const uint32_t sbase = smem_u32(smem) + 150 * 1024 + (uint32_t)((threadIdx.x - 64) & 127) * 16u;
     long long n_it = 0;
     const long long tn0 = clock64();
     while (!done_flag) {
@@ -189,10 +191,21 @@ __global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_
         for (int r = 0; r < 4; ++r)
           asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sbase + r * 2048u), "r"(lane) : "memory");
       }
+      if (w.noise & 16) {    // spin on an mbarrier that never completes (what a waiting epilogue warp does)
+#pragma unroll 1
+        for (int r = 0; r < 64; ++r)
+          if (mbar_try_wait(smem_u32(&bar2), 0)) acc += 1.f;
+      }
+      if (w.noise & 32) {    // TMEM writes
+        tmem_ld32(tm + ((uint32_t)(q * 32) << 16) + 128u, v);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tm + ((uint32_t)(q * 32) << 16) + 192u),
+                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       if (w.noise & 8) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          reinterpret_cast<float4*>(w.gbuf)[((size_t)blockIdx.x * 4 + r) * 128 + (threadIdx.x - 64)] = make_float4(acc, 0, 0, 0);
+          reinterpret_cast<float4*>(w.gbuf)[((size_t)blockIdx.x * 4 + r) * 128 + ((threadIdx.x - 64) & 127)] = make_float4(acc, 0, 0, 0);
       }
     }
     if (lane == 0 && warp == 2) out_clk[300 + blockIdx.x] = (clock64() - tn0) / (n_it > 0 ? n_it : 1);
@@ -204,11 +217,12 @@ __global__ void __launch_bounds__(192, 2) mma_walk(const Walk w, long long* out_
 }
 
 static long long* d_clk;
+static float* gbuf0() { static float* g = nullptr; if (!g) cudaMalloc(&g, (size_t)300 * 4 * 128 * 16); return g; }
 static double g_noise_clk = 0;   // clocks per iteration of the background loop (CTA 0, warp 2)
 static double run(Walk w, int per_sm) {
   static long long h[512];
   const int smem = per_sm == 1 ? 200 * 1024 : 100 * 1024;
-  mma_walk<<<148 * per_sm, w.noise ? 192 : 64, smem>>>(w, d_clk);
+  mma_walk<<<148 * per_sm, w.noise ? (w.noise & 64 ? 320 : 192) : 64, smem>>>(w, d_clk);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
   cudaMemcpy(h, d_clk, sizeof(long long) * 512, cudaMemcpyDeviceToHost);
@@ -219,9 +233,28 @@ static double run(Walk w, int per_sm) {
   return avg / ((double)w.iters * w.tiles * w.taps * w.nks) / per_sm;   // clocks per MMA per SM
 }
 
-int main() {
+int main(int argc, char** argv) {
   cudaMalloc(&d_clk, 512 * sizeof(long long));
   cudaFuncSetAttribute(mma_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (argc > 1 && std::string(argv[1]) == "pitch") {
+    // 3. does the pitch between the two K-chunk planes of one MMA (LBO = rows_a * 16 B) matter?  (unrolled issue loop, 1 CTA/SM)
+    printf("plane pitch sweep, N = C, k = 7, d = 1: rows_a (pitch mod 128 B) -> clk/MMA/SM\n");
+    for (int c : {32, 64})
+      for (int rows_a : {262, 256, 258, 260, 264, 832, 833, 834, 836, 838, 840, 784, 786}) {
+        if ((size_t)rows_a * c * 2 > 150 * 1024) continue;
+        Walk w{c, 7, 1, c / 16, rows_a, 2, 100, 0, 0, 1, 0, 0, nullptr};
+        printf("  C=%3d rows_a=%4d (%3d) : %6.1f\n", c, rows_a, (rows_a * 16) % 128, run(w, 1));
+      }
+    printf("background warps (C = 32, k = 7, unrolled issue loop, 1 CTA/SM): clk/MMA/SM with 4 / 8 background warps\n");
+    const char* names[] = {"none", "tcgen05.ld", "LDS", "STS", "STG", "mbarrier spin", "tcgen05.ld+st", "spin+STS+ld"};
+    const int modes[] = {0, 1, 2, 4, 8, 16, 32, 16 | 4 | 1};
+    for (int i = 0; i < 8; ++i) {
+      Walk w{32, 7, 1, 2, 262, 2, 100, 0, 0, 1, 0, modes[i], gbuf0()};
+      Walk w8 = w; w8.noise |= modes[i] ? 64 : 0;
+      printf("  %-14s : %6.1f  %6.1f\n", names[i], run(w, 1), run(w8, 1));
+    }
+    return 0;
+  }
   printf("fixed operands (floors): clk/MMA/SM at 1 and 2 CTAs/SM\n");
   for (int n : {32, 64, 128, 256}) {
     Walk w{n, 8, 1, 4, 256, 1, 200, 1, 1, 0, 0, 0, nullptr};

@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvispeech_b200.so")
+LIB_PATH = os.path.join(os.environ.get("VS_LIB_DIR") or os.path.join(HERE, "lib"), "libvispeech_b200.so")
 
 VS_DTYPE_F32, VS_DTYPE_F16, VS_DTYPE_I64, VS_DTYPE_F64 = 0, 1, 2, 3
 

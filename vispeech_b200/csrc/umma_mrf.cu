@@ -19,19 +19,20 @@
 // fetch floor, not by HBM).  TMEM (512 columns): X[t] 32 columns per tile (192), SUM[t] (192), and a ring of 4
 // accumulators for conv1 (128).
 //
-// Roles (320 threads):
+// Roles (608 threads):
 //   warp 0      weight producer: streams the 18 convs' weight slabs (<= 22 KB each) through a 4-slot ring, in the order
-//               the MMA warp consumes them (out of L2: 252 KB per super tile);
-//   warp 1      MMA issuer.  Per ResBlock iteration: conv1(t) : A -> ring slot;  conv2(t) : MID -> X[t] (accumulate).
-//               conv1 runs 3 tiles ahead of conv2 so that epilogue 1 has tensor time to hide behind;
-//   warps 2-5   epilogue 1: ring slot -> + b1 -> lrelu -> mask -> fp16 -> MID (smem, UMMA layout);
-//   warps 6-9   epilogue 2: X[t] -> + cumulative b2 -> lrelu -> mask -> fp16 -> A (the next iteration's operand);
-//               after a ResBlock's last iteration: SUM[t] (+)= X[t], then X[t] <- x0 and A <- lrelu(x0) for the next
-//               ResBlock (x0 = hi + lo read from HBM/L2 as two fp16 planar tensors: fp32-exact to 22 bits);
-//               after the last ResBlock: v = lrelu(SUM/3, 0.01); conv_post as 7 per-tap partial dot products per row
-//               into a small smem table; once per super tile the crew combines the taps across rows, tanh, stores.
-// Every hand-off is an mbarrier; dependencies between neighbouring tiles (a conv at tile t reads rows of t-1 and t+1)
-// are covered by waiting for tile t+1, because every crew finishes tiles in order.
+//               the MMA warps consume them (out of L2: 252 KB per super tile);
+//   warps 1, 2  MMA issuers: warp 1 issues conv1(t) : A -> ring slot, warp 2 conv2(t) : MID -> X[t] (accumulate);
+//   warps 3-10  epilogue 1 (two groups of 4 warps, one warp per TMEM lane quarter; group g takes tiles t = g mod 2):
+//               ring slot -> + b1 -> lrelu -> mask -> fp16 -> MID (smem, UMMA layout);
+//   warps 11-18 epilogue 2 (same grouping): X[t] -> + cumulative b2 -> lrelu -> mask -> fp16 -> A (the next iteration's
+//               operand); after a ResBlock's last iteration: SUM[t] (+)= X[t], then X[t] <- x0 and A <- lrelu(x0) for the
+//               next ResBlock (x0 = hi + lo read from HBM/L2 as two fp16 planar tensors: fp32-exact to 22 bits); after the
+//               last ResBlock: v = lrelu(SUM/3, 0.01); conv_post as 7 per-tap partial dot products per row into a small
+//               smem table; once per super tile the crew combines the taps across rows, tanh, stores.
+// The epilogue of one tile is a chain of shared-memory / TMEM round trips (~1.2k clk with the tensor pipe running) and
+// the kernel is bound by how many such chains are in flight, hence two tiles per crew; every hand-off is an mbarrier, and a
+// conv at tile t (which reads rows of tiles t-1 and t+1) waits for all three tiles.
 #include "umma_conv.cuh"
 #include "umma_common.cuh"
 
@@ -51,11 +52,13 @@ constexpr int kRowsA = kRows + 2 * kPadA;           // 832
 constexpr int kRowsM = kRows + 2 * kPadM;           // 784
 constexpr int kPlanes = kC / 8;
 constexpr int kRing = (512 - 2 * kC * kS) / kC;     // 4 conv1 accumulators
-constexpr int kLag = 3;                             // conv1 runs this many tiles ahead of conv2 (< kRing)
 constexpr int kWSlots = 4;
 constexpr uint32_t kTapBytes = kC * kC * 2;         // 2 KB: one tap's [K = 32][N = 32] slab
 constexpr uint32_t kWSlotBytes = 11 * kTapBytes;    // one conv, k <= 11
-constexpr int kThreads = 64 + 8 * 32;
+constexpr int kIssuers = 2;                         // MMA-issuing warps: conv1 | conv2
+constexpr int kGroups = 2;                          // tiles in flight per epilogue crew: group g takes tiles t = g (mod kGroups)
+constexpr int kCrewWarps = 4 * kGroups;             // one warp per TMEM lane quarter and group
+constexpr int kThreads = (1 + kIssuers + 2 * kCrewWarps) * 32;
 constexpr int kPostTaps = 7;
 
 constexpr uint32_t kOffA = 0;
@@ -66,10 +69,21 @@ constexpr uint32_t kOffBar = kOffP + kPostTaps * kRows * 4;
 constexpr int kNumBars = 2 * kWSlots + 2 * kRing + 3 * kS;
 constexpr uint32_t kSmemBytes = kOffBar + 8 * kNumBars + 16;
 static_assert(kSmemBytes <= 227 * 1024, "umma_mrf: shared memory");
-static_assert(kLag < kRing && kLag >= 1, "umma_mrf: lag");
+
+#ifdef VS_UMMA_TIMING
+#define VS_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = dbg ? clock64() : 0;      \
+    stmt;                                           \
+    if (dbg) var += clock64() - _t0;                \
+  } while (0)
+#else
+#define VS_TIMED(var, stmt) stmt
+#endif
 
 struct Params {
   UmmaMrf c;
+  long long* dbg;              // wait-clock counters (only with -DVS_UMMA_TIMING; tools/mrf_timing.py)
   int row_div_shift, n_super;
   float b1[3][3][kC];          // c1 biases                              [resblock][iteration][channel]
   float bcum[3][3][kC];        // cumulative c2 biases: x_m = X[t] + bcum[j][m] after iteration m
@@ -98,6 +112,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
   extern __shared__ __align__(128) uint8_t smem[];
   const UmmaMrf& c = prm.c;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef VS_UMMA_TIMING
+  long long* const dbg = prm.dbg;
+  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0;
+  const long long t_start = dbg ? clock64() : 0;
+#endif
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = smem_base + kOffA, m_base = smem_base + kOffM, w_base = smem_base + kOffW;
   const uint32_t bar = smem_base + kOffBar;
@@ -155,8 +174,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
           bulk_g2s(w_base + slot * kWSlotBytes, c.w[j][m][which], bytes, w_full(slot));
         }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform, elected lane issues)
+  } else if (warp <= kIssuers) {
+    // ------------------------------------------------------------------ MMA issuers (warp-uniform, elected lane issues)
+    // Two of them, on two schedulers: warp 1 issues every conv1 (A -> ring slot), warp 2 every conv2 (MID -> X[t],
+    // accumulate).  The streams are independent: every ordering between them is a data dependency that already goes
+    // through an mbarrier (conv2(t) waits for epilogue 1 of tiles t-1..t+1, i.e. for conv1 of those tiles; conv1 of the next
+    // iteration waits for epilogue 2 of tiles t-1..t+1, i.e. for conv2 of those tiles), so a tcgen05.commit only ever has to
+    // cover the issuing warp's own MMAs.
+    const bool is_c1 = warp == 1;
     const uint32_t idesc = make_idesc(kC);
     constexpr uint32_t b_lbo = (uint32_t)kC * 16u, b_kstep = 2u * kC;
     const uint32_t b_hi = (uint32_t)(make_desc(0, b_lbo, 128u) >> 32), b_lo_fixed = (uint32_t)make_desc(0, b_lbo, 128u);
@@ -164,67 +189,66 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
     const uint32_t a1_hi = (uint32_t)(make_desc(0, a1_lbo, 128u) >> 32), a1_lo_fixed = (uint32_t)make_desc(0, a1_lbo, 128u);
     const uint32_t a2_hi = (uint32_t)(make_desc(0, a2_lbo, 128u) >> 32), a2_lo_fixed = (uint32_t)make_desc(0, a2_lbo, 128u);
     constexpr uint32_t a1_kstep = 2u * kRowsA, a2_kstep = 2u * kRowsM;
-    uint32_t wi = 0, ring_i = 0, gen = 0;
+    uint32_t wi = is_c1 ? 0u : 1u, gen = 0;
     for (int u = blockIdx.x; u < prm.n_super; u += gridDim.x)
       for (int j = 0; j < 3; ++j)
         for (int m = 0; m < 3; ++m, wi += 2, ++gen) {
           const int taps = 3 + 4 * j, dil = 2 * m + 1;
-          const int h1 = dil * (taps - 1) / 2, h2 = (taps - 1) / 2;
-          const uint32_t s1 = wi % kWSlots, p1 = (wi / kWSlots) & 1u;
-          const uint32_t s2 = (wi + 1) % kWSlots, p2 = ((wi + 1) / kWSlots) & 1u;
+          const uint32_t ws = wi % kWSlots, wp = (wi / kWSlots) & 1u;      // this conv's weight slot
           const uint32_t pg = gen & 1u;
-          const uint32_t w1_lo = b_lo_fixed + ((w_base + s1 * kWSlotBytes) >> 4);
-          const uint32_t w2_lo = b_lo_fixed + ((w_base + s2 * kWSlotBytes) >> 4);
-          auto conv1 = [&](int t) {
-            const uint32_t slot = ring_i % kRing, rp = (ring_i / kRing) & 1u;
-            mbar_wait(a_ready(t + 1 < kS ? t + 1 : kS - 1), pg, 42);
-            mbar_wait(acc1_empty(slot), rp ^ 1u, 43);
-            if (t == 0) mbar_wait(w_full(s1), p1, 44);
-            tc_fence_after();
-            issue_tile_acc<kC / 16>(tm_ring + slot * kC, a1_lo_fixed + ((a_base + (uint32_t)(kPadA + t * kTileM - h1) * 16u) >> 4),
-                                    a1_hi, w1_lo, b_hi, idesc, taps, (uint32_t)dil, a1_kstep, b_kstep, 0u);
-            tc_commit(acc1_full(slot));
-            if (t == kS - 1) tc_commit(w_empty(s1));
-            ++ring_i;
-          };
-          auto conv2 = [&](int t) {
-            mbar_wait(mid_ready(t + 1 < kS ? t + 1 : kS - 1), pg, 45);
-            if (t == 0) mbar_wait(w_full(s2), p2, 46);
-            tc_fence_after();
-            issue_tile_acc<kC / 16>(tm_x + (uint32_t)t * kC, a2_lo_fixed + ((m_base + (uint32_t)(kPadM + t * kTileM - h2) * 16u) >> 4),
-                                    a2_hi, w2_lo, b_hi, idesc, taps, 1u, a2_kstep, b_kstep, 1u);
-            tc_commit(x_full(t));
-            if (t == kS - 1) tc_commit(w_empty(s2));
-          };
-          for (int t = 0; t < kLag; ++t) conv1(t);
-          for (int t = 0; t < kS; ++t) {
-            if (t + kLag < kS) conv1(t + kLag);
-            conv2(t);
+          const uint32_t w_lo = b_lo_fixed + ((w_base + ws * kWSlotBytes) >> 4);
+          VS_TIMED(tw3, mbar_wait(w_full(ws), wp, 44));
+          // a conv at tile t reads rows of tiles t-1, t, t+1 (reach <= 25 rows); the crews finish tiles out of order
+          // (kGroups in flight), so each of the three is waited for - t-1 and t were already seen at the previous tile
+          if (is_c1) {
+            const int h1 = dil * (taps - 1) / 2;
+            VS_TIMED(tw0, mbar_wait(a_ready(0), pg, 41));
+            for (int t = 0; t < kS; ++t) {
+              const uint32_t ring_i = gen * kS + (uint32_t)t;
+              const uint32_t slot = ring_i % kRing, rp = (ring_i / kRing) & 1u;
+              if (t + 1 < kS) VS_TIMED(tw0, mbar_wait(a_ready(t + 1), pg, 42));
+              VS_TIMED(tw1, mbar_wait(acc1_empty(slot), rp ^ 1u, 43));
+              tc_fence_after();
+              VS_TIMED(tw2, issue_tile_acc<kC / 16>(tm_ring + slot * kC, a1_lo_fixed + ((a_base + (uint32_t)(kPadA + t * kTileM - h1) * 16u) >> 4),
+                                      a1_hi, w_lo, b_hi, idesc, taps, (uint32_t)dil, a1_kstep, b_kstep, 0u));
+              tc_commit(acc1_full(slot));
+            }
+          } else {
+            const int h2 = (taps - 1) / 2;
+            VS_TIMED(tw0, mbar_wait(mid_ready(0), pg, 40));
+            for (int t = 0; t < kS; ++t) {
+              if (t + 1 < kS) VS_TIMED(tw0, mbar_wait(mid_ready(t + 1), pg, 45));
+              tc_fence_after();
+              VS_TIMED(tw2, issue_tile_acc<kC / 16>(tm_x + (uint32_t)t * kC, a2_lo_fixed + ((m_base + (uint32_t)(kPadM + t * kTileM - h2) * 16u) >> 4),
+                                      a2_hi, w_lo, b_hi, idesc, taps, 1u, a2_kstep, b_kstep, 1u));
+              tc_commit(x_full(t));
+            }
           }
+          tc_commit(w_empty(ws));           // every MMA of this conv has read its weights
         }
-  } else if (warp < 6) {
+  } else if (warp < 1 + kIssuers + kCrewWarps) {
     // ------------------------------------------------------------------ epilogue 1: ring slot -> MID = lrelu(c1 + b1)
-    const int q = warp & 3;
+    const int q = warp & 3;                               // TMEM lane quarter this warp may touch
+    const int grp = (warp - 1 - kIssuers) >> 2;           // takes tiles t = grp (mod kGroups)
     const int lrow = q * 32 + lane;                       // row within a tile = TMEM lane
     const uint32_t t_lane = tm_ring + ((uint32_t)(q * 32) << 16);
     const uint32_t mid_row = m_base + (uint32_t)(kPadM + lrow) * 16u;
-    uint32_t ring_i = 0;
+    uint32_t gen = 0;
     for (int u = blockIdx.x; u < prm.n_super; u += gridDim.x) {
       const int g0 = u * kValid - kHalo;
       uint32_t keepbits = 0;                              // rows in gaps / outside the sequence must read as zero padding
-      for (int t = 0; t < kS; ++t) {
+      for (int t = grp; t < kS; t += kGroups) {
         const int g = g0 + t * kTileM + lrow;
         if (g >= 0 && g < R && c.row_utt[g >> prm.row_div_shift] >= 0) keepbits |= 1u << t;
       }
       for (int j = 0; j < 3; ++j)
-        for (int m = 0; m < 3; ++m) {
-          float b[kC];
-#pragma unroll
-          for (int e = 0; e < kC; ++e) b[e] = prm.b1[j][m][e];
-          for (int t = 0; t < kS; ++t, ++ring_i) {
+        for (int m = 0; m < 3; ++m, ++gen) {
+          const float* b = prm.b1[j][m];
+          for (int t = grp; t < kS; t += kGroups) {
+            const uint32_t ring_i = gen * kS + (uint32_t)t;
             const uint32_t slot = ring_i % kRing, rp = (ring_i / kRing) & 1u;
             const uint32_t keep = (keepbits >> t) & 1u ? 0xFFFFFFFFu : 0u;
-            mbar_wait(acc1_full(slot), rp, 47);
+            VS_TIMED(tw0, mbar_wait(acc1_full(slot), rp, 47));
             tc_fence_after();
             uint32_t v[32];
             tmem_ld32(t_lane + slot * kC, v);
@@ -253,14 +277,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
     // ------------------------------------------------------------------ epilogue 2 / ResBlock hand-over / conv_post
     const int q = warp & 3;
     const int lrow = q * 32 + lane;
-    const int ctid = (warp - 6) * 32 + lane;              // 0..127 within the crew
+    const int grp = (warp - 1 - kIssuers - kCrewWarps) >> 2;         // takes tiles t = grp (mod kGroups)
+    const int ctid = (warp - 1 - kIssuers - kCrewWarps) * 32 + lane; // 0 .. 32 * kCrewWarps - 1 within the crew
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t a_row = a_base + (uint32_t)(kPadA + lrow) * 16u;
     float* const P = reinterpret_cast<float*>(smem + kOffP);          // [7][kRows] conv_post per-tap partial sums
     const size_t plane_elems = (size_t)R * 8;
-    // X[t] <- x0 = hi + lo,  A[t] <- lrelu(x0): the start of a ResBlock.  hi/lo were fetched by load_x0().
-    uint4 xh[kPlanes], xl[kPlanes];
-    auto load_x0 = [&](int g) {
+    // X[t] <- x0 = hi + lo,  A[t] <- lrelu(x0): the start of a ResBlock
+    auto init_tile = [&](int t, int g) {
+      uint4 xh[kPlanes], xl[kPlanes];
 #pragma unroll
       for (int pl = 0; pl < kPlanes; ++pl) { xh[pl] = make_uint4(0u, 0u, 0u, 0u); xl[pl] = make_uint4(0u, 0u, 0u, 0u); }
       if (g >= 0 && g < R) {
@@ -270,8 +295,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
           xl[pl] = *reinterpret_cast<const uint4*>(c.x_lo + (size_t)pl * plane_elems + (size_t)g * 8);
         }
       }
-    };
-    auto init_tile = [&](int t) {
       uint32_t v[32];
       const uint32_t dst = a_row + (uint32_t)(t * kTileM) * 16u;
 #pragma unroll
@@ -301,25 +324,21 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
       const bool has_next = u + (int)gridDim.x < prm.n_super;
       const int g0_next = (u + (int)gridDim.x) * kValid - kHalo;
       uint32_t keepbits = 0;
-      for (int t = 0; t < kS; ++t) {
+      for (int t = grp; t < kS; t += kGroups) {
         const int g = g0 + t * kTileM + lrow;
         if (g >= 0 && g < R && c.row_utt[g >> prm.row_div_shift] >= 0) keepbits |= 1u << t;
       }
       if (first) {
-        for (int t = 0; t < kS; ++t) { load_x0(g0 + t * kTileM + lrow); init_tile(t); }
+        for (int t = grp; t < kS; t += kGroups) init_tile(t, g0 + t * kTileM + lrow);
         first = false;
       }
       for (int j = 0; j < 3; ++j)
         for (int m = 0; m < 3; ++m, ++gen) {
           const uint32_t pg = gen & 1u;
-          float b[kC];
-#pragma unroll
-          for (int e = 0; e < kC; ++e) b[e] = prm.bcum[j][m][e];
-          for (int t = 0; t < kS; ++t) {
+          const float* b = prm.bcum[j][m];
+          for (int t = grp; t < kS; t += kGroups) {
             const uint32_t keep = (keepbits >> t) & 1u ? 0xFFFFFFFFu : 0u;
-            const bool reinit = m == 2 && (j < 2 || has_next);
-            if (reinit) load_x0((j < 2 ? g0 : g0_next) + t * kTileM + lrow);   // in flight while we wait for conv2
-            mbar_wait(x_full(t), pg, 48);
+            VS_TIMED(tw0, mbar_wait(x_full(t), pg, 48));
             tc_fence_after();
             uint32_t v[32];
             tmem_ld32(tm_x + lane_off + (uint32_t)t * kC, v);
@@ -357,39 +376,43 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
                 tmem_st32(tm_sum + lane_off + (uint32_t)t * kC, v);
               } else {
                 // xs / 3 -> leaky_relu (default slope 0.01, models.py:286) -> conv_post taps as per-row partial sums
-                float f[kC];
 #pragma unroll
                 for (int e = 0; e < kC; ++e) {
                   const float x = __uint_as_float(v[e]) * (1.f / 3.f);
-                  f[e] = keep ? fmaxf(x, 0.01f * x) : 0.f;
+                  v[e] = keep ? __float_as_uint(fmaxf(x, 0.01f * x)) : 0u;
                 }
 #pragma unroll
                 for (int tp = 0; tp < kPostTaps; ++tp) {
                   float acc = 0.f;
 #pragma unroll
-                  for (int e = 0; e < kC; ++e) acc = fmaf(f[e], prm.post_w[tp][e], acc);
+                  for (int e = 0; e < kC; ++e) acc = fmaf(__uint_as_float(v[e]), prm.post_w[tp][e], acc);
                   P[tp * kRows + t * kTileM + lrow] = acc;
                 }
               }
             }
-            if (reinit) init_tile(t);
+            if (j < 2) init_tile(t, g0 + t * kTileM + lrow);
+            else if (has_next) init_tile(t, g0_next + t * kTileM + lrow);
           }
         }
       // conv_post: out[r] = tanh(sum_tap P[tap][r + tap - 3]) for the 640 rows this super tile owns
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < kValid / 128; ++i) {
-        const int r = kHalo + i * 128 + ctid;
+      VS_TIMED(tw1, asm volatile("bar.sync 1, %0;" ::"n"(32 * kCrewWarps) : "memory"));
+      for (int r = kHalo + ctid; r < kHalo + kValid; r += 32 * kCrewWarps) {
         const int g = g0 + r;
         float acc = 0.f;
 #pragma unroll
         for (int tp = 0; tp < kPostTaps; ++tp) acc += P[tp * kRows + r + tp - 3];
         if (g < R) c.wave[g] = c.row_utt[g >> prm.row_div_shift] >= 0 ? tanhf(acc) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kCrewWarps) : "memory");
     }
   }
 
+#ifdef VS_UMMA_TIMING
+  if (dbg && lane == 0 && (warp == 1 || warp == 2 || warp == 1 + kIssuers || warp == 1 + kIssuers + kCrewWarps)) {   // [cta][conv1 | conv2 | epilogue 1 | epilogue 2][total, waits x 4]
+    long long* o = dbg + ((size_t)blockIdx.x * 4 + (warp == 1 ? 0 : warp == 2 ? 1 : warp == 1 + kIssuers ? 2 : 3)) * 5;
+    o[0] = clock64() - t_start; o[1] = tw0; o[2] = tw1; o[3] = tw2; o[4] = tw3;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -404,6 +427,7 @@ int umma_mrf(const UmmaMrf& c, cudaStream_t st) {
   VS_REQUIRE(c.x_hi && c.x_lo && c.wave && c.row_utt && c.post_w_host && c.R > 0, "umma_mrf: null pointer");
   Params prm;
   prm.c = c;
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   int s = 0;
   while ((1 << s) < c.row_div) ++s;
   VS_REQUIRE((1 << s) == c.row_div, "umma_mrf: row_div=%d must be a power of two", c.row_div);
