@@ -19,20 +19,23 @@
 // fetch floor, not by HBM).  TMEM (512 columns): X[t] 32 columns per tile (192), SUM[t] (192), and a ring of 4
 // accumulators for conv1 (128).
 //
-// Roles (608 threads):
+// Roles (864 threads):
 //   warp 0      weight producer: streams the 18 convs' weight slabs (<= 22 KB each) through a 4-slot ring, in the order
 //               the MMA warps consume them (out of L2: 252 KB per super tile);
 //   warps 1, 2  MMA issuers: warp 1 issues conv1(t) : A -> ring slot, warp 2 conv2(t) : MID -> X[t] (accumulate);
-//   warps 3-10  epilogue 1 (two groups of 4 warps, one warp per TMEM lane quarter; group g takes tiles t = g mod 2):
-//               ring slot -> + b1 -> lrelu -> mask -> fp16 -> MID (smem, UMMA layout);
-//   warps 11-18 epilogue 2 (same grouping): X[t] -> + cumulative b2 -> lrelu -> mask -> fp16 -> A (the next iteration's
-//               operand); after a ResBlock's last iteration: SUM[t] (+)= X[t], then X[t] <- x0 and A <- lrelu(x0) for the
-//               next ResBlock (x0 = hi + lo read from HBM/L2 as two fp16 planar tensors: fp32-exact to 22 bits); after the
-//               last ResBlock: v = lrelu(SUM/3, 0.01); conv_post as 7 per-tap partial dot products per row into a small
-//               smem table; once per super tile the crew combines the taps across rows, tanh, stores.
-// The epilogue of one tile is a chain of shared-memory / TMEM round trips (~1.2k clk with the tensor pipe running) and
-// the kernel is bound by how many such chains are in flight, hence two tiles per crew; every hand-off is an mbarrier, and a
-// conv at tile t (which reads rows of tiles t-1 and t+1) waits for all three tiles.
+//   warps 3-26  six TILE CREWS of four warps (one warp per TMEM lane quarter); the crew of tile t runs both epilogues of
+//               its tile, which alternate in time anyway:
+//               epilogue 1: ring slot -> + b1 -> lrelu -> mask -> fp16 -> MID (smem, UMMA layout);
+//               epilogue 2: X[t] -> + cumulative b2 -> lrelu -> mask -> fp16 -> A (the next iteration's operand); after a
+//               ResBlock's last iteration: SUM[t] (+)= X[t], then X[t] <- x0 and A <- lrelu(x0) for the next ResBlock
+//               (x0 = hi + lo read from HBM/L2 as two fp16 planar tensors: fp32-exact to 22 bits); after the last ResBlock:
+//               v = lrelu(SUM/3, 0.01); conv_post as 7 per-tap partial dot products per row into a small smem table; once
+//               per super tile all crews combine the taps across rows, tanh, store.
+// One epilogue is a chain of shared-memory / TMEM round trips (~1.2k clk with the tensor pipe running), i.e. longer than
+// the MMAs of a k = 3 conv on all six tiles (1.6k clk): the kernel is bound by how many such chains are in flight.  With
+// two crews of 2 x 4 warps (tiles round-robin) it took 7.3 ms at the C2 size, k = 3 and k = 7 iterations waiting for the
+// epilogues; one crew per tile keeps six chains in flight.  Every hand-off is an mbarrier, and a conv at tile t (which
+// reads rows of tiles t-1 and t+1) waits for all three tiles.
 #include "umma_conv.cuh"
 #include "umma_common.cuh"
 
@@ -56,9 +59,9 @@ constexpr int kWSlots = 4;
 constexpr uint32_t kTapBytes = kC * kC * 2;         // 2 KB: one tap's [K = 32][N = 32] slab
 constexpr uint32_t kWSlotBytes = 11 * kTapBytes;    // one conv, k <= 11
 constexpr int kIssuers = 2;                         // MMA-issuing warps: conv1 | conv2
-constexpr int kGroups = 2;                          // tiles in flight per epilogue crew: group g takes tiles t = g (mod kGroups)
-constexpr int kCrewWarps = 4 * kGroups;             // one warp per TMEM lane quarter and group
-constexpr int kThreads = (1 + kIssuers + 2 * kCrewWarps) * 32;
+constexpr int kCrewWarps = 4 * kS;                  // one crew of four warps (one per TMEM lane quarter) per tile
+constexpr int kThreads = (1 + kIssuers + kCrewWarps) * 32;
+static_assert(kThreads <= 1024 && 32 * kCrewWarps >= kValid, "umma_mrf: crew size");
 constexpr int kPostTaps = 7;
 
 constexpr uint32_t kOffA = 0;
@@ -66,7 +69,7 @@ constexpr uint32_t kOffM = kOffA + kPlanes * kRowsA * 16;
 constexpr uint32_t kOffW = kOffM + kPlanes * kRowsM * 16;
 constexpr uint32_t kOffP = kOffW + kWSlots * kWSlotBytes;
 constexpr uint32_t kOffBar = kOffP + kPostTaps * kRows * 4;
-constexpr int kNumBars = 2 * kWSlots + 2 * kRing + 3 * kS;
+constexpr int kNumBars = 2 * kWSlots + kRing + 4 * kS;
 constexpr uint32_t kSmemBytes = kOffBar + 8 * kNumBars + 16;
 static_assert(kSmemBytes <= 227 * 1024, "umma_mrf: shared memory");
 
@@ -104,6 +107,26 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16h(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -122,17 +145,19 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
   const uint32_t bar = smem_base + kOffBar;
   auto w_full = [&](uint32_t i) { return bar + 8u * i; };
   auto w_empty = [&](uint32_t i) { return bar + 8u * (kWSlots + i); };
-  auto acc1_full = [&](uint32_t i) { return bar + 8u * (2 * kWSlots + i); };
-  auto acc1_empty = [&](uint32_t i) { return bar + 8u * (2 * kWSlots + kRing + i); };
-  auto a_ready = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + 2 * kRing + t); };
-  auto mid_ready = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + 2 * kRing + kS + t); };
-  auto x_full = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + 2 * kRing + 2 * kS + t); };
+  // acc1_full is per TILE (phase = ResBlock iteration), not per ring slot: the tile crews wait independently of each other,
+  // and a parity wait on a slot shared with another tile could pass on that tile's completion
+  auto acc1_empty = [&](uint32_t i) { return bar + 8u * (2 * kWSlots + i); };
+  auto acc1_full = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + kRing + t); };
+  auto a_ready = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + kRing + kS + t); };
+  auto mid_ready = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + kRing + 2 * kS + t); };
+  auto x_full = [&](uint32_t t) { return bar + 8u * (2 * kWSlots + kRing + 3 * kS + t); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 8 * kNumBars);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWSlots; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
-    for (int i = 0; i < kRing; ++i) { mbar_init(acc1_full(i), 1); mbar_init(acc1_empty(i), 4); }
-    for (int t = 0; t < kS; ++t) { mbar_init(a_ready(t), 4); mbar_init(mid_ready(t), 4); mbar_init(x_full(t), 1); }
+    for (int i = 0; i < kRing; ++i) mbar_init(acc1_empty(i), 4);
+    for (int t = 0; t < kS; ++t) { mbar_init(acc1_full(t), 1); mbar_init(a_ready(t), 4); mbar_init(mid_ready(t), 4); mbar_init(x_full(t), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -199,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
           const uint32_t w_lo = b_lo_fixed + ((w_base + ws * kWSlotBytes) >> 4);
           VS_TIMED(tw3, mbar_wait(w_full(ws), wp, 44));
           // a conv at tile t reads rows of tiles t-1, t, t+1 (reach <= 25 rows); the crews finish tiles out of order
-          // (kGroups in flight), so each of the three is waited for - t-1 and t were already seen at the previous tile
+          // (one crew per tile), so each of the three is waited for - t-1 and t were already seen at the previous tile
           if (is_c1) {
             const int h1 = dil * (taps - 1) / 2;
             VS_TIMED(tw0, mbar_wait(a_ready(0), pg, 41));
@@ -211,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
               tc_fence_after();
               VS_TIMED(tw2, issue_tile_acc<kC / 16>(tm_ring + slot * kC, a1_lo_fixed + ((a_base + (uint32_t)(kPadA + t * kTileM - h1) * 16u) >> 4),
                                       a1_hi, w_lo, b_hi, idesc, taps, (uint32_t)dil, a1_kstep, b_kstep, 0u));
-              tc_commit(acc1_full(slot));
+              tc_commit(acc1_full(t));
             }
           } else {
             const int h2 = (taps - 1) / 2;
@@ -226,65 +251,23 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
           }
           tc_commit(w_empty(ws));           // every MMA of this conv has read its weights
         }
-  } else if (warp < 1 + kIssuers + kCrewWarps) {
-    // ------------------------------------------------------------------ epilogue 1: ring slot -> MID = lrelu(c1 + b1)
-    const int q = warp & 3;                               // TMEM lane quarter this warp may touch
-    const int grp = (warp - 1 - kIssuers) >> 2;           // takes tiles t = grp (mod kGroups)
-    const int lrow = q * 32 + lane;                       // row within a tile = TMEM lane
-    const uint32_t t_lane = tm_ring + ((uint32_t)(q * 32) << 16);
-    const uint32_t mid_row = m_base + (uint32_t)(kPadM + lrow) * 16u;
-    uint32_t gen = 0;
-    for (int u = blockIdx.x; u < prm.n_super; u += gridDim.x) {
-      const int g0 = u * kValid - kHalo;
-      uint32_t keepbits = 0;                              // rows in gaps / outside the sequence must read as zero padding
-      for (int t = grp; t < kS; t += kGroups) {
-        const int g = g0 + t * kTileM + lrow;
-        if (g >= 0 && g < R && c.row_utt[g >> prm.row_div_shift] >= 0) keepbits |= 1u << t;
-      }
-      for (int j = 0; j < 3; ++j)
-        for (int m = 0; m < 3; ++m, ++gen) {
-          const float* b = prm.b1[j][m];
-          for (int t = grp; t < kS; t += kGroups) {
-            const uint32_t ring_i = gen * kS + (uint32_t)t;
-            const uint32_t slot = ring_i % kRing, rp = (ring_i / kRing) & 1u;
-            const uint32_t keep = (keepbits >> t) & 1u ? 0xFFFFFFFFu : 0u;
-            VS_TIMED(tw0, mbar_wait(acc1_full(slot), rp, 47));
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(t_lane + slot * kC, v);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc1_empty(slot));   // the accumulator is in registers: hand the slot back
-            const uint32_t dst = mid_row + (uint32_t)(t * kTileM) * 16u;
-#pragma unroll
-            for (int gq = 0; gq < kPlanes; ++gq) {
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float s = __uint_as_float(v[8 * gq + e]) + b[8 * gq + e];
-                y[e] = fmaxf(s, 0.1f * s);
-              }
-              sts128(dst + (uint32_t)(gq * kRowsM) * 16u, pack_f16x2(y[0], y[1]) & keep, pack_f16x2(y[2], y[3]) & keep,
-                     pack_f16x2(y[4], y[5]) & keep, pack_f16x2(y[6], y[7]) & keep);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(mid_ready(t));
-          }
-        }
-    }
   } else {
-    // ------------------------------------------------------------------ epilogue 2 / ResBlock hand-over / conv_post
-    const int q = warp & 3;
-    const int lrow = q * 32 + lane;
-    const int grp = (warp - 1 - kIssuers - kCrewWarps) >> 2;         // takes tiles t = grp (mod kGroups)
-    const int ctid = (warp - 1 - kIssuers - kCrewWarps) * 32 + lane; // 0 .. 32 * kCrewWarps - 1 within the crew
+    // ------------------------------------------------------------------ tile crews: epilogue 1, epilogue 2, hand-over, conv_post
+    // Four warps (one per TMEM lane quarter) own ONE tile of the super tile and run both of its epilogues, which alternate
+    // in time anyway (conv1 -> epilogue 1 -> conv2 -> epilogue 2 -> next conv1).  Six tiles = six epilogue chains in flight.
+    const int q = warp & 3;                                          // TMEM lane quarter this warp may touch
+    const int t = (warp - 1 - kIssuers) >> 2;                        // the tile this crew owns
+    const int lrow = q * 32 + lane;                                  // row within the tile = TMEM lane
+    const int ctid = (warp - 1 - kIssuers) * 32 + lane;              // 0 .. 32 * kCrewWarps - 1 over all crews
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t a_row = a_base + (uint32_t)(kPadA + lrow) * 16u;
+    const uint32_t t_ring = tm_ring + lane_off;
+    const uint32_t x_addr = tm_x + lane_off + (uint32_t)t * kC, sum_addr = tm_sum + lane_off + (uint32_t)t * kC;
+    const uint32_t mid_dst = m_base + (uint32_t)(kPadM + t * kTileM + lrow) * 16u;
+    const uint32_t a_dst = a_base + (uint32_t)(kPadA + t * kTileM + lrow) * 16u;
     float* const P = reinterpret_cast<float*>(smem + kOffP);          // [7][kRows] conv_post per-tap partial sums
     const size_t plane_elems = (size_t)R * 8;
     // X[t] <- x0 = hi + lo,  A[t] <- lrelu(x0): the start of a ResBlock
-    auto init_tile = [&](int t, int g) {
+    auto init_tile = [&](int g) {
       uint4 xh[kPlanes], xl[kPlanes];
 #pragma unroll
       for (int pl = 0; pl < kPlanes; ++pl) { xh[pl] = make_uint4(0u, 0u, 0u, 0u); xl[pl] = make_uint4(0u, 0u, 0u, 0u); }
@@ -296,7 +279,6 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
         }
       }
       uint32_t v[32];
-      const uint32_t dst = a_row + (uint32_t)(t * kTileM) * 16u;
 #pragma unroll
       for (int pl = 0; pl < kPlanes; ++pl) {
         float h[8], l[8], y[8];
@@ -308,107 +290,145 @@ __global__ void __launch_bounds__(kThreads, 1) umma_mrf_kernel(const __grid_cons
           v[8 * pl + e] = __float_as_uint(x);
           y[e] = fmaxf(x, 0.1f * x);
         }
-        sts128(dst + (uint32_t)(pl * kRowsA) * 16u, pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
+        sts128(a_dst + (uint32_t)(pl * kRowsA) * 16u, pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
                pack_f16x2(y[6], y[7]));
       }
-      tmem_st32(tm_x + lane_off + (uint32_t)t * kC, v);
+      tmem_st32(x_addr, v);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready(t));
+    };
+    // x0 of the NEXT super tile comes from HBM: pull its lines into L2 an iteration ahead of the hand-over
+    auto prefetch_x0 = [&](int g) {
+      if (g >= 0 && g < R) {
+#pragma unroll
+        for (int pl = 0; pl < kPlanes; ++pl) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(c.x_hi + (size_t)pl * plane_elems + (size_t)g * 8));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(c.x_lo + (size_t)pl * plane_elems + (size_t)g * 8));
+        }
+      }
     };
     uint32_t gen = 0;
     bool first = true;
     for (int u = blockIdx.x; u < prm.n_super; u += gridDim.x) {
       const int g0 = u * kValid - kHalo;
       const bool has_next = u + (int)gridDim.x < prm.n_super;
-      const int g0_next = (u + (int)gridDim.x) * kValid - kHalo;
-      uint32_t keepbits = 0;
-      for (int t = grp; t < kS; t += kGroups) {
-        const int g = g0 + t * kTileM + lrow;
-        if (g >= 0 && g < R && c.row_utt[g >> prm.row_div_shift] >= 0) keepbits |= 1u << t;
-      }
+      const int g = g0 + t * kTileM + lrow;
+      const int g_next = (u + (int)gridDim.x) * kValid - kHalo + t * kTileM + lrow;
+      // rows in gaps / outside the sequence must read as zero padding
+      const uint32_t keep = (g >= 0 && g < R && c.row_utt[g >> prm.row_div_shift] >= 0) ? 0xFFFFFFFFu : 0u;
       if (first) {
-        for (int t = grp; t < kS; t += kGroups) init_tile(t, g0 + t * kTileM + lrow);
+        init_tile(g);
         first = false;
       }
       for (int j = 0; j < 3; ++j)
         for (int m = 0; m < 3; ++m, ++gen) {
-          const uint32_t pg = gen & 1u;
-          const float* b = prm.bcum[j][m];
-          for (int t = grp; t < kS; t += kGroups) {
-            const uint32_t keep = (keepbits >> t) & 1u ? 0xFFFFFFFFu : 0u;
-            VS_TIMED(tw0, mbar_wait(x_full(t), pg, 48));
+          // ---------------- epilogue 1: ring slot -> MID = lrelu(c1 + b1)
+          {
+            const float* b = prm.b1[j][m];
+            const uint32_t ring_i = gen * kS + (uint32_t)t;
+            const uint32_t slot = ring_i % kRing;
+            VS_TIMED(tw0, mbar_wait(acc1_full(t), gen & 1u, 47));
             tc_fence_after();
             uint32_t v[32];
-            tmem_ld32(tm_x + lane_off + (uint32_t)t * kC, v);
-            if (m < 2) {
-              // x_{m+1} = X + bcum: the next iteration's operand a = lrelu(x) (fp16), x itself stays in TMEM
-              const uint32_t dst = a_row + (uint32_t)(t * kTileM) * 16u;
+            tmem_ld32(t_ring + slot * kC, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc1_empty(slot));   // the accumulator is in registers: hand the slot back
 #pragma unroll
-              for (int gq = 0; gq < kPlanes; ++gq) {
-                float y[8];
+            for (int gq = 0; gq < kPlanes; ++gq) {
+              float y[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float s = __uint_as_float(v[8 * gq + e]) + b[8 * gq + e];
-                  y[e] = fmaxf(s, 0.1f * s);
-                }
-                sts128(dst + (uint32_t)(gq * kRowsA) * 16u, pack_f16x2(y[0], y[1]) & keep, pack_f16x2(y[2], y[3]) & keep,
-                       pack_f16x2(y[4], y[5]) & keep, pack_f16x2(y[6], y[7]) & keep);
+              for (int e = 0; e < 8; ++e) {
+                const float s = __uint_as_float(v[8 * gq + e]) + b[8 * gq + e];
+                y[e] = fmaxf(s, 0.1f * s);
               }
-              fence_proxy_async();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(a_ready(t));
-              continue;
+              sts128(mid_dst + (uint32_t)(gq * kRowsM) * 16u, pack_f16x2(y[0], y[1]) & keep, pack_f16x2(y[2], y[3]) & keep,
+                     pack_f16x2(y[4], y[5]) & keep, pack_f16x2(y[6], y[7]) & keep);
             }
-            // the ResBlock's output y_j = X + bcum[j][2]
-            if (j == 0) {
-#pragma unroll
-              for (int e = 0; e < kC; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + b[e]);
-              tmem_st32(tm_sum + lane_off + (uint32_t)t * kC, v);
-            } else {
-              uint32_t s[32];
-              tmem_ld32(tm_sum + lane_off + (uint32_t)t * kC, s);
-#pragma unroll
-              for (int e = 0; e < kC; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + b[e] + __uint_as_float(s[e]));
-              if (j == 1) {
-                tmem_st32(tm_sum + lane_off + (uint32_t)t * kC, v);
-              } else {
-                // xs / 3 -> leaky_relu (default slope 0.01, models.py:286) -> conv_post taps as per-row partial sums
-#pragma unroll
-                for (int e = 0; e < kC; ++e) {
-                  const float x = __uint_as_float(v[e]) * (1.f / 3.f);
-                  v[e] = keep ? __float_as_uint(fmaxf(x, 0.01f * x)) : 0u;
-                }
-#pragma unroll
-                for (int tp = 0; tp < kPostTaps; ++tp) {
-                  float acc = 0.f;
-#pragma unroll
-                  for (int e = 0; e < kC; ++e) acc = fmaf(__uint_as_float(v[e]), prm.post_w[tp][e], acc);
-                  P[tp * kRows + t * kTileM + lrow] = acc;
-                }
-              }
-            }
-            if (j < 2) init_tile(t, g0 + t * kTileM + lrow);
-            else if (has_next) init_tile(t, g0_next + t * kTileM + lrow);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mid_ready(t));
           }
+          if (j == 2 && m == 1 && has_next) prefetch_x0(g_next);
+          // ---------------- epilogue 2: X[t] (fp32, stays in TMEM) -> A = lrelu(X + bcum), or the ResBlock hand-over
+          const float* b = prm.bcum[j][m];
+          VS_TIMED(tw1, mbar_wait(x_full(t), gen & 1u, 48));
+          tc_fence_after();
+          if (m < 2) {
+            uint32_t v[32];
+            tmem_ld32(x_addr, v);
+#pragma unroll
+            for (int gq = 0; gq < kPlanes; ++gq) {
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float s = __uint_as_float(v[8 * gq + e]) + b[8 * gq + e];
+                y[e] = fmaxf(s, 0.1f * s);
+              }
+              sts128(a_dst + (uint32_t)(gq * kRowsA) * 16u, pack_f16x2(y[0], y[1]) & keep, pack_f16x2(y[2], y[3]) & keep,
+                     pack_f16x2(y[4], y[5]) & keep, pack_f16x2(y[6], y[7]) & keep);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready(t));
+            continue;
+          }
+          // the ResBlock's output y_j = X + bcum[j][2]; SUM (+)= y_j, in two halves of 16 channels (register budget)
+          float pacc[kPostTaps];
+#pragma unroll
+          for (int tp = 0; tp < kPostTaps; ++tp) pacc[tp] = 0.f;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[16];
+            tmem_ld16h(x_addr + 16u * hf, v);
+            if (j > 0) {
+              uint32_t s[16];
+              tmem_ld16h(sum_addr + 16u * hf, s);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + b[16 * hf + e] + __uint_as_float(s[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + b[16 * hf + e]);
+            }
+            if (j < 2) {
+              tmem_st16(sum_addr + 16u * hf, v);
+            } else {
+              // xs / 3 -> leaky_relu (default slope 0.01, models.py:286) -> conv_post taps as per-row partial sums
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float x = __uint_as_float(v[e]) * (1.f / 3.f);
+                const float f = keep ? fmaxf(x, 0.01f * x) : 0.f;
+#pragma unroll
+                for (int tp = 0; tp < kPostTaps; ++tp) pacc[tp] = fmaf(f, prm.post_w[tp][16 * hf + e], pacc[tp]);
+              }
+            }
+          }
+          if (j == 2) {
+#pragma unroll
+            for (int tp = 0; tp < kPostTaps; ++tp) P[tp * kRows + t * kTileM + lrow] = pacc[tp];
+          }
+          if (j < 2) init_tile(g);
+          else if (has_next) init_tile(g_next);
         }
       // conv_post: out[r] = tanh(sum_tap P[tap][r + tap - 3]) for the 640 rows this super tile owns
-      VS_TIMED(tw1, asm volatile("bar.sync 1, %0;" ::"n"(32 * kCrewWarps) : "memory"));
-      for (int r = kHalo + ctid; r < kHalo + kValid; r += 32 * kCrewWarps) {
-        const int g = g0 + r;
+      VS_TIMED(tw2, asm volatile("bar.sync 1, %0;" ::"n"(32 * kCrewWarps) : "memory"));
+      if (ctid < kValid) {
+        const int r = kHalo + ctid;
+        const int go = g0 + r;
         float acc = 0.f;
 #pragma unroll
         for (int tp = 0; tp < kPostTaps; ++tp) acc += P[tp * kRows + r + tp - 3];
-        if (g < R) c.wave[g] = c.row_utt[g >> prm.row_div_shift] >= 0 ? tanhf(acc) : 0.f;
+        if (go < R) c.wave[go] = c.row_utt[go >> prm.row_div_shift] >= 0 ? tanhf(acc) : 0.f;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kCrewWarps) : "memory");
     }
   }
 
 #ifdef VS_UMMA_TIMING
-  if (dbg && lane == 0 && (warp == 1 || warp == 2 || warp == 1 + kIssuers || warp == 1 + kIssuers + kCrewWarps)) {   // [cta][conv1 | conv2 | epilogue 1 | epilogue 2][total, waits x 4]
+  if (dbg && lane == 0 && (warp == 1 || warp == 2 || warp == 1 + kIssuers || warp == 1 + kIssuers + 4 * (kS / 2))) {   // [cta][conv1 | conv2 | crew of tile 0 | crew of tile kS/2][total, waits x 4]
     long long* o = dbg + ((size_t)blockIdx.x * 4 + (warp == 1 ? 0 : warp == 2 ? 1 : warp == 1 + kIssuers ? 2 : 3)) * 5;
     o[0] = clock64() - t_start; o[1] = tw0; o[2] = tw1; o[3] = tw2; o[4] = tw3;
   }
