@@ -93,8 +93,12 @@ int64_t vs_launch_count(void);
  * run on a side stream (no gain measured).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).
  * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 148*24 int64 where the tcgen05 kernels built with
  * -DVS_UMMA_TIMING leave per-CTA clocks spent waiting on each mbarrier (tools/conv_timing.py, tf32_timing.py, wn_timing.py).
- * One CUDA device per process (the library caches per-kernel attributes process-wide), as torchrun launches it. */
+ * vs_set_option sets the PROCESS DEFAULT of an option; vs_model_set_option overrides it for one model handle.  Every entry
+ * point that takes a model freezes "defaults overlaid with that model's overrides" into a thread-local snapshot for the
+ * duration of the call, so models on different threads / devices never see each other's settings, and per-kernel launch
+ * attributes are kept per device (a process may hold models on several GPUs). */
 int vs_set_option(const char* name, int64_t value);
+int vs_model_set_option(VsModel* m, const char* name, int64_t value);
 
 /* ---- weights: replaces utils.load_checkpoint (utils.py:21-51) + the implicit weight-norm fold.
  * Tensors are registered by name in the PACKED layouts listed in vispeech_b200/packing.py
@@ -107,6 +111,9 @@ int vs_model_finalize(VsModel* m);                       /* VS_ERR_MISSING if an
 
 /* workspace bytes needed by any single call below for these row counts */
 int64_t vs_workspace_bytes(const VsModel* m, int32_t n_rows_phoneme, int32_t n_rows_frame);
+/* the same split by consumer: every call except vs_hifigan_decode | vs_hifigan_decode at the given precision */
+int64_t vs_workspace_bytes_latent(const VsModel* m, int32_t n_rows_phoneme, int32_t n_rows_frame);
+int64_t vs_workspace_bytes_decoder(const VsModel* m, int32_t n_rows_frame, int32_t precision);
 
 /* ---- a3-a7: TextEncoder.forward (models.py:168-174) = embedding*sqrt(H) + 4-layer attentions.Encoder */
 int vs_text_encode(const VsModel* m, const VsRows* rows_p, const int32_t* ids_rows /*[n_rows], -1 in gaps*/,

@@ -30,11 +30,14 @@ _SIGNATURES = {
     "vs_version": (c_int32, []),
     "vs_launch_count": (c_int64, []),
     "vs_set_option": (c_int32, [c_char_p, c_int64]),
+    "vs_model_set_option": (c_int32, [c_void_p, c_char_p, c_int64]),
     "vs_model_create": (c_int32, [POINTER(VsConfig), POINTER(c_void_p)]),
     "vs_model_destroy": (None, [c_void_p]),
     "vs_model_set_tensor": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_int32]),
     "vs_model_finalize": (c_int32, [c_void_p]),
     "vs_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32]),
+    "vs_workspace_bytes_latent": (c_int64, [c_void_p, c_int32, c_int32]),
+    "vs_workspace_bytes_decoder": (c_int64, [c_void_p, c_int32, c_int32]),
     "vs_text_encode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_variance_adapter": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_int32, c_float, c_void_p, c_int32, c_float,
                                       c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

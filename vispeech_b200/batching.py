@@ -32,15 +32,22 @@ def synthesize(net, utts: Sequence[Dict], noise_scale: float = 0.667, rank: int 
     plan = plan_shards(frames, world_size)
     mine = plan.indices(rank)
     out: Dict[int, torch.Tensor] = {}
-    for batch in bucket_batches(mine, frames, max_frames_per_batch):
+    # one `infer` call takes pitch / energy controls for all of its utterances or for none: utterances are grouped by
+    # which controls they carry BEFORE bucketing, so a supplied control is never dropped (and the audio of an utterance
+    # does not depend on what it happens to share a bucket with)
+    groups: Dict[tuple, List[int]] = {}
+    for i in mine:
+        groups.setdefault((utts[i].get("f0") is not None, utts[i].get("energy") is not None), []).append(int(i))
+    batches = [b for key in sorted(groups) for b in bucket_batches(groups[key], frames, max_frames_per_batch)]
+    for batch in batches:
         sel = [utts[i] for i in batch]
         ids = _pad([u["ids"] for u in sel], torch.long)
         float_dur = any(u["duration"].is_floating_point() for u in sel)
         dur = _pad([u["duration"] for u in sel], torch.float64 if float_dur else torch.long)
         kw = {}
-        if all(u.get("f0") is not None for u in sel):
+        if sel[0].get("f0") is not None:
             kw["pitch_control"] = _pad([u["f0"] for u in sel], torch.float32)
-        if all(u.get("energy") is not None for u in sel):
+        if sel[0].get("energy") is not None:
             kw["energy_control"] = _pad([u["energy"] for u in sel], torch.float32)
         if noises is not None:
             kw["noise"] = [noises[i] for i in batch]

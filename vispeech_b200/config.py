@@ -7,36 +7,26 @@ import os
 DEFAULT_CONFIG_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs", "config.json")
 
 
-class HParams:
+class HParams(dict):
+    """Nested config with both `hps.data.hop_length` and `hps["data"]["hop_length"]` access - what the reference scripts
+    use from utils.HParams (utils.py:281-310).  A dict underneath (keys / items / values / len / in come with it); nested
+    dicts become HParams on the way in."""
+
     def __init__(self, **kwargs):
+        super().__init__()
         for k, v in kwargs.items():
-            if isinstance(v, dict):
-                v = HParams(**v)
             self[k] = v
 
-    def keys(self):
-        return self.__dict__.keys()
-
-    def items(self):
-        return self.__dict__.items()
-
-    def values(self):
-        return self.__dict__.values()
-
-    def __len__(self):
-        return len(self.__dict__)
-
-    def __getitem__(self, key):
-        return getattr(self, key)
-
     def __setitem__(self, key, value):
-        return setattr(self, key, value)
+        super().__setitem__(key, HParams(**value) if isinstance(value, dict) and not isinstance(value, HParams) else value)
 
-    def __contains__(self, key):
-        return key in self.__dict__
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError:
+            raise AttributeError(key) from None
 
-    def __repr__(self):
-        return self.__dict__.__repr__()
+    __setattr__ = __setitem__
 
 
 def get_hparams_from_file(config_path: str = DEFAULT_CONFIG_PATH) -> HParams:
@@ -44,7 +34,9 @@ def get_hparams_from_file(config_path: str = DEFAULT_CONFIG_PATH) -> HParams:
         return HParams(**json.loads(f.read()))
 
 
-N_SYMBOLS = 519   # len(text/symbols.py:22): "_" + 401 zh + 42 ja + 69 en + 6 punctuation
+from .text import symbols as _symbols
+
+N_SYMBOLS = len(_symbols)   # 519 = len(text/symbols.py:22): "_" + 401 zh + 42 ja + 69 en + 6 punctuation
 
 
 def build_from_hparams(hps: HParams, device=None):

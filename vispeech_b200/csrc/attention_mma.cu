@@ -264,17 +264,13 @@ __global__ void __launch_bounds__(128, 2) rel_attention_mma_kernel(VsRows rows, 
 
 int rel_attention_mma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out,
                       cudaStream_t st) {
-  static bool configured = false;
   const size_t smem = sizeof(Smem);
-  if (!configured) {
-    VS_CUDA_CHECK(cudaFuncSetAttribute(rel_attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VS_CUDA_CHECK(cudaFuncSetAttribute(rel_attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_mma_kernel<true>), (int)smem));
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_mma_kernel<false>), (int)smem));
   VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));   // gap rows stay zero
   VS_REQUIRE(rows.max_len > 0 && rows.max_len <= rows.n_rows, "rel_attention: bad max_len %d", rows.max_len);
   dim3 grid((rows.max_len + TQ - 1) / TQ, kHeads, rows.n_utt);
-  if (g_attention_mma == 3) rel_attention_mma_kernel<false><<<grid, 128, smem, st>>>(rows, qkv, ek, ev, out);   // plain TF32: A/B only
+  if (opts().v[OPT_ATTENTION_MMA] == 3) rel_attention_mma_kernel<false><<<grid, 128, smem, st>>>(rows, qkv, ek, ev, out);   // plain TF32: A/B only
   else rel_attention_mma_kernel<true><<<grid, 128, smem, st>>>(rows, qkv, ek, ev, out);
   VS_LAUNCH_CHECK();
   return VS_OK;

@@ -74,11 +74,31 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st);
 int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
                    const int32_t* row_utt, cudaStream_t st);
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
-// tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on g_attention_mma
+// tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on opts() "attention_mma"
 int rel_attention_mma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
-extern int g_attention_mma;                        // vs_set_option("attention_mma", 0..3), default 1 = auto
 int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,
             const int32_t* row_utt, cudaStream_t st);
+
+// Per-device launch configuration.  cudaFuncSetAttribute applies to the device that is current when it is called and a
+// process may hold models on several devices (and call from several threads: serving.py's worker), so the "done once"
+// state is kept per (kernel, device) behind a mutex instead of in function-local statics.
+int device_sm_count(int* n_sm);                            // SM count of the CURRENT device
+int ensure_dynamic_smem(const void* kernel, int bytes);    // opt in to `bytes` of dynamic shared memory, once per device
+
+// Runtime options (include/vispeech_b200.h lists them).  Two layers: process-wide defaults (vs_set_option) and per-model
+// overrides (vs_model_set_option).  Every C-ABI entry point that takes a model opens an OptionScope, which freezes
+// "defaults overlaid with that model's overrides" into a thread-local snapshot for the duration of the call: kernels'
+// host code reads opts() and never a mutable global, so two models (or two threads) cannot see each other's settings.
+enum Opt { OPT_TF32_MIN_ROWS, OPT_X3_MIN_ROWS, OPT_TF32_PRIOR, OPT_WN_FUSED, OPT_ATTENTION_MMA, OPT_TF32_CLUSTER,
+           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_COUNT };
+constexpr int64_t kOptUnset = INT64_MIN;
+struct Options { int64_t v[OPT_COUNT]; };
+const Options& opts();                                     // the executing call's snapshot (outside a scope: the defaults)
+int option_set(Options* o /*null = process defaults*/, const char* name, int64_t value);
+struct OptionScope {
+  explicit OptionScope(const Options* overrides);
+  ~OptionScope();
+};
 
 // bump allocator over the caller's workspace
 struct Workspace {

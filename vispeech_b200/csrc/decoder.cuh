@@ -41,8 +41,6 @@ int ups_taps(int stage, int* pad_l);   // taps of the polyphase form of ups[stag
 int64_t decoder_ws_floats(int n_rows_frame);
 int decode_f32(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                cudaStream_t st);
-void decoder_set_mrf_fused(int on);  // 1 (default) = last MRF stage + conv_post as one kernel (umma_mrf.cu); 0 = conv-pair chain (A/B)
-void decoder_set_streams(int n);     // 1 (default) = every launch on the caller's stream, 2 = k=11 chains on a side stream (A/B knob)
 int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                 cudaStream_t st);
 

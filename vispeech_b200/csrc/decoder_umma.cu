@@ -105,10 +105,8 @@ __global__ void conv_post_kernel(const __half* __restrict__ x, const float* __re
 // chain's CTAs - 3-5 % per pair of launches in isolation (tools/cosched_pairs.py), but nothing inside the decoder (measured
 // 25.77 vs 25.74 ms per step), so it is OFF by default.  Fork / join through events; the side chain has its own intermediate
 // buffers; the sum keeps its order (k3 + k7) + k11.
-int g_mrf_fused = 1;                     // vs_set_option("mrf_fused", 0 | 1): the last MRF stage + conv_post as ONE kernel (umma_mrf.cu)
-void decoder_set_mrf_fused(int on) { g_mrf_fused = on != 0; }
-int g_decoder_streams = 1;               // vs_set_option("decoder_streams", 1 | 2); in situ 2 gains nothing (25.77 vs 25.74 ms)
-void decoder_set_streams(int n) { g_decoder_streams = n < 2 ? 1 : 2; }
+// options "mrf_fused" (0 | 1: the last MRF stage + conv_post as ONE kernel, umma_mrf.cu) and "decoder_streams" (1 | 2; in situ 2
+// gains nothing: 25.77 vs 25.74 ms) come from opts()
 
 struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, sum = nullptr, join = nullptr; };
 static int side_stream(SideStream** out) {
@@ -133,7 +131,8 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
   const int R = rows.n_rows;
   int32_t* valid = ws.take<int32_t>(R);
   __half* zin = ws.take<__half>((int64_t)R * kHidden);
-  const bool two = g_decoder_streams == 2;
+  const bool two = opts().v[OPT_DECODER_STREAMS] == 2;
+  const bool mrf_fused = opts().v[OPT_MRF_FUSED] != 0;
   __half* buf[9];
   for (int i = 0; i < (two ? 9 : 6); ++i) buf[i] = ws.take<__half>((int64_t)R * 16384);
   if (!ws.ok) { set_error("decode_f16: workspace too small"); return VS_ERR_WORKSPACE; }
@@ -165,7 +164,7 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
     c = UmmaConv();
     // only the ACTIVATED stream a = lrelu(x) is stored between ResBlock iterations: it is the next conv's operand as
     // is, and the residual x is recovered in the c2 epilogue as min(a, a/slope) (same f16 relative rounding as storing x)
-    const bool mrf = g_mrf_fused && i == kDecStages - 1;                 // last stage: x0 in 22 bits (hi + lo), then umma_mrf
+    const bool mrf = mrf_fused && i == kDecStages - 1;                 // last stage: x0 in 22 bits (hi + lo), then umma_mrf
     c.in = NEXT; c.w = w.ups16[i].w; c.bias = w.ups16[i].b; c.out_raw = nullptr; c.out_act = XA;
     c.act_slope = 0.1f;
     if (mrf) { c.out_act = nullptr; c.out_raw = XA; c.out_lo = buf[1]; }

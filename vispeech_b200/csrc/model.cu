@@ -46,18 +46,15 @@ struct PosteriorW {                                      // enc_q (models.py:212
 //   otherwise                                                  -> fp32 CUDA cores
 // Phoneme-level convs (text encoder, predictors) never take the plain-TF32 route: their error feeds back through the
 // F0 / energy prenets (measured: z error 7.5e-3 with plain TF32 there vs 4.6e-3 without; bar 1e-2).
-static int g_tf32_min_rows = 4096;      // vs_set_option("tf32_min_rows", n)
-static int g_x3_min_rows = 512;         // vs_set_option("x3_min_rows", n)
-// The frame prior network and the projection to (m_p, logs_p) stay on 3xTF32 at every size: z_p = m_p + eps * exp(logs_p)
-// amplifies their error (measured on C4: plain TF32 there gives |dz| = 1.2e-2 > the 1e-2 bar, 3xTF32 1.4e-4).
-static int g_tf32_prior = 0;            // vs_set_option("tf32_prior", 0 | 1)
-static int g_wn_fused = 1;              // vs_set_option("wn_fused", 0 | 1): one kernel per WN layer on the plain-TF32 path (umma_wn.cu)
-
+// Options "tf32_min_rows" (4096), "x3_min_rows" (512), "tf32_prior" (0) and "wn_fused" (1) come from opts() (common.cuh).
+// The frame prior network and the projection to (m_p, logs_p) stay on 3xTF32 at every size unless tf32_prior = 1:
+// z_p = m_p + eps * exp(logs_p) amplifies their error (measured on C4: plain TF32 there gives |dz| = 1.2e-2 > the 1e-2 bar,
+// 3xTF32 1.4e-4).
 static int conv_rows(const ConvF32& c, const float* w_tf32, const float* w_x3, cudaStream_t st) {
   const bool shape_ok = !c.res && !c.accumulate && c.in_slope == 1.f && c.out_row_mul == 1 && c.out_row_off == 0 &&
                         c.out_scale == 1.f && c.act <= 1 && c.row_div == 1 && c.Cout % 32 == 0;
-  const bool use_tf32 = shape_ok && w_tf32 && c.R >= g_tf32_min_rows;
-  const bool use_x3 = shape_ok && !use_tf32 && w_x3 && c.R >= g_x3_min_rows;
+  const bool use_tf32 = shape_ok && w_tf32 && c.R >= opts().v[OPT_TF32_MIN_ROWS];
+  const bool use_x3 = shape_ok && !use_tf32 && w_x3 && c.R >= opts().v[OPT_X3_MIN_ROWS];
   if (!use_tf32 && !use_x3) return conv1d_f32(c, st);
   UmmaTf32 u;
   u.in = c.in; u.in_ld = c.in_ld; u.w = use_tf32 ? w_tf32 : w_x3; u.split3 = use_x3 ? 1 : 0; u.bias = c.bias;
@@ -70,6 +67,7 @@ static int conv_rows(const ConvF32& c, const float* w_tf32, const float* w_x3, c
 
 struct VsModel {
   VsConfig cfg;
+  vs::Options overrides;        // vs_model_set_option: kOptUnset = follow the process default
   std::unordered_map<std::string, vs::Tensor> tensors;
   bool finalized = false;
   // resolved views
@@ -240,56 +238,11 @@ const char* vs_last_error(void) { return vs::last_error(); }
 int vs_version(void) { return 1; }
 int64_t vs_launch_count(void) { return (int64_t)vs::g_launch_count; }
 
-int vs_set_option(const char* name, int64_t value) {
-  VS_REQUIRE(name, "vs_set_option: null name");
-  if (std::string(name) == "tf32_min_rows") {
-    VS_REQUIRE(value >= 1, "vs_set_option: tf32_min_rows must be >= 1");
-    vs::g_tf32_min_rows = (int)value;
-    return VS_OK;
-  }
-  if (std::string(name) == "x3_min_rows") {
-    VS_REQUIRE(value >= 1, "vs_set_option: x3_min_rows must be >= 1");
-    vs::g_x3_min_rows = (int)value;
-    return VS_OK;
-  }
-  if (std::string(name) == "tf32_prior") {
-    vs::g_tf32_prior = value != 0;
-    return VS_OK;
-  }
-  if (std::string(name) == "attention_mma") {          // 0 CUDA-core fp32 kernel, 1 auto, 2 always 3xTF32 MMA, 3 plain-TF32 MMA (A/B)
-    vs::g_attention_mma = (int)value;
-    return VS_OK;
-  }
-  if (std::string(name) == "tf32_cluster") {
-    vs::umma_tf32_set_cluster((int)value);
-    return VS_OK;
-  }
-  if (std::string(name) == "wn_fused") {
-    vs::g_wn_fused = value != 0;
-    return VS_OK;
-  }
-  if (std::string(name) == "mrf_fused") {
-    vs::decoder_set_mrf_fused((int)value);
-    return VS_OK;
-  }
-  if (std::string(name) == "decoder_streams") {
-    vs::decoder_set_streams((int)value);
-    return VS_OK;
-  }
-  if (std::string(name) == "respair_grid_div") {
-    vs::umma_respair_grid_div((int)value);
-    return VS_OK;
-  }
-  if (std::string(name) == "fused_respair") {
-    vs::umma_respair_enable((int)value);
-    return VS_OK;
-  }
-  if (std::string(name) == "umma_timing_buffer") {   // diagnostics (tools/conv_timing.py): device pointer or 0
-    vs::umma_conv_set_timing_buffer(reinterpret_cast<void*>(value));
-    return VS_OK;
-  }
-  vs::set_error("vs_set_option: unknown option '%s'", name);
-  return VS_ERR_INVALID;
+int vs_set_option(const char* name, int64_t value) { return vs::option_set(nullptr, name, value); }
+
+int vs_model_set_option(VsModel* m, const char* name, int64_t value) {
+  VS_REQUIRE(m, "vs_model_set_option: null model");
+  return vs::option_set(&m->overrides, name, value);
 }
 
 int vs_model_create(const VsConfig* cfg, VsModel** out) {
@@ -303,6 +256,7 @@ int vs_model_create(const VsConfig* cfg, VsModel** out) {
   VS_REQUIRE(n_dev > 0, "vs_model_create: no CUDA device; there is no CPU fallback");
   VsModel* m = new VsModel();
   m->cfg = *cfg;
+  for (int i = 0; i < vs::OPT_COUNT; ++i) m->overrides.v[i] = vs::kOptUnset;
   *out = m;
   return VS_OK;
 }
@@ -321,24 +275,43 @@ int vs_model_finalize(VsModel* m) {
   return vs::finalize(m);
 }
 
-int64_t vs_workspace_bytes(const VsModel* m, int32_t rp, int32_t rf) {
+// Workspace sizes.  Latent stages (text encoder ... flow, posterior encoder) and the decoder are sized separately: the
+// decoder's activation buffers dominate (fp32 cross-check decoder 5 x 16384 floats per frame row = 328 KB, the f16
+// product decoder 6 x 16384 halves = 197 KB), the latent stages need ~10 KB per row - a side-stream latent workspace must
+// not pay for a second set of decoder buffers.
+int64_t vs_workspace_bytes_latent(const VsModel* m, int32_t rp, int32_t rf) {
   (void)m;
   const int64_t H = kHidden;
   const int64_t enc_p = encoder_ws_floats(rp), enc_f = encoder_ws_floats(rf);
   const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8);
   const int64_t prior = enc_f + (int64_t)rf * 2 * H;
   const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + 2 * H);   // also covers vs_posterior_encode
-  const int64_t dec = decoder_ws_floats(rf);
   int64_t mx = variance;
   if (prior > mx) mx = prior;
   if (flow > mx) mx = flow;
-  if (dec > mx) mx = dec;
   return mx * 4 + (1 << 20);
+}
+
+int64_t vs_workspace_bytes_decoder(const VsModel* m, int32_t rf, int32_t precision) {
+  if (precision == 1) return decoder_ws_floats(rf) * 4 + (1 << 20);
+  vs::OptionScope option_scope(m ? &m->overrides : nullptr);
+  const int64_t bufs = vs::opts().v[vs::OPT_DECODER_STREAMS] == 2 ? 9 : 6;
+  return (int64_t)rf * (bufs * 16384 * 2 + kHidden * 2 + 4) + (1 << 20);
+}
+
+/* any single call, either decoder precision */
+int64_t vs_workspace_bytes(const VsModel* m, int32_t rp, int32_t rf) {
+  const int64_t lat = vs_workspace_bytes_latent(m, rp, rf);
+  int64_t dec = vs_workspace_bytes_decoder(m, rf, 1);
+  const int64_t dec16 = vs_workspace_bytes_decoder(m, rf, 0);
+  if (dec16 > dec) dec = dec16;
+  return lat > dec ? lat : dec;
 }
 
 #define VS_ENTER(m, rows, what)                                                          \
   VS_REQUIRE((m) && (m)->finalized, what ": model not finalized");                       \
   VS_TRY(check_rows(rows, what));                                                        \
+  vs::OptionScope option_scope(&(m)->overrides);                                         \
   cudaStream_t st = static_cast<cudaStream_t>(stream);                                   \
   Workspace W(ws, ws_bytes);
 
@@ -431,11 +404,12 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   if (!W.ok) { set_error("vs_frame_prior: workspace too small"); return VS_ERR_WORKSPACE; }
   if (x_frame_out != x_f)
     VS_CUDA_CHECK(cudaMemcpyAsync(x_frame_out, x_f, sizeof(float) * (size_t)R * H, cudaMemcpyDeviceToDevice, st));
-  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st, g_tf32_prior != 0));       // FramePriorNet.forward models.py:466-470
+  const bool tf32_prior = opts().v[OPT_TF32_PRIOR] != 0;
+  VS_TRY(encoder_forward(m->enc_prior, *rows, x_frame_out, W, st, tf32_prior));       // FramePriorNet.forward models.py:466-470
   ConvF32 c;                                                               // Projection.forward models.py:526-529
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
-  VS_TRY(conv_rows(c, g_tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
+  VS_TRY(conv_rows(c, tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
   return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 
@@ -443,9 +417,9 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
 struct WnBufs { float *a, *acts, *rs; };
 static int wn_forward(const WnW& w, const VsRows& rows, float* h, float* skip, const WnBufs& b, cudaStream_t st) {
   const int R = rows.n_rows, H = kHidden, L = w.n_layers;
-  const bool wn_tf32 = R >= g_tf32_min_rows, wn_x3 = !wn_tf32 && R >= g_x3_min_rows;
+  const bool wn_tf32 = R >= opts().v[OPT_TF32_MIN_ROWS], wn_x3 = !wn_tf32 && R >= opts().v[OPT_X3_MIN_ROWS];
   const bool fused_wn = wn_tf32 || wn_x3;            // tensor-core path: gate and res/skip update live in the conv epilogues
-  if (wn_tf32 && g_wn_fused) {                       // one kernel per layer on planar fp32 h / skip (umma_wn.cu)
+  if (wn_tf32 && opts().v[OPT_WN_FUSED]) {                       // one kernel per layer on planar fp32 h / skip (umma_wn.cu)
     float* hb[2] = {b.a, b.a + (size_t)R * H};       // b.a and b.rs are [R][2H] scratch of the unfused path
     float* skip_pl = b.rs;
     VS_TRY(rows_to_planar4(h, hb[0], R, H, st));

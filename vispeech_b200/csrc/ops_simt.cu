@@ -4,6 +4,8 @@
 // the decoder's dense contractions run on tcgen05 (umma_conv.cu).
 #include <stdarg.h>
 #include <cooperative_groups.h>
+#include <mutex>
+#include <unordered_set>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -19,6 +21,81 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+namespace {
+std::mutex g_cfg_mutex;
+int g_sm_count[64];                                   // 0 = not queried yet
+std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device) pairs already configured
+}  // namespace
+
+namespace {
+const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
+                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer"};
+Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0}};
+thread_local Options tl_opts;
+thread_local int tl_scope_depth = 0;
+}  // namespace
+
+const Options& opts() {
+  if (tl_scope_depth == 0) {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    tl_opts = g_defaults;
+  }
+  return tl_opts;
+}
+
+OptionScope::OptionScope(const Options* overrides) {
+  if (tl_scope_depth++ == 0) {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    tl_opts = g_defaults;
+    if (overrides)
+      for (int i = 0; i < OPT_COUNT; ++i)
+        if (overrides->v[i] != kOptUnset) tl_opts.v[i] = overrides->v[i];
+  }
+}
+OptionScope::~OptionScope() { --tl_scope_depth; }
+
+int option_set(Options* o, const char* name, int64_t value) {
+  VS_REQUIRE(name, "option: null name");
+  int idx = -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (std::string(name) == kOptNames[i]) idx = i;
+  VS_REQUIRE(idx >= 0, "unknown option '%s'", name);
+  switch (idx) {
+    case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
+    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: value = value != 0; break;
+    case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 3, "option attention_mma must be 0..3"); break;
+    case OPT_TF32_CLUSTER: case OPT_DECODER_STREAMS: value = value == 2 ? 2 : 1; break;
+    case OPT_RESPAIR_GRID_DIV: value = value < 1 ? 1 : value; break;
+    case OPT_FUSED_RESPAIR: VS_REQUIRE(value >= 0 && value <= 2, "option fused_respair must be 0..2"); break;
+    default: break;
+  }
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  (o ? o : &g_defaults)->v[idx] = value;
+  return VS_OK;
+}
+
+int device_sm_count(int* n_sm) {
+  int dev = 0;
+  VS_CUDA_CHECK(cudaGetDevice(&dev));
+  VS_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  if (!g_sm_count[dev]) VS_CUDA_CHECK(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+  *n_sm = g_sm_count[dev];
+  return VS_OK;
+}
+
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  int dev = 0;
+  VS_CUDA_CHECK(cudaGetDevice(&dev));
+  VS_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  const uint64_t key = (reinterpret_cast<uint64_t>(kernel) << 6) ^ (uint64_t)dev;
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  if (g_smem_optin.count(key)) return VS_OK;
+  VS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  g_smem_optin.insert(key);
+  return VS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // conv1d_f32: out[orow(r)][co] = f( sum_{j<k} sum_ci W[j][ci][co] * lrelu(in[r + (j-pad_l)*dil][ci]) )
@@ -463,17 +540,12 @@ static size_t attention_smem_bytes() {
   return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * AT_SLD + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
 }
 
-int g_attention_mma = 1;
-
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st) {
   // 1 = auto (tensor cores from 128 rows per utterance up), 2/3 = always MMA (3xTF32 / plain TF32), 0 = never
-  if (g_attention_mma >= 2 || (g_attention_mma == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
-  static bool configured = false;
+  const int mode = (int)opts().v[OPT_ATTENTION_MMA];
+  if (mode >= 2 || (mode == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
   const size_t smem = attention_smem_bytes();
-  if (!configured) {
-    VS_CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_kernel), (int)smem));
   // gap rows of `out` must be zero: the caller feeds out into a k=1 conv whose epilogue masks, but keep it clean
   VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));
   // grid.x covers the longest utterance; CTAs beyond an utterance's length exit immediately

@@ -475,22 +475,16 @@ int make_plan(const UmmaConv& c, Plan* out) {
 
 }  // namespace
 
-static long long* g_timing = nullptr;
-void umma_conv_set_timing_buffer(void* dev) { g_timing = static_cast<long long*>(dev); }
-void* umma_conv_timing_buffer() { return g_timing; }
+void* umma_conv_timing_buffer() { return reinterpret_cast<void*>(opts().v[OPT_TIMING_BUFFER]); }
 
 int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
-  prm.dbg = g_timing;
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   VS_TRY(make_plan(c, &prm.p));
   VS_REQUIRE(c.in && c.w && (c.out_raw || c.out_act), "umma_conv1d: null pointer");
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    VS_CUDA_CHECK(cudaGetDevice(&dev));
-    VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
   VS_REQUIRE(c.act_slope > 0.f && c.act_slope <= 1.f, "umma_conv1d: act_slope must be in (0, 1]");
   const int per_sm = prm.p.ctas_per_sm;
   int grid = n_sm * per_sm;
@@ -501,11 +495,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   VS_REQUIRE(!c.out_lo || c.out_raw, "umma_conv1d: out_lo needs out_raw");
 #define VS_UMMA_CASE(FL)                                                                                              \
   case FL: {                                                                                                          \
-    static bool cfg = false;                                                                                          \
-    if (!cfg) {                                                                                                       \
-      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      cfg = true;                                                                                                     \
-    }                                                                                                                 \
+    VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_conv1d_kernel<FL>), 227 * 1024));                   \
     umma_conv1d_kernel<FL><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);                                            \
     break;                                                                                                            \
   }
@@ -535,11 +525,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
     VS_UMMA_CASE(F_RAW | F_UP)
     VS_UMMA_CASE(F_RAW | F_UP | F_LO)
     default: {
-      static bool cfg = false;
-      if (!cfg) {
-        VS_CUDA_CHECK(cudaFuncSetAttribute(umma_conv1d_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        cfg = true;
-      }
+      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_conv1d_kernel<-1>), 227 * 1024));
       umma_conv1d_kernel<-1><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
     }
   }

@@ -33,8 +33,7 @@ struct UmmaConv {
 };
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
-void* umma_conv_timing_buffer();
-void umma_conv_set_timing_buffer(void* dev);   // diagnostics: >= 296*12 int64 of per-CTA wait clocks, or null
+void* umma_conv_timing_buffer();   // option "umma_timing_buffer": >= 296*12 int64 of per-CTA wait clocks, or null
 
 // One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
 struct UmmaPair {
@@ -68,8 +67,6 @@ struct UmmaMrf {
 int umma_mrf(const UmmaMrf& c, cudaStream_t st);
 
 bool umma_respair_supported(int C, int taps, int dil);
-void umma_respair_grid_div(int d);    // experiment knob: use 1/d of the CTA slots (co-scheduling tests)
-void umma_respair_enable(int mode);   // 0 off (default), 1 where the isolated kernel is faster, 2 wherever it fits
 int umma_respair(const UmmaPair& c, cudaStream_t st);
 
 }  // namespace vs

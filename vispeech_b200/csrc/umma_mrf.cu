@@ -465,17 +465,9 @@ int umma_mrf(const UmmaMrf& c, cudaStream_t st) {
     }
   }
   for (int i = 0; i < kPostTaps * kC; ++i) prm.post_w[i / kC][i % kC] = c.post_w_host[i];
-  int dev = 0, n_sm = 0;
-  VS_CUDA_CHECK(cudaGetDevice(&dev));
-  VS_REQUIRE(dev >= 0 && dev < 64, "umma_mrf: device index %d", dev);
-  static int sm_count[64];
-  static bool configured[64];
-  if (!configured[dev]) {
-    VS_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    VS_CUDA_CHECK(cudaFuncSetAttribute(umma_mrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    configured[dev] = true;
-  }
-  n_sm = sm_count[dev];
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_mrf_kernel), (int)kSmemBytes));
   const int grid = prm.n_super < n_sm ? prm.n_super : n_sm;
   umma_mrf_kernel<<<grid, kThreads, kSmemBytes, st>>>(prm);
   VS_LAUNCH_CHECK();

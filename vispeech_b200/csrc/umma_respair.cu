@@ -434,15 +434,13 @@ int make_plan(const UmmaPair& c, Plan* out) {
   return VS_OK;
 }
 
-int g_grid_div = 1;  // experiment knob (vs_set_option "respair_grid_div"): launch 1/div of the CTA slots, for co-scheduling tests
-int g_mode = 2;      // 0 off, 1 the C = 32 stage only, 2 (default) every ResBlock iteration whose two weight sets fit in smem
-
 }  // namespace
 
-void umma_respair_enable(int mode) { g_mode = mode; }
-void umma_respair_grid_div(int d) { g_grid_div = d < 1 ? 1 : d; }
+// options: "respair_grid_div" (experiment knob: launch 1/div of the CTA slots, for co-scheduling tests) and "fused_respair"
+// (0 off, 1 the C = 32 stage only, 2 (default) every ResBlock iteration whose two weight sets fit in smem)
 
 bool umma_respair_supported(int C, int taps, int dil) {
+  const int g_mode = (int)opts().v[OPT_FUSED_RESPAIR];
   if (g_mode == 0) return false;
   if (!(C == 32 || (C == 64 && g_mode == 2))) return false;
   UmmaPair c;
@@ -464,13 +462,9 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
     VS_CUDA_CHECK(cudaMemcpyAsync(prm.bias[1], c.b2, c.C * sizeof(float), cudaMemcpyDeviceToHost, st));
     VS_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    VS_CUDA_CHECK(cudaGetDevice(&dev));
-    VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
-  int grid = n_sm * prm.p.ctas_per_sm / g_grid_div;
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
+  int grid = n_sm * prm.p.ctas_per_sm / (int)opts().v[OPT_RESPAIR_GRID_DIV];
   if (grid < n_sm) grid = n_sm;
   if (grid > prm.p.n_tiles) grid = prm.p.n_tiles;
   int mode = M_GENERIC;
@@ -481,20 +475,12 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
   else if (c.out_act && !c.out_raw && c.res2 && scale) mode = M_ACT_RES2_SCALE;
 #define VS_PAIR_CASE(NN, MM)                                                                                          \
   if (c.C == NN && mode == MM && !(NN == 64 && prm.p.tight)) {                                                        \
-    static bool cfg = false;                                                                                          \
-    if (!cfg) {                                                                                                       \
-      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<NN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      cfg = true;                                                                                                     \
-    }                                                                                                                 \
+    VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<NN, MM>), 227 * 1024));              \
     umma_respair_kernel<NN, MM><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                \
   }
 #define VS_PAIR_TIGHT(MM)                                                                                             \
   if (c.C == 64 && mode == MM && prm.p.tight) {                                                                       \
-    static bool cfg = false;                                                                                          \
-    if (!cfg) {                                                                                                       \
-      VS_CUDA_CHECK(cudaFuncSetAttribute(umma_respair_kernel<64, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      cfg = true;                                                                                                     \
-    }                                                                                                                 \
+    VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<64, MM, true>), 227 * 1024));        \
     umma_respair_kernel<64, MM, true><<<grid, threads_for(64), prm.p.smem_bytes, st>>>(prm);                          \
   }
   VS_PAIR_CASE(32, M_ACT) else VS_PAIR_CASE(32, M_RAW) else VS_PAIR_CASE(32, M_RAW_RES2) else VS_PAIR_CASE(32, M_ACT_RES2_SCALE)

@@ -25,7 +25,7 @@ constexpr int kThreads = 32 * (kLoaderWarps + 2 + kEpiWarps);   // loaders | wei
 constexpr int kSA = 2, kMaxSB = 16;   // weight ring: as many slabs as fit (>= 3): the stream is latency-bound otherwise
 // plain TF32: 96 channels per activation stage, 32 per weight slab; 3xTF32: 48 / 16 with [hi|lo] pairs (same bytes)
 
-int g_tf32_cluster = 1;        // vs_set_option("tf32_cluster", 1 | 2): CTAs sharing each weight slab by TMA multicast (off: no gain)
+// option "tf32_cluster" (1 | 2): CTAs sharing each weight slab by TMA multicast (off: no gain)
 
 struct Plan {
   int rows_a, halo_l, n_ka, slabs_per_ka, Nblk, NB, NACC, tmem_cols, n_tiles, n_units;
@@ -467,7 +467,7 @@ int make_plan(const UmmaTf32& c, Plan* out) {
   p.smem_bytes = p.off_bar + bar_bytes;
   VS_REQUIRE(p.smem_bytes <= 227u * 1024, "umma_tf32: tile does not fit in shared memory");
   if (p.smem_bytes < 120u * 1024) p.smem_bytes = 120u * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
-  p.cl = (g_tf32_cluster == 2 && p.n_tiles >= 2) ? 2 : 1;
+  p.cl = (opts().v[OPT_TF32_CLUSTER] == 2 && p.n_tiles >= 2) ? 2 : 1;
   p.n_units = ((p.n_tiles + p.cl - 1) / p.cl) * p.NB;
   *out = p;
   return VS_OK;
@@ -475,22 +475,14 @@ int make_plan(const UmmaTf32& c, Plan* out) {
 
 }  // namespace
 
-void umma_tf32_set_cluster(int n) { g_tf32_cluster = n == 2 ? 2 : 1; }
-
 int umma_tf32(const UmmaTf32& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
   VS_REQUIRE(c.in && c.w && c.out, "umma_tf32: null pointer");
   VS_REQUIRE(c.epi != 2 || (c.out2 && c.out2_ld % 4 == 0), "umma_tf32: epi=2 needs out2");
-  static int n_sm = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    VS_CUDA_CHECK(cudaGetDevice(&dev));
-    VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    VS_CUDA_CHECK(cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_tf32_kernel), 227 * 1024));
   VS_TRY(make_plan(c, &prm.p));
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   const int cl = prm.p.cl;

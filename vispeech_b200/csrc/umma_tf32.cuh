@@ -29,7 +29,6 @@ struct UmmaTf32 {
   float* out2 = nullptr; int out2_ld = 0; int nb_split = 0; int accumulate2 = 0;
 };
 int umma_tf32(const UmmaTf32& c, cudaStream_t st);
-void umma_tf32_set_cluster(int n);   // 1 | 2 CTAs share each weight slab (TMA multicast); default 1 (no gain measured)
 
 // One whole WN layer (in_layer k5 -> gate -> res_skip 1x1 -> h / skip update) in one kernel, plain TF32.  See umma_wn.cu.
 struct UmmaWn {

@@ -376,13 +376,9 @@ int umma_wn_layer(const UmmaWn& c, cudaStream_t st) {
                reinterpret_cast<uintptr_t>(c.b_in) | reinterpret_cast<uintptr_t>(c.b_rs) | reinterpret_cast<uintptr_t>(c.cond)) & 15) == 0 &&
                  c.cond_ld % 4 == 0,
              "umma_wn_layer: pointers must be 16-byte aligned");
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    VS_CUDA_CHECK(cudaGetDevice(&dev));
-    VS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    VS_CUDA_CHECK(cudaFuncSetAttribute(umma_wn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  }
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_wn_kernel), (int)SMEM_BYTES));
   Params prm;
   prm.c = c;
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());

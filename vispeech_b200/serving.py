@@ -6,9 +6,10 @@ utterances costs about as much wall time as a handful, so here requests queue up
 into length-bucketed batches (`sharding.bucket_batches`): nothing is rejected, latency under load is one batch time.
 
 `BatchingSynthesizer.submit()` returns a `concurrent.futures.Future` of the int16 PCM (22.05 kHz by default, like the
-reference's `ffmpeg -ar 22050` output).  `create_app()` wraps it in an ASGI app with the reference's route shape
-(`GET /tts`), taking phoneme ids instead of raw text: the text front end (text/cleaner.py and its G2P dependencies) is out
-of scope for this path and plugs in front of `submit()` unchanged.
+reference's `ffmpeg -ar 22050` output); `submit_text()` puts `text.TextFrontend` (symbol table + LRU phoneme cache, the
+reference's G2P when importable) in front of it.  `create_app()` wraps both in an ASGI app with the reference's route shape:
+`GET /tts?text=...` (inference_api.py:59-65; `text` may also be a phoneme string), or `GET /tts?ids=...` for callers that
+run their own front end.
 """
 from __future__ import annotations
 
@@ -58,11 +59,47 @@ class BatchingSynthesizer:
                     None if duration is None else torch.as_tensor(duration).reshape(-1),
                     None if f0 is None else torch.as_tensor(f0).float().reshape(-1),
                     None if energy is None else torch.as_tensor(energy).float().reshape(-1), float(noise_scale))
-        if r.ids.numel() < 2:
-            r.future.set_exception(ValueError("need at least 2 phonemes (the reference fails on 1, models.py:420)"))
+        err = self._validate(r)
+        if err is not None:                      # a malformed request fails alone, never its batch
+            r.future.set_exception(ValueError(err))
             return r.future
         self._q.put(r)
         return r.future
+
+    def _validate(self, r: Request) -> Optional[str]:
+        n = int(r.ids.numel())
+        if n < 2:
+            return "need at least 2 phonemes (the reference fails on 1, models.py:420)"
+        n_vocab = getattr(self.net, "n_vocab", None)
+        n_spk = getattr(self.net, "n_speakers", None)
+        if n_vocab is not None and (int(r.ids.min()) < 0 or int(r.ids.max()) >= n_vocab):
+            return "phoneme id out of range [0, %d)" % n_vocab
+        if n_spk is not None and not (0 <= r.sid < n_spk):
+            return "sid out of range [0, %d)" % n_spk
+        for name, c in (("duration", r.duration), ("f0", r.f0), ("energy", r.energy)):
+            if c is not None and int(c.numel()) != n:
+                return "%s must have one entry per phoneme (%d), got %d" % (name, n, int(c.numel()))
+        if not (r.noise_scale >= 0.0):
+            return "noise_scale must be >= 0"
+        return None
+
+    def submit_text(self, text: str, sid: int, frontend=None, **kw) -> Future:
+        """What inference_api.py:15-19,40-47 does per request: text -> ids (cached) -> synthesis.  A front-end error
+        (unknown symbols, no G2P for raw text) fails this request's future only."""
+        fe = frontend if frontend is not None else self._frontend()
+        try:
+            ids = fe.text_to_sequence(text)
+        except (ValueError, KeyError) as e:
+            f: Future = Future()
+            f.set_exception(ValueError(str(e)))
+            return f
+        return self.submit(ids, sid, **kw)
+
+    def _frontend(self):
+        if getattr(self, "_fe", None) is None:
+            from .text import TextFrontend
+            self._fe = TextFrontend()
+        return self._fe
 
     def close(self):
         self._q.put(None)
@@ -103,10 +140,17 @@ class BatchingSynthesizer:
                         outs = self._synth(sub)
                         for r, o in zip(sub, outs):
                             r.future.set_result(o)
-                    except Exception as e:           # a failed batch must not take the server down
-                        for r in sub:
-                            if not r.future.done():
-                                r.future.set_exception(e)
+                    except Exception as e:           # a failed batch must not take the server down ...
+                        if len(sub) == 1:
+                            sub[0].future.set_exception(e)
+                            continue
+                        for r in sub:                # ... nor its innocent members: retry them one by one
+                            if r.future.done():
+                                continue
+                            try:
+                                r.future.set_result(self._synth([r])[0])
+                            except Exception as e1:
+                                r.future.set_exception(e1)
 
     def _split(self, reqs: List[Request]) -> List[List[Request]]:
         if reqs[0].duration is None:                 # frame counts unknown before the duration predictor ran
@@ -144,22 +188,28 @@ class BatchingSynthesizer:
         return [pcm[b, : (int(n[b]) + dec - 1) // dec].copy() for b in range(B)]
 
 
-def create_app(synth: BatchingSynthesizer):
-    """ASGI app with the reference's route shape: GET /tts?ids=12,7,33&sid=1[&durations=4,6,5] -> audio/wav (s16)."""
-    from fastapi import FastAPI, HTTPException, Query
+def create_app(synth: BatchingSynthesizer, frontend=None):
+    """ASGI app with the reference's route shape (inference_api.py:59-65):
+        GET /tts?text=<raw text or phoneme string>[&sid=1]        -> audio/wav (s16, 22.05 kHz)
+        GET /tts?ids=12,7,33&sid=1[&durations=4,6,5]               -> the same, ids from the caller's own front end
+    The reference hard-codes speaker 1 (inference_api.py:44); `sid` defaults to that."""
+    from fastapi import FastAPI, HTTPException
     from fastapi.responses import Response
 
     from .postprocess import wav_bytes
     app = FastAPI(title="vispeech_b200")
 
     @app.get("/tts")
-    def tts(ids: str = Query(...), sid: int = 1, durations: Optional[str] = None):
+    def tts(text: Optional[str] = None, ids: Optional[str] = None, sid: int = 1, durations: Optional[str] = None):
         try:
-            id_list = [int(v) for v in ids.split(",") if v != ""]
+            if (text is None) == (ids is None):
+                raise ValueError("pass exactly one of text= and ids=")
             dur = None if durations is None else [float(v) for v in durations.split(",")]
-            if dur is not None and len(dur) != len(id_list):
-                raise ValueError("durations must have one entry per phoneme")
-            pcm = synth.submit(id_list, sid, duration=dur).result(timeout=120)
+            if text is not None:
+                fut = synth.submit_text(text, sid, frontend=frontend, duration=dur)
+            else:
+                fut = synth.submit([int(v) for v in ids.split(",") if v != ""], sid, duration=dur)
+            pcm = fut.result(timeout=120)
         except ValueError as e:
             raise HTTPException(status_code=400, detail=str(e))
         return Response(content=wav_bytes(pcm, synth.rate_out), media_type="audio/wav")

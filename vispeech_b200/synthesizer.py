@@ -36,6 +36,10 @@ class SynthesizerTrn:
         if not torch.cuda.is_available():
             raise _lib.VsError("vispeech_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise _lib.VsError("vispeech_b200 runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if (inter_channels, hidden_channels, filter_channels, n_heads, kernel_size) != (192, 192, 768, 2, 3) or \
                 str(resblock) != "1" or list(resblock_kernel_sizes) != [3, 7, 11] or \
                 [list(d) for d in resblock_dilation_sizes] != [[1, 3, 5]] * 3 or \
@@ -69,10 +73,19 @@ class SynthesizerTrn:
         return self
 
     def to(self, device):
-        if torch.device(device) != self.device and self._loaded:
+        d = torch.device(device)
+        if d.type != "cuda":
+            raise _lib.VsError("vispeech_b200 runs on CUDA devices only")
+        if d.index is None:                      # "cuda" means the current device, like torch
+            d = torch.device("cuda", torch.cuda.current_device())
+        if d != self.device and self._loaded:
             raise _lib.VsError("move before loading weights")
-        self.device = torch.device(device)
+        self.device = d
         return self
+
+    def set_option(self, name: str, value: int) -> None:
+        """Per-model runtime option (include/vispeech_b200.h lists them); overrides the process default for this handle."""
+        check(self._lib.vs_model_set_option(self._model, name.encode(), int(value)), "vs_model_set_option(%s)" % name)
 
     def __del__(self):
         try:
@@ -96,14 +109,15 @@ class SynthesizerTrn:
 
     # -- helpers
     def _workspace(self, rp: int, rf: int) -> torch.Tensor:
-        need = int(self._lib.vs_workspace_bytes(self._model, rp, rf))
+        need = max(int(self._lib.vs_workspace_bytes_latent(self._model, rp, rf)),
+                   int(self._lib.vs_workspace_bytes_decoder(self._model, rf, int(self.decoder_precision))))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
     def _workspace_lat(self, rp: int, rf: int) -> torch.Tensor:
-        need = int(self._lib.vs_workspace_bytes(self._model, rp, rf))
+        need = int(self._lib.vs_workspace_bytes_latent(self._model, rp, rf))      # the side stream never runs a decoder
         if self._ws_lat is None or self._ws_lat.numel() < need:
             torch.cuda.synchronize(self.device)          # an older, smaller buffer may still be in use on the side stream
             self._ws_lat = None
@@ -150,6 +164,10 @@ class SynthesizerTrn:
             raise ValueError("phonemes_lengths out of range")
         if sids.min() < 0 or sids.max() >= self.n_speakers:
             raise ValueError("sid out of range")
+        for b in range(B):                         # nn.Embedding raises IndexError on these (models.py:169); so do we,
+            v = phon[b, :lens[b]]                  # instead of synthesising from a zero embedding
+            if v.min() < 0 or v.max() >= self.n_vocab:
+                raise IndexError("phoneme id out of range [0, %d) in utterance %d" % (self.n_vocab, b))
         P = Prepared()
         P.B, P.Tp, P.lens, P.sids = B, Tp, lens, sids
         P.noise_scale, P.max_len = float(noise_scale), (-1 if max_len is None else int(max_len))
