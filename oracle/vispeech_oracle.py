@@ -1,4 +1,6 @@
-"""CPU fp32 restatement of `SynthesizerTrn.infer` (reference models.py:672-722).
+"""CPU fp32 restatement of `SynthesizerTrn.infer` (reference models.py:672-722).  Device-agnostic: with a state dict on
+`cuda` the same eager op sequence runs on the GPU - bench.py's clearly-labelled `gpu_eager_baseline` (what the reference's
+own ATen / cuDNN path would do on this box), never the product path.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): the checker for the CUDA path and the
 `cpu_baseline` of bench.py.  It is a *restatement*, not an import: `/root/reference` does
@@ -53,20 +55,20 @@ def relative_attention(sd, p, x, cfg: ModelConfig):
     ek = sd[p + ".emb_rel_k"][0]                               # [2w+1, dk], shared by heads (:125-128)
     ev = sd[p + ".emb_rel_v"][0]
     rel = torch.matmul(q, ek.t())                              # [nh, T, 2w+1]
-    idx = torch.arange(T)
+    idx = torch.arange(T, device=x.device)
     band = idx[None, :] - idx[:, None]                         # j - i
     inband = band.abs() <= w
     bidx = (band + w).clamp(0, 2 * w)
     scores = scores + torch.where(inband[None], torch.gather(rel, 2, bidx[None].expand(nh, T, T)),
-                                  torch.zeros((), dtype=x.dtype))
+                                  torch.zeros((), dtype=x.dtype, device=x.device))
     pr = F.softmax(scores, dim=-1)                             # (:171)
     out = torch.matmul(pr, v)                                  # [nh, T, dk]
     # relative values: weights on the band only (:174-177)
-    pb = torch.zeros(nh, T, 2 * w + 1, dtype=x.dtype)
+    pb = torch.zeros(nh, T, 2 * w + 1, dtype=x.dtype, device=x.device)
     for d in range(-w, w + 1):
         lo, hi = max(0, -d), min(T, T - d)
         if hi > lo:
-            ii = torch.arange(lo, hi)
+            ii = torch.arange(lo, hi, device=x.device)
             pb[:, ii, d + w] = pr[:, ii, ii + d]
     out = out + torch.matmul(pb, ev)
     out = out.transpose(1, 2).contiguous().view(1, H, T)       # (:178)
@@ -142,7 +144,7 @@ def expansion_counts(duration: torch.Tensor) -> torch.Tensor:
 def expansion_indices(duration: torch.Tensor) -> torch.Tensor:
     """Frame t copies phoneme idx[t] (models.py:418-427 `expand` + cat)."""
     n = expansion_counts(duration)
-    return torch.repeat_interleave(torch.arange(n.numel()), n)
+    return torch.repeat_interleave(torch.arange(n.numel(), device=n.device), n)
 
 
 def wn(sd, p, x, g, cfg: ModelConfig, n_layers=None):
@@ -299,7 +301,7 @@ def infer_one(sd: Dict[str, torch.Tensor], ids: torch.Tensor, sid: int, noise_sc
     Tf = idx.numel()
     x_frame = x[:, :, idx]
     taps["x_lr"] = x_frame[0].clone()
-    taps["x_mask"] = torch.ones(1, Tf, dtype=torch.bool)                      # :713 (bool, Q5)
+    taps["x_mask"] = torch.ones(1, Tf, dtype=torch.bool, device=x.device)                      # :713 (bool, Q5)
     if stop_after == "lr":
         return taps
 
@@ -308,7 +310,7 @@ def infer_one(sd: Dict[str, torch.Tensor], ids: torch.Tensor, sid: int, noise_sc
     stats = F.conv1d(x_frame, sd["project.proj.weight"], sd["project.proj.bias"])     # :717
     m_p, logs_p = stats[:, :cfg.inter_channels], stats[:, cfg.inter_channels:]
     if noise is None:
-        noise = torch.randn(cfg.inter_channels, Tf)
+        noise = torch.randn(cfg.inter_channels, Tf, device=x.device)
     z_p = m_p + noise.reshape(1, cfg.inter_channels, Tf) * torch.exp(logs_p) * noise_scale   # :718
     taps.update(m_p=m_p[0], logs_p=logs_p[0], z_p=z_p[0])
     if stop_after == "prior":

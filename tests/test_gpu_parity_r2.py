@@ -1,0 +1,144 @@
+"""GPU parity at the sizes BASELINE.json names (round-1 review: the bench batch itself, C5 at 256 utterances and the C3
+latents were never compared with the oracle; the serving test compared the server with `infer` itself)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def net(state_dict):
+    from vispeech_b200 import build_from_hparams, get_hparams_from_file
+    n = build_from_hparams(get_hparams_from_file(), device="cuda:0")
+    n.load_state_dict(state_dict)
+    return n
+
+
+def snr_db(ref, x):
+    ref, x = ref.double().reshape(-1), x.double().reshape(-1)
+    return float(10 * torch.log10((ref ** 2).sum() / ((ref - x) ** 2).sum().clamp_min(1e-300)))
+
+
+def _pad(utts, key, dtype):
+    tp = max(u["ids"].numel() for u in utts)
+    out = torch.zeros(len(utts), tp, dtype=dtype)
+    for b, u in enumerate(utts):
+        out[b, : u[key].numel()] = u[key].to(dtype)
+    return out
+
+
+def test_bench_batch_b64_matches_oracle(net, state_dict):
+    """The exact configs[1] batch bench.py times on rank 0 (oracle.inputs.c2(batch=64, seed=1): 64 utterances, 27.6 k frame
+    rows, i.e. every precision regime the bench runs in: TF32 flow, 3xTF32 frame prior / phoneme level, fp16 decoder with the
+    fp32-residual last stage), with injected noise, against per-utterance oracle runs of three of its utterances."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import infer_one
+    utts = oin.c2(batch=64, seed=1)
+    frames = oin.frame_counts(utts)
+    noises = oin.draw_noise(frames, 77)
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = net.infer(
+        _pad(utts, "ids", torch.long), torch.LongTensor([u["ids"].numel() for u in utts]),
+        sid=torch.LongTensor([u["sid"] for u in utts]), noise_scale=0.667, duration_control=_pad(utts, "duration", torch.long),
+        noise=noises)
+    torch.cuda.synchronize()
+    assert int(x_mask.sum()) == sum(frames)
+    worst = {"z": 0.0, "m_p": 0.0, "logs_p": 0.0, "f0": 0.0, "snr": 1e9}
+    for b in (0, 31, 63):
+        u, tf = utts[b], frames[b]
+        ref = infer_one(state_dict, u["ids"], u["sid"], 0.667, noises[b], duration_control=u["duration"])
+        worst["z"] = max(worst["z"], float((z[b, :, :tf].cpu() - ref["z"]).abs().max()))
+        worst["m_p"] = max(worst["m_p"], float((m_p[b, :, :tf].cpu() - ref["m_p"]).abs().max()))
+        worst["logs_p"] = max(worst["logs_p"], float((logs_p[b, :, :tf].cpu() - ref["logs_p"]).abs().max()))
+        worst["f0"] = max(worst["f0"], float((f0[b, : u["ids"].numel()].cpu() - ref["F0"]).abs().max()))
+        worst["snr"] = min(worst["snr"], snr_db(ref["o"], o[b, 0, : tf * 512].cpu()))
+        assert float(o[b, 0, tf * 512:].abs().max() if tf * 512 < o.shape[2] else 0) == 0
+    print("bench batch (B=64) worst case over 3 utterances:", worst)
+    assert worst["z"] <= 1e-2 and worst["m_p"] <= 1e-2 and worst["logs_p"] <= 1e-2 and worst["f0"] <= 5e-2 and worst["snr"] >= 30.0, worst
+
+
+def test_c5_b256_all_indices_exact(net, state_dict):
+    """configs[4] at the size BASELINE.json names: 256 manual-edit utterances (float / zero / negative / very long durations,
+    F0 and energy given).  Every utterance's expansion indices must equal the reference rule exactly (models.py:418-427);
+    latents of two utterances against the oracle."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import expansion_indices, infer_one
+    utts = oin.c5(batch=256, seed=4)
+    frames = [int(expansion_indices(u["duration"]).numel()) for u in utts]
+    noises = oin.draw_noise(frames, 55)
+    P = net.prepare(_pad(utts, "ids", torch.long), torch.LongTensor([u["ids"].numel() for u in utts]),
+                    sid=torch.LongTensor([u["sid"] for u in utts]), noise_scale=0.667,
+                    duration_control=_pad(utts, "duration", torch.float64), pitch_control=_pad(utts, "f0", torch.float32),
+                    energy_control=_pad(utts, "energy", torch.float32), noise=noises)
+    z, rf = net.run(P, outputs="latents")                    # everything up to the decoder, one call for all 256
+    torch.cuda.synchronize()
+    idx = net.last_lr_index.cpu().numpy()
+    covered = np.zeros(rf.n_rows, bool)
+    for b, u in enumerate(utts):
+        want = expansion_indices(u["duration"]).numpy()
+        s, n = int(rf.starts[b]), int(rf.lengths[b])
+        assert n == want.size and np.array_equal(idx[s:s + n], want), b
+        covered[s:s + n] = True
+    assert (idx[~covered] == -1).all() and int(covered.sum()) == sum(frames)
+    zc = z.cpu()
+    for b in (17, 200):
+        u = utts[b]
+        ref = infer_one(state_dict, u["ids"], u["sid"], 0.667, noises[b], duration_control=u["duration"], pitch_control=u["f0"],
+                        energy_control=u["energy"], stop_after="flow")
+        s, n = int(rf.starts[b]), int(rf.lengths[b])
+        assert float((zc[s:s + n].t() - ref["z"]).abs().max()) <= 1e-2, b
+
+
+def test_c3_sampled_latents_match_oracle(net, state_dict):
+    """configs[2]: five of the 512 mixed-length (1-15 s) utterances as ONE ragged call - m_p, z and the waveform of each
+    against its batch-1 oracle run (the round-1 C3 test only checked waveforms)."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import infer_one
+    utts_all = oin.c3(batch=512, seed=2)
+    pick = [3, 77, 200, 311, 508]
+    utts = [utts_all[i] for i in pick]
+    frames = oin.frame_counts(utts)
+    noises = [oin.draw_noise([frames[k]], 1000 + i)[0] for k, i in enumerate(pick)]
+    o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = net.infer(
+        _pad(utts, "ids", torch.long), torch.LongTensor([u["ids"].numel() for u in utts]),
+        sid=torch.LongTensor([u["sid"] for u in utts]), noise_scale=0.667,
+        duration_control=_pad(utts, "duration", torch.float64 if any(u["duration"].is_floating_point() for u in utts) else torch.long),
+        noise=noises)
+    torch.cuda.synchronize()
+    for b, u in enumerate(utts):
+        tf = frames[b]
+        ref = infer_one(state_dict, u["ids"], u["sid"], 0.667, noises[b], duration_control=u["duration"])
+        assert float((m_p[b, :, :tf].cpu() - ref["m_p"]).abs().max()) <= 1e-2, b
+        assert float((z[b, :, :tf].cpu() - ref["z"]).abs().max()) <= 1e-2, b
+        assert snr_db(ref["o"], o[b, 0, : tf * 512].cpu()) >= 30.0, b
+
+
+def test_serving_queue_matches_oracle_and_numpy_pcm(net, state_dict):
+    """8(f) ranks 1-2 against the ORACLE: requests through the batching server (text route included) come back as the
+    s16 / 22.05 kHz stream that the oracle's waveform gives under a float64 numpy statement of the post-processing."""
+    from oracle.vispeech_oracle import infer_one
+    from vispeech_b200.postprocess import halfband_fir
+    from vispeech_b200.serving import BatchingSynthesizer
+    from vispeech_b200.text import cleaned_text_to_sequence
+    g = torch.Generator().manual_seed(12)
+    srv = BatchingSynthesizer(net, max_batch=16, max_wait_ms=20)
+    reqs = [(torch.randint(1, 500, (8 + 3 * i,), generator=g), 10 * i, torch.randint(2, 9, (8 + 3 * i,), generator=g)) for i in range(5)]
+    futs = [srv.submit(ids, sid, duration=dur, noise_scale=0.0) for ids, sid, dur in reqs]
+    phones = "n i3 h ao3 sp sh iii4 j ie4".split()
+    t_dur = torch.randint(3, 9, (len(phones),), generator=g)
+    futs.append(srv.submit_text(" ".join(phones), 1, duration=t_dur, noise_scale=0.0))
+    reqs.append((torch.LongTensor(cleaned_text_to_sequence(phones)), 1, t_dur))
+    outs = [f.result(timeout=120) for f in futs]
+    srv.close()
+    h = halfband_fir().astype(np.float64)
+    for (ids, sid, dur), got in zip(reqs, outs):
+        tf = int(dur.sum())
+        ref = infer_one(state_dict, ids, sid, 0.0, torch.zeros(192, tf), duration_control=dur)["o"].double().numpy().reshape(-1)
+        n = ref.size
+        xb = np.zeros(n + 64)
+        xb[31:31 + n] = ref
+        t_out = (n + 1) // 2
+        dec = np.array([np.dot(h, xb[2 * t: 2 * t + 63]) for t in range(t_out)])
+        want = np.clip(np.rint(dec * 32768.0), -32768, 32767)
+        assert got.dtype == np.int16 and got.shape[0] == t_out
+        assert snr_db(torch.from_numpy(want), torch.from_numpy(got.astype(np.float64))) >= 30.0

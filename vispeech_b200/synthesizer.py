@@ -289,6 +289,8 @@ class SynthesizerTrn:
             for t in (z, z_p, m_p, logs_p, dur, f0, energy, lr_index, rf.row_utt, rp.row_utt):
                 if t is not None:
                     t.record_stream(main)      # allocated on the side stream, read by the decoder / unpack kernels on `main`
+        self.last_rows = (rp, rf)
+        self.last_lr_index = lr_index
         if outputs == "latents":               # infer_stream: the decoder runs chunk by chunk on these rows
             if timings is not None:
                 timings["_events"] = ev
@@ -321,8 +323,6 @@ class SynthesizerTrn:
             else:
                 o = unpack(wave, 1, self.hop_length, t_dec * self.hop_length)
             mark("unpack", main)
-            self.last_rows = (rp, rf)
-            self.last_lr_index = lr_index
             if timings is not None:
                 timings["_events"] = ev
             x_mask = (torch.arange(Tf, device=dev)[None, :] < P.frames_dev()[:, None])[:, None, :]
