@@ -271,7 +271,7 @@ def test_voice_conversion_matches_reference_golden():
 def test_pcm16_postprocess_and_serving_queue(net):
     """8(f) ranks 1-2: float -> s16 (exact integer rule), 2:1 FIR decimation (vs a float64 numpy statement of the same
     FIR; +-1 LSB from fp32 accumulation), and the batching server returning what a direct call returns."""
-    from vispeech_b200.postprocess import halfband_fir, to_pcm16
+    from vispeech_b200.postprocess import decimate_reference, default_fir, halfband_fir, to_pcm16
     from vispeech_b200.serving import BatchingSynthesizer
     g = torch.Generator().manual_seed(4)
     x = (torch.rand(3, 1, 5000, generator=g) * 2.4 - 1.2).cuda()         # some samples clip
@@ -282,15 +282,14 @@ def test_pcm16_postprocess_and_serving_queue(net):
         ref = np.clip(np.rint(xc[b].astype(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
         ref[n[b]:] = 0
         assert np.array_equal(p44[b], ref)
-    p22 = to_pcm16(x, n, 44100, 22050).cpu().numpy()
-    h = halfband_fir().astype(np.float64)
-    for b in range(3):
-        xb = np.zeros(5000 + 64)
-        xb[31:31 + n[b]] = xc[b, :n[b]]
-        full = np.array([np.dot(h, xb[2 * t: 2 * t + 63]) for t in range(2500)])
-        ref = np.clip(np.rint(full * 32768.0), -32768, 32767)
-        d = np.abs(p22[b].astype(np.int64) - ref.astype(np.int64))
-        assert d.max() <= 1 and (d == 0).mean() > 0.99
+    for fir_name, h in (("swr", default_fir()), ("halfband", halfband_fir())):       # libswresample's default design | round 1's
+        p22 = to_pcm16(x, n, 44100, 22050, fir=fir_name).cpu().numpy()
+        for b in range(3):
+            xb = np.zeros(5000)
+            xb[:n[b]] = xc[b, :n[b]]
+            ref = np.clip(np.rint(decimate_reference(xb, h) * 32768.0), -32768, 32767)
+            d = np.abs(p22[b].astype(np.int64) - ref.astype(np.int64))
+            assert d.max() <= 1 and (d == 0).mean() > 0.99, fir_name
     # serving queue: 10 concurrent requests come back equal to direct synthesis of the same inputs (noise_scale 0)
     srv = BatchingSynthesizer(net, max_batch=16, max_wait_ms=20)
     reqs = [(torch.randint(1, 500, (6 + i,), generator=g), i, torch.randint(2, 6, (6 + i,), generator=g)) for i in range(10)]

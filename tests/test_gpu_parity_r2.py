@@ -117,7 +117,7 @@ def test_serving_queue_matches_oracle_and_numpy_pcm(net, state_dict):
     """8(f) ranks 1-2 against the ORACLE: requests through the batching server (text route included) come back as the
     s16 / 22.05 kHz stream that the oracle's waveform gives under a float64 numpy statement of the post-processing."""
     from oracle.vispeech_oracle import infer_one
-    from vispeech_b200.postprocess import halfband_fir
+    from vispeech_b200.postprocess import decimate_reference, default_fir
     from vispeech_b200.serving import BatchingSynthesizer
     from vispeech_b200.text import cleaned_text_to_sequence
     g = torch.Generator().manual_seed(12)
@@ -130,15 +130,11 @@ def test_serving_queue_matches_oracle_and_numpy_pcm(net, state_dict):
     reqs.append((torch.LongTensor(cleaned_text_to_sequence(phones)), 1, t_dur))
     outs = [f.result(timeout=120) for f in futs]
     srv.close()
-    h = halfband_fir().astype(np.float64)
+    h = default_fir()
     for (ids, sid, dur), got in zip(reqs, outs):
         tf = int(dur.sum())
         ref = infer_one(state_dict, ids, sid, 0.0, torch.zeros(192, tf), duration_control=dur)["o"].double().numpy().reshape(-1)
-        n = ref.size
-        xb = np.zeros(n + 64)
-        xb[31:31 + n] = ref
-        t_out = (n + 1) // 2
-        dec = np.array([np.dot(h, xb[2 * t: 2 * t + 63]) for t in range(t_out)])
-        want = np.clip(np.rint(dec * 32768.0), -32768, 32767)
+        t_out = (ref.size + 1) // 2
+        want = np.clip(np.rint(decimate_reference(ref, h) * 32768.0), -32768, 32767)
         assert got.dtype == np.int16 and got.shape[0] == t_out
         assert snr_db(torch.from_numpy(want), torch.from_numpy(got.astype(np.float64))) >= 30.0

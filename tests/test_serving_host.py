@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-from vispeech_b200.postprocess import halfband_fir, wav_bytes
+from vispeech_b200.postprocess import decimate_reference, default_fir, halfband_fir, swr_kaiser_fir, wav_bytes
 from vispeech_b200.serving import BatchingSynthesizer
 
 
@@ -61,3 +61,24 @@ def test_wav_container_and_fir():
     H = np.abs(np.fft.rfft(h, 4096))
     f = np.fft.rfftfreq(4096)                               # cycles/sample at 44.1 kHz
     assert H[f < 0.20].min() > 0.99 and H[f > 0.30].max() < 1e-3     # flat to 8.8 kHz, > 60 dB down above 13.2 kHz
+
+
+def test_swr_default_filter_design_and_decimation_pin():
+    """The resampler is pinned to a definition, not to itself: (a) the restated libswresample default design (filter_size 32,
+    cutoff 0.97, Kaiser beta 9 -> 66 taps, peak at tap 32, unit DC gain, flat to 8.5 kHz, -6 dB at 0.97 x the new Nyquist, > 80 dB down above 13 kHz);
+    (b) the float64 statement the kernel is tested against equals an independent implementation (scipy's correlate + slicing)."""
+    from scipy import signal
+    h = swr_kaiser_fir()
+    assert h.shape == (66,) and int(np.argmax(h)) == 32 and abs(float(h.sum()) - 1) < 1e-6 and np.array_equal(h, default_fir())
+    assert np.allclose(h[32 - 30: 32], h[32 + 30: 32: -1], atol=1e-8)          # symmetric around the peak (even length: one extra tap)
+    H = np.abs(np.fft.rfft(h.astype(np.float64), 8192))
+    f = np.fft.rfftfreq(8192) * 44100
+    assert H[f < 8500].min() > 0.9999 and abs(H[np.argmin(np.abs(f - 0.97 * 11025))] - 0.5) < 0.02 and H[f > 13000].max() < 1e-4
+    g = np.random.default_rng(0)
+    x = g.standard_normal(4001)
+    want = decimate_reference(x, h)
+    c = (h.size - 1) // 2
+    xz = np.concatenate([np.zeros(c), x, np.zeros(h.size)])
+    alt = signal.correlate(xz, h.astype(np.float64), mode="valid")[::2][: want.size]
+    assert want.shape == (2001,) and np.abs(want - alt).max() < 1e-12
+    assert np.abs(decimate_reference(x, halfband_fir())[5:-5] - signal.correlate(np.concatenate([np.zeros(31), x, np.zeros(63)]), halfband_fir().astype(np.float64), mode="valid")[::2][5:1996]).max() < 1e-12

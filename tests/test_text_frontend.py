@@ -129,7 +129,7 @@ def test_batching_groups_by_control_signature():
     calls = []
 
     class Net:
-        hop_length = 512
+        hop_length, sampling_rate, device = 512, 44100, torch.device("cpu")
 
         def infer(self, ids, lens, sid=None, noise_scale=1, duration_control=None, outputs="all", pitch_control=None,
                   energy_control=None, noise=None):
@@ -145,7 +145,9 @@ def test_batching_groups_by_control_signature():
         if i % 3 == 0:
             u["energy"] = torch.full((4,), 50.0)
         utts.append(u)
-    out = batching.synthesize(Net(), utts)
+    stats = {}
+    out = batching.synthesize(Net(), utts, keep_on_device=True, stats=stats)
+    assert stats["infer_calls"] == 4 and stats["utterances"] == 6 and abs(stats["imbalance"] - 1) < 1e-9
     assert sorted(out) == list(range(6))
     assert sorted(calls) == sorted([(1, True, True), (2, True, False), (1, False, True), (2, False, False)])
 

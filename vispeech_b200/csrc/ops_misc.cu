@@ -434,7 +434,7 @@ int mel_unpack(const VsRows& rows, const float* x, int ld, int C, int t_max, int
 }
 
 // ---- 8(f) waveform post-processing (reference inference_api.py:50-51: scipy wav write + `ffmpeg -ar 22050`) ------------
-// out[b][t] = s16( sum_k fir[k] * x[b][decimate*t + k - ntaps/2] ), samples outside [0, n_samples[b]) are zero;
+// out[b][t] = s16( sum_k fir[k] * x[b][decimate*t + k - (ntaps-1)/2] ), samples outside [0, n_samples[b]) are zero;
 // decimate == 1 and ntaps == 0: plain float -> s16.  s16(v) = clip(rint(v * 32768)) (round half to even), ffmpeg's rule.
 __global__ void pcm16_kernel(const float* __restrict__ x, int T, const int32_t* __restrict__ n_samples, int decimate,
                              const float* __restrict__ fir, int ntaps, int16_t* __restrict__ out, int T_out) {
@@ -451,7 +451,7 @@ __global__ void pcm16_kernel(const float* __restrict__ x, int T, const int32_t* 
     const int i = decimate * t;
     v = (i < n && i < T) ? xb[i] : 0.f;
   } else {
-    const int c = decimate * t - ntaps / 2;
+    const int c = decimate * t - (ntaps - 1) / 2;
     for (int k = 0; k < ntaps; ++k) {
       const int i = c + k;
       if (i >= 0 && i < n && i < T) v = fmaf(taps[k], xb[i], v);
