@@ -138,8 +138,10 @@ int vs_length_regulate_count(const VsRows* rows_p, const double* duration /*[n_r
 int vs_length_regulate_gather(const VsRows* rows_p, const VsRows* rows_f, const float* x_p, const int32_t* cum,
                               float* x_f /*[rows_f.n_rows][192]*/, int32_t* lr_index /*[rows_f.n_rows]*/, void* stream);
 
-/* ---- a14-a16: FramePriorNet + Projection + prior sample (models.py:715-718) */
-int vs_frame_prior(const VsModel* m, const VsRows* rows_f, const float* x_f, const float* noise /*[n_rows][192]*/,
+/* ---- a14-a16: FramePriorNet + Projection + prior sample (models.py:715-718).
+ * noise: the eps of models.py:718 ([n_rows][192], injected for parity runs) or NULL = drawn inside the sampling kernel from
+ * a counter-based Philox4x32-10 stream keyed by noise_seed (N(0,1) by Box-Muller; the same seed gives the same eps). */
+int vs_frame_prior(const VsModel* m, const VsRows* rows_f, const float* x_f, const float* noise, uint64_t noise_seed,
                    float noise_scale, float* x_frame_out, float* m_p, float* logs_p, float* z_p,
                    void* ws, int64_t ws_bytes, void* stream);
 
@@ -149,8 +151,8 @@ int vs_flow_reverse(const VsModel* m, const VsRows* rows_f, float* z, void* ws, 
 /* ---- 8(f) voice_conversion (models.py:724-732): PosteriorEncoder.forward (models.py:233-241) on a linear spectrogram
  * laid out as ragged rows [n_rows][c_in] (c_in = spec channels zero-padded to a multiple of 96, see packing.py), and the
  * flow in forward direction (models.py:203-205), in place.  Needs the enc_q.* tensors (VS_ERR_MISSING otherwise). */
-int vs_posterior_encode(const VsModel* m, const VsRows* rows_f, const float* spec, const float* noise /*[n_rows][192]*/,
-                        float* z, float* m_q, float* logs_q, void* ws, int64_t ws_bytes, void* stream);
+int vs_posterior_encode(const VsModel* m, const VsRows* rows_f, const float* spec, const float* noise /*[n_rows][192] or NULL*/,
+                        uint64_t noise_seed, float* z, float* m_q, float* logs_q, void* ws, int64_t ws_bytes, void* stream);
 int vs_flow_forward(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- a18: HiFi-GAN Generator (models.py:271-290).  max_len < 0 = no truncation (models.py:720).

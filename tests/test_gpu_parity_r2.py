@@ -138,3 +138,28 @@ def test_serving_queue_matches_oracle_and_numpy_pcm(net, state_dict):
         want = np.clip(np.rint(decimate_reference(ref, h) * 32768.0), -32768, 32767)
         assert got.dtype == np.int16 and got.shape[0] == t_out
         assert snr_db(torch.from_numpy(want), torch.from_numpy(got.astype(np.float64))) >= 30.0
+
+
+def test_in_kernel_philox_noise_is_standard_normal_and_seeded(net):
+    """a16: without an injected eps the sampling kernel draws it itself (Philox4x32-10 + Box-Muller, csrc/ops_misc.cu).
+    Recovered from the outputs, eps = (z_p - m_p) / (exp(logs_p) noise_scale) must be N(0, 1), reproducible under
+    torch.manual_seed and different from call to call."""
+    from oracle import inputs as oin
+    utts = oin.c2(batch=8, seed=3)
+    args = (_pad(utts, "ids", torch.long), torch.LongTensor([u["ids"].numel() for u in utts]))
+    kw = dict(sid=torch.LongTensor([u["sid"] for u in utts]), noise_scale=0.667, duration_control=_pad(utts, "duration", torch.long))
+
+    def eps_of(seed):
+        torch.manual_seed(seed)
+        o, x_mask, (z, z_p, m_p, logs_p), *_ = net.infer(*args, **kw)
+        m = x_mask.expand_as(z_p)
+        return ((z_p - m_p) / (torch.exp(logs_p) * 0.667))[m].double().cpu()
+
+    a, b, c = eps_of(123), eps_of(123), eps_of(124)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    n = a.numel()
+    assert n > 500000
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1) < 5e-3
+    assert abs(float((a ** 4).mean()) - 3) < 0.05 and abs(float((a ** 3).mean())) < 0.02           # kurtosis 3, no skew
+    assert 4.0 < float(a.abs().max()) < 7.0
+    assert abs(float((a[:-1] * a[1:]).mean())) < 5e-3                                                # neighbours uncorrelated

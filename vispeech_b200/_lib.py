@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.environ.get("VS_LIB_DIR") or os.path.join(HERE, "lib"), "libvispeech_b200.so")
@@ -45,11 +45,11 @@ _SIGNATURES = {
     "vs_length_regulate_count": (c_int32, [POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p]),
     "vs_length_regulate_gather": (c_int32, [POINTER(VsRows), POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p]),
-    "vs_frame_prior": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+    "vs_frame_prior": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_uint64, c_float, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_flow_reverse": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_flow_forward": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
-    "vs_posterior_encode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "vs_posterior_encode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_void_p]),
     "vs_hifigan_decode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64,
                                     c_void_p]),

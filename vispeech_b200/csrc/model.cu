@@ -395,8 +395,8 @@ int vs_length_regulate_gather(const VsRows* rows_p, const VsRows* rows_f, const 
   return lr_gather(*rows_p, *rows_f, x_p, cum, x_f, lr_index, static_cast<cudaStream_t>(stream));
 }
 
-int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const float* noise, float noise_scale,
-                   float* x_frame_out, float* m_p, float* logs_p, float* z_p, void* ws, int64_t ws_bytes,
+int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const float* noise, uint64_t noise_seed,
+                   float noise_scale, float* x_frame_out, float* m_p, float* logs_p, float* z_p, void* ws, int64_t ws_bytes,
                    void* stream) {
   VS_ENTER(m, rows, "vs_frame_prior");
   const int R = rows->n_rows, H = kHidden;
@@ -410,7 +410,7 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
   VS_TRY(conv_rows(c, tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
-  return prior_sample(stats, noise, noise_scale, *rows, m_p, logs_p, z_p, st);
+  return prior_sample(stats, noise, noise_seed, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 
 // WN.forward (modules.py:148-176): h is consumed (updated in place), skip receives the output (already masked).
@@ -506,8 +506,8 @@ int vs_flow_forward(const VsModel* m, const VsRows* rows, float* z, void* ws, in
   return flow_run(m, rows, z, false, W, st);
 }
 
-int vs_posterior_encode(const VsModel* m, const VsRows* rows, const float* spec, const float* noise, float* z, float* m_q,
-                        float* logs_q, void* ws, int64_t ws_bytes, void* stream) {
+int vs_posterior_encode(const VsModel* m, const VsRows* rows, const float* spec, const float* noise, uint64_t noise_seed,
+                        float* z, float* m_q, float* logs_q, void* ws, int64_t ws_bytes, void* stream) {
   VS_ENTER(m, rows, "vs_posterior_encode");
   if (!m->enc_q.present) { set_error("vs_posterior_encode: enc_q.* weights were not registered"); return VS_ERR_MISSING; }
   const PosteriorW& q = m->enc_q;
@@ -528,7 +528,7 @@ int vs_posterior_encode(const VsModel* m, const VsRows* rows, const float* spec,
   c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.in = skip; c.in_ld = H; c.Cin = H; c.w = q.proj_w; c.bias = q.proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
   VS_TRY(conv_rows(c, q.t_proj, q.x_proj, st));                            // stats = proj(x) * x_mask  (models.py:237)
-  return prior_sample(stats, noise, 1.f, *rows, m_q, logs_q, z, st);       // z = (m + eps*exp(logs)) * x_mask  (:239)
+  return prior_sample(stats, noise, noise_seed, 1.f, *rows, m_q, logs_q, z, st);       // z = (m + eps*exp(logs)) * x_mask  (:239)
 }
 
 int vs_hifigan_decode(const VsModel* m, const VsRows* rows, const float* z, int32_t max_len, float* wave_out,

@@ -188,7 +188,30 @@ int lr_gather(const VsRows& rp, const VsRows& rf, const float* xp, const int32_t
 }
 
 // ---- prior sample: z_p = m_p + eps * exp(logs_p) * noise_scale (models.py:718); stats = [m_p | logs_p] ----
-__global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, float ns,
+// eps ~ N(0, 1) is the one RNG draw of the path (`torch.randn_like`, models.py:718).  Injected by the caller for parity
+// runs; otherwise generated here, in the kernel that consumes it: counter-based Philox4x32-10 (Salmon et al., SC'11;
+// key = the call's 64-bit seed, counter = element index) -> two uniforms -> Box-Muller.  No eps tensor ever exists in HBM
+// and the result does not depend on the launch geometry.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t index) {
+  uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.f / 16777216.f);      // (0, 1): log() stays finite
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.f / 16777216.f);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+__global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, uint64_t seed, float ns,
                                     const int32_t* __restrict__ row_utt, float* __restrict__ m_p,
                                     float* __restrict__ logs_p, float* __restrict__ z_p, int R) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,12 +221,13 @@ __global__ void prior_sample_kernel(const float* __restrict__ stats, const float
   const float m = stats[(size_t)r * 2 * kHidden + c], ls = stats[(size_t)r * 2 * kHidden + kHidden + c];
   m_p[i] = m;
   logs_p[i] = ls;
-  z_p[i] = m + noise[i] * expf(ls) * ns;
+  const float eps = noise ? noise[i] : philox_normal(seed, (uint64_t)i);
+  z_p[i] = m + eps * expf(ls) * ns;
 }
-int prior_sample(const float* stats, const float* noise, float ns, const VsRows& rows, float* m_p, float* logs_p,
-                 float* z_p, cudaStream_t st) {
-  prior_sample_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(stats, noise, ns, rows.row_utt, m_p, logs_p,
-                                                                          z_p, rows.n_rows);
+int prior_sample(const float* stats, const float* noise, uint64_t seed, float ns, const VsRows& rows, float* m_p,
+                 float* logs_p, float* z_p, cudaStream_t st) {
+  prior_sample_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(stats, noise, seed, ns, rows.row_utt, m_p,
+                                                                          logs_p, z_p, rows.n_rows);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

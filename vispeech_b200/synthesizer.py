@@ -270,11 +270,13 @@ class SynthesizerTrn:
             check(lib.vs_length_regulate_gather(ctypes.byref(rp.struct), ctypes.byref(rf.struct), ptr(x), ptr(cum),
                                                 ptr(x_f), ptr(lr_index), stream), "vs_length_regulate_gather")
             mark("length_regulator", lat)
-            eps = P.eps if P.eps is not None else torch.randn(Rf, 192, dtype=torch.float32, device=dev)  # models.py:718
+            # eps of models.py:718: injected (parity runs) or drawn inside the sampling kernel (Philox keyed by this seed);
+            # seeds come from torch's default CPU generator, so torch.manual_seed() makes a run reproducible
+            seed = 0 if P.eps is not None else self._next_seed()
             m_p = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             logs_p = torch.empty_like(m_p)
             z = torch.empty_like(m_p)
-            check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(eps), P.noise_scale,
+            check(lib.vs_frame_prior(self._model, ctypes.byref(rf.struct), ptr(x_f), ptr(P.eps), seed, P.noise_scale,
                                      ptr(x_f), ptr(m_p), ptr(logs_p), ptr(z), ptr(ws), ws.numel(), stream),
                   "vs_frame_prior")
             mark("frame_prior", lat)
@@ -344,6 +346,10 @@ class SynthesizerTrn:
             else:
                 duration = phon_out(dur).to(torch.float32)[:, None, :]
             return o, x_mask, lat_out, duration, phon_out(f0), phon_out(energy)
+
+    @staticmethod
+    def _next_seed() -> int:
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
     def _side_stream(self) -> torch.cuda.Stream:
         if self._lat_stream is None:
@@ -450,7 +456,7 @@ class SynthesizerTrn:
             spec = torch.from_numpy(rows_src.scatter([np.pad(yh[b, :, :lens[b]].T, ((0, 0), (0, c_pad - C))) for b in range(B)],
                                                      np.float32, width=c_pad)).to(dev)
             if noise is None:
-                eps = torch.randn(R, 192, dtype=torch.float32, device=dev)
+                eps = None
             else:
                 per = [(noise[b] if not isinstance(noise, torch.Tensor) else noise[b])[:, :lens[b]].t().cpu().numpy()
                        for b in range(B)]
@@ -458,7 +464,8 @@ class SynthesizerTrn:
             ws = self._workspace(16, R)
             z = torch.empty(R, 192, dtype=torch.float32, device=dev)
             m_q, logs_q = torch.empty_like(z), torch.empty_like(z)
-            check(lib.vs_posterior_encode(self._model, ctypes.byref(rows_src.struct), ptr(spec), ptr(eps), ptr(z), ptr(m_q),
+            check(lib.vs_posterior_encode(self._model, ctypes.byref(rows_src.struct), ptr(spec), ptr(eps),
+                                          0 if eps is not None else self._next_seed(), ptr(z), ptr(m_q),
                                           ptr(logs_q), ptr(ws), ws.numel(), stream), "vs_posterior_encode")
             z_p = z.clone()
             check(lib.vs_flow_forward(self._model, ctypes.byref(rows_src.struct), ptr(z_p), ptr(ws), ws.numel(), stream),
