@@ -82,8 +82,9 @@ int64_t vs_launch_count(void);
  * sampling amplifies their error), 1 = plain TF32 above tf32_min_rows like the flow (A/B measurements).
  * "fused_respair": 0 = never, 1 = only the C=32 stage's ResBlock iterations run as one fused conv-pair kernel,
  * 2 (default) = wherever both weight sets fit in shared memory (C=32 and C=64, all k; C=64 k=11 in its TIGHT form).
- * "attention_mma": 1 (default) = sequences of >= 128 rows use the 3xTF32 tensor-core attention kernel, shorter ones the
- * fp32 CUDA-core kernel; 0 = always CUDA cores, 2 = always tensor cores, 3 = tensor cores in plain TF32 (A/B only).
+ * "attention_mma": 1 (default) = sequences of >= 128 rows use the tcgen05 attention kernel (csrc/attention_umma.cu: fp16
+ * hi/lo operands, S and O in TMEM, band terms by a CUDA-core fix-up), shorter ones the fp32 CUDA-core kernel; 0 = always
+ * CUDA cores, 2 = always the 3xTF32 mma.sync kernel, 3 = the same in plain TF32 (A/B only), 4 = always tcgen05.
  * "wn_fused": 1 (default) = on the plain-TF32 route every WN layer is ONE kernel on planar fp32 state (csrc/umma_wn.cu),
  * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
  * "mrf_fused": 1 (default) = the decoder's last MRF stage (C = 32: three ResBlocks, sum, conv_post, tanh) is ONE kernel with the
@@ -145,6 +146,10 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows_f, const float* x_f, con
                    float noise_scale, float* x_frame_out, float* m_p, float* logs_p, float* z_p,
                    void* ws, int64_t ws_bytes, void* stream);
 
+/* N(0,1) samples of the same Philox stream as a tensor: out[i] = what vs_frame_prior(noise = NULL, noise_seed = seed) would use
+ * for element i.  For callers that replay a captured CUDA graph (kernel arguments are frozen: eps is read from memory). */
+int vs_randn(float* out, int64_t n, uint64_t seed, void* stream);
+
 /* ---- a17: ResidualCouplingBlock reverse (models.py:202-209), in place on z ([n_rows][192]) */
 int vs_flow_reverse(const VsModel* m, const VsRows* rows_f, float* z, void* ws, int64_t ws_bytes, void* stream);
 
@@ -187,8 +192,9 @@ int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w /*[k][Cin][C
                      int32_t pad_l, float in_slope, int32_t act, const int32_t* row_utt, int32_t row_div, void* stream);
 int vs_op_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float* out,
                     int32_t n_rows, int32_t C, const int32_t* row_utt, void* stream);
+/* ws: scratch for the tcgen05 kernel (>= n_rows * 3100 bytes + 4 KB), or NULL = the register-accumulator kernels only */
 int vs_op_rel_attention(const VsRows* rows, const float* qkv /*[n_rows][576]*/, const float* emb_rel_k,
-                        const float* emb_rel_v, float* out /*[n_rows][192]*/, void* stream);
+                        const float* emb_rel_v, float* out /*[n_rows][192]*/, void* ws, int64_t ws_bytes, void* stream);
 /* TF32 tcgen05 conv over fp32 row-major rows (csrc/umma_tf32.cu): out = act(conv(in) + bias), zeros on invalid rows.
  * split3 = 1: error-compensated 3xTF32 (weights packed with pack_tf32(split3=True)), fp32-level accuracy. */
 int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,

@@ -258,12 +258,12 @@ def test_layernorm_rows(G):
         assert (out.cpu() - ref).abs().max().item() <= 2e-5
 
 
-@pytest.mark.parametrize("kernel", [0, 2])
-@pytest.mark.parametrize("lengths", [[40], [3, 1, 70, 130], [431, 200]])
+@pytest.mark.parametrize("kernel", [0, 2, 4])
+@pytest.mark.parametrize("lengths", [[40], [3, 1, 70, 130], [431, 200], [129, 128, 127, 640]])
 def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     """Banded relative attention (attentions.py:148-179) vs the oracle's restatement, several ragged lengths
-    including T < window+1 and T > one key tile, for both kernels (0 = CUDA-core fp32, 2 = 3xTF32 tensor-core MMA,
-    which the model uses from 128 rows per utterance up).  fp32 tolerance 2e-5 on O(1) outputs."""
+    including T < window+1 and T > one key tile, for all three kernels (0 = CUDA-core fp32, 2 = 3xTF32 mma.sync, 4 = tcgen05
+    with fp16 hi/lo operands, which the model uses from 128 rows per utterance up).  fp32 tolerance 2e-5 on O(1) outputs."""
     from oracle.vispeech_oracle import DEFAULT_CONFIG, relative_attention
     from vispeech_b200 import _lib
     lib = _lib.load()
@@ -292,8 +292,9 @@ def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     d_ev = sd[p + ".emb_rel_v"][0].contiguous().to(G.DEV)
     _lib.check(lib.vs_set_option(b"attention_mma", kernel))
     try:
+        ws = torch.empty(rows.n_rows * 3100 + 4096, dtype=torch.uint8, device=G.DEV)
         _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
-                                           out.data_ptr(), G.stream()))
+                                           out.data_ptr(), ws.data_ptr(), ws.numel(), G.stream()))
         torch.cuda.synchronize()
     finally:
         _lib.check(lib.vs_set_option(b"attention_mma", 1))

@@ -163,3 +163,44 @@ def test_in_kernel_philox_noise_is_standard_normal_and_seeded(net):
     assert abs(float((a ** 4).mean()) - 3) < 0.05 and abs(float((a ** 3).mean())) < 0.02           # kurtosis 3, no skew
     assert 4.0 < float(a.abs().max()) < 7.0
     assert abs(float((a[:-1] * a[1:]).mean())) < 5e-3                                                # neighbours uncorrelated
+
+
+def test_cuda_graph_latency_path_matches_infer(net, state_dict):
+    """infer_graphed (one CUDA-graph launch per row bucket) against `infer` and the oracle: utterances of different lengths
+    replay the SAME captured graph (bucket = frame rows rounded up to 64) - the second and third calls below never capture."""
+    from oracle import inputs as oin
+    from oracle.vispeech_oracle import infer_one
+    g = torch.Generator().manual_seed(21)
+    base = oin.c1()[0]
+    tp = base["ids"].numel()
+    cases = []
+    for k in range(4):
+        dur = base["duration"].clone()
+        dur[k] += 3 * k                                    # 0 .. 9 more frames: same 64-row bucket for the first three
+        if k == 3:
+            dur[5] += 70                                   # another bucket
+        cases.append(dict(ids=torch.randint(1, 400, (tp,), generator=g), sid=7 * k, duration=dur))
+    n_graphs = []
+    for u in cases:
+        tf = int(u["duration"].sum())
+        eps = oin.draw_noise([tf], 400 + tf)[0]
+        args = (u["ids"][None], torch.LongTensor([tp]))
+        kw = dict(sid=torch.LongTensor([u["sid"]]), noise_scale=0.667, duration_control=u["duration"][None], noise=[eps])
+        o_g, mask_g = net.infer_graphed(*args, **kw)
+        o_g = o_g.clone()
+        n_graphs.append(len(net._graphs))
+        o_e, mask_e, *_ = net.infer(*args, outputs="audio", **kw)
+        torch.cuda.synchronize()
+        assert o_g.shape == o_e.shape == (1, 1, tf * 512) and torch.equal(mask_g, mask_e)
+        assert snr_db(o_e, o_g) >= 60.0
+        ref = infer_one(state_dict, u["ids"], u["sid"], 0.667, eps, duration_control=u["duration"])
+        assert snr_db(ref["o"], o_g[0, 0].cpu()) >= 30.0
+    assert n_graphs == [1, 1, 1, 2], n_graphs
+    # without injected noise: eps is drawn by the library (vs_randn) into the graph's static buffer, fresh for every call
+    u = cases[0]
+    a = net.infer_graphed(u["ids"][None], torch.LongTensor([tp]), sid=torch.LongTensor([0]), noise_scale=0.667,
+                          duration_control=u["duration"][None])[0].clone()
+    b = net.infer_graphed(u["ids"][None], torch.LongTensor([tp]), sid=torch.LongTensor([0]), noise_scale=0.667,
+                          duration_control=u["duration"][None])[0].clone()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(a).all()) and not torch.equal(a, b)

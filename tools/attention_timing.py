@@ -1,4 +1,4 @@
-"""A/B of the two relative-attention kernels (CUDA-core fp32 vs 3xTF32 mma.sync) at a given shape:
+"""A/B of the relative-attention kernels (0 CUDA-core fp32, 2 3xTF32 mma.sync, 3 plain-TF32 mma.sync, 4 tcgen05 fp16 hi/lo) at a given shape:
    python tools/attention_timing.py [n_utt=64] [T=431]
 Prints ms per launch (CUDA events, 20 launches) for both and the max abs difference between their outputs."""
 import ctypes, os, sys, torch
@@ -17,19 +17,20 @@ qkv *= (rows.row_utt >= 0).float()[:, None]
 ek = torch.randn(9, 96, device=dev, generator=g) * 0.1
 ev = torch.randn(9, 96, device=dev, generator=g) * 0.1
 outs = {}
-for mode in (0, 2, 3):
+ws = torch.empty(rows.n_rows * 3100 + 4096, dtype=torch.uint8, device=dev)
+for mode in (0, 2, 3, 4):
     check(lib.vs_set_option(b"attention_mma", mode))
     out = torch.empty(rows.n_rows, 192, device=dev)
     for _ in range(3):
-        check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), out.data_ptr(), st))
+        check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), out.data_ptr(), st))
+        check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st))
     e1.record(); torch.cuda.synchronize()
     flop = 2 * B * T * T * 96 * 4
     ms = e0.elapsed_time(e1) / 20
     print("attention_mma=%d  B=%d T=%d  %.3f ms  %.1f TFLOP/s (algorithmic)" % (mode, B, T, ms, flop / ms / 1e9))
     outs[mode] = out
-for m in (2, 3):
+for m in (2, 3, 4):
     print("mode %d: max |mma - fp32| = %.3e   (max |out| = %.3f)" % (m, float((outs[0] - outs[m]).abs().max()), float(outs[0].abs().max())))

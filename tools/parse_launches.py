@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
 `bench.py --steps 1 --warmup 1`: per-launch time and DRAM bytes of the LAST step (one step = one embed_rows launch), and
-the decoder's totals (to_planar_bf16 .. conv_post).   python tools/parse_launches.py gpurun_out/launches_traffic.csv"""
+the decoder's totals (to_planar_f16 .. umma_mrf / conv_post).   python tools/parse_launches.py gpurun_out/launches_traffic.csv"""
 import collections
 import csv
 import re
@@ -40,7 +40,7 @@ def main():
             dec_b += b; dec_t += t; dec_n += 1
         tot_t += t; tot_b += b
         print("%d,%s,%.1f,%.1f,%.0f" % (i, nm, t, b / 1e6, b / t / 1e3 if t else 0))
-        if "conv_post" in nm:
+        if "conv_post" in nm or "umma_mrf" in nm:       # the decoder's last launch (one-kernel last MRF stage, or conv_post)
             in_dec = False
     print("# step: %d launches, %.1f us serialised, %.2f GB DRAM" % (len(step), tot_t, tot_b / 1e9))
     print("# decoder: %d launches, %.1f us, %.3f GB DRAM (read+write)" % (dec_n, dec_t, dec_b / 1e9))

@@ -47,6 +47,7 @@ _SIGNATURES = {
                                             c_void_p]),
     "vs_frame_prior": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_uint64, c_float, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_void_p]),
+    "vs_randn": (c_int32, [c_void_p, c_int64, c_uint64, c_void_p]),
     "vs_flow_reverse": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_flow_forward": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_posterior_encode": (c_int32, [c_void_p, POINTER(VsRows), c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -60,7 +61,7 @@ _SIGNATURES = {
     "vs_op_conv1d_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                    c_int32, c_int32, c_int32, c_float, c_int32, c_void_p, c_int32, c_void_p]),
     "vs_op_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "vs_op_rel_attention": (c_int32, [POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vs_op_rel_attention": (c_int32, [POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_op_conv1d_tf32": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "vs_op_wn_layer": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

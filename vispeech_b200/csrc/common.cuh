@@ -73,7 +73,14 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st);
 
 int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
                    const int32_t* row_utt, cudaStream_t st);
-int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
+struct Workspace;
+// `ws`: scratch for the tcgen05 kernel (attention_umma.cu, attention_umma_ws_floats(n_rows) floats); without it the
+// frame-level path falls back to the mma.sync kernel
+int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
+                  Workspace* ws = nullptr);
+int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
+                       cudaStream_t st);
+int64_t attention_umma_ws_floats(int n_rows);
 // tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on opts() "attention_mma"
 int rel_attention_mma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
 int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,

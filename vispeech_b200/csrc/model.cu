@@ -194,7 +194,9 @@ static int finalize(VsModel* m) {
 }
 
 // ---- attentions.Encoder.forward (attentions.py:35-47), in place on x -------------------------------
-static int64_t encoder_ws_floats(int R) { return (int64_t)R * (3 * kHidden + kHidden + kHidden + kFilter); }
+static int64_t encoder_ws_floats(int R) {
+  return (int64_t)R * (3 * kHidden + kHidden + kHidden + kFilter) + attention_umma_ws_floats(R) + 4 * 64;
+}
 
 static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& rows, float* x, Workspace& ws,
                            cudaStream_t st, bool frame_level) {
@@ -209,7 +211,7 @@ static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& ro
     c.R = R; c.row_utt = rows.row_utt;
     c.in = x; c.in_ld = H; c.Cin = H; c.w = L.wqkv; c.bias = L.bqkv; c.out = qkv; c.out_ld = 3 * H; c.Cout = 3 * H;
     VS_TRY(conv_rows(c, frame_level ? L.t_wqkv : nullptr, L.x_wqkv, st));                                    // conv_q|k|v (attentions.py:139-141)
-    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st));                 // attentions.py:148-179
+    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st, &ws));            // attentions.py:148-179 (scratch: what is left of ws)
     c.in = att; c.w = L.wo; c.bias = L.bo; c.out = y; c.out_ld = H; c.Cout = H;
     VS_TRY(conv_rows(c, frame_level ? L.t_wo : nullptr, L.x_wo, st));                                      // conv_o
     VS_TRY(layernorm_rows(x, y, L.g1, L.b1, x, R, H, rows.row_utt, st));   // x = LN(x + y)
@@ -539,6 +541,10 @@ int vs_hifigan_decode(const VsModel* m, const VsRows* rows, const float* z, int3
   return decode_f16(m->dec, *rows, z, max_len, wave_out, W, st);
 }
 
+int vs_randn(float* out, int64_t n, uint64_t seed, void* stream) {
+  return randn_fill(out, n, seed, static_cast<cudaStream_t>(stream));
+}
+
 int vs_unpack_rows(const VsRows* rows, const float* x, int32_t C, int32_t rows_mul, int32_t t_max, float* out,
                    void* stream) {
   VS_TRY(check_rows(rows, "vs_unpack_rows"));
@@ -566,9 +572,10 @@ int vs_op_layernorm(const float* a, const float* b, const float* gamma, const fl
 }
 
 int vs_op_rel_attention(const VsRows* rows, const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
-                        float* out, void* stream) {
+                        float* out, void* ws, int64_t ws_bytes, void* stream) {
   VS_TRY(check_rows(rows, "vs_op_rel_attention"));
-  return rel_attention(*rows, qkv, emb_rel_k, emb_rel_v, out, static_cast<cudaStream_t>(stream));
+  vs::Workspace w(ws, ws_bytes);
+  return rel_attention(*rows, qkv, emb_rel_k, emb_rel_v, out, static_cast<cudaStream_t>(stream), ws ? &w : nullptr);
 }
 
 int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, const float* bias, float* out, int32_t out_ld,

@@ -211,6 +211,18 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t index) {
   const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.f / 16777216.f);
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
+// eps as a tensor: the same stream as the in-kernel draw (element i of a call with this seed), for callers that must keep the
+// seed out of the kernel arguments (CUDA-graph replays: the graph reads eps from a static buffer refilled before each replay)
+__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_normal(seed, (uint64_t)i);
+}
+int randn_fill(float* out, int64_t n, uint64_t seed, cudaStream_t st) {
+  VS_REQUIRE(out && n > 0, "randn_fill: bad arguments");
+  randn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, seed);
+  VS_LAUNCH_CHECK();
+  return VS_OK;
+}
 __global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, uint64_t seed, float ns,
                                     const int32_t* __restrict__ row_utt, float* __restrict__ m_p,
                                     float* __restrict__ logs_p, float* __restrict__ z_p, int R) {

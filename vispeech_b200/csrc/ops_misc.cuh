@@ -17,6 +17,7 @@ int lr_gather(const VsRows& rp, const VsRows& rf, const float* xp, const int32_t
               cudaStream_t st);
 int prior_sample(const float* stats, const float* noise /*null: Philox(seed)*/, uint64_t seed, float ns, const VsRows& rows,
                  float* m_p, float* logs_p, float* z_p, cudaStream_t st);
+int randn_fill(float* out, int64_t n, uint64_t seed, cudaStream_t st);
 int wn_gate(const float* a, const float* cond, int cond_ld, int cond_off, const VsRows& rows, float* acts,
             cudaStream_t st);
 int wn_update(const float* rs, int rs_ld, int last, int first, const VsRows& rows, float* h, float* skip,

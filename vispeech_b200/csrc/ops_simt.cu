@@ -64,7 +64,7 @@ int option_set(Options* o, const char* name, int64_t value) {
   switch (idx) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
     case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: value = value != 0; break;
-    case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 3, "option attention_mma must be 0..3"); break;
+    case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 4, "option attention_mma must be 0..4"); break;
     case OPT_TF32_CLUSTER: case OPT_DECODER_STREAMS: value = value == 2 ? 2 : 1; break;
     case OPT_RESPAIR_GRID_DIV: value = value < 1 ? 1 : value; break;
     case OPT_FUSED_RESPAIR: VS_REQUIRE(value >= 0 && value <= 2, "option fused_respair must be 0..2"); break;
@@ -540,9 +540,15 @@ static size_t attention_smem_bytes() {
   return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * AT_SLD + kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
 }
 
-int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st) {
-  // 1 = auto (tensor cores from 128 rows per utterance up), 2/3 = always MMA (3xTF32 / plain TF32), 0 = never
+int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
+                  Workspace* ws) {
+  // option "attention_mma": 1 = auto (from 128 rows per utterance up: tcgen05 when the caller gave a workspace, else mma.sync),
+  // 0 = CUDA cores, 2 / 3 = always mma.sync (3xTF32 / plain TF32), 4 = always tcgen05
   const int mode = (int)opts().v[OPT_ATTENTION_MMA];
+  if (ws && (mode == 4 || (mode == 1 && rows.max_len >= 128))) {
+    Workspace scratch = *ws;                       // a copy: the caller's allocations stay where they are
+    return rel_attention_umma(rows, qkv, ek, ev, out, scratch, st);
+  }
   if (mode >= 2 || (mode == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
   const size_t smem = attention_smem_bytes();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_kernel), (int)smem));

@@ -60,13 +60,22 @@ def plan_starts(lengths: Sequence[int], gap: int, align: int = ROW_ALIGN):
     return starts.astype(np.int32), n_rows
 
 
-def make_rows(lengths: Sequence[int], sids: Sequence[int], gap: int, device) -> RaggedRows:
+def make_rows(lengths: Sequence[int], sids: Sequence[int], gap: int, device, n_rows: int = 0,
+              out: "RaggedRows" = None) -> RaggedRows:
+    """`n_rows` > 0: lay the batch out in a BUCKET of that many rows (>= what the batch needs): the tail is gap rows and
+    `max_len` (a launch-geometry bound only; kernels read the true lengths from device memory) becomes the bucket size, so
+    the layout's shape no longer depends on the utterance - what a captured CUDA graph needs.  `out`: reuse that layout's
+    device arrays (same bucket, same utterance count) instead of allocating new ones."""
     lengths = np.asarray(lengths, dtype=np.int32)
     if lengths.ndim != 1 or lengths.size == 0:
         raise ValueError("need at least one utterance")
     if (lengths < 0).any():
         raise ValueError("negative length")
-    starts, n_rows = plan_starts(lengths, gap)
+    starts, need = plan_starts(lengths, gap)
+    bucket = n_rows > 0
+    if bucket and n_rows < need:
+        raise ValueError("bucket of %d rows is too small for %d" % (n_rows, need))
+    n_rows = n_rows if bucket else need
     if n_rows >= 2 ** 31 // 512:
         raise ValueError("batch too long for 32-bit row indices at sample rate")
     row_utt = np.full(n_rows, -1, dtype=np.int32)
@@ -77,15 +86,22 @@ def make_rows(lengths: Sequence[int], sids: Sequence[int], gap: int, device) -> 
     # engine's throughput mode that is the previous call's latent stage, which shares the SMs with a decoder - the host then
     # falls behind and the GPU idles; seen as sporadic 20-40 % slower end-to-end runs)
     meta_host = torch.from_numpy(meta).pin_memory() if torch.cuda.is_available() else torch.from_numpy(meta)
-    meta_dev = meta_host.to(device, non_blocking=True)
+    if out is not None:
+        if out.meta_dev.numel() != meta_host.numel() or out.n_rows != n_rows:
+            raise ValueError("layout does not match the bucket it is written into")
+        meta_dev = out.meta_dev
+        meta_dev.copy_(meta_host, non_blocking=True)
+    else:
+        meta_dev = meta_host.to(device, non_blocking=True)
     B = lengths.size
     d_row_utt = meta_dev[:n_rows]
     d_start = meta_dev[n_rows:n_rows + B]
     d_len = meta_dev[n_rows + B:n_rows + 2 * B]
     d_sid = meta_dev[n_rows + 2 * B:]
-    st = VsRows(n_utt=B, n_rows=n_rows, max_len=max(1, int(lengths.max())), reserved=0,
+    st = VsRows(n_utt=B, n_rows=n_rows, max_len=n_rows if bucket else max(1, int(lengths.max())), reserved=0,
                 row_utt=d_row_utt.data_ptr(), utt_start=d_start.data_ptr(), utt_len=d_len.data_ptr(),
                 sid=d_sid.data_ptr())
     rows = RaggedRows(lengths, starts, n_rows, row_utt, d_row_utt, d_start, d_len, d_sid, st)
     rows.meta_host = meta_host          # keeps the staging buffer referenced with the layout
+    rows.meta_dev = meta_dev
     return rows

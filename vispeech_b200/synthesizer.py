@@ -145,8 +145,11 @@ class SynthesizerTrn:
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def prepare(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, max_len=None, energy_control: Control = None,
-                pitch_control: Control = None, duration_control: Control = None, noise=None) -> "Prepared":
-        """Host side of `infer`: everything up to (and including) the host->device copies of the inputs."""
+                pitch_control: Control = None, duration_control: Control = None, noise=None,
+                bucket: Optional[tuple] = None, static: Optional["Prepared"] = None) -> "Prepared":
+        """Host side of `infer`: everything up to (and including) the host->device copies of the inputs.
+        `bucket` = (phoneme rows, frame rows): lay the batch out in row buckets of these sizes (layout.make_rows);
+        `static`: a Prepared of the same bucket whose device buffers receive the uploads (CUDA-graph replays read them)."""
         if not self._loaded:
             raise _lib.VsError("load_state_dict()/load_checkpoint() first")
         if sid is None:
@@ -176,18 +179,22 @@ class SynthesizerTrn:
         # behind the previous call's decoder)
         up = self._side_stream() if self.overlap_calls else torch.cuda.current_stream(dev)
         with torch.cuda.device(dev), torch.cuda.stream(up):
-            P.rp = make_rows(lens, sids, PHONEME_GAP, dev)
-            P.ids_rows = _upload(P.rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1), dev)
+            P.bucket, P.static = bucket, static
+            P.rp = make_rows(lens, sids, PHONEME_GAP, dev, n_rows=bucket[0] if bucket else 0,
+                             out=static.rp if static is not None else None)
+            P.ids_rows = _upload(P.rp.scatter([phon[b] for b in range(B)], np.int32, fill=-1), dev,
+                                 static.ids_rows if static is not None else None)
 
-            def control(c, name, dtype):
+            def control(c, name, dtype, prev):
                 if isinstance(c, torch.Tensor):
                     per = self._per_utt(c, B, lens, name)
-                    return 2, 1.0, _upload(P.rp.scatter(per, dtype), dev), per
+                    return 2, 1.0, _upload(P.rp.scatter(per, dtype), dev, prev), per
                 return 0, 1.0 if c is None else float(c), None, None
 
-            P.d_mode, P.d_scale, P.d_ctrl, d_per = control(duration_control, "duration_control", np.float64)
-            P.p_mode, P.p_scale, P.p_ctrl, _ = control(pitch_control, "pitch_control", np.float32)
-            P.e_mode, P.e_scale, P.e_ctrl, _ = control(energy_control, "energy_control", np.float32)
+            st = static
+            P.d_mode, P.d_scale, P.d_ctrl, d_per = control(duration_control, "duration_control", np.float64, st.d_ctrl if st else None)
+            P.p_mode, P.p_scale, P.p_ctrl, _ = control(pitch_control, "pitch_control", np.float32, st.p_ctrl if st else None)
+            P.e_mode, P.e_scale, P.e_ctrl, _ = control(energy_control, "energy_control", np.float32, st.e_ctrl if st else None)
             P.noise = noise
             P.frames = None
             P.rf = None
@@ -204,14 +211,16 @@ class SynthesizerTrn:
         if int(P.frames.max()) < 1:
             raise ValueError("all durations are <= 0: nothing to synthesise")
         dev = self.device
-        P.rf = make_rows(P.frames, P.sids, FRAME_GAP, dev)
+        bucket, static = getattr(P, "bucket", None), getattr(P, "static", None)
+        P.rf = make_rows(P.frames, P.sids, FRAME_GAP, dev, n_rows=bucket[1] if bucket else 0,
+                         out=static.rf if static is not None else None)
         if P.noise is not None:
             fr = P.frames
             if isinstance(P.noise, torch.Tensor):
                 per = [P.noise[b, :, :fr[b]].t().cpu().numpy() for b in range(P.B)]
             else:
                 per = [P.noise[b][:, :fr[b]].t().cpu().numpy() for b in range(P.B)]
-            P.eps = _upload(P.rf.scatter(per, np.float32, width=192), dev)
+            P.eps = _upload(P.rf.scatter(per, np.float32, width=192), dev, static.eps if static is not None else None)
 
     @torch.no_grad()
     def run(self, P: "Prepared", outputs: str = "all", timings: Optional[dict] = None):
@@ -264,7 +273,9 @@ class SynthesizerTrn:
                 self._layout_frames(P)
                 ws = self._workspace_lat(Rp, P.rf.n_rows) if overlap else self._workspace(Rp, P.rf.n_rows)
             rf, frames = P.rf, P.frames
-            Rf, Tf = rf.n_rows, int(frames.max())
+            # bucketed layouts (infer_graphed): output shapes follow the bucket, not the utterance, so a captured graph fits
+            # every utterance of the bucket; the caller slices
+            Rf, Tf = rf.n_rows, (rf.n_rows if P.bucket else int(frames.max()))
             x_f = torch.empty(Rf, 192, dtype=torch.float32, device=dev)
             lr_index = torch.empty(Rf, dtype=torch.int32, device=dev)
             check(lib.vs_length_regulate_gather(ctypes.byref(rp.struct), ctypes.byref(rf.struct), ptr(x), ptr(cum),
@@ -378,6 +389,76 @@ class SynthesizerTrn:
         P = self.prepare(phonemes, phonemes_lengths, sid, noise_scale, max_len, energy_control, pitch_control,
                          duration_control, noise)
         return self.run(P, outputs)
+
+    # ------------------------------------------------------------------------------------------------
+    # Latency path: the whole device side of one call as ONE CUDA-graph launch per row bucket
+    # ------------------------------------------------------------------------------------------------
+    GRAPH_BUCKET_PHONEME_ROWS = 16
+    GRAPH_BUCKET_FRAME_ROWS = 64
+
+    @torch.no_grad()
+    def infer_graphed(self, phonemes, phonemes_lengths, sid=None, noise_scale=1, energy_control: Control = None,
+                      pitch_control: Control = None, duration_control: Control = None, noise=None):
+        """`infer(..., outputs="audio")` for the latency path (every reference call site is one utterance per call,
+        inference.py:40-44): the ~250 kernel launches of a call are captured once per ROW BUCKET (phoneme rows rounded up
+        to 16, frame rows to 64; the tail of a bucket is gap rows, which every kernel already treats as padding) and
+        replayed as a single graph launch - same kernels, same arithmetic as `infer` on the same layout.  Needs durations
+        as a tensor (the frame layout must be known on the host before the launch).  Returns (o [B,1,hop*Tf], x_mask)."""
+        if not isinstance(duration_control, torch.Tensor):
+            raise ValueError("infer_graphed needs duration_control as a tensor (frame counts fix the graph's bucket)")
+        from .layout import plan_starts
+        from .sharding import frames_from_durations
+        lens = phonemes_lengths.detach().cpu().numpy().astype(np.int32).reshape(-1)
+        B = int(lens.shape[0])
+        dc = duration_control.detach()
+        dc = dc.reshape(dc.shape[0], -1) if dc.dim() == 3 else (dc[None] if dc.dim() == 1 else dc)
+        frames = frames_from_durations([dc[b, :lens[b]].cpu().numpy() for b in range(B)])
+        up = lambda n, m: -(-int(n) // m) * m
+        bucket = (up(plan_starts(lens, PHONEME_GAP)[1], self.GRAPH_BUCKET_PHONEME_ROWS),
+                  up(plan_starts(frames, FRAME_GAP)[1], self.GRAPH_BUCKET_FRAME_ROWS))
+        sig = tuple(isinstance(c, torch.Tensor) or (1.0 if c is None else float(c)) for c in (pitch_control, energy_control))
+        key = (B, int(phonemes.shape[-1]), bucket, sig, float(noise_scale), int(self.decoder_precision))
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        dev = self.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if ent is None:
+                # eps always comes from a static buffer here (a kernel argument such as the Philox seed would be frozen)
+                eps0 = torch.zeros(B, 192, int(frames.max()))
+                P = self.prepare(phonemes, phonemes_lengths, sid, noise_scale, None, energy_control, pitch_control,
+                                 duration_control, eps0, bucket=bucket)
+                self.run(P, outputs="audio")                     # eager once: kernel attributes, allocator warm-up
+                torch.cuda.synchronize(dev)
+                saved = (self._ws, self.overlap_calls)
+                self._ws, self.overlap_calls = None, False       # the graph owns its workspace (allocated from its private pool)
+                g = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(g, stream=self._graph_stream()):
+                        o, _, _, _, _, _ = self.run(P, outputs="audio")
+                    ws = self._ws
+                finally:
+                    self._ws, self.overlap_calls = saved
+                ent = self._graphs[key] = dict(graph=g, P=P, o=o, ws=ws)
+            P = self.prepare(phonemes, phonemes_lengths, sid, noise_scale, None, energy_control, pitch_control,
+                             duration_control, None, bucket=bucket, static=ent["P"])
+            sP = ent["P"]
+            if noise is not None:
+                per = [(noise[b] if not isinstance(noise, torch.Tensor) else noise[b])[:, :frames[b]].t().cpu().numpy() for b in range(B)]
+                _upload(P.rf.scatter(per, np.float32, width=192), dev, sP.eps)
+            else:
+                check(self._lib.vs_randn(sP.eps.data_ptr(), sP.eps.numel(), self._next_seed(), stream.cuda_stream), "vs_randn")
+            ent["graph"].replay()
+            tf = int(frames.max())
+            o = ent["o"][:, :, : tf * self.hop_length]
+            x_mask = (torch.arange(tf, device=dev)[None, :] < P.frames_dev()[:, None])[:, None, :]
+            return o, x_mask
+
+    def _graph_stream(self) -> torch.cuda.Stream:
+        if getattr(self, "_gstream", None) is None:
+            self._gstream = torch.cuda.Stream(device=self.device)
+        return self._gstream
 
     # ------------------------------------------------------------------------------------------------
     # Long-form path (BASELINE.json configs[3]): chunked decoder with receptive-field overlap
@@ -496,10 +577,14 @@ class Prepared:
         return self.rf.utt_len                      # int32 [B] on the device: the frame counts of the row layout
 
 
-def _upload(a: np.ndarray, dev) -> torch.Tensor:
+def _upload(a: np.ndarray, dev, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     # always through pinned memory: a copy from pageable memory first synchronises the stream it is queued on, i.e. the
     # host would wait for whatever the previous call left there (see layout.make_rows)
-    return torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)
+    src = torch.from_numpy(a).pin_memory()
+    if out is not None:                        # refill a static buffer (CUDA-graph replays read it)
+        out.copy_(src, non_blocking=True)
+        return out
+    return src.to(dev, non_blocking=True)
 
 
 def load_checkpoint(checkpoint_path: str, model: SynthesizerTrn, optimizer=None, skip_optimizer: bool = False):
