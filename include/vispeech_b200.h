@@ -192,7 +192,7 @@ int vs_op_conv1d_f32(const float* in, int32_t in_ld, const float* w /*[k][Cin][C
                      int32_t pad_l, float in_slope, int32_t act, const int32_t* row_utt, int32_t row_div, void* stream);
 int vs_op_layernorm(const float* a, const float* b, const float* gamma, const float* beta, float* out,
                     int32_t n_rows, int32_t C, const int32_t* row_utt, void* stream);
-/* ws: scratch for the tcgen05 kernel (>= n_rows * 3100 bytes + 4 KB), or NULL = the register-accumulator kernels only */
+/* ws: scratch for the tcgen05 kernel (>= n_rows * 8 KB + n_utt * 200 KB), or NULL = the register-accumulator kernels only */
 int vs_op_rel_attention(const VsRows* rows, const float* qkv /*[n_rows][576]*/, const float* emb_rel_k,
                         const float* emb_rel_v, float* out /*[n_rows][192]*/, void* ws, int64_t ws_bytes, void* stream);
 /* TF32 tcgen05 conv over fp32 row-major rows (csrc/umma_tf32.cu): out = act(conv(in) + bias), zeros on invalid rows.

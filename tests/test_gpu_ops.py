@@ -292,7 +292,7 @@ def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     d_ev = sd[p + ".emb_rel_v"][0].contiguous().to(G.DEV)
     _lib.check(lib.vs_set_option(b"attention_mma", kernel))
     try:
-        ws = torch.empty(rows.n_rows * 3100 + 4096, dtype=torch.uint8, device=G.DEV)
+        ws = torch.empty(rows.n_rows * 8192 + len(lengths) * 200000 + 65536, dtype=torch.uint8, device=G.DEV)
         _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
                                            out.data_ptr(), ws.data_ptr(), ws.numel(), G.stream()))
         torch.cuda.synchronize()

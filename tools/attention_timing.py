@@ -17,7 +17,7 @@ qkv *= (rows.row_utt >= 0).float()[:, None]
 ek = torch.randn(9, 96, device=dev, generator=g) * 0.1
 ev = torch.randn(9, 96, device=dev, generator=g) * 0.1
 outs = {}
-ws = torch.empty(rows.n_rows * 3100 + 4096, dtype=torch.uint8, device=dev)
+ws = torch.empty(rows.n_rows * 8192 + B * 200000 + 65536, dtype=torch.uint8, device=dev)
 for mode in (0, 2, 3, 4):
     check(lib.vs_set_option(b"attention_mma", mode))
     out = torch.empty(rows.n_rows, 192, device=dev)
@@ -34,3 +34,16 @@ for mode in (0, 2, 3, 4):
     outs[mode] = out
 for m in (2, 3, 4):
     print("mode %d: max |mma - fp32| = %.3e   (max |out| = %.3f)" % (m, float((outs[0] - outs[m]).abs().max()), float(outs[0].abs().max())))
+
+if os.environ.get("VS_LIB_DIR"):      # diagnostics build (VS_UMMA_TIMING=1 VS_LIB_DIR=... python vispeech_b200/build.py): clock stamps of the tcgen05 kernel
+    n_cta = ((T + 127) // 128) * 2 * B
+    buf = torch.zeros(n_cta * 16, dtype=torch.int64, device=dev)
+    check(lib.vs_set_option(b"attention_mma", 4))
+    check(lib.vs_set_option(b"umma_timing_buffer", buf.data_ptr()))
+    check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    torch.cuda.synchronize()
+    check(lib.vs_set_option(b"umma_timing_buffer", 0))
+    t = buf.view(n_cta, 16).double()
+    t = t[t[:, 12] > 0].mean(0)
+    names = ["setup done", "Q+K0 landed", "PV0 issued", "PV1", "PV2", "PV3", "PV4", "PV5", "P(g0,t0) stored", "P(g0,t1)", "P(g0,t2)", "last O_DONE", "output stored"]
+    print("attention_umma_kernel, mean clocks since CTA start: " + "  ".join("%s %.0f" % (n, v) for n, v in zip(names, t.tolist())))

@@ -81,6 +81,7 @@ int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const f
 int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
                        cudaStream_t st);
 int64_t attention_umma_ws_floats(int n_rows);
+bool rel_attention_umma_fits(const VsRows& rows, const Workspace& ws);   // enough scratch left for this batch's tiles?
 // tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on opts() "attention_mma"
 int rel_attention_mma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st);
 int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,

@@ -545,7 +545,7 @@ int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const f
   // option "attention_mma": 1 = auto (from 128 rows per utterance up: tcgen05 when the caller gave a workspace, else mma.sync),
   // 0 = CUDA cores, 2 / 3 = always mma.sync (3xTF32 / plain TF32), 4 = always tcgen05
   const int mode = (int)opts().v[OPT_ATTENTION_MMA];
-  if (ws && (mode == 4 || (mode == 1 && rows.max_len >= 128))) {
+  if (ws && (mode == 4 || (mode == 1 && rows.max_len >= 128 && rel_attention_umma_fits(rows, *ws)))) {
     Workspace scratch = *ws;                       // a copy: the caller's allocations stay where they are
     return rel_attention_umma(rows, qkv, ek, ev, out, scratch, st);
   }
