@@ -205,6 +205,12 @@ int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, con
  * last layer's res_skip has 192 outputs, all skip; h_out may be NULL).  h_in / h_out / skip are row-major [n_rows][192] here
  * (the model keeps them planar across the stack); w_in_packed: gate-interleaved columns (packing.gate_columns), pack_tf32
  * slabs; cond: [n_spk][cond_ld] rows of this layer's 384 gate-interleaved columns; ws >= 3 * n_rows * 192 floats. */
+/* fp32-accurate conv on tcgen05 kind::f16 with fp16 hi/lo operands (csrc/umma_split.cu; weights packed with pack_split16):
+ * out = act(conv(in) + bias) over fp32 row-major rows, zeros on invalid rows; act: 0 none, 1 ReLU; c_in <= 192 or a multiple of
+ * 192 (K-slices).  ws >= n_rows * (4 c_in + 4 c_out c_in/192) bytes. */
+int vs_op_conv1d_split(const float* in, int32_t in_ld, const void* w_packed, const float* bias, float* out, int32_t out_ld,
+                       int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
+                       const int32_t* row_utt, void* ws, int64_t ws_bytes, void* stream);
 int vs_op_wn_layer(const float* h_in, const float* w_in_packed, const float* b_in, const float* cond, int32_t cond_ld,
                    const int32_t* cond_idx, const float* w_rs_packed, const float* b_rs, const int32_t* row_utt,
                    int32_t n_rows, int32_t first, int32_t last, float* h_out, float* skip, void* ws, int64_t ws_bytes,

@@ -112,6 +112,21 @@ def conv_tf32(x, w_tcn, bias=None, dil=1, pad_l=0, act=0, row_utt=None, split3=F
     return out
 
 
+def conv_split16(x, w_tcn, bias=None, dil=1, pad_l=0, act=0, row_utt=None):
+    """fp16 hi/lo three-term conv on tcgen05 kind::f16 (csrc/umma_split.cu) through its op-level hook."""
+    from vispeech_b200.packing import pack_split16
+    lib = _lib.load()
+    R, cin = x.shape
+    k, _, cout = w_tcn.shape
+    wp = pack_split16(w_tcn.cpu()).to(x.device)
+    out = torch.full((R, cout), float("nan"), dtype=torch.float32, device=x.device)
+    ws = torch.empty(R * (4 * cin + 4 * cout * max(1, cin // 192)) + (1 << 16), dtype=torch.uint8, device=x.device)
+    check(lib.vs_op_conv1d_split(ptr(x), cin, ptr(wp), ptr(bias), ptr(out), cout, R, cin, cout, k, dil, pad_l, act,
+                                 ptr(row_utt), ptr(ws), ws.numel(), stream()), "vs_op_conv1d_split")
+    torch.cuda.synchronize()
+    return out
+
+
 def ref_conv_rows(x, w_tcn, bias=None, dil=1, pad_l=0):
     """CPU reference of the row conv: out[r] = sum_t in[r + (t-pad_l)*dil] @ W[t] (+bias); zero outside [0,R)."""
     x = x.double().cpu()

@@ -240,6 +240,30 @@ def test_conv_3xtf32_is_fp32_accurate(G, R, cin, cout, k, act):
     assert (out - ref).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("R,cin,cout,k,act", [(300, 192, 576, 1, 0), (1000, 192, 768, 3, 1), (260, 768, 192, 3, 0), (2560, 768, 192, 3, 0),
+                                             (500, 96, 192, 1, 0), (700, 192, 384, 5, 0), (2816, 192, 256, 3, 1), (27840, 192, 192, 1, 0),
+                                             (129, 192, 96, 1, 0)])
+def test_conv_split16_is_fp32_accurate(G, R, cin, cout, k, act):
+    """fp16 hi/lo three-term conv (a_hi w_hi + a_lo w_hi + a_hi w_lo on tcgen05 kind::f16, csrc/umma_split.cu) vs fp64: the same
+    fp32-level bar as 3xTF32 (1e-4 absolute on O(1) outputs), including K-slices (Cin = 768), n-blocks spread over CTAs (few
+    row tiles), ragged row counts and gap rows."""
+    g = torch.Generator().manual_seed(k * 13 + cout + R)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(k, cin, cout, generator=g) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    row_utt[R // 3: R // 3 + 4] = -1                      # a gap: the conv must write exact zeros there
+    x[R // 3: R // 3 + 4] = 0
+    out = G.conv_split16(x.to(G.DEV), w, b.to(G.DEV), pad_l=(k - 1) // 2, act=act, row_utt=row_utt.to(G.DEV)).cpu().double()
+    ref = G.ref_conv_rows(x, w, b, pad_l=(k - 1) // 2)
+    if act:
+        ref = ref.clamp_min(0)
+    ref[R // 3: R // 3 + 4] = 0
+    assert bool(torch.isfinite(out).all())
+    assert float(out[R // 3: R // 3 + 4].abs().max()) == 0.0
+    assert (out - ref).abs().max().item() <= 1e-4
+
+
 def test_layernorm_rows(G):
     from vispeech_b200 import _lib
     lib = _lib.load()

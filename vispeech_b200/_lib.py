@@ -64,6 +64,8 @@ _SIGNATURES = {
     "vs_op_rel_attention": (c_int32, [POINTER(VsRows), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_op_conv1d_tf32": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "vs_op_conv1d_split": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_op_wn_layer": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_op_conv1d_umma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,

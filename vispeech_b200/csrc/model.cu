@@ -587,6 +587,29 @@ int vs_op_conv1d_tf32(const float* in, int32_t in_ld, const float* w_packed, con
   return umma_tf32(u, static_cast<cudaStream_t>(stream));
 }
 
+// op-level hook for the fp16 hi/lo conv (csrc/umma_split.cu): fp32 rows in, fp32 rows out; the split / partial-sum kernels around it
+// are the ones the model uses
+int vs_op_conv1d_split(const float* in, int32_t in_ld, const void* w_packed, const float* bias, float* out, int32_t out_ld,
+                       int32_t n_rows, int32_t c_in, int32_t c_out, int32_t taps, int32_t dil, int32_t pad_l, int32_t act,
+                       const int32_t* row_utt, void* ws, int64_t ws_bytes, void* stream) {
+  VS_REQUIRE(in && w_packed && out && ws && n_rows > 0 && out_ld == c_out, "vs_op_conv1d_split: bad arguments (out must be dense)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vs::Workspace w(ws, ws_bytes);
+  const int slices = c_in <= 192 ? 1 : c_in / 192;
+  __half* hi = w.take<__half>((int64_t)n_rows * c_in);
+  __half* lo = w.take<__half>((int64_t)n_rows * c_in);
+  float* part = slices > 1 ? w.take<float>((int64_t)slices * n_rows * c_out) : nullptr;
+  if (!w.ok) { vs::set_error("vs_op_conv1d_split: workspace too small"); return VS_ERR_WORKSPACE; }
+  VS_TRY(vs::rows_to_split(in, in_ld, 0, 1, nullptr, hi, lo, n_rows, c_in, st));
+  vs::UmmaSplit u;
+  u.in_hi = hi; u.in_lo = lo; u.w = static_cast<const __half*>(w_packed); u.bias = bias; u.row_utt = row_utt;
+  u.out32 = slices > 1 ? part : out; u.out32_ld = out_ld; u.out32_slice = (int64_t)n_rows * c_out;
+  u.R = n_rows; u.Cin = c_in; u.N = c_out; u.taps = taps; u.dil = dil; u.pad_l = pad_l; u.act = act; u.k_slices = slices;
+  VS_TRY(vs::umma_split(u, st));
+  if (slices > 1) VS_TRY(vs::sum_partials(part, (int64_t)n_rows * c_out, slices, out, (int64_t)n_rows * c_out, st));
+  return VS_OK;
+}
+
 // 8(f) rank 4: spectrogram_torch / mel_spectrogram_torch (reference mel_processing.py:50-112) as frame rows -> 3xTF32 DFT
 // GEMM (tcgen05) -> magnitude -> 3xTF32 mel GEMM -> log.  rows: n_frames[b] + 3 rows per utterance (vispeech_b200/mel.py).
 int vs_mel_spectrogram(const VsRows* rows, const float* wave, int32_t t_max, const int32_t* n_samples, int32_t hop,

@@ -66,6 +66,29 @@ struct UmmaMrf {
 };
 int umma_mrf(const UmmaMrf& c, cudaStream_t st);
 
+// fp32-accurate conv over planar fp16 hi / lo operands (umma_split.cu): D += a_hi w_hi + a_lo w_hi + a_hi w_lo.
+struct UmmaSplit {
+  const __half* in_hi = nullptr;    // planar [Cin/8][R][8]
+  const __half* in_lo = nullptr;
+  const __half* w = nullptr;        // packing.py pack_split16: [K-slice][NB][tap][3 cs / KC][KC/8][Nblk][8], K' = [w_hi ; w_hi ; w_lo]
+  const float* bias = nullptr;      // [N] or null (added by K-slice 0)
+  float* out32 = nullptr;           // optional fp32 row-major [R][out32_ld]; K-slice s writes out32 + s * out32_slice
+  int out32_ld = 0;
+  int64_t out32_slice = 0;
+  __half* out_hi = nullptr;         // optional planar [N/8][R][8] hi / lo of the result (k_slices == 1 only)
+  __half* out_lo = nullptr;
+  const int32_t* row_utt = nullptr; // validity: zeros are written on rows with row_utt < 0
+  int R = 0, Cin = 0, N = 0, taps = 1, dil = 1, pad_l = 0;
+  int act = 0;                      // 0 none, 1 ReLU
+  int k_slices = 1;                 // Cin / k_slices channels (<= 192) per slice
+};
+int umma_split(const UmmaSplit& c, cudaStream_t st);
+// fp32 rows -> planar hi / lo; n_sum > 1 sums that many partials (x + s * x_stride) first; zeros on invalid rows
+int rows_to_split(const float* x, int ld, int64_t x_stride, int n_sum, const int32_t* row_utt, __half* hi, __half* lo, int R, int C,
+                  cudaStream_t st);
+
+int sum_partials(const float* x, int64_t stride, int n, float* out, int64_t total, cudaStream_t st);   // out = sum_s x[s * stride + .]
+
 bool umma_respair_supported(int C, int taps, int dil);
 int umma_respair(const UmmaPair& c, cudaStream_t st);
 

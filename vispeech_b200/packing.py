@@ -69,6 +69,32 @@ def pack_umma(w: torch.Tensor) -> torch.Tensor:
     return x.to(torch.float16).reshape(-1)
 
 
+def split16_slice(cin: int) -> int:
+    """Channels per K-slice of the fp16 hi/lo conv (csrc/umma_split.cu): the whole K up to 192, else slices of 192."""
+    return cin if cin <= 192 else 192
+
+
+def pack_split16(w: torch.Tensor) -> torch.Tensor:
+    """[taps][Cin][N] fp32 -> fp16 slabs of csrc/umma_split.cu: w = hi + lo (each fp16); per K-slice of cs channels the K axis
+    becomes K' = [w_hi ; w_hi ; w_lo] (3 cs rows: the passes a_hi w_hi, a_lo w_hi, a_hi w_lo share one accumulator), laid out
+    [slice][NB][tap][3 cs / KC][KC/8][Nblk][8] with KC = 64 (32 when cs is not a multiple of 64)."""
+    taps, cin, n = w.shape
+    cs = split16_slice(cin)
+    assert cin % cs == 0 and cs % 32 == 0
+    kc = 64 if cs % 64 == 0 else 32
+    nblk = next(n // nb for nb in range(1, 17) if n % nb == 0 and n // nb <= 256 and (n // nb) % 32 == 0)
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    out = []
+    for s in range(cin // cs):
+        h, l = hi[:, s * cs:(s + 1) * cs], lo[:, s * cs:(s + 1) * cs]
+        k3 = torch.cat([h, h, l], dim=1)                                   # [taps][3 cs][N]
+        x = k3.reshape(taps, 3 * cs // kc, kc // 8, 8, n // nblk, nblk)
+        #              t     kc             p       e  nb         n
+        out.append(x.permute(4, 0, 1, 2, 5, 3).contiguous().reshape(-1))   # nb t kc p n e
+    return torch.cat(out)
+
+
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> nearest TF32 (10-bit mantissa), kept in fp32 words (what tcgen05 kind::tf32 reads)."""
     i = x.contiguous().view(torch.int32)
@@ -244,7 +270,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
     # tensor-core copies of the GEMM-shaped conv weights: "tf32." = plain TF32 (frame level, >= 4096 rows),
     # "x3." = error-compensated 3xTF32 (fp32-level accuracy: phoneme level and small frame-level calls)
     def is_gemm(name):
-        if name.startswith(("tf32.", "x3.", "dec", "emb")) or not name.endswith((".wqkv", ".wo", ".w1", ".w2", ".w")):
+        if name.startswith(("tf32.", "x3.", "s16.", "dec", "emb")) or not name.endswith((".wqkv", ".wo", ".w1", ".w2", ".w")):
             return False
         return name.startswith(("enc_p.", "pitch_predictor.", "frame_prior_net.", "dp.w", "ep.w", "proj.", "flow.", "enc_q."))
     for name in [k for k in out if is_gemm(k)]:
@@ -253,6 +279,9 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
             out["tf32." + name] = pack_tf32(w)
         if w.shape[1] % 16 == 0 and (w.shape[1] < 48 or w.shape[1] % 48 == 0) and w.shape[2] % 32 == 0:
             out["x3." + name] = pack_tf32(w, split3=True)
+        cs = split16_slice(w.shape[1])
+        if w.shape[1] % cs == 0 and cs % 32 == 0 and w.shape[2] % 32 == 0:
+            out["s16." + name] = pack_split16(w)
     for pre_, nl in wn_prefixes:
         for l in range(nl):
             del out["%s%d.in_gate.w" % (pre_, l)]              # only its packed copies are used
