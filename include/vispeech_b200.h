@@ -89,6 +89,8 @@ int64_t vs_launch_count(void);
  * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
  * "mrf_fused": 1 (default) = the decoder's last MRF stage (C = 32: three ResBlocks, sum, conv_post, tanh) is ONE kernel with the
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
+ * "split16": 1 (default) = every conv in the 3xTF32 regime of the encoders / predictors / projection runs as the three-term fp16
+ * hi/lo conv on tcgen05 kind::f16 (csrc/umma_split.cu: same fp32-level accuracy, TMA-fed planar operands), 0 = 3xTF32 (A/B).
  * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast
  * (bit-identical; no gain measured).  "decoder_streams": 1 (default) | 2 = the k=11 ResBlock chains of each decoder stage
  * run on a side stream (no gain measured).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).

@@ -76,6 +76,9 @@ int layernorm_rows(const float* a, const float* b, const float* gamma, const flo
 struct Workspace;
 // `ws`: scratch for the tcgen05 kernel (attention_umma.cu, attention_umma_ws_floats(n_rows) floats); without it the
 // frame-level path falls back to the mma.sync kernel
+// LN(a + sum of n_b partials of b) with an optional second output: the row as planar fp16 hi / lo (umma_split.cu's operand)
+int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride, const float* gamma, const float* beta, float* out,
+                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st);
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
                   Workspace* ws = nullptr);
 int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
@@ -98,7 +101,7 @@ int ensure_dynamic_smem(const void* kernel, int bytes);    // opt in to `bytes` 
 // "defaults overlaid with that model's overrides" into a thread-local snapshot for the duration of the call: kernels'
 // host code reads opts() and never a mutable global, so two models (or two threads) cannot see each other's settings.
 enum Opt { OPT_TF32_MIN_ROWS, OPT_X3_MIN_ROWS, OPT_TF32_PRIOR, OPT_WN_FUSED, OPT_ATTENTION_MMA, OPT_TF32_CLUSTER,
-           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_COUNT };
+           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_SPLIT16, OPT_COUNT };
 constexpr int64_t kOptUnset = INT64_MIN;
 struct Options { int64_t v[OPT_COUNT]; };
 const Options& opts();                                     // the executing call's snapshot (outside a scope: the defaults)

@@ -17,6 +17,7 @@ struct EncLayer {
   const float *wqkv, *bqkv, *wo, *bo, *ek, *ev, *g1, *b1, *g2, *b2, *w1, *bf1, *w2, *bf2;
   const float *t_wqkv, *t_wo, *t_w1, *t_w2;            // TF32 slab copies (umma_tf32.cuh)
   const float *x_wqkv, *x_wo, *x_w1, *x_w2;            // 3xTF32 [hi|lo] slab copies
+  const __half *s_wqkv, *s_wo, *s_w1, *s_w2;           // fp16 hi/lo slabs of umma_split.cu (packing.py pack_split16)
 };
 constexpr int kMaxWnLayers = 16;
 // WN (modules.py:111-184) weights: flow coupling layers (4 layers) and the posterior encoder (16 layers)
@@ -78,6 +79,7 @@ struct VsModel {
   const float *ep_cond, *ep_w1, *ep_b1, *ep_g1, *ep_be1, *ep_w2, *ep_b2, *ep_g2, *ep_be2, *ep_wl, *ep_bl;
   const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
   const float *proj_w, *proj_b, *t_proj_w, *x_proj_w, *x_dp_w1, *x_ep_w1, *x_ep_w2;
+  const __half *s_proj_w, *s_dp_w1, *s_ep_w1;
   std::vector<vs::FlowW> flows;
   vs::PosteriorW enc_q;
   vs::DecoderW dec;
@@ -97,6 +99,7 @@ static int fetch(VsModel* m, const std::string& name, int64_t numel, int32_t dty
   return VS_OK;
 }
 #define FETCH_F32(field, name, numel) VS_TRY(fetch(m, name, numel, VS_DTYPE_F32, reinterpret_cast<const void**>(&(field))))
+#define FETCH_F16(field, name, numel) VS_TRY(fetch(m, name, numel, VS_DTYPE_F16, reinterpret_cast<const void**>(&(field))))
 
 static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::vector<EncLayer>* out) {
   const int H = kHidden, F = kFilter;
@@ -115,6 +118,8 @@ static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::
     FETCH_F32(L.t_w1, "tf32." + q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.t_w2, "tf32." + q + "w2", (int64_t)3 * F * H);
     FETCH_F32(L.x_wqkv, "x3." + q + "wqkv", (int64_t)2 * H * 3 * H);  FETCH_F32(L.x_wo, "x3." + q + "wo", (int64_t)2 * H * H);
     FETCH_F32(L.x_w1, "x3." + q + "w1", (int64_t)2 * 3 * H * F);      FETCH_F32(L.x_w2, "x3." + q + "w2", (int64_t)2 * 3 * F * H);
+    FETCH_F16(L.s_wqkv, "s16." + q + "wqkv", (int64_t)3 * H * 3 * H);   FETCH_F16(L.s_wo, "s16." + q + "wo", (int64_t)3 * H * H);
+    FETCH_F16(L.s_w1, "s16." + q + "w1", (int64_t)3 * 3 * H * F);       FETCH_F16(L.s_w2, "s16." + q + "w2", (int64_t)3 * 3 * F * H);
   }
   return VS_OK;
 }
@@ -164,6 +169,8 @@ static int finalize(VsModel* m) {
   FETCH_F32(m->t_proj_w, "tf32.proj.w", H * 2 * H);       FETCH_F32(m->x_proj_w, "x3.proj.w", 2 * H * 2 * H);
   FETCH_F32(m->x_dp_w1, "x3.dp.w1", 2 * 3 * H * 256);
   FETCH_F32(m->x_ep_w1, "x3.ep.w1", 2 * 3 * H * 768);     FETCH_F32(m->x_ep_w2, "x3.ep.w2", 2 * 3 * 768 * 768);
+  FETCH_F16(m->s_proj_w, "s16.proj.w", 3 * H * 2 * H);    FETCH_F16(m->s_dp_w1, "s16.dp.w1", 3 * 3 * H * 256);
+  FETCH_F16(m->s_ep_w1, "s16.ep.w1", 3 * 3 * H * 768);
   const int L = m->cfg.flow_layers;
   m->flows.resize(m->cfg.n_flows);
   for (int f = 0; f < m->cfg.n_flows; ++f) {
@@ -195,12 +202,70 @@ static int finalize(VsModel* m) {
 
 // ---- attentions.Encoder.forward (attentions.py:35-47), in place on x -------------------------------
 static int64_t encoder_ws_floats(int R) {
-  return (int64_t)R * (3 * kHidden + kHidden + kHidden + kFilter) + attention_umma_ws_floats(R) + 4 * 64;
+  // qkv, att, y (4 K-slice partials), h (fp32, or hi + lo halves), planar hi / lo copies of x and att, attention scratch
+  return (int64_t)R * (3 * kHidden + kHidden + 4 * kHidden + kFilter + 2 * kHidden) + attention_umma_ws_floats(R) + 16 * 64;
+}
+
+// Where the three-term fp16 conv (umma_split.cu) replaces 3xTF32: calls in the 3xTF32 regime (>= x3_min_rows rows, and not the
+// plain-TF32 one), option "split16" (default 1).
+static bool use_split16(int R, bool tf32_allowed) {
+  if (!opts().v[OPT_SPLIT16] || R < opts().v[OPT_X3_MIN_ROWS]) return false;
+  return !(tf32_allowed && R >= opts().v[OPT_TF32_MIN_ROWS]);
+}
+
+// one conv: fp32 rows in (converted to planar hi / lo in `scratch`) -> fp32 rows out
+static int conv_rows_split(const ConvF32& c, const __half* w_s16, Workspace scratch, cudaStream_t st) {
+  __half* hi = scratch.take<__half>((int64_t)c.R * c.Cin);
+  __half* lo = scratch.take<__half>((int64_t)c.R * c.Cin);
+  if (!scratch.ok) { set_error("conv_rows_split: workspace too small"); return VS_ERR_WORKSPACE; }
+  VS_TRY(rows_to_split(c.in, c.in_ld, 0, 1, nullptr, hi, lo, c.R, c.Cin, st));
+  UmmaSplit u;
+  u.in_hi = hi; u.in_lo = lo; u.w = w_s16; u.bias = c.bias; u.out32 = c.out; u.out32_ld = c.out_ld; u.row_utt = c.row_utt;
+  u.R = c.R; u.Cin = c.Cin; u.N = c.Cout; u.taps = c.k; u.dil = c.dil; u.pad_l = c.pad_l; u.act = c.act;
+  return umma_split(u, st);
+}
+
+// attentions.Encoder.forward on the fp16 hi/lo tensor-core conv: x stays fp32 row-major (residual stream, LayerNorm), every
+// conv operand is its planar hi / lo copy, written by the kernel that produced it where that kernel is ours to change
+static int encoder_forward_split(const std::vector<EncLayer>& layers, const VsRows& rows, float* x, Workspace& ws, cudaStream_t st) {
+  const int R = rows.n_rows, H = kHidden, F = kFilter;
+  float* qkv = ws.take<float>((int64_t)R * 3 * H);
+  float* att = ws.take<float>((int64_t)R * H);
+  float* y = ws.take<float>((int64_t)4 * R * H);
+  __half* xs_hi = ws.take<__half>((int64_t)R * H);
+  __half* xs_lo = ws.take<__half>((int64_t)R * H);
+  __half* as_hi = ws.take<__half>((int64_t)R * H);
+  __half* as_lo = ws.take<__half>((int64_t)R * H);
+  __half* h_hi = ws.take<__half>((int64_t)R * F);
+  __half* h_lo = ws.take<__half>((int64_t)R * F);
+  if (!ws.ok) { set_error("encoder: workspace too small"); return VS_ERR_WORKSPACE; }
+  VS_TRY(rows_to_split(x, H, 0, 1, rows.row_utt, xs_hi, xs_lo, R, H, st));
+  for (const EncLayer& L : layers) {
+    UmmaSplit u;
+    u.R = R; u.row_utt = rows.row_utt;
+    u.in_hi = xs_hi; u.in_lo = xs_lo; u.Cin = H; u.w = L.s_wqkv; u.bias = L.bqkv; u.out32 = qkv; u.out32_ld = 3 * H; u.N = 3 * H;
+    VS_TRY(umma_split(u, st));                                               // conv_q|k|v (attentions.py:139-141)
+    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st, &ws));              // attentions.py:148-179
+    VS_TRY(rows_to_split(att, H, 0, 1, rows.row_utt, as_hi, as_lo, R, H, st));
+    u.in_hi = as_hi; u.in_lo = as_lo; u.w = L.s_wo; u.bias = L.bo; u.out32 = y; u.out32_ld = H; u.N = H;
+    VS_TRY(umma_split(u, st));                                               // conv_o
+    VS_TRY(layernorm_rows_ex(x, y, 1, 0, L.g1, L.b1, x, xs_hi, xs_lo, R, H, rows.row_utt, st));   // x = LN(x + y), + its hi / lo copy
+    u = UmmaSplit();
+    u.R = R; u.row_utt = rows.row_utt; u.taps = 3; u.pad_l = 1;
+    u.in_hi = xs_hi; u.in_lo = xs_lo; u.Cin = H; u.w = L.s_w1; u.bias = L.bf1; u.act = 1; u.out_hi = h_hi; u.out_lo = h_lo; u.N = F;
+    VS_TRY(umma_split(u, st));                                               // FFN conv_1 + relu -> planar hi / lo (attentions.py:278-282)
+    u.in_hi = h_hi; u.in_lo = h_lo; u.Cin = F; u.w = L.s_w2; u.bias = L.bf2; u.act = 0; u.out_hi = nullptr; u.out_lo = nullptr;
+    u.out32 = y; u.out32_ld = H; u.out32_slice = (int64_t)R * H; u.N = H; u.k_slices = F / H;
+    VS_TRY(umma_split(u, st));                                               // FFN conv_2: four K-slices, fp32 partials
+    VS_TRY(layernorm_rows_ex(x, y, F / H, (int64_t)R * H, L.g2, L.b2, x, xs_hi, xs_lo, R, H, rows.row_utt, st));
+  }
+  return VS_OK;
 }
 
 static int encoder_forward(const std::vector<EncLayer>& layers, const VsRows& rows, float* x, Workspace& ws,
                            cudaStream_t st, bool frame_level) {
   const int R = rows.n_rows, H = kHidden, F = kFilter;
+  if (use_split16(R, frame_level)) return encoder_forward_split(layers, rows, x, ws, st);
   float* qkv = ws.take<float>((int64_t)R * 3 * H);
   float* att = ws.take<float>((int64_t)R * H);
   float* y = ws.take<float>((int64_t)R * H);
@@ -286,7 +351,7 @@ int64_t vs_workspace_bytes_latent(const VsModel* m, int32_t rp, int32_t rf) {
   const int64_t H = kHidden;
   const int64_t enc_p = encoder_ws_floats(rp), enc_f = encoder_ws_floats(rf);
   const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8);
-  const int64_t prior = enc_f + (int64_t)rf * 2 * H;
+  const int64_t prior = enc_f + (int64_t)rf * (2 * H + H);                   // stats + the projection's hi / lo operand copy
   const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + 2 * H);   // also covers vs_posterior_encode
   int64_t mx = variance;
   if (prior > mx) mx = prior;
@@ -346,7 +411,8 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
     VS_TRY(add_speaker_rows(x, m->dp_cond, *rows, t, H, st));
     c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
     c.in = t; c.in_ld = H; c.Cin = H; c.w = m->dp_w1; c.bias = m->dp_b1; c.out = h1; c.out_ld = 256; c.Cout = 256;
-    VS_TRY(conv_rows(c, nullptr, m->x_dp_w1, st));
+    if (use_split16(R, false)) VS_TRY(conv_rows_split(c, m->s_dp_w1, W, st));
+    else VS_TRY(conv_rows(c, nullptr, m->x_dp_w1, st));
     VS_TRY(layernorm_rows(h1, nullptr, m->dp_g1, m->dp_be1, h1, R, 256, rows->row_utt, st));
     c.in = h1; c.in_ld = 256; c.Cin = 256; c.w = m->dp_w2; c.bias = m->dp_b2; c.out = h2;
     VS_TRY(conv1d_f32(c, st));
@@ -370,7 +436,8 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
     VS_TRY(add_speaker_rows(x, m->ep_cond, *rows, t, H, st));
     c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
     c.in = t; c.in_ld = H; c.Cin = H; c.w = m->ep_w1; c.bias = m->ep_b1; c.out = h1; c.out_ld = 768; c.Cout = 768;
-    VS_TRY(conv_rows(c, nullptr, m->x_ep_w1, st));
+    if (use_split16(R, false)) VS_TRY(conv_rows_split(c, m->s_ep_w1, W, st));
+    else VS_TRY(conv_rows(c, nullptr, m->x_ep_w1, st));
     VS_TRY(layernorm_rows(h1, nullptr, m->ep_g1, m->ep_be1, h1, R, 768, rows->row_utt, st));
     c.in = h1; c.in_ld = 768; c.Cin = 768; c.w = m->ep_w2; c.bias = m->ep_b2; c.out = h2;
     VS_TRY(conv_rows(c, nullptr, m->x_ep_w2, st));
@@ -411,7 +478,8 @@ int vs_frame_prior(const VsModel* m, const VsRows* rows, const float* x_f, const
   ConvF32 c;                                                               // Projection.forward models.py:526-529
   c.R = R; c.row_utt = rows->row_utt; c.in = x_frame_out; c.in_ld = H; c.Cin = H; c.w = m->proj_w; c.bias = m->proj_b;
   c.out = stats; c.out_ld = 2 * H; c.Cout = 2 * H;
-  VS_TRY(conv_rows(c, tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
+  if (use_split16(R, tf32_prior)) VS_TRY(conv_rows_split(c, m->s_proj_w, W, st));
+  else VS_TRY(conv_rows(c, tf32_prior ? m->t_proj_w : nullptr, m->x_proj_w, st));
   return prior_sample(stats, noise, noise_seed, noise_scale, *rows, m_p, logs_p, z_p, st);
 }
 

@@ -30,8 +30,8 @@ std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device
 
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
-                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer"};
-Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0}};
+                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16"};
+Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1}};
 thread_local Options tl_opts;
 thread_local int tl_scope_depth = 0;
 }  // namespace
@@ -63,7 +63,7 @@ int option_set(Options* o, const char* name, int64_t value) {
   VS_REQUIRE(idx >= 0, "unknown option '%s'", name);
   switch (idx) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
-    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: value = value != 0; break;
+    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: value = value != 0; break;
     case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 4, "option attention_mma must be 0..4"); break;
     case OPT_TF32_CLUSTER: case OPT_DECODER_STREAMS: value = value == 2 ? 2 : 1; break;
     case OPT_RESPAIR_GRID_DIV: value = value < 1 ? 1 : value; break;
@@ -303,25 +303,39 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, const float* b,   // a/b may alias out (in-place residual LN)
+                                                             int n_b, int64_t b_stride,        // b = sum of n_b partials (K-slices of umma_split.cu)
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             float* out, int R, const int32_t* __restrict__ row_utt) {
+                                                             float* out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                             int R, const int32_t* __restrict__ row_utt) {
   constexpr int PER = C / 64;                          // float2 per lane: one warp owns a row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= R) return;
   const float2* a2 = reinterpret_cast<const float2*>(a + (size_t)warp * C);
   const float2* b2 = b ? reinterpret_cast<const float2*>(b + (size_t)warp * C) : nullptr;
   float2* o2 = reinterpret_cast<float2*>(out + (size_t)warp * C);
+  // optional second output: the row as planar fp16 hi / lo [C/8][R][8] (the next conv's operand, umma_split.cu); the float2 with
+  // index k = lane + 32 i holds channels 2k, 2k+1, i.e. 4 bytes of plane k / 4
+  auto planar = [&](int k) { return ((size_t)(k >> 2) * R + warp) * 8 + (size_t)(k & 3) * 2; };
   if (row_utt && row_utt[warp] < 0) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) o2[lane + 32 * i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < PER; ++i) {
+      o2[lane + 32 * i] = make_float2(0.f, 0.f);
+      if (out_hi) {
+        *reinterpret_cast<uint32_t*>(out_hi + planar(lane + 32 * i)) = 0u;
+        *reinterpret_cast<uint32_t*>(out_lo + planar(lane + 32 * i)) = 0u;
+      }
+    }
     return;
   }
   float2 v[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) v[i] = a2[lane + 32 * i];
   if (b2) {
+    for (int s = 0; s < n_b; ++s) {                      // fixed order: deterministic
+      const float2* bs = b2 + (size_t)s * (b_stride / 2);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { const float2 w = b2[lane + 32 * i]; v[i].x += w.x; v[i].y += w.y; }
+      for (int i = 0; i < PER; ++i) { const float2 w = bs[lane + 32 * i]; v[i].x += w.x; v[i].y += w.y; }
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -340,19 +354,32 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, con
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const float2 g = g2[lane + 32 * i], be = be2[lane + 32 * i];
-    o2[lane + 32 * i] = make_float2((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
+    const float2 y = make_float2((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
+    o2[lane + 32 * i] = y;
+    if (out_hi) {
+      const __half2 h = __floats2half2_rn(y.x, y.y);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(y.x - hf.x, y.y - hf.y);
+      *reinterpret_cast<__half2*>(out_hi + planar(lane + 32 * i)) = h;
+      *reinterpret_cast<__half2*>(out_lo + planar(lane + 32 * i)) = l;
+    }
   }
 }
 
-int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
-                   const int32_t* row_utt, cudaStream_t st) {
+int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride, const float* gamma, const float* beta, float* out,
+                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st) {
   VS_REQUIRE(C == 192 || C == 256 || C == 768, "layernorm: C=%d unsupported (192, 256 or 768)", C);
+  VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && b_stride % 2 == 0, "layernorm: bad planar outputs / partial stride");
   const int warps_per_block = 8, grid = (R + warps_per_block - 1) / warps_per_block;
-  if (C == 192) layernorm_rows_kernel<192><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
-  else if (C == 256) layernorm_rows_kernel<256><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
-  else layernorm_rows_kernel<768><<<grid, warps_per_block * 32, 0, st>>>(a, b, gamma, beta, out, R, row_utt);
+  if (C == 192) layernorm_rows_kernel<192><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
+  else if (C == 256) layernorm_rows_kernel<256><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
+  else layernorm_rows_kernel<768><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
   VS_LAUNCH_CHECK();
   return VS_OK;
+}
+int layernorm_rows(const float* a, const float* b, const float* gamma, const float* beta, float* out, int R, int C,
+                   const int32_t* row_utt, cudaStream_t st) {
+  return layernorm_rows_ex(a, b, 1, 0, gamma, beta, out, nullptr, nullptr, R, C, row_utt, st);
 }
 
 // ------------------------------------------------------------------------------------------------
