@@ -118,8 +118,8 @@ static int resolve_encoder(VsModel* m, const std::string& p, int n_layers, std::
     FETCH_F32(L.t_w1, "tf32." + q + "w1", (int64_t)3 * H * F);      FETCH_F32(L.t_w2, "tf32." + q + "w2", (int64_t)3 * F * H);
     FETCH_F32(L.x_wqkv, "x3." + q + "wqkv", (int64_t)2 * H * 3 * H);  FETCH_F32(L.x_wo, "x3." + q + "wo", (int64_t)2 * H * H);
     FETCH_F32(L.x_w1, "x3." + q + "w1", (int64_t)2 * 3 * H * F);      FETCH_F32(L.x_w2, "x3." + q + "w2", (int64_t)2 * 3 * F * H);
-    FETCH_F16(L.s_wqkv, "s16." + q + "wqkv", (int64_t)3 * H * 3 * H);   FETCH_F16(L.s_wo, "s16." + q + "wo", (int64_t)3 * H * H);
-    FETCH_F16(L.s_w1, "s16." + q + "w1", (int64_t)3 * 3 * H * F);       FETCH_F16(L.s_w2, "s16." + q + "w2", (int64_t)3 * 3 * F * H);
+    FETCH_F16(L.s_wqkv, "s16." + q + "wqkv", (int64_t)2 * H * 3 * H);   FETCH_F16(L.s_wo, "s16." + q + "wo", (int64_t)2 * H * H);
+    FETCH_F16(L.s_w1, "s16." + q + "w1", (int64_t)2 * 3 * H * F);       FETCH_F16(L.s_w2, "s16." + q + "w2", (int64_t)2 * 3 * F * H);
   }
   return VS_OK;
 }
@@ -169,8 +169,8 @@ static int finalize(VsModel* m) {
   FETCH_F32(m->t_proj_w, "tf32.proj.w", H * 2 * H);       FETCH_F32(m->x_proj_w, "x3.proj.w", 2 * H * 2 * H);
   FETCH_F32(m->x_dp_w1, "x3.dp.w1", 2 * 3 * H * 256);
   FETCH_F32(m->x_ep_w1, "x3.ep.w1", 2 * 3 * H * 768);     FETCH_F32(m->x_ep_w2, "x3.ep.w2", 2 * 3 * 768 * 768);
-  FETCH_F16(m->s_proj_w, "s16.proj.w", 3 * H * 2 * H);    FETCH_F16(m->s_dp_w1, "s16.dp.w1", 3 * 3 * H * 256);
-  FETCH_F16(m->s_ep_w1, "s16.ep.w1", 3 * 3 * H * 768);
+  FETCH_F16(m->s_proj_w, "s16.proj.w", 2 * H * 2 * H);    FETCH_F16(m->s_dp_w1, "s16.dp.w1", 2 * 3 * H * 256);
+  FETCH_F16(m->s_ep_w1, "s16.ep.w1", 2 * 3 * H * 768);
   const int L = m->cfg.flow_layers;
   m->flows.resize(m->cfg.n_flows);
   for (int f = 0; f < m->cfg.n_flows; ++f) {

@@ -70,7 +70,7 @@ int umma_mrf(const UmmaMrf& c, cudaStream_t st);
 struct UmmaSplit {
   const __half* in_hi = nullptr;    // planar [Cin/8][R][8]
   const __half* in_lo = nullptr;
-  const __half* w = nullptr;        // packing.py pack_split16: [K-slice][NB][tap][3 cs / KC][KC/8][Nblk][8], K' = [w_hi ; w_hi ; w_lo]
+  const __half* w = nullptr;        // packing.py pack_split16: [K-slice][NB][tap][cs / KC][hi|lo][KC/8][Nblk][8]
   const float* bias = nullptr;      // [N] or null (added by K-slice 0)
   float* out32 = nullptr;           // optional fp32 row-major [R][out32_ld]; K-slice s writes out32 + s * out32_slice
   int out32_ld = 0;

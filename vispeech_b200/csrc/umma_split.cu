@@ -8,8 +8,9 @@
 //   * activations are PLANAR fp16 [C/8][R][8] tensors (a hi and a lo one): a plane-slab of a row tile is contiguous in HBM and
 //     is one K-chunk column of the UMMA K-major no-swizzle layout, so the A tile arrives by plain TMA bulk copies and a conv
 //     tap is the same tile at a row offset;
-//   * the three terms are three passes over K with the SAME accumulator: K' = [hi | lo | hi] against weight slabs packed as
-//     [w_hi ; w_hi ; w_lo] (packing.py pack_split16); the A tile holds hi and lo once (the third pass re-reads the hi planes);
+//   * the three terms accumulate into the SAME accumulator; per 64-channel K-chunk the weight slabs stream as [w_hi, w_lo]
+//     (packing.py pack_split16): the w_hi slab multiplies the chunk's hi AND lo planes while it is resident, the w_lo slab its
+//     hi planes, so two slabs stream per twelve MMAs; the A tile holds hi and lo once;
 //   * half the tensor time of 3xTF32 (kind::f16 runs at twice the kind::tf32 rate) and half the operand bytes.
 // K-slices: a conv with Cin = 768 (FFN conv_2) runs as four independent K-slices of 192 channels, each a unit of its own
 // writing its own fp32 partial (the consumer - LayerNorm - sums them in a fixed order: deterministic, and four times the
@@ -148,18 +149,22 @@ __global__ void __launch_bounds__(kThreads, 1) umma_split_kernel(const __grid_co
         for (int t = 0; t < taps; ++t) {
           const uint32_t a_tap = a_lo_fixed + a_stage16 + (uint32_t)(t * dil);
           for (int kc = 0; kc < n_kc; ++kc) {
-            // pass 0: hi planes x w_hi, pass 1: lo planes x w_hi, pass 2: hi planes x w_lo
-            const int pass = kc / nkc1, kk = kc - pass * nkc1;
-            uint32_t a_lo = a_tap + (uint32_t)((pass == 1 ? nkc1 : 0) + kk) * chunk16;
+            // slabs alternate w_hi(kk), w_lo(kk) over the K-chunks kk: the w_hi slab serves BOTH a_hi and a_lo while it is
+            // resident (two of the three terms), the w_lo slab a_hi - two slabs stream per 12 MMAs instead of three
+            const int kk = kc >> 1;
+            const bool w_is_lo = kc & 1;
             mbar_wait(b_full(b_slot), b_phase, 5);
             tc_fence_after();
-            uint32_t b_lo = b_lo_fixed + b_base16 + b_slot * slab16;
+            for (int pass = 0; pass < (w_is_lo ? 1 : 2); ++pass) {               // pass 0: a_hi planes, pass 1: a_lo planes
+              uint32_t a_lo = a_tap + (uint32_t)((pass ? nkc1 : 0) + kk) * chunk16;
+              uint32_t b_lo = b_lo_fixed + b_base16 + b_slot * slab16;
 #pragma unroll 4
-            for (int k16 = 0; k16 < k16s; ++k16) {
-              tc_mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
-              accumulate = 1;
-              a_lo += a_kstep;
-              b_lo += b_kstep;
+              for (int k16 = 0; k16 < k16s; ++k16) {
+                tc_mma_f16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                accumulate = 1;
+                a_lo += a_kstep;
+                b_lo += b_kstep;
+              }
             }
             tc_commit(b_empty(b_slot));
             if (++b_slot == (uint32_t)p.SB) { b_slot = 0; b_phase ^= 1; }
@@ -270,7 +275,7 @@ int make_plan(const UmmaSplit& c, Plan* out) {
   VS_REQUIRE(p.cs % 32 == 0 && p.cs <= 192, "umma_split: K-slice of %d channels (multiple of 32, <= 192)", p.cs);
   p.KC = p.cs % 64 == 0 ? 64 : 32;
   p.nkc1 = p.cs / p.KC;
-  p.n_kc = 3 * p.nkc1;
+  p.n_kc = 2 * p.nkc1;                          // weight slabs per tap: [w_hi(kk), w_lo(kk)] for every K-chunk kk
   p.P = p.cs / 8;
   VS_REQUIRE(c.N % 32 == 0 && c.N >= 32, "umma_split: N=%d must be a multiple of 32", c.N);
   p.Nblk = 0;

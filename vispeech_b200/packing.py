@@ -75,9 +75,10 @@ def split16_slice(cin: int) -> int:
 
 
 def pack_split16(w: torch.Tensor) -> torch.Tensor:
-    """[taps][Cin][N] fp32 -> fp16 slabs of csrc/umma_split.cu: w = hi + lo (each fp16); per K-slice of cs channels the K axis
-    becomes K' = [w_hi ; w_hi ; w_lo] (3 cs rows: the passes a_hi w_hi, a_lo w_hi, a_hi w_lo share one accumulator), laid out
-    [slice][NB][tap][3 cs / KC][KC/8][Nblk][8] with KC = 64 (32 when cs is not a multiple of 64)."""
+    """[taps][Cin][N] fp32 -> fp16 slabs of csrc/umma_split.cu: w = hi + lo (each fp16); per K-slice of cs channels and per
+    KC-channel chunk the slabs alternate [w_hi, w_lo] (the w_hi slab serves the products a_hi w_hi and a_lo w_hi, the w_lo slab
+    a_hi w_lo; all three accumulate into one accumulator), laid out [slice][NB][tap][cs / KC][hi|lo][KC/8][Nblk][8] with KC = 64
+    (32 when cs is not a multiple of 64)."""
     taps, cin, n = w.shape
     cs = split16_slice(cin)
     assert cin % cs == 0 and cs % 32 == 0
@@ -88,8 +89,8 @@ def pack_split16(w: torch.Tensor) -> torch.Tensor:
     out = []
     for s in range(cin // cs):
         h, l = hi[:, s * cs:(s + 1) * cs], lo[:, s * cs:(s + 1) * cs]
-        k3 = torch.cat([h, h, l], dim=1)                                   # [taps][3 cs][N]
-        x = k3.reshape(taps, 3 * cs // kc, kc // 8, 8, n // nblk, nblk)
+        k2 = torch.stack([h.reshape(taps, cs // kc, kc, n), l.reshape(taps, cs // kc, kc, n)], dim=2)   # [taps][cs/kc][hi|lo][kc][N]
+        x = k2.reshape(taps, 2 * cs // kc, kc // 8, 8, n // nblk, nblk)
         #              t     kc             p       e  nb         n
         out.append(x.permute(4, 0, 1, 2, 5, 3).contiguous().reshape(-1))   # nb t kc p n e
     return torch.cat(out)
