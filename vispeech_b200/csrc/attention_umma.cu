@@ -424,7 +424,8 @@ struct FxSmem {
 __global__ void __launch_bounds__(256, 2) rel_band_fixup_kernel(VsRows rows, const float* __restrict__ qkv, const float* __restrict__ ek,
                                                              const float* __restrict__ ev, const float* __restrict__ o_main,
                                                              const float* __restrict__ m_in, const float* __restrict__ l_in,
-                                                             float* __restrict__ out, int R) {
+                                                             float* __restrict__ out, __half* __restrict__ out_hi,
+                                                             __half* __restrict__ out_lo, int R) {
   extern __shared__ __align__(16) unsigned char fx_raw[];
   FxSmem& S = *reinterpret_cast<FxSmem*>(fx_raw);
   const int tid = threadIdx.x, h = blockIdx.y, r0 = blockIdx.x * FX_ROWS;
@@ -566,8 +567,19 @@ __global__ void __launch_bounds__(256, 2) rel_band_fixup_kernel(VsRows rows, con
       if (g >= R) continue;
       const float inv = S.inv[R0 + r];
 #pragma unroll
-      for (int st = 0; st < 3; ++st)
-        *reinterpret_cast<float2*>(out + (size_t)g * kHidden + h * D + C0 + 2 * st) = make_float2(acc[r][st].x * inv, acc[r][st].y * inv);
+      for (int st = 0; st < 3; ++st) {
+        const float2 y = make_float2(acc[r][st].x * inv, acc[r][st].y * inv);
+        const int ch = h * D + C0 + 2 * st;                                     // even: the pair sits in one 8-channel plane
+        if (out_hi) {                                                            // the O conv's operand: planar fp16 hi / lo
+          const size_t o = ((size_t)(ch >> 3) * R + g) * 8 + (ch & 7);
+          const __half2 hh = __floats2half2_rn(y.x, y.y);
+          const float2 hf = __half22float2(hh);
+          *reinterpret_cast<__half2*>(out_hi + o) = hh;
+          *reinterpret_cast<__half2*>(out_lo + o) = __floats2half2_rn(y.x - hf.x, y.y - hf.y);
+        } else {
+          *reinterpret_cast<float2*>(out + (size_t)g * kHidden + ch) = y;
+        }
+      }
     }
   }
 }
@@ -587,7 +599,7 @@ bool rel_attention_umma_fits(const VsRows& rows, const Workspace& ws) {
 }
 
 int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
-                       cudaStream_t st) {
+                       cudaStream_t st, __half* out_hi, __half* out_lo) {
   const int R = rows.n_rows;
   VS_REQUIRE(rows.max_len > 0 && rows.max_len <= R, "rel_attention_umma: bad max_len %d", rows.max_len);
   const int64_t tk = R / TK + rows.n_utt + 1, tq = R / TQ + rows.n_utt + 1;
@@ -608,7 +620,7 @@ int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, co
   attention_umma_kernel<<<grid, kThreads, kSmemBytes, st>>>(prm);
   VS_LAUNCH_CHECK();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_band_fixup_kernel), (int)sizeof(FxSmem)));
-  rel_band_fixup_kernel<<<dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads), 256, sizeof(FxSmem), st>>>(rows, qkv, ek, ev, o_main, m, l, out, R);
+  rel_band_fixup_kernel<<<dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads), 256, sizeof(FxSmem), st>>>(rows, qkv, ek, ev, o_main, m, l, out, out_hi, out_lo, R);
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

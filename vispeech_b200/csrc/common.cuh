@@ -79,10 +79,12 @@ struct Workspace;
 // LN(a + sum of n_b partials of b) with an optional second output: the row as planar fp16 hi / lo (umma_split.cu's operand)
 int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride, const float* gamma, const float* beta, float* out,
                       __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st);
+// `out_hi` / `out_lo` (optional, with `wrote_planar`): where the tcgen05 path may write the result as planar fp16 hi / lo INSTEAD
+// of fp32 rows (the O conv's operand); *wrote_planar tells the caller which form it got
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
-                  Workspace* ws = nullptr);
+                  Workspace* ws = nullptr, __half* out_hi = nullptr, __half* out_lo = nullptr, bool* wrote_planar = nullptr);
 int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
-                       cudaStream_t st);
+                       cudaStream_t st, __half* out_hi = nullptr, __half* out_lo = nullptr);
 int64_t attention_umma_ws_floats(int n_rows);
 bool rel_attention_umma_fits(const VsRows& rows, const Workspace& ws);   // enough scratch left for this batch's tiles?
 // tensor-core (3xTF32 mma.sync) form of the same op, attention_mma.cu; rel_attention() dispatches on opts() "attention_mma"

@@ -568,13 +568,16 @@ static size_t attention_smem_bytes() {
 }
 
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
-                  Workspace* ws) {
+                  Workspace* ws, __half* out_hi, __half* out_lo, bool* wrote_planar) {
+  if (wrote_planar) *wrote_planar = false;
   // option "attention_mma": 1 = auto (from 128 rows per utterance up: tcgen05 when the caller gave a workspace, else mma.sync),
   // 0 = CUDA cores, 2 / 3 = always mma.sync (3xTF32 / plain TF32), 4 = always tcgen05
   const int mode = (int)opts().v[OPT_ATTENTION_MMA];
   if (ws && (mode == 4 || (mode == 1 && rows.max_len >= 128 && rel_attention_umma_fits(rows, *ws)))) {
     Workspace scratch = *ws;                       // a copy: the caller's allocations stay where they are
-    return rel_attention_umma(rows, qkv, ek, ev, out, scratch, st);
+    const bool planar = out_hi && out_lo && wrote_planar;
+    if (planar) *wrote_planar = true;
+    return rel_attention_umma(rows, qkv, ek, ev, out, scratch, st, planar ? out_hi : nullptr, planar ? out_lo : nullptr);
   }
   if (mode >= 2 || (mode == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
   const size_t smem = attention_smem_bytes();
