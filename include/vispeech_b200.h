@@ -89,6 +89,10 @@ int64_t vs_launch_count(void);
  * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
  * "mrf_fused": 1 (default) = the decoder's last MRF stage (C = 32: three ResBlocks, sum, conv_post, tanh) is ONE kernel with the
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
+ * "pair_conv": 1 (default) = the decoder's Cin = Cout = 128 convs run on a CTA pair (tcgen05 cta_group::2: weights resident, split
+ * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
+ * "resblock_fused": 1 = the k = 3 ResBlock of the C = 64 stage is ONE kernel with its residual stream in fp32 in TMEM
+ * (csrc/umma_resblock.cu), 0 (default) = three fused conv-pair launches.
  * "split16": 1 (default) = every conv in the 3xTF32 regime of the encoders / predictors / projection runs as the three-term fp16
  * hi/lo conv on tcgen05 kind::f16 (csrc/umma_split.cu: same fp32-level accuracy, TMA-fed planar operands), 0 = 3xTF32 (A/B).
  * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast
@@ -225,6 +229,14 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
                       const int32_t* row_utt, int32_t row_div, void* stream);
 
+/* the same with the c2 epilogue's extra inputs: res2 (the MRF running sum) and res_inv_slope != 0 (res holds a = lrelu(x, 1 / slope);
+ * the residual added is x = min(a, a * res_inv_slope)).  Cin = N = 128 (and 256 at taps <= 3 with option pair_conv = 2) run on a CTA
+ * pair (tcgen05 cta_group::2, csrc/umma_pair.cu) unless option "pair_conv" is 0. */
+int vs_op_conv1d_umma2(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar, const void* res2_planar,
+                       float res_inv_slope, void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
+                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
+                       const int32_t* row_utt, int32_t row_div, void* stream);
+
 /* fused ResBlock1 iteration y = c2(lrelu(c1(lrelu(x)))) + x (+ res2) on planar f16 rows (csrc/umma_respair.cu) */
 int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
                   const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
@@ -237,6 +249,13 @@ int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_pa
  * ([7][32]) HOST pointers (they travel in the kernel's parameter block). */
 int vs_op_mrf32(const void* x_hi, const void* x_lo, const void* const* w_packed, const float* const* b_host,
                 const float* post_w_host, const int32_t* row_utt, int32_t row_div, int32_t n_rows, float* wave, void* stream);
+
+/* A whole ResBlock1 of the C = 64 decoder stage's k = 3 branch in one kernel (csrc/umma_resblock.cu; reference modules.py:210-223:
+ * three iterations x = x + c2(lrelu(c1(lrelu(x)))), dilations 1, 3, 5), residual stream in fp32 in TMEM.  a_planar = lrelu(x0, 0.1) as
+ * planar f16 [8][n_rows][8]; w_packed[6] / b_host[6]: (c1, c2) of iteration m at index 2 m + {0, 1} (device pack_umma slabs, HOST biases);
+ * out_raw = the ResBlock's output x3, planar f16, zeros on gap rows. */
+int vs_op_resblock64(const void* a_planar, const void* const* w_packed, const float* const* b_host, const int32_t* row_utt,
+                     int32_t row_div, int32_t n_rows, void* out_raw, void* stream);
 
 #ifdef __cplusplus
 }

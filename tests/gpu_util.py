@@ -33,7 +33,7 @@ def f16_round(x: torch.Tensor) -> torch.Tensor:
 
 
 def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0, act_scale=1.0, row_utt=None,
-              row_div=1, want_raw=True, want_act=True):
+              row_div=1, want_raw=True, want_act=True, res2=None, res_inv_slope=0.0):
     """x [R][Cin] fp32 (device), w_tcn [taps][Cin][N] fp32.  Returns (raw, act) as [R*up][N/up] fp32."""
     lib = _lib.load()
     R, cin = x.shape
@@ -44,9 +44,10 @@ def umma_conv(x, w_tcn, bias=None, res=None, dil=1, pad_l=0, up=1, act_slope=1.0
     raw = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.float16, device=x.device) if want_raw else None
     act = torch.full((cout // 8, R * up, 8), float("nan"), dtype=torch.float16, device=x.device) if want_act else None
     resp = to_planar(res) if res is not None else None
-    check(lib.vs_op_conv1d_umma(ptr(xin), ptr(wp), ptr(bias), ptr(resp), ptr(raw), ptr(act), R, cin, n, taps, dil, pad_l,
-                                up, float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()),
-          "vs_op_conv1d_umma")
+    res2p = to_planar(res2) if res2 is not None else None
+    check(lib.vs_op_conv1d_umma2(ptr(xin), ptr(wp), ptr(bias), ptr(resp), ptr(res2p), float(res_inv_slope), ptr(raw), ptr(act), R, cin, n,
+                                 taps, dil, pad_l, up, float(act_slope), float(act_scale), ptr(row_utt), row_div, stream()),
+          "vs_op_conv1d_umma2")
     torch.cuda.synchronize()
     return (from_planar(raw) if want_raw else None), (from_planar(act) if want_act else None)
 
@@ -87,6 +88,23 @@ def mrf32(x0, W, B, post_w, row_utt, row_div=1):
                           ptr(row_utt), row_div, R, ptr(wave), stream()), "vs_op_mrf32")
     torch.cuda.synchronize()
     return wave
+
+
+def resblock64(a, W, B, row_utt, row_div=1):
+    """Whole k = 3 ResBlock1 of the C = 64 stage (csrc/umma_resblock.cu).  a = lrelu(x0) [R][64] fp32 (device), W[m][c] = [3][64][64],
+    B[m][c] = [64] (CPU).  Returns the ResBlock's output [R][64] fp32."""
+    lib = _lib.load()
+    R = a.shape[0]
+    ap = to_planar(a)
+    wp = [pack_umma(W[m][c].cpu()).to(a.device) for m in range(3) for c in range(2)]
+    bh = [B[m][c].float().contiguous().cpu() for m in range(3) for c in range(2)]
+    w_arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in wp])
+    b_arr = (ctypes.c_void_p * 6)(*[t.data_ptr() for t in bh])
+    out = torch.full((8, R, 8), float("nan"), dtype=torch.float16, device=a.device)
+    check(lib.vs_op_resblock64(ptr(ap), ctypes.cast(w_arr, ctypes.c_void_p), ctypes.cast(b_arr, ctypes.c_void_p), ptr(row_utt), row_div,
+                               R, ptr(out), stream()), "vs_op_resblock64")
+    torch.cuda.synchronize()
+    return from_planar(out)
 
 
 def conv_f32(x, w_tcn, bias=None, dil=1, pad_l=0, in_slope=1.0, act=0, row_utt=None, row_div=1):

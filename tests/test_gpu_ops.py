@@ -59,6 +59,62 @@ def test_umma_conv_residual_mask_and_scale(G):
     assert raw[160:200].abs().max().item() == 0 and act[160:200].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("R,C,k,dil,form", [(300, 128, 3, 1, "c1"), (384, 128, 11, 5, "c2_mid"), (256 * 150 + 77, 128, 7, 3, "c2_sum"),
+                                           (256 * 75 + 130, 128, 11, 5, "c2_last"), (129, 128, 7, 5, "c1"), (100, 128, 11, 1, "c2_sum0"),
+                                           (5000, 256, 3, 5, "c2_mid")])
+def test_pair_conv_matches_cpu(G, R, C, k, dil, form):
+    """The decoder's wide convs on a CTA pair (tcgen05 cta_group::2, csrc/umma_pair.cu) in each of the decoder's epilogue forms
+    (modules.py:211-220, models.py:280-285) vs an fp64 conv of the fp16-rounded operands; incl. a masked gap, a ragged tail
+    whose second CTA's tile is entirely out of range, and more units than CTA pairs."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(R + k)
+    x = torch.randn(R, C, generator=g)
+    w = torch.randn(k, C, C, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    res = G.f16_round(torch.randn(R, C, generator=g))
+    res2 = G.f16_round(torch.randn(R, C, generator=g))
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    lo, hi = min(40, R // 2), min(90, R // 2 + 10)
+    row_utt[lo:hi] = -1
+    x[lo:hi] = 0
+    kw = dict(dil=dil, pad_l=(k - 1) // 2 * 1, row_utt=row_utt.to(G.DEV))
+    ref = G.ref_conv_rows(G.f16_round(x), G.f16_round(w), b, dil=dil, pad_l=(k - 1) // 2)
+    resd = res.double()
+    x_rec = torch.minimum(resd, resd * float(np.float32(10.0)))
+    _lib.check(lib.vs_set_option(b"pair_conv", 2))
+    try:
+        if form == "c1":
+            raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), act_slope=0.1, want_raw=False, **kw)
+            want_raw, want_act = None, torch.where(ref > 0, ref, 0.1 * ref)
+        elif form == "c2_mid":
+            raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), res_inv_slope=10.0, act_slope=0.1, want_raw=False, **kw)
+            y = ref + x_rec
+            want_raw, want_act = None, torch.where(y > 0, y, 0.1 * y)
+        elif form == "c2_sum0":
+            raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), res_inv_slope=10.0, want_act=False, **kw)
+            want_raw, want_act = ref + x_rec, None
+        elif form == "c2_sum":
+            raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), res2=res2.to(G.DEV), res_inv_slope=10.0, want_act=False, **kw)
+            want_raw, want_act = ref + x_rec + res2.double(), None
+        else:
+            raw, act = G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), res2=res2.to(G.DEV), res_inv_slope=10.0, act_slope=0.1,
+                                   act_scale=1 / 3, want_raw=False, **kw)
+            y = (ref + x_rec + res2.double()) / 3
+            want_raw, want_act = None, torch.where(y > 0, y, 0.1 * y)
+    finally:
+        _lib.check(lib.vs_set_option(b"pair_conv", 1))
+    for got, want in ((raw, want_raw), (act, want_act)):
+        if want is None:
+            continue
+        want = want.clone()
+        want[lo:hi] = 0
+        got = got.cpu().double()
+        assert torch.isfinite(got).all()
+        assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+        assert got[lo:hi].abs().max().item() == 0
+
+
 @pytest.mark.parametrize("R,C,k,dil", [(1000, 32, 3, 1), (777, 32, 11, 5), (1500, 32, 7, 3), (600, 64, 3, 5), (129, 32, 11, 1),
                                       (246 * 3, 32, 11, 3), (5000, 64, 7, 5), (118 * 40, 32, 11, 1), (70000, 32, 7, 1),
                                       (5000, 64, 11, 5), (118 * 9 + 5, 64, 11, 1), (40000, 64, 11, 3)])
@@ -136,6 +192,43 @@ def test_mrf_stage_matches_cpu(G, R, row_div, gaps):
     assert torch.isfinite(wave).all()
     assert err <= 2e-3 * max(1.0, ref.abs().max().item())
     assert wave[~valid].abs().max().item() == 0 if (~valid).any() else True
+
+
+@pytest.mark.parametrize("R,row_div,gaps", [(100, 1, []), (480 * 3 + 77, 1, [(900, 960)]), (4096, 4, [(0, 8), (2000, 2100), (4000, 4096)]),
+                                              (480 * 160 + 31, 256, [(25600, 26112)])])
+def test_resblock64_matches_cpu(G, R, row_div, gaps):
+    """The k = 3 ResBlock1 of the C = 64 stage as one kernel (csrc/umma_resblock.cu; modules.py:210-223) against an fp64 chain
+    in which only the conv OPERANDS are rounded to fp16 (the residual stream stays in full precision, as it does in TMEM).
+    Covers a partial super tile, ragged tails, gaps at both ends and more super tiles than CTAs."""
+    g = torch.Generator().manual_seed(R + 1)
+    ds = (1, 3, 5)
+    valid = torch.ones(R, dtype=torch.bool)
+    for lo, hi in gaps:
+        valid[lo:hi] = False
+    row_utt = torch.where(valid[::row_div], 0, -1).to(torch.int32)
+    valid = (row_utt >= 0).repeat_interleave(row_div)[:R]
+    x0 = torch.randn(R, 64, generator=g) * 0.7
+    x0[~valid] = 0
+    W = [[torch.randn(3, 64, 64, generator=g) / (64 * 3) ** 0.5 for _ in range(2)] for _ in ds]
+    B = [[torch.randn(64, generator=g) * 0.1 for _ in range(2)] for _ in ds]
+    lrelu = lambda t, s=0.1: torch.where(t > 0, t, s * t)
+    a0 = G.f16_round(lrelu(x0))                            # what the previous kernel stores
+    out = G.resblock64(a0.to(G.DEV), W, B, row_utt.to(G.DEV), row_div).cpu().double()
+
+    vm = valid.double()[:, None]
+    ad = a0.double()
+    x = torch.minimum(ad, ad * float(np.float32(10.0)))   # the kernel's x0 = min(a, 10 a) in fp32
+    for m, d in enumerate(ds):
+        a = (ad if m == 0 else G.f16_round(lrelu(x).float()).double()) * vm
+        c1 = G.ref_conv_rows(a, G.f16_round(W[m][0]), B[m][0], dil=d, pad_l=1)
+        t = G.f16_round(lrelu(c1).float()).double() * vm
+        x = x + G.ref_conv_rows(t, G.f16_round(W[m][1]), B[m][1], dil=1, pad_l=1)
+    ref = x * vm
+    err = (out - ref).abs().max().item()
+    print("R=%d  max|out - ref| = %.3e  (|ref| max %.3f)" % (R, err, ref.abs().max().item()))
+    assert torch.isfinite(out).all()
+    assert err <= 2e-3 * ref.abs().max().item()
+    assert out[~valid].abs().max().item() == 0 if (~valid).any() else True
 
 
 @pytest.mark.parametrize("stage", [0, 2, 3])

@@ -70,9 +70,12 @@ _SIGNATURES = {
                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vs_op_conv1d_umma": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
+    "vs_op_conv1d_umma2": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
     "vs_op_respair": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                 c_int32, c_int32, c_float, c_float, c_void_p, c_int32, c_void_p]),
     "vs_op_mrf32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "vs_op_resblock64": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

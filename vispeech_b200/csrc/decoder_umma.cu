@@ -199,6 +199,17 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
       __half* AA = on_side ? buf[7] : buf[2];
       __half* BA = on_side ? buf[8] : buf[3];
       if (two && j == kDecKernels - 1) VS_CUDA_CHECK(cudaEventRecord(side->sum, st_main));   // S = k3 + k7 is enqueued
+      if (!on_side && opts().v[OPT_RESBLOCK_FUSED] && umma_resblock_supported(cout, k) && j == 0) {
+        // the whole k = 3 ResBlock of the C = 64 stage as one kernel: residual stream in fp32 in TMEM (umma_resblock.cu)
+        UmmaResBlock rb;
+        rb.a = XA; rb.out_raw = S; rb.row_utt = valid; rb.row_div = mul; rb.R = Rs;
+        for (int mth = 0; mth < kDecDils; ++mth) {
+          rb.w[mth][0] = w.c1_16[n][mth].w; rb.w[mth][1] = w.c2_16[n][mth].w;
+          rb.b1_host[mth] = w.bias_host[n][mth][0]; rb.b2_host[mth] = w.bias_host[n][mth][1];
+        }
+        VS_TRY(umma_resblock(rb, st));
+        continue;
+      }
       if (fused[j]) {
         const __half* cur = XA;                                   // a = lrelu(x): the only stream between iterations
         for (int mth = 0; mth < kDecDils; ++mth) {

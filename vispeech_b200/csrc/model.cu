@@ -751,6 +751,20 @@ int vs_op_conv1d_umma(const void* in_planar, const void* w_packed, const float* 
   return umma_conv1d(c, static_cast<cudaStream_t>(stream));
 }
 
+int vs_op_conv1d_umma2(const void* in_planar, const void* w_packed, const float* bias, const void* res_planar, const void* res2_planar,
+                       float res_inv_slope, void* out_raw, void* out_act, int32_t n_rows, int32_t c_in, int32_t n_cols, int32_t taps,
+                       int32_t dil, int32_t pad_l, int32_t up, float act_slope, float act_scale,
+                       const int32_t* row_utt, int32_t row_div, void* stream) {
+  UmmaConv c;
+  c.in = static_cast<const __half*>(in_planar); c.w = static_cast<const __half*>(w_packed);
+  c.bias = bias; c.res = static_cast<const __half*>(res_planar); c.res2 = static_cast<const __half*>(res2_planar);
+  c.res_inv_slope = res_inv_slope;
+  c.out_raw = static_cast<__half*>(out_raw); c.out_act = static_cast<__half*>(out_act);
+  c.R = n_rows; c.Cin = c_in; c.N = n_cols; c.taps = taps; c.dil = dil; c.pad_l = pad_l; c.up = up;
+  c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
+  return umma_conv1d(c, static_cast<cudaStream_t>(stream));
+}
+
 int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_packed, const float* b1, const float* b2,
                   const void* res2_planar, void* out_raw, void* out_act, int32_t n_rows, int32_t channels, int32_t taps,
                   int32_t dil, float act_slope, float act_scale, const int32_t* row_utt, int32_t row_div, void* stream) {
@@ -761,6 +775,19 @@ int vs_op_respair(const void* x_planar, const void* w1_packed, const void* w2_pa
   c.out_act = static_cast<__half*>(out_act); c.R = n_rows; c.C = channels; c.taps = taps; c.dil = dil;
   c.act_slope = act_slope; c.act_scale = act_scale; c.row_utt = row_utt; c.row_div = row_div > 0 ? row_div : 1;
   return umma_respair(c, static_cast<cudaStream_t>(stream));
+}
+
+int vs_op_resblock64(const void* a_planar, const void* const* w_packed /*[6]*/, const float* const* b_host /*[6]*/,
+                     const int32_t* row_utt, int32_t row_div, int32_t n_rows, void* out_raw, void* stream) {
+  VS_REQUIRE(w_packed && b_host, "vs_op_resblock64: null pointer");
+  UmmaResBlock f;
+  f.a = static_cast<const __half*>(a_planar); f.out_raw = static_cast<__half*>(out_raw);
+  for (int m = 0; m < 3; ++m) {
+    f.w[m][0] = static_cast<const __half*>(w_packed[2 * m]); f.w[m][1] = static_cast<const __half*>(w_packed[2 * m + 1]);
+    f.b1_host[m] = b_host[2 * m]; f.b2_host[m] = b_host[2 * m + 1];
+  }
+  f.row_utt = row_utt; f.row_div = row_div > 0 ? row_div : 1; f.R = n_rows;
+  return umma_resblock(f, static_cast<cudaStream_t>(stream));
 }
 
 int vs_op_mrf32(const void* x_hi, const void* x_lo, const void* const* w_packed /*[18]*/, const float* const* b_host /*[18]*/,

@@ -33,6 +33,10 @@ struct UmmaConv {
 };
 
 int umma_conv1d(const UmmaConv& a, cudaStream_t st);
+// The same conv on a CTA pair (tcgen05 cta_group::2, weights resident and split between the two CTAs; umma_pair.cu): Cin = N = 128
+// (any k of the decoder) and 256 (k = 3).  umma_conv1d routes to it when option "pair_conv" is on.
+bool umma_pair_supported(const UmmaConv& c);
+int umma_pair_conv(const UmmaConv& c, cudaStream_t st);
 void* umma_conv_timing_buffer();   // option "umma_timing_buffer": >= 296*12 int64 of per-CTA wait clocks, or null
 
 // One fused ResBlock1 iteration y = c2(lrelu(c1(a))) + lrelu^-1(a), a = lrelu(x) (umma_respair.cu), C in {32, 64}.
@@ -88,6 +92,19 @@ int rows_to_split(const float* x, int ld, int64_t x_stride, int n_sum, const int
                   cudaStream_t st);
 
 int sum_partials(const float* x, int64_t stride, int n, float* out, int64_t total, cudaStream_t st);   // out = sum_s x[s * stride + .]
+
+// A whole ResBlock1 of the C = 64 stage's k = 3 branch in one kernel, residual stream in fp32 in TMEM (umma_resblock.cu).
+struct UmmaResBlock {
+  const __half* a = nullptr;             // ACTIVATED input a = lrelu(x0, 0.1), planar [8][R][8]; x0 is recovered as min(a, 10 a)
+  const __half* w[3][2] = {};            // [iteration d = 1, 3, 5][c1 | c2], slabs as in UmmaConv
+  const float* b1_host[3] = {};          // host copies of the biases (64 floats each): they travel in the parameter block
+  const float* b2_host[3] = {};
+  __half* out_raw = nullptr;             // the ResBlock's output, planar [8][R][8], zeros on gap rows
+  const int32_t* row_utt = nullptr; int row_div = 1;
+  int R = 0;
+};
+bool umma_resblock_supported(int C, int taps);
+int umma_resblock(const UmmaResBlock& c, cudaStream_t st);
 
 bool umma_respair_supported(int C, int taps, int dil);
 int umma_respair(const UmmaPair& c, cudaStream_t st);
