@@ -91,8 +91,11 @@ int64_t vs_launch_count(void);
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
  * "pair_conv": 1 (default) = the decoder's Cin = Cout = 128 convs run on a CTA pair (tcgen05 cta_group::2: weights resident, split
  * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
- * "resblock_fused": 1 = the k = 3 ResBlock of the C = 64 stage is ONE kernel with its residual stream in fp32 in TMEM
- * (csrc/umma_resblock.cu), 0 (default) = three fused conv-pair launches.
+ * "pair_fused": 1 (default) = the k = 3 ResBlock iterations of the C = 128 stage run as ONE kernel per iteration on a CTA pair (conv1,
+ * leaky-ReLU, conv2, residual; the intermediate stays in shared memory; csrc/umma_pairfused.cu), 2 = also every iteration of the C = 64
+ * stage (measured: no gain over the single-CTA fused kernel there), 0 = two CTA-pair conv launches per iteration (A/B).
+ * "resblock_fused": 1 (default) = the k = 3 ResBlock of the C = 64 stage is ONE kernel with its residual stream in fp32 in TMEM
+ * (csrc/umma_resblock.cu), 0 = three fused conv-pair launches (A/B).
  * "split16": 1 (default) = every conv in the 3xTF32 regime of the encoders / predictors / projection runs as the three-term fp16
  * hi/lo conv on tcgen05 kind::f16 (csrc/umma_split.cu: same fp32-level accuracy, TMA-fed planar operands), 0 = 3xTF32 (A/B).
  * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast

@@ -320,6 +320,23 @@ def test_c1_log_mel_of_waveform(net, precision):
     assert float(err.max()) <= 1e-2
 
 
+@pytest.mark.parametrize("path", [p for p in GOLDEN if not p.endswith("c1.npz")], ids=lambda p: os.path.basename(p)[:-4])
+def test_log_mel_of_waveform_other_goldens(net, path):
+    """The same unrelaxed bar (log-mel max-abs <= 1e-2, product decoder) on every other golden utterance that stores the
+    reference waveform: given durations, predicted durations, manual edits, the 2-phoneme utterance."""
+    from oracle.metrics import mel_spectrogram
+    d = dict(np.load(path))
+    if "o" not in d:
+        pytest.skip("fixture holds no waveform")
+    o, *_ = run_golden(net, d, 0)
+    ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d.get("o_is_f16x64", 0)) else 1)
+    w = o[0, 0].cpu()
+    assert w.numel() == ref.numel()
+    err = (mel_spectrogram(ref) - mel_spectrogram(w)).abs()
+    print(os.path.basename(path), "log-mel max-abs %.4f mean-abs %.5f  snr %.1f dB" % (float(err.max()), float(err.mean()), snr_db(ref, w)))
+    assert float(err.max()) <= 1e-2
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_unfused_resblock_paths_still_match(net, mode):
     """The default decoder fuses every ResBlock iteration that fits (C=32 all k, C=64 k=3,7).  Switch the fusion off

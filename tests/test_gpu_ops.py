@@ -119,6 +119,24 @@ def test_pair_conv_matches_cpu(G, R, C, k, dil, form):
                                       (246 * 3, 32, 11, 3), (5000, 64, 7, 5), (118 * 40, 32, 11, 1), (70000, 32, 7, 1),
                                       (5000, 64, 11, 5), (118 * 9 + 5, 64, 11, 1), (40000, 64, 11, 3)])
 def test_fused_resblock_pair_matches_cpu(G, R, C, k, dil):
+    _check_respair(G, R, C, k, dil)
+
+
+@pytest.mark.parametrize("R,C,k,dil", [(600, 64, 3, 5), (5000, 64, 7, 5), (5000, 64, 11, 5), (118 * 9 + 5, 64, 11, 1), (236 * 80 + 3, 64, 11, 3),
+                                      (122 * 2 * 90 + 7, 64, 7, 1), (300, 128, 3, 1), (126 * 2 * 80 + 100, 128, 3, 5), (127, 128, 3, 3)])
+def test_pair_fused_resblock_iteration_matches_cpu(G, R, C, k, dil):
+    """The same fused iteration on a CTA pair (tcgen05 cta_group::2, csrc/umma_pairfused.cu): C = 64 at every k and C = 128 at
+    k = 3, incl. single-tile inputs (the pair's second CTA has no rows), ragged tails and more units than CTA pairs."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.vs_set_option(b"pair_fused", 2))
+    try:
+        _check_respair(G, R, C, k, dil)
+    finally:
+        _lib.check(lib.vs_set_option(b"pair_fused", 1))
+
+
+def _check_respair(G, R, C, k, dil):
     """y = c2(lrelu(c1(lrelu(x)))) + x (modules.py:211-220) in one kernel.  The kernel takes a = lrelu(x) and recovers
     the residual as min(a, a/slope); compared with an fp64 chain using the same fp16 roundings (a, the intermediate),
     incl. a masked gap (rows that must act as zero padding for BOTH convs).  C = 64, k = 11 takes the kernel's TIGHT form

@@ -20,13 +20,13 @@ for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
         continue
     ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d.get("o_is_f16x64", 0)) else 1)
     m_ref = mel_spectrogram(ref)
-    for label, prec, opts in (("fp32", 1, {}), ("f16", 0, {}), ("f16 no-resblock", 0, {"resblock_fused": 0}),
-                              ("f16 no-mrf", 0, {"mrf_fused": 0}), ("f16 unfused pairs", 0, {"fused_respair": 0, "resblock_fused": 0})):
+    for label, prec, opts in (("fp32", 1, {}), ("f16", 0, {}), ("f16 no resblock64", 0, {"resblock_fused": 0}), ("f16 no pair conv", 0, {"pair_conv": 0, "pair_fused": 0}),
+                              ("f16 no-mrf", 0, {"mrf_fused": 0}), ("f16 unfused pairs", 0, {"fused_respair": 0})):
         for k, v in opts.items():
             net.set_option(k, v)
         o = run_golden(net, d, prec)[0]
         for k in opts:
-            net.set_option(k, {"resblock_fused": 1, "mrf_fused": 1, "fused_respair": 2}[k])
+            net.set_option(k, {"resblock_fused": 1, "mrf_fused": 1, "fused_respair": 2, "pair_conv": 1, "pair_fused": 1}[k])
         w = o[0, 0].cpu()
         n = min(w.numel(), ref.numel())
         m = mel_spectrogram(w)

@@ -29,8 +29,8 @@ struct DecoderW {
   // f16 tcgen05 path
   ConvW16 pre16, ups16[kDecStages];
   ConvW16 c1_16[kDecStages * kDecKernels][kDecDils], c2_16[kDecStages * kDecKernels][kDecDils];
-  // host copies of the ResBlock biases of the narrow stages (C <= 64): parameters of the fused pair kernel
-  float bias_host[kDecStages * kDecKernels][kDecDils][2][64];
+  // host copies of the ResBlock biases of the stages with fused kernels (C <= 128): they travel in the kernels' parameter blocks
+  float bias_host[kDecStages * kDecKernels][kDecDils][2][128];
   float post_w_host[7 * 32];                  // conv_post weights for umma_mrf.cu (kernel parameters)
 };
 

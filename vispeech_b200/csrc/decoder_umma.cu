@@ -39,7 +39,7 @@ int resolve_decoder_f16(const FetchFn& fetch, DecoderW* d) {
         DF16(d->c2_16[n][mth].w, q + "c2." + std::to_string(mth) + ".w", numel);
         d->c1_16[n][mth].b = d->c1[n][mth].b;
         d->c2_16[n][mth].b = d->c2[n][mth].b;
-        if (cout <= 64) {   // parameters of the fused kernels (umma_respair.cu, umma_mrf.cu)
+        if (cout <= 128) {   // parameters of the fused kernels (umma_respair.cu, umma_pairfused.cu, umma_resblock.cu, umma_mrf.cu)
           VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][0], d->c1[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
           VS_CUDA_CHECK(cudaMemcpy(d->bias_host[n][mth][1], d->c2[n][mth].b, cout * sizeof(float), cudaMemcpyDeviceToHost));
         }

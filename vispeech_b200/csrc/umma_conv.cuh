@@ -107,6 +107,9 @@ bool umma_resblock_supported(int C, int taps);
 int umma_resblock(const UmmaResBlock& c, cudaStream_t st);
 
 bool umma_respair_supported(int C, int taps, int dil);
+// the same fused iteration on a CTA pair (tcgen05 cta_group::2; umma_pairfused.cu): C = 64 (every k) and C = 128 (k = 3)
+bool umma_pairfused_supported(int C, int taps, int dil);
+int umma_pairfused(const UmmaPair& c, cudaStream_t st);
 int umma_respair(const UmmaPair& c, cudaStream_t st);
 
 }  // namespace vs

@@ -24,7 +24,7 @@ namespace {
 
 using namespace umma;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = (3 + kEpiWarps) * 32;     // producer | MMA issuer (leader) | relay | 8 epilogue warps
+constexpr int kThreads = (4 + kEpiWarps) * 32;     // producer | MMA issuer (leader) | relay | 8 epilogue warps | second MMA issuer
 constexpr int kMaxSlots = 8;
 constexpr int kMaxAcc = 4;
 constexpr int kKCH = 64;                            // channels per A chunk
@@ -33,7 +33,7 @@ constexpr int kPairM = 2 * kTileM;
 constexpr int kMaxCC = 2;                           // 32-column chunks per epilogue warp (N = 128: 64 columns each)
 
 struct Plan {
-  int rows_a, halo_l, n_chunks, planes, nhalf, nslot, nacc, n_units, row_div_shift;
+  int rows_a, halo_l, n_chunks, planes, nhalf, nslot, nacc, n_units, row_div_shift, n_issuers;
   uint32_t slot_bytes, w_bytes, off_w, off_bar, off_bias, smem_bytes;
 };
 struct Params {
@@ -220,8 +220,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
           if (++slot == (uint32_t)p.nslot) { slot = 0; ph ^= 1u; }
         }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+  } else if (warp == 1 || warp == 3 + kEpiWarps) {
+    // ------------------------------------------------------------------ MMA issuers (leader CTA only)
     if (rank == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(kPairM >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)p.rows_a * 16u, b_lbo = (uint32_t)p.nhalf * 16u;
@@ -233,28 +233,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
       const uint32_t w16 = b_lo_fixed + (w_base >> 4);
       const uint32_t nslot = (uint32_t)p.nslot, nacc = (uint32_t)p.nacc, ncols = (uint32_t)c.N;
       const int n_chunks = p.n_chunks;
-      uint32_t slot = 0, ph = 0, acc_slot = 0, acc_phase = 0;
+      // Two issuing warps take alternate units (issuer iw: local units iw, iw + n_issuers, ...): one warp's barrier round trips and
+      // descriptor arithmetic overlap the other's MMAs (in isolation one warp sustains 64 clk per N = 128 MMA, next to eight busy
+      // epilogue warps it measured 80-110, tools/pair_microbench.cu / pair_timing.py).  Slots and accumulators are functions of
+      // the unit index; the plan makes the ring sizes multiples of n_issuers x (chunks per unit), so consecutive users of one
+      // barrier are always the same warp and its phases are consumed in order.
+      const int iw = warp == 1 ? 0 : 1, n_iss = p.n_issuers;
+      const uint32_t units_in_ring = nslot / (uint32_t)n_chunks;
       mbar_wait_cluster(w_full, 0, 4);
       tc_fence_after();
-      // A satisfied mbarrier probe still costs the issuer a few hundred clocks while the tensor pipe is busy (and the pipe only
-      // queues a handful of MMAs), so every barrier is PROBED one step early - the probe's round trip overlaps the MMAs issued
-      // in between - and the blocking wait is taken only if that probe failed.
-      bool a_ready = false, acc_ready = false;
-      for (int u = pair; u < p.n_units; u += n_pairs) {
-        if (!acc_ready) VS_TIMED(tw1, mbar_wait_cluster(acc_empty(acc_slot), acc_phase ^ 1u, 5));
+      // A satisfied mbarrier probe still costs the issuer a few hundred clocks while the tensor pipe is busy, so the next chunk's
+      // barrier is probed before the current chunk's MMAs are issued and the blocking wait is taken only if that probe failed.
+      if (iw < n_iss)
+      for (int n = iw, u = pair + iw * n_pairs; u < p.n_units; n += n_iss, u += n_iss * n_pairs) {
+        const uint32_t acc_slot = (uint32_t)n % nacc, acc_phase = ((uint32_t)n / nacc) & 1u;
+        uint32_t slot = ((uint32_t)n % units_in_ring) * (uint32_t)n_chunks, ph = ((uint32_t)n / units_in_ring) & 1u;
+        VS_TIMED(tw1, mbar_wait_cluster(acc_empty(acc_slot), acc_phase ^ 1u, 5));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_slot * ncols;
-        uint32_t next_acc = acc_slot + 1, next_acc_phase = acc_phase;
-        if (next_acc == nacc) { next_acc = 0; next_acc_phase ^= 1u; }
         uint32_t accumulate = 0;
         uint32_t b_chunk = w16;
-        for (int ch = 0; ch < n_chunks; ++ch, b_chunk += b_chunkstep) {
+        bool a_ready = false;
+        for (int ch = 0; ch < n_chunks; ++ch, b_chunk += b_chunkstep, ++slot) {
           if (!a_ready) VS_TIMED(tw0, mbar_wait_cluster(a_full(slot), ph, 6));
           tc_fence_after();
-          uint32_t nslot_i = slot + 1, nph = ph;
-          if (nslot_i == nslot) { nslot_i = 0; nph ^= 1u; }
-          a_ready = mbar_test_wait(a_full(nslot_i), nph);                       // consumed at the top of the next chunk
-          if (ch == n_chunks - 1) acc_ready = mbar_test_wait(acc_empty(next_acc), next_acc_phase ^ 1u);
+          a_ready = ch + 1 < n_chunks ? mbar_test_wait(a_full(slot + 1), ph) : false;     // consumed at the top of the next chunk
           uint32_t a_tap = a_lo_fixed + ((a_base + slot * p.slot_bytes) >> 4);
           uint32_t b_tap = b_chunk;
 #pragma unroll 1
@@ -266,10 +269,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
               tc_mma_pair(d_tmem, a_tap + (uint32_t)k16 * a_kstep, a_hi, b_tap + (uint32_t)k16 * b_kstep, b_hi, idesc, 1u);
           }
           VS_TIMED(tw2, tc_commit_pair(a_empty(slot)));          // both CTAs' producers may refill the slot once these MMAs have read it
-          slot = nslot_i; ph = nph;
         }
         VS_TIMED(tw2, tc_commit_pair(acc_full(acc_slot)));       // accumulator complete in both CTAs' TMEM -> both epilogues
-        acc_slot = next_acc; acc_phase = next_acc_phase;
       }
     }
     __syncwarp();
@@ -395,8 +396,12 @@ int make_plan(const UmmaConv& c, Plan* out) {
   const uint32_t fixed = bar_bytes + 256u + (uint32_t)c.N * 4u;
   const uint32_t cap = 227u * 1024;
   VS_REQUIRE(p.w_bytes + fixed + 2 * p.slot_bytes <= cap, "umma_pair: weights + 2 A chunks do not fit in shared memory");
-  int nslot = (int)((cap - fixed - p.w_bytes) / p.slot_bytes);
-  p.nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
+  const int nslot = (int)((cap - fixed - p.w_bytes) / p.slot_bytes);
+  // whole units in the ring; with two issuing warps an even number of units (see the kernel), else one issuer
+  const int units = nslot / p.n_chunks;
+  p.n_issuers = units >= 2 ? 2 : 1;
+  p.nslot = (units >= 4 ? 4 : units >= 2 ? 2 : 1) * p.n_chunks;
+  VS_REQUIRE(p.nslot <= kMaxSlots, "umma_pair: A ring deeper than its barrier table");
   p.nacc = 512 / c.N > kMaxAcc ? kMaxAcc : 512 / c.N;
   p.off_w = (uint32_t)p.nslot * p.slot_bytes;
   p.off_bar = (p.off_w + p.w_bytes + 127u) & ~127u;

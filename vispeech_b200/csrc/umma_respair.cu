@@ -442,6 +442,7 @@ int make_plan(const UmmaPair& c, Plan* out) {
 bool umma_respair_supported(int C, int taps, int dil) {
   const int g_mode = (int)opts().v[OPT_FUSED_RESPAIR];
   if (g_mode == 0) return false;
+  if (C == 128) return g_mode == 2 && opts().v[OPT_PAIR_FUSED] != 0 && umma_pairfused_supported(C, taps, dil);   // CTA-pair form only
   if (!(C == 32 || (C == 64 && g_mode == 2))) return false;
   UmmaPair c;
   c.C = C; c.taps = taps; c.dil = dil; c.R = 1024; c.row_div = 1; c.in_slope = 0.1f;
@@ -450,6 +451,10 @@ bool umma_respair_supported(int C, int taps, int dil) {
 }
 
 int umma_respair(const UmmaPair& c, cudaStream_t st) {
+  {   // option "pair_fused": 1 = C = 128 (k = 3) on the CTA-pair kernel, 2 = also C = 64 (umma_pairfused.cu)
+    const int pf = (int)opts().v[OPT_PAIR_FUSED];
+    if ((c.C == 128 || (c.C == 64 && pf >= 2)) && pf && umma_pairfused_supported(c.C, c.taps, c.dil)) return umma_pairfused(c, st);
+  }
   Params prm;
   prm.c = c;
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
