@@ -333,7 +333,7 @@ def main():
     net = build_from_hparams(get_hparams_from_file(), device=dev)
     net.load_state_dict(sd)
     lib = _lib.load()
-    for opt in ("fused_respair", "tf32_min_rows", "x3_min_rows", "tf32_prior", "decoder_streams", "attention_mma", "wn_fused", "tf32_cluster", "mrf_fused", "split16", "resblock_fused", "pair_conv", "pair_fused"):     # A/B knobs for profiling runs (defaults otherwise)
+    for opt in ("fused_respair", "tf32_min_rows", "x3_min_rows", "tf32_prior", "decoder_streams", "attention_mma", "wn_fused", "tf32_cluster", "mrf_fused", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused"):     # A/B knobs for profiling runs (defaults otherwise)
         if os.environ.get("VS_" + opt.upper()):
             _lib.check(lib.vs_set_option(opt.encode(), int(os.environ["VS_" + opt.upper()])))
 
@@ -483,8 +483,9 @@ def main():
                                    "pitch/energy, noise_scale .667), random-init configs/config.json seed 1234" % args.batch,
                        "utterances_per_gpu": args.batch, "valid_frames_per_gpu": int(sum(frames)),
                        "audio_s_per_step_all_gpus": audio_all, "parallelism": "utterance-sharded x%d, no collectives" % world,
-                       "precision": "decoder: fp16 operands, fp32 accumulate (tcgen05 kind::f16), last MRF stage with an fp32 residual stream in TMEM; flow GEMMs: TF32; frame prior, projection, "
-                                    "text encoder and predictors: 3xTF32 (error-compensated, tcgen05 kind::tf32); attention / layernorm: fp32",
+                       "precision": "decoder: fp16 operands, fp32 accumulate (tcgen05 kind::f16); the last MRF stage and the k=3 ResBlock of the C=64 stage keep their residual stream in fp32 in TMEM; "
+                                    "flow GEMMs: TF32 (kind::tf32); frame prior, projection, text encoder and predictors: three-term fp16 hi/lo products on kind::f16 (fp32-level accuracy); "
+                                    "attention: the same three-term form on tcgen05 at frame level, fp32 CUDA cores at phoneme level; layernorm fp32",
                        "pipelining": "value/roofline: stages serialised on one stream; e2e: public infer() in throughput mode "
                                      "(latent stages of call i+1 overlap the decoder of call i on a second stream, waveform "
                                      "D2H of call i overlaps call i+1)" if net.overlap_calls else "none",
@@ -497,7 +498,8 @@ def main():
                               "note": "same loop, waveform converted to s16 on the device (vs_wave_pcm16) before the D2H copy"}},
             "gpu_launches": int(launches),
             "stages_ms": {k: round(v, 3) for k, v in stages.items()},
-            "roofline": {"bound": "tensor", "kernel": "umma_conv1d_kernel + umma_respair_kernel + umma_mrf_kernel (the whole decoder: ~50 launches per step)",
+            "roofline": {"bound": "tensor", "kernel": "the whole decoder, 47 launches per step: umma_conv1d_kernel (conv_pre, ups, C=256 stage), umma_pair_kernel + umma_pairfused_kernel (C=128 stage on CTA pairs, "
+                                   "tcgen05 cta_group::2), umma_resblock_kernel + umma_respair_kernel (C=64 stage), umma_mrf_kernel (C=32 stage + conv_post + tanh)",
                          "achieved": dec_tflops, "peak": peak, "unit": "TFLOP/s", "frac": dec_tflops / peak,
                          "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": peak_src,

@@ -91,6 +91,9 @@ int64_t vs_launch_count(void);
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
  * "pair_conv": 1 (default) = the decoder's Cin = Cout = 128 convs run on a CTA pair (tcgen05 cta_group::2: weights resident, split
  * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
+ * "coupling_fused": 1 (default) = in the plain-TF32 regime (>= tf32_min_rows frame rows) every coupling layer of the flow is ONE kernel
+ * (pre, the 4-layer WN stack, post and the x1 update; residual stream and skip sum in fp32 in TMEM, fp16 operands; csrc/umma_coupling.cu),
+ * 0 = pre / per-layer WN kernels / post / update as separate launches (A/B).
  * "pair_fused": 1 (default) = the k = 3 ResBlock iterations of the C = 128 stage run as ONE kernel per iteration on a CTA pair (conv1,
  * leaky-ReLU, conv2, residual; the intermediate stays in shared memory; csrc/umma_pairfused.cu), 2 = also every iteration of the C = 64
  * stage (measured: no gain over the single-CTA fused kernel there), 0 = two CTA-pair conv launches per iteration (A/B).

@@ -204,3 +204,51 @@ def test_cuda_graph_latency_path_matches_infer(net, state_dict):
                           duration_control=u["duration"][None])[0].clone()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(a).all()) and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("direction", ["reverse", "forward"])
+def test_coupling_layer_kernel_matches_oracle_flow(net, state_dict, direction):
+    """The flow with every coupling layer as ONE kernel (csrc/umma_coupling.cu; modules.py:324-343 + its WN, 148-176; models.py:202-209):
+    13 utterances of ragged lengths (5,300 frame rows: the regime the kernel serves, >= tf32_min_rows), different speakers, gaps
+    between utterances, tiles that straddle utterance boundaries - against the fp32 oracle per utterance (bar: latent <= 1e-2)
+    and against the layer-by-layer TF32 path it replaces."""
+    import ctypes
+    from oracle.vispeech_oracle import DEFAULT_CONFIG, flow_forward, flow_reverse
+    from vispeech_b200 import _lib
+    from vispeech_b200._lib import check, ptr
+    from vispeech_b200.layout import make_rows
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    lens = [431, 17, 900, 112, 113, 640, 5, 777, 300, 224, 1000, 450, 391]
+    sids = [int(x) for x in torch.randint(0, 200, (len(lens),), generator=g)]
+    rows = make_rows(lens, sids, 4, "cuda:0")
+    R = rows.n_rows
+    assert R >= 4096
+    zs = [torch.randn(192, n, generator=g) for n in lens]
+    z0 = torch.zeros(R, 192)
+    row_utt = rows.row_utt.cpu().numpy()
+    for b, n in enumerate(lens):
+        s = int(np.nonzero(row_utt == b)[0][0])
+        z0[s:s + n] = zs[b].t()
+    ws = torch.empty(int(lib.vs_workspace_bytes_latent(net._model, R, R)), dtype=torch.uint8, device="cuda:0")
+    fn = lib.vs_flow_reverse if direction == "reverse" else lib.vs_flow_forward
+    outs = {}
+    for fused in (1, 0):
+        net.set_option("coupling_fused", fused)
+        z = z0.to("cuda:0")
+        check(fn(net._model, ctypes.byref(rows.struct), ptr(z), ptr(ws), ws.numel(), torch.cuda.current_stream().cuda_stream), "flow")
+        torch.cuda.synchronize()
+        outs[fused] = z.cpu()
+    net.set_option("coupling_fused", 1)
+    worst = 0.0
+    for b, n in enumerate(lens):
+        s = int(np.nonzero(row_utt == b)[0][0])
+        gvec = state_dict["emb_g.weight"][sids[b]].reshape(1, -1, 1)
+        ref = (flow_reverse if direction == "reverse" else flow_forward)(state_dict, zs[b][None], gvec, DEFAULT_CONFIG)[0].t()
+        err = float((outs[1][s:s + n] - ref).abs().max())
+        err0 = float((outs[0][s:s + n] - ref).abs().max())
+        worst = max(worst, err)
+        assert err <= 1e-2, (b, n, err, err0)
+    print("coupling kernel, %s: worst |z - oracle| = %.2e; vs the layer-by-layer TF32 path %.2e" %
+          (direction, worst, float((outs[1] - outs[0]).abs().max())))
+    assert float(outs[1][row_utt < 0].abs().max()) == 0.0          # gap rows stay zero

@@ -123,8 +123,8 @@ int main() {
   const int rounds = 200;
   printf("%5s %4s %4s %6s %7s %5s %10s %10s %8s\n", "pair", "N", "m", "chains", "commits", "intl", "clk/round", "clk/MMA", "ms");
   for (int pair = 0; pair < 2; ++pair)
-    for (int n : {64, 128})
-     if (pair || n == 64)
+    for (int n : {32, 64, 128})
+     if (pair || n <= 64)
       for (int m : {12, 44})
         for (int variant = 0; variant < 8; ++variant) {
           // 0: one chain, no commits   1: two chains, no commits   2: two chains, 1 commit per round   3: two chains, 2 commits per round

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.environ.get("VS_LIB_DIR") or os.path.join(HERE, "lib")     # VS_LIB_DIR: a second (diagnostics) build next to the product one
 LIB_PATH = os.path.join(LIB_DIR, "libvispeech_b200.so")
-SOURCES = ["ops_simt.cu", "ops_misc.cu", "attention_mma.cu", "attention_umma.cu", "umma_conv.cu", "umma_tf32.cu", "umma_wn.cu", "umma_respair.cu", "umma_mrf.cu", "umma_split.cu", "umma_resblock.cu", "umma_pair.cu", "umma_pairfused.cu", "decoder.cu", "decoder_umma.cu", "model.cu"]
+SOURCES = ["ops_simt.cu", "ops_misc.cu", "attention_mma.cu", "attention_umma.cu", "umma_conv.cu", "umma_tf32.cu", "umma_wn.cu", "umma_respair.cu", "umma_mrf.cu", "umma_split.cu", "umma_resblock.cu", "umma_pair.cu", "umma_pairfused.cu", "umma_coupling.cu", "decoder.cu", "decoder_umma.cu", "model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

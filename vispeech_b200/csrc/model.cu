@@ -32,6 +32,8 @@ struct WnW {
 struct FlowW {
   const float *pre_w, *pre_b, *post_w, *post_b;
   const float *t_pre, *t_post, *x_pre, *x_post;
+  const __half* c16_w = nullptr;                         // the whole coupling layer as one kernel (umma_coupling.cu; packing.py pack_coupling)
+  const float* c16_b = nullptr;
   WnW wn;
 };
 struct PosteriorW {                                      // enc_q (models.py:212-241), only needed by voice_conversion
@@ -181,6 +183,10 @@ static int finalize(VsModel* m) {
     FETCH_F32(w.t_pre, "tf32." + p + "pre.w", (H / 2) * H);   FETCH_F32(w.t_post, "tf32." + p + "post.w", H * (H / 2));
     FETCH_F32(w.x_pre, "x3." + p + "pre.w", 2 * (H / 2) * H); FETCH_F32(w.x_post, "x3." + p + "post.w", 2 * H * (H / 2));
     VS_TRY(resolve_wn(m, p, L, S, &w.wn));
+    if (L == 4 && m->tensors.count("c16." + p + "w")) {
+      FETCH_F16(w.c16_w, "c16." + p + "w", (int64_t)92 * 24 * 96 * 8);
+      FETCH_F32(w.c16_b, "c16." + p + "b", (int64_t)4 * H + H / 2 + (int64_t)S * 4 * 2 * H);
+    }
   }
   // posterior encoder: optional (inference never touches it; voice_conversion does)
   m->enc_q.present = m->tensors.count("enc_q.pre.w") != 0;
@@ -554,6 +560,15 @@ static int flow_run(const VsModel* m, const VsRows* rows, float* z, bool reverse
     const FlowW& w = m->flows[f];
     const bool flipped = (f & 1) != 0;
     const int in_off = flipped ? H / 2 : 0, upd_off = flipped ? 0 : H / 2;
+    if (w.c16_w && opts().v[OPT_COUPLING_FUSED] && R >= opts().v[OPT_TF32_MIN_ROWS]) {
+      // the plain-TF32 regime (frame level, >= tf32_min_rows rows): the whole coupling layer as ONE kernel, residual stream and
+      // skip sum in fp32 in TMEM, fp16 operands (the same 11-bit significand as TF32)  modules.py:324-343, 148-176
+      UmmaCoupling u;
+      u.z = z; u.w = w.c16_w; u.bias = w.c16_b; u.row_utt = rows->row_utt; u.sid = rows->sid; u.R = R;
+      u.in_off = in_off; u.upd_off = upd_off; u.sign = reverse ? -1.f : 1.f;
+      VS_TRY(umma_coupling(u, st));
+      continue;
+    }
     ConvF32 c;
     c.R = R; c.row_utt = rows->row_utt;
     c.in = z + in_off; c.in_ld = H; c.Cin = H / 2; c.w = w.pre_w; c.bias = w.pre_b; c.out = h; c.out_ld = H; c.Cout = H;

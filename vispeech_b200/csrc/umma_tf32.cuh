@@ -1,5 +1,6 @@
 // TF32 tcgen05 conv over fp32 row-major ragged rows.  See umma_tf32.cu.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace vs {
@@ -46,6 +47,17 @@ struct UmmaWn {
   int R = 0, first = 0, last = 0;
 };
 int umma_wn_layer(const UmmaWn& c, cudaStream_t st);
+// One whole mean-only coupling layer of the flow (pre, 4-layer WN, post, x1 update) in one kernel (umma_coupling.cu), fp16 operands.
+struct UmmaCoupling {
+  float* z = nullptr;                                // [R][192] fp32 rows; x0 = columns [in_off, +96) is read, x1 = [upd_off, +96) updated in place
+  const __half* w = nullptr;                         // packing.py pack_coupling: 92 slabs of 36,864 bytes
+  const float* bias = nullptr;                       // packing.py pack_coupling_bias: [4][192] h biases | [96] m bias | [n_spk][4][384]
+  const int32_t* row_utt = nullptr;                  // [R] utterance of a row, < 0: gap row
+  const int32_t* sid = nullptr;                      // [n_utt] speaker of an utterance
+  int R = 0, in_off = 0, upd_off = 96;
+  float sign = -1.f;                                 // reverse: x1 -= m; forward: x1 += m
+};
+int umma_coupling(const UmmaCoupling& c, cudaStream_t st);
 int rows_to_planar4(const float* in, float* out, int R, int C, cudaStream_t st);    // [R][C] -> [C/4][R][4]
 int planar4_to_rows(const float* in, float* out, int R, int C, cudaStream_t st);    // [C/4][R][4] -> [R][C]
 

@@ -131,6 +131,62 @@ def gate_columns(h: int = 192) -> torch.Tensor:
     return torch.cat([c, c + h], dim=1).reshape(-1)
 
 
+COUPLING_SLAB = 24 * 96 * 8          # halves per weight slab of csrc/umma_coupling.cu: [K = 192 as 24 planes][N = 96][8]
+
+
+def gate96_columns(h: int = 192) -> torch.Tensor:
+    """Column order of a WN in_layer for csrc/umma_coupling.cu: four blocks of [48 tanh channels | the same 48 sigmoid channels]."""
+    c = torch.arange(h).reshape(h // 48, 48)
+    return torch.cat([c, c + h], dim=1).reshape(-1)
+
+
+def pack_coupling(pre, in_w, rs_w, post) -> torch.Tensor:
+    """All GEMM operands of one mean-only coupling layer (modules.py:324-343 with its WN, modules.py:148-176) as the fp16 slab
+    stream csrc/umma_coupling.cu consumes, in consumption order; every slab is [K/8 planes][96 columns][8] padded to COUPLING_SLAB:
+      pre (K = 96) columns 0-95, 96-191;  then per WN layer l: in_layer n-block nb = 0..3 (gate96 column order) x tap 0..4,
+      res_skip -> h columns 0-95, 96-191 (not in the last layer), res_skip -> m: the skip half of res_skip folded with `post`
+      (m = post(sum_l skip_l) = sum_l acts_l (W_skip_l W_post): the skip tensor itself is never formed).
+    pre [96][192], in_w[l] [5][192][384], rs_w[l] [192][384 | 192], post [192][96] (all fp32, K-major rows = input channels)."""
+    def slab(w):                                       # w [K][96] -> planes
+        k = w.shape[0]
+        x = w.reshape(k // 8, 8, 96).permute(0, 2, 1).contiguous().reshape(-1)
+        return torch.cat([x, torch.zeros(COUPLING_SLAB - x.numel())])
+    out = [slab(pre[:, :96]), slab(pre[:, 96:])]
+    gp = gate96_columns(192)
+    L = len(in_w)
+    for l in range(L):
+        wg = in_w[l][:, :, gp]                         # [5][192][384]
+        for nb in range(4):
+            for t in range(5):
+                out.append(slab(wg[t][:, 96 * nb:96 * nb + 96]))
+        last = l == L - 1
+        if not last:
+            out += [slab(rs_w[l][:, :96]), slab(rs_w[l][:, 96:192])]
+        skip_w = rs_w[l] if last else rs_w[l][:, 192:]
+        out.append(slab((skip_w.double() @ post.double()).float()))
+    return torch.cat(out).to(torch.float16).contiguous()
+
+
+def pack_coupling_bias(pre_b, in_b, cond_tab, rs_b, post, post_b) -> torch.Tensor:
+    """fp32 side table of pack_coupling: [hb: L x 192 cumulative biases of h before layer l][mb: 96][per speaker: L x 384 =
+    in_layer bias + cond_layer(emb_g) in gate96 order].  cond_tab [n_spk][L * 384]."""
+    L = len(in_b)
+    gp = gate96_columns(192)
+    hb, acc = [], pre_b.clone()
+    skip_b = torch.zeros(192)
+    for l in range(L):
+        hb.append(acc.clone())
+        if l < L - 1:
+            acc = acc + rs_b[l][:192]
+            skip_b = skip_b + rs_b[l][192:]
+        else:
+            skip_b = skip_b + rs_b[l]
+    mb = post_b + (skip_b.double() @ post.double()).float()
+    n_spk = cond_tab.shape[0]
+    cg = (cond_tab.reshape(n_spk, L, 384) + torch.stack(in_b)[None])[:, :, gp]
+    return torch.cat([torch.cat(hb), mb, cg.reshape(-1)]).float().contiguous()
+
+
 def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_flows=4, flow_layers=4) -> Dict[str, torch.Tensor]:
     """Returns {packed name: CPU tensor (fp32 or f16, contiguous)}."""
     sd = {k: v.detach().float().cpu() for k, v in sd.items()}
@@ -211,6 +267,12 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], n_layers=4, pitch_layers=6, n_f
             out["%s%d.in.b" % (dst, l)] = sd["%s.enc.in_layers.%d.bias" % (src, l)]
             out["%s%d.rs.w" % (dst, l)] = tcn(fold(sd, "%s.enc.res_skip_layers.%d" % (src, l)))[0].contiguous()
             out["%s%d.rs.b" % (dst, l)] = sd["%s.enc.res_skip_layers.%d.bias" % (src, l)]
+        # the whole coupling layer as one kernel (csrc/umma_coupling.cu): fp16 slab stream + fp32 bias / per-speaker table
+        out["c16." + dst + "w"] = pack_coupling(out[dst + "pre.w"], [out["%s%d.in.w" % (dst, l)] for l in range(flow_layers)],
+                                               [out["%s%d.rs.w" % (dst, l)] for l in range(flow_layers)], out[dst + "post.w"])
+        out["c16." + dst + "b"] = pack_coupling_bias(out[dst + "pre.b"], [out["%s%d.in.b" % (dst, l)] for l in range(flow_layers)],
+                                                    out[dst + "cond_tab"], [out["%s%d.rs.b" % (dst, l)] for l in range(flow_layers)],
+                                                    out[dst + "post.w"], out[dst + "post.b"])
 
     # ---- posterior encoder (only voice_conversion uses it; skipped when the checkpoint has no enc_q.*)
     wn_prefixes = [("flow.%d." % f, flow_layers) for f in range(n_flows)]
