@@ -49,7 +49,18 @@ constexpr uint32_t TM_H = 0, TM_M = 192, TM_ACC = 288;
 struct Params {
   UmmaCoupling c;
   int n_tiles;
+  long long* dbg;        // wait-clock counters of the MMA issuer (-DVS_UMMA_TIMING builds, option "umma_timing_buffer")
 };
+#ifdef VS_UMMA_TIMING
+#define VS_TIMED(var, stmt)                         \
+  do {                                              \
+    const long long _t0 = prm.dbg ? clock64() : 0;  \
+    stmt;                                           \
+    if (prm.dbg) var += clock64() - _t0;            \
+  } while (0)
+#else
+#define VS_TIMED(var, stmt) stmt
+#endif
 
 __device__ __forceinline__ float gate_fast(float a, float b) {
   const float ea = __expf(-2.f * fminf(fmaxf(a, -40.f), 40.f));     // clamped: e^80 stays finite in fp32
@@ -125,10 +136,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
     const uint32_t aa_hi = (uint32_t)(make_desc(0, kTileM * 16u, 128u) >> 32), aa_fixed = (uint32_t)make_desc(0, kTileM * 16u, 128u);
     constexpr uint32_t b_kstep = 2u * NBLK, ah_kstep = 2u * ROWS_H, aa_kstep = 2u * kTileM;
     uint32_t wi = 0, n_h16 = 0, n_acts = 0, n_acc[2] = {0, 0}, n_tile = 0;
+#ifdef VS_UMMA_TIMING
+    long long tw_w = 0, tw_h16 = 0, tw_acc = 0, tw_acts = 0, tw_x0 = 0;
+    const long long t_start = clock64();
+#endif
     // one slab = NK MMAs (K = 16 each) of A (start a_lo, K step a_kstep) against the slab, into d
     auto slab_mmas = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t a_kstep, int nk, uint32_t accumulate) {
       const uint32_t slot = wi % kWSlots, ph = (wi / kWSlots) & 1u;
-      mbar_wait(w_full(slot), ph, 2);
+      VS_TIMED(tw_w, mbar_wait(w_full(slot), ph, 2));
       tc_fence_after();
       uint32_t b_lo = b_fixed + ((w_base + slot * kSlabBytes) >> 4);
 #pragma unroll 4
@@ -140,25 +155,25 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
       ++wi;
     };
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++n_tile) {
-      mbar_wait(x0_ready, n_tile & 1u, 3);
+      VS_TIMED(tw_x0, mbar_wait(x0_ready, n_tile & 1u, 3));
       tc_fence_after();
       for (int s = 0; s < 2; ++s)                                        // h = pre(x0)
         slab_mmas(tmem + TM_H + (uint32_t)s * NBLK, aa_fixed + (act16 >> 4), aa_hi, aa_kstep, HALF / 16, 0u);
       tc_commit(h_done);
       for (int l = 0; l < L; ++l) {
-        mbar_wait(h16_ready, n_h16 & 1u, 4);
+        VS_TIMED(tw_h16, mbar_wait(h16_ready, n_h16 & 1u, 4));
         ++n_h16;
         tc_fence_after();
         for (int nb = 0; nb < 4; ++nb) {                                 // in_layer, n-block nb -> acc[nb & 1]
           const uint32_t a = nb & 1;
-          mbar_wait(acc_empty(a), (n_acc[a] & 1u) ^ 1u, 5);
+          VS_TIMED(tw_acc, mbar_wait(acc_empty(a), (n_acc[a] & 1u) ^ 1u, 5));
           ++n_acc[a];
           tc_fence_after();
           const uint32_t d = tmem + TM_ACC + a * NBLK;
           for (int t = 0; t < TAPS; ++t) slab_mmas(d, ah_fixed + ((h16 + (uint32_t)t * 16u) >> 4), ah_hi, ah_kstep, H / 16, t ? 1u : 0u);
           tc_commit(acc_full(a));
         }
-        mbar_wait(acts_ready, n_acts & 1u, 6);
+        VS_TIMED(tw_acts, mbar_wait(acts_ready, n_acts & 1u, 6));
         ++n_acts;
         tc_fence_after();
         if (l < L - 1)                                                    // h += res (the residual add happens in the accumulator)
@@ -167,6 +182,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
         tc_commit(h_done);
       }
     }
+#ifdef VS_UMMA_TIMING
+    if (prm.dbg && lane == 0) {
+      long long* o = prm.dbg + (size_t)blockIdx.x * 8;
+      o[0] = clock64() - t_start; o[1] = tw_w; o[2] = tw_h16; o[3] = tw_acc; o[4] = tw_acts; o[5] = tw_x0;
+    }
+#endif
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue crew: thread = one row, two warps per lane quarter
@@ -305,6 +326,7 @@ int umma_coupling(const UmmaCoupling& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
   prm.n_tiles = (c.R + kValid - 1) / kValid;
+  prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
   int n_sm = 0;
   VS_TRY(device_sm_count(&n_sm));
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_coupling_kernel), (int)SMEM_BYTES));
