@@ -91,6 +91,10 @@ int64_t vs_launch_count(void);
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
  * "pair_conv": 1 (default) = the decoder's Cin = Cout = 128 convs run on a CTA pair (tcgen05 cta_group::2: weights resident, split
  * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
+ * "pdl": bit mask of the kernel groups launched with programmatic dependent launch (the next kernel's launch, CTA scheduling and prologue
+ * overlap its predecessor's tail; every such kernel executes griddepcontrol.wait before it touches global memory): 1 = three-term conv,
+ * LayerNorm, rows_to_split; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention, row_dot; 2 = frame-level
+ * attention kernels; 4 = decoder; 8 = flow.  Default 33 (the groups that measured faster), 0 = every launch fully serialised (A/B).
  * "coupling_fused": 1 (default) = in the plain-TF32 regime (>= tf32_min_rows frame rows) every coupling layer of the flow is ONE kernel
  * (pre, the 4-layer WN stack, post and the x1 update; residual stream and skip sum in fp32 in TMEM, fp16 operands; csrc/umma_coupling.cu),
  * 0 = pre / per-layer WN kernels / post / update as separate launches (A/B).

@@ -16,8 +16,12 @@ ids = torch.stack([u["ids"] for u in utts]); dur = torch.stack([u["duration"] fo
 sid = torch.LongTensor([u["sid"] for u in utts])
 o, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, duration_control=dur)
 from vispeech_b200 import _lib
-_lib.check(_lib.load().vs_set_option(b"tf32_min_rows", 1))          # plain-TF32 route incl. the one-kernel WN layer (umma_wn.cu)
+_lib.check(_lib.load().vs_set_option(b"tf32_min_rows", 1))          # plain-TF32 route: the one-kernel coupling layer (umma_coupling.cu) ...
 o3, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, duration_control=dur, outputs="audio")
+net.set_option("coupling_fused", 0)                                 # ... and the one-kernel WN layer (umma_wn.cu)
+net.set_option("pair_fused", 2)                                     # the CTA-pair fused iteration at C = 64 too
+o4, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, duration_control=dur, outputs="audio")
+net.set_option("coupling_fused", 1); net.set_option("pair_fused", 1)
 _lib.check(_lib.load().vs_set_option(b"tf32_min_rows", 4096))
 net.overlap_calls = True
 o2, *_ = net.infer(ids, torch.LongTensor([40] * 4), sid=sid, noise_scale=0.667, outputs="audio")        # predicted durations

@@ -120,6 +120,7 @@ __device__ __forceinline__ uint32_t idesc_f16(int n, int b_mn) {
 
 __global__ void __launch_bounds__(kThreads, 1) attention_umma_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const int b = blockIdx.z, h = blockIdx.y;
   const int T = prm.rows.utt_len[b], start = prm.rows.utt_start[b];
   const int q0 = blockIdx.x * TQ;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_umma_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tm_s = tmem, tm_o = tmem + 2 * TK;            // O of group g at tm_o + 96 g
 
   if (warp == 0) {
@@ -364,6 +366,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_umma_kernel(const __gri
 // kernel never reads a byte nobody wrote and needs no bounds handling.
 __global__ void __launch_bounds__(256) qkv_to_tiles_kernel(VsRows rows, const float* __restrict__ x, __half* __restrict__ qt,
                                                            __half* __restrict__ kt, __half* __restrict__ vt) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, j = blockIdx.x;
   const int T = rows.utt_len[b], start = rows.utt_start[b];
   if (j * TK >= T) return;
@@ -426,6 +430,8 @@ __global__ void __launch_bounds__(256, 2) rel_band_fixup_kernel(VsRows rows, con
                                                              const float* __restrict__ m_in, const float* __restrict__ l_in,
                                                              float* __restrict__ out, __half* __restrict__ out_hi,
                                                              __half* __restrict__ out_lo, int R) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char fx_raw[];
   FxSmem& S = *reinterpret_cast<FxSmem*>(fx_raw);
   const int tid = threadIdx.x, h = blockIdx.y, r0 = blockIdx.x * FX_ROWS;
@@ -610,17 +616,17 @@ int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, co
   float* m = ws.take<float>((int64_t)R * kHeads);
   float* l = ws.take<float>((int64_t)R * kHeads);
   if (!ws.ok) { set_error("rel_attention_umma: workspace too small"); return VS_ERR_WORKSPACE; }
-  qkv_to_tiles_kernel<<<dim3((rows.max_len + TK - 1) / TK, rows.n_utt), 256, 0, st>>>(rows, qkv, qt, kt, vt);
+  VS_CUDA_CHECK(launch_pdl<2>(qkv_to_tiles_kernel, dim3(dim3((rows.max_len + TK - 1) / TK, rows.n_utt)), dim3(256), 0, st, rows, qkv, qt, kt, vt));
   VS_LAUNCH_CHECK();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_umma_kernel), (int)kSmemBytes));
   Params prm;
   prm.rows = rows; prm.q_tiles = qt; prm.k_tiles = kt; prm.v_tiles = vt; prm.o_main = o_main; prm.m_out = m; prm.l_out = l; prm.R = R;
   prm.dbg = reinterpret_cast<long long*>(opts().v[OPT_TIMING_BUFFER]);
   dim3 grid((rows.max_len + TQ - 1) / TQ, kHeads, rows.n_utt);
-  attention_umma_kernel<<<grid, kThreads, kSmemBytes, st>>>(prm);
+  VS_CUDA_CHECK(launch_pdl<2>(attention_umma_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, prm));
   VS_LAUNCH_CHECK();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_band_fixup_kernel), (int)sizeof(FxSmem)));
-  rel_band_fixup_kernel<<<dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads), 256, sizeof(FxSmem), st>>>(rows, qkv, ek, ev, o_main, m, l, out, out_hi, out_lo, R);
+  VS_CUDA_CHECK(launch_pdl<2>(rel_band_fixup_kernel, dim3(dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads)), dim3(256), sizeof(FxSmem), st, rows, qkv, ek, ev, o_main, m, l, out, out_hi, out_lo, R));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -82,7 +82,8 @@ int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride,
 // `out_hi` / `out_lo` (optional, with `wrote_planar`): where the tcgen05 path may write the result as planar fp16 hi / lo INSTEAD
 // of fp32 rows (the O conv's operand); *wrote_planar tells the caller which form it got
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
-                  Workspace* ws = nullptr, __half* out_hi = nullptr, __half* out_lo = nullptr, bool* wrote_planar = nullptr);
+                  Workspace* ws = nullptr, __half* out_hi = nullptr, __half* out_lo = nullptr, bool* wrote_planar = nullptr,
+                  bool gaps_dont_care = false);   // true: the caller masks gap rows itself (no memset of `out` on the CUDA-core path)
 int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, Workspace& ws,
                        cudaStream_t st, __half* out_hi = nullptr, __half* out_lo = nullptr);
 int64_t attention_umma_ws_floats(int n_rows);
@@ -95,6 +96,29 @@ int row_dot(const float* x, int ld, const float* w, const float* bias, float* ou
 // Per-device launch configuration.  cudaFuncSetAttribute applies to the device that is current when it is called and a
 // process may hold models on several devices (and call from several threads: serving.py's worker), so the "done once"
 // state is kept per (kernel, device) behind a mutex instead of in function-local statics.
+// Programmatic dependent launch: a kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still
+// draining - launch latency, CTA scheduling and the kernel's own prologue (barrier init, TMEM allocation) overlap the predecessor's
+// tail.  Protocol, in EVERY kernel launched this way: pdl_trigger() first thing (lets the next kernel in), pdl_wait() before the
+// first access to global memory another kernel writes or reads (it returns once every preceding grid has completed and flushed).
+// Option "pdl" is a bit mask of kernel groups launched this way (0 = everything fully serialised): 1 the three-term conv, LayerNorm and
+// rows_to_split, 32 the small element-wise kernels of the latent stages (default 33: text encoder 0.54 -> 0.47 ms, variance adapter 0.99 ->
+// 0.88 at the C2 size, where ~100 kernels of 5 - 20 us on 20 - 90 CTAs run back to back), 16 the CUDA-core attention and row_dot (measured:
+// cancels that gain), 2 the frame-level attention kernels (frame prior 2.15 -> 2.4 ms), 4 the decoder, 8 the flow (both +-0).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled(int group);
+template <int GROUP = 1, typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(GROUP) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 int device_sm_count(int* n_sm);                            // SM count of the CURRENT device
 int ensure_dynamic_smem(const void* kernel, int bytes);    // opt in to `bytes` of dynamic shared memory, once per device
 
@@ -103,7 +127,7 @@ int ensure_dynamic_smem(const void* kernel, int bytes);    // opt in to `bytes` 
 // "defaults overlaid with that model's overrides" into a thread-local snapshot for the duration of the call: kernels'
 // host code reads opts() and never a mutable global, so two models (or two threads) cannot see each other's settings.
 enum Opt { OPT_TF32_MIN_ROWS, OPT_X3_MIN_ROWS, OPT_TF32_PRIOR, OPT_WN_FUSED, OPT_ATTENTION_MMA, OPT_TF32_CLUSTER,
-           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_SPLIT16, OPT_RESBLOCK_FUSED, OPT_PAIR_CONV, OPT_PAIR_FUSED, OPT_COUPLING_FUSED, OPT_COUNT };
+           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_SPLIT16, OPT_RESBLOCK_FUSED, OPT_PAIR_CONV, OPT_PAIR_FUSED, OPT_COUPLING_FUSED, OPT_PDL, OPT_COUNT };
 constexpr int64_t kOptUnset = INT64_MIN;
 struct Options { int64_t v[OPT_COUNT]; };
 const Options& opts();                                     // the executing call's snapshot (outside a scope: the defaults)

@@ -54,6 +54,8 @@ int resolve_decoder_f16(const FetchFn& fetch, DecoderW* d) {
 // fp32 row-major [R][C] -> planar f16 [C/8][R][8], zero on invalid rows
 __global__ void to_planar_f16_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_utt,
                                       __half* __restrict__ out, int R, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (plane, row)
   if (i >= (C / 8) * R) return;
   const int pl = i / R, r = i % R;
@@ -141,7 +143,7 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
   if (two) VS_TRY(side_stream(&side));
 
   VS_TRY(mask_frames(rows, max_len, valid, st));                         // (z * x_mask)[:, :, :max_len]  models.py:720
-  to_planar_f16_kernel<<<((kHidden / 8) * R + 255) / 256, 256, 0, st>>>(z, valid, zin, R, kHidden);
+  VS_CUDA_CHECK(launch_pdl<4>(to_planar_f16_kernel, dim3(((kHidden / 8) * R + 255) / 256), dim3(256), 0, st, z, valid, zin, R, kHidden));
   VS_LAUNCH_CHECK();
 
   UmmaConv c;

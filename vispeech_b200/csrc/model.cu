@@ -252,8 +252,8 @@ static int encoder_forward_split(const std::vector<EncLayer>& layers, const VsRo
     u.in_hi = xs_hi; u.in_lo = xs_lo; u.Cin = H; u.w = L.s_wqkv; u.bias = L.bqkv; u.out32 = qkv; u.out32_ld = 3 * H; u.N = 3 * H;
     VS_TRY(umma_split(u, st));                                               // conv_q|k|v (attentions.py:139-141)
     bool planar = false;                                                     // the tcgen05 path writes the O conv's operand itself
-    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st, &ws, as_hi, as_lo, &planar));   // attentions.py:148-179
-    if (!planar) VS_TRY(rows_to_split(att, H, 0, 1, rows.row_utt, as_hi, as_lo, R, H, st));
+    VS_TRY(rel_attention(rows, qkv, L.ek, L.ev, att, st, &ws, as_hi, as_lo, &planar, true));   // attentions.py:148-179
+    if (!planar) VS_TRY(rows_to_split(att, H, 0, 1, rows.row_utt, as_hi, as_lo, R, H, st));   // masks gap rows itself
     u.in_hi = as_hi; u.in_lo = as_lo; u.w = L.s_wo; u.bias = L.bo; u.out32 = y; u.out32_ld = H; u.N = H;
     VS_TRY(umma_split(u, st));                                               // conv_o
     VS_TRY(layernorm_rows_ex(x, y, 1, 0, L.g1, L.b1, x, xs_hi, xs_lo, R, H, rows.row_utt, st));   // x = LN(x + y), + its hi / lo copy

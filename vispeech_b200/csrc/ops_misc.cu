@@ -8,6 +8,8 @@ namespace vs {
 // ---- TextEncoder embedding: x = emb[id] * sqrt(H) (models.py:169); gaps -> 0 -----------------------
 __global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
                                   int R, int n_vocab, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * kHidden) return;
   const int r = i / kHidden, c = i % kHidden;
@@ -15,7 +17,7 @@ __global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const float* 
   x[i] = (id >= 0 && id < n_vocab) ? emb[(size_t)id * kHidden + c] * scale : 0.f;
 }
 int embed_rows(const int32_t* ids, const float* emb, float* x, int R, int n_vocab, cudaStream_t st) {
-  embed_rows_kernel<<<(R * kHidden + 255) / 256, 256, 0, st>>>(ids, emb, x, R, n_vocab, sqrtf((float)kHidden));
+  VS_CUDA_CHECK(launch_pdl<32>(embed_rows_kernel, dim3((R * kHidden + 255) / 256), dim3(256), 0, st, ids, emb, x, R, n_vocab, sqrtf((float)kHidden)));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -24,6 +26,8 @@ int embed_rows(const int32_t* ids, const float* emb, float* x, int R, int n_voca
 __global__ void add_speaker_rows_kernel(const float* __restrict__ x, const float* __restrict__ tab,
                                         const int32_t* __restrict__ row_utt, const int32_t* __restrict__ sid,
                                         float* __restrict__ out, int R, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * C) return;
   const int r = i / C, c = i % C;
@@ -31,8 +35,8 @@ __global__ void add_speaker_rows_kernel(const float* __restrict__ x, const float
   out[i] = (u >= 0) ? x[i] + tab[(size_t)sid[u] * C + c] : 0.f;
 }
 int add_speaker_rows(const float* x, const float* tab, const VsRows& rows, float* out, int C, cudaStream_t st) {
-  add_speaker_rows_kernel<<<(rows.n_rows * C + 255) / 256, 256, 0, st>>>(x, tab, rows.row_utt, rows.sid, out,
-                                                                        rows.n_rows, C);
+  VS_CUDA_CHECK(launch_pdl<32>(add_speaker_rows_kernel, dim3((rows.n_rows * C + 255) / 256), dim3(256), 0, st, x, tab, rows.row_utt, rows.sid, out,
+                                                                        rows.n_rows, C));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -41,6 +45,8 @@ int add_speaker_rows(const float* x, const float* tab, const VsRows& rows, float
 // duration: mode 0: ceil((exp(logw) - 1) * scale) (x_mask == 1 on valid rows); mode 2: control verbatim.
 __global__ void duration_kernel(const float* __restrict__ logw, const double* __restrict__ ctrl, int mode, float scale,
                                 const int32_t* __restrict__ row_utt, double* __restrict__ dur, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   if (row_utt[r] < 0) { dur[r] = 0.0; return; }
@@ -50,6 +56,8 @@ __global__ void duration_kernel(const float* __restrict__ logw, const double* __
 // pitch: lf0 (mode 0: pred*scale; mode 2: 2595*log10(1+hz/700)/500), F0 = (10^(lf0*500/2590)-1)*700 (sic, Q2)
 __global__ void pitch_kernel(const float* __restrict__ pred, const float* __restrict__ ctrl, int mode, float scale,
                              const int32_t* __restrict__ row_utt, float* __restrict__ lf0, float* __restrict__ f0, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   if (row_utt[r] < 0) { lf0[r] = 0.f; f0[r] = 0.f; return; }
@@ -63,6 +71,8 @@ __global__ void pitch_kernel(const float* __restrict__ pred, const float* __rest
 __global__ void energy_kernel(const float* __restrict__ pred, const float* __restrict__ ctrl, int mode, float scale,
                               const int32_t* __restrict__ row_utt, float* __restrict__ norm, float* __restrict__ energy,
                               int R) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   if (row_utt[r] < 0) { norm[r] = 0.f; energy[r] = 0.f; return; }
@@ -74,20 +84,20 @@ __global__ void energy_kernel(const float* __restrict__ pred, const float* __res
 }
 int duration_rows(const float* logw, const double* ctrl, int mode, float scale, const VsRows& rows, double* dur,
                   cudaStream_t st) {
-  duration_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(logw, ctrl, mode, scale, rows.row_utt, dur, rows.n_rows);
+  VS_CUDA_CHECK(launch_pdl<32>(duration_kernel, dim3((rows.n_rows + 255) / 256), dim3(256), 0, st, logw, ctrl, mode, scale, rows.row_utt, dur, rows.n_rows));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 int pitch_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* lf0, float* f0,
                cudaStream_t st) {
-  pitch_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(pred, ctrl, mode, scale, rows.row_utt, lf0, f0, rows.n_rows);
+  VS_CUDA_CHECK(launch_pdl<32>(pitch_kernel, dim3((rows.n_rows + 255) / 256), dim3(256), 0, st, pred, ctrl, mode, scale, rows.row_utt, lf0, f0, rows.n_rows));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
 int energy_rows(const float* pred, const float* ctrl, int mode, float scale, const VsRows& rows, float* norm,
                 float* energy, cudaStream_t st) {
-  energy_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(pred, ctrl, mode, scale, rows.row_utt, norm, energy,
-                                                          rows.n_rows);
+  VS_CUDA_CHECK(launch_pdl<32>(energy_kernel, dim3((rows.n_rows + 255) / 256), dim3(256), 0, st, pred, ctrl, mode, scale, rows.row_utt, norm, energy,
+                                                          rows.n_rows));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -96,6 +106,8 @@ int energy_rows(const float* pred, const float* ctrl, int mode, float scale, con
 // v is zero on gap rows, which is exactly the zero padding of a batch-1 call.
 __global__ void prenet_add_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ w,
                                   const float* __restrict__ b, const int32_t* __restrict__ row_utt, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * kHidden) return;
   const int r = i / kHidden, c = i % kHidden;
@@ -104,7 +116,7 @@ __global__ void prenet_add_kernel(float* __restrict__ x, const float* __restrict
   x[i] += b[c] + w[c * 3 + 0] * vm + w[c * 3 + 1] * v0 + w[c * 3 + 2] * vp;
 }
 int prenet_add(float* x, const float* v, const float* w, const float* b, const VsRows& rows, cudaStream_t st) {
-  prenet_add_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(x, v, w, b, rows.row_utt, rows.n_rows);
+  VS_CUDA_CHECK(launch_pdl<32>(prenet_add_kernel, dim3((rows.n_rows * kHidden + 255) / 256), dim3(256), 0, st, x, v, w, b, rows.row_utt, rows.n_rows));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -114,6 +126,8 @@ int prenet_add(float* x, const float* v, const float* w, const float* b, const V
 // Python float that .item() returned (models.py:421-423); inclusive scan in phoneme order.
 __global__ void lr_count_kernel(VsRows rows, const double* __restrict__ dur, int32_t* __restrict__ cum,
                                 int32_t* __restrict__ frames) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry_s;
   const int b = blockIdx.x, T = rows.utt_len[b], start = rows.utt_start[b];
@@ -151,7 +165,7 @@ __global__ void lr_count_kernel(VsRows rows, const double* __restrict__ dur, int
 }
 int lr_count(const VsRows& rows, const double* dur, int32_t* cum, int32_t* frames, cudaStream_t st) {
   VS_CUDA_CHECK(cudaMemsetAsync(cum, 0, sizeof(int32_t) * rows.n_rows, st));
-  lr_count_kernel<<<rows.n_utt, 256, 0, st>>>(rows, dur, cum, frames);
+  VS_CUDA_CHECK(launch_pdl<32>(lr_count_kernel, dim3(rows.n_utt), dim3(256), 0, st, rows, dur, cum, frames));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -160,6 +174,8 @@ int lr_count(const VsRows& rows, const double* dur, int32_t* cum, int32_t* frame
 // which is the index the reference's expand()+cat() places at frame t.  One warp per frame row.
 __global__ void lr_gather_kernel(VsRows rp, VsRows rf, const float* __restrict__ xp, const int32_t* __restrict__ cum,
                                  float* __restrict__ xf, int32_t* __restrict__ lr_index) {
+  pdl_trigger();
+  pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (r >= rf.n_rows) return;
   const int b = rf.row_utt[r];
@@ -182,7 +198,7 @@ __global__ void lr_gather_kernel(VsRows rp, VsRows rf, const float* __restrict__
 }
 int lr_gather(const VsRows& rp, const VsRows& rf, const float* xp, const int32_t* cum, float* xf, int32_t* lr_index,
               cudaStream_t st) {
-  lr_gather_kernel<<<(rf.n_rows + 7) / 8, 256, 0, st>>>(rp, rf, xp, cum, xf, lr_index);
+  VS_CUDA_CHECK(launch_pdl<32>(lr_gather_kernel, dim3((rf.n_rows + 7) / 8), dim3(256), 0, st, rp, rf, xp, cum, xf, lr_index));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -226,6 +242,8 @@ int randn_fill(float* out, int64_t n, uint64_t seed, cudaStream_t st) {
 __global__ void prior_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise, uint64_t seed, float ns,
                                     const int32_t* __restrict__ row_utt, float* __restrict__ m_p,
                                     float* __restrict__ logs_p, float* __restrict__ z_p, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * kHidden) return;
   const int r = i / kHidden, c = i % kHidden;
@@ -238,8 +256,8 @@ __global__ void prior_sample_kernel(const float* __restrict__ stats, const float
 }
 int prior_sample(const float* stats, const float* noise, uint64_t seed, float ns, const VsRows& rows, float* m_p,
                  float* logs_p, float* z_p, cudaStream_t st) {
-  prior_sample_kernel<<<(rows.n_rows * kHidden + 255) / 256, 256, 0, st>>>(stats, noise, seed, ns, rows.row_utt, m_p,
-                                                                          logs_p, z_p, rows.n_rows);
+  VS_CUDA_CHECK(launch_pdl<32>(prior_sample_kernel, dim3((rows.n_rows * kHidden + 255) / 256), dim3(256), 0, st, stats, noise, seed, ns, rows.row_utt, m_p,
+                                                                          logs_p, z_p, rows.n_rows));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -306,6 +324,8 @@ int coupling_update(float* z, int z_off, const float* m, float sign, const VsRow
 
 // ---- copy with validity mask limited to the first max_len frames of each utterance (models.py:720) ----
 __global__ void mask_frames_kernel(VsRows rows, int max_len, int32_t* __restrict__ row_utt_out) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows.n_rows) return;
   int u = rows.row_utt[r];
@@ -313,7 +333,7 @@ __global__ void mask_frames_kernel(VsRows rows, int max_len, int32_t* __restrict
   row_utt_out[r] = u;
 }
 int mask_frames(const VsRows& rows, int max_len, int32_t* row_utt_out, cudaStream_t st) {
-  mask_frames_kernel<<<(rows.n_rows + 255) / 256, 256, 0, st>>>(rows, max_len, row_utt_out);
+  VS_CUDA_CHECK(launch_pdl<32>(mask_frames_kernel, dim3((rows.n_rows + 255) / 256), dim3(256), 0, st, rows, max_len, row_utt_out));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -332,6 +352,8 @@ int masked_copy(const float* x, const int32_t* row_utt, float* out, int R, int C
 // ---- ragged rows -> [n_utt][C][t_max] (the reference's output layout), tiled transpose ----------------
 __global__ void unpack_rows_kernel(VsRows rows, const float* __restrict__ x, int C, int mul, int t_max,
                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -349,6 +371,8 @@ __global__ void unpack_rows_kernel(VsRows rows, const float* __restrict__ x, int
 }
 // C == 1 (the waveform): no transpose, a masked contiguous copy per utterance, 4 samples per thread
 __global__ void unpack_wave_kernel(VsRows rows, const float* __restrict__ x, int mul, int t_max, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int len = rows.utt_len[b] * mul;
   const size_t start = (size_t)rows.utt_start[b] * mul;
@@ -375,12 +399,12 @@ int unpack_rows(const VsRows& rows, const float* x, int C, int mul, int t_max, f
   if (C == 1 && mul % 4 == 0 && t_max % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     dim3 grid((t_max / 4 + 255) / 256, rows.n_utt);
-    unpack_wave_kernel<<<grid, 256, 0, st>>>(rows, x, mul, t_max, out);
+    VS_CUDA_CHECK(launch_pdl<32>(unpack_wave_kernel, dim3(grid), dim3(256), 0, st, rows, x, mul, t_max, out));
     VS_LAUNCH_CHECK();
     return VS_OK;
   }
   dim3 grid((t_max + 31) / 32, (C + 31) / 32, rows.n_utt);
-  unpack_rows_kernel<<<grid, dim3(32, 8), 0, st>>>(rows, x, C, mul, t_max, out);
+  VS_CUDA_CHECK(launch_pdl<32>(unpack_rows_kernel, dim3(grid), dim3(dim3(32, 8)), 0, st, rows, x, C, mul, t_max, out));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -30,8 +30,8 @@ std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device
 
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
-                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused"};
-Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1}};
+                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl"};
+Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33}};
 thread_local Options tl_opts;
 thread_local int tl_scope_depth = 0;
 }  // namespace
@@ -55,6 +55,8 @@ OptionScope::OptionScope(const Options* overrides) {
 }
 OptionScope::~OptionScope() { --tl_scope_depth; }
 
+bool pdl_enabled(int group) { return (opts().v[OPT_PDL] & group) != 0; }
+
 int option_set(Options* o, const char* name, int64_t value) {
   VS_REQUIRE(name, "option: null name");
   int idx = -1;
@@ -64,6 +66,7 @@ int option_set(Options* o, const char* name, int64_t value) {
   switch (idx) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
     case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: value = value != 0; break;
+    case OPT_PDL: VS_REQUIRE(value >= 0 && value <= 63, "option pdl is a bit mask 0..63"); break;
     case OPT_PAIR_FUSED: VS_REQUIRE(value >= 0 && value <= 2, "option pair_fused must be 0, 1 (C = 128) or 2 (also C = 64)"); break;
     case OPT_PAIR_CONV: VS_REQUIRE(value >= 0 && value <= 2, "option pair_conv must be 0 (off), 1 (C = 128) or 2 (also C = 256, k = 3)"); break;
     case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 4, "option attention_mma must be 0..4"); break;
@@ -310,6 +313,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, con
                                                              float* out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                              int R, const int32_t* __restrict__ row_utt) {
   constexpr int PER = C / 64;                          // float2 per lane: one warp owns a row
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= R) return;
   const float2* a2 = reinterpret_cast<const float2*>(a + (size_t)warp * C);
@@ -373,9 +378,9 @@ int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride,
   VS_REQUIRE(C == 192 || C == 256 || C == 768, "layernorm: C=%d unsupported (192, 256 or 768)", C);
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && b_stride % 2 == 0, "layernorm: bad planar outputs / partial stride");
   const int warps_per_block = 8, grid = (R + warps_per_block - 1) / warps_per_block;
-  if (C == 192) layernorm_rows_kernel<192><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
-  else if (C == 256) layernorm_rows_kernel<256><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
-  else layernorm_rows_kernel<768><<<grid, warps_per_block * 32, 0, st>>>(a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt);
+  if (C == 192) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<192>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
+  else if (C == 256) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<256>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
+  else VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<768>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -398,6 +403,8 @@ constexpr int AT_SLD = 68;   // row pitch of the score tile (16 B aligned)
 __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const float* __restrict__ qkv,
                                                             const float* __restrict__ ek,
                                                             const float* __restrict__ ev, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                          // [64][100]
   float* Ks = Qs + AT_BQ * AT_LD;          // [64][100]
@@ -570,7 +577,7 @@ static size_t attention_smem_bytes() {
 }
 
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
-                  Workspace* ws, __half* out_hi, __half* out_lo, bool* wrote_planar) {
+                  Workspace* ws, __half* out_hi, __half* out_lo, bool* wrote_planar, bool gaps_dont_care) {
   if (wrote_planar) *wrote_planar = false;
   // option "attention_mma": 1 = auto (from 128 rows per utterance up: tcgen05 when the caller gave a workspace, else mma.sync),
   // 0 = CUDA cores, 2 / 3 = always mma.sync (3xTF32 / plain TF32), 4 = always tcgen05
@@ -585,11 +592,11 @@ int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const f
   const size_t smem = attention_smem_bytes();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_kernel), (int)smem));
   // gap rows of `out` must be zero: the caller feeds out into a k=1 conv whose epilogue masks, but keep it clean
-  VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));
+  if (!gaps_dont_care) VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));
   // grid.x covers the longest utterance; CTAs beyond an utterance's length exit immediately
   VS_REQUIRE(rows.max_len > 0 && rows.max_len <= rows.n_rows, "rel_attention: bad max_len %d", rows.max_len);
   dim3 grid((rows.max_len + AT_BQ - 1) / AT_BQ, kHeads, rows.n_utt);
-  rel_attention_kernel<<<grid, 256, smem, st>>>(rows, qkv, ek, ev, out);
+  VS_CUDA_CHECK(launch_pdl<16>(rel_attention_kernel, dim3(grid), dim3(256), smem, st, rows, qkv, ek, ev, out));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -600,6 +607,8 @@ int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const f
 __global__ void row_dot_kernel(const float* __restrict__ x, int ld, const float* __restrict__ w,
                                const float* __restrict__ bias, float* __restrict__ out, int R, int C,
                                const int32_t* __restrict__ row_utt) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= R) return;
   float s = 0.f;
@@ -613,7 +622,7 @@ __global__ void row_dot_kernel(const float* __restrict__ x, int ld, const float*
 
 int row_dot(const float* x, int ld, const float* w, const float* bias, float* out, int R, int C,
             const int32_t* row_utt, cudaStream_t st) {
-  row_dot_kernel<<<(R + 7) / 8, 256, 0, st>>>(x, ld, w, bias, out, R, C, row_utt);
+  VS_CUDA_CHECK(launch_pdl<16>(row_dot_kernel, dim3((R + 7) / 8), dim3(256), 0, st, x, ld, w, bias, out, R, C, row_utt));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

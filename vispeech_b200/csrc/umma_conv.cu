@@ -66,6 +66,7 @@ constexpr int F_RES = 1, F_RES2 = 2, F_UBIAS = 4, F_RAW = 8, F_ACT = 16, F_SCALE
 template <int F>
 __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaConv& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
 
   const int n_units_per_tile = p.NB;
   const int stages_per_unit = c.taps * p.n_kc;
@@ -497,7 +499,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
 #define VS_UMMA_CASE(FL)                                                                                              \
   case FL: {                                                                                                          \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_conv1d_kernel<FL>), 227 * 1024));                   \
-    umma_conv1d_kernel<FL><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);                                            \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_conv1d_kernel<FL>, dim3(grid), dim3(kThreads), prm.p.smem_bytes, st, prm));                                            \
     break;                                                                                                            \
   }
   switch (flags) {
@@ -527,7 +529,7 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
     VS_UMMA_CASE(F_RAW | F_UP | F_LO)
     default: {
       VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_conv1d_kernel<-1>), 227 * 1024));
-      umma_conv1d_kernel<-1><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+      VS_CUDA_CHECK(launch_pdl<4>(umma_conv1d_kernel<-1>, dim3(grid), dim3(kThreads), prm.p.smem_bytes, st, prm));
     }
   }
 #undef VS_UMMA_CASE

@@ -80,6 +80,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaCoupling& c = prm.c;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t smem_base = smem_u32(smem);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem = *tmem_slot;
   const int R = c.R;
 
@@ -331,7 +333,7 @@ int umma_coupling(const UmmaCoupling& c, cudaStream_t st) {
   VS_TRY(device_sm_count(&n_sm));
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_coupling_kernel), (int)SMEM_BYTES));
   const int grid = prm.n_tiles < n_sm ? prm.n_tiles : n_sm;
-  umma_coupling_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(prm);
+  VS_CUDA_CHECK(launch_pdl<8>(umma_coupling_kernel, dim3(grid), dim3(kThreads), SMEM_BYTES, st, prm));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -122,6 +122,7 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint32_t a_lo, uint
 template <int F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pair_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaConv& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -162,6 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
   __syncthreads();
   cluster_sync_all();                 // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const int R = c.R, taps = c.taps, dil = c.dil;
 
@@ -457,7 +459,7 @@ int umma_pair_conv(const UmmaConv& c, cudaStream_t st) {
 #define VS_PAIR_CASE(FL)                                                                                  \
   case FL: {                                                                                              \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<FL>), 227 * 1024));         \
-    umma_pair_kernel<FL><<<2 * n_pairs, kThreads, prm.p.smem_bytes, st>>>(prm);                           \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<FL>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));                           \
     break;                                                                                                \
   }
   switch (flags) {
@@ -468,7 +470,7 @@ int umma_pair_conv(const UmmaConv& c, cudaStream_t st) {
     VS_PAIR_CASE(F_RES | F_RESINV | F_RES2 | F_ACT | F_SCALE)
     default: {
       VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1>), 227 * 1024));
-      umma_pair_kernel<-1><<<2 * n_pairs, kThreads, prm.p.smem_bytes, st>>>(prm);
+      VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<-1>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));
     }
   }
 #undef VS_PAIR_CASE

@@ -121,6 +121,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 template <int C, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pairfused_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaPair& c = prm.c;
   const Plan& p = prm.p;
   constexpr int N = C, NK = C / 16;                       // K = 16 steps per tap over all channels
@@ -170,6 +171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_acc1 = tmem_base, tm_acc2 = tmem_base + 256u;
   const int R = c.R, taps = c.taps, dil = c.dil;
@@ -504,7 +506,7 @@ int launch(const Params& prm, int grid, cudaStream_t st) {
 #define VS_PF_CASE(MD)                                                                                         \
   case MD: {                                                                                                   \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pairfused_kernel<C, MD>), 227 * 1024));      \
-    umma_pairfused_kernel<C, MD><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);                               \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_pairfused_kernel<C, MD>, dim3(grid), dim3(kThreads), prm.p.smem_bytes, st, prm));                               \
     break;                                                                                                     \
   }
   switch (mode) {
@@ -514,7 +516,7 @@ int launch(const Params& prm, int grid, cudaStream_t st) {
     VS_PF_CASE(M_ACT_RES2_SCALE)
     default:
       VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pairfused_kernel<C, M_GENERIC>), 227 * 1024));
-      umma_pairfused_kernel<C, M_GENERIC><<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+      VS_CUDA_CHECK(launch_pdl<4>(umma_pairfused_kernel<C, M_GENERIC>, dim3(grid), dim3(kThreads), prm.p.smem_bytes, st, prm));
   }
 #undef VS_PF_CASE
   VS_LAUNCH_CHECK();

@@ -82,6 +82,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 
 __global__ void __launch_bounds__(kThreads, 1) umma_resblock_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaResBlock& c = prm.c;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const uint32_t smem_base = smem_u32(smem);
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_resblock_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_x = tmem_base, tm_ring = tmem_base + kC * kS;
   const int R = c.R;
@@ -342,7 +344,7 @@ int umma_resblock(const UmmaResBlock& c, cudaStream_t st) {
   VS_TRY(device_sm_count(&n_sm));
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_resblock_kernel), (int)kSmemBytes));
   const int grid = prm.n_super < n_sm ? prm.n_super : n_sm;
-  umma_resblock_kernel<<<grid, kThreads, kSmemBytes, st>>>(prm);
+  VS_CUDA_CHECK(launch_pdl<4>(umma_resblock_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, prm));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -80,6 +80,7 @@ template <int N, int MODE, bool TIGHT = false>
 __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
   constexpr int EW = N / 8, kThreads = threads_for(N);
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaPair& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                              // the prologue above overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;     // columns [0, 2N): acc1 ring, [2N, 4N): acc2 ring
   const uint32_t SX = (uint32_t)p.SX;
 
@@ -481,12 +483,12 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
 #define VS_PAIR_CASE(NN, MM)                                                                                          \
   if (c.C == NN && mode == MM && !(NN == 64 && prm.p.tight)) {                                                        \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<NN, MM>), 227 * 1024));              \
-    umma_respair_kernel<NN, MM><<<grid, threads_for(NN), prm.p.smem_bytes, st>>>(prm);                                \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_respair_kernel<NN, MM>, dim3(grid), dim3(threads_for(NN)), prm.p.smem_bytes, st, prm));                                \
   }
 #define VS_PAIR_TIGHT(MM)                                                                                             \
   if (c.C == 64 && mode == MM && prm.p.tight) {                                                                       \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<64, MM, true>), 227 * 1024));        \
-    umma_respair_kernel<64, MM, true><<<grid, threads_for(64), prm.p.smem_bytes, st>>>(prm);                          \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_respair_kernel<64, MM, true>, dim3(grid), dim3(threads_for(64)), prm.p.smem_bytes, st, prm));                          \
   }
   VS_PAIR_CASE(32, M_ACT) else VS_PAIR_CASE(32, M_RAW) else VS_PAIR_CASE(32, M_RAW_RES2) else VS_PAIR_CASE(32, M_ACT_RES2_SCALE)
   else VS_PAIR_CASE(32, M_GENERIC) else VS_PAIR_CASE(64, M_ACT) else VS_PAIR_CASE(64, M_RAW) else VS_PAIR_CASE(64, M_RAW_RES2)

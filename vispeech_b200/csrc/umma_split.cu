@@ -38,6 +38,7 @@ struct Params {
 
 __global__ void __launch_bounds__(kThreads, 1) umma_split_kernel(const __grid_constant__ Params prm) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const UmmaSplit& c = prm.c;
   const Plan& p = prm.p;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_split_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();            // everything above (barriers, TMEM, the bias = a weight) overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const int slabs_per_nb = c.taps * p.n_kc;
   // unit u -> (row tile, n-block group, K-slice); consecutive units are consecutive tiles
@@ -246,6 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_split_kernel(const __grid_co
 // (K-slice partials), zeros on invalid rows.  One thread per (plane, row): 16-byte stores, coalesced over rows.
 __global__ void rows_to_split_kernel(const float* __restrict__ x, int ld, int64_t x_stride, int n_sum, const int32_t* __restrict__ row_utt,
                                      __half* __restrict__ hi, __half* __restrict__ lo, int R, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (C / 8) * R) return;
   const int pl = i / R, r = i % R;
@@ -329,7 +333,7 @@ int umma_split(const UmmaSplit& c, cudaStream_t st) {
   VS_TRY(device_sm_count(&n_sm));
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_split_kernel), 227 * 1024));
   const int grid = prm.p.n_units < n_sm ? prm.p.n_units : n_sm;
-  umma_split_kernel<<<grid, kThreads, prm.p.smem_bytes, st>>>(prm);
+  VS_CUDA_CHECK(launch_pdl(umma_split_kernel, dim3(grid), dim3(kThreads), prm.p.smem_bytes, st, prm));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
@@ -354,7 +358,7 @@ int sum_partials(const float* x, int64_t stride, int n, float* out, int64_t tota
 int rows_to_split(const float* x, int ld, int64_t x_stride, int n_sum, const int32_t* row_utt, __half* hi, __half* lo, int R, int C,
                   cudaStream_t st) {
   VS_REQUIRE(x && hi && lo && R > 0 && C % 8 == 0 && ld % 4 == 0 && n_sum >= 1, "rows_to_split: bad arguments");
-  rows_to_split_kernel<<<((C / 8) * R + 255) / 256, 256, 0, st>>>(x, ld, x_stride, n_sum, row_utt, hi, lo, R, C);
+  VS_CUDA_CHECK(launch_pdl(rows_to_split_kernel, dim3(((C / 8) * R + 255) / 256), dim3(256), 0, st, x, ld, x_stride, n_sum, row_utt, hi, lo, R, C));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
