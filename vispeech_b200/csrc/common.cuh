@@ -108,6 +108,11 @@ int row_dot(const float* x, int ld, const float* w, const float* bias, float* ou
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled(int group);
+struct PdlExtra {                 // for the lifetime of the object (this thread): also launch these groups' kernels that way
+  explicit PdlExtra(int groups);
+  ~PdlExtra();
+  int saved;
+};
 template <int GROUP = 1, typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

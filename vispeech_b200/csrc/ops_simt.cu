@@ -55,7 +55,10 @@ OptionScope::OptionScope(const Options* overrides) {
 }
 OptionScope::~OptionScope() { --tl_scope_depth; }
 
-bool pdl_enabled(int group) { return (opts().v[OPT_PDL] & group) != 0; }
+thread_local int tl_pdl_extra = 0;
+bool pdl_enabled(int group) { return ((opts().v[OPT_PDL] | tl_pdl_extra) & group) != 0; }
+PdlExtra::PdlExtra(int groups) : saved(tl_pdl_extra) { tl_pdl_extra |= groups; }
+PdlExtra::~PdlExtra() { tl_pdl_extra = saved; }
 
 int option_set(Options* o, const char* name, int64_t value) {
   VS_REQUIRE(name, "option: null name");
@@ -129,6 +132,8 @@ __device__ __forceinline__ void cv_cp_async16(void* dst, const void* src, bool v
 template <bool CLUSTER>
 __global__ void __launch_bounds__(256) conv1d_f32_kernel(ConvF32 a, int nchunk) {
   __shared__ __align__(16) float ring[CV_ST * (CV_BM * CV_ALD + CV_BK * CV_BN)];   // 36 KB; reused for the cluster reduce
+  pdl_trigger();
+  pdl_wait();
   float* const As = ring;                                  // [stage][row][CV_ALD]  (row-major: k contiguous)
   float* const Bs = ring + CV_ST * CV_BM * CV_ALD;         // [stage][k][CV_BN]
   const int tid = threadIdx.x;
@@ -287,15 +292,17 @@ int conv1d_f32(const ConvF32& a, cudaStream_t st) {
   int nchunk = 1;
   while (nchunk < 8 && n_it / (nchunk * 2) >= 4) nchunk *= 2;
   if (nchunk == 1 || tiles * nchunk > 296) {
-    conv1d_f32_kernel<false><<<grid, 256, 0, st>>>(a, nchunk);
+    VS_CUDA_CHECK(launch_pdl(conv1d_f32_kernel<false>, grid, dim3(256), 0, st, a, nchunk));
   } else {
     grid.z = nchunk;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = nchunk;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled(1) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     VS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv1d_f32_kernel<true>, a, nchunk));
   }
   VS_LAUNCH_CHECK();
