@@ -95,6 +95,9 @@ int64_t vs_launch_count(void);
  * overlap its predecessor's tail; every such kernel executes griddepcontrol.wait before it touches global memory): 1 = three-term conv,
  * LayerNorm, rows_to_split; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention, row_dot; 2 = frame-level
  * attention kernels; 4 = decoder; 8 = flow.  Default 33 (the groups that measured faster), 0 = every launch fully serialised (A/B).
+ * "coupling_min_rows": frame rows from which the flow takes the one-kernel coupling layer (default 4096 = tf32_min_rows: smaller calls
+ * keep their fp32-accurate kernels); 1 = always (a latency knob: 76 -> 4 launches per flow pass, C1 3.66 -> 3.18 ms per call, z within
+ * 5e-4 of the fp32 path instead of 1e-5).
  * "coupling_fused": 1 (default) = in the plain-TF32 regime (>= tf32_min_rows frame rows) every coupling layer of the flow is ONE kernel
  * (pre, the 4-layer WN stack, post and the x1 update; residual stream and skip sum in fp32 in TMEM, fp16 operands; csrc/umma_coupling.cu),
  * 0 = pre / per-layer WN kernels / post / update as separate launches (A/B).

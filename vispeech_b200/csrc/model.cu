@@ -560,7 +560,7 @@ static int flow_run(const VsModel* m, const VsRows* rows, float* z, bool reverse
     const FlowW& w = m->flows[f];
     const bool flipped = (f & 1) != 0;
     const int in_off = flipped ? H / 2 : 0, upd_off = flipped ? 0 : H / 2;
-    if (w.c16_w && opts().v[OPT_COUPLING_FUSED] && R >= opts().v[OPT_TF32_MIN_ROWS]) {
+    if (w.c16_w && opts().v[OPT_COUPLING_FUSED] && R >= opts().v[OPT_COUPLING_MIN_ROWS] && (R >= opts().v[OPT_TF32_MIN_ROWS] || opts().v[OPT_COUPLING_MIN_ROWS] < 4096)) {
       // the plain-TF32 regime (frame level, >= tf32_min_rows rows): the whole coupling layer as ONE kernel, residual stream and
       // skip sum in fp32 in TMEM, fp16 operands (the same 11-bit significand as TF32)  modules.py:324-343, 148-176
       UmmaCoupling u;
