@@ -134,3 +134,58 @@ def test_dft_basis_reproduces_torch_stft():
     out = sum(rows[t: t + n_frames] @ w[t].double() for t in range(4))                       # [frames, 2 * half]
     re, im = out[:, :1025].t(), out[:, half:half + 1025].t()
     assert float((re - ref.real).abs().max()) <= 1e-4 and float((im - ref.imag).abs().max()) <= 1e-4
+
+
+def test_coupling_pack_reproduces_oracle_coupling_layer(state_dict):
+    """Host logic of the one-kernel coupling layer (packing.pack_coupling / pack_coupling_bias; csrc/umma_coupling.cu): a numpy
+    statement of exactly what the kernel computes from the packed slab stream and bias table - post folded into the skip half of
+    res_skip, cumulative h biases, gate96 column order, the Flip folded into the odd layers - must reproduce the oracle's coupling
+    layers (modules.py:324-343 + WN 148-176) on a random input, for a flipped and an unflipped layer, up to the fp16 rounding of
+    the weights."""
+    import torch.nn.functional as F
+    from oracle.vispeech_oracle import DEFAULT_CONFIG as cfg, wn
+    from vispeech_b200.packing import COUPLING_SLAB, pack_state_dict
+    packed = pack_state_dict(state_dict)
+    g = torch.Generator().manual_seed(3)
+    T, sid = 50, 17
+    gvec = state_dict["emb_g.weight"][sid].reshape(1, -1, 1)
+    for f in (0, 1):
+        blob = packed["c16.flow.%d.w" % f].float().reshape(92, COUPLING_SLAB)
+        bias = packed["c16.flow.%d.b" % f]
+        def slab(i, k):                                                     # -> [K][96]
+            return blob[i][: (k // 8) * 96 * 8].reshape(k // 8, 96, 8).permute(0, 2, 1).reshape(k, 96).double()
+        hb, mb = bias[: 4 * 192].reshape(4, 192).double(), bias[768:864].double()
+        cg = bias[864:].reshape(-1, 4, 384)[sid].double()
+        z = torch.randn(T, 192, generator=g).double()                        # PHYSICAL layout (the flips are folded into the weights)
+        flipped = f % 2 == 1
+        x0 = z[:, 96:] if flipped else z[:, :96]
+        # ---- what the kernel computes
+        h = x0 @ torch.cat([slab(0, 96), slab(1, 96)], 1)                    # pre (bias in hb[0])
+        m = torch.zeros(T, 96, dtype=torch.float64)
+        s = 2
+        for l in range(4):
+            hin = F.pad((h + hb[l]).t()[None], (2, 2))[0].t()                # [T + 4][192], zero padding
+            acts = torch.zeros(T, 192, dtype=torch.float64)
+            for nb in range(4):
+                a = sum(hin[t:t + T] @ slab(s + t, 192) for t in range(5)) + cg[l, 96 * nb: 96 * nb + 96]
+                acts[:, 48 * nb: 48 * nb + 48] = torch.tanh(a[:, :48]) * torch.sigmoid(a[:, 48:])
+                s += 5
+            if l < 3:
+                h = h + acts @ torch.cat([slab(s, 192), slab(s + 1, 192)], 1)
+                s += 2
+            m = m + acts @ slab(s, 192)
+            s += 1
+        assert s == 92
+        m = m + mb
+        # ---- the oracle on the logical (flipped) tensor
+        src = "flow.flows.%d" % (2 * f)
+        x = torch.flip(z, [1]) if flipped else z
+        xl = x.t()[None].float()
+        hh = F.conv1d(xl[:, :96], state_dict[src + ".pre.weight"], state_dict[src + ".pre.bias"])
+        hh = wn(state_dict, src + ".enc", hh, gvec, cfg)
+        m_ref = F.conv1d(hh, state_dict[src + ".post.weight"], state_dict[src + ".post.bias"])[0].t().double()   # logical channel order
+        if flipped:
+            m_ref = torch.flip(m_ref, [1])                                  # m_phys[p] = m[95 - p]
+        scale = float(m_ref.abs().max())
+        err = float((m - m_ref).abs().max())
+        assert err <= 5e-3 * max(scale, 1.0), (f, err, scale)
