@@ -43,7 +43,7 @@ constexpr uint32_t kOffBar = kOffW + kWSlots * kWSlotBytes;
 constexpr int kNumBars = 2 * kWSlots + kRing + 4 * kS;
 constexpr uint32_t kSmemBytes = kOffBar + 8 * kNumBars + 16;
 static_assert(kSmemBytes <= 227 * 1024, "umma_resblock: shared memory");
-static_assert(kRing >= 2 && kThreads <= 1024, "umma_resblock: ring / crew size");
+static_assert(kRing == kS && kThreads <= 1024, "umma_resblock: one c1 accumulator per tile (the issuer relies on it)");
 
 struct Params {
   UmmaResBlock c;
@@ -163,9 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_resblock_kernel(const __grid
           mbar_wait(a_ready(0), pg, 82);
           for (int t = 0; t < kS; ++t) {
             const uint32_t ring_i = gen * kS + (uint32_t)t;
-            const uint32_t slot = ring_i % kRing, rp = (ring_i / kRing) & 1u;
+            const uint32_t slot = ring_i % kRing;
             if (t + 1 < kS) mbar_wait(a_ready(t + 1), pg, 83);
-            mbar_wait(acc1_empty(slot), rp ^ 1u, 85);
+            // no wait on acc1_empty: with kRing == kS the slot of tile t is always slot t, and a_ready(t) of this iteration is arrived
+            // by crew t AFTER its epilogue 1 of the previous iteration read that slot - one barrier round trip less per tile
+            // (a satisfied wait costs the issuer ~250 clk next to a busy pipe, a k = 3 conv of one tile is 12 MMAs = ~600)
             tc_fence_after();
             issue_tile_acc<kC / 16>(tm_ring + slot * kC, a1_lo_fixed + ((a_base + (uint32_t)(kPadA + t * kTileM - dil) * 16u) >> 4), a1_hi,
                                     w_lo, b_hi, idesc, kTaps, (uint32_t)dil, a1_kstep, b_kstep, 0u);
