@@ -136,6 +136,20 @@ def test_pair_fused_resblock_iteration_matches_cpu(G, R, C, k, dil):
         _lib.check(lib.vs_set_option(b"pair_fused", 1))
 
 
+@pytest.mark.parametrize("R,C,k,dil", [(600, 64, 3, 5), (5000, 64, 7, 5), (5000, 64, 11, 5), (118 * 9 + 5, 64, 11, 1), (40000, 64, 11, 3), (777, 64, 7, 1)])
+def test_tap_paired_resblock_iteration_matches_cpu(G, R, C, k, dil):
+    """The same fused iteration with the conv taps issued in pairs as N = 128 MMAs (option tap_pairs; csrc/umma_respair.cu): the odd
+    taps' half of the accumulator is re-aligned in the epilogue (lane shuffle + exchange between lane quarters) - covers both convs
+    paired (k = 3, 7; k = 11 at d = 1, 3) and conv2 only (k = 11, d = 5: no room for conv1's exchange buffer)."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.vs_set_option(b"tap_pairs", 1))
+    try:
+        _check_respair(G, R, C, k, dil)
+    finally:
+        _lib.check(lib.vs_set_option(b"tap_pairs", 0))
+
+
 def _check_respair(G, R, C, k, dil):
     """y = c2(lrelu(c1(lrelu(x)))) + x (modules.py:211-220) in one kernel.  The kernel takes a = lrelu(x) and recovers
     the residual as min(a, a/slope); compared with an fp64 chain using the same fp16 roundings (a, the intermediate),

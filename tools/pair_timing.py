@@ -9,6 +9,8 @@ from vispeech_b200._lib import check, ptr
 lib = _lib.load(); dev = "cuda:0"; st = torch.cuda.current_stream().cuda_stream
 FRAMES = 28800
 buf = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
+if os.environ.get("VS_TAP_PAIRS"):
+    check(lib.vs_set_option(b"tap_pairs", int(os.environ["VS_TAP_PAIRS"])))
 
 
 def run(name, R, C, taps, dil, res):

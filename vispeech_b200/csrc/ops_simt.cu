@@ -30,8 +30,8 @@ std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device
 
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
-                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "coupling_min_rows"};
-Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33, 4096}};
+                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "coupling_min_rows", "tap_pairs"};
+Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33, 4096, 0}};
 thread_local Options tl_opts;
 thread_local int tl_scope_depth = 0;
 }  // namespace
@@ -68,7 +68,7 @@ int option_set(Options* o, const char* name, int64_t value) {
   VS_REQUIRE(idx >= 0, "unknown option '%s'", name);
   switch (idx) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: case OPT_COUPLING_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
-    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: value = value != 0; break;
+    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: case OPT_TAP_PAIRS: value = value != 0; break;
     case OPT_PDL: VS_REQUIRE(value >= 0 && value <= 63, "option pdl is a bit mask 0..63"); break;
     case OPT_PAIR_FUSED: VS_REQUIRE(value >= 0 && value <= 2, "option pair_fused must be 0, 1 (C = 128) or 2 (also C = 64)"); break;
     case OPT_PAIR_CONV: VS_REQUIRE(value >= 0 && value <= 2, "option pair_conv must be 0 (off), 1 (C = 128) or 2 (also C = 256, k = 3)"); break;

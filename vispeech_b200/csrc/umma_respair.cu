@@ -46,8 +46,9 @@ constexpr int kMaxSX = 4;         // input ring depth (>= 3 keeps load(i+2), con
 struct Plan {
   int L, h1, h2, planes, rows_x, rows_a2, n_tiles, tmem_cols, ctas_per_sm, row_div_shift, SX;
   int tight;              // 1: two buffers shared by input rows and intermediate, residual re-read from L2 (C = 64, k = 11)
+  int pm;                 // tap pairing (C = 64): bit 0 conv1, bit 1 conv2 run as N = 128 MMAs over PAIRS of taps (see the kernel)
   uint32_t xa_bytes, a2_bytes, w_bytes, smem_bytes;
-  uint32_t off_a2, off_w1, off_w2, off_bar;
+  uint32_t off_a2, off_w1, off_w2, off_bar, off_xch;
 };
 struct Params {
   UmmaPair c;
@@ -76,9 +77,59 @@ struct Params {
 // a whole conv of tensor time to hide behind.  Measured per pair at the C2 size: 1.23 ms (~1040 TFLOP/s) against 1.30-1.45
 // for the two unfused kernels; a first form with ONE buffer of each kind ran at 1.27, a second MMA-issuing warp for conv2
 // at 1.31 (no gain: at N = 64 the 48-clk operand fetch, not the issue loop, is what the tensor pipe waits for).
-template <int N, int MODE, bool TIGHT = false>
+// out[j] += odd[j + d] for the paired form: vo holds this thread's row of the odd half; the value of row j + d comes from lane + d of
+// the same warp, or - for the last d lanes - from the first d lanes of the next lane quarter's warp (same column chunk) through `xch`
+// (f16 [quarter][chunk][d rows][32]); the last quarter's last d rows have no neighbour (those rows are outside the tile's valid range).
+// Two named barriers per call: all `nthreads` threads of this epilogue stage pass them once per tile.
+__device__ __forceinline__ void add_shifted_odd(uint32_t (&v)[32], const uint32_t (&vo)[32], int d, int q, int cc, int lane, uint32_t xch,
+                                                int bar_id, int nthreads) {
+  const uint32_t my = xch + (uint32_t)((q * 2 + cc) * d) * 64u, next = xch + (uint32_t)(((q + 1) * 2 + cc) * d) * 64u;
+  if (lane < d) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my + (uint32_t)lane * 64u + (uint32_t)i * 2u),
+                   "r"(pack_f16x2(__uint_as_float(vo[i]), __uint_as_float(vo[i + 1]))), "r"(pack_f16x2(__uint_as_float(vo[i + 2]), __uint_as_float(vo[i + 3]))),
+                   "r"(pack_f16x2(__uint_as_float(vo[i + 4]), __uint_as_float(vo[i + 5]))), "r"(pack_f16x2(__uint_as_float(vo[i + 6]), __uint_as_float(vo[i + 7])))
+                   : "memory");
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  const bool from_next = lane >= 32 - d;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    uint32_t ww[4] = {0u, 0u, 0u, 0u};
+    if (from_next && q < 3)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ww[0]), "=r"(ww[1]), "=r"(ww[2]), "=r"(ww[3])
+                   : "r"(next + (uint32_t)(lane - (32 - d)) * 64u + (uint32_t)i * 2u));
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[h]));
+      const float s0 = __shfl_down_sync(0xffffffffu, __uint_as_float(vo[i + 2 * h]), d);
+      const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(vo[i + 2 * h + 1]), d);
+      v[i + 2 * h] = __float_as_uint(__uint_as_float(v[i + 2 * h]) + (from_next ? f.x : s0));
+      v[i + 2 * h + 1] = __float_as_uint(__uint_as_float(v[i + 2 * h + 1]) + (from_next ? f.y : s1));
+    }
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");    // nobody overwrites xch for the next tile before every read is done
+}
+
+// TAP PAIRING (PM != 0, C = 64): an SS-mode MMA re-reads its 4 KB A tile from shared memory for every K = 16 step, so at N = 64
+// it costs 51 clk for 32 clk of tensor time (tools/pair_microbench.cu).  Two taps t, t + 1 of a conv read the SAME A rows if the
+// second one's result is allowed to land one tap offset lower: D[i][0:64] += W_t a[i + t d] is tap t's share of out[i], and
+// D[i][64:128] += W_{t+1} a[i + t d] is tap t + 1's share of out[i - d].  So the taps are issued in pairs as ONE N = 128 MMA
+// (64 clk, tensor-bound) against [W_t | W_{t+1}], the A offset advances by 2 d per pair (the odd last tap runs alone at N = 64
+// into the even half), and the epilogue forms out[i] = D[i][0:64] + D[i + d][64:128]: a warp shuffle down by d lanes, plus, for
+// the last d rows of every 32-row lane quarter, an exchange with the next quarter's warp through a few hundred bytes of shared
+// memory (f16: it is half of a sum that is rounded to f16 right afterwards anyway).  The last d rows of the tile have no
+// neighbour: a tile yields d rows less (113 - 117 instead of 118 at k = 11).  MMA time per tile: -37 %.
+// MEASURED (tools/pair_timing.py, C2 size): k = 11 1.244 -> 1.205 ms, k = 7 0.875 -> 1.01, k = 3 0.52 -> 0.83: the second TMEM load, the two
+// named barriers and the exchange lengthen the chain conv1 -> epilogue 1 -> conv2 by more than the MMAs save (two tiles in flight per
+// CTA cannot hide it; TMEM and shared memory have no room for a third).  Option "tap_pairs" (default 0) keeps the form testable.
+template <int N, int MODE, bool TIGHT = false, int PM = 0>
 __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_kernel(const __grid_constant__ Params prm) {
+  static_assert(PM == 0 || N == 64, "tap pairing is for C = 64");
   constexpr int EW = N / 8, kThreads = threads_for(N);
+  constexpr uint32_t ACCW = PM ? 128u : (uint32_t)N;          // accumulator slot width; acc1 ring [0, 2 ACCW), acc2 ring [2 ACCW, 4 ACCW)
+  constexpr bool P1 = (PM & 1) != 0, P2 = (PM & 2) != 0;
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   const UmmaPair& c = prm.c;
@@ -139,10 +190,27 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, 2 * p.w_bytes);
-      bulk_g2s(w1, c.w1, p.w_bytes, w_full);
-      bulk_g2s(w2, c.w2, p.w_bytes, w_full);
+    if (lane == 0) mbar_arrive_expect_tx(w_full, 2 * p.w_bytes);
+    __syncwarp();
+    if (PM == 0) {
+      if (lane == 0) {
+        bulk_g2s(w1, c.w1, p.w_bytes, w_full);
+        bulk_g2s(w2, c.w2, p.w_bytes, w_full);
+      }
+    } else {
+      // a paired conv keeps its taps as [pair g][plane][128 columns = tap 2g | tap 2g + 1][8], then the odd last tap as [plane][64][8];
+      // the packed source is [tap][plane][64][8]: one 1 KB copy per (tap, plane)
+      const int per_conv = c.taps * p.planes, n_pairs2 = c.taps - 1;           // taps below n_pairs2 are paired
+      for (int i = lane; i < 2 * per_conv; i += 32) {
+        const int cv = i / per_conv, t = (i % per_conv) / p.planes, pl = i % p.planes;
+        const bool paired = cv == 0 ? P1 : P2;
+        const __half* src = (cv ? c.w2 : c.w1) + (size_t)(t * p.planes + pl) * N * 8;
+        uint32_t dst = cv ? w2 : w1;
+        if (!paired) dst += (uint32_t)(t * p.planes + pl) * (N * 16u);
+        else if (t < n_pairs2) dst += (uint32_t)(((t >> 1) * p.planes + pl) * 2 * N + (t & 1) * N) * 16u;
+        else dst += (uint32_t)(n_pairs2 / 2) * (uint32_t)p.planes * 2u * N * 16u + (uint32_t)pl * (N * 16u);
+        bulk_g2s(dst, src, N * 16u, w_full);
+      }
     }
     uint32_t slot = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -183,6 +251,25 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     const uint32_t w1_lo = b_lo_fixed + (w1 >> 4), w2_lo = b_lo_fixed + (w2 >> 4);
     const int taps = c.taps;
     const uint32_t dil = (uint32_t)c.dil;
+    // paired issue (see the kernel's head comment): (taps - 1) / 2 MMA groups of N = 128 over tap pairs, then the odd last tap at N = 64
+    const uint32_t idesc2 = make_idesc(2 * N);
+    const uint32_t b2_hi = (uint32_t)(make_desc(0, 2u * N * 16u, 128u) >> 32), b2_lo_fixed = (uint32_t)make_desc(0, 2u * N * 16u, 128u);
+    auto issue_pairs = [&](uint32_t d_tmem, uint32_t a_tile, uint32_t a_hi_, uint32_t w_addr, uint32_t step, uint32_t a_kstep_) {
+      const int np = (taps - 1) / 2;
+      uint32_t a_tap = a_tile, b = b2_lo_fixed + (w_addr >> 4), accumulate = 0;
+#pragma unroll 1
+      for (int g = 0; g < np; ++g, a_tap += 2u * step) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          tc_mma_f16_lohi(d_tmem, a_tap + (uint32_t)k * a_kstep_, a_hi_, b + (uint32_t)k * (4u * N), b2_hi, idesc2, accumulate);
+          accumulate = 1;
+        }
+        b += (uint32_t)p.planes * 2u * N;
+      }
+      uint32_t bs = b_lo_fixed + ((w_addr + (uint32_t)np * (uint32_t)p.planes * 2u * N * 16u) >> 4);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) tc_mma_f16_lohi(d_tmem, a_tap + (uint32_t)k * a_kstep_, a_hi_, bs + (uint32_t)k * b_kstep, b_hi, idesc, 1u);
+    };
     mbar_wait(w_full, 0, 22);
     tc_fence_after();
     auto conv2 = [&](uint32_t j, bool ready) {   // conv2 of this CTA's j-th tile: A2 rows o + t
@@ -192,8 +279,11 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
         VS_TIMED(tw2, mbar_wait(acc2_empty(b), ph ^ 1u, 25));
       }
       tc_fence_after();
-      issue_tile<NK>(tmem_base + (2u + b) * N, a2_lo_fixed + ((TIGHT ? xa + b * p.xa_bytes : a2 + b * p.a2_bytes) >> 4), a2_hi, w2_lo,
-                     b_hi, idesc, taps, 1u, a2_kstep, b_kstep);
+      if (P2)
+        issue_pairs(tmem_base + (2u + b) * ACCW, a2_lo_fixed + ((TIGHT ? xa + b * p.xa_bytes : a2 + b * p.a2_bytes) >> 4), a2_hi, w2, 1u, a2_kstep);
+      else
+        issue_tile<NK>(tmem_base + (2u + b) * ACCW, a2_lo_fixed + ((TIGHT ? xa + b * p.xa_bytes : a2 + b * p.a2_bytes) >> 4), a2_hi, w2_lo,
+                       b_hi, idesc, taps, 1u, a2_kstep, b_kstep);
       tc_commit(acc2_full(b));
       if (TIGHT) tc_commit(xa_empty(b));          // the buffer goes back to the producer (tile j + 2)
     };
@@ -204,8 +294,9 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
         VS_TIMED(tw0, mbar_wait(xa_full(b), ph, 23));
         VS_TIMED(tw0, mbar_wait(acc1_empty(b), ph ^ 1u, 26));
         tc_fence_after();
-        issue_tile<NK>(tmem_base + b * N, a1_lo_fixed + ((xa + b * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
-                       a1_kstep, b_kstep);
+        if (P1) issue_pairs(tmem_base + b * ACCW, a1_lo_fixed + ((xa + b * p.xa_bytes) >> 4), a1_hi, w1, dil, a1_kstep);
+        else issue_tile<NK>(tmem_base + b * ACCW, a1_lo_fixed + ((xa + b * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
+                            a1_kstep, b_kstep);
         tc_commit(acc1_full(b));
       };
       uint32_t n_mine = 0;
@@ -228,8 +319,9 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       if (!r0) VS_TIMED(tw0, mbar_wait(xa_full(slot), phase, 23));
       if (!r1) VS_TIMED(tw0, mbar_wait(acc1_empty(b), ph ^ 1u, 26));
       tc_fence_after();
-      issue_tile<NK>(tmem_base + b * N, a1_lo_fixed + ((xa + slot * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
-                     a1_kstep, b_kstep);     // conv1: XA rows j + t*d
+      if (P1) issue_pairs(tmem_base + b * ACCW, a1_lo_fixed + ((xa + slot * p.xa_bytes) >> 4), a1_hi, w1, dil, a1_kstep);
+      else issue_tile<NK>(tmem_base + b * ACCW, a1_lo_fixed + ((xa + slot * p.xa_bytes) >> 4), a1_hi, w1_lo, b_hi, idesc, taps, dil,
+                          a1_kstep, b_kstep);     // conv1: XA rows j + t*d
       tc_commit(acc1_full(b));
       tc_commit(xa_empty(slot));
       if (++slot == SX) { slot = 0; phase ^= 1; }
@@ -243,6 +335,7 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     const float slope = c.in_slope;
     const int j = q * 32 + lane;                        // A2 local row = conv1 output row
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+    const uint32_t xch1 = smem_base + p.off_xch;
     const uint32_t a2_lane = (TIGHT ? xa : a2) + (uint32_t)j * 16u + (uint32_t)(cc * 4 * p.rows_a2) * 16u;
     const uint32_t a2_plane = (uint32_t)p.rows_a2 * 16u;
     uint32_t i = 0;
@@ -255,7 +348,12 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
       VS_TIMED(tw0, mbar_wait(acc1_full(b), ph, 27));
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(t_lane + b * N, v);
+      tmem_ld32(t_lane + b * ACCW, v);
+      if (P1) {                                          // out1[j] = even[j] + odd[j + d]
+        uint32_t vo[32];
+        tmem_ld32(t_lane + b * ACCW + (uint32_t)N, vo);
+        add_shifted_odd(v, vo, c.dil, q, cc, lane, xch1, 1, EW * 32);
+      }
       const uint32_t a2_row = a2_lane + b * (TIGHT ? p.xa_bytes : p.a2_bytes);   // TIGHT: over the tile's own input rows
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
@@ -291,7 +389,8 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
     const float oslope = c.act_slope, oscale = c.act_scale;
     const __half2 inv2 = __float2half2_rn(1.f / c.in_slope);
     const int o = q * 32 + lane;                        // conv2 output position within the tile
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * N + (uint32_t)(cc * 32);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * ACCW + (uint32_t)(cc * 32);
+    const uint32_t xch2 = smem_base + p.off_xch + (P1 ? 8u * (uint32_t)c.dil * 64u : 0u);
     const uint32_t xa_lane = xa + (uint32_t)(p.h1 + p.h2 + o) * 16u + (uint32_t)(cc * 4 * p.rows_x) * 16u;
     const uint32_t xa_plane = (uint32_t)p.rows_x * 16u;
     const size_t plane_elems = (size_t)c.R * 8;         // elements between consecutive 8-channel planes in HBM
@@ -327,7 +426,12 @@ __global__ void __launch_bounds__(threads_for(N), N == 32 ? 2 : 1) umma_respair_
                        : "r"(xa_lane + slot * p.xa_bytes + (uint32_t)gq * xa_plane));
       }
       uint32_t v[32];
-      tmem_ld32(t_lane + b * N, v);
+      tmem_ld32(t_lane + b * ACCW, v);
+      if (P2) {                                          // out2[o] = even[o] + odd[o + 1]
+        uint32_t vo[32];
+        tmem_ld32(t_lane + b * ACCW + (uint32_t)N, vo);
+        add_shifted_odd(v, vo, 1, q, cc, lane, xch2, 2, EW * 32);
+      }
       auto chunk = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
 #pragma unroll
@@ -406,6 +510,7 @@ int make_plan(const UmmaPair& c, Plan* out) {
   VS_REQUIRE((1 << s) == c.row_div, "umma_respair: row_div=%d must be a power of two", c.row_div);
   p.row_div_shift = s;
   p.L = kTileM - 2 * p.h2;
+  p.pm = 0;
   p.rows_x = kTileM + 2 * p.h1;
   p.rows_a2 = kTileM + 2 * p.h2;
   p.xa_bytes = (uint32_t)p.planes * p.rows_x * 16u;
@@ -427,6 +532,20 @@ int make_plan(const UmmaPair& c, Plan* out) {
   p.off_bar = (p.off_w2 + p.w_bytes + 127u) & ~127u;
   p.smem_bytes = p.off_bar + bar_bytes;
   p.tmem_cols = 4 * c.C;                               // 128 or 256: a power of two >= 32
+  // tap pairing (C = 64, option "tap_pairs"): conv2 always when its 512-byte exchange buffer fits, conv1 too when its d x 512 bytes do
+  p.off_xch = (p.smem_bytes + 15u) & ~15u;
+  if (c.C == 64 && opts().v[OPT_TAP_PAIRS] && c.dil <= 5) {
+    const uint32_t cap = 227u * 1024;
+    const uint32_t x1 = 8u * (uint32_t)c.dil * 64u, x2 = 8u * 64u;
+    if (p.off_xch + x1 + x2 <= cap) p.pm = 3;
+    else if (p.off_xch + x2 <= cap) p.pm = 2;
+    if (p.pm) {
+      p.smem_bytes = p.off_xch + ((p.pm & 1) ? x1 : 0u) + x2;
+      p.tmem_cols = 512;
+      if (p.pm & 1) p.L -= c.dil;                      // the last d conv1 rows of a tile have no neighbour to take their odd half from
+      per_sm = 1;
+    }
+  }
   // never more CTAs on an SM than planned (TMEM: 512 columns)
   const uint32_t min_smem = (227u * 1024) / (uint32_t)(per_sm + 1) + 1024u;
   if (p.smem_bytes < min_smem) p.smem_bytes = min_smem;
@@ -481,20 +600,39 @@ int umma_respair(const UmmaPair& c, cudaStream_t st) {
   else if (c.out_raw && !c.out_act && c.res2) mode = M_RAW_RES2;
   else if (c.out_act && !c.out_raw && c.res2 && scale) mode = M_ACT_RES2_SCALE;
 #define VS_PAIR_CASE(NN, MM)                                                                                          \
-  if (c.C == NN && mode == MM && !(NN == 64 && prm.p.tight)) {                                                        \
+  if (c.C == NN && mode == MM && !(NN == 64 && (prm.p.tight || prm.p.pm))) {                                          \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<NN, MM>), 227 * 1024));              \
     VS_CUDA_CHECK(launch_pdl<4>(umma_respair_kernel<NN, MM>, dim3(grid), dim3(threads_for(NN)), prm.p.smem_bytes, st, prm));                                \
   }
 #define VS_PAIR_TIGHT(MM)                                                                                             \
-  if (c.C == 64 && mode == MM && prm.p.tight) {                                                                       \
+  if (c.C == 64 && mode == MM && prm.p.tight && !prm.p.pm) {                                                          \
     VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<64, MM, true>), 227 * 1024));        \
     VS_CUDA_CHECK(launch_pdl<4>(umma_respair_kernel<64, MM, true>, dim3(grid), dim3(threads_for(64)), prm.p.smem_bytes, st, prm));                          \
   }
+#define VS_PAIR_PM(MM, TT, PP)                                                                                        \
+  if (c.C == 64 && mode == MM && (prm.p.tight != 0) == TT && prm.p.pm == PP) {                                        \
+    VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_respair_kernel<64, MM, TT, PP>), 227 * 1024));      \
+    VS_CUDA_CHECK(launch_pdl<4>(umma_respair_kernel<64, MM, TT, PP>, dim3(grid), dim3(threads_for(64)), prm.p.smem_bytes, st, prm)); \
+  }
+  if (prm.p.pm) {
+    // tap-paired forms: the decoder's modes per branch (k = 7: act, raw + sum; k = 11: act, act + sum + scale; k = 3: act, raw) + generic
+    const bool decoder_mode = mode == M_ACT || mode == M_RAW || mode == M_RAW_RES2 || mode == M_ACT_RES2_SCALE;
+    if (!decoder_mode) mode = M_GENERIC;
+    VS_PAIR_PM(M_ACT, false, 3) else VS_PAIR_PM(M_RAW, false, 3) else VS_PAIR_PM(M_RAW_RES2, false, 3) else VS_PAIR_PM(M_ACT_RES2_SCALE, false, 3)
+    else VS_PAIR_PM(M_GENERIC, false, 3)
+    else VS_PAIR_PM(M_ACT, true, 3) else VS_PAIR_PM(M_RAW, true, 3) else VS_PAIR_PM(M_RAW_RES2, true, 3) else VS_PAIR_PM(M_ACT_RES2_SCALE, true, 3)
+    else VS_PAIR_PM(M_GENERIC, true, 3)
+    else VS_PAIR_PM(M_ACT, true, 2) else VS_PAIR_PM(M_RAW, true, 2) else VS_PAIR_PM(M_RAW_RES2, true, 2) else VS_PAIR_PM(M_ACT_RES2_SCALE, true, 2)
+    else VS_PAIR_PM(M_GENERIC, true, 2)
+    else VS_PAIR_PM(M_ACT, false, 2) else VS_PAIR_PM(M_GENERIC, false, 2)
+    else { set_error("umma_respair: no tap-paired instantiation for mode %d tight %d pm %d", mode, prm.p.tight, prm.p.pm); return VS_ERR_INVALID; }
+  } else
   VS_PAIR_CASE(32, M_ACT) else VS_PAIR_CASE(32, M_RAW) else VS_PAIR_CASE(32, M_RAW_RES2) else VS_PAIR_CASE(32, M_ACT_RES2_SCALE)
   else VS_PAIR_CASE(32, M_GENERIC) else VS_PAIR_CASE(64, M_ACT) else VS_PAIR_CASE(64, M_RAW) else VS_PAIR_CASE(64, M_RAW_RES2)
   else VS_PAIR_CASE(64, M_ACT_RES2_SCALE) else VS_PAIR_CASE(64, M_GENERIC)
   else VS_PAIR_TIGHT(M_ACT) else VS_PAIR_TIGHT(M_RAW) else VS_PAIR_TIGHT(M_RAW_RES2) else VS_PAIR_TIGHT(M_ACT_RES2_SCALE)
   else VS_PAIR_TIGHT(M_GENERIC)
+#undef VS_PAIR_PM
 #undef VS_PAIR_TIGHT
 #undef VS_PAIR_CASE
   VS_LAUNCH_CHECK();
