@@ -95,9 +95,9 @@ int64_t vs_launch_count(void);
  * overlap its predecessor's tail; every such kernel executes griddepcontrol.wait before it touches global memory): 1 = three-term conv,
  * LayerNorm, rows_to_split; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention, row_dot; 2 = frame-level
  * attention kernels; 4 = decoder; 8 = flow.  Default 33 (the groups that measured faster), 0 = every launch fully serialised (A/B).
- * "tap_pairs": 1 = the fused ResBlock iterations of the C = 64 stage issue their conv taps in PAIRS as N = 128 MMAs (half the shared-memory
- * operand traffic per tap; the epilogue re-aligns the odd taps' half by a lane shuffle + a small exchange between lane quarters).  Default 0:
- * measured slower except at k = 11 (csrc/umma_respair.cu).
+ * "tap_pairs": the fused ResBlock iterations of the C = 64 stage may issue their conv taps in PAIRS as N = 128 MMAs (half the shared-memory
+ * operand traffic per tap; the epilogue re-aligns the odd taps' half by a lane shuffle + a small exchange between lane quarters): 0 (default)
+ * = never (measured slower in the whole decoder), 1 = at k = 11 only, 2 = at every k (csrc/umma_respair.cu).
  * "coupling_min_rows": frame rows from which the flow takes the one-kernel coupling layer (default 4096 = tf32_min_rows: smaller calls
  * keep their fp32-accurate kernels); 1 = always (a latency knob: 76 -> 4 launches per flow pass, C1 3.66 -> 3.18 ms per call, z within
  * 5e-4 of the fp32 path instead of 1e-5).

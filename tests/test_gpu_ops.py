@@ -143,7 +143,7 @@ def test_tap_paired_resblock_iteration_matches_cpu(G, R, C, k, dil):
     paired (k = 3, 7; k = 11 at d = 1, 3) and conv2 only (k = 11, d = 5: no room for conv1's exchange buffer)."""
     from vispeech_b200 import _lib
     lib = _lib.load()
-    _lib.check(lib.vs_set_option(b"tap_pairs", 1))
+    _lib.check(lib.vs_set_option(b"tap_pairs", 2))
     try:
         _check_respair(G, R, C, k, dil)
     finally:

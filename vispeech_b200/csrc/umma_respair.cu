@@ -534,7 +534,7 @@ int make_plan(const UmmaPair& c, Plan* out) {
   p.tmem_cols = 4 * c.C;                               // 128 or 256: a power of two >= 32
   // tap pairing (C = 64, option "tap_pairs"): conv2 always when its 512-byte exchange buffer fits, conv1 too when its d x 512 bytes do
   p.off_xch = (p.smem_bytes + 15u) & ~15u;
-  if (c.C == 64 && opts().v[OPT_TAP_PAIRS] && c.dil <= 5) {
+  if (c.C == 64 && c.dil <= 5 && (opts().v[OPT_TAP_PAIRS] == 2 || (opts().v[OPT_TAP_PAIRS] == 1 && c.taps >= 11))) {   // 1: only where it measured faster
     const uint32_t cap = 227u * 1024;
     const uint32_t x1 = 8u * (uint32_t)c.dil * 64u, x2 = 8u * 64u;
     if (p.off_xch + x1 + x2 <= cap) p.pm = 3;
