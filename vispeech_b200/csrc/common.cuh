@@ -76,9 +76,10 @@ int layernorm_rows(const float* a, const float* b, const float* gamma, const flo
 struct Workspace;
 // `ws`: scratch for the tcgen05 kernel (attention_umma.cu, attention_umma_ws_floats(n_rows) floats); without it the
 // frame-level path falls back to the mma.sync kernel
-// LN(a + sum of n_b partials of b) with an optional second output: the row as planar fp16 hi / lo (umma_split.cu's operand)
+// LN(a + sum of n_b partials of b) with an optional second output: the row as planar fp16 hi / lo (umma_split.cu's operand);
+// a may be null; pre_relu: LN(relu(a + sum b)) (a conv whose ReLU has to wait for the sum of its K-slice partials)
 int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride, const float* gamma, const float* beta, float* out,
-                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st);
+                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st, int pre_relu = 0);
 // `out_hi` / `out_lo` (optional, with `wrote_planar`): where the tcgen05 path may write the result as planar fp16 hi / lo INSTEAD
 // of fp32 rows (the O conv's operand); *wrote_planar tells the caller which form it got
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,

@@ -81,7 +81,7 @@ struct VsModel {
   const float *ep_cond, *ep_w1, *ep_b1, *ep_g1, *ep_be1, *ep_w2, *ep_b2, *ep_g2, *ep_be2, *ep_wl, *ep_bl;
   const float *pitch_pre_w, *pitch_pre_b, *energy_pre_w, *energy_pre_b;
   const float *proj_w, *proj_b, *t_proj_w, *x_proj_w, *x_dp_w1, *x_ep_w1, *x_ep_w2;
-  const __half *s_proj_w, *s_dp_w1, *s_ep_w1;
+  const __half *s_proj_w, *s_dp_w1, *s_ep_w1, *s_ep_w2;
   std::vector<vs::FlowW> flows;
   vs::PosteriorW enc_q;
   vs::DecoderW dec;
@@ -172,7 +172,7 @@ static int finalize(VsModel* m) {
   FETCH_F32(m->x_dp_w1, "x3.dp.w1", 2 * 3 * H * 256);
   FETCH_F32(m->x_ep_w1, "x3.ep.w1", 2 * 3 * H * 768);     FETCH_F32(m->x_ep_w2, "x3.ep.w2", 2 * 3 * 768 * 768);
   FETCH_F16(m->s_proj_w, "s16.proj.w", 2 * H * 2 * H);    FETCH_F16(m->s_dp_w1, "s16.dp.w1", 2 * 3 * H * 256);
-  FETCH_F16(m->s_ep_w1, "s16.ep.w1", 2 * 3 * H * 768);
+  FETCH_F16(m->s_ep_w1, "s16.ep.w1", 2 * 3 * H * 768);    FETCH_F16(m->s_ep_w2, "s16.ep.w2", 2 * 3 * 768 * 768);
   const int L = m->cfg.flow_layers;
   m->flows.resize(m->cfg.n_flows);
   for (int f = 0; f < m->cfg.n_flows; ++f) {
@@ -357,7 +357,7 @@ int64_t vs_workspace_bytes_latent(const VsModel* m, int32_t rp, int32_t rf) {
   (void)m;
   const int64_t H = kHidden;
   const int64_t enc_p = encoder_ws_floats(rp), enc_f = encoder_ws_floats(rf);
-  const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8);
+  const int64_t variance = enc_p + (int64_t)rp * (H + 2 * 768 + 8 + 5 * 768);   // + the energy predictor's conv_2 operand and K-slice partials
   const int64_t prior = enc_f + (int64_t)rf * (2 * H + H);                   // stats + the projection's hi / lo operand copy
   const int64_t flow = (int64_t)rf * (H + 2 * H + H + 2 * H + H + 2 * H);   // also covers vs_posterior_encode
   int64_t mx = variance;
@@ -443,12 +443,28 @@ int vs_variance_adapter(const VsModel* m, const VsRows* rows, float* x, int32_t 
     VS_TRY(add_speaker_rows(x, m->ep_cond, *rows, t, H, st));
     c = ConvF32(); c.R = R; c.row_utt = rows->row_utt; c.k = 3; c.pad_l = 1; c.act = 1;
     c.in = t; c.in_ld = H; c.Cin = H; c.w = m->ep_w1; c.bias = m->ep_b1; c.out = h1; c.out_ld = 768; c.Cout = 768;
-    if (use_split16(R, false)) VS_TRY(conv_rows_split(c, m->s_ep_w1, W, st));
-    else VS_TRY(conv_rows(c, nullptr, m->x_ep_w1, st));
-    VS_TRY(layernorm_rows(h1, nullptr, m->ep_g1, m->ep_be1, h1, R, 768, rows->row_utt, st));
-    c.in = h1; c.in_ld = 768; c.Cin = 768; c.w = m->ep_w2; c.bias = m->ep_b2; c.out = h2;
-    VS_TRY(conv_rows(c, nullptr, m->x_ep_w2, st));
-    VS_TRY(layernorm_rows(h2, nullptr, m->ep_g2, m->ep_be2, h2, R, 768, rows->row_utt, st));
+    if (use_split16(R, false)) {
+      // both convs on the three-term fp16 conv: LayerNorm 1 writes conv_2's planar hi / lo operand, conv_2 (Cin = 768) runs as four
+      // K-slices with fp32 partials, and LayerNorm 2 sums them, applies the ReLU that had to wait for the sum, and normalises
+      VS_TRY(conv_rows_split(c, m->s_ep_w1, W, st));
+      Workspace W2 = W;
+      __half* e_hi = W2.take<__half>((int64_t)R * 768);
+      __half* e_lo = W2.take<__half>((int64_t)R * 768);
+      float* part = W2.take<float>((int64_t)4 * R * 768);
+      if (!W2.ok) { set_error("vs_variance_adapter: workspace too small"); return VS_ERR_WORKSPACE; }
+      VS_TRY(layernorm_rows_ex(h1, nullptr, 1, 0, m->ep_g1, m->ep_be1, h1, e_hi, e_lo, R, 768, rows->row_utt, st));
+      UmmaSplit u;
+      u.R = R; u.row_utt = rows->row_utt; u.taps = 3; u.pad_l = 1; u.in_hi = e_hi; u.in_lo = e_lo; u.Cin = 768; u.w = m->s_ep_w2;
+      u.bias = m->ep_b2; u.act = 0; u.out32 = part; u.out32_ld = 768; u.out32_slice = (int64_t)R * 768; u.N = 768; u.k_slices = 4;
+      VS_TRY(umma_split(u, st));
+      VS_TRY(layernorm_rows_ex(nullptr, part, 4, (int64_t)R * 768, m->ep_g2, m->ep_be2, h2, nullptr, nullptr, R, 768, rows->row_utt, st, 1));
+    } else {
+      VS_TRY(conv_rows(c, nullptr, m->x_ep_w1, st));
+      VS_TRY(layernorm_rows(h1, nullptr, m->ep_g1, m->ep_be1, h1, R, 768, rows->row_utt, st));
+      c.in = h1; c.in_ld = 768; c.Cin = 768; c.w = m->ep_w2; c.bias = m->ep_b2; c.out = h2;
+      VS_TRY(conv_rows(c, nullptr, m->x_ep_w2, st));
+      VS_TRY(layernorm_rows(h2, nullptr, m->ep_g2, m->ep_be2, h2, R, 768, rows->row_utt, st));
+    }
     VS_TRY(row_dot(h2, 768, m->ep_wl, m->ep_bl, s0, R, 768, rows->row_utt, st));
   }
   VS_TRY(energy_rows(s0, energy_ctrl, energy_mode, energy_scale, *rows, s1, energy_out, st));

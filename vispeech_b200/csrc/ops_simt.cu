@@ -319,13 +319,13 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, con
                                                              int n_b, int64_t b_stride,        // b = sum of n_b partials (K-slices of umma_split.cu)
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* out, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                             int R, const int32_t* __restrict__ row_utt) {
+                                                             int R, const int32_t* __restrict__ row_utt, int pre_relu) {   // pre_relu: LN(relu(a + sum b))
   constexpr int PER = C / 64;                          // float2 per lane: one warp owns a row
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= R) return;
-  const float2* a2 = reinterpret_cast<const float2*>(a + (size_t)warp * C);
+  const float2* a2 = a ? reinterpret_cast<const float2*>(a + (size_t)warp * C) : nullptr;     // a may be null (= 0)
   const float2* b2 = b ? reinterpret_cast<const float2*>(b + (size_t)warp * C) : nullptr;
   float2* o2 = reinterpret_cast<float2*>(out + (size_t)warp * C);
   // optional second output: the row as planar fp16 hi / lo [C/8][R][8] (the next conv's operand, umma_split.cu); the float2 with
@@ -344,13 +344,17 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, con
   }
   float2 v[PER];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) v[i] = a2[lane + 32 * i];
+  for (int i = 0; i < PER; ++i) v[i] = a2 ? a2[lane + 32 * i] : make_float2(0.f, 0.f);
   if (b2) {
     for (int s = 0; s < n_b; ++s) {                      // fixed order: deterministic
       const float2* bs = b2 + (size_t)s * (b_stride / 2);
 #pragma unroll
       for (int i = 0; i < PER; ++i) { const float2 w = bs[lane + 32 * i]; v[i].x += w.x; v[i].y += w.y; }
     }
+  }
+  if (pre_relu) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); }
   }
   float s = 0.f;
 #pragma unroll
@@ -382,13 +386,14 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* a, con
 }
 
 int layernorm_rows_ex(const float* a, const float* b, int n_b, int64_t b_stride, const float* gamma, const float* beta, float* out,
-                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st) {
+                      __half* out_hi, __half* out_lo, int R, int C, const int32_t* row_utt, cudaStream_t st, int pre_relu) {
   VS_REQUIRE(C == 192 || C == 256 || C == 768, "layernorm: C=%d unsupported (192, 256 or 768)", C);
+  VS_REQUIRE(a || b, "layernorm: no input");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && b_stride % 2 == 0, "layernorm: bad planar outputs / partial stride");
   const int warps_per_block = 8, grid = (R + warps_per_block - 1) / warps_per_block;
-  if (C == 192) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<192>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
-  else if (C == 256) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<256>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
-  else VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<768>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt));
+  if (C == 192) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<192>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt, pre_relu));
+  else if (C == 256) VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<256>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt, pre_relu));
+  else VS_CUDA_CHECK(launch_pdl(layernorm_rows_kernel<768>, dim3(grid), dim3(warps_per_block * 32), 0, st, a, b, n_b, b_stride, gamma, beta, out, out_hi, out_lo, R, row_utt, pre_relu));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }
