@@ -93,8 +93,10 @@ int64_t vs_launch_count(void);
  * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
  * "pdl": bit mask of the kernel groups launched with programmatic dependent launch (the next kernel's launch, CTA scheduling and prologue
  * overlap its predecessor's tail; every such kernel executes griddepcontrol.wait before it touches global memory): 1 = three-term conv,
- * LayerNorm, rows_to_split; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention, row_dot; 2 = frame-level
- * attention kernels; 4 = decoder; 8 = flow.  Default 33 (the groups that measured faster), 0 = every launch fully serialised (A/B).
+ * LayerNorm, rows_to_split, the fp32 cluster conv; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention,
+ * row_dot; 2 / 64 / 128 = the frame-level attention kernel / its tile re-layout / its band fix-up; 4 = decoder (always on for calls below
+ * 2048 frame rows); 8 = flow.  Default 33 (the groups that measured faster; 64 alone costs the frame prior 0.3 ms), 0 = every launch
+ * fully serialised (A/B).
  * "tap_pairs": the fused ResBlock iterations of the C = 64 stage may issue their conv taps in PAIRS as N = 128 MMAs (half the shared-memory
  * operand traffic per tap; the epilogue re-aligns the odd taps' half by a lane shuffle + a small exchange between lane quarters): 0 (default)
  * = never (measured slower in the whole decoder), 1 = at k = 11 only, 2 = at every k (csrc/umma_respair.cu).

@@ -616,7 +616,7 @@ int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, co
   float* m = ws.take<float>((int64_t)R * kHeads);
   float* l = ws.take<float>((int64_t)R * kHeads);
   if (!ws.ok) { set_error("rel_attention_umma: workspace too small"); return VS_ERR_WORKSPACE; }
-  VS_CUDA_CHECK(launch_pdl<2>(qkv_to_tiles_kernel, dim3(dim3((rows.max_len + TK - 1) / TK, rows.n_utt)), dim3(256), 0, st, rows, qkv, qt, kt, vt));
+  VS_CUDA_CHECK(launch_pdl<64>(qkv_to_tiles_kernel, dim3(dim3((rows.max_len + TK - 1) / TK, rows.n_utt)), dim3(256), 0, st, rows, qkv, qt, kt, vt));
   VS_LAUNCH_CHECK();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_umma_kernel), (int)kSmemBytes));
   Params prm;
@@ -626,7 +626,7 @@ int rel_attention_umma(const VsRows& rows, const float* qkv, const float* ek, co
   VS_CUDA_CHECK(launch_pdl<2>(attention_umma_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, prm));
   VS_LAUNCH_CHECK();
   VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_band_fixup_kernel), (int)sizeof(FxSmem)));
-  VS_CUDA_CHECK(launch_pdl<2>(rel_band_fixup_kernel, dim3(dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads)), dim3(256), sizeof(FxSmem), st, rows, qkv, ek, ev, o_main, m, l, out, out_hi, out_lo, R));
+  VS_CUDA_CHECK(launch_pdl<128>(rel_band_fixup_kernel, dim3(dim3((R + FX_ROWS - 1) / FX_ROWS, kHeads)), dim3(256), sizeof(FxSmem), st, rows, qkv, ek, ev, o_main, m, l, out, out_hi, out_lo, R));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -104,7 +104,8 @@ int row_dot(const float* x, int ld, const float* w, const float* bias, float* ou
 // Option "pdl" is a bit mask of kernel groups launched this way (0 = everything fully serialised): 1 the three-term conv, LayerNorm and
 // rows_to_split, 32 the small element-wise kernels of the latent stages (default 33: text encoder 0.54 -> 0.47 ms, variance adapter 0.99 ->
 // 0.88 at the C2 size, where ~100 kernels of 5 - 20 us on 20 - 90 CTAs run back to back), 16 the CUDA-core attention and row_dot (measured:
-// cancels that gain), 2 the frame-level attention kernels (frame prior 2.15 -> 2.4 ms), 4 the decoder, 8 the flow (both +-0).
+// cancels that gain), 2 / 64 / 128 the frame-level attention kernel, its tile re-layout and its band fix-up (64 alone: frame prior 2.19 ->
+// 2.49 ms; the other two +-0), 4 the decoder (+-0 at batch size, on for small calls), 8 the flow (+-0).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -70,7 +70,7 @@ int option_set(Options* o, const char* name, int64_t value) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: case OPT_COUPLING_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
     case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: value = value != 0; break;
     case OPT_TAP_PAIRS: VS_REQUIRE(value >= 0 && value <= 2, "option tap_pairs must be 0, 1 (k = 11 only) or 2 (every k)"); break;
-    case OPT_PDL: VS_REQUIRE(value >= 0 && value <= 63, "option pdl is a bit mask 0..63"); break;
+    case OPT_PDL: VS_REQUIRE(value >= 0 && value <= 255, "option pdl is a bit mask 0..255"); break;
     case OPT_PAIR_FUSED: VS_REQUIRE(value >= 0 && value <= 2, "option pair_fused must be 0, 1 (C = 128) or 2 (also C = 64)"); break;
     case OPT_PAIR_CONV: VS_REQUIRE(value >= 0 && value <= 2, "option pair_conv must be 0 (off), 1 (C = 128) or 2 (also C = 256, k = 3)"); break;
     case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 4, "option attention_mma must be 0..4"); break;
