@@ -178,10 +178,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
         VS_TIMED(tw_acts, mbar_wait(acts_ready, n_acts & 1u, 6));
         ++n_acts;
         tc_fence_after();
-        if (l < L - 1)                                                    // h += res (the residual add happens in the accumulator)
+        if (l < L - 1) {                                                  // h += res (the residual add happens in the accumulator)
           for (int s = 0; s < 2; ++s) slab_mmas(tmem + TM_H + (uint32_t)s * NBLK, aa_fixed + (act16 >> 4), aa_hi, aa_kstep, H / 16, 1u);
+          tc_commit(h_done);                                              // the crew turns h into the next operand while m is updated
+        }
         slab_mmas(tmem + TM_M, aa_fixed + (act16 >> 4), aa_hi, aa_kstep, H / 16, l ? 1u : 0u);     // m += acts (W_skip W_post)
-        tc_commit(h_done);
+        if (l == L - 1) tc_commit(h_done);
       }
     }
 #ifdef VS_UMMA_TIMING
@@ -200,20 +202,27 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
     const float* mb = c.bias + L * H;                                    // [96]
     const float* cg = c.bias + L * H + HALF;                             // [n_spk][L][384]
     uint32_t n_hdone = 0, n_acc[2] = {0, 0};
+    // this warp's 48 channels of x0 of a tile's row, fetched one tile ahead (the loads of tile n + 1 fly during tile n's last layer)
+    float4 xr[12];
+    auto fetch_x0 = [&](int tile_) {
+      const int g_ = tile_ * kValid - kHalo + j;
+      const bool ok = g_ >= 0 && g_ < R && c.row_utt[g_] >= 0;
+      const float4* src = reinterpret_cast<const float4*>(c.z + (size_t)(ok ? g_ : 0) * H + c.in_off + 48 * hh);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) xr[i] = ok ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if ((int)blockIdx.x < prm.n_tiles) fetch_x0(blockIdx.x);
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
       const int g = tile * kValid - kHalo + j;
       const bool in_seq = g >= 0 && g < R;
       const int utt = in_seq ? c.row_utt[g] : -1;
       const bool valid = utt >= 0;
       const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
-      const float* zrow = c.z + (size_t)(in_seq ? g : 0) * H;
-      // ---- x0 (fp32 rows) -> x0_16 in the first 12 planes of the acts buffer; this warp's 48 channels
+      // ---- x0 (fp32 rows) -> x0_16 in the first 12 planes of the acts buffer
       {
-        const float4* src = reinterpret_cast<const float4*>(zrow + c.in_off + 48 * hh);
 #pragma unroll
         for (int p6 = 0; p6 < 6; ++p6) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (valid) { a = src[2 * p6]; b = src[2 * p6 + 1]; }
+          const float4 a = xr[2 * p6], b = xr[2 * p6 + 1];
           sts128(act16 + (uint32_t)((6 * hh + p6) * kTileM + j) * 16u, pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y),
                  pack_f16x2(b.z, b.w));
         }
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_coupling_kernel(const __grid
         if (lane == 0) mbar_arrive(acts_ready);
       }
       // ---- m (TMEM) + bias -> x1 <- (x1 + sign m) * mask, rows this tile owns; this warp's 48 channels
+      if (tile + (int)gridDim.x < prm.n_tiles) fetch_x0(tile + gridDim.x);      // x0 is the half of z this kernel does not write
       mbar_wait(h_done, n_hdone & 1u, 9);
       ++n_hdone;
       tc_fence_after();
