@@ -89,8 +89,9 @@ int64_t vs_launch_count(void);
  * 0 = in_layer and res_skip as two launches of the generic TF32 conv.
  * "mrf_fused": 1 (default) = the decoder's last MRF stage (C = 32: three ResBlocks, sum, conv_post, tanh) is ONE kernel with the
  * residual stream and the MRF sum in fp32 in TMEM (csrc/umma_mrf.cu), 0 = the chain of fused conv-pair kernels + conv_post (A/B).
- * "pair_conv": 1 (default) = the decoder's Cin = Cout = 128 convs run on a CTA pair (tcgen05 cta_group::2: weights resident, split
- * between the two CTAs' shared memories; csrc/umma_pair.cu), 2 = also Cin = Cout = 256 at k = 3, 0 = the single-CTA kernel (A/B).
+ * "pair_conv": the decoder's wide convs on a CTA pair (tcgen05 cta_group::2: weights resident, split between the two CTAs' shared
+ * memories; csrc/umma_pair.cu): 1 (default) = Cin = Cout = 128, 2 = also Cin = Cout = 256 at k = 3 (0.107 -> 0.083 ms per launch alone, no
+ * gain inside the decoder), 0 = the single-CTA kernel (A/B).
  * "pdl": bit mask of the kernel groups launched with programmatic dependent launch (the next kernel's launch, CTA scheduling and prologue
  * overlap its predecessor's tail; every such kernel executes griddepcontrol.wait before it touches global memory): 1 = three-term conv,
  * LayerNorm, rows_to_split, the fp32 cluster conv; 32 = the small element-wise kernels of the latent stages; 16 = CUDA-core attention,

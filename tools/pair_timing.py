@@ -109,3 +109,4 @@ for k in (3, 7, 11):
     run("s1 c1 k%d d1" % k, FRAMES * 64, 128, k, 1, False)
     run("s1 c2 k%d +res" % k, FRAMES * 64, 128, k, 1, True)
 run("s0 c1 k3 d5", FRAMES * 8, 256, 3, 5, False)
+run("s0 c2 k3 +res", FRAMES * 8, 256, 3, 1, True)

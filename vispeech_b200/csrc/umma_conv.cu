@@ -480,7 +480,7 @@ int make_plan(const UmmaConv& c, Plan* out) {
 void* umma_conv_timing_buffer() { return reinterpret_cast<void*>(opts().v[OPT_TIMING_BUFFER]); }
 
 int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
-  if (opts().v[OPT_PAIR_CONV] && umma_pair_supported(c) && (opts().v[OPT_PAIR_CONV] > 1 || c.Cin == 128)) return umma_pair_conv(c, st);
+  if (opts().v[OPT_PAIR_CONV] && umma_pair_supported(c) && (opts().v[OPT_PAIR_CONV] > 1 || c.Cin == 128)) return umma_pair_conv(c, st);   // 1: C = 128 only
   Params prm;
   prm.c = c;
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());

@@ -27,10 +27,11 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;     // producer | MMA issuer (leader) | relay | 8 epilogue warps | second MMA issuer
 constexpr int kMaxSlots = 8;
 constexpr int kMaxAcc = 4;
-constexpr int kKCH = 64;                            // channels per A chunk
-constexpr int kChunkPlanes = kKCH / 8;
+// channels per A chunk: 64 at C = 128 (fewer chunk hand-offs per unit); 32 at C = 256, whose 192 KB of resident k = 3 weights leave room for
+// three small slots only
+__host__ __device__ constexpr int kch_for(int c) { return c == 128 ? 64 : 32; }
 constexpr int kPairM = 2 * kTileM;
-constexpr int kMaxCC = 2;                           // 32-column chunks per epilogue warp (N = 128: 64 columns each)
+
 
 struct Plan {
   int rows_a, halo_l, n_chunks, planes, nhalf, nslot, nacc, n_units, row_div_shift, n_issuers;
@@ -119,8 +120,11 @@ __device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint32_t a_lo, uint
       : "memory");
 }
 
-template <int F>
+template <int F, int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pair_kernel(const __grid_constant__ Params prm) {
+  constexpr int kKCH = kch_for(C), kChunkPlanes = kKCH / 8;
+  constexpr int kMaxCC = C / 64;                      // 32-column chunks per epilogue warp (each warp owns N / 2 columns of its lane quarter)
+  constexpr bool kPrefetchRes2 = C == 128;            // at C = 256 the MRF-sum rows are fetched chunk by chunk (registers)
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   const UmmaConv& c = prm.c;
@@ -235,44 +239,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
       const uint32_t w16 = b_lo_fixed + (w_base >> 4);
       const uint32_t nslot = (uint32_t)p.nslot, nacc = (uint32_t)p.nacc, ncols = (uint32_t)c.N;
       const int n_chunks = p.n_chunks;
-      // Two issuing warps take alternate units (issuer iw: local units iw, iw + n_issuers, ...): one warp's barrier round trips and
-      // descriptor arithmetic overlap the other's MMAs (in isolation one warp sustains 64 clk per N = 128 MMA, next to eight busy
-      // epilogue warps it measured 80-110, tools/pair_microbench.cu / pair_timing.py).  Slots and accumulators are functions of
-      // the unit index; the plan makes the ring sizes multiples of n_issuers x (chunks per unit), so consecutive users of one
-      // barrier are always the same warp and its phases are consumed in order.
-      const int iw = warp == 1 ? 0 : 1, n_iss = p.n_issuers;
-      const uint32_t units_in_ring = nslot / (uint32_t)n_chunks;
       mbar_wait_cluster(w_full, 0, 4);
       tc_fence_after();
-      // A satisfied mbarrier probe still costs the issuer a few hundred clocks while the tensor pipe is busy, so the next chunk's
-      // barrier is probed before the current chunk's MMAs are issued and the blocking wait is taken only if that probe failed.
-      if (iw < n_iss)
-      for (int n = iw, u = pair + iw * n_pairs; u < p.n_units; n += n_iss, u += n_iss * n_pairs) {
-        const uint32_t acc_slot = (uint32_t)n % nacc, acc_phase = ((uint32_t)n / nacc) & 1u;
-        uint32_t slot = ((uint32_t)n % units_in_ring) * (uint32_t)n_chunks, ph = ((uint32_t)n / units_in_ring) & 1u;
-        VS_TIMED(tw1, mbar_wait_cluster(acc_empty(acc_slot), acc_phase ^ 1u, 5));
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_slot * ncols;
-        uint32_t accumulate = 0;
-        uint32_t b_chunk = w16;
-        bool a_ready = false;
-        for (int ch = 0; ch < n_chunks; ++ch, b_chunk += b_chunkstep, ++slot) {
-          if (!a_ready) VS_TIMED(tw0, mbar_wait_cluster(a_full(slot), ph, 6));
-          tc_fence_after();
-          a_ready = ch + 1 < n_chunks ? mbar_test_wait(a_full(slot + 1), ph) : false;     // consumed at the top of the next chunk
-          uint32_t a_tap = a_lo_fixed + ((a_base + slot * p.slot_bytes) >> 4);
-          uint32_t b_tap = b_chunk;
+      auto chunk_mmas = [&](uint32_t d_tmem, uint32_t slot, uint32_t b_chunk, uint32_t accumulate) {
+        uint32_t a_tap = a_lo_fixed + ((a_base + slot * p.slot_bytes) >> 4), b_tap = b_chunk;
 #pragma unroll 1
-          for (int t = 0; t < taps; ++t, a_tap += (uint32_t)dil, b_tap += b_tapstep) {
-            tc_mma_pair(d_tmem, a_tap, a_hi, b_tap, b_hi, idesc, accumulate);
-            accumulate = 1;
+        for (int t = 0; t < taps; ++t, a_tap += (uint32_t)dil, b_tap += b_tapstep) {
+          tc_mma_pair(d_tmem, a_tap, a_hi, b_tap, b_hi, idesc, accumulate);
+          accumulate = 1;
 #pragma unroll
-            for (int k16 = 1; k16 < kKCH / 16; ++k16)
-              tc_mma_pair(d_tmem, a_tap + (uint32_t)k16 * a_kstep, a_hi, b_tap + (uint32_t)k16 * b_kstep, b_hi, idesc, 1u);
-          }
-          VS_TIMED(tw2, tc_commit_pair(a_empty(slot)));          // both CTAs' producers may refill the slot once these MMAs have read it
+          for (int k16 = 1; k16 < kKCH / 16; ++k16)
+            tc_mma_pair(d_tmem, a_tap + (uint32_t)k16 * a_kstep, a_hi, b_tap + (uint32_t)k16 * b_kstep, b_hi, idesc, 1u);
         }
-        VS_TIMED(tw2, tc_commit_pair(acc_full(acc_slot)));       // accumulator complete in both CTAs' TMEM -> both epilogues
+      };
+      // A satisfied mbarrier probe still costs the issuer a few hundred clocks while the tensor pipe is busy, so the next chunk's
+      // barrier is PROBED before the current chunk's MMAs are issued and the blocking wait is taken only if that probe failed.
+      if (p.n_issuers == 2) {
+        // Two issuing warps take alternate units (issuer iw: local units iw, iw + 2, ...): one warp's barrier round trips and
+        // descriptor arithmetic overlap the other's MMAs (c2 forms of the C = 128 stage: -4 %).  Slots and accumulators are
+        // functions of the unit index; the plan makes the ring a whole, even number of units, so consecutive users of one barrier
+        // are always the same warp and its phases are consumed in order.
+        const int iw = warp == 1 ? 0 : 1;
+        const uint32_t units_in_ring = nslot / (uint32_t)n_chunks;
+        for (int n = iw, u = pair + iw * n_pairs; u < p.n_units; n += 2, u += 2 * n_pairs) {
+          const uint32_t acc_slot = (uint32_t)n % nacc, acc_phase = ((uint32_t)n / nacc) & 1u;
+          uint32_t slot = ((uint32_t)n % units_in_ring) * (uint32_t)n_chunks;
+          const uint32_t ph = ((uint32_t)n / units_in_ring) & 1u;
+          VS_TIMED(tw1, mbar_wait_cluster(acc_empty(acc_slot), acc_phase ^ 1u, 5));
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc_slot * ncols;
+          uint32_t b_chunk = w16;
+          bool a_ready = false;
+          for (int ch = 0; ch < n_chunks; ++ch, b_chunk += b_chunkstep, ++slot) {
+            if (!a_ready) VS_TIMED(tw0, mbar_wait_cluster(a_full(slot), ph, 6));
+            tc_fence_after();
+            a_ready = ch + 1 < n_chunks ? mbar_test_wait(a_full(slot + 1), ph) : false;
+            chunk_mmas(d_tmem, slot, b_chunk, ch ? 1u : 0u);
+            VS_TIMED(tw2, tc_commit_pair(a_empty(slot)));        // both CTAs' producers may refill the slot once these MMAs have read it
+          }
+          VS_TIMED(tw2, tc_commit_pair(acc_full(acc_slot)));     // accumulator complete in both CTAs' TMEM -> both epilogues
+        }
+      } else if (warp == 1) {
+        // one issuer, chunk-granular ring (C = 256: three small slots next to 192 KB of weights)
+        uint32_t slot = 0, ph = 0, acc_slot = 0, acc_phase = 0;
+        bool a_ready = false, acc_ready = false;
+        for (int u = pair; u < p.n_units; u += n_pairs) {
+          if (!acc_ready) VS_TIMED(tw1, mbar_wait_cluster(acc_empty(acc_slot), acc_phase ^ 1u, 5));
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc_slot * ncols;
+          uint32_t next_acc = acc_slot + 1, next_acc_phase = acc_phase;
+          if (next_acc == nacc) { next_acc = 0; next_acc_phase ^= 1u; }
+          uint32_t b_chunk = w16;
+          for (int ch = 0; ch < n_chunks; ++ch, b_chunk += b_chunkstep) {
+            if (!a_ready) VS_TIMED(tw0, mbar_wait_cluster(a_full(slot), ph, 6));
+            tc_fence_after();
+            uint32_t nslot_i = slot + 1, nph = ph;
+            if (nslot_i == nslot) { nslot_i = 0; nph ^= 1u; }
+            a_ready = mbar_test_wait(a_full(nslot_i), nph);                     // consumed at the top of the next chunk
+            if (ch == n_chunks - 1) acc_ready = mbar_test_wait(acc_empty(next_acc), next_acc_phase ^ 1u);
+            chunk_mmas(d_tmem, slot, b_chunk, ch ? 1u : 0u);
+            VS_TIMED(tw2, tc_commit_pair(a_empty(slot)));
+            slot = nslot_i; ph = nph;
+          }
+          VS_TIMED(tw2, tc_commit_pair(acc_full(acc_slot)));
+          acc_slot = next_acc; acc_phase = next_acc_phase;
+        }
       }
     }
     __syncwarp();
@@ -298,14 +329,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
       if (in_range && c.row_utt) valid = c.row_utt[r >> p.row_div_shift] >= 0;
       const size_t row_elem = (size_t)r * 8;
       // the residual reads do not depend on the accumulator: they are in flight while this unit's MMAs still run
-      uint4 rv[kMaxCC * 4], rv2[kMaxCC * 4];
+      uint4 rv[kMaxCC * 4], rv2[kPrefetchRes2 ? kMaxCC * 4 : 4];
       if (valid && (has_res || has_res2)) {
 #pragma unroll
         for (int g = 0; g < kMaxCC * 4; ++g)
           if (g < n_cc * 4) {
             const size_t o = (size_t)(g8_0 + g) * plane_stride + row_elem;
             if (has_res) rv[g] = *reinterpret_cast<const uint4*>(c.res + o);
-            if (has_res2) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + o);
+            if (has_res2 && kPrefetchRes2) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + o);
           }
       }
       VS_TIMED(tw0, mbar_wait(acc_full(acc_slot), acc_phase, 7));
@@ -315,6 +346,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
       for (int cc = 0; cc < kMaxCC; ++cc) {
         if (cc >= n_cc) break;
         const uint32_t g8 = g8_0 + (uint32_t)(cc * 4);
+        if (has_res2 && !kPrefetchRes2 && valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rv2[g] = *reinterpret_cast<const uint4*>(c.res2 + (size_t)(g8 + g) * plane_stride + row_elem);
+        }
         uint32_t v[32];
         VS_TIMED(tw1, tmem_ld32(t_row + (uint32_t)(cc * 32), v));
         if (in_range) {
@@ -339,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
               }
               if (has_res2) {
                 float f[8];
-                unpack_f16x8(rv2[cc * 4 + g], f);
+                unpack_f16x8(rv2[kPrefetchRes2 ? cc * 4 + g : g], f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) y[e] += f[e];
               }
@@ -384,11 +419,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) umma_pa
 int make_plan(const UmmaConv& c, Plan* out) {
   Plan p{};
   p.planes = c.Cin / 8;
-  p.n_chunks = c.Cin / kKCH;
+  const int kch = kch_for(c.Cin);
+  p.n_chunks = c.Cin / kch;
   p.nhalf = c.N / 2;
   p.halo_l = c.pad_l * c.dil;
   p.rows_a = kTileM + (c.taps - 1) * c.dil;
-  p.slot_bytes = (uint32_t)kChunkPlanes * (uint32_t)p.rows_a * 16u;
+  p.slot_bytes = (uint32_t)(kch / 8) * (uint32_t)p.rows_a * 16u;
   p.w_bytes = (uint32_t)c.taps * (uint32_t)c.Cin * (uint32_t)p.nhalf * 2u;
   int s = 0;
   while ((1 << s) < c.row_div) ++s;
@@ -399,10 +435,10 @@ int make_plan(const UmmaConv& c, Plan* out) {
   const uint32_t cap = 227u * 1024;
   VS_REQUIRE(p.w_bytes + fixed + 2 * p.slot_bytes <= cap, "umma_pair: weights + 2 A chunks do not fit in shared memory");
   const int nslot = (int)((cap - fixed - p.w_bytes) / p.slot_bytes);
-  // whole units in the ring; with two issuing warps an even number of units (see the kernel), else one issuer
+  // two issuing warps need a ring of a whole, even number of units (see the kernel); else one issuer and a chunk-granular ring
   const int units = nslot / p.n_chunks;
   p.n_issuers = units >= 2 ? 2 : 1;
-  p.nslot = (units >= 4 ? 4 : units >= 2 ? 2 : 1) * p.n_chunks;
+  p.nslot = units >= 2 ? (units >= 4 ? 4 : 2) * p.n_chunks : (nslot > kMaxSlots ? kMaxSlots : nslot);
   VS_REQUIRE(p.nslot <= kMaxSlots, "umma_pair: A ring deeper than its barrier table");
   p.nacc = 512 / c.N > kMaxAcc ? kMaxAcc : 512 / c.N;
   p.off_w = (uint32_t)p.nslot * p.slot_bytes;
@@ -418,10 +454,10 @@ int make_plan(const UmmaConv& c, Plan* out) {
 }  // namespace
 
 bool umma_pair_supported(const UmmaConv& c) {
-  if (!(c.Cin == c.N && c.Cin == 128)) return false;
+  if (!(c.Cin == c.N && (c.Cin == 128 || (c.Cin == 256 && c.taps <= 3)))) return false;
   if (c.up != 1 || c.ubias || c.out_lo || c.taps < 1 || c.dil < 1) return false;
   const uint32_t w_bytes = (uint32_t)c.taps * c.Cin * (c.N / 2) * 2u;
-  const uint32_t slot = (uint32_t)kChunkPlanes * (uint32_t)(kTileM + (c.taps - 1) * c.dil) * 16u;
+  const uint32_t slot = (uint32_t)(kch_for(c.Cin) / 8) * (uint32_t)(kTileM + (c.taps - 1) * c.dil) * 16u;
   return w_bytes + 2 * slot + 2048u + (uint32_t)c.N * 4u <= 227u * 1024;
 }
 
@@ -441,14 +477,14 @@ int umma_pair_conv(const UmmaConv& c, cudaStream_t st) {
     int dev = 0;
     VS_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 16 && cached[dev] == 0) {
-      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1>), 227 * 1024));
+      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1, 128>), 227 * 1024));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * n_pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 227 * 1024 - 1024;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, umma_pair_kernel<-1>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_pairs; }
+      if (cudaOccupancyMaxActiveClusters(&n, umma_pair_kernel<-1, 128>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_pairs; }
       cached[dev] = n;
     }
     if (dev >= 0 && dev < 16 && cached[dev] < n_pairs) n_pairs = cached[dev];
@@ -458,8 +494,13 @@ int umma_pair_conv(const UmmaConv& c, cudaStream_t st) {
                     (c.act_scale != 1.f ? F_SCALE : 0) | ((c.res && c.res_inv_slope != 0.f) ? F_RESINV : 0);
 #define VS_PAIR_CASE(FL)                                                                                  \
   case FL: {                                                                                              \
-    VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<FL>), 227 * 1024));         \
-    VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<FL>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));                           \
+    if (c.Cin == 128) {                                                                                   \
+      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<FL, 128>), 227 * 1024));  \
+      VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<FL, 128>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm)); \
+    } else {                                                                                              \
+      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<FL, 256>), 227 * 1024));  \
+      VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<FL, 256>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm)); \
+    }                                                                                                     \
     break;                                                                                                \
   }
   switch (flags) {
@@ -469,8 +510,13 @@ int umma_pair_conv(const UmmaConv& c, cudaStream_t st) {
     VS_PAIR_CASE(F_RES | F_RESINV | F_RES2 | F_RAW)
     VS_PAIR_CASE(F_RES | F_RESINV | F_RES2 | F_ACT | F_SCALE)
     default: {
-      VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1>), 227 * 1024));
-      VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<-1>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));
+      if (c.Cin == 128) {
+        VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1, 128>), 227 * 1024));
+        VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<-1, 128>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));
+      } else {
+        VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(umma_pair_kernel<-1, 256>), 227 * 1024));
+        VS_CUDA_CHECK(launch_pdl<4>(umma_pair_kernel<-1, 256>, dim3(2 * n_pairs), dim3(kThreads), prm.p.smem_bytes, st, prm));
+      }
     }
   }
 #undef VS_PAIR_CASE
