@@ -101,9 +101,9 @@ int64_t vs_launch_count(void);
  * "tap_pairs": the fused ResBlock iterations of the C = 64 stage may issue their conv taps in PAIRS as N = 128 MMAs (half the shared-memory
  * operand traffic per tap; the epilogue re-aligns the odd taps' half by a lane shuffle + a small exchange between lane quarters): 0 (default)
  * = never (measured slower in the whole decoder), 1 = at k = 11 only, 2 = at every k (csrc/umma_respair.cu).
- * "coupling_min_rows": frame rows from which the flow takes the one-kernel coupling layer (default 4096 = tf32_min_rows: smaller calls
- * keep their fp32-accurate kernels); 1 = always (a latency knob: 76 -> 4 launches per flow pass, C1 3.66 -> 3.18 ms per call, z within
- * 5e-4 of the fp32 path instead of 1e-5).
+ * "coupling_min_rows": frame rows from which the flow takes the one-kernel coupling layer.  Default 1 = always: 76 -> 4 launches per flow
+ * pass on the batch-1 path (C1 3.66 -> 3.18 ms per call), z within 4.2e-4 of the reference on the golden utterances (bar 1e-2), and an
+ * utterance's flow no longer changes regime with the batch it is in; 4096 = small calls keep the fp32 / three-term kernels (z within 1e-5).
  * "coupling_fused": 1 (default) = in the plain-TF32 regime (>= tf32_min_rows frame rows) every coupling layer of the flow is ONE kernel
  * (pre, the 4-layer WN stack, post and the x1 update; residual stream and skip sum in fp32 in TMEM, fp16 operands; csrc/umma_coupling.cu),
  * 0 = pre / per-layer WN kernels / post / update as separate launches (A/B).

@@ -252,3 +252,26 @@ def test_coupling_layer_kernel_matches_oracle_flow(net, state_dict, direction):
     print("coupling kernel, %s: worst |z - oracle| = %.2e; vs the layer-by-layer TF32 path %.2e" %
           (direction, worst, float((outs[1] - outs[0]).abs().max())))
     assert float(outs[1][row_utt < 0].abs().max()) == 0.0          # gap rows stay zero
+
+
+def test_coupling_kernel_on_the_latency_path_meets_the_bars(net):
+    """The one-kernel coupling layer on small calls (option coupling_min_rows = 1, the default: 76 -> 4 launches per flow pass) AND the
+    fp32 / three-term kernels it replaces there (coupling_min_rows = 4096) on the golden utterances: latent z within 1e-2 of the
+    reference, waveform SNR >= 30 dB."""
+    import glob, os
+    paths = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                   if not os.path.basename(p).startswith(("vc", "filelist")))
+    from test_gpu_infer import run_golden
+    try:
+        for min_rows in (1, 4096):
+            net.set_option("coupling_min_rows", min_rows)
+            for path in paths:
+                d = dict(np.load(path))
+                o, x_mask, (z, z_p, m_p, logs_p), duration, f0, energy = run_golden(net, d, 0)
+                err = float(np.abs(z[0].cpu().numpy() - d["z"]).max())
+                ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d["o_is_f16x64"]) else 1)
+                snr = snr_db(ref, o[0, 0].cpu())
+                print(min_rows, os.path.basename(path), "z err %.2e  snr %.1f dB" % (err, snr))
+                assert err <= 1e-2 and snr >= 30.0, (path, err, snr)
+    finally:
+        net.set_option("coupling_min_rows", 1)

@@ -577,8 +577,8 @@ static int flow_run(const VsModel* m, const VsRows* rows, float* z, bool reverse
     const bool flipped = (f & 1) != 0;
     const int in_off = flipped ? H / 2 : 0, upd_off = flipped ? 0 : H / 2;
     if (w.c16_w && opts().v[OPT_COUPLING_FUSED] && R >= opts().v[OPT_COUPLING_MIN_ROWS] && (R >= opts().v[OPT_TF32_MIN_ROWS] || opts().v[OPT_COUPLING_MIN_ROWS] < 4096)) {
-      // the plain-TF32 regime (frame level, >= tf32_min_rows rows): the whole coupling layer as ONE kernel, residual stream and
-      // skip sum in fp32 in TMEM, fp16 operands (the same 11-bit significand as TF32)  modules.py:324-343, 148-176
+      // the whole coupling layer as ONE kernel, residual stream and skip sum in fp32 in TMEM, fp16 operands (the 11-bit significand
+      // of the TF32 regime it replaced for large calls; small calls take it too by default, option coupling_min_rows)  modules.py:324-343, 148-176
       UmmaCoupling u;
       u.z = z; u.w = w.c16_w; u.bias = w.c16_b; u.row_utt = rows->row_utt; u.sid = rows->sid; u.R = R;
       u.in_off = in_off; u.upd_off = upd_off; u.sign = reverse ? -1.f : 1.f;
