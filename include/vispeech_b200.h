@@ -76,8 +76,8 @@ int vs_version(void);
 int64_t vs_launch_count(void);
 /* process-wide knobs. "tf32_min_rows": convs over at least this many rows run on the tensor cores in TF32 (default
  * 4096; fewer rows stay on the fp32 CUDA-core kernel).  Used by the parity tests to force either path.
- * "x3_min_rows": convs over at least this many rows (and below tf32_min_rows, or phoneme level) run as error-
- * compensated 3xTF32 on the tensor cores (default 512; fp32-level accuracy).
+ * "x3_min_rows": convs over at least this many rows (and below tf32_min_rows, or phoneme level) run in the error-
+ * compensated three-term form on the tensor cores (fp16 hi/lo, or 3xTF32 with split16 = 0; fp32-level accuracy); default 256.
  * "tf32_prior": 0 (default) = the frame prior network and the (m_p, logs_p) projection use 3xTF32 at every size (prior
  * sampling amplifies their error), 1 = plain TF32 above tf32_min_rows like the flow (A/B measurements).
  * "fused_respair": 0 = never, 1 = only the C=32 stage's ResBlock iterations run as one fused conv-pair kernel,

@@ -1,5 +1,5 @@
 """Shape sweep: the same utterance inside batches of very different sizes (every precision regime and tile-count parity of the
-kernels: fp32 < 512 rows, 3xTF32 < 4096, plain TF32 + one-kernel WN layers above; odd / even tile counts; > 1 wave).
+kernels: fp32 < 256 rows, 3xTF32 < 4096, plain TF32 + one-kernel WN layers above; odd / even tile counts; > 1 wave).
 Prints the difference of utterance 0's latent and waveform to its batch-1 result; asserts the parity bars."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -45,11 +45,11 @@ struct PosteriorW {                                      // enc_q (models.py:212
 
 // Precision / engine policy for the GEMM-shaped convs upstream of the decoder (all rows counts are per call):
 //   rows >= tf32_min_rows (4096) and the conv is frame level  -> tcgen05 kind::tf32, operands rounded to TF32
-//   rows >= x3_min_rows (512)                                  -> tcgen05 3xTF32 (hi/lo split, fp32-level accuracy)
+//   rows >= x3_min_rows (256)                                  -> tcgen05 3xTF32 (hi/lo split, fp32-level accuracy)
 //   otherwise                                                  -> fp32 CUDA cores
 // Phoneme-level convs (text encoder, predictors) never take the plain-TF32 route: their error feeds back through the
 // F0 / energy prenets (measured: z error 7.5e-3 with plain TF32 there vs 4.6e-3 without; bar 1e-2).
-// Options "tf32_min_rows" (4096), "x3_min_rows" (512), "tf32_prior" (0) and "wn_fused" (1) come from opts() (common.cuh).
+// Options "tf32_min_rows" (4096), "x3_min_rows" (256), "tf32_prior" (0) and "wn_fused" (1) come from opts() (common.cuh).
 // The frame prior network and the projection to (m_p, logs_p) stay on 3xTF32 at every size unless tf32_prior = 1:
 // z_p = m_p + eps * exp(logs_p) amplifies their error (measured on C4: plain TF32 there gives |dz| = 1.2e-2 > the 1e-2 bar,
 // 3xTF32 1.4e-4).

@@ -31,7 +31,7 @@ std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
                                           "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "coupling_min_rows", "tap_pairs"};
-Options g_defaults = {{4096, 512, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33, 1, 0}};
+Options g_defaults = {{4096, 256, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33, 1, 0}};
 thread_local Options tl_opts;
 thread_local int tl_scope_depth = 0;
 }  // namespace
