@@ -333,7 +333,7 @@ def main():
     net = build_from_hparams(get_hparams_from_file(), device=dev)
     net.load_state_dict(sd)
     lib = _lib.load()
-    for opt in ("fused_respair", "tf32_min_rows", "x3_min_rows", "tf32_prior", "decoder_streams", "attention_mma", "wn_fused", "tf32_cluster", "mrf_fused", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "tap_pairs"):     # A/B knobs for profiling runs (defaults otherwise)
+    for opt in ("fused_respair", "tf32_min_rows", "x3_min_rows", "tf32_prior", "decoder_streams", "attention_mma", "wn_fused", "tf32_cluster", "mrf_fused", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "tap_pairs", "conv_spread", "attention_small"):     # A/B knobs for profiling runs (defaults otherwise)
         if os.environ.get("VS_" + opt.upper()):
             _lib.check(lib.vs_set_option(opt.encode(), int(os.environ["VS_" + opt.upper()])))
 

@@ -98,6 +98,11 @@ int64_t vs_launch_count(void);
  * row_dot; 2 / 64 / 128 = the frame-level attention kernel / its tile re-layout / its band fix-up; 4 = decoder (always on for calls below
  * 2048 frame rows); 8 = flow.  Default 33 (the groups that measured faster; 64 alone costs the frame prior 0.3 ms), 0 = every launch
  * fully serialised (A/B).
+ * "conv_spread": 1 (default) = a decoder conv with streamed weights and fewer 128-row tiles than half the SMs is also cut along its output
+ * channels (n-blocks narrowed to >= 64 columns, one CTA per (row tile, n-block group)), so the first ConvTranspose of a 4-second call
+ * runs on 96 CTAs instead of 3; results are bit-identical to 0 (= row tiles only, A/B).  Batch-size calls never take it.
+ * "attention_small": 1 (default) = the CUDA-core attention kernel takes 16 queries per CTA instead of 64 when the batch is too small to
+ * fill half the SMs with 64-query CTAs (the batch-1 latency path), 0 = always 64.
  * "tap_pairs": the fused ResBlock iterations of the C = 64 stage may issue their conv taps in PAIRS as N = 128 MMAs (half the shared-memory
  * operand traffic per tap; the epilogue re-aligns the odd taps' half by a lane shuffle + a small exchange between lane quarters): 0 (default)
  * = never (measured slower in the whole decoder), 1 = at k = 11 only, 2 = at every k (csrc/umma_respair.cu).
@@ -115,8 +120,9 @@ int64_t vs_launch_count(void);
  * "split16": 1 (default) = every conv in the 3xTF32 regime of the encoders / predictors / projection runs as the three-term fp16
  * hi/lo conv on tcgen05 kind::f16 (csrc/umma_split.cu: same fp32-level accuracy, TMA-fed planar operands), 0 = 3xTF32 (A/B).
  * "tf32_cluster": 1 (default) | 2 = two CTAs of a cluster share every weight slab of the TF32 conv by TMA multicast
- * (bit-identical; no gain measured).  "decoder_streams": 1 (default) | 2 = the k=11 ResBlock chains of each decoder stage
- * run on a side stream (no gain measured).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).
+ * (bit-identical; no gain measured).  "decoder_streams": 2 = the k=11 ResBlock chains of each decoder stage run on a side
+ * stream (fork / join by events, graph-capturable; bit-identical), 1 = one stream, 0 (default) = 2 for calls below 2048 frame rows (where
+ * the kernels are small enough to run side by side: chunked 60 s decode 32.8 -> 28.1 ms) and 1 above (no gain at batch size).  "respair_grid_div": co-scheduling experiments (tools/cosched_pairs.py).
  * "umma_timing_buffer": diagnostics - a device pointer (or 0) to >= 148*24 int64 where the tcgen05 kernels built with
  * -DVS_UMMA_TIMING leave per-CTA clocks spent waiting on each mbarrier (tools/conv_timing.py, tf32_timing.py, wn_timing.py).
  * vs_set_option sets the PROCESS DEFAULT of an option; vs_model_set_option overrides it for one model handle.  Every entry

@@ -40,6 +40,38 @@ def test_umma_conv_matches_cpu(G, R, cin, n, taps, dil):
     assert (act.cpu().double() - ref_act).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("R,cin,n,taps,dil", [(370, 192, 512, 7, 1), (2960, 256, 256, 11, 5), (300, 512, 2048, 2, 1), (2960, 256, 1024, 2, 1),
+                                              (130, 256, 256, 3, 1), (9000, 256, 256, 7, 3)])
+def test_umma_conv_spread_over_n_blocks_is_bit_identical(G, R, cin, n, taps, dil):
+    """Small calls cut the streamed-weight convs along N too (option conv_spread: n-blocks narrowed to >= 64 columns, fetched as column
+    ranges of the packed slabs, one CTA per (row tile, n-block group)): the batch-1 shapes of conv_pre, the first two ConvTranspose and the
+    C = 256 ResBlock convs (models.py:250-285), a masked gap and a ragged tail.  Same MMAs per output element -> identical bits; the
+    last case has too many tiles to spread and checks the dispatch leaves it alone."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(R + n)
+    x = torch.randn(R, cin, generator=g)
+    w = torch.randn(taps, cin, n, generator=g) / (cin * taps) ** 0.5
+    b = torch.randn(n, generator=g) * 0.1
+    res = G.f16_round(torch.randn(R, n, generator=g))
+    row_utt = torch.zeros(R, dtype=torch.int32)
+    row_utt[50:61] = -1
+    x[50:61] = 0
+    pad_l = (taps - 1) // 2
+    outs = []
+    for spread in (1, 0):
+        _lib.check(lib.vs_set_option(b"conv_spread", spread))
+        try:
+            outs.append(G.umma_conv(x.to(G.DEV), w, b.to(G.DEV), res=res.to(G.DEV), dil=dil, pad_l=pad_l, act_slope=0.1,
+                                    row_utt=row_utt.to(G.DEV)))
+        finally:
+            _lib.check(lib.vs_set_option(b"conv_spread", 1))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = G.ref_conv_rows(G.f16_round(x), G.f16_round(w), b, dil=dil, pad_l=pad_l) + res.double()
+    ref[50:61] = 0
+    assert (outs[0][0].cpu().double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
 def test_umma_conv_residual_mask_and_scale(G):
     R, C = 700, 64
     g = torch.Generator().manual_seed(5)
@@ -450,6 +482,34 @@ def test_rel_attention_matches_oracle(G, lengths, state_dict, kernel):
     for b, ref in enumerate(refs):
         s = rows.starts[b]
         assert (out[s:s + lengths[b]].cpu() - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("lengths", [[70], [3, 1, 70, 100], [127, 64]])
+def test_rel_attention_small_batch_variant_is_bit_identical(G, lengths, state_dict):
+    """The CUDA-core attention takes 16 queries per CTA when 64-query CTAs would leave most SMs idle (option attention_small, the
+    batch-1 path): same dot-product, softmax and P.V association per row, so an utterance's bits do not depend on the batch it is in."""
+    from vispeech_b200 import _lib
+    lib = _lib.load()
+    p = "enc_p.encoder.attn_layers.0"
+    rows = G.make_rows(lengths, [0] * len(lengths), 4, G.DEV)
+    g = torch.Generator().manual_seed(len(lengths))
+    d_qkv = torch.randn(rows.n_rows, 576, generator=g).to(G.DEV)
+    d_ek = state_dict[p + ".emb_rel_k"][0].contiguous().to(G.DEV)
+    d_ev = state_dict[p + ".emb_rel_v"][0].contiguous().to(G.DEV)
+    outs = []
+    _lib.check(lib.vs_set_option(b"attention_mma", 0))
+    try:
+        for small in (1, 0):
+            _lib.check(lib.vs_set_option(b"attention_small", small))
+            out = torch.zeros(rows.n_rows, 192, device=G.DEV)
+            _lib.check(lib.vs_op_rel_attention(ctypes.byref(rows.struct), d_qkv.data_ptr(), d_ek.data_ptr(), d_ev.data_ptr(),
+                                               out.data_ptr(), 0, 0, G.stream()))
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        _lib.check(lib.vs_set_option(b"attention_mma", 1))
+        _lib.check(lib.vs_set_option(b"attention_small", 1))
+    assert torch.equal(outs[0], outs[1]) and outs[0].abs().max().item() > 0
 
 
 @pytest.mark.parametrize("R,first,last", [(300, 1, 0), (1000, 0, 0), (4229, 0, 1), (129, 1, 1)])

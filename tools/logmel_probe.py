@@ -21,12 +21,16 @@ for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
     ref = torch.from_numpy(d["o"].astype(np.float32)) / (64 if int(d.get("o_is_f16x64", 0)) else 1)
     m_ref = mel_spectrogram(ref)
     for label, prec, opts in (("fp32", 1, {}), ("f16", 0, {}), ("f16 no resblock64", 0, {"resblock_fused": 0}), ("f16 no pair conv", 0, {"pair_conv": 0, "pair_fused": 0}),
-                              ("f16 no-mrf", 0, {"mrf_fused": 0}), ("f16 unfused pairs", 0, {"fused_respair": 0})):
+                              ("f16 no-mrf", 0, {"mrf_fused": 0}), ("f16 unfused pairs", 0, {"fused_respair": 0}),
+                              ("f16 one stream", 0, {"decoder_streams": 1}), ("f16 no conv spread", 0, {"conv_spread": 0}),
+                              ("f16 attention 64", 0, {"attention_small": 0}),
+                              ("f16 small-call paths off", 0, {"decoder_streams": 1, "conv_spread": 0, "attention_small": 0})):
         for k, v in opts.items():
             net.set_option(k, v)
         o = run_golden(net, d, prec)[0]
         for k in opts:
-            net.set_option(k, {"resblock_fused": 1, "mrf_fused": 1, "fused_respair": 2, "pair_conv": 1, "pair_fused": 1}[k])
+            net.set_option(k, {"resblock_fused": 1, "mrf_fused": 1, "fused_respair": 2, "pair_conv": 1, "pair_fused": 1, "decoder_streams": 0, "conv_spread": 1,
+                               "attention_small": 1}[k])
         w = o[0, 0].cpu()
         n = min(w.numel(), ref.numel())
         m = mel_spectrogram(w)

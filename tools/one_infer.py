@@ -10,6 +10,9 @@ case = sys.argv[1] if len(sys.argv) > 1 else "c1"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 net = build_from_hparams(get_hparams_from_file(), device="cuda:0")
 net.load_state_dict(make_state_dict(1234))
+for opt in ("pdl", "conv_spread", "attention_small", "coupling_min_rows", "x3_min_rows"):     # A/B knobs: VS_CONV_SPREAD=0 python tools/one_infer.py
+    if os.environ.get("VS_" + opt.upper()):
+        net.set_option(opt, int(os.environ["VS_" + opt.upper()]))
 u = (oin.c4 if case == "c4" else oin.c1)()[0]
 a = (u["ids"][None], torch.LongTensor([u["ids"].numel()]))
 kw = dict(sid=torch.LongTensor([u["sid"]]), noise_scale=0.667, duration_control=u["duration"][None])

@@ -134,7 +134,7 @@ int ensure_dynamic_smem(const void* kernel, int bytes);    // opt in to `bytes` 
 // "defaults overlaid with that model's overrides" into a thread-local snapshot for the duration of the call: kernels'
 // host code reads opts() and never a mutable global, so two models (or two threads) cannot see each other's settings.
 enum Opt { OPT_TF32_MIN_ROWS, OPT_X3_MIN_ROWS, OPT_TF32_PRIOR, OPT_WN_FUSED, OPT_ATTENTION_MMA, OPT_TF32_CLUSTER,
-           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_SPLIT16, OPT_RESBLOCK_FUSED, OPT_PAIR_CONV, OPT_PAIR_FUSED, OPT_COUPLING_FUSED, OPT_PDL, OPT_COUPLING_MIN_ROWS, OPT_TAP_PAIRS, OPT_COUNT };
+           OPT_MRF_FUSED, OPT_DECODER_STREAMS, OPT_RESPAIR_GRID_DIV, OPT_FUSED_RESPAIR, OPT_TIMING_BUFFER, OPT_SPLIT16, OPT_RESBLOCK_FUSED, OPT_PAIR_CONV, OPT_PAIR_FUSED, OPT_COUPLING_FUSED, OPT_PDL, OPT_COUPLING_MIN_ROWS, OPT_TAP_PAIRS, OPT_CONV_SPREAD, OPT_ATTENTION_SMALL, OPT_COUNT };
 constexpr int64_t kOptUnset = INT64_MIN;
 struct Options { int64_t v[OPT_COUNT]; };
 const Options& opts();                                     // the executing call's snapshot (outside a scope: the defaults)

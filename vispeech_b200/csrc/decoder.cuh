@@ -41,6 +41,7 @@ int ups_taps(int stage, int* pad_l);   // taps of the polyphase form of ups[stag
 int64_t decoder_ws_floats(int n_rows_frame);
 int decode_f32(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                cudaStream_t st);
+bool decoder_two_streams(int frame_rows);      // option decoder_streams resolved for a call of this many frame rows (decoder_umma.cu)
 int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_len, float* wave, Workspace& ws,
                 cudaStream_t st);
 

@@ -108,11 +108,17 @@ __global__ void conv_post_kernel(const __half* __restrict__ x, const float* __re
 // 25.77 vs 25.74 ms per step), so it is OFF by default.  Fork / join through events; the side chain has its own intermediate
 // buffers; the sum keeps its order (k3 + k7) + k11.
 // options "mrf_fused" (0 | 1: the last MRF stage + conv_post as ONE kernel, umma_mrf.cu) and "decoder_streams" (1 | 2; in situ 2
-// gains nothing: 25.77 vs 25.74 ms) come from opts()
+// gains nothing at batch size: 25.77 vs 25.74 ms) come from opts().  Small calls are different: below ~2048 frame rows the C = 256
+// stage's kernels are 24 - 96 CTAs each and the two chains really run side by side (chunked 60 s decode 32.8 -> 28.1 ms, C1 2.78 ->
+// 2.74), so decoder_streams = 0 (auto, the default) takes the side stream there and only there.
+bool decoder_two_streams(int frame_rows) {
+  const int64_t v = opts().v[OPT_DECODER_STREAMS];
+  return v == 2 || (v == 0 && frame_rows < 2048);
+}
 
 struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, sum = nullptr, join = nullptr; };
 static int side_stream(SideStream** out) {
-  static SideStream tab[16];
+  static thread_local SideStream tab[16];        // per thread: two threads decoding on one device must not share the fork / join events
   int dev = 0;
   VS_CUDA_CHECK(cudaGetDevice(&dev));
   VS_REQUIRE(dev >= 0 && dev < 16, "decode: device index %d", dev);
@@ -137,7 +143,7 @@ int decode_f16(const DecoderW& w, const VsRows& rows, const float* z, int max_le
   PdlExtra pdl_small(R < 2048 ? 4 : 0);
   int32_t* valid = ws.take<int32_t>(R);
   __half* zin = ws.take<__half>((int64_t)R * kHidden);
-  const bool two = opts().v[OPT_DECODER_STREAMS] == 2;
+  const bool two = decoder_two_streams(R);
   const bool mrf_fused = opts().v[OPT_MRF_FUSED] != 0;
   __half* buf[9];
   for (int i = 0; i < (two ? 9 : 6); ++i) buf[i] = ws.take<__half>((int64_t)R * 16384);

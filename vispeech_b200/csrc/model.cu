@@ -369,7 +369,7 @@ int64_t vs_workspace_bytes_latent(const VsModel* m, int32_t rp, int32_t rf) {
 int64_t vs_workspace_bytes_decoder(const VsModel* m, int32_t rf, int32_t precision) {
   if (precision == 1) return decoder_ws_floats(rf) * 4 + (1 << 20);
   vs::OptionScope option_scope(m ? &m->overrides : nullptr);
-  const int64_t bufs = vs::opts().v[vs::OPT_DECODER_STREAMS] == 2 ? 9 : 6;
+  const int64_t bufs = vs::decoder_two_streams(rf) ? 9 : 6;
   return (int64_t)rf * (bufs * 16384 * 2 + kHidden * 2 + 4) + (1 << 20);
 }
 

@@ -30,8 +30,8 @@ std::unordered_set<uint64_t> g_smem_optin;            // (kernel address, device
 
 namespace {
 const char* const kOptNames[OPT_COUNT] = {"tf32_min_rows", "x3_min_rows", "tf32_prior", "wn_fused", "attention_mma", "tf32_cluster",
-                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "coupling_min_rows", "tap_pairs"};
-Options g_defaults = {{4096, 256, 0, 1, 1, 1, 1, 1, 1, 2, 0, 1, 1, 1, 1, 1, 33, 1, 0}};
+                                          "mrf_fused", "decoder_streams", "respair_grid_div", "fused_respair", "umma_timing_buffer", "split16", "resblock_fused", "pair_conv", "pair_fused", "coupling_fused", "pdl", "coupling_min_rows", "tap_pairs", "conv_spread", "attention_small"};
+Options g_defaults = {{4096, 256, 0, 1, 1, 1, 1, 0, 1, 2, 0, 1, 1, 1, 1, 1, 33, 1, 0, 1, 1}};
 thread_local Options tl_opts;
 thread_local int tl_scope_depth = 0;
 }  // namespace
@@ -68,13 +68,14 @@ int option_set(Options* o, const char* name, int64_t value) {
   VS_REQUIRE(idx >= 0, "unknown option '%s'", name);
   switch (idx) {
     case OPT_TF32_MIN_ROWS: case OPT_X3_MIN_ROWS: case OPT_COUPLING_MIN_ROWS: VS_REQUIRE(value >= 1, "option %s must be >= 1", name); break;
-    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: value = value != 0; break;
+    case OPT_TF32_PRIOR: case OPT_WN_FUSED: case OPT_MRF_FUSED: case OPT_SPLIT16: case OPT_RESBLOCK_FUSED: case OPT_COUPLING_FUSED: case OPT_CONV_SPREAD: case OPT_ATTENTION_SMALL: value = value != 0; break;
     case OPT_TAP_PAIRS: VS_REQUIRE(value >= 0 && value <= 2, "option tap_pairs must be 0, 1 (k = 11 only) or 2 (every k)"); break;
     case OPT_PDL: VS_REQUIRE(value >= 0 && value <= 255, "option pdl is a bit mask 0..255"); break;
     case OPT_PAIR_FUSED: VS_REQUIRE(value >= 0 && value <= 2, "option pair_fused must be 0, 1 (C = 128) or 2 (also C = 64)"); break;
     case OPT_PAIR_CONV: VS_REQUIRE(value >= 0 && value <= 2, "option pair_conv must be 0 (off), 1 (C = 128) or 2 (also C = 256, k = 3)"); break;
     case OPT_ATTENTION_MMA: VS_REQUIRE(value >= 0 && value <= 4, "option attention_mma must be 0..4"); break;
-    case OPT_TF32_CLUSTER: case OPT_DECODER_STREAMS: value = value == 2 ? 2 : 1; break;
+    case OPT_TF32_CLUSTER: value = value == 2 ? 2 : 1; break;
+    case OPT_DECODER_STREAMS: VS_REQUIRE(value >= 0 && value <= 2, "option decoder_streams must be 0 (auto), 1 or 2"); break;
     case OPT_RESPAIR_GRID_DIV: value = value < 1 ? 1 : value; break;
     case OPT_FUSED_RESPAIR: VS_REQUIRE(value >= 0 && value <= 2, "option fused_respair must be 0..2"); break;
     default: break;
@@ -409,26 +410,30 @@ int layernorm_rows(const float* a, const float* b, const float* gamma, const flo
 // out = softmax(scores).(v) + sum_d p[i,i+d] Ev[d+4].  Keys are the utterance's own rows only, so the
 // reference's -1e4 pad fill (attentions.py:166) never triggers (batch-1 semantics).
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_BQ = 64, AT_BK = 64, AT_D = kHeadDim;
+constexpr int AT_BK = 64, AT_D = kHeadDim;
 constexpr int AT_LD = 100;   // row pitch of Q/K/V tiles: 16 B aligned, 400 B = 4 banks apart -> LDS.128 conflict-free
 constexpr int AT_SLD = 68;   // row pitch of the score tile (16 B aligned)
 
+// RI = query rows per thread: 4 (64 queries per CTA) or 1 (16 per CTA: the batch-1 path, where 64-query CTAs leave a 70-phoneme call on
+// 4 CTAs of serial work)
+template <int RI>
 __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const float* __restrict__ qkv,
                                                             const float* __restrict__ ek,
                                                             const float* __restrict__ ev, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
+  constexpr int AT_BQ = 16 * RI;     // queries per CTA
   extern __shared__ __align__(16) float sm[];
-  float* Qs = sm;                          // [64][100]
+  float* Qs = sm;                          // [BQ][100]
   float* Ks = Qs + AT_BQ * AT_LD;          // [64][100]
   float* Vs = Ks + AT_BK * AT_LD;          // [64][100]
-  float* Ss = Vs + AT_BK * AT_LD;          // [64][68]
+  float* Ss = Vs + AT_BK * AT_LD;          // [BQ][68]
   float* Ev = Ss + AT_BQ * AT_SLD;         // [9][96]
   float* Ek = Ev + kRel * AT_D;            // [9][96]
-  float* relq = Ek + kRel * AT_D;          // [64][9]
-  float* row_m = relq + AT_BQ * kRel;      // [64]
-  float* row_l = row_m + AT_BQ;            // [64]
-  float* row_alpha = row_l + AT_BQ;        // [64]
+  float* relq = Ek + kRel * AT_D;          // [BQ][9]
+  float* row_m = relq + AT_BQ * kRel;      // [BQ]
+  float* row_l = row_m + AT_BQ;            // [BQ]
+  float* row_alpha = row_l + AT_BQ;        // [BQ]
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int T = rows.utt_len[b], start = rows.utt_start[b];
@@ -459,11 +464,11 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     relq[i] = s0 + s1;
   }
 
-  // S tile: rows 4ty..+3, key columns tx+16c (c<4).  O tile: rows 4ty..+3, head dims 6tx..6tx+5.
+  // S tile: rows RI*ty..+RI-1, key columns tx+16c (c<4).  O tile: the same rows, head dims 6tx..6tx+5.
   const int ty = tid / 16, tx = tid % 16;
-  float o_acc[4][6];
+  float o_acc[RI][6];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int c = 0; c < 6; ++c) o_acc[i][c] = 0.f;
 
@@ -481,20 +486,20 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
       *reinterpret_cast<float4*>(Vs + r * AT_LD + 4 * d4) = vv;
     }
     __syncthreads();
-    float s[4][4];
+    float s[RI][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) s[i][c] = 0.f;
 #pragma unroll 2
     for (int d = 0; d < AT_D; d += 4) {            // 8 LDS.128 per 64 FMA
-      float4 qa[4], kb[4];
+      float4 qa[RI], kb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(Qs + (4 * ty + i) * AT_LD + d);
+      for (int i = 0; i < RI; ++i) qa[i] = *reinterpret_cast<const float4*>(Qs + (RI * ty + i) * AT_LD + d);
 #pragma unroll
       for (int c = 0; c < 4; ++c) kb[c] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * c) * AT_LD + d);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           s[i][c] = fmaf(qa[i].x, kb[c].x, s[i][c]);
@@ -504,19 +509,20 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int qi = q0 + 4 * ty + i, kj = k0 + tx + 16 * c;
+        const int qi = q0 + RI * ty + i, kj = k0 + tx + 16 * c;
         float v = s[i][c];
         const int dd = kj - qi;
-        if (dd >= -kWindow && dd <= kWindow) v += relq[(4 * ty + i) * kRel + dd + kWindow];
+        if (dd >= -kWindow && dd <= kWindow) v += relq[(RI * ty + i) * kRel + dd + kWindow];
         if (kj >= T) v = -INFINITY;
-        Ss[(4 * ty + i) * AT_SLD + tx + 16 * c] = v;
+        Ss[(RI * ty + i) * AT_SLD + tx + 16 * c] = v;
       }
     __syncthreads();
-    // row-wise streaming softmax: 4 threads per row
-    {
+    // row-wise streaming softmax: 4 threads per row in BOTH variants (with 16 queries per CTA only two warps work here), so the row
+    // sums associate the same way and an utterance's bits do not depend on which variant its batch selects
+    if (tid < AT_BQ * 4) {
       const int r = tid / 4, part = tid % 4;
       float mx = -INFINITY;
       for (int c = part; c < AT_BK; c += 4) mx = fmaxf(mx, Ss[r * AT_SLD + c]);
@@ -542,23 +548,23 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float al = row_alpha[4 * ty + i];
+    for (int i = 0; i < RI; ++i) {
+      const float al = row_alpha[RI * ty + i];
 #pragma unroll
       for (int c = 0; c < 6; ++c) o_acc[i][c] *= al;
     }
 #pragma unroll 2
     for (int j = 0; j < AT_BK; j += 4) {            // 4 LDS.128 (P) + 12 LDS.64 (V) per 96 FMA
-      float4 p4[4];
+      float4 p4[RI];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p4[i] = *reinterpret_cast<const float4*>(Ss + (4 * ty + i) * AT_SLD + j);
+      for (int i = 0; i < RI; ++i) p4[i] = *reinterpret_cast<const float4*>(Ss + (RI * ty + i) * AT_SLD + j);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const float* vr = Vs + (j + jj) * AT_LD + 6 * tx;
         const float2 v0 = *reinterpret_cast<const float2*>(vr), v1 = *reinterpret_cast<const float2*>(vr + 2),
                      v2 = *reinterpret_cast<const float2*>(vr + 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RI; ++i) {
           const float p = jj == 0 ? p4[i].x : jj == 1 ? p4[i].y : jj == 2 ? p4[i].z : p4[i].w;
           o_acc[i][0] = fmaf(p, v0.x, o_acc[i][0]); o_acc[i][1] = fmaf(p, v0.y, o_acc[i][1]);
           o_acc[i][2] = fmaf(p, v1.x, o_acc[i][2]); o_acc[i][3] = fmaf(p, v1.y, o_acc[i][3]);
@@ -568,30 +574,30 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(VsRows rows, const f
     }
     // relative values on the band (attentions.py:174-177)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qi = q0 + 4 * ty + i;
+    for (int i = 0; i < RI; ++i) {
+      const int qi = q0 + RI * ty + i;
       for (int dd = -kWindow; dd <= kWindow; ++dd) {
         const int j = qi + dd - k0;
         if (j < 0 || j >= AT_BK || qi + dd >= T) continue;
-        const float p = Ss[(4 * ty + i) * AT_SLD + j];
+        const float p = Ss[(RI * ty + i) * AT_SLD + j];
 #pragma unroll
         for (int c = 0; c < 6; ++c) o_acc[i][c] = fmaf(p, Ev[(dd + kWindow) * AT_D + 6 * tx + c], o_acc[i][c]);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int qi = q0 + 4 * ty + i;
+  for (int i = 0; i < RI; ++i) {
+    const int qi = q0 + RI * ty + i;
     if (qi >= T) continue;
-    const float inv = 1.f / row_l[4 * ty + i];
+    const float inv = 1.f / row_l[RI * ty + i];
     float* o = out + (size_t)(start + qi) * kHidden + h * AT_D + 6 * tx;
 #pragma unroll
     for (int c = 0; c < 6; c += 2) *reinterpret_cast<float2*>(o + c) = make_float2(o_acc[i][c] * inv, o_acc[i][c + 1] * inv);
   }
 }
 
-static size_t attention_smem_bytes() {
-  return sizeof(float) * (3 * AT_BQ * AT_LD + AT_BQ * AT_SLD + 2 * kRel * AT_D + AT_BQ * kRel + 3 * AT_BQ);
+static size_t attention_smem_bytes(int bq) {
+  return sizeof(float) * ((bq + 2 * AT_BK) * AT_LD + bq * AT_SLD + 2 * kRel * AT_D + bq * kRel + 3 * bq);
 }
 
 int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const float* ev, float* out, cudaStream_t st,
@@ -607,14 +613,20 @@ int rel_attention(const VsRows& rows, const float* qkv, const float* ek, const f
     return rel_attention_umma(rows, qkv, ek, ev, out, scratch, st, planar ? out_hi : nullptr, planar ? out_lo : nullptr);
   }
   if (mode >= 2 || (mode == 1 && rows.max_len >= 128)) return rel_attention_mma(rows, qkv, ek, ev, out, st);
-  const size_t smem = attention_smem_bytes();
-  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(rel_attention_kernel), (int)smem));
+  int n_sm = 0;
+  VS_TRY(device_sm_count(&n_sm));
+  // too few 64-query CTAs for half the SMs (the batch-1 latency path): 16 queries per CTA
+  const bool small = opts().v[OPT_ATTENTION_SMALL] && ((rows.max_len + 63) / 64) * kHeads * rows.n_utt * 2 <= n_sm;
+  const int bq = small ? 16 : 64;
+  const size_t smem = attention_smem_bytes(bq);
+  VS_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(small ? rel_attention_kernel<1> : rel_attention_kernel<4>), (int)smem));
   // gap rows of `out` must be zero: the caller feeds out into a k=1 conv whose epilogue masks, but keep it clean
   if (!gaps_dont_care) VS_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows.n_rows * kHidden, st));
   // grid.x covers the longest utterance; CTAs beyond an utterance's length exit immediately
   VS_REQUIRE(rows.max_len > 0 && rows.max_len <= rows.n_rows, "rel_attention: bad max_len %d", rows.max_len);
-  dim3 grid((rows.max_len + AT_BQ - 1) / AT_BQ, kHeads, rows.n_utt);
-  VS_CUDA_CHECK(launch_pdl<16>(rel_attention_kernel, dim3(grid), dim3(256), smem, st, rows, qkv, ek, ev, out));
+  dim3 grid((rows.max_len + bq - 1) / bq, kHeads, rows.n_utt);
+  if (small) VS_CUDA_CHECK(launch_pdl<16>(rel_attention_kernel<1>, dim3(grid), dim3(256), smem, st, rows, qkv, ek, ev, out));
+  else VS_CUDA_CHECK(launch_pdl<16>(rel_attention_kernel<4>, dim3(grid), dim3(256), smem, st, rows, qkv, ek, ev, out));
   VS_LAUNCH_CHECK();
   return VS_OK;
 }

@@ -37,6 +37,11 @@ struct Plan {
   int MT;                 // row tiles (128 rows each) per A stage
   int resident_b;         // 1: every weight slab stays in smem for the whole kernel; 0: slabs stream through a ring
   int n_super;            // number of A stages' worth of work = ceil(n_tiles / MT)
+  // Small calls (option "conv_spread"): a streamed-weight conv with fewer row tiles than SMs is cut along N as well - the n-block
+  // shrinks from the packed width Nw to Nblk (a column range of each packed slab, fetched plane by plane) and one work item is
+  // (A stage, NB / NS consecutive n-blocks), so a 3-tile ConvTranspose with N = 2048 runs on 96 CTAs instead of 3.
+  int Nw, n_sub;          // packed n-block width (packing.py: min(N, 256)) and Nw / Nblk
+  int NS, nb_per, n_items;   // n-block groups per A stage, n-blocks per group, work items = n_super * NS
   uint32_t w_bytes;       // all weight slabs
   uint32_t a_bytes, b_bytes, smem_bytes;
   uint32_t off_b, off_bar, off_bias;
@@ -109,7 +114,6 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                              // the prologue above overlapped the previous kernel's tail
 
-  const int n_units_per_tile = p.NB;
   const int stages_per_unit = c.taps * p.n_kc;
 
   if (warp == 0) {
@@ -123,7 +127,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
         bulk_g2s(b_base + sl * p.b_bytes, reinterpret_cast<const uint8_t*>(c.w) + (size_t)sl * p.b_bytes, p.b_bytes,
                  b_full(0));
     }
-    auto issue_a = [&](int super) {
+    auto issue_a = [&](int item) {
+      const int super = item / p.NS;
       const int sa = a_it % p.SA;
       const uint32_t ph = (a_it / p.SA) & 1;
       VS_TIMED(tw0, mbar_wait(a_empty(sa), ph ^ 1, 1));
@@ -151,13 +156,42 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     };
     const int look = p.SA - 1;
     int next_a = blockIdx.x;
-    for (int i = 0; i < look && next_a < p.n_super; ++i, next_a += gridDim.x) issue_a(next_a);
-    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x) {
-      if (next_a < p.n_super) { issue_a(next_a); next_a += gridDim.x; }
-      if (!p.resident_b && lane == 0) {
+    for (int i = 0; i < look && next_a < p.n_items; ++i, next_a += gridDim.x) issue_a(next_a);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      if (next_a < p.n_items) { issue_a(next_a); next_a += gridDim.x; }
+      if (!p.resident_b && p.n_sub > 1) {
+        // narrowed n-blocks: columns [sub * Nblk, +Nblk) of packed slab (nb / n_sub, stage), one copy per 8-channel plane; the planes go
+        // out from different lanes (one thread issuing 8 small copies per slab was the whole kernel's pace at k = 11)
+        const int super = item / p.NS, grp = item - super * p.NS;
         const int tiles_here = min(p.MT, p.n_tiles - super * p.MT);
+        const int sl_lo = grp * p.nb_per * stages_per_unit, sl_hi = sl_lo + p.nb_per * stages_per_unit;
+        const uint32_t plane_bytes = (uint32_t)p.Nblk * 16u;
         for (int m = 0; m < tiles_here; ++m)
-          for (int sl = 0; sl < n_slabs; ++sl) {
+          for (int sl = sl_lo; sl < sl_hi; ++sl) {
+            const int sb = b_it % p.SB;
+            const uint32_t ph = (b_it / p.SB) & 1;
+            if (lane == 0) {
+              VS_TIMED(tw1, mbar_wait(b_empty(sb), ph ^ 1, 2));
+              mbar_arrive_expect_tx(b_full(sb), p.b_bytes);
+            }
+            __syncwarp();
+            // packed [NB][taps][Cin / 8 planes][Nw][8]: the plane pitch is Nw * 16 bytes across the whole of Cin, so a stage may be
+            // any run of planes (KC here is not packing.py's 64)
+            const int nb = sl / stages_per_unit, stg = sl - nb * stages_per_unit;
+            const int nb_w = nb / p.n_sub, sub = nb - nb_w * p.n_sub;
+            const int t = stg / p.n_kc, kc = stg - t * p.n_kc;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(c.w) +
+                                 ((size_t)(nb_w * c.taps + t) * p.planes + (size_t)kc * (p.KC / 8) + lane) * ((size_t)p.Nw * 16u) +
+                                 (size_t)sub * plane_bytes;
+            if (lane < p.KC / 8) bulk_g2s(b_base + sb * p.b_bytes + lane * plane_bytes, src, plane_bytes, b_full(sb));
+            ++b_it;
+          }
+      } else if (!p.resident_b && lane == 0) {
+        const int super = item / p.NS, grp = item - super * p.NS;
+        const int tiles_here = min(p.MT, p.n_tiles - super * p.MT);
+        const int sl_lo = grp * p.nb_per * stages_per_unit, sl_hi = sl_lo + p.nb_per * stages_per_unit;
+        for (int m = 0; m < tiles_here; ++m)
+          for (int sl = sl_lo; sl < sl_hi; ++sl) {
             const int sb = b_it % p.SB;
             const uint32_t ph = (b_it / p.SB) & 1;
             VS_TIMED(tw1, mbar_wait(b_empty(sb), ph ^ 1, 2));
@@ -180,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       const uint32_t a_kstep = 2u * (uint32_t)p.rows_a;          // two planes per K=16 step
       const uint32_t b_kstep = 2u * (uint32_t)p.Nblk;
       const int taps = c.taps, dil = c.dil, n_kc = p.n_kc, k16s = p.KC / 16, MT = p.MT, NACC = p.NACC, SB = p.SB, SA = p.SA;
-      const int n_tiles = p.n_tiles, n_super = p.n_super;
+      const int n_tiles = p.n_tiles, n_items = p.n_items, NS = p.NS, nb_per = p.nb_per;
       const bool resident = p.resident_b != 0;
       const int nks = n_kc * k16s;
       const bool lean = resident && p.NB == 1 && (nks == 2 || nks == 4 || nks == 8);
@@ -188,7 +222,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       const uint32_t b_base16 = b_base >> 4;
       uint32_t acc_slot = 0, acc_phase = 0, b_slot = 0, b_phase = 0, a_slot = 0, a_phase = 0;
       if (resident) { mbar_wait(b_full(0), 0, 7); tc_fence_after(); }
-      for (int super = blockIdx.x; super < n_super; super += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int super = item / NS, nb_lo = (item - super * NS) * nb_per, nb_hi = nb_lo + nb_per;
         VS_TIMED(tw0, mbar_wait(a_full(a_slot), a_phase, 3));
         tc_fence_after();
         const uint32_t a_stage16 = (a_base + a_slot * a_bytes) >> 4;
@@ -211,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
           }
         } else {
           for (int m = 0; m < tiles_here; ++m)
-            for (int nb = 0; nb < n_units_per_tile; ++nb) {
+            for (int nb = nb_lo; nb < nb_hi; ++nb) {
               VS_TIMED(tw1, mbar_wait(acc_empty(acc_slot), acc_phase ^ 1, 4));
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + acc_slot * nblk;
@@ -275,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
     const uint32_t up_mask = (uint32_t)c.up - 1u;
     const size_t plane_stride = (size_t)R_out * 8;          // elements between consecutive 8-channel planes
     const float slope = c.act_slope, scale = c.act_scale;
-    for (int super = blockIdx.x; super < p.n_super; super += gridDim.x)
-    for (int tile = super * p.MT; tile < min(p.n_tiles, (super + 1) * p.MT); ++tile) {
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x)
+    for (int super = item / p.NS, nb_lo = (item - super * p.NS) * p.nb_per, tile = super * p.MT; tile < min(p.n_tiles, (super + 1) * p.MT); ++tile) {
       const int r = tile * kTileM + q * 32 + lane;
       const bool in_range = r < c.R;
       int utt = -1;
@@ -285,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
       const float* ub = nullptr;
       if (has_ub && valid) ub = c.ubias + (size_t)(c.ubias_idx ? c.ubias_idx[utt] : utt) * c.N;
       const size_t row_elem = (size_t)c.up * r * 8;         // element offset of this thread's (first) output row in a plane
-      for (int nb = 0; nb < n_units_per_tile; ++nb) {
+      for (int nb = nb_lo; nb < nb_lo + p.nb_per; ++nb) {
         const int ab = (int)acc_slot;
         VS_TIMED(tw0, mbar_wait(acc_full(ab), acc_phase, 6));
         tc_fence_after();
@@ -392,17 +427,34 @@ __global__ void __launch_bounds__(kThreads, 2) umma_conv1d_kernel(const __grid_c
   }
 }
 
-int make_plan(const UmmaConv& c, Plan* out) {
+int make_plan(const UmmaConv& c, int n_sm, Plan* out) {
   Plan p{};
   VS_REQUIRE(c.Cin % 16 == 0 && c.Cin >= 16, "umma_conv1d: Cin=%d must be a multiple of 16", c.Cin);
   VS_REQUIRE(c.N % 32 == 0, "umma_conv1d: N=%d must be a multiple of 32", c.N);
   VS_REQUIRE(c.up >= 1 && c.N % c.up == 0 && (c.N / c.up) % 8 == 0, "umma_conv1d: bad upsample factor");
   VS_REQUIRE(c.R > 0 && c.taps >= 1 && c.dil >= 1 && c.pad_l >= 0, "umma_conv1d: bad shape");
   p.Cout = c.N / c.up;
-  p.Nblk = c.N < 256 ? c.N : 256;
-  VS_REQUIRE(c.N % p.Nblk == 0, "umma_conv1d: N=%d not a multiple of the 256-column block", c.N);
+  p.Nw = c.N < 256 ? c.N : 256;
+  VS_REQUIRE(c.N % p.Nw == 0, "umma_conv1d: N=%d not a multiple of the 256-column block", c.N);
+  p.Nblk = p.Nw;
+  p.n_tiles = (c.R + kTileM - 1) / kTileM;
+  // small call with streamed weights: narrow the n-block until the (row tile, n-block) units fill the SMs (never below 64 columns:
+  // an N = 32 MMA costs what an N = 64 one does)
+  const bool streamed = (uint64_t)c.Cin * c.N * c.taps * 2u > 96u * 1024;
+  const bool spread = streamed && opts().v[OPT_CONV_SPREAD] && p.n_tiles * (c.N / p.Nw) * 2 <= n_sm;
+  if (spread)
+    for (int cand = 64; cand < p.Nw; cand *= 2)
+      if (p.Nw % cand == 0 && p.n_tiles * (c.N / cand) <= n_sm) { p.Nblk = cand; break; }
+  p.n_sub = p.Nw / p.Nblk;
   p.NB = c.N / p.Nblk;
   p.KC = c.Cin < 64 ? c.Cin : 64;
+  if (p.n_sub > 1) {        // narrowed slabs are fetched plane by plane anyway: make them deep instead (<= 32 planes = one per lane, <= 32 KB),
+    int kc = 32768 / (p.Nblk * 2);   // so that a k = 11 item is 11 fetches in flight at once and not 44 small ones behind a 4-slot ring
+    if (kc > c.Cin) kc = c.Cin;
+    if (kc > 256) kc = 256;
+    while (c.Cin % kc) kc -= 16;
+    p.KC = kc;
+  }
   VS_REQUIRE(c.Cin % p.KC == 0, "umma_conv1d: Cin=%d not a multiple of the %d-channel chunk", c.Cin, p.KC);
   p.n_kc = c.Cin / p.KC;
   p.planes = c.Cin / 8;
@@ -439,7 +491,8 @@ int make_plan(const UmmaConv& c, Plan* out) {
     p.MT = 1;
     const uint32_t a1 = a_bytes_for(1);
     auto fits = [&](int sa, int sb, uint32_t lim) { return sa * a1 + sb * p.b_bytes + fixed <= lim; };
-    if (fits(2, 4, half_sm)) { p.SA = 2; cap = half_sm; }
+    if (p.n_sub > 1) { p.SA = 1; cap = full_sm; }          // one item per CTA: the whole SM for the weight ring
+    else if (fits(2, 4, half_sm)) { p.SA = 2; cap = half_sm; }
     else if (fits(1, 4, half_sm)) { p.SA = 1; cap = half_sm; }
     else if (fits(2, 3, full_sm)) { p.SA = 2; cap = full_sm; }
     else { p.SA = 1; cap = full_sm; }
@@ -469,8 +522,14 @@ int make_plan(const UmmaConv& c, Plan* out) {
   const uint32_t min_smem = (227u * 1024) / (uint32_t)(per_sm + 1) + 1024u;
   if (p.smem_bytes < min_smem) p.smem_bytes = min_smem;
   p.ctas_per_sm = per_sm;
-  p.n_tiles = (c.R + kTileM - 1) / kTileM;
   p.n_super = (p.n_tiles + p.MT - 1) / p.MT;
+  p.NS = 1;
+  if (spread)                                   // as many n-block groups per A stage as keep the items within one wave
+    for (int ns = p.NB; ns >= 1; --ns)
+      if (p.NB % ns == 0 && p.n_super * ns <= n_sm) { p.NS = ns; break; }
+  p.nb_per = p.NB / p.NS;
+  p.n_items = p.n_super * p.NS;
+  VS_REQUIRE(p.n_sub == 1 || !p.resident_b, "umma_conv1d: internal: narrowed n-block with resident weights");
   *out = p;
   return VS_OK;
 }
@@ -484,14 +543,14 @@ int umma_conv1d(const UmmaConv& c, cudaStream_t st) {
   Params prm;
   prm.c = c;
   prm.dbg = static_cast<long long*>(umma_conv_timing_buffer());
-  VS_TRY(make_plan(c, &prm.p));
-  VS_REQUIRE(c.in && c.w && (c.out_raw || c.out_act), "umma_conv1d: null pointer");
   int n_sm = 0;
   VS_TRY(device_sm_count(&n_sm));
+  VS_TRY(make_plan(c, n_sm, &prm.p));
+  VS_REQUIRE(c.in && c.w && (c.out_raw || c.out_act), "umma_conv1d: null pointer");
   VS_REQUIRE(c.act_slope > 0.f && c.act_slope <= 1.f, "umma_conv1d: act_slope must be in (0, 1]");
   const int per_sm = prm.p.ctas_per_sm;
   int grid = n_sm * per_sm;
-  if (grid > prm.p.n_super) grid = prm.p.n_super;
+  if (grid > prm.p.n_items) grid = prm.p.n_items;
   int flags = (c.res ? F_RES : 0) | (c.res2 ? F_RES2 : 0) | (c.ubias ? F_UBIAS : 0) | (c.out_raw ? F_RAW : 0) |
               (c.out_act ? F_ACT : 0) | (c.act_scale != 1.f ? F_SCALE : 0) | (c.up != 1 ? F_UP : 0) |
               (prm.p.Nblk < 64 ? F_CW16 : 0) | ((c.res && c.res_inv_slope != 0.f) ? F_RESINV : 0) | (c.out_lo ? F_LO : 0);
