@@ -31,7 +31,7 @@ def main():
 
     net = build_from_hparams(get_hparams_from_file(), device="cuda:0")
     net.load_state_dict(make_state_dict(1234))
-    for opt in ("pdl", "pair_conv", "pair_fused", "resblock_fused", "coupling_fused", "coupling_min_rows", "x3_min_rows", "tf32_min_rows", "conv_spread", "attention_small", "decoder_streams"):       # A/B knobs: VS_PDL=37 python tools/latency.py
+    for opt in ("pdl", "pair_conv", "pair_fused", "resblock_fused", "coupling_fused", "coupling_min_rows", "x3_min_rows", "tf32_min_rows", "conv_spread", "attention_small", "decoder_streams", "attention_mma"):       # A/B knobs: VS_PDL=37 python tools/latency.py
         if os.environ.get("VS_" + opt.upper()):
             net.set_option(opt, int(os.environ["VS_" + opt.upper()]))
 
